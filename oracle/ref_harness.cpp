@@ -1,0 +1,282 @@
+// TEST INFRASTRUCTURE ONLY -- part of the CPU oracle, never of the product.
+//
+// C-ABI around the reference's OWN layer code (compiled in place from
+// /root/reference by oracle/Makefile, CPU_ONLY).  Layers are created through the
+// reference's LayerRegistry::CreateLayer (include/caffe/layer_factory.hpp:73-81)
+// and driven through Layer::SetUp / Forward / Backward (include/caffe/layer.hpp:
+// 67-77, 451-500) -- the same entry points caffe::Net uses (src/caffe/net.cpp:
+// 139, 541, 586).  Loaded from Python with ctypes (oracle/refbind.py) by tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "caffe/blob.hpp"
+#include "caffe/layer.hpp"
+#include "caffe/layer_factory.hpp"
+#include "caffe/layers/pair_rank_loss_layer.hpp"
+
+namespace caffe {
+// pair_rank_loss_layer.cpp:86-87 has no STUB_GPU, so a CPU_ONLY link lacks the
+// Forward_gpu/Backward_gpu bodies its header declares; supply the stubs here.
+STUB_GPU(PairRankLossLayer);
+template class PairRankLossLayer<float>;
+template class PairRankLossLayer<double>;
+}  // namespace caffe
+
+namespace {
+
+using caffe::Blob;
+using caffe::Layer;
+using caffe::LayerParameter;
+using caffe::shared_ptr;
+using std::vector;
+
+struct SessionBase {
+  virtual ~SessionBase() {}
+  LayerParameter param;
+  int dtype = 0;
+  std::string error;
+};
+
+template <typename Dtype>
+struct Session : public SessionBase {
+  vector<shared_ptr<Blob<Dtype> > > bottom_own, top_own;
+  vector<Blob<Dtype>*> bottom, top;
+  shared_ptr<Layer<Dtype> > layer;
+};
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(SessionBase* s, F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    if (s) s->error = e.what();
+    return 1;
+  }
+}
+
+caffe::FillerParameter* filler_of(LayerParameter* p, const std::string& which) {
+  const std::string& t = p->type();
+  if (t == "SimCross") {
+    return which == "weight_filler" ? p->mutable_sim_cross_param()->mutable_weight_filler()
+                                    : p->mutable_sim_cross_param()->mutable_bias_filler();
+  } else if (t == "SimMatrix") {
+    return p->mutable_sim_matrix_param()->mutable_weight_filler();
+  } else if (t == "Embed") {
+    return which == "weight_filler" ? p->mutable_embed_param()->mutable_weight_filler()
+                                    : p->mutable_embed_param()->mutable_bias_filler();
+  }
+  return nullptr;
+}
+
+#define DISPATCH(s, ...)                                         \
+  do {                                                           \
+    if ((s)->dtype == 0) {                                       \
+      auto* S = static_cast<Session<float>*>(s);                 \
+      typedef float Dtype;                                       \
+      (void)sizeof(Dtype);                                       \
+      __VA_ARGS__;                                                   \
+    } else {                                                     \
+      auto* S = static_cast<Session<double>*>(s);                \
+      typedef double Dtype;                                      \
+      (void)sizeof(Dtype);                                       \
+      __VA_ARGS__;                                                   \
+    }                                                            \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char* mmsref_last_error() { return g_last_error.c_str(); }
+
+void mmsref_set_blas_threads(int n) { openblas_set_num_threads(n); }
+int mmsref_get_blas_threads() { return openblas_get_num_threads(); }
+
+void* mmsref_create(const char* type, int dtype) {
+  SessionBase* s = dtype == 0 ? static_cast<SessionBase*>(new Session<float>())
+                              : static_cast<SessionBase*>(new Session<double>());
+  s->dtype = dtype;
+  s->param.set_type(type);
+  s->param.set_name(std::string("ref_") + type);
+  return s;
+}
+
+void mmsref_destroy(void* h) { delete static_cast<SessionBase*>(h); }
+
+// Integer/boolean prototxt fields.  Returns 0 on success, 2 for an unknown key.
+int mmsref_set_i(void* h, const char* key, long long v) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  const std::string k(key);
+  if (k == "dist_mode") s->param.mutable_sim_cross_param()->set_dist_mode(static_cast<int>(v));
+  else if (k == "mesure_count") s->param.mutable_sim_cross_param()->set_mesure_count(static_cast<int>(v));
+  else if (k == "sim_cross.bias_term") s->param.mutable_sim_cross_param()->set_bias_term(v != 0);
+  else if (k == "num_output") s->param.mutable_embed_param()->set_num_output(static_cast<unsigned>(v));
+  else if (k == "input_dim") s->param.mutable_embed_param()->set_input_dim(static_cast<unsigned>(v));
+  else if (k == "embed.bias_term") s->param.mutable_embed_param()->set_bias_term(v != 0);
+  else if (k == "fm.bias_term") s->param.mutable_fm_param()->set_bias_term(v != 0);
+  else if (k == "phase") s->param.set_phase(v ? caffe::TEST : caffe::TRAIN);
+  else return 2;
+  return 0;
+}
+
+// Float prototxt fields, incl. "<weight_filler|bias_filler>.<value|min|max|mean|std>".
+int mmsref_set_f(void* h, const char* key, double v) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  const std::string k(key);
+  if (k == "margin") { s->param.mutable_pair_rank_loss_param()->set_margin(static_cast<float>(v)); return 0; }
+  if (k == "loss_weight") { s->param.add_loss_weight(static_cast<float>(v)); return 0; }
+  const size_t dot = k.find('.');
+  if (dot == std::string::npos) return 2;
+  caffe::FillerParameter* f = filler_of(&s->param, k.substr(0, dot));
+  if (!f) return 2;
+  const std::string field = k.substr(dot + 1);
+  if (field == "value") f->set_value(static_cast<float>(v));
+  else if (field == "min") f->set_min(static_cast<float>(v));
+  else if (field == "max") f->set_max(static_cast<float>(v));
+  else if (field == "mean") f->set_mean(static_cast<float>(v));
+  else if (field == "std") f->set_std(static_cast<float>(v));
+  else return 2;
+  return 0;
+}
+
+// String prototxt fields: "<weight_filler|bias_filler>.type", "weight_source".
+int mmsref_set_s(void* h, const char* key, const char* v) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  const std::string k(key);
+  if (k == "weight_source") { s->param.mutable_embed_param()->set_weight_source(v); return 0; }
+  const size_t dot = k.find('.');
+  if (dot == std::string::npos) return 2;
+  caffe::FillerParameter* f = filler_of(&s->param, k.substr(0, dot));
+  if (!f || k.substr(dot + 1) != "type") return 2;
+  f->set_type(v);
+  return 0;
+}
+
+void mmsref_seed(unsigned int seed) { caffe::Caffe::set_random_seed(seed); }
+
+int mmsref_add_bottom(void* h, int ndim, const int* shape) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  int idx = -1;
+  int rc = guarded(s, [&] {
+    vector<int> sh(shape, shape + ndim);
+    DISPATCH(s, {
+      S->bottom_own.push_back(shared_ptr<Blob<Dtype> >(new Blob<Dtype>(sh)));
+      S->bottom.push_back(S->bottom_own.back().get());
+      idx = static_cast<int>(S->bottom.size()) - 1;
+    });
+  });
+  return rc ? -1 : idx;
+}
+
+int mmsref_reshape_bottom(void* h, int i, int ndim, const int* shape) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  return guarded(s, [&] {
+    vector<int> sh(shape, shape + ndim);
+    DISPATCH(s, S->bottom[i]->Reshape(sh));
+  });
+}
+
+int mmsref_setup(void* h, int num_top) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  return guarded(s, [&] {
+    DISPATCH(s, {
+      for (int t = 0; t < num_top; ++t) {
+        S->top_own.push_back(shared_ptr<Blob<Dtype> >(new Blob<Dtype>()));
+        S->top.push_back(S->top_own.back().get());
+      }
+      S->layer = caffe::LayerRegistry<Dtype>::CreateLayer(S->param);
+      S->layer->SetUp(S->bottom, S->top);
+    });
+  });
+}
+
+int mmsref_num_blobs(void* h) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  int n = 0;
+  DISPATCH(s, n = static_cast<int>(S->layer->blobs().size()));
+  return n;
+}
+
+// kind: 0 bottom, 1 top, 2 param blob.  Writes up to 8 dims; returns ndim.
+int mmsref_shape(void* h, int kind, int i, int* shape_out) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  int nd = 0;
+  DISPATCH(s, {
+    const Blob<Dtype>* b = kind == 0 ? S->bottom[i] : kind == 1 ? S->top[i] : S->layer->blobs()[i].get();
+    nd = b->num_axes();
+    for (int a = 0; a < nd && a < 8; ++a) shape_out[a] = b->shape(a);
+  });
+  return nd;
+}
+
+// what: 0 data, 1 diff.  Buffers hold count() elements of the session dtype.
+int mmsref_write(void* h, int kind, int i, int what, const void* src) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  return guarded(s, [&] {
+    DISPATCH(s, {
+      Blob<Dtype>* b = kind == 0 ? S->bottom[i] : kind == 1 ? S->top[i] : S->layer->blobs()[i].get();
+      Dtype* dst = what == 0 ? b->mutable_cpu_data() : b->mutable_cpu_diff();
+      std::memcpy(dst, src, sizeof(Dtype) * b->count());
+    });
+  });
+}
+
+int mmsref_read(void* h, int kind, int i, int what, void* dst) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  return guarded(s, [&] {
+    DISPATCH(s, {
+      const Blob<Dtype>* b = kind == 0 ? S->bottom[i] : kind == 1 ? S->top[i] : S->layer->blobs()[i].get();
+      const Dtype* src = what == 0 ? b->cpu_data() : b->cpu_diff();
+      std::memcpy(dst, src, sizeof(Dtype) * b->count());
+    });
+  });
+}
+
+int mmsref_forward(void* h, double* loss_out) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  return guarded(s, [&] {
+    DISPATCH(s, {
+      Dtype loss = S->layer->Forward(S->bottom, S->top);
+      if (loss_out) *loss_out = static_cast<double>(loss);
+    });
+  });
+}
+
+int mmsref_backward(void* h, const int* propagate_down) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  return guarded(s, [&] {
+    DISPATCH(s, {
+      vector<bool> pd(S->bottom.size());
+      for (size_t i = 0; i < pd.size(); ++i) pd[i] = propagate_down[i] != 0;
+      S->layer->Backward(S->top, pd, S->bottom);
+    });
+  });
+}
+
+// `caffe time` protocol (tools/caffe.cpp:345-365): the caller does the warm-up;
+// this runs `iters` forward(+backward) passes and returns mean wall ms per pass.
+int mmsref_time(void* h, int iters, int do_backward, const int* propagate_down, double* ms_out) {
+  SessionBase* s = static_cast<SessionBase*>(h);
+  return guarded(s, [&] {
+    DISPATCH(s, {
+      vector<bool> pd(S->bottom.size());
+      for (size_t i = 0; i < pd.size(); ++i) pd[i] = propagate_down ? propagate_down[i] != 0 : false;
+      auto t0 = std::chrono::steady_clock::now();
+      for (int it = 0; it < iters; ++it) {
+        S->layer->Forward(S->bottom, S->top);
+        if (do_backward) S->layer->Backward(S->top, pd, S->bottom);
+      }
+      auto t1 = std::chrono::steady_clock::now();
+      *ms_out = std::chrono::duration<double, std::milli>(t1 - t0).count() / iters;
+    });
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,265 @@
+"""CPU tests: pin the plain-C oracle (oracle/mms_oracle.c).
+
+Three anchors, per the parity contract:
+ 1. the reference's only known-answer tests for this path,
+    src/caffe/test/test_embed_layer.cpp:54-176, restated;
+ 2. the committed golden fixtures tests/golden/mms_golden.npz (outputs of the
+    reference's own layer code, see tests/golden/make_golden.py);
+ 3. the reference itself (oracle/_ref) on fresh random inputs, when it is present.
+plus GradientChecker-style finite differences (test_gradient_check_util.hpp:148-175).
+"""
+import numpy as np
+import pytest
+
+from conftest import scaled_err
+from oracle import cport, refbind
+
+DTYPES = [np.float32, np.float64]
+TAG = {np.float32: "f32", np.float64: "f64"}
+# contractions go through BLAS in the reference: summation order unspecified
+TOL = {np.float32: 2e-5, np.float64: 1e-12}
+
+
+def g(golden, dtype, key):
+    return golden["%s/%s" % (TAG[dtype], key)]
+
+
+# ---------------------------------------------------------------- 1. reference KATs
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_embed_forward_kat(dtype, bias):
+    # test_embed_layer.cpp:54-135: bottom (4,1,1,1) random ids in [0,5), W 5x10 ~ U(-10,10)
+    rng = np.random.default_rng(1701)
+    W = rng.uniform(-10, 10, (5, 10)).astype(dtype)
+    b = rng.uniform(-10, 10, 10).astype(dtype) if bias else None
+    idx = rng.integers(0, 5, size=(4, 1, 1, 1)).astype(dtype)
+    top = cport.embed_forward(idx, W, b)
+    assert top.shape == (4, 1, 1, 1, 10)              # TestSetUp :38-52
+    for i in range(4):
+        want = W[int(idx.reshape(-1)[i])] + (b if bias else 0)
+        assert np.array_equal(top.reshape(4, 10)[i], want.astype(dtype))   # EXPECT_EQ :84,125
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_embed_gradient_kat(dtype, bias):
+    # test_embed_layer.cpp:137-176: ids {4,2,2,3}; duplicate id 2 exercises accumulation.
+    # Embed is linear in W and b, so central differences are exact up to rounding:
+    # objective = sum(top * R)  =>  dW[v] = sum_{n: idx[n]==v} R[n], db = sum_n R[n].
+    rng = np.random.default_rng(7)
+    idx = np.array([4, 2, 2, 3], dtype=dtype).reshape(4, 1, 1, 1)
+    R = rng.uniform(-1, 1, (4, 10)).astype(dtype)
+    dW = np.zeros((5, 10), dtype=dtype)
+    db = np.zeros(10, dtype=dtype) if bias else None
+    cport.embed_backward(idx, R, dW, db)
+    want = np.zeros((5, 10), dtype=np.float64)
+    for n, v in enumerate([4, 2, 2, 3]):
+        want[v] += R[n]
+    assert scaled_err(dW, want, 1.0) <= 1e-3           # GradientChecker(1e-2, 1e-3) :147
+    if bias:
+        assert scaled_err(db, R.astype(np.float64).sum(0), 1.0) <= 1e-3
+
+
+# ---------------------------------------------------------------- 2. golden fixtures
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_embed_golden(golden, dtype, bias):
+    k = "embed_b%d" % int(bias)
+    idx, W = g(golden, dtype, k + "/idx"), g(golden, dtype, k + "/W")
+    b = g(golden, dtype, k + "/b") if bias else None
+    assert np.array_equal(cport.embed_forward(idx, W, b), g(golden, dtype, k + "/top"))
+    dW = g(golden, dtype, k + "/dW0").copy()
+    db = g(golden, dtype, k + "/db0").copy() if bias else None
+    cport.embed_backward(idx, g(golden, dtype, k + "/dtop"), dW, db)
+    assert np.array_equal(dW, g(golden, dtype, k + "/dW"))       # same axpy order => bit-exact
+    if bias:
+        assert scaled_err(db, g(golden, dtype, k + "/db")) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_simcross_golden(golden, dtype, mode):
+    k = "simcross_m%d" % mode
+    q, a = g(golden, dtype, k + "/q"), g(golden, dtype, k + "/a")
+    Mw = g(golden, dtype, k + "/M") if mode == 2 else None
+    B = g(golden, dtype, k + "/B") if mode == 2 else None
+    S, n0, n1 = cport.simcross_forward(mode, q, a, Mw, B)
+    assert S.shape == g(golden, dtype, k + "/S").shape
+    assert scaled_err(S, g(golden, dtype, k + "/S")) <= TOL[dtype]
+    dB = g(golden, dtype, k + "/dB0").copy() if mode == 2 else None
+    dq, da, dM, dB = cport.simcross_backward(mode, q, a, Mw if mode == 2 else q, S,
+                                             g(golden, dtype, k + "/dS"), n0, n1, dB)
+    assert scaled_err(dq, g(golden, dtype, k + "/dq")) <= 10 * TOL[dtype]
+    assert scaled_err(da, g(golden, dtype, k + "/da")) <= 10 * TOL[dtype]
+    if mode == 2:
+        # dM is zeroed by the layer (dM0 discarded), dB accumulates on top of dB0
+        assert scaled_err(dM, g(golden, dtype, k + "/dM")) <= 10 * TOL[dtype]
+        assert scaled_err(dB, g(golden, dtype, k + "/dB")) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_simmatrix_golden(golden, dtype):
+    k = "simmatrix"
+    q, a, W = (g(golden, dtype, k + "/" + n) for n in ("q", "a", "W"))
+    s, T = cport.simmatrix_forward(q, a, W)
+    assert scaled_err(s, g(golden, dtype, k + "/s")) <= TOL[dtype]
+    assert scaled_err(T, g(golden, dtype, k + "/T")) <= TOL[dtype]     # bottom[1].diff scratch
+    dW = g(golden, dtype, k + "/dW0").copy()
+    dW, dq, da = cport.simmatrix_backward(q, a, W, g(golden, dtype, k + "/ds"), dW)
+    assert scaled_err(dW, g(golden, dtype, k + "/dW")) <= TOL[dtype]
+    assert scaled_err(dq, g(golden, dtype, k + "/dq")) <= TOL[dtype]
+    assert scaled_err(da, g(golden, dtype, k + "/da")) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("margin", [1.0, 0.5])
+def test_pairrankloss_golden(golden, dtype, margin):
+    k = "pairrank_m%g" % margin
+    a, b, y = (g(golden, dtype, k + "/" + n) for n in ("a", "b", "y"))
+    loss, ordered, similar = cport.pairrankloss_forward(a, b, y, margin)
+    assert loss == g(golden, dtype, k + "/loss")[0]                    # explicit loops: bit-exact
+    da, db = cport.pairrankloss_backward(y, ordered, similar, top_diff=2.0, ge=False)
+    assert np.array_equal(da, g(golden, dtype, k + "/da"))
+    assert np.array_equal(db, g(golden, dtype, k + "/db"))
+    # the reference's GPU kernel differs only where ordered == 0 (>= instead of >)
+    da_ge, _ = cport.pairrankloss_backward(y, ordered, similar, top_diff=2.0, ge=True)
+    diff = (da_ge != da).reshape(-1)
+    assert np.array_equal(diff, (ordered.reshape(-1) == 0) & (y.reshape(-1) != 0))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_fm_golden(golden, dtype, bias):
+    k = "fm_b%d" % int(bias)
+    x = g(golden, dtype, k + "/x")
+    b = np.array([0.375], dtype=dtype) if bias else None
+    assert np.array_equal(cport.fm_forward(x, b), g(golden, dtype, k + "/y"))
+    dx, db = cport.fm_backward(x, g(golden, dtype, k + "/dy"), bias_term=bias)
+    assert np.array_equal(dx, g(golden, dtype, k + "/dx"))
+    if bias:
+        assert np.array_equal(db, g(golden, dtype, k + "/db"))
+
+
+# ---------------------------------------------------------------- 3. the reference itself
+needs_ref = pytest.mark.skipif(not refbind.ref_available(), reason="oracle/_ref not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 3, 4, 5, 1), (4, 40, 40, 50, 4), (3, 7, 11, 13, 3)])
+def test_simcross_mode2_vs_reference(dtype, shape):
+    N, Lq, La, D, mc = shape
+    rng = np.random.default_rng(sum(shape))
+    q = rng.uniform(-0.08, 0.08, (N, Lq, D)).astype(dtype)
+    a = rng.uniform(-0.08, 0.08, (N, La, D)).astype(dtype)
+    lay = refbind.RefLayer("SimCross", [q, a], {"dist_mode": 2, "mesure_count": mc,
+                           "weight_filler.type": "uniform", "weight_filler.min": -0.1,
+                           "weight_filler.max": 0.1}, dtype=dtype)
+    Mw, B = lay.read("blob", 0), lay.read("blob", 1)
+    assert Mw.shape == (mc, D, D) and B.shape == (mc, Lq, La)
+    lay.forward()
+    S_ref = lay.read("top", 0)
+    S, _, _ = cport.simcross_forward(2, q, a, Mw, B)
+    assert scaled_err(S, S_ref) <= TOL[dtype]
+    dS = rng.uniform(-1, 1, S.shape).astype(dtype)
+    lay.write("top", 0, dS, diff=True)
+    lay.backward([True, True])
+    dq, da, dM, dB = cport.simcross_backward(2, q, a, Mw, S, dS)
+    assert scaled_err(dq, lay.read("bottom", 0, diff=True)) <= 10 * TOL[dtype]
+    assert scaled_err(da, lay.read("bottom", 1, diff=True)) <= 10 * TOL[dtype]
+    assert scaled_err(dM, lay.read("blob", 0, diff=True)) <= 10 * TOL[dtype]
+    assert scaled_err(dB, lay.read("blob", 1, diff=True)) <= TOL[dtype]
+    # second backward: dM is re-zeroed, dB keeps accumulating (sim_cross_layer.cpp:256,301-304)
+    lay.backward([True, True])
+    assert scaled_err(2 * dB, lay.read("blob", 1, diff=True)) <= TOL[dtype]
+    assert scaled_err(dM, lay.read("blob", 0, diff=True)) <= 10 * TOL[dtype]
+
+
+@needs_ref
+def test_simcross_default_filler_is_zero():
+    # caffe.proto:43-47: default filler constant 0 => iteration-0 scores equal B (= 0)
+    rng = np.random.default_rng(3)
+    q = rng.uniform(-1, 1, (2, 4, 6)).astype(np.float32)
+    a = rng.uniform(-1, 1, (2, 5, 6)).astype(np.float32)
+    lay = refbind.RefLayer("SimCross", [q, a], {"dist_mode": 2, "mesure_count": 3})
+    lay.forward()
+    assert not lay.read("top", 0).any()
+    S, _, _ = cport.simcross_forward(2, q, a, lay.read("blob", 0), lay.read("blob", 1))
+    assert not S.any()
+
+
+@needs_ref
+def test_reference_error_behaviour():
+    e = refbind.RefLayer("Embed", [np.zeros((2, 2), np.float32)], {"num_output": 3, "input_dim": 4})
+    e.forward()
+    with pytest.raises(refbind.RefError, match="Can't backpropagate to EmbedLayer input"):
+        e.backward([True])                                   # embed_layer.cpp:158
+    z = np.zeros((3, 1), np.float32)
+    p = refbind.RefLayer("PairRankLoss", [z, z, z], {"loss_weight": 1.0})
+    p.forward()
+    with pytest.raises(refbind.RefError, match="cannot backpropagate to label"):
+        p.backward([True, True, True])                       # pair_rank_loss_layer.cpp:58-61
+    with pytest.raises(refbind.RefError):
+        refbind.RefLayer("SimCross", [np.zeros((2, 3, 4), np.float32), np.zeros((2, 3, 5), np.float32)],
+                         {"dist_mode": 2})                   # height mismatch, sim_cross_layer.cpp:14
+
+
+# ---------------------------------------------------------------- finite differences
+def _fd(f, x, h):
+    gnum = np.zeros_like(x, dtype=np.float64)
+    it = np.nditer(x, flags=["multi_index"])
+    for _ in it:
+        i = it.multi_index
+        old = x[i]
+        x[i] = old + h; fp = f()
+        x[i] = old - h; fm = f()
+        x[i] = old
+        gnum[i] = (fp - fm) / (2 * h)
+    return gnum
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_simcross_finite_differences(mode):
+    rng = np.random.default_rng(11 + mode)
+    N, Lq, La, D, mc = 2, 3, 4, 5, 2
+    q = rng.uniform(-0.5, 0.5, (N, Lq, D))
+    a = rng.uniform(-0.5, 0.5, (N, La, D))
+    Mw = rng.uniform(-0.3, 0.3, (mc, D, D))
+    B = rng.uniform(-0.3, 0.3, (mc, Lq, La))
+    R = rng.uniform(-1, 1, (N, mc if mode == 2 else 1, Lq, La))
+
+    def obj():
+        S, _, _ = cport.simcross_forward(mode, q, a, Mw, B)
+        return float((S * R).sum())
+
+    S, n0, n1 = cport.simcross_forward(mode, q, a, Mw, B)
+    dq, da, dM, dB = cport.simcross_backward(mode, q, a, Mw, S, R, n0, n1)
+    assert scaled_err(dq, _fd(obj, q, 1e-5), 1.0) < 1e-6
+    assert scaled_err(da, _fd(obj, a, 1e-5), 1.0) < 1e-6
+    if mode == 2:
+        assert scaled_err(dM, _fd(obj, Mw, 1e-5), 1.0) < 1e-6
+        assert scaled_err(dB, _fd(obj, B, 1e-5), 1.0) < 1e-6
+
+
+def test_simmatrix_fm_finite_differences():
+    rng = np.random.default_rng(5)
+    q, a, W = rng.uniform(-1, 1, (3, 4)), rng.uniform(-1, 1, (3, 5)), rng.uniform(-1, 1, (4, 5))
+    R = rng.uniform(-1, 1, (3, 1))
+    obj = lambda: float((cport.simmatrix_forward(q, a, W)[0] * R).sum())
+    dW, dq, da = cport.simmatrix_backward(q, a, W, R, np.zeros_like(W))
+    assert scaled_err(dq, _fd(obj, q, 1e-5), 1.0) < 1e-7
+    assert scaled_err(da, _fd(obj, a, 1e-5), 1.0) < 1e-7
+    assert scaled_err(dW, _fd(obj, W, 1e-5), 1.0) < 1e-7
+    x = rng.uniform(-1, 1, (3, 4, 5)); Ry = rng.uniform(-1, 1, (3, 1))
+    objf = lambda: float((cport.fm_forward(x, np.array([0.1])) * Ry).sum())
+    dx, db = cport.fm_backward(x, Ry)
+    assert scaled_err(dx, _fd(objf, x, 1e-5), 1.0) < 1e-7
+    assert abs(db[0] - Ry.sum()) < 1e-12
+
+
+def test_pairrankloss_label_table():
+    # y=1 ordered hinge, y=0 similar |a-b| + margin, y=-1 reversed (+2|a-b|)
+    for y, a, b, want in [(1, 2.0, 0.0, 0.0), (1, 0.0, 2.0, 3.0), (0, 2.0, 0.5, 1.0 + 1.5),
+                          (-1, 0.0, 2.0, 0.0 + 2 * 2.0), (-1, 2.0, 0.0, 3.0 + 4.0)]:
+        loss, _, _ = cport.pairrankloss_forward(np.array([a]), np.array([b]), np.array([float(y)]), 1.0)
+        assert loss == pytest.approx(want)

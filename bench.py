@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the MMS hot path on B200 (see the contract in DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+
+A "step" is one forward+backward pass of the hot path (Embed x2 -> SimCross mode 2 ->
+loss plumbing -> SimCross backward -> Embed scatter-add) over one batch of synthetic
+TREC-QA-shaped QA pairs.  Default workload: BASELINE.json configs[1] (C2: batch 50,
+q/a length 40, 300-d embeddings, mesure_count 4, V = 60002).  With N > 1 every rank runs
+its own batch (weak scaling, as each Caffe solver does) and the flat gradient buffer is
+all-reduced over NCCL and scaled by 1/N inside the step.
+
+Prints ONE JSON line (rank 0).  `value` = QA pairs/s with inputs resident in HBM;
+`e2e` = the same through the public API with pinned-host inputs, H2D of the step's token
+ids and D2H of the step's loss inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "qa_pairs_per_sec_fwd_bwd"
+UNIT = "QA pairs/s"
+
+
+def flops_per_pair(L, D, mc):
+    """Algorithmic FLOPs of SimCross mode 2 per QA pair, fwd+bwd:
+    (6 L D^2 + 8 L^2 D) per measure."""
+    return mc * (6.0 * L * D * D + 8.0 * L * L * D)
+
+
+def workload_config(name):
+    from mms_answer_selection_b200 import synth
+    c = dict(synth.CONFIGS[name])
+    return c
+
+
+# ---------------------------------------------------------------------------- reference arm
+def ref_step_builder(cfg, pairs, threads):
+    """One fwd+bwd step over `pairs` QA pairs through the reference's own layer code
+    (oracle/_ref), or through the C port of it when /root/reference was never built."""
+    from mms_answer_selection_b200 import synth
+    d = synth.make_qa_batch(N=pairs, L=cfg["L"], D=cfg["D"], mc=cfg["mc"], V=cfg["V"])
+    from oracle import refbind
+    if refbind.ref_available():
+        refbind.set_ref_blas_threads(threads)
+        ep = {"num_output": cfg["D"], "input_dim": cfg["V"]}
+        eq = refbind.RefLayer("Embed", [d["idx_q"]], ep)
+        ea = refbind.RefLayer("Embed", [d["idx_a"]], ep)
+        for e in (eq, ea):
+            e.write("blob", 0, d["W"]); e.write("blob", 1, d["b"])
+        eq.forward(); ea.forward()
+        sim = refbind.RefLayer("SimCross", [eq.read("top", 0), ea.read("top", 0)],
+                               {"dist_mode": 2, "mesure_count": cfg["mc"], "loss_weight": 1.0})
+        sim.write("blob", 0, d["M"]); sim.write("blob", 1, d["B"])
+        sim.forward()
+        sim.write("top", 0, d["dS"], diff=True)
+
+        def step():
+            eq.forward(); ea.forward()
+            sim.write("bottom", 0, eq.read("top", 0)); sim.write("bottom", 1, ea.read("top", 0))
+            loss = sim.forward()
+            sim.backward([True, True])
+            eq.write("top", 0, sim.read("bottom", 0, diff=True), diff=True)
+            ea.write("top", 0, sim.read("bottom", 1, diff=True), diff=True)
+            eq.backward([False]); ea.backward([False])
+            return loss
+        return step, "reference"
+    from oracle import cport
+
+    def step():
+        q = cport.embed_forward(d["idx_q"], d["W"], d["b"]); a = cport.embed_forward(d["idx_a"], d["W"], d["b"])
+        S, _, _ = cport.simcross_forward(2, q, a, d["M"], d["B"])
+        dq, da, dM, dB = cport.simcross_backward(2, q, a, d["M"], S, d["dS"])
+        dW, db = np.zeros_like(d["W"]), np.zeros_like(d["b"])
+        cport.embed_backward(d["idx_q"], dq, dW, db); cport.embed_backward(d["idx_a"], da, dW, db)
+        return float((S * d["dS"]).sum())
+    return step, "port"
+
+
+def time_reference(cfg, steps, warmup, budget_s):
+    """Times the CPU implementation on a bounded sample: calibrates seconds/pair, then
+    sizes the per-step sample so that (steps+warmup) steps fit in `budget_s`."""
+    cores = os.cpu_count() or 1
+    probe_pairs = 2
+    step, kind = ref_step_builder(cfg, probe_pairs, cores)
+    step()
+    t0 = time.perf_counter(); step(); t_pair = (time.perf_counter() - t0) / probe_pairs
+    full = cfg["N"]
+    pairs = int(max(1, min(full, budget_s / max(steps + warmup, 1) / max(t_pair, 1e-9))))
+    step, kind = ref_step_builder(cfg, pairs, cores)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    used = cores if kind == "reference" else 1
+    return dict(value=pairs * steps / dt, ms_per_step=dt / steps * 1e3, pairs=pairs, kind=kind, cores=used,
+                sample="%d steps of %d QA pairs (of the %d-pair batch), Embed x2 + SimCross(mode 2) fwd+bwd, "
+                       "%s, BLAS threads=%d" % (steps, pairs, full,
+                                                "reference layer code compiled in place (oracle/_ref)"
+                                                if kind == "reference" else "C port (oracle/mms_oracle.c)", used))
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = workload_config(args.workload)
+    r = time_reference(cfg, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, cfg), "pairs_per_step": r["pairs"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(name, cfg):
+    return ("%s: synthetic TREC-QA-shaped batch, %d QA pairs/step/GPU, q/a len %d, %d-d embeddings, "
+            "mesure_count %d, V=%d; Embed x2 -> SimCross(mode 2) fwd+bwd"
+            % (name.upper(), cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]))
+
+
+# ---------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------- our arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mms_answer_selection_b200 as mms
+    from mms_answer_selection_b200 import synth
+    from mms_answer_selection_b200.parallel import GradientExchange
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = workload_config(args.workload)
+    N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
+
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V, seed=synth.SEED + rank)
+    net = mms.MMSNet(N, L, D, mc, V)
+    w = synth.make_qa_batch(N=1, L=L, D=D, mc=mc, V=V, seed=synth.SEED)      # same weights on every rank
+    net.set_params(w["W"], w["b"], w["M"], w["B"])
+    net.set_inputs(d["idx_q"], d["idx_a"])
+    net.set_upstream_gradient(d["dS"])
+    exch = GradientExchange(net.params()) if world > 1 else None
+    if exch:
+        exch.broadcast_params(0)
+    host_q = torch.from_numpy(d["idx_q"]).pin_memory()
+    host_a = torch.from_numpy(d["idx_a"]).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+    handles = [net.embed_q.handle, net.embed_a.handle, net.sim.handle]
+
+    def device_step():
+        net.ClearParamDiffs()          # Net::ClearParamDiffs (solver.cpp:203): zeroes the V x D diff too
+        net.ForwardBackward(with_loss=False)
+        if exch:
+            exch.allreduce()
+
+    def e2e_step():
+        net.set_inputs_from_pinned(host_q, host_a)      # H2D of this step's inputs
+        net.ClearParamDiffs()
+        loss = net.ForwardBackward(with_loss=True)      # D2H of the step's loss (4 bytes) + sync
+        if exch:
+            exch.allreduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Per-step CUDA-event timing with an L2 flush (untimed) between steps."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for e0, e1 in evs:
+            flush.fill_(1)
+            e0.record()
+            fn()
+            e1.record()
+        barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = sum(h.launch_count() for h in handles)
+    total_ms = timed(device_step, args.steps)
+    launches = sum(h.launch_count() for h in handles) - l0
+    clocks = sampler.stop()
+
+    for _ in range(3):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps)
+
+    # roofline of the dominant kernel, measured live with CUDA events around each launch
+    for h in handles:
+        h.profile_enable(True)
+    for _ in range(min(args.steps, 20)):
+        flush.fill_(1)
+        device_step()
+    prof = {}
+    for h in handles:
+        for k, (n, ms) in h.profile_report().items():
+            pn, pms = prof.get(k, (0, 0.0))
+            prof[k] = (pn + n, pms + ms)
+        h.profile_enable(False)
+    prof_steps = min(args.steps, 20)
+    step_ms_prof = sum(ms for _, ms in prof.values()) / prof_steps
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roof = roofline_for(dom[0], dom[1], prof, prof_steps, cfg, peaks)
+
+    value = N * world * args.steps / (total_ms / 1e3)
+    e2e_value = N * world * args.steps / (e2e_ms / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core contractions, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, cfg), "parallelism": "dp%d" % world,
+                   "l2": "256 MiB L2 flush between timed steps (inputs+table < L2)",
+                   "grad_exchange": "NCCL all-reduce of the flat gradient buffer + 1/N scale" if world > 1 else "none"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(host_q.numel() * 4 + host_a.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels_ms_per_step": {k: round(ms / prof_steps, 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        "kernel_step_ms_sum": step_ms_prof,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = time_reference(cfg, steps=3, warmup=1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline_for(name, rec, prof, steps, cfg, peaks):
+    """Roofline entry for the dominant kernel `name` (launch count, total ms over `steps`)."""
+    n, ms = rec
+    per_launch_s = ms / n / 1e3
+    N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
+    launches_per_step = n / steps
+    tensor_kernels = ("simcross", "tc_", "simt_gemm")
+    if any(t in name for t in tensor_kernels):
+        # the contraction kernels share the algorithmic FLOPs of the step in proportion to
+        # their launches; conservative: attribute the whole SimCross FLOPs to the dominant
+        # kernel family and divide by the family's total device time.
+        fam_ms = sum(m for k, (_, m) in prof.items() if any(t in k for t in tensor_kernels))
+        flops_step = N * flops_per_pair(L, D, mc)
+        achieved = flops_step * steps / (fam_ms / 1e3) / 1e12
+        peak = peaks.get("bf16_tflops", 1590.0) / 2.0       # TF32 dense = half the bf16 rate
+        return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "note": "algorithmic SimCross fwd+bwd FLOPs / summed device time of the contraction kernels; "
+                        "peak = measured cuBLAS bf16 burst / 2 (TF32), %s" % ("of measured" if peaks else "of fallback")}
+    rows = N * 2 * L
+    bytes_launch = rows * (4 + 8 * D) / max(launches_per_step, 1) * 1.0
+    achieved = bytes_launch / per_launch_s / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None,
+            "note": "algorithmic bytes per launch / mean launch time; %s" % ("of measured" if peaks else "of fallback")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

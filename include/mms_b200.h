@@ -1,0 +1,209 @@
+/*
+ * mms_b200.h -- C-ABI of the B200-native MMS hot path (libmms_b200.so).
+ *
+ * Drop-in boundary: every entry point below is what a Caffe Layer subclass's
+ * Forward_gpu / Backward_gpu for this path binds to (see INTEGRATION.md and
+ * mms_answer_selection_b200/caffe_layers/).  Each declaration cites the reference
+ * routine it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no C++/torch types cross this boundary;
+ *  - all data pointers are DEVICE pointers (cudaMalloc'ed, e.g. Blob::gpu_data())
+ *    unless the parameter name ends in _host;
+ *  - tensors are dense row-major, exactly Caffe's Blob layout;
+ *  - <name>_f32 computes on float blobs, <name>_f64 on double blobs
+ *    (Caffe instantiates every layer for both, common.hpp:41-66);
+ *  - work is enqueued on the handle's stream (default: the legacy default stream 0,
+ *    which is what Caffe uses); calls do not synchronise unless
+ *    stated;
+ *  - every function returns 0 on success.  A positive value is a cudaError_t, a
+ *    negative value one of MMS_E_* below; mms_last_error() gives a message for the
+ *    calling thread.  There is NO CPU fallback: without a CUDA device every compute
+ *    entry point fails with a CUDA error.
+ *  - "ACCUMULATES" / "OVERWRITES" state the diff semantics, which follow the
+ *    reference layer by layer (SURVEY.md 8(a)/8(b) "Diff conventions").
+ */
+#ifndef MMS_B200_H_
+#define MMS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMS_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  MMS_E_INVALID = -1,     /* bad argument (null pointer, non-positive size, bad mode) */
+  MMS_E_UNSUPPORTED = -2, /* shape outside what the kernels implement */
+  MMS_E_NOMEM = -3,       /* workspace allocation failed */
+  MMS_E_FAULT = -4        /* a kernel flagged a data fault (e.g. Embed index out of range) */
+};
+
+/* Arithmetic used by the float contractions (SimCross mode 2, SimMatrix, rerank). */
+enum {
+  MMS_MATH_TF32 = 0, /* default: tcgen05 kind::tf32, fp32 accumulate in TMEM */
+  MMS_MATH_FP32 = 1  /* SIMT FFMA path, fp32 throughout (also the shape fallback) */
+};
+
+enum {
+  MMS_OPT_MATH = 1,          /* MMS_MATH_* */
+  MMS_OPT_PRL_GE = 2,        /* PairRankLoss backward hinge test: 0 `ordered > 0` (reference CPU,
+                                pair_rank_loss_layer.cpp:76), 1 `ordered >= 0` (reference GPU,
+                                pair_rank_loss_layer.cu:51).  Default 0. */
+  MMS_OPT_SCRATCH_BYTES = 3, /* cap for the per-call scratch chunk (default 256 MiB) */
+  MMS_OPT_EMBED_DETERMINISTIC = 4 /* Embed backward: 1 = order-independent segmented reduction
+                                (bit-reproducible), 0 = block-aggregated atomics.  Default 0. */
+};
+
+typedef struct mms_context* mms_handle_t;
+
+/* Opaque per-layer workspace: stream, scratch, options.  Create in LayerSetUp,
+ * destroy in the layer destructor; one handle is used by one host thread at a time
+ * (Caffe enters a layer instance from one thread, layer.hpp:451-487). */
+int mms_create(mms_handle_t* out);
+int mms_destroy(mms_handle_t h);
+int mms_set_stream(mms_handle_t h, void* cuda_stream /* cudaStream_t */);
+int mms_set_option(mms_handle_t h, int option, long long value);
+int mms_get_option(mms_handle_t h, int option, long long* value);
+/* Synchronises the handle's stream and reports (then clears) kernel-flagged data
+ * faults: returns MMS_E_FAULT if any Embed index was outside [0, V). */
+int mms_check_faults(mms_handle_t h);
+/* Number of kernels launched through this handle so far (bench.py's gpu_launches). */
+unsigned long long mms_launch_count(mms_handle_t h);
+/* Per-launch device timing with CUDA events on the handle's stream (used by bench.py for
+ * the roofline line; never on by default).  mms_profile_report writes one line per kernel
+ * name, "<name> <launches> <total_ms>", synchronises the stream and clears the records. */
+int mms_profile_enable(mms_handle_t h, int on);
+int mms_profile_report(mms_handle_t h, char* buf, size_t size);
+const char* mms_last_error(void);
+int mms_version(void);
+/* 1 if the library can run here (CUDA device of compute capability 10.x present). */
+int mms_device_ok(void);
+
+/* ------------------------------------------------------------------ Embed --
+ * Replaces EmbedLayer::Forward_gpu (src/caffe/layers/embed_layer.cu:42-56):
+ * top[n,:] = W[(int)idx[n],:] (+ bias).  idx holds M float-encoded row ids.
+ * Bit-exact.  bias may be NULL (bias_term: false). */
+int mms_embed_forward_f32(mms_handle_t h, const float* idx, const float* W, const float* bias,
+                          float* top, long long M, int D, int V);
+int mms_embed_forward_f64(mms_handle_t h, const double* idx, const double* W, const double* bias,
+                          double* top, long long M, int D, int V);
+/* Replaces EmbedLayer::Backward_gpu (embed_layer.cu:59-77): dW[idx[n],:] += dtop[n,:],
+ * dbias += sum_n dtop[n,:].  ACCUMULATES into dW/dbias (the solver zeroes them).
+ * dW or dbias may be NULL (param_propagate_down_ false / no bias). */
+int mms_embed_backward_f32(mms_handle_t h, const float* idx, const float* dtop, float* dW,
+                           float* dbias, long long M, int D, int V);
+int mms_embed_backward_f64(mms_handle_t h, const double* idx, const double* dtop, double* dW,
+                           double* dbias, long long M, int D, int V);
+
+/* --------------------------------------------------------------- SimCross --
+ * Replaces SimCrossLayer::Forward_gpu (src/caffe/layers/sim_cross_layer.cu:127-190,
+ * whose mode 2 falls back to Forward_cpu, sim_cross_layer.cpp:140-161).
+ *   q (N,Lq,D), a (N,La,D); mode 0 cosine, 1 1/(1+||q-a||), 2 bilinear.
+ *   mode 2: Mw (mc,D,D), B (mc,Lq,La) or NULL; S (N,mc,Lq,La) = Q M_k A^T + B_k.
+ *   modes 0/1: S (N,1,Lq,La); Mw/B ignored; norm0 (N,Lq) / norm1 (N,La) are the
+ *   mode-0 row-norm caches (data0_norm_/data1_norm_), NULL otherwise. */
+int mms_simcross_forward_f32(mms_handle_t h, int mode, const float* q, const float* a,
+                             const float* Mw, const float* B, float* S, float* norm0, float* norm1,
+                             int N, int Lq, int La, int D, int mc);
+int mms_simcross_forward_f64(mms_handle_t h, int mode, const double* q, const double* a,
+                             const double* Mw, const double* B, double* S, double* norm0,
+                             double* norm1, int N, int Lq, int La, int D, int mc);
+/* Replaces SimCrossLayer::Backward_gpu (sim_cross_layer.cu:193-243 -> Backward_cpu,
+ * sim_cross_layer.cpp:166-307).  OVERWRITES dq and da (zeroed first, :176-177, even when
+ * nothing propagates); the rest runs only if prop0 || prop1 (:201).  Mode 2: OVERWRITES dM
+ * (zeroed, :256) and ACCUMULATES into dB (:301-304; NULL when bias_term is false).
+ * S is the forward output (read by modes 0/1 only). */
+int mms_simcross_backward_f32(mms_handle_t h, int mode, const float* q, const float* a,
+                              const float* Mw, const float* S, const float* dS, const float* norm0,
+                              const float* norm1, float* dq, float* da, float* dM, float* dB,
+                              int N, int Lq, int La, int D, int mc, int prop0, int prop1);
+int mms_simcross_backward_f64(mms_handle_t h, int mode, const double* q, const double* a,
+                              const double* Mw, const double* S, const double* dS,
+                              const double* norm0, const double* norm1, double* dq, double* da,
+                              double* dM, double* dB, int N, int Lq, int La, int D, int mc,
+                              int prop0, int prop1);
+
+/* -------------------------------------------------------------- SimMatrix --
+ * Replaces SimMatrixLayer::Forward_gpu (src/caffe/layers/sim_matrix_layer.cu:20-40):
+ * T = q W (N,K2), written to `T` -- the reference keeps it in bottom[1]'s diff buffer
+ * (sim_matrix_layer.cpp:58) -- and s_n = <a_n, T_n>.  q (N,K1), a (N,K2), W (K1,K2), s (N). */
+int mms_simmatrix_forward_f32(mms_handle_t h, const float* q, const float* a, const float* W,
+                              float* s, float* T, int N, int K1, int K2);
+int mms_simmatrix_forward_f64(mms_handle_t h, const double* q, const double* a, const double* W,
+                              double* s, double* T, int N, int K1, int K2);
+/* Replaces SimMatrixLayer::Backward_gpu (= Backward_cpu, sim_matrix_layer.cpp:68-95):
+ * dW += sum_n ds_n q_n a_n^T (ACCUMULATES, if prop_w); dq_n = ds_n W a_n (OVERWRITES, if
+ * prop0); da_n = ds_n W^T q_n (OVERWRITES, if prop1). */
+int mms_simmatrix_backward_f32(mms_handle_t h, const float* q, const float* a, const float* W,
+                               const float* ds, float* dW, float* dq, float* da, int N, int K1,
+                               int K2, int prop_w, int prop0, int prop1);
+int mms_simmatrix_backward_f64(mms_handle_t h, const double* q, const double* a, const double* W,
+                               const double* ds, double* dW, double* dq, double* da, int N, int K1,
+                               int K2, int prop_w, int prop0, int prop1);
+
+/* ----------------------------------------------------------- PairRankLoss --
+ * Replaces PairRankLossLayer::Forward_gpu (src/caffe/layers/pair_rank_loss_layer.cu:11-43):
+ * ordered = margin - y (a-b), similar = a-b (both cached, `count` elements each),
+ * *loss = (1/count) sum[max(0,ordered) + |(1-y) similar|].  loss is a DEVICE scalar. */
+int mms_pairrankloss_forward_f32(mms_handle_t h, const float* a, const float* b, const float* y,
+                                 float margin, long long count, float* loss, float* ordered,
+                                 float* similar);
+int mms_pairrankloss_forward_f64(mms_handle_t h, const double* a, const double* b, const double* y,
+                                 double margin, long long count, double* loss, double* ordered,
+                                 double* similar);
+/* Replaces PairRankLossLayer::Backward_gpu (pair_rank_loss_layer.cu:46-82):
+ * d{a,b}[i] = sign * (top_diff/count) * ([ordered>0] y - sgn((1-y) similar) (1-y)), sign -1 for a,
+ * +1 for b, sgn(0) = -1.  OVERWRITES; da / db may be NULL (propagate_down false).
+ * top_diff_host is top[0]->cpu_diff()[0] (the loss weight), a host scalar. */
+int mms_pairrankloss_backward_f32(mms_handle_t h, const float* y, const float* ordered,
+                                  const float* similar, float top_diff_host, long long count,
+                                  float* da, float* db);
+int mms_pairrankloss_backward_f64(mms_handle_t h, const double* y, const double* ordered,
+                                  const double* similar, double top_diff_host, long long count,
+                                  double* da, double* db);
+
+/* --------------------------------------------------------------------- FM --
+ * Replaces FMLayer::Forward_gpu (src/caffe/layers/fm_layer.cu:12-15 -> Forward_cpu,
+ * fm_layer.cpp:33-62): x (N,C,Dm), y_n = 1/2 sum_{j>=1}[(sum_k x_kj)^2 - sum_k x_kj^2]
+ * + sum_k x_k0 + bias.  bias: device scalar or NULL. */
+int mms_fm_forward_f32(mms_handle_t h, const float* x, const float* bias, float* y, int N, int C,
+                       int Dm);
+int mms_fm_forward_f64(mms_handle_t h, const double* x, const double* bias, double* y, int N, int C,
+                       int Dm);
+/* Replaces FMLayer::Backward_gpu (fm_layer.cu:18-21 -> Backward_cpu, fm_layer.cpp:65-99):
+ * dbias = sum dy (OVERWRITES, :77; NULL to skip); dx OVERWRITTEN if prop0. */
+int mms_fm_backward_f32(mms_handle_t h, const float* x, const float* dy, float* dx, float* dbias,
+                        int N, int C, int Dm, int prop0);
+int mms_fm_backward_f64(mms_handle_t h, const double* x, const double* dy, double* dx,
+                        double* dbias, int N, int C, int Dm, int prop0);
+
+/* ------------------------------------------------------- loss plumbing ------
+ * Replaces the loss reduction in Layer::Forward (include/caffe/layer.hpp:471-479,
+ * caffe_gpu_dot(count, top.data, top.diff)): *out = sum_i data[i]*diff[i], device scalar. */
+int mms_dot_f32(mms_handle_t h, const float* data, const float* diff, long long count, float* out);
+int mms_dot_f64(mms_handle_t h, const double* data, const double* diff, long long count,
+                double* out);
+
+/* ------------------------------------------------- data-parallel exchange ---
+ * Replaces the root's 1/solver_count scaling of the summed gradient buffer in
+ * P2PSync::on_gradients_ready (src/caffe/parallel.cpp:377, caffe_gpu_scal): x *= alpha.
+ * The cross-GPU sum itself is an NCCL all-reduce issued by the host layer. */
+int mms_scale_f32(mms_handle_t h, float* x, long long count, float alpha);
+int mms_scale_f64(mms_handle_t h, double* x, long long count, double alpha);
+
+/* ------------------------------------------------------ candidate scoring ---
+ * Reranking with the SimMatrix bilinear form (BASELINE config "1k queries x 1M candidates"):
+ * scores[i,j] = q_i^T W c_j.  Q (Nq,K1), C (Nc,K2), W (K1,K2), scores (Nq,Nc) row-major.
+ * Same arithmetic as SimMatrixLayer::Forward (sim_matrix_layer.cpp:53-65) applied to every
+ * (query, candidate) pair; QW (Nq,K2) is scratch supplied by the caller. */
+int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W,
+                          float* QW, float* scores, int Nq, long long Nc, int K1, int K2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMS_B200_H_ */

@@ -1,0 +1,126 @@
+"""ctypes binding of libmms_b200.so -- the reference-side stub for a Python host
+(INTEGRATION.md shows the C++ one for Caffe).  Signatures follow include/mms_b200.h."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmms_b200.so")
+_lib = None
+
+c_int, c_ll, c_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p
+c_f, c_d = ctypes.c_float, ctypes.c_double
+
+MMS_MATH_TF32, MMS_MATH_FP32 = 0, 1
+MMS_OPT_MATH, MMS_OPT_PRL_GE, MMS_OPT_SCRATCH_BYTES, MMS_OPT_EMBED_DETERMINISTIC = 1, 2, 3, 4
+MMS_E_INVALID, MMS_E_UNSUPPORTED, MMS_E_NOMEM, MMS_E_FAULT = -1, -2, -3, -4
+
+
+class MMSError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "libmms_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def _typed(real):
+    p = c_p
+    return {
+        "mms_embed_forward": [p, p, p, p, p, c_ll, c_int, c_int],
+        "mms_embed_backward": [p, p, p, p, p, c_ll, c_int, c_int],
+        "mms_simcross_forward": [p, c_int, p, p, p, p, p, p, p, c_int, c_int, c_int, c_int, c_int],
+        "mms_simcross_backward": [p, c_int, p, p, p, p, p, p, p, p, p, p, p, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int],
+        "mms_simmatrix_forward": [p, p, p, p, p, p, c_int, c_int, c_int],
+        "mms_simmatrix_backward": [p, p, p, p, p, p, p, p, c_int, c_int, c_int, c_int, c_int, c_int],
+        "mms_pairrankloss_forward": [p, p, p, p, real, c_ll, p, p, p],
+        "mms_pairrankloss_backward": [p, p, p, p, real, c_ll, p, p],
+        "mms_fm_forward": [p, p, p, p, c_int, c_int, c_int],
+        "mms_fm_backward": [p, p, p, p, p, c_int, c_int, c_int, c_int],
+        "mms_dot": [p, p, p, c_ll, p],
+        "mms_scale": [p, p, c_ll, real],
+    }
+
+
+def lib():
+    """Load libmms_b200.so.  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise MMSError(0, "%s is missing: run `python -m mms_answer_selection_b200.build` "
+                              "(no CPU/PyTorch fallback exists)" % _LIB_PATH)
+        L = ctypes.CDLL(_LIB_PATH)
+        L.mms_last_error.restype = ctypes.c_char_p
+        L.mms_create.argtypes = [ctypes.POINTER(c_p)]
+        L.mms_destroy.argtypes = [c_p]
+        L.mms_set_stream.argtypes = [c_p, c_p]
+        L.mms_set_option.argtypes = [c_p, c_int, c_ll]
+        L.mms_get_option.argtypes = [c_p, c_int, ctypes.POINTER(c_ll)]
+        L.mms_check_faults.argtypes = [c_p]
+        L.mms_launch_count.argtypes = [c_p]
+        L.mms_launch_count.restype = ctypes.c_ulonglong
+        L.mms_profile_enable.argtypes = [c_p, c_int]
+        L.mms_profile_report.argtypes = [c_p, ctypes.c_char_p, ctypes.c_size_t]
+        for suffix, real in (("_f32", c_f), ("_f64", c_d)):
+            for name, args in _typed(real).items():
+                fn = getattr(L, name + suffix)
+                fn.argtypes = args
+                fn.restype = c_int
+        L.mms_rerank_scores_f32.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_ll, c_int, c_int]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MMSError(rc, lib().mms_last_error().decode(errors="replace"))
+
+
+class Handle(object):
+    """Owns one mms_handle_t (per layer, like the reference's per-layer state)."""
+
+    def __init__(self):
+        self._h = c_p()
+        check(lib().mms_create(ctypes.byref(self._h)))
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def set_stream(self, cuda_stream):
+        check(lib().mms_set_stream(self._h, c_p(cuda_stream)))
+
+    def set_option(self, opt, value):
+        check(lib().mms_set_option(self._h, opt, int(value)))
+
+    def launch_count(self):
+        return int(lib().mms_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        check(lib().mms_profile_enable(self._h, int(on)))
+
+    def profile_report(self):
+        """{kernel name: (launches, total_ms)} since profiling was enabled / last report."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(lib().mms_profile_report(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
+
+    def check_faults(self):
+        check(lib().mms_check_faults(self._h))
+
+    def close(self):
+        if self._h:
+            lib().mms_destroy(self._h)
+            self._h = c_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

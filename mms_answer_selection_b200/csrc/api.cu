@@ -1,0 +1,268 @@
+// C-ABI of libmms_b200.so (declared in include/mms_b200.h): context management and thin
+// extern "C" wrappers over the templated layer implementations.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "mms_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mms_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_bytes) {
+    if (ctx->scratch) {
+      // earlier launches on the stream may still read the old buffer
+      MMS_CUDA(cudaStreamSynchronize(ctx->stream));
+      MMS_CUDA(cudaFree(ctx->scratch));
+      ctx->scratch = nullptr;
+      ctx->scratch_bytes = 0;
+    }
+    const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    cudaError_t e = cudaMalloc(&ctx->scratch, want);
+    if (e != cudaSuccess) {
+      mms_set_error("scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+      return MMS_E_NOMEM;
+    }
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->scratch;
+  return 0;
+}
+
+void mms_tc_destroy_state(mms_context* ctx);
+
+// ---- per-launch CUDA-event profiler -----------------------------------------------------
+#include <map>
+#include <string>
+#include <vector>
+namespace {
+struct ProfRecord { const char* name; cudaEvent_t e0, e1; };
+std::vector<ProfRecord>* prof_of(mms_context* ctx) {
+  if (!ctx->prof) ctx->prof = new std::vector<ProfRecord>();
+  return static_cast<std::vector<ProfRecord>*>(ctx->prof);
+}
+void prof_clear(mms_context* ctx) {
+  if (!ctx->prof) return;
+  for (auto& r : *prof_of(ctx)) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  prof_of(ctx)->clear();
+}
+}  // namespace
+
+MmsKernelScope::MmsKernelScope(mms_context* c, const char* name) : ctx(c), slot(-1) {
+  ctx->launches++;
+  if (!ctx->profile) return;
+  ProfRecord r; r.name = name;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, ctx->stream);
+  prof_of(ctx)->push_back(r);
+  slot = (int)prof_of(ctx)->size() - 1;
+}
+MmsKernelScope::~MmsKernelScope() {
+  if (slot >= 0) cudaEventRecord((*prof_of(ctx))[slot].e1, ctx->stream);
+}
+
+extern "C" {
+
+const char* mms_last_error(void) { return g_err; }
+int mms_version(void) { return MMS_B200_VERSION; }
+
+int mms_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int mms_create(mms_handle_t* out) {
+  MMS_REQUIRE(out, MMS_E_INVALID, "null handle pointer");
+  *out = nullptr;
+  int dev = 0;
+  MMS_CUDA(cudaGetDevice(&dev));
+  int major = 0, sms = 0;
+  MMS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  MMS_REQUIRE(major == 10, MMS_E_UNSUPPORTED,
+              "libmms_b200 is built for sm_100a only; no CPU or other-GPU fallback exists");
+  mms_context* ctx = new (std::nothrow) mms_context();
+  MMS_REQUIRE(ctx, MMS_E_NOMEM, "out of host memory");
+  ctx->device = dev;
+  ctx->sm_count = sms;
+  cudaError_t e = cudaMalloc(&ctx->fault_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->fault_flag, 0, sizeof(int));
+  if (e != cudaSuccess) {
+    mms_set_error("context allocation failed: %s", cudaGetErrorString(e));
+    delete ctx;
+    return (int)e;
+  }
+  *out = ctx;
+  return 0;
+}
+
+int mms_destroy(mms_handle_t h) {
+  if (!h) return 0;
+  cudaStreamSynchronize(h->stream);
+  mms_tc_destroy_state(h);
+  prof_clear(h);
+  delete static_cast<std::vector<ProfRecord>*>(h->prof);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->fault_flag) cudaFree(h->fault_flag);
+  delete h;
+  return 0;
+}
+
+int mms_set_stream(mms_handle_t h, void* s) {
+  MMS_REQUIRE(h, MMS_E_INVALID, "null handle");
+  h->stream = static_cast<cudaStream_t>(s);
+  return 0;
+}
+
+int mms_set_option(mms_handle_t h, int option, long long value) {
+  MMS_REQUIRE(h, MMS_E_INVALID, "null handle");
+  switch (option) {
+    case MMS_OPT_MATH:
+      MMS_REQUIRE(value == MMS_MATH_TF32 || value == MMS_MATH_FP32, MMS_E_INVALID, "bad math mode");
+      h->math = (int)value; return 0;
+    case MMS_OPT_PRL_GE: h->prl_ge = value != 0; return 0;
+    case MMS_OPT_SCRATCH_BYTES:
+      MMS_REQUIRE(value >= (1 << 20), MMS_E_INVALID, "scratch cap below 1 MiB");
+      h->scratch_cap = (size_t)value; return 0;
+    case MMS_OPT_EMBED_DETERMINISTIC: h->embed_deterministic = value != 0; return 0;
+    default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
+  }
+}
+
+int mms_get_option(mms_handle_t h, int option, long long* value) {
+  MMS_REQUIRE(h && value, MMS_E_INVALID, "null argument");
+  switch (option) {
+    case MMS_OPT_MATH: *value = h->math; return 0;
+    case MMS_OPT_PRL_GE: *value = h->prl_ge; return 0;
+    case MMS_OPT_SCRATCH_BYTES: *value = (long long)h->scratch_cap; return 0;
+    case MMS_OPT_EMBED_DETERMINISTIC: *value = h->embed_deterministic; return 0;
+    default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
+  }
+}
+
+unsigned long long mms_launch_count(mms_handle_t h) { return h ? h->launches : 0; }
+
+int mms_profile_enable(mms_handle_t h, int on) {
+  MMS_REQUIRE(h, MMS_E_INVALID, "null handle");
+  MMS_CUDA(cudaStreamSynchronize(h->stream));
+  prof_clear(h);
+  h->profile = on != 0;
+  return 0;
+}
+
+// Writes one line per kernel name: "<name> <launches> <total_ms>\n"; clears the records.
+int mms_profile_report(mms_handle_t h, char* buf, size_t size) {
+  MMS_REQUIRE(h && buf && size > 0, MMS_E_INVALID, "null argument");
+  MMS_CUDA(cudaStreamSynchronize(h->stream));
+  std::map<std::string, std::pair<long long, double> > agg;
+  std::vector<std::string> order;
+  if (h->prof) {
+    for (auto& r : *prof_of(h)) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (!agg.count(r.name)) order.push_back(r.name);
+      agg[r.name].first += 1;
+      agg[r.name].second += ms;
+    }
+  }
+  std::string out;
+  char line[256];
+  for (auto& n : order) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+    out += line;
+  }
+  snprintf(buf, size, "%s", out.c_str());
+  prof_clear(h);
+  return 0;
+}
+
+int mms_check_faults(mms_handle_t h) {
+  MMS_REQUIRE(h, MMS_E_INVALID, "null handle");
+  int flag = 0;
+  MMS_CUDA(cudaMemcpyAsync(&flag, h->fault_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MMS_CUDA(cudaStreamSynchronize(h->stream));
+  if (flag) {
+    MMS_CUDA(cudaMemsetAsync(h->fault_flag, 0, sizeof(int), h->stream));
+    mms_set_error("Embed: an input index was outside [0, input_dim)");
+    return MMS_E_FAULT;
+  }
+  return 0;
+}
+
+#define H MMS_REQUIRE(h, MMS_E_INVALID, "null handle")
+
+#define MMS_DEFINE_TYPED(T, SUF)                                                                   \
+  int mms_embed_forward_##SUF(mms_handle_t h, const T* idx, const T* W, const T* bias, T* top,     \
+                              long long M, int D, int V) {                                         \
+    H; return mms_embed_forward_impl<T>(h, idx, W, bias, top, M, D, V);                            \
+  }                                                                                                \
+  int mms_embed_backward_##SUF(mms_handle_t h, const T* idx, const T* dtop, T* dW, T* dbias,       \
+                               long long M, int D, int V) {                                        \
+    H; return mms_embed_backward_impl<T>(h, idx, dtop, dW, dbias, M, D, V);                        \
+  }                                                                                                \
+  int mms_simcross_forward_##SUF(mms_handle_t h, int mode, const T* q, const T* a, const T* Mw,    \
+                                 const T* B, T* S, T* n0, T* n1, int N, int Lq, int La, int D,     \
+                                 int mc) {                                                         \
+    H; return mms_simcross_forward_impl<T>(h, mode, q, a, Mw, B, S, n0, n1, N, Lq, La, D, mc);     \
+  }                                                                                                \
+  int mms_simcross_backward_##SUF(mms_handle_t h, int mode, const T* q, const T* a, const T* Mw,   \
+                                  const T* S, const T* dS, const T* n0, const T* n1, T* dq, T* da, \
+                                  T* dM, T* dB, int N, int Lq, int La, int D, int mc, int p0,      \
+                                  int p1) {                                                        \
+    H; return mms_simcross_backward_impl<T>(h, mode, q, a, Mw, S, dS, n0, n1, dq, da, dM, dB, N,   \
+                                            Lq, La, D, mc, p0, p1);                                \
+  }                                                                                                \
+  int mms_simmatrix_forward_##SUF(mms_handle_t h, const T* q, const T* a, const T* W, T* s, T* Tm, \
+                                  int N, int K1, int K2) {                                         \
+    H; return mms_simmatrix_forward_impl<T>(h, q, a, W, s, Tm, N, K1, K2);                         \
+  }                                                                                                \
+  int mms_simmatrix_backward_##SUF(mms_handle_t h, const T* q, const T* a, const T* W,             \
+                                   const T* ds, T* dW, T* dq, T* da, int N, int K1, int K2,        \
+                                   int pw, int p0, int p1) {                                       \
+    H; return mms_simmatrix_backward_impl<T>(h, q, a, W, ds, dW, dq, da, N, K1, K2, pw, p0, p1);   \
+  }                                                                                                \
+  int mms_pairrankloss_forward_##SUF(mms_handle_t h, const T* a, const T* b, const T* y, T margin, \
+                                     long long count, T* loss, T* ordered, T* similar) {           \
+    H; return mms_pairrankloss_forward_impl<T>(h, a, b, y, margin, count, loss, ordered, similar); \
+  }                                                                                                \
+  int mms_pairrankloss_backward_##SUF(mms_handle_t h, const T* y, const T* ordered,                \
+                                      const T* similar, T top_diff, long long count, T* da,        \
+                                      T* db) {                                                     \
+    H; return mms_pairrankloss_backward_impl<T>(h, y, ordered, similar, top_diff, count, da, db);  \
+  }                                                                                                \
+  int mms_fm_forward_##SUF(mms_handle_t h, const T* x, const T* bias, T* y, int N, int C, int Dm) {\
+    H; return mms_fm_forward_impl<T>(h, x, bias, y, N, C, Dm);                                     \
+  }                                                                                                \
+  int mms_fm_backward_##SUF(mms_handle_t h, const T* x, const T* dy, T* dx, T* dbias, int N,       \
+                            int C, int Dm, int prop0) {                                            \
+    H; return mms_fm_backward_impl<T>(h, x, dy, dx, dbias, N, C, Dm, prop0);                       \
+  }                                                                                                \
+  int mms_dot_##SUF(mms_handle_t h, const T* data, const T* diff, long long count, T* out) {       \
+    H; MMS_REQUIRE(diff, MMS_E_INVALID, "null pointer");                                           \
+    return mms_dot_impl<T>(h, data, diff, count, out);                                             \
+  }                                                                                                \
+  int mms_scale_##SUF(mms_handle_t h, T* x, long long count, T alpha) {                            \
+    H; return mms_scale_impl<T>(h, x, count, alpha);                                               \
+  }
+
+MMS_DEFINE_TYPED(float, f32)
+MMS_DEFINE_TYPED(double, f64)
+
+int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W, float* QW,
+                          float* scores, int Nq, long long Nc, int K1, int K2) {
+  H; return mms_rerank_scores_impl(h, Q, C, W, QW, scores, Nq, Nc, K1, K2);
+}
+
+}  // extern "C"

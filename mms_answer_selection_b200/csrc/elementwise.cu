@@ -1,0 +1,253 @@
+// PairRankLoss, FM, the loss dot-product and the 1/n gradient scaling: HBM-bound
+// elementwise / reduction kernels.  Row and block reductions use warp shuffles; the
+// cross-block step is a second fixed-order pass, so results are run-to-run
+// reproducible (no floating-point atomics).
+#include "mms_common.cuh"
+
+namespace {
+
+constexpr int kRedThreads = 256;
+constexpr int kMaxPartials = 1024;
+
+// round-to-nearest mul/add that the compiler never contracts into an FMA: the hinge
+// test `ordered > 0` must see exactly the reference's two-rounding value.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v) {
+  __shared__ T s[kRedThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < kRedThreads / 32) ? s[threadIdx.x] : T(0);
+  if (w == 0) v = warp_sum(v);
+  return v;   // valid in thread 0
+}
+
+// second pass: out = sum(partials[0..n)) / divisor
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads) finish_sum_kernel(const T* __restrict__ partials, int n,
+                                                                 T divisor, T* __restrict__ out) {
+  T v = T(0);
+  for (int i = threadIdx.x; i < n; i += kRedThreads) v += partials[i];
+  v = block_sum(v);
+  if (threadIdx.x == 0) *out = v / divisor;
+}
+
+// ---- PairRankLoss (pair_rank_loss_layer.cu:17-41 / .cpp:26-52, MKL axpby semantics) ----
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+prl_forward_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ y, T margin,
+                   long long count, T* __restrict__ ordered, T* __restrict__ similar,
+                   T* __restrict__ partials) {
+  T acc = T(0);
+  for (long long i = blockIdx.x * (long long)kRedThreads + threadIdx.x; i < count;
+       i += (long long)gridDim.x * kRedThreads) {
+    const T d = a[i] - b[i];
+    const T yy = y[i];
+    const T o = add_rn(mul_rn(T(-1), mul_rn(d, yy)), margin);   // mul, axpby(-1), add_scalar
+    similar[i] = d;
+    ordered[i] = o;
+    acc += max(T(0), o) + abs(mul_rn(T(1) - yy, d));
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// pair_rank_loss_layer.cu:46-55 (GE) / pair_rank_loss_layer.cpp:70-80 (GT)
+template <typename T>
+__global__ void prl_backward_kernel(const T* __restrict__ y, const T* __restrict__ ordered,
+                                    const T* __restrict__ similar, T sign_a, T sign_b, int ge,
+                                    long long count, T* __restrict__ da, T* __restrict__ db) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const T yy = y[i];
+    const T o = ordered[i];
+    const T ot = (ge ? (o >= T(0)) : (o > T(0))) ? T(1) : T(0);
+    const T st = ((T(1) - yy) * similar[i] > T(0)) ? T(1) : T(-1);
+    const T core = add_rn(mul_rn(ot, yy), -mul_rn(st, T(1) - yy));
+    if (da) da[i] = mul_rn(sign_a, core);
+    if (db) db[i] = mul_rn(sign_b, core);
+  }
+}
+
+// ---- FM (fm_layer.cpp:33-99): one warp per sample ----------------------------------------
+template <typename T>
+__global__ void fm_forward_kernel(const T* __restrict__ x, const T* __restrict__ bias, T* __restrict__ y,
+                                  int N, int C, int Dm) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < N; i += nwarps) {
+    const T* xi = x + (size_t)i * C * Dm;
+    T t1 = T(0);
+    for (int j = 1 + lane; j < Dm; j += 32) {
+      T t2 = T(0), sq = T(0);
+      for (int k = 0; k < C; ++k) { const T v = xi[k * Dm + j]; t2 += v; sq += v * v; }
+      t1 += t2 * t2 - sq;
+    }
+    t1 = warp_sum(t1) / T(2);
+    T lin = T(0);
+    for (int k = lane; k < C; k += 32) lin += xi[k * Dm];
+    lin = warp_sum(lin);
+    if (lane == 0) y[i] = t1 + lin + (bias ? bias[0] : T(0));
+  }
+}
+
+template <typename T>
+__global__ void fm_backward_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                   int N, int C, int Dm) {
+  const long long total = (long long)N * Dm;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % Dm);
+    const int i = (int)(e / Dm);
+    const T g = dy[i];
+    const T* xi = x + (size_t)i * C * Dm;
+    T* di = dx + (size_t)i * C * Dm;
+    if (j == 0) {
+      for (int k = 0; k < C; ++k) di[k * Dm] = g;
+    } else {
+      T tt = T(0);
+      for (int k = 0; k < C; ++k) tt += xi[k * Dm + j];
+      for (int k = 0; k < C; ++k) di[k * Dm + j] = g * (tt - xi[k * Dm + j]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+sum_kernel(const T* __restrict__ x, const T* __restrict__ yv, long long n, T* __restrict__ partials) {
+  T acc = T(0);
+  for (long long i = blockIdx.x * (long long)kRedThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kRedThreads)
+    acc += yv ? x[i] * yv[i] : x[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+template <typename T>
+__global__ void scale_kernel(T* __restrict__ x, long long n, T alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    x[i] *= alpha;
+}
+
+inline int red_grid(mms_context* ctx, long long n) {
+  long long g = (n + kRedThreads - 1) / kRedThreads;
+  g = mms_min<long long>(g, mms_min<long long>(kMaxPartials, (long long)ctx->sm_count * 4));
+  return (int)mms_max<long long>(g, 1);
+}
+inline int ew_grid(mms_context* ctx, long long n) {
+  return (int)mms_max<long long>(1, mms_min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16));
+}
+
+}  // namespace
+
+template <typename T>
+int mms_pairrankloss_forward_impl(mms_context* ctx, const T* a, const T* b, const T* y, T margin,
+                                  long long count, T* loss, T* ordered, T* similar) {
+  MMS_REQUIRE(a && b && y && loss && ordered && similar, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(count > 0, MMS_E_INVALID, "count must be positive");
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(T) * kMaxPartials, &sp));
+  T* partials = static_cast<T*>(sp);
+  const int grid = red_grid(ctx, count);
+  { MmsKernelScope ks_(ctx, "prl_forward_kernel");
+    prl_forward_kernel<T><<<grid, kRedThreads, 0, ctx->stream>>>(a, b, y, margin, count, ordered, similar, partials); }
+  MMS_LAUNCH_CHECK();
+  { MmsKernelScope ks_(ctx, "finish_sum_kernel");
+    finish_sum_kernel<T><<<1, kRedThreads, 0, ctx->stream>>>(partials, grid, static_cast<T>(count), loss); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_pairrankloss_backward_impl(mms_context* ctx, const T* y, const T* ordered, const T* similar,
+                                   T top_diff, long long count, T* da, T* db) {
+  MMS_REQUIRE(y && ordered && similar, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(count > 0, MMS_E_INVALID, "count must be positive");
+  if (!da && !db) return 0;
+  const T base = top_diff / static_cast<T>(count);   // sign *= top.diff / count (:67)
+  { MmsKernelScope ks_(ctx, "prl_backward_kernel");
+    prl_backward_kernel<T><<<ew_grid(ctx, count), 256, 0, ctx->stream>>>(y, ordered, similar, T(-1) * base,
+                                                                       T(1) * base, ctx->prl_ge, count, da, db); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_fm_forward_impl(mms_context* ctx, const T* x, const T* bias, T* y, int N, int C, int Dm) {
+  MMS_REQUIRE(x && y, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && C > 0 && Dm > 0, MMS_E_INVALID, "bad size");
+  if (N == 0) return 0;
+  { MmsKernelScope ks_(ctx, "fm_forward_kernel");
+    fm_forward_kernel<T><<<ew_grid(ctx, (long long)N * 32), 256, 0, ctx->stream>>>(x, bias, y, N, C, Dm); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_fm_backward_impl(mms_context* ctx, const T* x, const T* dy, T* dx, T* dbias, int N, int C, int Dm,
+                         int prop0) {
+  MMS_REQUIRE(x && dy, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && C > 0 && Dm > 0, MMS_E_INVALID, "bad size");
+  if (N == 0) return 0;
+  if (dbias) MMS_TRY(mms_dot_impl<T>(ctx, dy, nullptr, N, dbias));   // db = sum dy, overwritten (:77)
+  if (prop0) {
+    MMS_REQUIRE(dx, MMS_E_INVALID, "null dx");
+    { MmsKernelScope ks_(ctx, "fm_backward_kernel");
+      fm_backward_kernel<T><<<ew_grid(ctx, (long long)N * Dm), 256, 0, ctx->stream>>>(x, dy, dx, N, C, Dm); }
+    MMS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+template <typename T>
+int mms_dot_impl(mms_context* ctx, const T* x, const T* y, long long n, T* out) {
+  MMS_REQUIRE(x && out, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(n >= 0, MMS_E_INVALID, "bad size");
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(T) * kMaxPartials, &sp));
+  T* partials = static_cast<T*>(sp);
+  const int grid = red_grid(ctx, n);
+  { MmsKernelScope ks_(ctx, "sum_kernel");
+    sum_kernel<T><<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, partials); }
+  MMS_LAUNCH_CHECK();
+  { MmsKernelScope ks_(ctx, "finish_sum_kernel");
+    finish_sum_kernel<T><<<1, kRedThreads, 0, ctx->stream>>>(partials, grid, T(1), out); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_scale_impl(mms_context* ctx, T* x, long long n, T alpha) {
+  MMS_REQUIRE(x || n == 0, MMS_E_INVALID, "null pointer");
+  if (n <= 0) return 0;
+  { MmsKernelScope ks_(ctx, "scale_kernel");
+    scale_kernel<T><<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(x, n, alpha); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+#define INST(T)                                                                                        \
+  template int mms_pairrankloss_forward_impl<T>(mms_context*, const T*, const T*, const T*, T, long long, T*, T*, T*); \
+  template int mms_pairrankloss_backward_impl<T>(mms_context*, const T*, const T*, const T*, T, long long, T*, T*);    \
+  template int mms_fm_forward_impl<T>(mms_context*, const T*, const T*, T*, int, int, int);            \
+  template int mms_fm_backward_impl<T>(mms_context*, const T*, const T*, T*, T*, int, int, int, int);  \
+  template int mms_dot_impl<T>(mms_context*, const T*, const T*, long long, T*);                       \
+  template int mms_scale_impl<T>(mms_context*, T*, long long, T);
+INST(float)
+INST(double)

@@ -1,0 +1,161 @@
+// Embed layer on sm_100a: index -> row gather (+bias) and gradient scatter-add.
+// HBM-bound byte work; no tensor cores.  Reference: src/caffe/layers/embed_layer.cu.
+//
+// Forward  : one warp per token row; the float-encoded id is read once per row
+//            (the reference re-reads it once per output float, embed_layer.cu:15-19),
+//            the table row moves as 16-byte vectors when D and the pointers allow,
+//            bias is fused (the reference runs a K=1 cuBLAS gemm, :51-55).
+// Backward : each CTA owns a contiguous tile of token rows; a thread walks its column
+//            down the tile and merges RUNS of equal ids before issuing one atomic per
+//            run (centre-padded sentences put long runs of the pad id back to back),
+//            which removes most of the same-address contention the reference's
+//            one-atomic-per-float kernel has on the pad row (embed_layer.cu:29-39).
+//            The bias gradient (a column sum) rides along in the same pass.
+#include "mms_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+template <typename T, int VEC>
+struct Vec;
+template <> struct Vec<float, 4> { typedef float4 type; };
+template <> struct Vec<double, 2> { typedef double2 type; };
+
+__device__ __forceinline__ float4 vadd(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ double2 vadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vzero(double2& a) { a = make_double2(0., 0.); }
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+embed_forward_vec(const T* __restrict__ idx, const T* __restrict__ W, const T* __restrict__ bias,
+                  T* __restrict__ top, long long M, int D, int V, int* fault) {
+  typedef typename Vec<T, VEC>::type VT;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+  const int nvec = D / VEC;
+  for (long long row = warp; row < M; row += nwarps) {
+    const int index = static_cast<int>(idx[row]);
+    const bool ok = index >= 0 && index < V;
+    if (!ok && lane == 0) atomicExch(fault, 1);
+    const VT* src = reinterpret_cast<const VT*>(W + (size_t)(ok ? index : 0) * D);
+    VT* dst = reinterpret_cast<VT*>(top + (size_t)row * D);
+    for (int c = lane; c < nvec; c += 32) {
+      VT v;
+      if (ok) v = __ldg(src + c); else vzero(v);
+      if (bias) v = vadd(v, __ldg(reinterpret_cast<const VT*>(bias) + c));
+      __stcs(dst + c, v);   // streaming store: the gathered rows are consumed once
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+embed_forward_scalar(const T* __restrict__ idx, const T* __restrict__ W, const T* __restrict__ bias,
+                     T* __restrict__ top, long long M, int D, int V, int* fault) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+  for (long long row = warp; row < M; row += nwarps) {
+    const int index = static_cast<int>(idx[row]);
+    const bool ok = index >= 0 && index < V;
+    if (!ok && lane == 0) atomicExch(fault, 1);
+    const T* src = W + (size_t)(ok ? index : 0) * D;
+    T* dst = top + (size_t)row * D;
+    for (int c = lane; c < D; c += 32) {
+      T v = ok ? __ldg(src + c) : T(0);
+      if (bias) v += __ldg(bias + c);
+      dst[c] = v;
+    }
+  }
+}
+
+constexpr int kBwdRows = 64;      // token rows per CTA
+constexpr int kBwdThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kBwdThreads)
+embed_backward_runs(const T* __restrict__ idx, const T* __restrict__ dtop, T* __restrict__ dW,
+                    T* __restrict__ dbias, long long M, int D, int V, int* fault) {
+  __shared__ int s_idx[kBwdRows];
+  const long long row0 = (long long)blockIdx.x * kBwdRows;
+  const int rows = (int)mms_min<long long>(kBwdRows, M - row0);
+  for (int r = threadIdx.x; r < rows; r += kBwdThreads) {
+    const int index = static_cast<int>(idx[row0 + r]);
+    const bool ok = index >= 0 && index < V;
+    if (!ok) atomicExch(fault, 1);
+    s_idx[r] = ok ? index : -1;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += kBwdThreads) {
+    T run = T(0), col = T(0);
+    int cur = -1;
+    for (int r = 0; r < rows; ++r) {
+      const int index = s_idx[r];
+      const T g = __ldg(dtop + (size_t)(row0 + r) * D + c);
+      col += g;
+      if (index != cur) {
+        if (cur >= 0 && dW) atomicAdd(dW + (size_t)cur * D + c, run);
+        cur = index;
+        run = T(0);
+      }
+      run += g;
+    }
+    if (cur >= 0 && dW) atomicAdd(dW + (size_t)cur * D + c, run);
+    if (dbias) atomicAdd(dbias + c, col);
+  }
+}
+
+template <typename T> struct VecWidth;
+template <> struct VecWidth<float> { static constexpr int value = 4; };
+template <> struct VecWidth<double> { static constexpr int value = 2; };
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+template <typename T>
+int mms_embed_forward_impl(mms_context* ctx, const T* idx, const T* W, const T* bias, T* top,
+                           long long M, int D, int V) {
+  MMS_REQUIRE(M >= 0 && D > 0 && V > 0, MMS_E_INVALID, "bad size");
+  if (M == 0) return 0;
+  MMS_REQUIRE(idx && W && top, MMS_E_INVALID, "null pointer");
+  constexpr int VEC = VecWidth<T>::value;
+  const int grid = (int)mms_min<long long>((M + kWarpsPerCta - 1) / kWarpsPerCta, (long long)ctx->sm_count * 16);
+  const bool vec_ok = (D % VEC == 0) && aligned16(W) && aligned16(top) && (!bias || aligned16(bias));
+  if (vec_ok) {
+    { MmsKernelScope ks_(ctx, "embed_forward_vec");
+      embed_forward_vec<T, VEC><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, top, M, D, V,
+                                                                           ctx->fault_flag); }
+  } else {
+    { MmsKernelScope ks_(ctx, "embed_forward_scalar");
+      embed_forward_scalar<T><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, top, M, D, V,
+                                                                         ctx->fault_flag); }
+  }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_embed_backward_impl(mms_context* ctx, const T* idx, const T* dtop, T* dW, T* dbias,
+                            long long M, int D, int V) {
+  MMS_REQUIRE(M >= 0 && D > 0 && V > 0, MMS_E_INVALID, "bad size");
+  if (M == 0 || (!dW && !dbias)) return 0;
+  MMS_REQUIRE(idx && dtop, MMS_E_INVALID, "null pointer");
+  const long long grid = (M + kBwdRows - 1) / kBwdRows;
+  MMS_REQUIRE(grid <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "too many rows");
+  { MmsKernelScope ks_(ctx, "embed_backward_runs");
+    embed_backward_runs<T><<<(unsigned)grid, kBwdThreads, 0, ctx->stream>>>(idx, dtop, dW, dbias, M, D, V,
+                                                                         ctx->fault_flag); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template int mms_embed_forward_impl<float>(mms_context*, const float*, const float*, const float*, float*, long long, int, int);
+template int mms_embed_forward_impl<double>(mms_context*, const double*, const double*, const double*, double*, long long, int, int);
+template int mms_embed_backward_impl<float>(mms_context*, const float*, const float*, float*, float*, long long, int, int);
+template int mms_embed_backward_impl<double>(mms_context*, const double*, const double*, double*, double*, long long, int, int);

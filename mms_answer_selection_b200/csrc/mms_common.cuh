@@ -1,0 +1,146 @@
+// Shared host/device plumbing for libmms_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mms_b200.h"
+
+struct mms_context {
+  cudaStream_t stream = 0;
+  int math = MMS_MATH_TF32;
+  int prl_ge = 0;
+  int embed_deterministic = 0;
+  size_t scratch_cap = (size_t)256 << 20;
+  void* scratch = nullptr;       // grows on demand, reused across calls
+  size_t scratch_bytes = 0;
+  int* fault_flag = nullptr;     // device word set by kernels on data faults
+  int sm_count = 148;
+  int device = 0;
+  void* tc_state = nullptr;      // tensor-core path private state (tensor maps etc.)
+  unsigned long long launches = 0;   // kernels launched through this handle
+  int profile = 0;               // 1: bracket every launch with CUDA events (mms_profile_*)
+  void* prof = nullptr;          // std::vector<ProfRecord>*
+};
+
+// Placed in front of every kernel launch: counts it and, when profiling is on, records a
+// CUDA event on the handle's stream before and after the launch.
+struct MmsKernelScope {
+  mms_context* ctx;
+  int slot;
+  MmsKernelScope(mms_context* c, const char* name);
+  ~MmsKernelScope();
+};
+
+void mms_set_error(const char* fmt, ...);
+
+#define MMS_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      mms_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+#define MMS_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      mms_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+#define MMS_REQUIRE(cond, code, msg)                                                    \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      mms_set_error("%s:%d: %s (%s)", __FILE__, __LINE__, msg, #cond);                  \
+      return (code);                                                                    \
+    }                                                                                   \
+  } while (0)
+
+#define MMS_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+// Returns a scratch buffer of at least `bytes` (owned by the context).
+int mms_scratch(mms_context* ctx, size_t bytes, void** out);
+
+static inline int mms_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+template <typename T> __host__ __device__ inline T mms_min(T a, T b) { return a < b ? a : b; }
+template <typename T> __host__ __device__ inline T mms_max(T a, T b) { return a > b ? a : b; }
+
+// ---- SIMT batched GEMM (gemm_simt.cu): the fp32/fp64 fallback contraction ------------
+// C[z][m][n] = alpha * sum_k A(z,m,k) * B(z,k,n) + beta * C[z][m][n]
+// A(z,m,k) = A[z1*sA1 + z2*sA2 + m*sAm + k*sAk],  z = z1*nb2 + z2  (likewise B, C).
+// ksplit > 1 splits K across CTAs and combines with atomicAdd (beta must be 1 then).
+template <typename T>
+struct SimtGemmArgs {
+  const T* A; const T* B; T* C;
+  int M, N, K;
+  long long sAm, sAk, sBk, sBn;
+  int ldc;
+  long long sA1, sA2, sB1, sB2, sC1, sC2;
+  int nb1, nb2;
+  T alpha, beta;
+  int ksplit;
+};
+template <typename T>
+int mms_simt_gemm(mms_context* ctx, const SimtGemmArgs<T>& args);
+
+template <typename T>
+int mms_fill(mms_context* ctx, T* p, long long n, T v);
+
+// ---- layer implementations (templated on the blob dtype) ------------------------------
+template <typename T>
+int mms_embed_forward_impl(mms_context*, const T* idx, const T* W, const T* bias, T* top,
+                           long long M, int D, int V);
+template <typename T>
+int mms_embed_backward_impl(mms_context*, const T* idx, const T* dtop, T* dW, T* dbias,
+                            long long M, int D, int V);
+template <typename T>
+int mms_simcross_forward_impl(mms_context*, int mode, const T* q, const T* a, const T* Mw,
+                              const T* B, T* S, T* norm0, T* norm1, int N, int Lq, int La, int D,
+                              int mc);
+template <typename T>
+int mms_simcross_backward_impl(mms_context*, int mode, const T* q, const T* a, const T* Mw,
+                               const T* S, const T* dS, const T* norm0, const T* norm1, T* dq,
+                               T* da, T* dM, T* dB, int N, int Lq, int La, int D, int mc,
+                               int prop0, int prop1);
+template <typename T>
+int mms_simmatrix_forward_impl(mms_context*, const T* q, const T* a, const T* W, T* s, T* Tm,
+                               int N, int K1, int K2);
+template <typename T>
+int mms_simmatrix_backward_impl(mms_context*, const T* q, const T* a, const T* W, const T* ds,
+                                T* dW, T* dq, T* da, int N, int K1, int K2, int prop_w,
+                                int prop0, int prop1);
+template <typename T>
+int mms_pairrankloss_forward_impl(mms_context*, const T* a, const T* b, const T* y, T margin,
+                                  long long count, T* loss, T* ordered, T* similar);
+template <typename T>
+int mms_pairrankloss_backward_impl(mms_context*, const T* y, const T* ordered, const T* similar,
+                                   T top_diff, long long count, T* da, T* db);
+template <typename T>
+int mms_fm_forward_impl(mms_context*, const T* x, const T* bias, T* y, int N, int C, int Dm);
+template <typename T>
+int mms_fm_backward_impl(mms_context*, const T* x, const T* dy, T* dx, T* dbias, int N, int C,
+                         int Dm, int prop0);
+template <typename T>
+int mms_dot_impl(mms_context*, const T* x, const T* y, long long n, T* out);
+template <typename T>
+int mms_scale_impl(mms_context*, T* x, long long n, T alpha);
+
+int mms_rerank_scores_impl(mms_context*, const float* Q, const float* C, const float* W, float* QW,
+                           float* scores, int Nq, long long Nc, int K1, int K2);
+
+// ---- tensor-core (tcgen05, TF32) path, float only (tc/*.cu) ---------------------------
+// Each returns MMS_E_UNSUPPORTED when the shape is outside what the tcgen05 kernels
+// handle; the caller then uses the SIMT path (still on the GPU).
+int mms_tc_simcross2_forward(mms_context*, const float* q, const float* a, const float* Mw,
+                             const float* B, float* S, int N, int Lq, int La, int D, int mc);
+int mms_tc_simcross2_backward(mms_context*, const float* q, const float* a, const float* Mw,
+                              const float* dS, float* dq, float* da, float* dM, float* dB, int N,
+                              int Lq, int La, int D, int mc);

@@ -1,0 +1,133 @@
+// SimMatrix layer (reference: src/caffe/layers/sim_matrix_layer.{cpp,cu}) and the
+// candidate-scoring (reranking) entry point built on the same bilinear form.
+//   forward : T = q W  (kept, as the reference keeps it in bottom[1].diff), s_n = <a_n, T_n>
+//   backward: dW += q^T diag(ds) a ;  dq = diag(ds) a W^T ;  da = diag(ds) q W
+// The reference's backward is N cblas_sger / cblas_sgemv calls on the host
+// (sim_matrix_layer.cpp:73-93); here each gradient is one GEMM over the whole batch.
+#include "mms_common.cuh"
+
+namespace {
+
+// s[n] = sum_c a[n,c] * T[n,c]  -- one warp per row, shuffle reduction
+template <typename T>
+__global__ void rowdot_kernel(const T* __restrict__ a, const T* __restrict__ Tm, T* __restrict__ s,
+                              int N, int K2) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = warp; n < N; n += nwarps) {
+    T acc = T(0);
+    for (int c = lane; c < K2; c += 32) acc += a[(size_t)n * K2 + c] * Tm[(size_t)n * K2 + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s[n] = acc;
+  }
+}
+
+// out[n,c] = ds[n] * in[n,c]
+template <typename T>
+__global__ void rowscale_kernel(const T* __restrict__ in, const T* __restrict__ ds, T* __restrict__ out,
+                                long long total, int K) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x)
+    out[e] = ds[e / K] * in[e];
+}
+
+template <typename T>
+int gemm2d(mms_context* ctx, const T* A, long long sAm, long long sAk, const T* B, long long sBk,
+           long long sBn, T* C, int ldc, int M, int N, int K, T beta, int ksplit = 1) {
+  SimtGemmArgs<T> g;
+  g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K;
+  g.sAm = sAm; g.sAk = sAk; g.sBk = sBk; g.sBn = sBn; g.ldc = ldc;
+  g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0;
+  g.nb1 = g.nb2 = 1; g.alpha = T(1); g.beta = beta; g.ksplit = ksplit;
+  // grid.y limit: tile rows of 64
+  if (mms_ceil_div(M, 64) > 65535) {
+    // split the M range
+    const int step = 65535 * 64;
+    for (int m0 = 0; m0 < M; m0 += step) {
+      SimtGemmArgs<T> h = g;
+      h.A = A + (long long)m0 * sAm; h.C = C + (long long)m0 * ldc; h.M = min(step, M - m0);
+      MMS_TRY(mms_simt_gemm<T>(ctx, h));
+    }
+    return 0;
+  }
+  return mms_simt_gemm<T>(ctx, g);
+}
+
+inline int ew_grid(mms_context* ctx, long long n) {
+  return (int)mms_min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+}
+
+}  // namespace
+
+template <typename T>
+int mms_simmatrix_forward_impl(mms_context* ctx, const T* q, const T* a, const T* W, T* s, T* Tm,
+                               int N, int K1, int K2) {
+  MMS_REQUIRE(q && a && W && s && Tm, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
+  if (N == 0) return 0;
+  // T = q W   (gemm NoTrans,NoTrans M_ x K2 x K1, sim_matrix_layer.cpp:60-61)
+  MMS_TRY(gemm2d<T>(ctx, q, K1, 1, W, K2, 1, Tm, K2, N, K2, K1, T(0)));
+  { MmsKernelScope ks_(ctx, "rowdot_kernel");
+    rowdot_kernel<T><<<ew_grid(ctx, (long long)N * 32), 256, 0, ctx->stream>>>(a, Tm, s, N, K2); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_simmatrix_backward_impl(mms_context* ctx, const T* q, const T* a, const T* W, const T* ds,
+                                T* dW, T* dq, T* da, int N, int K1, int K2, int prop_w, int prop0,
+                                int prop1) {
+  MMS_REQUIRE(q && a && W && ds, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
+  if (N == 0) return 0;
+  const bool need_as = (prop_w && dW) || (prop0 && dq);
+  const bool need_qs = (prop1 && da);
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(T) * ((size_t)N * K2 * need_as + (size_t)N * K1 * need_qs), &sp));
+  T* As = static_cast<T*>(sp);
+  T* Qs = As + (size_t)N * K2 * need_as;
+  if (need_as) {
+    { MmsKernelScope ks_(ctx, "rowscale_kernel");
+      rowscale_kernel<T><<<ew_grid(ctx, (long long)N * K2), 256, 0, ctx->stream>>>(a, ds, As, (long long)N * K2, K2); }
+    MMS_LAUNCH_CHECK();
+  }
+  if (need_qs) {
+    { MmsKernelScope ks_(ctx, "rowscale_kernel");
+      rowscale_kernel<T><<<ew_grid(ctx, (long long)N * K1), 256, 0, ctx->stream>>>(q, ds, Qs, (long long)N * K1, K1); }
+    MMS_LAUNCH_CHECK();
+  }
+  if (prop_w && dW) {
+    // dW += q^T (ds o a)      (sum of the reference's N rank-1 updates, :75-79)
+    const int tiles = mms_ceil_div(K1, 64) * mms_ceil_div(K2, 64);
+    const int ksplit = max(1, min(mms_ceil_div(2 * ctx->sm_count, tiles), mms_ceil_div(N, 256)));
+    MMS_TRY(gemm2d<T>(ctx, q, 1, K1, As, K2, 1, dW, K2, K1, K2, N, T(1), ksplit));
+  }
+  if (prop0 && dq)   // dq = (ds o a) W^T     (gemv NoTrans per sample, :88-90)
+    MMS_TRY(gemm2d<T>(ctx, As, K2, 1, W, 1, K2, dq, K1, N, K1, K2, T(0)));
+  if (prop1 && da)   // da = (ds o q) W       (gemv Trans per sample)
+    MMS_TRY(gemm2d<T>(ctx, Qs, K1, 1, W, K2, 1, da, K2, N, K2, K1, T(0)));
+  return 0;
+}
+
+// scores = (Q W) C^T : the SimMatrix bilinear form for every (query, candidate) pair.
+int mms_rerank_scores_impl(mms_context* ctx, const float* Q, const float* C, const float* W, float* QW,
+                           float* scores, int Nq, long long Nc, int K1, int K2) {
+  MMS_REQUIRE(Q && C && W && QW && scores, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(Nq > 0 && Nc > 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
+  MMS_REQUIRE(Nc <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "candidate count exceeds int range");
+  MMS_TRY(gemm2d<float>(ctx, Q, K1, 1, W, K2, 1, QW, K2, Nq, K2, K1, 0.f));
+  // scores[i][j] = sum_c QW[i][c] * C[j][c]; scores row stride = Nc
+  SimtGemmArgs<float> g;
+  g.A = QW; g.B = C; g.C = scores; g.M = Nq; g.N = (int)Nc; g.K = K2;
+  g.sAm = K2; g.sAk = 1; g.sBk = 1; g.sBn = K2; g.ldc = (int)Nc;
+  g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0;
+  g.nb1 = g.nb2 = 1; g.alpha = 1.f; g.beta = 0.f; g.ksplit = 1;
+  return mms_simt_gemm<float>(ctx, g);
+}
+
+template int mms_simmatrix_forward_impl<float>(mms_context*, const float*, const float*, const float*, float*, float*, int, int, int);
+template int mms_simmatrix_forward_impl<double>(mms_context*, const double*, const double*, const double*, double*, double*, int, int, int);
+template int mms_simmatrix_backward_impl<float>(mms_context*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int);
+template int mms_simmatrix_backward_impl<double>(mms_context*, const double*, const double*, const double*, const double*, double*, double*, double*, int, int, int, int, int, int);

@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference's Caffe layers for the MMS hot path.
+
+Same names, argument meaning and error behaviour as the reference classes
+(paths relative to the reference tree):
+
+  EmbedLayer         src/caffe/layers/embed_layer.{cpp,cu}
+  SimCrossLayer      src/caffe/layers/sim_cross_layer.{cpp,cu}
+  SimMatrixLayer     src/caffe/layers/sim_matrix_layer.{cpp,cu}
+  PairRankLossLayer  src/caffe/layers/pair_rank_loss_layer.{cpp,cu}
+  FMLayer            src/caffe/layers/fm_layer.{cpp,cu}
+
+driven through the Layer API of include/caffe/layer.hpp: ``SetUp`` (= CheckBlobCounts,
+LayerSetUp, Reshape, SetLossWeights, :67-77), ``Forward`` (= Reshape, Forward_gpu, loss
+reduction, :451-487), ``Backward`` (:490-500).  Forward_gpu / Backward_gpu only marshal raw
+device pointers and sizes into the C-ABI of libmms_b200.so -- exactly what the C++ drop-in
+classes in caffe_layers/ do.  There is no Forward_cpu: Caffe::mode() is always GPU here.
+
+A failed CHECK aborts the process in the reference (glog LOG(FATAL)); here it raises
+``CheckError`` carrying the reference's message.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Handle, c_p, check, lib
+from .blob import Blob
+
+
+class CheckError(RuntimeError):
+    """A Caffe CHECK / LOG(FATAL) of the reference layer would have fired."""
+
+
+def _check(cond, msg):
+    if not cond:
+        raise CheckError("Check failed: " + msg)
+
+
+# ------------------------------------------------------------------------- parameters
+class FillerParameter(dict):
+    """caffe.proto:41-62.  Default: type 'constant', value 0."""
+
+    def __init__(self, **kw):
+        dict.__init__(self, type="constant", value=0.0, min=0.0, max=1.0, mean=0.0, std=1.0)
+        self.update(kw)
+
+
+_DEFAULTS = {
+    # caffe.proto:471-477 (the reference's spelling: mesure_count)
+    "sim_cross_param": dict(dist_mode=1, mesure_count=1, weight_filler=None, bias_term=True, bias_filler=None),
+    "sim_matrix_param": dict(weight_filler=None),                       # caffe.proto:430-432
+    "pair_rank_loss_param": dict(margin=1.0),                           # caffe.proto:479-481
+    "fm_param": dict(bias_term=True),                                   # caffe.proto:418-420
+    "embed_param": dict(num_output=0, input_dim=0, bias_term=True, weight_filler=None,   # :790-803
+                        bias_filler=None, weight_source=""),
+}
+
+
+class LayerParameter(object):
+    """The subset of caffe.proto's LayerParameter (:310-416) the MMS layers read."""
+
+    def __init__(self, type, name="", phase="TRAIN", loss_weight=(), dtype=np.float32, **params):
+        self.type = type
+        self.name = name or type
+        self.phase = phase
+        self.loss_weight = list(loss_weight)
+        self.dtype = np.dtype(dtype)
+        for key, dflt in _DEFAULTS.items():
+            vals = dict(dflt)
+            given = params.pop(key, {})
+            unknown = set(given) - set(vals)
+            if unknown:
+                raise KeyError("unknown field(s) %s in %s" % (sorted(unknown), key))
+            vals.update(given)
+            for f in ("weight_filler", "bias_filler"):
+                if f in vals:
+                    vals[f] = FillerParameter(**(vals[f] or {}))
+            setattr(self, key, vals)
+        if params:
+            raise KeyError("unknown LayerParameter field(s): %s" % sorted(params))
+
+
+def _fill(blob, filler, rng):
+    """include/caffe/filler.hpp: constant / uniform / gaussian / xavier (fan_in)."""
+    shape, t = blob.shape, filler["type"]
+    if t == "constant":
+        arr = np.full(shape, filler["value"], dtype=blob.dtype)
+    elif t == "uniform":
+        arr = rng.uniform(filler["min"], filler["max"], size=shape).astype(blob.dtype)
+    elif t == "gaussian":
+        arr = rng.normal(filler["mean"], filler["std"], size=shape).astype(blob.dtype)
+    elif t == "xavier":
+        fan_in = blob.count() // max(shape[0], 1)
+        scale = np.sqrt(3.0 / fan_in)
+        arr = rng.uniform(-scale, scale, size=shape).astype(blob.dtype)
+    else:
+        raise CheckError("Unknown filler name: %s" % t)
+    blob.set_cpu_data(arr)
+
+
+# ------------------------------------------------------------------------- base class
+class Layer(object):
+    exact_num_bottom = None
+    exact_num_top = 1
+
+    def __init__(self, param):
+        self.layer_param_ = param
+        self.blobs_ = []
+        self.param_propagate_down_ = []
+        self.loss_ = []
+        self.dtype = param.dtype
+        self.sfx = "_f32" if self.dtype == np.float32 else "_f64"
+        self.real = ctypes.c_float if self.dtype == np.float32 else ctypes.c_double
+        self.handle = Handle()          # raises without a B200 / without the built library
+        self.rng = np.random.default_rng(1701)
+
+    # -- Caffe public API -------------------------------------------------------
+    def type(self):
+        return self.layer_param_.type
+
+    @property
+    def blobs(self):
+        return self.blobs_
+
+    def SetUp(self, bottom, top):
+        self.CheckBlobCounts(bottom, top)
+        self.LayerSetUp(bottom, top)
+        self.Reshape(bottom, top)
+        self.SetLossWeights(top)
+
+    def CheckBlobCounts(self, bottom, top):
+        if self.exact_num_bottom is not None:
+            _check(len(bottom) == self.exact_num_bottom, "%s Layer takes %d bottom blob(s) as input."
+                   % (self.type(), self.exact_num_bottom))
+        if self.exact_num_top is not None:
+            _check(len(top) == self.exact_num_top, "%s Layer produces %d top blob(s) as output."
+                   % (self.type(), self.exact_num_top))
+
+    def SetLossWeights(self, top):
+        lw = self.layer_param_.loss_weight
+        self.loss_ = [0.0] * len(top)
+        if lw:
+            _check(len(lw) == len(top), "loss_weight must be unspecified or specified once per top blob.")
+            for i, w in enumerate(lw):
+                if w == 0:
+                    continue
+                self.loss_[i] = float(w)
+                top[i].diff.fill_(float(w))          # layer.hpp:414-428
+
+    def Forward(self, bottom, top):
+        self.Reshape(bottom, top)                    # layer.hpp:456
+        self._bind_stream()
+        self.Forward_gpu(bottom, top)
+        loss = 0.0
+        for i, t in enumerate(top):                  # layer.hpp:471-479
+            if i < len(self.loss_) and self.loss_[i]:
+                out = torch.empty(1, dtype=t.data.dtype, device=t.data.device)
+                self._call("mms_dot", c_p(t.gpu_data()), c_p(t.gpu_diff()), t.count(), c_p(out.data_ptr()))
+                loss += float(out.item())
+        return loss
+
+    def Backward(self, top, propagate_down, bottom):
+        self._bind_stream()
+        self.Backward_gpu(top, list(propagate_down), bottom)
+
+    # -- helpers ----------------------------------------------------------------
+    def _bind_stream(self):
+        self.handle.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def _call(self, name, *args):
+        check(getattr(lib(), name + self.sfx)(self.handle.ptr, *args))
+
+    def _new_blob(self, shape, like):
+        return Blob(shape, dtype=self.dtype, device=like.device)
+
+    def set_math(self, mode):
+        self.handle.set_option(_lib.MMS_OPT_MATH, mode)
+
+
+def _p(blob_or_none, diff=False):
+    if blob_or_none is None:
+        return c_p(0)
+    return c_p(blob_or_none.gpu_diff() if diff else blob_or_none.gpu_data())
+
+
+# ------------------------------------------------------------------------- Embed
+class EmbedLayer(Layer):
+    exact_num_bottom = 1
+
+    def LayerSetUp(self, bottom, top):
+        ep = self.layer_param_.embed_param
+        self.N_ = int(ep["num_output"])
+        _check(self.N_ > 0, "EmbedLayer num_output must be positive.")
+        self.K_ = int(ep["input_dim"])
+        _check(self.K_ > 0, "EmbedLayer input_dim must be positive.")
+        self.bias_term_ = bool(ep["bias_term"])
+        if not self.blobs_:                                   # embed_layer.cpp:18-44
+            self.blobs_.append(self._new_blob((self.K_, self.N_), bottom[0]))
+            _fill(self.blobs_[0], ep["weight_filler"], self.rng)
+            if self.bias_term_:
+                self.blobs_.append(self._new_blob((self.N_,), bottom[0]))
+                _fill(self.blobs_[1], ep["bias_filler"], self.rng)
+            if ep["weight_source"]:
+                from .formats import load_weight_source      # embed_layer.cpp:46-113
+                load_weight_source(ep["weight_source"], self.blobs_[0])
+        self.param_propagate_down_ = [True] * len(self.blobs_)
+
+    def Reshape(self, bottom, top):
+        self.M_ = bottom[0].count()
+        top[0].Reshape(tuple(bottom[0].shape) + (self.N_,))   # embed_layer.cpp:121-125
+
+    def Forward_gpu(self, bottom, top):
+        bias = self.blobs_[1] if self.bias_term_ else None
+        self._call("mms_embed_forward", _p(bottom[0]), _p(self.blobs_[0]), _p(bias), _p(top[0]),
+                   self.M_, self.N_, self.K_)
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        _check(not propagate_down[0], "!propagate_down[0] Can't backpropagate to EmbedLayer input.")
+        dW = self.blobs_[0] if self.param_propagate_down_[0] else None
+        db = self.blobs_[1] if (self.bias_term_ and self.param_propagate_down_[1]) else None
+        self._call("mms_embed_backward", _p(bottom[0]), _p(top[0], True), _p(dW, True), _p(db, True),
+                   self.M_, self.N_, self.K_)
+
+
+# ------------------------------------------------------------------------- SimCross
+class SimCrossLayer(Layer):
+    exact_num_bottom = 2
+
+    def LayerSetUp(self, bottom, top):
+        _check(len(bottom) == 2, "bottom.size() == 2")
+        _check(bottom[0].num() == bottom[1].num(), "bottom[0]->num() == bottom[1]->num()")
+        _check(bottom[0].height() == bottom[1].height(), "bottom[0]->height() == bottom[1]->height()")
+        sp = self.layer_param_.sim_cross_param
+        self.dist_mode_ = int(sp["dist_mode"])
+        self.bias_term_ = bool(sp["bias_term"])
+        self.mc_ = int(sp["mesure_count"])
+        if self.dist_mode_ == 2:                              # sim_cross_layer.cpp:17-46
+            D = bottom[0].height()
+            self.blobs_ = [self._new_blob((self.mc_, D, bottom[1].height()), bottom[0])]
+            _fill(self.blobs_[0], sp["weight_filler"], self.rng)
+            if self.bias_term_:
+                self.blobs_.append(self._new_blob((self.mc_, bottom[0].channels(), bottom[1].channels()), bottom[0]))
+                _fill(self.blobs_[1], sp["bias_filler"], self.rng)
+        self.data0_norm_ = self._new_blob((), bottom[0])
+        self.data1_norm_ = self._new_blob((), bottom[0])
+
+    def Reshape(self, bottom, top):
+        N, Lq, La = bottom[0].num(), bottom[0].channels(), bottom[1].channels()
+        top[0].Reshape((N, self.mc_ if self.dist_mode_ == 2 else 1, Lq, La))   # :52-62
+        if self.dist_mode_ == 0:
+            self.data0_norm_.Reshape((N, Lq))
+            self.data1_norm_.Reshape((N, La))
+
+    def _dims(self, bottom):
+        return (bottom[0].num(), bottom[0].channels(), bottom[1].channels(), bottom[0].height(),
+                self.mc_ if self.dist_mode_ == 2 else 1)
+
+    def Forward_gpu(self, bottom, top):
+        N, Lq, La, D, mc = self._dims(bottom)
+        Mw = self.blobs_[0] if self.dist_mode_ == 2 else None
+        B = self.blobs_[1] if (self.dist_mode_ == 2 and self.bias_term_) else None
+        n0 = self.data0_norm_ if self.dist_mode_ == 0 else None
+        n1 = self.data1_norm_ if self.dist_mode_ == 0 else None
+        self._call("mms_simcross_forward", self.dist_mode_, _p(bottom[0]), _p(bottom[1]), _p(Mw), _p(B),
+                   _p(top[0]), _p(n0), _p(n1), N, Lq, La, D, mc)
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        N, Lq, La, D, mc = self._dims(bottom)
+        Mw = self.blobs_[0] if self.dist_mode_ == 2 else None
+        B = self.blobs_[1] if (self.dist_mode_ == 2 and self.bias_term_) else None
+        n0 = self.data0_norm_ if self.dist_mode_ == 0 else None
+        n1 = self.data1_norm_ if self.dist_mode_ == 0 else None
+        self._call("mms_simcross_backward", self.dist_mode_, _p(bottom[0]), _p(bottom[1]), _p(Mw),
+                   _p(top[0]), _p(top[0], True), _p(n0), _p(n1), _p(bottom[0], True), _p(bottom[1], True),
+                   _p(Mw, True), _p(B, True), N, Lq, La, D, mc, int(propagate_down[0]), int(propagate_down[1]))
+
+
+# ------------------------------------------------------------------------- SimMatrix
+class SimMatrixLayer(Layer):
+    exact_num_bottom = 2
+
+    def LayerSetUp(self, bottom, top):
+        _check(bottom[0].num() == bottom[1].num(), "bottom[0]->num() == bottom[1]->num()")
+        self.K1_ = bottom[0].count(1)
+        self.K2_ = bottom[1].count(1)
+        if not self.blobs_:                                    # sim_matrix_layer.cpp:17-32
+            self.blobs_.append(self._new_blob((self.K1_, self.K2_), bottom[0]))
+            _fill(self.blobs_[0], self.layer_param_.sim_matrix_param["weight_filler"], self.rng)
+        self.param_propagate_down_ = [True] * len(self.blobs_)
+
+    def Reshape(self, bottom, top):
+        _check(self.K1_ == bottom[0].count(1), "Input size incompatible with inner product parameters.")
+        _check(self.K2_ == bottom[1].count(1), "Input size incompatible with inner product parameters.")
+        self.M_ = bottom[0].count(0, 1)
+        top[0].Reshape((bottom[0].shape[0], 1))                # :46-49
+
+    def Forward_gpu(self, bottom, top):
+        # T = q W lands in bottom[1]'s diff buffer, as in the reference (:58)
+        self._call("mms_simmatrix_forward", _p(bottom[0]), _p(bottom[1]), _p(self.blobs_[0]), _p(top[0]),
+                   _p(bottom[1], True), self.M_, self.K1_, self.K2_)
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        self._call("mms_simmatrix_backward", _p(bottom[0]), _p(bottom[1]), _p(self.blobs_[0]),
+                   _p(top[0], True), _p(self.blobs_[0], True), _p(bottom[0], True), _p(bottom[1], True),
+                   self.M_, self.K1_, self.K2_, int(self.param_propagate_down_[0]),
+                   int(propagate_down[0]), int(propagate_down[1]))
+
+
+# ------------------------------------------------------------------------- PairRankLoss
+class PairRankLossLayer(Layer):
+    exact_num_bottom = 3
+
+    def LayerSetUp(self, bottom, top):
+        if not self.layer_param_.loss_weight:                  # LossLayer::LayerSetUp, loss_layer.cpp
+            self.layer_param_.loss_weight = [1.0]
+        _check(bottom[0].num() == bottom[1].num(), "bottom[0]->num() == bottom[1]->num()")
+        _check(bottom[0].num() == bottom[2].num(), "bottom[0]->num() == bottom[2]->num()")
+        _check(bottom[0].count(1) == bottom[2].count(1), "bottom[0]->count(1) == bottom[2]->count(1)")
+        _check(bottom[0].count(1) == bottom[1].count(1), "bottom[0]->count(1) == bottom[1]->count(1)")
+        self.margin_ = float(self.layer_param_.pair_rank_loss_param["margin"])
+        shp = (bottom[0].num(), bottom[0].channels(), 1, 1)    # pair_rank_loss_layer.cpp:21-22
+        self.ordered_diff_ = self._new_blob(shp, bottom[0])
+        self.similar_diff_ = self._new_blob(shp, bottom[0])
+
+    def Reshape(self, bottom, top):
+        _check(bottom[0].num() == bottom[1].num(), "The data and label should have the same number.")
+        top[0].Reshape((1,))                                   # LossLayer::Reshape: scalar top
+
+    def Forward_gpu(self, bottom, top):
+        self._call("mms_pairrankloss_forward", _p(bottom[0]), _p(bottom[1]), _p(bottom[2]),
+                   self.real(self.margin_), bottom[0].count(), _p(top[0]), _p(self.ordered_diff_),
+                   _p(self.similar_diff_))
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        if propagate_down[2]:
+            raise CheckError(self.type() + " Layer cannot backpropagate to label inputs.")
+        top_diff = float(top[0].diff.reshape(-1)[0].item())    # top[0]->cpu_diff()[0]
+        self._call("mms_pairrankloss_backward", _p(bottom[2]), _p(self.ordered_diff_), _p(self.similar_diff_),
+                   self.real(top_diff), bottom[0].count(),
+                   _p(bottom[0] if propagate_down[0] else None, True),
+                   _p(bottom[1] if propagate_down[1] else None, True))
+
+
+# ------------------------------------------------------------------------- FM
+class FMLayer(Layer):
+    exact_num_bottom = 1
+
+    def LayerSetUp(self, bottom, top):
+        self.bias_term_ = bool(self.layer_param_.fm_param["bias_term"])
+        if self.bias_term_:                                    # fm_layer.cpp:13-19
+            self.blobs_ = [self._new_blob((1,), bottom[0])]
+        self.param_propagate_down_ = [True] * len(self.blobs_)
+
+    def Reshape(self, bottom, top):
+        top[0].Reshape((bottom[0].num(), 1))
+
+    def Forward_gpu(self, bottom, top):
+        b = self.blobs_[0] if self.bias_term_ else None
+        self._call("mms_fm_forward", _p(bottom[0]), _p(b), _p(top[0]), bottom[0].num(),
+                   bottom[0].channels(), bottom[0].height())
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        db = self.blobs_[0] if (self.bias_term_ and self.param_propagate_down_[0]) else None
+        self._call("mms_fm_backward", _p(bottom[0]), _p(top[0], True), _p(bottom[0], True), _p(db, True),
+                   bottom[0].num(), bottom[0].channels(), bottom[0].height(), int(propagate_down[0]))
+
+
+_REGISTRY = {"Embed": EmbedLayer, "SimCross": SimCrossLayer, "SimMatrix": SimMatrixLayer,
+             "PairRankLoss": PairRankLossLayer, "FM": FMLayer}
+
+
+def create_layer(param):
+    """LayerRegistry::CreateLayer (include/caffe/layer_factory.hpp:73-81)."""
+    if param.type not in _REGISTRY:
+        raise CheckError("Unknown layer type: %s (known types: %s)" % (param.type, ", ".join(sorted(_REGISTRY))))
+    return _REGISTRY[param.type](param)

@@ -1,0 +1,102 @@
+"""MMSNet: the slice of the reference's TREC-QA net that is the hot path
+(examples/trec_qa_w2v_mms/do_trec_qa_clean.py:452-468, ``network_v4``):
+
+    question ids (N,L) -> Embed --\
+                                   +--> SimCross(dist_mode=2, mesure_count=mc) -> S (N,mc,L,L)
+    answer   ids (N,L) -> Embed --/
+      (the two Embed layers share ``w2v-weights`` / ``w2v-bias`` by param name, :461-466)
+
+executed layer by layer the way caffe::Net does (net.cpp:535-591: ForwardFromTo /
+BackwardFromTo, ClearParamDiffs :923-941, ShareWeights :944-950).  The CNN that
+consumes S in the reference is out of scope, so S is treated as a loss top whose
+per-element loss weights (top.diff) stand for the upstream gradient: loss = <S, dS>
+(include/caffe/layer.hpp:471-479), which makes the step's scalar result well defined.
+"""
+import numpy as np
+import torch
+
+from .blob import Blob
+from .layers import EmbedLayer, LayerParameter, SimCrossLayer
+
+
+class MMSNet(object):
+    def __init__(self, N, L=40, D=300, mc=4, V=60002, dtype=np.float32, device="cuda", bias_term=True,
+                 embed_bias=True, math=None):
+        self.N, self.L, self.D, self.mc, self.V = N, L, D, mc, V
+        self.dtype = np.dtype(dtype)
+        self.device = torch.device(device)
+        mk = lambda shape: Blob(shape, dtype=dtype, device=device)
+        self.idx_q, self.idx_a = mk((N, L)), mk((N, L))
+        self.q, self.a = mk(()), mk(())
+        self.S = mk(())
+        ep = dict(num_output=D, input_dim=V, bias_term=embed_bias,
+                  weight_filler=dict(type="uniform", min=-0.08, max=0.08))
+        self.embed_q = EmbedLayer(LayerParameter("Embed", name="embed_q", dtype=dtype, embed_param=ep))
+        self.embed_a = EmbedLayer(LayerParameter("Embed", name="embed_a", dtype=dtype, embed_param=ep))
+        self.sim = SimCrossLayer(LayerParameter(
+            "SimCross", name="sim_cross", dtype=dtype, loss_weight=[1.0],
+            sim_cross_param=dict(dist_mode=2, mesure_count=mc, bias_term=bias_term,
+                                 weight_filler=dict(type="uniform", min=-0.1, max=0.1))))
+        self.embed_q.SetUp([self.idx_q], [self.q])
+        self.embed_a.SetUp([self.idx_a], [self.a])
+        # param sharing by name: embed_a uses embed_q's blobs (data and diff)
+        for j, b in enumerate(self.embed_q.blobs):
+            self.embed_a.blobs[j].ShareData(b)
+            self.embed_a.blobs[j].ShareDiff(b)
+        self.sim.SetUp([self.q, self.a], [self.S])
+        if math is not None:
+            self.sim.set_math(math)
+        self._pinned = None
+
+    # learnable params in net order, shared blobs once (net.cpp:440-530)
+    def params(self):
+        return list(self.embed_q.blobs) + list(self.sim.blobs)
+
+    def set_params(self, W=None, b=None, M=None, B=None):
+        if W is not None:
+            self.embed_q.blobs[0].set_cpu_data(W)
+        if b is not None and len(self.embed_q.blobs) > 1:
+            self.embed_q.blobs[1].set_cpu_data(b)
+        if M is not None:
+            self.sim.blobs[0].set_cpu_data(M)
+        if B is not None and len(self.sim.blobs) > 1:
+            self.sim.blobs[1].set_cpu_data(B)
+
+    def set_upstream_gradient(self, dS):
+        """top.diff of the loss top = per-element loss weights = dLoss/dS."""
+        self.S.set_cpu_diff(dS)
+
+    def set_inputs(self, idx_q, idx_a):
+        self.idx_q.set_cpu_data(idx_q)
+        self.idx_a.set_cpu_data(idx_a)
+
+    def set_inputs_from_pinned(self, host_q, host_a):
+        """H2D of this step's inputs from pinned host tensors (async on the current stream)."""
+        self.idx_q.data.copy_(host_q, non_blocking=True)
+        self.idx_a.data.copy_(host_a, non_blocking=True)
+
+    def ClearParamDiffs(self):
+        for p in self.params():
+            p.diff.zero_()
+
+    def Forward(self, with_loss=True):
+        self.embed_q.Forward([self.idx_q], [self.q])
+        self.embed_a.Forward([self.idx_a], [self.a])
+        if with_loss:
+            return self.sim.Forward([self.q, self.a], [self.S])
+        saved, self.sim.loss_ = self.sim.loss_, []
+        try:
+            self.sim.Forward([self.q, self.a], [self.S])
+        finally:
+            self.sim.loss_ = saved
+        return 0.0
+
+    def Backward(self):
+        self.sim.Backward([self.S], [True, True], [self.q, self.a])
+        self.embed_q.Backward([self.q], [False], [self.idx_q])
+        self.embed_a.Backward([self.a], [False], [self.idx_a])
+
+    def ForwardBackward(self, with_loss=True):
+        loss = self.Forward(with_loss)
+        self.Backward()
+        return loss

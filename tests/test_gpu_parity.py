@@ -1,0 +1,441 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI via the host-side
+Layer mirror, against (a) the committed golden fixtures produced by the reference's own
+layer code and (b) the C oracle on the same seeded inputs.
+
+Tolerances (scaled error |got-ref| / max(|got|,|ref|,max|ref|), the GradientChecker rule):
+  * Embed, PairRankLoss gradients, FM backward, gather indices: bit-exact;
+  * float64 and float32/MMS_MATH_FP32 contractions: 1e-12 / 2e-5 (summation order only);
+  * float32 TF32 tensor-core contractions (SimCross mode 2, SimMatrix): 1e-3, the
+    tolerance BASELINE.json's north_star states for fp32/TF32 scores and gradients.
+"""
+import numpy as np
+import pytest
+
+from conftest import scaled_err
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import mms_answer_selection_b200 as mms                      # noqa: E402
+from mms_answer_selection_b200 import _lib, synth             # noqa: E402
+from mms_answer_selection_b200.layers import CheckError       # noqa: E402
+from oracle import cport                                      # noqa: E402
+
+DTYPES = [np.float32, np.float64]
+TAG = {np.float32: "f32", np.float64: "f64"}
+TOL_EXACT = {np.float32: 2e-5, np.float64: 1e-12}
+TOL_TF32 = 1e-3
+
+
+def g(golden, dtype, key):
+    return golden["%s/%s" % (TAG[dtype], key)]
+
+
+def blob(arr, dtype):
+    b = mms.Blob(arr.shape, dtype=dtype)
+    b.set_cpu_data(arr)
+    return b
+
+
+def contraction_tol(dtype, math):
+    if dtype == np.float32 and math == _lib.MMS_MATH_TF32:
+        return TOL_TF32
+    return 10 * TOL_EXACT[dtype]
+
+
+# ------------------------------------------------------------------------------ Embed
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_embed_golden(golden, dtype, bias):
+    k = "embed_b%d" % int(bias)
+    idx = g(golden, dtype, k + "/idx")
+    V, D = g(golden, dtype, k + "/W").shape
+    lay = mms.EmbedLayer(mms.LayerParameter("Embed", dtype=dtype, embed_param=dict(
+        num_output=D, input_dim=V, bias_term=bias)))
+    bottom, top = blob(idx, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bottom], [top])
+    assert [b.shape for b in lay.blobs] == ([(V, D), (D,)] if bias else [(V, D)])
+    lay.blobs[0].set_cpu_data(g(golden, dtype, k + "/W"))
+    if bias:
+        lay.blobs[1].set_cpu_data(g(golden, dtype, k + "/b"))
+    lay.Forward([bottom], [top])
+    assert top.shape == idx.shape + (D,)
+    assert np.array_equal(top.cpu_data(), g(golden, dtype, k + "/top"))          # bit-exact
+    top.set_cpu_diff(g(golden, dtype, k + "/dtop"))
+    lay.blobs[0].set_cpu_diff(g(golden, dtype, k + "/dW0"))                      # accumulates
+    if bias:
+        lay.blobs[1].set_cpu_diff(g(golden, dtype, k + "/db0"))
+    lay.Backward([top], [False], [bottom])
+    assert scaled_err(lay.blobs[0].cpu_diff(), g(golden, dtype, k + "/dW")) <= TOL_EXACT[dtype]
+    if bias:
+        assert scaled_err(lay.blobs[1].cpu_diff(), g(golden, dtype, k + "/db")) <= TOL_EXACT[dtype]
+    with pytest.raises(CheckError, match="Can't backpropagate to EmbedLayer input"):
+        lay.Backward([top], [True], [bottom])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("D", [50, 300, 7])
+def test_embed_vs_oracle_trec_shaped(dtype, D):
+    V, N, L = 1000, 37, 40
+    rng = np.random.default_rng(D)
+    idx = synth.make_indices(rng, N, L, V, 3, 20).astype(dtype)
+    W = rng.uniform(-0.08, 0.08, (V, D)).astype(dtype)
+    b = rng.uniform(-0.01, 0.01, D).astype(dtype)
+    lay = mms.EmbedLayer(mms.LayerParameter("Embed", dtype=dtype, embed_param=dict(num_output=D, input_dim=V)))
+    bottom, top = blob(idx, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bottom], [top])
+    lay.blobs[0].set_cpu_data(W); lay.blobs[1].set_cpu_data(b)
+    lay.Forward([bottom], [top])
+    assert np.array_equal(top.cpu_data(), cport.embed_forward(idx, W, b))        # gather is bit-exact
+    dtop = rng.uniform(-1, 1, top.shape).astype(dtype)
+    top.set_cpu_diff(dtop)
+    lay.Backward([top], [False], [bottom])
+    dW, db = np.zeros_like(W), np.zeros_like(b)
+    cport.embed_backward(idx, dtop, dW, db)
+    # the pad row receives ~half of all rows: compare on the table's scale
+    assert scaled_err(lay.blobs[0].cpu_diff(), dW) <= 20 * TOL_EXACT[dtype]
+    assert scaled_err(lay.blobs[1].cpu_diff(), db) <= 20 * TOL_EXACT[dtype]
+    # rows never indexed stay exactly zero
+    untouched = np.setdiff1d(np.arange(V), idx.astype(np.int64).ravel())
+    assert not lay.blobs[0].cpu_diff()[untouched].any()
+
+
+def test_embed_out_of_range_index_is_flagged():
+    lay = mms.EmbedLayer(mms.LayerParameter("Embed", embed_param=dict(num_output=4, input_dim=5, bias_term=False)))
+    bottom, top = blob(np.array([[1, 7, -2, 4]], np.float32), np.float32), mms.Blob(())
+    lay.SetUp([bottom], [top])
+    lay.Forward([bottom], [top])
+    with pytest.raises(mms.MMSError) as ei:
+        lay.handle.check_faults()
+    assert ei.value.code == _lib.MMS_E_FAULT
+    out = top.cpu_data()[0]
+    assert not out[1].any() and not out[2].any()      # faulted rows are zero-filled, not garbage
+    lay.handle.check_faults()                         # flag is cleared after reporting
+
+
+def test_embed_empty_batch():
+    lay = mms.EmbedLayer(mms.LayerParameter("Embed", embed_param=dict(num_output=4, input_dim=5)))
+    bottom, top = mms.Blob((0, 40)), mms.Blob(())
+    lay.SetUp([bottom], [top])
+    lay.Forward([bottom], [top])
+    assert top.shape == (0, 40, 4)
+
+
+# ------------------------------------------------------------------------------ SimCross
+def run_simcross(dtype, mode, q, a, Mw, B, dS, math, dM0=None, dB0=None, prop=(True, True), bias=True):
+    N, Lq, D = q.shape
+    mc = Mw.shape[0] if mode == 2 else 1
+    lay = mms.SimCrossLayer(mms.LayerParameter("SimCross", dtype=dtype, sim_cross_param=dict(
+        dist_mode=mode, mesure_count=mc, bias_term=bias)))
+    bq, ba, top = blob(q, dtype), blob(a, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bq, ba], [top])
+    lay.set_math(math)
+    if mode == 2:
+        lay.blobs[0].set_cpu_data(Mw)
+        if bias:
+            lay.blobs[1].set_cpu_data(B)
+        if dM0 is not None:
+            lay.blobs[0].set_cpu_diff(dM0)
+        if dB0 is not None and bias:
+            lay.blobs[1].set_cpu_diff(dB0)
+    lay.Forward([bq, ba], [top])
+    S = top.cpu_data()
+    top.set_cpu_diff(dS)
+    bq.diff.fill_(7.0); ba.diff.fill_(7.0)            # bottom diffs must be overwritten
+    lay.Backward([top], list(prop), [bq, ba])
+    out = dict(S=S, dq=bq.cpu_diff(), da=ba.cpu_diff())
+    if mode == 2:
+        out["dM"] = lay.blobs[0].cpu_diff()
+        if bias:
+            out["dB"] = lay.blobs[1].cpu_diff()
+    return out
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("math", [_lib.MMS_MATH_TF32, _lib.MMS_MATH_FP32])
+def test_simcross_golden(golden, dtype, mode, math):
+    k = "simcross_m%d" % mode
+    q, a, dS = (g(golden, dtype, k + "/" + n) for n in ("q", "a", "dS"))
+    Mw = g(golden, dtype, k + "/M") if mode == 2 else np.zeros((1, 1, 1), dtype)
+    B = g(golden, dtype, k + "/B") if mode == 2 else None
+    out = run_simcross(dtype, mode, q, a, Mw, B, dS, math,
+                       dM0=g(golden, dtype, k + "/dM0") if mode == 2 else None,
+                       dB0=g(golden, dtype, k + "/dB0") if mode == 2 else None)
+    tol = contraction_tol(dtype, math) if mode == 2 else 50 * TOL_EXACT[dtype]
+    assert out["S"].shape == g(golden, dtype, k + "/S").shape
+    assert scaled_err(out["S"], g(golden, dtype, k + "/S")) <= tol
+    assert scaled_err(out["dq"], g(golden, dtype, k + "/dq")) <= tol
+    assert scaled_err(out["da"], g(golden, dtype, k + "/da")) <= tol
+    if mode == 2:
+        assert scaled_err(out["dM"], g(golden, dtype, k + "/dM")) <= tol          # dM0 discarded
+        assert scaled_err(out["dB"], g(golden, dtype, k + "/dB")) <= TOL_EXACT[dtype]  # dB0 kept
+
+
+SHAPES = [  # N, Lq, La, D, mc
+    (50, 40, 40, 50, 4),     # C1, the reference's own configuration
+    (8, 40, 40, 300, 4),     # C2/C3 shape, few pairs
+    (5, 17, 23, 36, 3),      # ragged
+    (3, 40, 40, 300, 1),
+    (1, 1, 1, 1, 1),
+    (7, 64, 64, 128, 2),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("math", [_lib.MMS_MATH_TF32, _lib.MMS_MATH_FP32])
+def test_simcross_mode2_vs_oracle(dtype, shape, math):
+    if dtype == np.float64 and math == _lib.MMS_MATH_FP32:
+        pytest.skip("math option only affects float")
+    N, Lq, La, D, mc = shape
+    rng = np.random.default_rng(sum(shape))
+    q = rng.uniform(-0.08, 0.08, (N, Lq, D)).astype(dtype)
+    a = rng.uniform(-0.08, 0.08, (N, La, D)).astype(dtype)
+    Mw = rng.uniform(-0.1, 0.1, (mc, D, D)).astype(dtype)
+    B = rng.uniform(-0.01, 0.01, (mc, Lq, La)).astype(dtype)
+    dS = (rng.uniform(-1, 1, (N, mc, Lq, La)) / (N * mc * Lq * La)).astype(dtype)
+    dB0 = rng.uniform(-1e-3, 1e-3, B.shape).astype(dtype)
+    out = run_simcross(dtype, 2, q, a, Mw, B, dS, math, dB0=dB0)
+    S, _, _ = cport.simcross_forward(2, q, a, Mw, B)
+    dq, da, dM, dB = cport.simcross_backward(2, q, a, Mw, S, dS, dB=dB0.copy())
+    tol = contraction_tol(dtype, math)
+    assert scaled_err(out["S"], S) <= tol
+    assert scaled_err(out["dq"], dq) <= tol
+    assert scaled_err(out["da"], da) <= tol
+    assert scaled_err(out["dM"], dM) <= tol
+    assert scaled_err(out["dB"], dB) <= 10 * TOL_EXACT[dtype]
+    # ranking order of the scores: identical wherever the oracle's gap exceeds the tolerance
+    flat_ref, flat_got = S.reshape(N * mc, -1), out["S"].reshape(N * mc, -1)
+    gap = tol * np.abs(S).max()
+    for r in range(flat_ref.shape[0]):
+        order = np.argsort(-flat_ref[r], kind="stable")
+        sr = flat_ref[r][order]
+        sg = flat_got[r][order]
+        clear = (sr[:-1] - sr[1:]) > 2 * gap
+        assert np.all(sg[:-1][clear] > sg[1:][clear])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_simcross_quirks(dtype):
+    """zero-initialised M gives S == B exactly; no bias blob when bias_term is false; nothing
+    propagates => bottom diffs are still zeroed and dM/dB untouched (sim_cross_layer.cpp:176-201)."""
+    rng = np.random.default_rng(9)
+    N, Lq, La, D, mc = 4, 40, 40, 50, 4
+    q = rng.uniform(-1, 1, (N, Lq, D)).astype(dtype)
+    a = rng.uniform(-1, 1, (N, La, D)).astype(dtype)
+    B = rng.uniform(-1, 1, (mc, Lq, La)).astype(dtype)
+    dS = rng.uniform(-1, 1, (N, mc, Lq, La)).astype(dtype)
+    out = run_simcross(dtype, 2, q, a, np.zeros((mc, D, D), dtype), B, dS, _lib.MMS_MATH_TF32)
+    assert np.array_equal(out["S"], np.broadcast_to(B, out["S"].shape))
+    assert not out["dq"].any() and not out["da"].any()
+    Mw = rng.uniform(-0.1, 0.1, (mc, D, D)).astype(dtype)
+    dM0 = rng.uniform(-1, 1, Mw.shape).astype(dtype)
+    dB0 = rng.uniform(-1, 1, B.shape).astype(dtype)
+    out = run_simcross(dtype, 2, q, a, Mw, B, dS, _lib.MMS_MATH_TF32, dM0=dM0, dB0=dB0, prop=(False, False))
+    assert not out["dq"].any() and not out["da"].any()
+    assert np.array_equal(out["dM"], dM0) and np.array_equal(out["dB"], dB0)
+    lay = mms.SimCrossLayer(mms.LayerParameter("SimCross", dtype=dtype, sim_cross_param=dict(
+        dist_mode=2, mesure_count=2, bias_term=False)))
+    lay.SetUp([blob(q, dtype), blob(a, dtype)], [mms.Blob((), dtype=dtype)])
+    assert len(lay.blobs) == 1
+    with pytest.raises(CheckError):
+        bad = mms.SimCrossLayer(mms.LayerParameter("SimCross", dtype=dtype, sim_cross_param=dict(dist_mode=2)))
+        bad.SetUp([blob(q, dtype), blob(a[:, :, :-1], dtype)], [mms.Blob((), dtype=dtype)])
+
+
+# ------------------------------------------------------------------------------ SimMatrix
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_simmatrix_golden(golden, dtype):
+    k = "simmatrix"
+    q, a, W, ds = (g(golden, dtype, k + "/" + n) for n in ("q", "a", "W", "ds"))
+    lay = mms.SimMatrixLayer(mms.LayerParameter("SimMatrix", dtype=dtype))
+    bq, ba, top = blob(q, dtype), blob(a, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bq, ba], [top])
+    lay.blobs[0].set_cpu_data(W)
+    lay.Forward([bq, ba], [top])
+    tol = contraction_tol(dtype, _lib.MMS_MATH_TF32)
+    assert top.shape == (q.shape[0], 1)
+    assert scaled_err(top.cpu_data(), g(golden, dtype, k + "/s")) <= tol
+    assert scaled_err(ba.cpu_diff(), g(golden, dtype, k + "/T")) <= tol           # forward scratch
+    top.set_cpu_diff(ds)
+    lay.blobs[0].set_cpu_diff(g(golden, dtype, k + "/dW0"))
+    lay.Backward([top], [True, True], [bq, ba])
+    assert scaled_err(lay.blobs[0].cpu_diff(), g(golden, dtype, k + "/dW")) <= tol
+    assert scaled_err(bq.cpu_diff(), g(golden, dtype, k + "/dq")) <= tol
+    assert scaled_err(ba.cpu_diff(), g(golden, dtype, k + "/da")) <= tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(64, 100, 100), (33, 70, 45), (256, 1024, 1024)])
+def test_simmatrix_vs_oracle(dtype, shape):
+    N, K1, K2 = shape
+    q, a, W = synth.make_sentence_vectors(N, K1, K2, seed=N, dtype=dtype)
+    rng = np.random.default_rng(N)
+    ds = rng.uniform(-1, 1, (N, 1)).astype(dtype)
+    lay = mms.SimMatrixLayer(mms.LayerParameter("SimMatrix", dtype=dtype))
+    bq, ba, top = blob(q, dtype), blob(a, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bq, ba], [top])
+    lay.blobs[0].set_cpu_data(W)
+    lay.Forward([bq, ba], [top])
+    s, T = cport.simmatrix_forward(q, a, W)
+    tol = contraction_tol(dtype, _lib.MMS_MATH_TF32)
+    assert scaled_err(top.cpu_data(), s) <= tol
+    top.set_cpu_diff(ds)
+    lay.Backward([top], [True, True], [bq, ba])
+    dW, dq, da = cport.simmatrix_backward(q, a, W, ds, np.zeros_like(W))
+    assert scaled_err(lay.blobs[0].cpu_diff(), dW) <= tol
+    assert scaled_err(bq.cpu_diff(), dq) <= tol
+    assert scaled_err(ba.cpu_diff(), da) <= tol
+
+
+# ------------------------------------------------------------------------------ PairRankLoss / FM
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("margin", [1.0, 0.5])
+def test_pairrankloss_golden(golden, dtype, margin):
+    k = "pairrank_m%g" % margin
+    a, b, y = (g(golden, dtype, k + "/" + n) for n in ("a", "b", "y"))
+    lay = mms.PairRankLossLayer(mms.LayerParameter("PairRankLoss", dtype=dtype,
+                                                   pair_rank_loss_param=dict(margin=margin)))
+    ba, bb, by, top = blob(a, dtype), blob(b, dtype), blob(y, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([ba, bb, by], [top])
+    loss = lay.Forward([ba, bb, by], [top])
+    want = g(golden, dtype, k + "/loss")[0]
+    assert abs(top.cpu_data()[0] - want) <= 4 * np.finfo(dtype).eps * abs(want)
+    assert loss == pytest.approx(float(want), rel=1e-6)          # loss weight 1 => Forward returns it
+    top.set_cpu_diff(np.array([2.0], dtype))
+    lay.Backward([top], [True, True, False], [ba, bb, by])
+    assert np.array_equal(ba.cpu_diff(), g(golden, dtype, k + "/da"))            # bit-exact
+    assert np.array_equal(bb.cpu_diff(), g(golden, dtype, k + "/db"))
+    with pytest.raises(CheckError, match="cannot backpropagate to label inputs"):
+        lay.Backward([top], [True, True, True], [ba, bb, by])
+    # the reference's GPU variant of the hinge test (>=) is selectable
+    lay.handle.set_option(_lib.MMS_OPT_PRL_GE, 1)
+    lay.Backward([top], [True, True, False], [ba, bb, by])
+    _, ordered, similar = cport.pairrankloss_forward(a, b, y, margin)
+    da_ge, db_ge = cport.pairrankloss_backward(y, ordered, similar, 2.0, ge=True)
+    assert np.array_equal(ba.cpu_diff(), da_ge) and np.array_equal(bb.cpu_diff(), db_ge)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pairrankloss_large_vs_oracle(dtype):
+    rng = np.random.default_rng(4)
+    n = 16384
+    a = rng.normal(0, 2, (n, 1)).astype(dtype); b = rng.normal(0, 2, (n, 1)).astype(dtype)
+    y = rng.choice([1.0, 0.0, -1.0], size=(n, 1), p=[0.7, 0.2, 0.1]).astype(dtype)
+    lay = mms.PairRankLossLayer(mms.LayerParameter("PairRankLoss", dtype=dtype))
+    ba, bb, by, top = blob(a, dtype), blob(b, dtype), blob(y, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([ba, bb, by], [top])
+    lay.Forward([ba, bb, by], [top])
+    loss, ordered, similar = cport.pairrankloss_forward(a, b, y, 1.0)
+    assert abs(top.cpu_data()[0] - loss) <= 1e-3 * abs(loss) * (1e-2 if dtype == np.float32 else 1e-9)
+    assert np.array_equal(lay.ordered_diff_.cpu_data().reshape(-1), ordered.reshape(-1))
+    lay.Backward([top], [True, True, False], [ba, bb, by])
+    da, db = cport.pairrankloss_backward(y, ordered, similar, 1.0)
+    assert np.array_equal(ba.cpu_diff(), da) and np.array_equal(bb.cpu_diff(), db)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_fm_golden(golden, dtype, bias):
+    k = "fm_b%d" % int(bias)
+    x = g(golden, dtype, k + "/x")
+    lay = mms.FMLayer(mms.LayerParameter("FM", dtype=dtype, fm_param=dict(bias_term=bias)))
+    bx, top = blob(x, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bx], [top])
+    if bias:
+        lay.blobs[0].set_cpu_data(np.array([0.375], dtype))
+        lay.blobs[0].set_cpu_diff(np.array([5.0], dtype))          # must be overwritten
+    lay.Forward([bx], [top])
+    assert scaled_err(top.cpu_data(), g(golden, dtype, k + "/y")) <= TOL_EXACT[dtype]
+    top.set_cpu_diff(g(golden, dtype, k + "/dy"))
+    lay.Backward([top], [True], [bx])
+    assert scaled_err(bx.cpu_diff(), g(golden, dtype, k + "/dx")) <= TOL_EXACT[dtype]
+    if bias:
+        assert scaled_err(lay.blobs[0].cpu_diff(), g(golden, dtype, k + "/db")) <= TOL_EXACT[dtype]
+
+
+# ------------------------------------------------------------------------------ whole path
+@pytest.mark.parametrize("cfg", ["c1", "c2"])
+def test_mmsnet_step_vs_oracle(cfg):
+    """Embed x2 -> SimCross(mode 2) forward+backward on a TREC-QA-shaped batch."""
+    c = dict(synth.CONFIGS[cfg]); c["N"] = 10; c["V"] = 2000
+    d = synth.make_qa_batch(**c)
+    d["b"] = np.random.default_rng(1).uniform(-0.01, 0.01, c["D"]).astype(np.float32)
+    net = mms.MMSNet(c["N"], c["L"], c["D"], c["mc"], c["V"])
+    net.set_params(d["W"], d["b"], d["M"], d["B"])
+    net.set_inputs(d["idx_q"], d["idx_a"])
+    net.set_upstream_gradient(d["dS"])
+    net.ClearParamDiffs()
+    loss = net.ForwardBackward()
+    q = cport.embed_forward(d["idx_q"], d["W"], d["b"]); a = cport.embed_forward(d["idx_a"], d["W"], d["b"])
+    assert np.array_equal(net.q.cpu_data(), q) and np.array_equal(net.a.cpu_data(), a)
+    S, _, _ = cport.simcross_forward(2, q, a, d["M"], d["B"])
+    dq, da, dM, dB = cport.simcross_backward(2, q, a, d["M"], S, d["dS"])
+    dW, db = np.zeros_like(d["W"]), np.zeros_like(d["b"])
+    cport.embed_backward(d["idx_q"], dq, dW, db); cport.embed_backward(d["idx_a"], da, dW, db)
+    assert scaled_err(net.S.cpu_data(), S) <= TOL_TF32
+    assert loss == pytest.approx(float((S.astype(np.float64) * d["dS"]).sum()), rel=5e-3, abs=1e-7)
+    W_b, b_b, M_b, B_b = net.params()
+    assert scaled_err(M_b.cpu_diff(), dM) <= TOL_TF32
+    assert scaled_err(B_b.cpu_diff(), dB) <= 10 * TOL_EXACT[np.float32]
+    assert scaled_err(W_b.cpu_diff(), dW) <= TOL_TF32
+    assert scaled_err(b_b.cpu_diff(), db) <= TOL_TF32
+
+
+def test_simcross_full_size_properties():
+    """C3-shaped batch (a 512-pair shard of the 4096 global batch): properties that need no
+    oracle -- linearity in q, bias-only scores, and dB = sum_n dS."""
+    N, L, D, mc = 512, 40, 300, 4
+    gen = torch.Generator(device="cuda").manual_seed(22)
+    q1 = (torch.rand((N, L, D), device="cuda", generator=gen) - 0.5) * 0.16
+    q2 = (torch.rand((N, L, D), device="cuda", generator=gen) - 0.5) * 0.16
+    a = (torch.rand((N, L, D), device="cuda", generator=gen) - 0.5) * 0.16
+    Mw = (torch.rand((mc, D, D), device="cuda", generator=gen) - 0.5) * 0.2
+    lay = mms.SimCrossLayer(mms.LayerParameter("SimCross", sim_cross_param=dict(dist_mode=2, mesure_count=mc)))
+    bq, ba, top = mms.Blob((N, L, D)), mms.Blob((N, L, D)), mms.Blob(())
+    lay.SetUp([bq, ba], [top])
+    lay.blobs[0].data.copy_(Mw)
+    ba.data.copy_(a)
+
+    def fwd(qt):
+        bq.data.copy_(qt)
+        lay.Forward([bq, ba], [top])
+        return top.data.clone()
+
+    s1, s2, s12 = fwd(q1), fwd(q2), fwd(q1 + q2)
+    scale = s12.abs().max().item()
+    assert (s1 + s2 - s12).abs().max().item() <= 2 * TOL_TF32 * scale
+    ref = torch.einsum("nld,kde,nme->nklm", q1.double(), Mw.double(), a.double())
+    assert (s1.double() - ref).abs().max().item() <= TOL_TF32 * ref.abs().max().item()
+    dS = (torch.rand(top.shape, device="cuda", generator=gen) - 0.5)
+    top.diff.copy_(dS)
+    lay.blobs[1].diff.zero_()
+    bq.data.copy_(q1)
+    lay.Backward([top], [True, True], [bq, ba])
+    assert (lay.blobs[1].diff - dS.sum(0)).abs().max().item() <= 1e-4 * dS.sum(0).abs().max().item()
+    dM_ref = torch.einsum("nld,nklm,nme->kde", q1.double(), dS.double(), a.double())
+    assert (lay.blobs[0].diff.double() - dM_ref).abs().max().item() <= TOL_TF32 * dM_ref.abs().max().item()
+    dq_ref = torch.einsum("nklm,nme,kde->nld", dS.double(), a.double(), Mw.double())
+    assert (bq.diff.double() - dq_ref).abs().max().item() <= TOL_TF32 * dq_ref.abs().max().item()
+    da_ref = torch.einsum("nklm,nld,kde->nme", dS.double(), q1.double(), Mw.double())
+    assert (ba.diff.double() - da_ref).abs().max().item() <= TOL_TF32 * da_ref.abs().max().item()
+
+
+def test_rerank_scores_vs_simmatrix_form():
+    """candidate scoring: scores[i,j] = q_i^T W c_j, checked against the SimMatrix oracle."""
+    import ctypes
+    Nq, Nc, K = 16, 3000, 128
+    Q, C, W = synth.make_rerank(Nq, Nc, K, seed=3)
+    h = _lib.Handle()
+    tQ, tC, tW = (torch.from_numpy(x).cuda() for x in (Q, C, W))
+    QW = torch.empty((Nq, K), device="cuda"); sc = torch.empty((Nq, Nc), device="cuda")
+    _lib.check(_lib.lib().mms_rerank_scores_f32(h.ptr, *(ctypes.c_void_p(t.data_ptr()) for t in (tQ, tC, tW, QW, sc)),
+                                                Nq, Nc, K, K))
+    got = sc.cpu().numpy()
+    ref = (Q.astype(np.float64) @ W.astype(np.float64)) @ C.astype(np.float64).T
+    assert scaled_err(got, ref) <= TOL_TF32
+    # one row through the SimMatrix oracle (q_i paired with every candidate)
+    s, _ = cport.simmatrix_forward(np.repeat(Q[:1], 64, 0), C[:64], W)
+    assert scaled_err(got[0, :64], s.reshape(-1)) <= TOL_TF32

@@ -1,0 +1,48 @@
+"""CPU tests of the host-side logic that needs no device: Blob shape arithmetic, layer
+parameters (prototxt defaults), synthetic TREC-QA-shaped data."""
+import numpy as np
+import pytest
+
+from mms_answer_selection_b200 import synth
+from mms_answer_selection_b200.blob import Blob
+from mms_answer_selection_b200.layers import LayerParameter, create_layer, CheckError
+
+
+def test_blob_shape_accessors():
+    b = Blob((50, 40, 300), device="cpu")
+    assert (b.num(), b.channels(), b.height(), b.width()) == (50, 40, 300, 1)   # sim_cross reads these
+    assert b.count() == 600000 and b.count(1) == 12000 and b.count(0, 1) == 50
+    b.set_cpu_data(np.arange(600000, dtype=np.float32))
+    assert b.cpu_data()[1, 0, 0] == 12000
+    b.Reshape((2, 3))
+    assert b.data.shape == (2, 3) and not b.data.any()
+    with pytest.raises(ValueError):
+        Blob((2, 2, 2, 2, 2), device="cpu").num()
+    with pytest.raises(TypeError):
+        Blob((1,), dtype=np.float16, device="cpu")
+
+
+def test_layer_parameter_defaults_match_caffe_proto():
+    p = LayerParameter("SimCross")
+    assert p.sim_cross_param["dist_mode"] == 1 and p.sim_cross_param["mesure_count"] == 1
+    assert p.sim_cross_param["bias_term"] is True
+    assert p.sim_cross_param["weight_filler"]["type"] == "constant"      # default filler: zeros
+    assert LayerParameter("PairRankLoss").pair_rank_loss_param["margin"] == 1.0
+    assert LayerParameter("Embed").embed_param["weight_source"] == ""
+    with pytest.raises(KeyError):
+        LayerParameter("SimCross", sim_cross_param=dict(measure_count=2))  # the reference spells it mesure_count
+    with pytest.raises(CheckError, match="Unknown layer type"):
+        create_layer(LayerParameter("Convolution"))
+
+
+def test_synthetic_batch_follows_the_reference_padding():
+    d = synth.make_qa_batch(N=20, L=40, D=8, mc=2, V=100)
+    assert d["idx_q"].dtype == np.float32 and d["idx_q"].shape == (20, 40)
+    pad = 99
+    for row, lo, hi in ((d["idx_q"], 3, 20), (d["idx_a"], 5, 40)):
+        for r in row.astype(int):
+            toks = np.flatnonzero(r != pad)
+            assert lo <= len(toks) <= hi and r.max() <= pad
+            assert toks[0] == (40 - len(toks)) // 2 and np.all(np.diff(toks) == 1)   # centre-padded
+    assert np.abs(d["W"]).max() <= 0.08 and not d["B"].any()
+    assert synth.pad_sentence(range(50), 40, -1).tolist() == list(range(40))         # truncation

@@ -203,6 +203,15 @@ int mms_scale_f64(mms_handle_t h, double* x, long long count, double alpha);
 int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W,
                           float* QW, float* scores, int Nq, long long Nc, int K1, int K2);
 
+/* --------------------------------------------------------- diagnostics ------
+ * The tcgen05 TF32 GEMM building block, exposed for tests and profiling:
+ * C (+)= op(A) op(B), M x N x K.  a_mn = 0: A(m,k) = A[m*lda + k] (K-major), 1: A[k*lda + m]
+ * (MN-major); b_mn likewise with B(n,k).  mode 0 store, 1 +=, 2 atomicAdd (required when
+ * ksplit > 1). */
+int mms_tc_gemm_f32(mms_handle_t h, const float* A, long long lda, int a_mn, const float* B,
+                    long long ldb, int b_mn, float* C, long long ldc, int M, int N, int K, int ksplit,
+                    int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ def lib():
                 fn.argtypes = args
                 fn.restype = c_int
         L.mms_rerank_scores_f32.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_ll, c_int, c_int]
+        L.mms_tc_gemm_f32.argtypes = [c_p, c_p, c_ll, c_int, c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int,
+                                      c_int, c_int]
         _lib = L
     return _lib
 

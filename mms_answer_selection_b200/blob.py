@@ -27,10 +27,15 @@ class Blob(object):
         if any(s < 0 for s in shape):
             raise ValueError("negative blob dimension")
         n = int(np.prod(shape)) if shape else 0
-        if n != self.count() or self._data is None:
+        if n != self.count():
             self._data = None   # reallocated lazily, like blob.cpp:40-44
             self._diff = None
         self._shape = shape
+        view = shape if shape else (0,)
+        if self._data is not None:
+            self._data = self._data.reshape(view)
+        if self._diff is not None:
+            self._diff = self._diff.reshape(view)
 
     @property
     def shape(self):

@@ -6,6 +6,7 @@
 #include <new>
 
 #include "mms_common.cuh"
+#include "tc/tc_gemm.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -263,6 +264,15 @@ MMS_DEFINE_TYPED(double, f64)
 int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W, float* QW,
                           float* scores, int Nq, long long Nc, int K1, int K2) {
   H; return mms_rerank_scores_impl(h, Q, C, W, QW, scores, Nq, Nc, K1, K2);
+}
+
+// Test/diagnostic entry: C (+)= op(A) op(B) on the tcgen05 TF32 GEMM (see tc/tc_gemm.cuh).
+int mms_tc_gemm_f32(mms_handle_t h, const float* A, long long lda, int a_mn, const float* B, long long ldb,
+                    int b_mn, float* C, long long ldc, int M, int N, int K, int ksplit, int mode) {
+  H;
+  TcGemmArgs g = tc_gemm_args(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, mode);
+  g.ksplit = ksplit;
+  return mms_tc_gemm(h, g);
 }
 
 }  // extern "C"

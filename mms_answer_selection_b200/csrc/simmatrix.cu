@@ -5,6 +5,7 @@
 // The reference's backward is N cblas_sger / cblas_sgemv calls on the host
 // (sim_matrix_layer.cpp:73-93); here each gradient is one GEMM over the whole batch.
 #include "mms_common.cuh"
+#include "tc/tc_gemm.cuh"
 
 namespace {
 
@@ -61,6 +62,37 @@ inline int ew_grid(mms_context* ctx, long long n) {
 
 }  // namespace
 
+// float + MMS_MATH_TF32: the three contractions run on tcgen05 (tc/tc_gemm.cu); diag(ds) is fused
+// into the operand staging, so no scaled copies of q / a are materialised.
+inline bool use_tc(mms_context* ctx, const float*) { return ctx->math == MMS_MATH_TF32; }
+inline bool use_tc(mms_context*, const double*) { return false; }
+
+inline int tc_T(mms_context* ctx, const float* q, const float* W, float* Tm, int N, int K1, int K2,
+                const float* rowscale) {
+  TcGemmArgs g = tc_gemm_args(q, K1, 0, W, K2, 1, Tm, K2, N, K2, K1);   // A K-major, B(n=c,k=t)=W[t][c] MN-major
+  g.a_rowscale = rowscale;
+  return mms_tc_gemm(ctx, g);
+}
+inline int tc_T(mms_context*, const double*, const double*, double*, int, int, int, const double*) { return MMS_E_UNSUPPORTED; }
+
+inline int tc_dW(mms_context* ctx, const float* q, const float* a, const float* ds, float* dW, int N, int K1, int K2) {
+  // dW[r][c] += sum_n q[n][r] * ds[n] * a[n][c]: both operands MN-major (rows = sample n = K index)
+  TcGemmArgs g = tc_gemm_args(q, K1, 1, a, K2, 1, dW, K2, K1, K2, N, TC_ATOMIC);
+  g.b_rowscale = ds;
+  const int tiles = mms_ceil_div(K1, 128) * mms_ceil_div(K2, 256);
+  g.ksplit = mms_max(1, mms_min(mms_ceil_div(ctx->sm_count, tiles), mms_ceil_div(N, 256)));
+  return mms_tc_gemm(ctx, g);
+}
+inline int tc_dW(mms_context*, const double*, const double*, const double*, double*, int, int, int) { return MMS_E_UNSUPPORTED; }
+
+inline int tc_dq(mms_context* ctx, const float* a, const float* W, const float* ds, float* dq, int N, int K1, int K2) {
+  // dq[n][r] = ds[n] * sum_c a[n][c] W[r][c]: A = a K-major (row-scaled), B(n=r,k=c)=W[r][c] K-major
+  TcGemmArgs g = tc_gemm_args(a, K2, 0, W, K2, 0, dq, K1, N, K1, K2);
+  g.a_rowscale = ds;
+  return mms_tc_gemm(ctx, g);
+}
+inline int tc_dq(mms_context*, const double*, const double*, const double*, double*, int, int, int) { return MMS_E_UNSUPPORTED; }
+
 template <typename T>
 int mms_simmatrix_forward_impl(mms_context* ctx, const T* q, const T* a, const T* W, T* s, T* Tm,
                                int N, int K1, int K2) {
@@ -68,7 +100,8 @@ int mms_simmatrix_forward_impl(mms_context* ctx, const T* q, const T* a, const T
   MMS_REQUIRE(N >= 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
   if (N == 0) return 0;
   // T = q W   (gemm NoTrans,NoTrans M_ x K2 x K1, sim_matrix_layer.cpp:60-61)
-  MMS_TRY(gemm2d<T>(ctx, q, K1, 1, W, K2, 1, Tm, K2, N, K2, K1, T(0)));
+  if (use_tc(ctx, q)) MMS_TRY(tc_T(ctx, q, W, Tm, N, K1, K2, nullptr));
+  else MMS_TRY(gemm2d<T>(ctx, q, K1, 1, W, K2, 1, Tm, K2, N, K2, K1, T(0)));
   { MmsKernelScope ks_(ctx, "rowdot_kernel");
     rowdot_kernel<T><<<ew_grid(ctx, (long long)N * 32), 256, 0, ctx->stream>>>(a, Tm, s, N, K2); }
   MMS_LAUNCH_CHECK();
@@ -82,6 +115,12 @@ int mms_simmatrix_backward_impl(mms_context* ctx, const T* q, const T* a, const 
   MMS_REQUIRE(q && a && W && ds, MMS_E_INVALID, "null pointer");
   MMS_REQUIRE(N >= 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
   if (N == 0) return 0;
+  if (use_tc(ctx, q)) {
+    if (prop_w && dW) MMS_TRY(tc_dW(ctx, q, a, ds, dW, N, K1, K2));
+    if (prop0 && dq) MMS_TRY(tc_dq(ctx, a, W, ds, dq, N, K1, K2));
+    if (prop1 && da) MMS_TRY(tc_T(ctx, q, W, da, N, K1, K2, ds));     // da = (ds o q) W
+    return 0;
+  }
   const bool need_as = (prop_w && dW) || (prop0 && dq);
   const bool need_qs = (prop1 && da);
   void* sp = nullptr;
@@ -117,6 +156,12 @@ int mms_rerank_scores_impl(mms_context* ctx, const float* Q, const float* C, con
   MMS_REQUIRE(Q && C && W && QW && scores, MMS_E_INVALID, "null pointer");
   MMS_REQUIRE(Nq > 0 && Nc > 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
   MMS_REQUIRE(Nc <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "candidate count exceeds int range");
+  if (ctx->math == MMS_MATH_TF32) {
+    MMS_TRY(tc_T(ctx, Q, W, QW, Nq, K1, K2, nullptr));
+    // scores = QW C^T: both K-major
+    TcGemmArgs t = tc_gemm_args(QW, K2, 0, C, K2, 0, scores, Nc, Nq, (int)Nc, K2);
+    return mms_tc_gemm(ctx, t);
+  }
   MMS_TRY(gemm2d<float>(ctx, Q, K1, 1, W, K2, 1, QW, K2, Nq, K2, K1, 0.f));
   // scores[i][j] = sum_c QW[i][c] * C[j][c]; scores row stride = Nc
   SimtGemmArgs<float> g;

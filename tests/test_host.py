@@ -46,3 +46,14 @@ def test_synthetic_batch_follows_the_reference_padding():
             assert toks[0] == (40 - len(toks)) // 2 and np.all(np.diff(toks) == 1)   # centre-padded
     assert np.abs(d["W"]).max() <= 0.08 and not d["B"].any()
     assert synth.pad_sentence(range(50), 40, -1).tolist() == list(range(40))         # truncation
+
+
+def test_blob_reshape_keeps_storage_when_count_is_unchanged():
+    b = Blob((1,), device="cpu")
+    b.diff.fill_(2.0)                 # diff allocated before data (SetLossWeights does this)
+    b.Reshape((1,))
+    assert b.diff.item() == 2.0
+    b.Reshape((1, 1))
+    assert b.diff.reshape(-1)[0].item() == 2.0
+    b.Reshape((3,))
+    assert not b.diff.any()

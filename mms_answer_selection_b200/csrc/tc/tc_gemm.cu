@@ -80,7 +80,7 @@ __device__ __forceinline__ void stage_operand(uint8_t* dst, const float* src, lo
         if (rowscale) { const float s = __ldg(rowscale + gr); v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
       }
       v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-      *reinterpret_cast<float4*>(dst + b * 4096 + swz128(r, c4)) = v;
+      *reinterpret_cast<float4*>(dst + b * 4096 + swz128_mn(r, c4)) = v;
     }
   }
 }

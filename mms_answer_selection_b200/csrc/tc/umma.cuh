@@ -6,10 +6,13 @@
 //  * shared-memory operand tiles use the 128-byte-swizzle canonical layouts that the
 //    UMMA shared-memory descriptor names:
 //      K-major  block: [rows][32 k-elements]  = rows x 128 B, 8-row groups 1024 B apart;
-//      MN-major block: [k-rows][32 mn-elements] = k x 128 B, 8-k groups 1024 B apart,
+//      MN-major block: [k-rows][32 mn-elements] = k x 128 B, 4-k groups 512 B apart,
 //                      successive 32-wide mn blocks `lbo` bytes apart;
-//    within every 1024-byte atom the 16-byte chunk index is XORed with (row & 7)
-//    (Swizzle<3,4,3> on the byte address), so tiles must be 1024-byte aligned;
+//    K-major uses SWIZZLE_128B: within every 1024-byte atom the 16-byte chunk index is XORed
+//    with (row & 7) (Swizzle<3,4,3> on the byte address).  MN-major 32-bit operands must use
+//    SWIZZLE_128B_BASE32B (the only MN-major layout the hardware accepts for tf32): within
+//    every 512-byte atom the 32-byte chunk index is XORed with (k-row & 3) (Swizzle<2,5,2>).
+//    Tiles are 1024-byte aligned;
 //  * descriptor bit layouts follow the PTX ISA "tcgen05 shared memory descriptor" /
 //    "instruction descriptor" tables (cross-checked against CUTLASS's
 //    cute/arch/mma_sm100_desc.hpp field definitions).
@@ -118,18 +121,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // K-major : LBO unused by the hardware for swizzled layouts (canonical value 1),
 //           SBO = distance between 8-row groups (1024 B for dense 128-byte rows).
 // MN-major: LBO = distance between 32-element mn blocks, SBO = distance between 8-k groups.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout codes: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (MN-major tf32)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return smem_desc(saddr, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return smem_desc(saddr, 16, 1024, 2); }
+// MN-major tf32: 32-wide mn blocks `lbo_bytes` apart, groups of 4 k-rows 512 B apart
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
-  return smem_desc(saddr, lbo_bytes, 1024);
+  return smem_desc(saddr, lbo_bytes, 512, 1);
 }
 
 // Instruction descriptor (32 bit) for kind::tf32, fp32 accumulate, dense:
@@ -180,10 +186,17 @@ __device__ __forceinline__ uint32_t swz128(uint32_t row, uint32_t c4) {
   return row * 128u + ((c4 ^ (row & 7u)) << 4);
 }
 
+// MN-major (SWIZZLE_128B_BASE32B): row = k index, 16-byte chunk c4 of the 128-byte row.
+__device__ __forceinline__ uint32_t swz128_mn(uint32_t row, uint32_t c4) {
+  return row * 128u + ((((c4 >> 1) ^ (row & 3u)) << 5) | ((c4 & 1u) << 4));
+}
+
 // Stage one [nrows x 32] fp32 block (rows 128 B apart, swizzled) from a row-major global
 // matrix: element (r, c) = src[(row0 + r) * ld + col0 + c], zero outside
 // [0,row_limit) x [0,col_limit).  `tid`/`nthreads` enumerate the cooperating loader threads.
 // vec_ok: src, ld and col0 allow 16-byte loads.
+// MN_LAYOUT selects the MN-major swizzle (rows are k indices) instead of the K-major one.
+template <bool MN_LAYOUT>
 __device__ __forceinline__ void stage_block(uint8_t* dst, const float* __restrict__ src, long long ld,
                                             long long row0, int nrows, long long row_limit, int col0,
                                             int col_limit, bool vec_ok, int tid, int nthreads) {
@@ -205,7 +218,7 @@ __device__ __forceinline__ void stage_block(uint8_t* dst, const float* __restric
       }
     }
     v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-    *reinterpret_cast<float4*>(dst + swz128(r, c4)) = v;
+    *reinterpret_cast<float4*>(dst + (MN_LAYOUT ? swz128_mn(r, c4) : swz128(r, c4))) = v;
   }
 }
 

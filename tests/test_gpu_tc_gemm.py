@@ -1,0 +1,63 @@
+"""GPU tests of the tcgen05 TF32 GEMM building block (mms_tc_gemm_f32) against a float64
+reference, for every operand majorness, ragged sizes, unaligned leading dimensions,
+split-K with the atomic epilogue and the accumulate epilogue.  Tolerance: 1e-3 of the
+output's largest magnitude (TF32 operands rounded to nearest, fp32 accumulation)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from mms_answer_selection_b200 import _lib   # noqa: E402
+
+TOL = 1e-3
+
+
+def run(M, N, K, a_mn, b_mn, ksplit=1, mode=0, pad=0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed + M + 7 * N + 13 * K)
+    lda = (M if a_mn else K) + pad
+    ldb = (N if b_mn else K) + pad
+    A = torch.rand(((K if a_mn else M), lda), device="cuda", generator=g) - 0.5
+    B = torch.rand(((K if b_mn else N), ldb), device="cuda", generator=g) - 0.5
+    C0 = torch.rand((M, N + pad), device="cuda", generator=g) - 0.5
+    C = C0.clone() if mode else torch.full((M, N + pad), 7.0, device="cuda")
+    if mode == 2:
+        C = C0.clone()
+    h = _lib.Handle()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib().mms_tc_gemm_f32(h.ptr, p(A), lda, a_mn, p(B), ldb, b_mn, p(C), N + pad, M, N, K,
+                                          ksplit, mode))
+    torch.cuda.synchronize()
+    Am = (A[:, :M].T if a_mn else A[:, :K]).double()
+    Bm = (B[:, :N].T if b_mn else B[:, :K]).double()
+    ref = Am @ Bm.T
+    if mode:
+        ref = ref + C0[:, :N].double()
+    got = C[:, :N].double()
+    err = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+    if pad and not mode:
+        assert (C[:, N:] == 7.0).all()          # nothing written outside the N columns
+    return err
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("shape", [(128, 64, 32), (128, 256, 64), (200, 300, 300), (40, 40, 50), (1, 1, 1),
+                                   (333, 130, 77), (1024, 1024, 1024)])
+def test_tc_gemm_majorness(shape, a_mn, b_mn):
+    M, N, K = shape
+    assert run(M, N, K, a_mn, b_mn) <= TOL
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (0, 1)])
+def test_tc_gemm_unaligned_leading_dims(a_mn, b_mn):
+    assert run(150, 90, 50, a_mn, b_mn, pad=1) <= TOL
+    assert run(150, 90, 50, a_mn, b_mn, pad=2) <= TOL
+
+
+def test_tc_gemm_split_k_atomic_and_accumulate():
+    assert run(300, 300, 20000, 1, 1, ksplit=8, mode=2) <= TOL
+    assert run(300, 300, 4096, 0, 0, ksplit=1, mode=1) <= TOL
+    assert run(128, 128, 10000, 1, 0, ksplit=7, mode=2) <= TOL

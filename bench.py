@@ -214,19 +214,28 @@ def main_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     handles = [net.embed_q.handle, net.embed_a.handle, net.sim.handle]
 
+    # The whole step (ClearParamDiffs + Forward + loss + Backward) is recorded once as a CUDA graph and
+    # replayed: issued launch by launch from the host the ~15 short kernels are launch-bound.
+    l0 = sum(h.launch_count() for h in handles)
+    net.capture(with_loss=True, clear_diffs=True)
+    launches_per_step = (sum(h.launch_count() for h in handles) - l0) // 3      # 2 warm-up passes + the capture
+
     def device_step():
-        net.ClearParamDiffs()          # Net::ClearParamDiffs (solver.cpp:203): zeroes the V x D diff too
-        net.ForwardBackward(with_loss=False)
+        net.replay(read_loss=False)
         if exch:
             exch.allreduce()
 
     def e2e_step():
         net.set_inputs_from_pinned(host_q, host_a)      # H2D of this step's inputs
-        net.ClearParamDiffs()
-        loss = net.ForwardBackward(with_loss=True)      # D2H of the step's loss (4 bytes) + sync
+        loss = net.replay(read_loss=not exch)           # D2H of the step's loss (4 bytes) + sync
         if exch:
             exch.allreduce()
+            loss = float(net.sim.loss_dev_[0].item())
         return loss
+
+    def eager_step():
+        net.ClearParamDiffs()          # Net::ClearParamDiffs (solver.cpp:203): zeroes the V x D diff too
+        net.ForwardBackward(with_loss=True)
 
     def barrier():
         if world > 1:
@@ -254,28 +263,35 @@ def main_ours(args):
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = sum(h.launch_count() for h in handles)
     total_ms = timed(device_step, args.steps)
-    launches = sum(h.launch_count() for h in handles) - l0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop()
 
     for _ in range(3):
         e2e_step()
     e2e_ms = timed(e2e_step, args.steps)
 
-    # roofline of the dominant kernel, measured live with CUDA events around each launch
+    # roofline of the dominant kernel, measured live with CUDA events around each launch of an
+    # eagerly issued step.  The GPU is first given ~0.5 ms of other work (L2 flushes) so that every
+    # launch of the step is already queued when it runs: the events then bracket device time, not
+    # host launch latency.
+    sim_state = net.sim.defer_loss_
+    net.sim.defer_loss_ = True
     for h in handles:
         h.profile_enable(True)
-    for _ in range(min(args.steps, 20)):
-        flush.fill_(1)
-        device_step()
+    prof_steps = min(args.steps, 20)
+    for _ in range(prof_steps):
+        for _ in range(8):
+            flush.fill_(1)
+        eager_step()
+        torch.cuda.synchronize()
+    net.sim.defer_loss_ = sim_state
     prof = {}
     for h in handles:
         for k, (n, ms) in h.profile_report().items():
             pn, pms = prof.get(k, (0, 0.0))
             prof[k] = (pn + n, pms + ms)
         h.profile_enable(False)
-    prof_steps = min(args.steps, 20)
     step_ms_prof = sum(ms for _, ms in prof.values()) / prof_steps
     dom = max(prof.items(), key=lambda kv: kv[1][1])
     peaks = {}
@@ -294,6 +310,7 @@ def main_ours(args):
         "data": "synthetic",
         "config": {"workload": workload_name(args.workload, cfg), "parallelism": "dp%d" % world,
                    "l2": "256 MiB L2 flush between timed steps (inputs+table < L2)",
+                   "launch": "step recorded as one CUDA graph (%d kernels of libmms_b200.so per step)" % launches_per_step,
                    "grad_exchange": "NCCL all-reduce of the flat gradient buffer + 1/N scale" if world > 1 else "none"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(host_q.numel() * 4 + host_a.numel() * 4), "d2h_bytes_per_step": 4},

@@ -53,7 +53,7 @@ enum {
   MMS_OPT_PRL_GE = 2,        /* PairRankLoss backward hinge test: 0 `ordered > 0` (reference CPU,
                                 pair_rank_loss_layer.cpp:76), 1 `ordered >= 0` (reference GPU,
                                 pair_rank_loss_layer.cu:51).  Default 0. */
-  MMS_OPT_SCRATCH_BYTES = 3, /* cap for the per-call scratch chunk (default 256 MiB) */
+  MMS_OPT_SCRATCH_BYTES = 3, /* cap for the per-call scratch chunk (default 4 GiB; grows on demand) */
   MMS_OPT_EMBED_DETERMINISTIC = 4 /* Embed backward: 1 = order-independent segmented reduction
                                 (bit-reproducible), 0 = block-aggregated atomics.  Default 0. */
 };
@@ -207,7 +207,8 @@ int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const 
  * The tcgen05 TF32 GEMM building block, exposed for tests and profiling:
  * C (+)= op(A) op(B), M x N x K.  a_mn = 0: A(m,k) = A[m*lda + k] (K-major), 1: A[k*lda + m]
  * (MN-major); b_mn likewise with B(n,k).  mode 0 store, 1 +=, 2 atomicAdd (required when
- * ksplit > 1). */
+ * ksplit > 1); mode | 0x100 declares that A and B already hold TF32-exact values, which lets the
+ * TMA-fed kernel fetch them (otherwise operands are rounded to TF32 in registers on the way in). */
 int mms_tc_gemm_f32(mms_handle_t h, const float* A, long long lda, int a_mn, const float* B,
                     long long ldb, int b_mn, float* C, long long ldc, int M, int N, int K, int ksplit,
                     int mode);

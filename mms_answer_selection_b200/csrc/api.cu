@@ -270,8 +270,9 @@ int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const 
 int mms_tc_gemm_f32(mms_handle_t h, const float* A, long long lda, int a_mn, const float* B, long long ldb,
                     int b_mn, float* C, long long ldc, int M, int N, int K, int ksplit, int mode) {
   H;
-  TcGemmArgs g = tc_gemm_args(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, mode);
+  TcGemmArgs g = tc_gemm_args(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, mode & 0xff);
   g.ksplit = ksplit;
+  g.operands_tf32 = (mode & 0x100) != 0;
   return mms_tc_gemm(h, g);
 }
 

@@ -11,7 +11,7 @@ struct mms_context {
   int math = MMS_MATH_TF32;
   int prl_ge = 0;
   int embed_deterministic = 0;
-  size_t scratch_cap = (size_t)256 << 20;
+  size_t scratch_cap = (size_t)4 << 30;
   void* scratch = nullptr;       // grows on demand, reused across calls
   size_t scratch_bytes = 0;
   int* fault_flag = nullptr;     // device word set by kernels on data faults
@@ -141,6 +141,7 @@ int mms_rerank_scores_impl(mms_context*, const float* Q, const float* C, const f
 // handle; the caller then uses the SIMT path (still on the GPU).
 int mms_tc_simcross2_forward(mms_context*, const float* q, const float* a, const float* Mw,
                              const float* B, float* S, int N, int Lq, int La, int D, int mc);
+// (dq, da, dM overwritten; dB is accumulated by the caller)
 int mms_tc_simcross2_backward(mms_context*, const float* q, const float* a, const float* Mw,
-                              const float* dS, float* dq, float* da, float* dM, float* dB, int N,
-                              int Lq, int La, int D, int mc);
+                              const float* dS, float* dq, float* da, float* dM, int N, int Lq, int La,
+                              int D, int mc);

@@ -163,7 +163,7 @@ int simcross2_forward_simt(mms_context* ctx, const T* q, const T* a, const T* Mw
 
 template <typename T>
 int simcross2_backward_simt(mms_context* ctx, const T* q, const T* a, const T* Mw, const T* dS, T* dq,
-                            T* da, T* dM, T* dB, int N, int Lq, int La, int D, int mc) {
+                            T* da, T* dM, int N, int Lq, int La, int D, int mc) {
   const int Lmax = max(Lq, La);
   const int nc_max = chunk_pairs<T>(ctx, N, Lmax, D, mc);
   void* sp = nullptr;
@@ -199,13 +199,17 @@ int simcross2_backward_simt(mms_context* ctx, const T* q, const T* a, const T* M
                       buf + (size_t)k * sU1, D, 1, 0, sU2, dac, D, 0, (long long)La * D, La, D, Lq, 1, nc,
                       T(1)));
   }
-  if (dB) {
-    const int per = mc * Lq * La;
-    dim3 grid(mms_ceil_div(per, 256), max(1, min(N, mms_ceil_div(4 * ctx->sm_count, mms_ceil_div(per, 256)))));
-    { MmsKernelScope ks_(ctx, "bias_grad_kernel");
-      bias_grad_kernel<T><<<grid, 256, 0, ctx->stream>>>(dS, dB, N, per); }
-    MMS_LAUNCH_CHECK();
-  }
+  return 0;
+}
+
+// dB += sum_n dS[n]   (sim_cross_layer.cpp:301-304; accumulates, never zeroed by the layer)
+template <typename T>
+int simcross2_bias_grad(mms_context* ctx, const T* dS, T* dB, int N, int Lq, int La, int mc) {
+  const int per = mc * Lq * La;
+  dim3 grid(mms_ceil_div(per, 256), max(1, min(N, mms_ceil_div(4 * ctx->sm_count, mms_ceil_div(per, 256)))));
+  { MmsKernelScope ks_(ctx, "bias_grad_kernel");
+    bias_grad_kernel<T><<<grid, 256, 0, ctx->stream>>>(dS, dB, N, per); }
+  MMS_LAUNCH_CHECK();
   return 0;
 }
 
@@ -219,11 +223,11 @@ inline int tc_fwd(mms_context* ctx, const float* q, const float* a, const float*
 inline int tc_fwd(mms_context*, const double*, const double*, const double*, const double*, double*,
                   int, int, int, int, int) { return MMS_E_UNSUPPORTED; }
 inline int tc_bwd(mms_context* ctx, const float* q, const float* a, const float* Mw, const float* dS,
-                  float* dq, float* da, float* dM, float* dB, int N, int Lq, int La, int D, int mc) {
-  return mms_tc_simcross2_backward(ctx, q, a, Mw, dS, dq, da, dM, dB, N, Lq, La, D, mc);
+                  float* dq, float* da, float* dM, int N, int Lq, int La, int D, int mc) {
+  return mms_tc_simcross2_backward(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
 }
 inline int tc_bwd(mms_context*, const double*, const double*, const double*, const double*, double*,
-                  double*, double*, double*, int, int, int, int, int) { return MMS_E_UNSUPPORTED; }
+                  double*, double*, int, int, int, int, int) { return MMS_E_UNSUPPORTED; }
 
 }  // namespace
 
@@ -279,14 +283,18 @@ int mms_simcross_backward_impl(mms_context* ctx, int mode, const T* q, const T* 
   }
   if (mode == 2) {
     MMS_REQUIRE(Mw && dM && mc > 0, MMS_E_INVALID, "mode 2 needs M, dM and mesure_count > 0");
-    if (IsFloat<T>::value && ctx->math == MMS_MATH_TF32) {
-      const int rc = tc_bwd(ctx, q, a, Mw, dS, dq, da, dM, dB, N, Lq, La, D, mc);
-      if (rc != MMS_E_UNSUPPORTED) return rc;
+    int rc = MMS_E_UNSUPPORTED;
+    if (IsFloat<T>::value && ctx->math == MMS_MATH_TF32)
+      rc = tc_bwd(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
+    if (rc == MMS_E_UNSUPPORTED) {
+      MMS_TRY(mms_fill<T>(ctx, dq, (long long)N * Lq * D, T(0)));
+      MMS_TRY(mms_fill<T>(ctx, da, (long long)N * La * D, T(0)));
+      MMS_TRY(mms_fill<T>(ctx, dM, (long long)mc * D * D, T(0)));     // :256
+      rc = simcross2_backward_simt<T>(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
     }
-    MMS_TRY(mms_fill<T>(ctx, dq, (long long)N * Lq * D, T(0)));
-    MMS_TRY(mms_fill<T>(ctx, da, (long long)N * La * D, T(0)));
-    MMS_TRY(mms_fill<T>(ctx, dM, (long long)mc * D * D, T(0)));     // :256
-    return simcross2_backward_simt<T>(ctx, q, a, Mw, dS, dq, da, dM, dB, N, Lq, La, D, mc);
+    MMS_TRY(rc);
+    if (dB) MMS_TRY(simcross2_bias_grad<T>(ctx, dS, dB, N, Lq, La, mc));
+    return 0;
   }
   MMS_REQUIRE(S, MMS_E_INVALID, "modes 0/1 read the forward output");
   const long long t0 = (long long)N * Lq * D, t1 = (long long)N * La * D;

@@ -1,8 +1,150 @@
-// placeholder until the tcgen05 kernels land: every shape reports "unsupported", so the
-// dispatcher in simcross.cu uses the SIMT composition.
+// SimCross mode 2 (S[n,k] = Q_n M_k A_n^T + B_k) on tcgen05 tensor cores (TF32 multiply, fp32
+// accumulate in TMEM).  Reference semantics: src/caffe/layers/sim_cross_layer.cpp:140-161
+// (forward) and :251-307 (backward); the reference runs 2 (fwd) / 6 (bwd) cblas_sgemm calls
+// per (pair, measure) on the host.
+//
+// Here the batch is flattened so that every contraction with a D x D operand is ONE GEMM
+// over all N*L token rows, and the per-pair contractions are one batched launch each:
+//
+//   forward   T[k]   = Qall M_k                (N*Lq x D x D,  batch k)
+//             S[n,k] = T[k][n] A_n^T + B_k     (Lq x La x D,   batch (k, n), bias fused)
+//   backward  U[k][n] = dS[n,k] A_n            (Lq x D x La,   batch (k, n))
+//             dM_k   += Qall^T U[k]            (D x D x N*Lq,  batch k, split-K, atomics)
+//             dQall   = sum_k U[k] M_k^T       (N*Lq x D x mc*D, k as reduction segments)
+//             T[k]    = Qall M_k               (recomputed: the C-ABI is stateless)
+//             dA_n    = sum_k dS[n,k]^T T[k][n] (La x D x mc*Lq, batch n, k as segments)
+//
+// No operand is ever transposed in memory: the UMMA descriptors take K-major and MN-major
+// tiles alike (tc_gemm.cu).  T / U live in the handle's scratch buffer; N is processed in
+// chunks when mc*N*L*D floats exceed MMS_OPT_SCRATCH_BYTES.
 #include "../mms_common.cuh"
-int mms_tc_simcross2_forward(mms_context*, const float*, const float*, const float*, const float*,
-                             float*, int, int, int, int, int) { return MMS_E_UNSUPPORTED; }
-int mms_tc_simcross2_backward(mms_context*, const float*, const float*, const float*, const float*,
-                              float*, float*, float*, float*, int, int, int, int, int) { return MMS_E_UNSUPPORTED; }
-void mms_tc_destroy_state(mms_context*) {}
+#include "tc_gemm.cuh"
+
+// Every operand of the contractions below is a TF32-rounded copy in the handle's scratch buffer
+// (external inputs q, a, M, dS pass through one rounding/repacking launch; T and U are rounded by
+// the epilogue that produces them), with leading dimensions padded to 4 floats, so that all of
+// them are fetched by TMA whatever D / La are.
+namespace {
+
+struct Plan {
+  int Dp, Lap;               // padded leading dimensions of the scratch copies
+  size_t per_pair, fixed;    // scratch floats per QA pair / independent of N
+  int nc_max;
+};
+
+Plan make_plan(mms_context* ctx, int N, int Lq, int La, int D, int mc, bool backward) {
+  Plan p;
+  p.Dp = (int)tc_pad4(D); p.Lap = (int)tc_pad4(La);
+  const int Lmax = mms_max(Lq, La);
+  p.per_pair = (size_t)(Lq + La) * p.Dp + (size_t)mc * (backward ? Lmax : Lq) * p.Dp +
+               (backward ? (size_t)mc * Lq * p.Lap : 0);
+  p.fixed = (size_t)mc * D * p.Dp;
+  long long c = ((long long)(ctx->scratch_cap / sizeof(float)) - (long long)p.fixed) / (long long)p.per_pair;
+  p.nc_max = (int)mms_max<long long>(1, mms_min<long long>(c, N));
+  return p;
+}
+
+// T[k][row][:] = Qall[row][:] M_k      (row = chunk-local token row; result rounded for reuse)
+int gemm_T(mms_context* ctx, const float* qr, const float* Mr, float* Tk, int rows, int D, int Dp, int mc) {
+  TcGemmArgs g = tc_gemm_args(qr, Dp, 0, Mr, Dp, 1, Tk, Dp, rows, D, D);
+  g.nb1 = mc; g.sB1 = (long long)D * Dp; g.sC1 = (long long)rows * Dp;
+  g.operands_tf32 = 1; g.round_out = 1;
+  return mms_tc_gemm(ctx, g);
+}
+
+}  // namespace
+
+int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, const float* Mw,
+                             const float* B, float* S, int N, int Lq, int La, int D, int mc) {
+  const Plan p = make_plan(ctx, N, Lq, La, D, mc, false);
+  const int Dp = p.Dp;
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * (p.fixed + p.per_pair * p.nc_max), &sp));
+  float* Mr = static_cast<float*>(sp);
+  float* qr = Mr + p.fixed;
+  float* ar = qr + (size_t)p.nc_max * Lq * Dp;
+  float* Tk = ar + (size_t)p.nc_max * La * Dp;
+  for (int n0 = 0; n0 < N; n0 += p.nc_max) {
+    const int nc = mms_min(p.nc_max, N - n0);
+    float* Sc = S + (size_t)n0 * mc * Lq * La;
+    const RoundJob jobs[3] = {
+        {q + (size_t)n0 * Lq * D, qr, (long long)nc * Lq, D, D, Dp, nullptr},
+        {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
+        {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
+    MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
+    MMS_TRY(gemm_T(ctx, qr, Mr, Tk, nc * Lq, D, Dp, mc));                  // sim_cross_layer.cpp:148-149
+    TcGemmArgs g = tc_gemm_args(Tk, Dp, 0, ar, Dp, 0, Sc, La, Lq, La, D);  // :151-153
+    g.nb1 = mc; g.nb2 = nc;
+    g.sA1 = (long long)nc * Lq * Dp; g.sA2 = (long long)Lq * Dp;
+    g.sB2 = (long long)La * Dp;
+    g.sC1 = (long long)Lq * La; g.sC2 = (long long)mc * Lq * La;
+    if (B) { g.c_add = B; g.ld_add = La; g.s_add1 = (long long)Lq * La; }  // :155-159
+    g.operands_tf32 = 1;
+    MMS_TRY(mms_tc_gemm(ctx, g));
+  }
+  return 0;
+}
+
+// Computes dq, da (overwritten) and dM (overwritten: zeroed here, :256).  dB is left to the caller.
+int mms_tc_simcross2_backward(mms_context* ctx, const float* q, const float* a, const float* Mw,
+                              const float* dS, float* dq, float* da, float* dM, int N, int Lq, int La,
+                              int D, int mc) {
+  const Plan p = make_plan(ctx, N, Lq, La, D, mc, true);
+  const int Dp = p.Dp, Lap = p.Lap, Lmax = mms_max(Lq, La);
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * (p.fixed + p.per_pair * p.nc_max), &sp));
+  float* Mr = static_cast<float*>(sp);
+  float* qr = Mr + p.fixed;
+  float* ar = qr + (size_t)p.nc_max * Lq * Dp;
+  float* Gr = ar + (size_t)p.nc_max * La * Dp;
+  float* buf = Gr + (size_t)p.nc_max * mc * Lq * Lap;
+  (void)Lmax;
+  MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));
+  for (int n0 = 0; n0 < N; n0 += p.nc_max) {
+    const int nc = mms_min(p.nc_max, N - n0);
+    float* dqc = dq + (size_t)n0 * Lq * D;
+    float* dac = da + (size_t)n0 * La * D;
+    const RoundJob jobs[4] = {
+        {q + (size_t)n0 * Lq * D, qr, (long long)nc * Lq, D, D, Dp, nullptr},
+        {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
+        {dS + (size_t)n0 * mc * Lq * La, Gr, (long long)nc * mc * Lq, La, La, Lap, nullptr},
+        {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
+    MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 4 : 3));
+    const long long sU1 = (long long)nc * Lq * Dp, sU2 = (long long)Lq * Dp;
+    const long long sG1 = (long long)Lq * Lap, sG2 = (long long)mc * Lq * Lap;
+    {  // U[k][n] = G_nk A_n
+      TcGemmArgs g = tc_gemm_args(Gr, Lap, 0, ar, Dp, 1, buf, Dp, Lq, D, La);
+      g.nb1 = mc; g.nb2 = nc;
+      g.sA1 = sG1; g.sA2 = sG2;
+      g.sB2 = (long long)La * Dp;
+      g.sC1 = sU1; g.sC2 = sU2;
+      g.operands_tf32 = 1; g.round_out = 1;
+      MMS_TRY(mms_tc_gemm(ctx, g));
+    }
+    {  // dM_k += Qall^T U[k]            (= sum_n Q_n^T G_nk A_n, :286-289)
+      const int kdim = nc * Lq;
+      TcGemmArgs g = tc_gemm_args(qr, Dp, 1, buf, Dp, 1, dM, D, D, D, kdim, TC_ATOMIC);
+      g.nb1 = mc; g.sB1 = sU1; g.sC1 = (long long)D * D;
+      const int tiles = mc * mms_ceil_div(D, 128) * mms_ceil_div(D, 256);
+      g.ksplit = mms_max(1, mms_min(mms_ceil_div(ctx->sm_count, tiles), mms_ceil_div(kdim, 128)));
+      g.operands_tf32 = 1;
+      MMS_TRY(mms_tc_gemm(ctx, g));
+    }
+    {  // dQall = sum_k U[k] M_k^T       (= G (M_k A^T)^T summed over k, :291-294)
+      TcGemmArgs g = tc_gemm_args(buf, Dp, 0, Mr, Dp, 0, dqc, D, nc * Lq, D, D);
+      g.nseg = mc; g.segA = sU1; g.segB = (long long)D * Dp;
+      g.operands_tf32 = 1;
+      MMS_TRY(mms_tc_gemm(ctx, g));
+    }
+    MMS_TRY(gemm_T(ctx, qr, Mr, buf, nc * Lq, D, Dp, mc));
+    {  // dA_n = sum_k G_nk^T T[k][n]    (:296-299)
+      TcGemmArgs g = tc_gemm_args(Gr, Lap, 1, buf, Dp, 1, dac, D, La, D, Lq);
+      g.nb2 = nc;
+      g.sA2 = sG2; g.sB2 = sU2; g.sC2 = (long long)La * D;
+      g.nseg = mc; g.segA = sG1; g.segB = sU1;
+      g.operands_tf32 = 1;
+      MMS_TRY(mms_tc_gemm(ctx, g));
+    }
+  }
+  return 0;
+}

@@ -4,27 +4,51 @@
 
 enum { TC_STORE = 0, TC_ACCUM = 1, TC_ATOMIC = 2 };
 
+// C[z1][z2] (+)= sum over K segments s of  op(A[z1][z2][s]) * op(B[z1][z2][s])   (+ c_add)
+//   A operand base for batch (z1, z2), segment s: A + z1*sA1 + z2*sA2 + s*segA   (likewise B)
+//   C base: C + z1*sC1 + z2*sC2;   c_add base: c_add + z1*s_add1 + z2*s_add2
 struct TcGemmArgs {
   const float* A; long long lda; int a_mn;   // a_mn = 0: A(m,k) = A[m*lda + k];  1: A[k*lda + m]
   const float* B; long long ldb; int b_mn;   // b_mn = 0: B(n,k) = B[n*ldb + k];  1: B[k*ldb + n]
   float* C; long long ldc;                   // C(m,n) = C[m*ldc + n]
-  int M, N, K;
-  long long sA, sB, sC;                      // batch strides in elements
-  int batch;
-  int ksplit;                                // > 1: K split over CTAs, needs mode == TC_ATOMIC
+  int M, N, K;                               // K = extent of ONE segment
+  int nb1, nb2;                              // batch grid (z = z1*nb2 + z2)
+  long long sA1, sA2, sB1, sB2, sC1, sC2;    // batch strides in elements
+  int nseg; long long segA, segB;            // the reduction runs over nseg segments of K each
+  int ksplit;                                // > 1: reduction split over CTAs, needs mode == TC_ATOMIC
   int mode;                                  // TC_STORE: C = acc, TC_ACCUM: C += acc, TC_ATOMIC: atomicAdd
   const float* a_rowscale;                   // optional: scales A's staged rows (K-major: per m, MN-major: per k)
   const float* b_rowscale;                   // optional: scales B's staged rows (K-major: per n, MN-major: per k)
   const float* out_rowscale;                 // optional: acc[m][n] *= out_rowscale[m]
+  const float* c_add; long long ld_add, s_add1, s_add2;   // optional: acc[m][n] += c_add[m*ld_add + n]
+  int operands_tf32;                         // 1: A and B already hold TF32-exact values (rounded by a previous
+                                             //    kernel) -> they may be fetched by TMA without a register pass
+  int round_out;                             // 1: round the stored result to TF32 (it feeds another contraction)
 };
 
 inline TcGemmArgs tc_gemm_args(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn,
                                float* C, long long ldc, int M, int N, int K, int mode = TC_STORE) {
   TcGemmArgs g;
   g.A = A; g.lda = lda; g.a_mn = a_mn; g.B = B; g.ldb = ldb; g.b_mn = b_mn; g.C = C; g.ldc = ldc;
-  g.M = M; g.N = N; g.K = K; g.sA = g.sB = g.sC = 0; g.batch = 1; g.ksplit = 1; g.mode = mode;
+  g.M = M; g.N = N; g.K = K;
+  g.nb1 = g.nb2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0;
+  g.nseg = 1; g.segA = g.segB = 0;
+  g.ksplit = 1; g.mode = mode;
   g.a_rowscale = g.b_rowscale = g.out_rowscale = nullptr;
+  g.c_add = nullptr; g.ld_add = g.s_add1 = g.s_add2 = 0;
+  g.operands_tf32 = 0; g.round_out = 0;
   return g;
 }
 
+// Dispatch: the TMA-fed kernel (tc_gemm_tma.cu) when the operands are TF32-exact and 16-byte
+// aligned in every stride, else the register-staged kernel (tc_gemm.cu), which rounds on the fly.
 int mms_tc_gemm(mms_context* ctx, const TcGemmArgs& args);
+int mms_tc_gemm_staged(mms_context* ctx, const TcGemmArgs& args);
+int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& args);   // MMS_E_UNSUPPORTED if not eligible
+
+// dst[r*ldd + c] = tf32_rna(src[r*lds + c] * (scale ? scale[r] : 1)) for up to 4 matrices in one launch.
+struct RoundJob {
+  const float* src; float* dst; long long rows; int cols; long long lds, ldd; const float* scale;
+};
+int mms_tf32_round(mms_context* ctx, const RoundJob* jobs, int njobs);
+inline long long tc_pad4(long long n) { return (n + 3) & ~3LL; }

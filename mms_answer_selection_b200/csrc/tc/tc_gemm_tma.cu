@@ -1,0 +1,425 @@
+// TMA-fed TF32 GEMM on tcgen05 (sm_100a): same contract as tc_gemm.cu, for operands that already
+// hold TF32-exact values (rounded by the producing kernel) and whose strides are 16-byte multiples.
+//
+//   warp 0     producer: one lane issues cp.async.bulk.tensor (5-D tiled TMA, 128-byte swizzle) for
+//              every stage as soon as its ring slot is free -- no registers, no generic-proxy
+//              stores, `stages` loads in flight per SM; out-of-range rows / k are zero-filled by TMA
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (accumulator double-buffered)
+//   warps 2-5  epilogue: tcgen05.ld -> registers -> global (store / += / atomicAdd, fused bias,
+//              optional TF32 rounding of results that feed the next contraction)
+// K-major operands are one [rows x 32 k] box per stage (CU_TENSOR_MAP_SWIZZLE_128B); MN-major
+// operands are [32 k x 32 mn] boxes (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, the only MN-major layout
+// tcgen05 takes for 32-bit types).  Batch indices and reduction segments are tensor-map dimensions.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <map>
+#include <tuple>
+
+#include "../mms_common.cuh"
+#include "tc_gemm.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kMaxStages = 6;
+
+struct Smem {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+constexpr int kEpiLd = 36;                                   // floats per staged row (32 + 4: conflict-free 16-byte accesses)
+constexpr int kEpiBytes = kEpiWarps * 32 * kEpiLd * 4;        // one 32 x 32 transposition buffer per epilogue warp
+
+struct Geometry {
+  int BN, stages, b_bytes, n_tiles, m_tiles;
+  unsigned total_tiles;
+  uint32_t tmem_cols;
+  // 0/1 multipliers: a broadcast (stride 0) batch / segment dimension has extent 1 in the tensor map
+  int a_z1, a_z2, a_seg, b_z1, b_z2, b_seg;
+};
+
+struct Tile {
+  int z1, z2, m0, n0, ibeg, nk;
+};
+
+__device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry& q, unsigned t, int sps) {
+  Tile tl;
+  const int n_tile = t % q.n_tiles; t /= q.n_tiles;
+  const int m_tile = t % q.m_tiles; t /= q.m_tiles;
+  const int split = t % g.ksplit;
+  const int z = t / g.ksplit;
+  tl.z1 = z / g.nb2; tl.z2 = z % g.nb2;
+  tl.m0 = m_tile * kBM; tl.n0 = n_tile * q.BN;
+  const int total_stages = g.nseg * sps;
+  const int per_split = (total_stages + g.ksplit - 1) / g.ksplit;
+  tl.ibeg = split * per_split;
+  tl.nk = max(0, min(total_stages, tl.ibeg + per_split) - tl.ibeg);
+  return tl;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const TcGemmArgs g, const Geometry q) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 16384 + q.b_bytes;
+  float* epi = reinterpret_cast<float*>(ring + q.stages * stage_bytes);
+  Smem* sm = reinterpret_cast<Smem*>(ring + q.stages * stage_bytes + kEpiBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sps = (g.K + kBK - 1) / kBK;
+  const int BN = q.BN, stages = q.stages;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], kEpiWarps); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm->tmem_base, q.tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      const int b_blocks = (BN + 31) >> 5;
+      int it = 0;
+      for (unsigned t = blockIdx.x; t < q.total_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(g, q, t, sps);
+        const int az1 = tl.z1 * q.a_z1, az2 = tl.z2 * q.a_z2;
+        const int bz1 = tl.z1 * q.b_z1, bz2 = tl.z2 * q.b_z2;
+        for (int i = 0; i < tl.nk; ++i, ++it) {
+          const int s = it % stages;
+          const int gi = tl.ibeg + i;
+          const int seg = gi / sps;
+          const int k0 = (gi - seg * sps) * kBK;
+          if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
+          uint8_t* a_dst = ring + s * stage_bytes;
+          uint8_t* b_dst = a_dst + 16384;
+          mbar_arrive_expect_tx(&sm->full[s], tx_bytes);
+          if (!A_MN) {
+            tma_load_5d(a_dst, &mapA, &sm->full[s], k0, tl.m0, az2, az1, seg * q.a_seg);
+          } else {
+#pragma unroll
+            for (int b = 0; b < kBM / 32; ++b)
+              tma_load_5d(a_dst + b * 4096, &mapA, &sm->full[s], tl.m0 + 32 * b, k0, az2, az1, seg * q.a_seg);
+          }
+          if (!B_MN) {
+            tma_load_5d(b_dst, &mapB, &sm->full[s], k0, tl.n0, bz2, bz1, seg * q.b_seg);
+          } else {
+            for (int b = 0; b < b_blocks; ++b)
+              tma_load_5d(b_dst + b * 4096, &mapB, &sm->full[s], tl.n0 + 32 * b, k0, bz2, bz1, seg * q.b_seg);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issue (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(kBM, BN, A_MN, B_MN);
+      int it = 0, tcount = 0;
+      for (unsigned t = blockIdx.x; t < q.total_tiles; t += gridDim.x, ++tcount) {
+        const Tile tl = decode_tile(g, q, t, sps);
+        const int buf = tcount & 1;
+        if (tcount >= 2) mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem + buf * BN;
+        for (int i = 0; i < tl.nk; ++i, ++it) {
+          const int s = it % stages;
+          mbar_wait(&sm->full[s], (it / stages) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(ring + s * stage_bytes);
+          const uint32_t b_base = a_base + 16384;
+#pragma unroll
+          for (int ks = 0; ks < kBK / 8; ++ks) {
+            const uint64_t da = A_MN ? desc_mnmajor(a_base + ks * 1024, 4096) : desc_kmajor(a_base + ks * 32);
+            const uint64_t db = B_MN ? desc_mnmajor(b_base + ks * 1024, 4096) : desc_kmajor(b_base + ks * 32);
+            mma_tf32_ss(acc, da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          }
+          mma_commit(&sm->empty[s]);
+        }
+        mma_commit(&sm->acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (TMEM lane quarter = warp % 4)
+    const int quarter = warp & 3;
+    int tcount = 0;
+    for (unsigned t = blockIdx.x; t < q.total_tiles; t += gridDim.x, ++tcount) {
+      const Tile tl = decode_tile(g, q, t, sps);
+      const int buf = tcount & 1;
+      float* C = g.C + tl.z1 * g.sC1 + tl.z2 * g.sC2;
+      const float* Cadd = g.c_add ? g.c_add + tl.z1 * g.s_add1 + tl.z2 * g.s_add2 : nullptr;
+      mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const bool c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (g.ldc % 4 == 0) && (tl.n0 % 4 == 0);
+      const int row_tm = tl.m0 + quarter * 32 + lane;           // the accumulator row this thread reads from TMEM
+      const float rs = (g.out_rowscale && row_tm < g.M) ? __ldg(g.out_rowscale + row_tm) : 1.f;
+      const uint32_t acc = tmem + buf * BN + ((uint32_t)(quarter * 32) << 16);
+      const int ncols = min(BN, g.N - tl.n0);
+      float* stage = epi + quarter * (32 * kEpiLd);
+      // rows of this warp that exist: a warp that owns none skips its TMEM reads altogether
+      const int warp_rows = min(32, g.M - (tl.m0 + quarter * 32));
+      for (int c0 = 0; warp_rows > 0 && c0 < ncols; c0 += 32) {
+        float v[32];
+        if (tl.nk > 0) {
+          if (c0 + 16 < BN) tmem_ld32(acc + c0, v);          // BN is a multiple of 16
+          else tmem_ld16(acc + c0, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        // transpose through shared memory: TMEM hands every thread one ROW (32 columns); global memory
+        // wants every warp instruction to cover whole 128-byte row segments
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4)
+          *reinterpret_cast<float4*>(stage + lane * kEpiLd + i4 * 4) =
+              make_float4(v[i4 * 4] * rs, v[i4 * 4 + 1] * rs, v[i4 * 4 + 2] * rs, v[i4 * 4 + 3] * rs);
+        __syncwarp();
+        const int cc = (lane & 7) * 4;                       // 4 columns of this thread
+        const int n = tl.n0 + c0 + cc;
+        const bool col_ok = n < g.N && c0 + cc < BN;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = rr * 4 + (lane >> 3);
+          if (r < warp_rows && col_ok) {
+            const int row = tl.m0 + quarter * 32 + r;
+            float4 o = *reinterpret_cast<const float4*>(stage + r * kEpiLd + cc);
+            const bool full = n + 3 < g.N;
+            if (Cadd) {
+              const float* ap = Cadd + (long long)row * g.ld_add + n;
+              o.x += __ldg(ap);
+              if (n + 1 < g.N) o.y += __ldg(ap + 1);
+              if (n + 2 < g.N) o.z += __ldg(ap + 2);
+              if (n + 3 < g.N) o.w += __ldg(ap + 3);
+            }
+            if (g.round_out) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
+            float* p = C + (long long)row * g.ldc + n;
+            if (g.mode == TC_STORE) {
+              if (c_vec && full) {
+                *reinterpret_cast<float4*>(p) = o;
+              } else {
+                p[0] = o.x;
+                if (n + 1 < g.N) p[1] = o.y;
+                if (n + 2 < g.N) p[2] = o.z;
+                if (n + 3 < g.N) p[3] = o.w;
+              }
+            } else if (g.mode == TC_ACCUM) {
+              p[0] += o.x;
+              if (n + 1 < g.N) p[1] += o.y;
+              if (n + 2 < g.N) p[2] += o.z;
+              if (n + 3 < g.N) p[3] += o.w;
+            } else {
+              if (c_vec && full) {
+                atomicAdd(reinterpret_cast<float4*>(p), o);
+              } else {
+                atomicAdd(p, o.x);
+                if (n + 1 < g.N) atomicAdd(p + 1, o.y);
+                if (n + 2 < g.N) atomicAdd(p + 2, o.z);
+                if (n + 3 < g.N) atomicAdd(p + 3, o.w);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->acc_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, q.tmem_cols);
+}
+
+// ---- tf32 rounding / repacking pass --------------------------------------------------------
+struct RoundJobs {
+  RoundJob j[4];
+};
+
+__global__ void __launch_bounds__(256) tf32_round_kernel(const RoundJobs jobs) {
+  const RoundJob jb = jobs.j[blockIdx.y];
+  const bool vec = (jb.cols % 4 == 0) && (jb.lds % 4 == 0) && (jb.ldd % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(jb.src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(jb.dst) & 15) == 0);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const int c4n = jb.cols >> 2;
+    const long long total = jb.rows * c4n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+      const long long r = e / c4n;
+      const int c = (int)(e - r * c4n) * 4;
+      float4 v = __ldg(reinterpret_cast<const float4*>(jb.src + r * jb.lds + c));
+      const float s = jb.scale ? __ldg(jb.scale + r) : 1.f;
+      v.x = to_tf32(v.x * s); v.y = to_tf32(v.y * s); v.z = to_tf32(v.z * s); v.w = to_tf32(v.w * s);
+      *reinterpret_cast<float4*>(jb.dst + r * jb.ldd + c) = v;
+    }
+  } else {
+    const long long total = jb.rows * jb.cols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+      const long long r = e / jb.cols;
+      const int c = (int)(e - r * jb.cols);
+      const float s = jb.scale ? __ldg(jb.scale + r) : 1.f;
+      jb.dst[r * jb.ldd + c] = to_tf32(__ldg(jb.src + r * jb.lds + c) * s);
+    }
+  }
+}
+
+// ---- host: tensor maps -------------------------------------------------------------------
+typedef std::tuple<const void*, long long, int, long long, long long, int, long long, long long, long long, int,
+                   int, int>
+    MapKey;
+
+struct TcState {
+  PFN_cuTensorMapEncodeTiled encode = nullptr;
+  std::map<MapKey, CUtensorMap> maps;
+};
+
+TcState* state_of(mms_context* ctx) {
+  if (!ctx->tc_state) ctx->tc_state = new TcState();
+  return static_cast<TcState*>(ctx->tc_state);
+}
+
+// Operand X(mn, k): K-major X[mn*ld + k] or MN-major X[k*ld + mn]; batch strides s1, s2 and segment
+// stride sseg in elements (0 = broadcast).  rows_box: rows per K-major box.
+int make_map(mms_context* ctx, CUtensorMap* out, const float* ptr, long long ld, bool mn_major, long long MN,
+             long long K, int rows_box, long long s1, long long s2, long long sseg, int nb1, int nb2, int nseg) {
+  TcState* st = state_of(ctx);
+  if (!st->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MMS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    MMS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MMS_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+    st->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  }
+  const MapKey key(ptr, ld, mn_major ? 1 : 0, MN, K, rows_box, s1, s2, sseg, nb1, nb2, nseg);
+  auto hit = st->maps.find(key);
+  if (hit != st->maps.end()) { *out = hit->second; return 0; }
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5] = {32, 32, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  dims[0] = (cuuint64_t)(mn_major ? MN : K);
+  dims[1] = (cuuint64_t)(mn_major ? K : MN);
+  if (!mn_major) box[1] = (cuuint32_t)rows_box;
+  strides[0] = (cuuint64_t)ld * 4;
+  // broadcast / singleton dimensions get extent 1; their stride only has to be a legal value
+  const cuuint64_t filler = strides[0] * dims[1];
+  dims[2] = s2 ? (cuuint64_t)nb2 : 1;   strides[1] = s2 ? (cuuint64_t)s2 * 4 : filler;
+  dims[3] = s1 ? (cuuint64_t)nb1 : 1;   strides[2] = s1 ? (cuuint64_t)s1 * 4 : filler;
+  dims[4] = sseg ? (cuuint64_t)nseg : 1; strides[3] = sseg ? (cuuint64_t)sseg * 4 : filler;
+  CUtensorMap m;
+  const CUresult r = st->encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mms_set_error("cuTensorMapEncodeTiled failed with CUresult %d (ld %lld, MN %lld, K %lld)", (int)r, ld, MN, K);
+    return MMS_E_UNSUPPORTED;
+  }
+  if (st->maps.size() > 256) st->maps.clear();
+  st->maps[key] = m;
+  *out = m;
+  return 0;
+}
+
+bool tma_ok(const float* p, long long ld, long long s1, long long s2, long long sseg) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0) && (s1 % 4 == 0) && (s2 % 4 == 0) &&
+         (sseg % 4 == 0) && ld > 0;
+}
+
+}  // namespace
+
+void mms_tc_destroy_state(mms_context* ctx) {
+  delete static_cast<TcState*>(ctx->tc_state);
+  ctx->tc_state = nullptr;
+}
+
+int mms_tf32_round(mms_context* ctx, const RoundJob* jobs, int njobs) {
+  MMS_REQUIRE(jobs && njobs > 0 && njobs <= 4, MMS_E_INVALID, "1..4 rounding jobs per launch");
+  RoundJobs js;
+  long long biggest = 0;
+  for (int i = 0; i < njobs; ++i) {
+    js.j[i] = jobs[i];
+    biggest = mms_max(biggest, jobs[i].rows * jobs[i].cols);
+  }
+  if (biggest == 0) return 0;
+  const int gx = (int)mms_min<long long>((biggest / 4 + 255) / 256 + 1, (long long)ctx->sm_count * 8);
+  { MmsKernelScope ks_(ctx, "tf32_round_kernel");
+    tf32_round_kernel<<<dim3(gx, njobs), 256, 0, ctx->stream>>>(js); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& a) {
+  MMS_REQUIRE(a.A && a.B && a.C, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.nb1 > 0 && a.nb2 > 0 && a.ksplit > 0 && a.nseg > 0,
+              MMS_E_INVALID, "bad size");
+  MMS_REQUIRE(a.ksplit == 1 || a.mode == TC_ATOMIC, MMS_E_INVALID, "split-K needs the atomic epilogue");
+  if (a.a_rowscale || a.b_rowscale) return MMS_E_UNSUPPORTED;     // row scaling needs the register pass
+  if (!tma_ok(a.A, a.lda, a.sA1, a.sA2, a.segA) || !tma_ok(a.B, a.ldb, a.sB1, a.sB2, a.segB))
+    return MMS_E_UNSUPPORTED;
+  Geometry q;
+  const int ntiles = mms_ceil_div(a.N, 256);
+  int BN = mms_ceil_div(mms_ceil_div(a.N, ntiles), 16) * 16;
+  if (a.b_mn) BN = mms_ceil_div(BN, 32) * 32 > 256 ? BN : mms_ceil_div(BN, 32) * 32;
+  q.BN = BN;
+  q.n_tiles = mms_ceil_div(a.N, BN);
+  q.m_tiles = mms_ceil_div(a.M, kBM);
+  q.b_bytes = a.b_mn ? mms_ceil_div(BN, 32) * 4096 : BN * 128;
+  const int stage_bytes = 16384 + q.b_bytes;
+  int stages = kMaxStages;
+  while (stages > 2 && (size_t)stages * stage_bytes + kEpiBytes + sizeof(Smem) + 1024 > 220 * 1024) --stages;
+  q.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + kEpiBytes + sizeof(Smem) + 1024;
+  const long long total = (long long)q.n_tiles * q.m_tiles * a.ksplit * a.nb1 * a.nb2;
+  MMS_REQUIRE(total <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "too many tiles");
+  q.total_tiles = (unsigned)total;
+  q.tmem_cols = umma::tmem_cols_pow2(2 * BN);
+  q.a_z1 = a.sA1 != 0; q.a_z2 = a.sA2 != 0; q.a_seg = a.segA != 0;
+  q.b_z1 = a.sB1 != 0; q.b_z2 = a.sB2 != 0; q.b_seg = a.segB != 0;
+
+  CUtensorMap mapA, mapB;
+  MMS_TRY(make_map(ctx, &mapA, a.A, a.lda, a.a_mn != 0, a.M, a.K, kBM, a.sA1, a.sA2, a.segA, a.nb1, a.nb2, a.nseg));
+  MMS_TRY(make_map(ctx, &mapB, a.B, a.ldb, a.b_mn != 0, a.N, a.K, a.b_mn ? 32 : BN, a.sB1, a.sB2, a.segB, a.nb1,
+                   a.nb2, a.nseg));
+
+  typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const TcGemmArgs, const Geometry);
+  static const kernel_t kernels[4] = {tc_gemm_tma_kernel<false, false>, tc_gemm_tma_kernel<false, true>,
+                                      tc_gemm_tma_kernel<true, false>, tc_gemm_tma_kernel<true, true>};
+  static bool configured = false;
+  if (!configured) {
+    for (int i = 0; i < 4; ++i)
+      MMS_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+    configured = true;
+  }
+  const kernel_t kernel = kernels[(a.a_mn ? 2 : 0) + (a.b_mn ? 1 : 0)];
+  const unsigned grid = (unsigned)mms_min<long long>(total, ctx->sm_count);
+  { MmsKernelScope ks_(ctx, "tc_gemm_tma_kernel");
+    kernel<<<grid, kThreads, smem, ctx->stream>>>(mapA, mapB, a, q); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}

@@ -114,6 +114,10 @@ class Layer(object):
         self.real = ctypes.c_float if self.dtype == np.float32 else ctypes.c_double
         self.handle = Handle()          # raises without a B200 / without the built library
         self.rng = np.random.default_rng(1701)
+        # When set, Forward leaves the loss in `loss_dev_` (a device scalar per loss top) instead of
+        # reading it back -- needed to record a step into a CUDA graph (no host sync while capturing).
+        self.defer_loss_ = False
+        self.loss_dev_ = {}
 
     # -- Caffe public API -------------------------------------------------------
     def type(self):
@@ -155,9 +159,12 @@ class Layer(object):
         loss = 0.0
         for i, t in enumerate(top):                  # layer.hpp:471-479
             if i < len(self.loss_) and self.loss_[i]:
-                out = torch.empty(1, dtype=t.data.dtype, device=t.data.device)
+                out = self.loss_dev_.get(i)
+                if out is None or out.dtype != t.data.dtype:
+                    out = self.loss_dev_[i] = torch.zeros(1, dtype=t.data.dtype, device=t.data.device)
                 self._call("mms_dot", c_p(t.gpu_data()), c_p(t.gpu_diff()), t.count(), c_p(out.data_ptr()))
-                loss += float(out.item())
+                if not self.defer_loss_:
+                    loss += float(out.item())
         return loss
 
     def Backward(self, top, propagate_down, bottom):

@@ -100,3 +100,38 @@ class MMSNet(object):
         loss = self.Forward(with_loss)
         self.Backward()
         return loss
+
+    # -- CUDA-graph replay of the whole step ----------------------------------------------
+    # The step is ~15 short kernels; issued one by one from the host it is launch-bound
+    # (the reference has the same problem in the small: 2*N*mc host BLAS calls).  Recording
+    # ClearParamDiffs + Forward + Backward once and replaying the graph removes the host from
+    # the loop.  Blob storage must not be re-allocated between capture and replay.
+    def capture(self, with_loss=True, clear_diffs=True):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        self.sim.defer_loss_ = True
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # sizes scratch, fills the tensor-map cache
+                    if clear_diffs:
+                        self.ClearParamDiffs()
+                    self.ForwardBackward(with_loss)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                if clear_diffs:
+                    self.ClearParamDiffs()
+                self.ForwardBackward(with_loss)
+        finally:
+            self.sim.defer_loss_ = False
+        self._graph = graph
+        self._graph_with_loss = with_loss
+        return graph
+
+    def replay(self, read_loss=True):
+        """One recorded step.  Returns the loss (D2H of one scalar + sync) when asked to."""
+        self._graph.replay()
+        if read_loss and self._graph_with_loss:
+            return float(self.sim.loss_dev_[0].item())
+        return 0.0

@@ -15,12 +15,23 @@ from mms_answer_selection_b200 import _lib   # noqa: E402
 TOL = 1e-3
 
 
-def run(M, N, K, a_mn, b_mn, ksplit=1, mode=0, pad=0, seed=0):
+def tf32_exact(x):
+    """Round to the nearest TF32 value (10-bit mantissa), ties away from zero, like cvt.rna."""
+    i = x.view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def run(M, N, K, a_mn, b_mn, ksplit=1, mode=0, pad=0, seed=0, tma=False):
     g = torch.Generator(device="cuda").manual_seed(seed + M + 7 * N + 13 * K)
     lda = (M if a_mn else K) + pad
     ldb = (N if b_mn else K) + pad
     A = torch.rand(((K if a_mn else M), lda), device="cuda", generator=g) - 0.5
     B = torch.rand(((K if b_mn else N), ldb), device="cuda", generator=g) - 0.5
+    if tma:
+        A, B = tf32_exact(A), tf32_exact(B)
+        mode_flag = 0x100
+    else:
+        mode_flag = 0
     C0 = torch.rand((M, N + pad), device="cuda", generator=g) - 0.5
     C = C0.clone() if mode else torch.full((M, N + pad), 7.0, device="cuda")
     if mode == 2:
@@ -28,7 +39,7 @@ def run(M, N, K, a_mn, b_mn, ksplit=1, mode=0, pad=0, seed=0):
     h = _lib.Handle()
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     _lib.check(_lib.lib().mms_tc_gemm_f32(h.ptr, p(A), lda, a_mn, p(B), ldb, b_mn, p(C), N + pad, M, N, K,
-                                          ksplit, mode))
+                                          ksplit, mode | mode_flag))
     torch.cuda.synchronize()
     Am = (A[:, :M].T if a_mn else A[:, :K]).double()
     Bm = (B[:, :N].T if b_mn else B[:, :K]).double()
@@ -61,3 +72,24 @@ def test_tc_gemm_split_k_atomic_and_accumulate():
     assert run(300, 300, 20000, 1, 1, ksplit=8, mode=2) <= TOL
     assert run(300, 300, 4096, 0, 0, ksplit=1, mode=1) <= TOL
     assert run(128, 128, 10000, 1, 0, ksplit=7, mode=2) <= TOL
+
+
+# ---- the TMA-fed kernel: operands are TF32-exact, so the result must match fp64 to fp32 rounding
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("shape", [(128, 64, 32), (128, 256, 64), (200, 300, 300), (40, 40, 52), (4, 4, 4),
+                                   (333, 132, 76), (1024, 1024, 1024)])
+def test_tc_gemm_tma_majorness(shape, a_mn, b_mn):
+    M, N, K = shape
+    assert run(M, N, K, a_mn, b_mn, tma=True) <= 1e-5
+
+
+def test_tc_gemm_tma_split_k_and_accumulate():
+    assert run(300, 300, 20000, 1, 1, ksplit=8, mode=2, tma=True) <= 1e-4
+    assert run(300, 300, 4096, 0, 0, ksplit=1, mode=1, tma=True) <= 1e-4
+    assert run(128, 128, 10000, 1, 0, ksplit=7, mode=2, tma=True) <= 1e-4
+
+
+def test_tc_gemm_tma_unaligned_falls_back_to_staged_kernel():
+    # leading dimensions that are not 16-byte multiples cannot be described to TMA
+    assert run(150, 90, 50, 0, 0, pad=1, tma=True) <= 1e-5

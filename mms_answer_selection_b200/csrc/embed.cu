@@ -74,16 +74,20 @@ embed_forward_scalar(const T* __restrict__ idx, const T* __restrict__ W, const T
   }
 }
 
-constexpr int kBwdRows = 64;      // token rows per CTA
-constexpr int kBwdThreads = 256;
+constexpr int kBwdMaxRows = 64;   // token rows per CTA (upper bound; small batches use fewer rows per CTA)
+constexpr int kBwdThreads = 128;
 
+// One CTA owns `rows_per_cta` consecutive token rows; thread c walks column c (and c + 128, ...)
+// down the tile.  The gradient values of up to 8 rows are loaded before the first is used, so the
+// loads overlap; runs of equal ids (the pad id in centre-padded sentences) are merged into one
+// atomic per run.
 template <typename T>
 __global__ void __launch_bounds__(kBwdThreads)
 embed_backward_runs(const T* __restrict__ idx, const T* __restrict__ dtop, T* __restrict__ dW,
-                    T* __restrict__ dbias, long long M, int D, int V, int* fault) {
-  __shared__ int s_idx[kBwdRows];
-  const long long row0 = (long long)blockIdx.x * kBwdRows;
-  const int rows = (int)mms_min<long long>(kBwdRows, M - row0);
+                    T* __restrict__ dbias, long long M, int D, int V, int rows_per_cta, int* fault) {
+  __shared__ int s_idx[kBwdMaxRows];
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  const int rows = (int)mms_min<long long>(rows_per_cta, M - row0);
   for (int r = threadIdx.x; r < rows; r += kBwdThreads) {
     const int index = static_cast<int>(idx[row0 + r]);
     const bool ok = index >= 0 && index < V;
@@ -94,16 +98,24 @@ embed_backward_runs(const T* __restrict__ idx, const T* __restrict__ dtop, T* __
   for (int c = threadIdx.x; c < D; c += kBwdThreads) {
     T run = T(0), col = T(0);
     int cur = -1;
-    for (int r = 0; r < rows; ++r) {
-      const int index = s_idx[r];
-      const T g = __ldg(dtop + (size_t)(row0 + r) * D + c);
-      col += g;
-      if (index != cur) {
-        if (cur >= 0 && dW) atomicAdd(dW + (size_t)cur * D + c, run);
-        cur = index;
-        run = T(0);
+    const T* src = dtop + (size_t)row0 * D + c;
+    for (int rb = 0; rb < rows; rb += 8) {
+      T g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = (rb + j < rows) ? __ldg(src + (size_t)(rb + j) * D) : T(0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (rb + j < rows) {
+          const int index = s_idx[rb + j];
+          col += g[j];
+          if (index != cur) {
+            if (cur >= 0 && dW) atomicAdd(dW + (size_t)cur * D + c, run);
+            cur = index;
+            run = T(0);
+          }
+          run += g[j];
+        }
       }
-      run += g;
     }
     if (cur >= 0 && dW) atomicAdd(dW + (size_t)cur * D + c, run);
     if (dbias) atomicAdd(dbias + c, col);
@@ -146,11 +158,14 @@ int mms_embed_backward_impl(mms_context* ctx, const T* idx, const T* dtop, T* dW
   MMS_REQUIRE(M >= 0 && D > 0 && V > 0, MMS_E_INVALID, "bad size");
   if (M == 0 || (!dW && !dbias)) return 0;
   MMS_REQUIRE(idx && dtop, MMS_E_INVALID, "null pointer");
-  const long long grid = (M + kBwdRows - 1) / kBwdRows;
+  // enough CTAs to cover the machine about four times over, 8..64 rows each
+  const long long want = mms_ceil_div(M, 4LL * ctx->sm_count);
+  const int rows_per_cta = (int)mms_min<long long>(kBwdMaxRows, mms_max<long long>(8, (want + 7) / 8 * 8));
+  const long long grid = (M + rows_per_cta - 1) / rows_per_cta;
   MMS_REQUIRE(grid <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "too many rows");
   { MmsKernelScope ks_(ctx, "embed_backward_runs");
     embed_backward_runs<T><<<(unsigned)grid, kBwdThreads, 0, ctx->stream>>>(idx, dtop, dW, dbias, M, D, V,
-                                                                         ctx->fault_flag); }
+                                                                         rows_per_cta, ctx->fault_flag); }
   MMS_LAUNCH_CHECK();
   return 0;
 }

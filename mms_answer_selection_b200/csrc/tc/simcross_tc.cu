@@ -134,6 +134,14 @@ int mms_tc_simcross2_backward(mms_context* ctx, const float* q, const float* a, 
       TcGemmArgs g = tc_gemm_args(buf, Dp, 0, Mr, Dp, 0, dqc, D, nc * Lq, D, D);
       g.nseg = mc; g.segA = sU1; g.segB = (long long)D * Dp;
       g.operands_tf32 = 1;
+      // a small batch has too few output tiles to fill the GPU: split the reduction over the measures
+      // (atomic accumulation into a zeroed dq) until there is about one tile per SM
+      const int tiles = mms_ceil_div(nc * Lq, 128) * mms_ceil_div(D, 256);
+      const int split = mms_min(mc, ctx->sm_count / mms_max(tiles, 1));
+      if (split > 1) {
+        MMS_CUDA(cudaMemsetAsync(dqc, 0, sizeof(float) * (size_t)nc * Lq * D, ctx->stream));
+        g.ksplit = split; g.mode = TC_ATOMIC;
+      }
       MMS_TRY(mms_tc_gemm(ctx, g));
     }
     MMS_TRY(gemm_T(ctx, qr, Mr, buf, nc * Lq, D, Dp, mc));

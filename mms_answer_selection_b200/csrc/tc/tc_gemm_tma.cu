@@ -13,8 +13,11 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <map>
 #include <tuple>
+#include <vector>
 
 #include "../mms_common.cuh"
 #include "tc_gemm.cuh"
@@ -53,6 +56,14 @@ struct Tile {
   int z1, z2, m0, n0, ibeg, nk;
 };
 
+// Optional per-CTA trace (MMS_TC_TRACE=1 in the environment): globaltimer stamps at 8 checkpoints.
+__device__ __forceinline__ void trace(long long* tr, int slot) {
+  if (!tr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  tr[(size_t)blockIdx.x * 8 + slot] = (long long)t;
+}
+
 __device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry& q, unsigned t, int sps) {
   Tile tl;
   const int n_tile = t % q.n_tiles; t /= q.n_tiles;
@@ -68,10 +79,71 @@ __device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry&
   return tl;
 }
 
+// Epilogue store of one 32 x 32 chunk that a warp has staged in shared memory.  Thread (lane) owns the
+// 4 columns cc = 4*(lane%8) of rows r0 + 4*rr, r0 = lane/8: every warp instruction covers 4 whole
+// 128-byte row segments.  MODE is resolved outside the row loop so that the loop body is a handful
+// of instructions (the epilogue is instruction-bound, not bandwidth-bound, at these tile counts).
+template <int MODE, bool ROUND, bool ADD>
+__device__ __forceinline__ void epi_store_vec(const float* sp, float* p, long long pstep, const float* ap,
+                                              long long astep, bool add_vec, int rows_left) {
+  float4 o[8];
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) o[rr] = *reinterpret_cast<const float4*>(sp + rr * 4 * kEpiLd);
+  if (ADD) {
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      if (rr * 4 < rows_left) {
+        const float* a = ap + rr * astep;
+        float4 b;
+        if (add_vec) b = __ldg(reinterpret_cast<const float4*>(a));
+        else b = make_float4(__ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(a + 3));
+        o[rr].x += b.x; o[rr].y += b.y; o[rr].z += b.z; o[rr].w += b.w;
+      }
+    }
+  }
+  if (ROUND) {
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      o[rr].x = to_tf32(o[rr].x); o[rr].y = to_tf32(o[rr].y); o[rr].z = to_tf32(o[rr].z); o[rr].w = to_tf32(o[rr].w);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    float4* dst = reinterpret_cast<float4*>(p + rr * pstep);
+    if (rr * 4 < rows_left) {
+      if (MODE == TC_STORE) {
+        *dst = o[rr];
+      } else if (MODE == TC_ACCUM) {
+        float4 c = *dst;
+        c.x += o[rr].x; c.y += o[rr].y; c.z += o[rr].z; c.w += o[rr].w;
+        *dst = c;
+      } else {
+        atomicAdd(dst, o[rr]);
+      }
+    }
+  }
+}
+
+// Ragged / unaligned tiles: element-wise, any mode.
+__device__ __noinline__ void epi_store_scalar(const float* sp, float* p, long long pstep, const float* ap,
+                                              long long astep, bool round_out, int rows_left, int nvalid, int mode) {
+  for (int rr = 0; rr * 4 < rows_left; ++rr) {
+    for (int j = 0; j < nvalid; ++j) {
+      float o = sp[rr * 4 * kEpiLd + j];
+      if (ap) o += __ldg(ap + rr * astep + j);
+      if (round_out) o = to_tf32(o);
+      float* d = p + rr * pstep + j;
+      if (mode == TC_STORE) *d = o;
+      else if (mode == TC_ACCUM) *d += o;
+      else atomicAdd(d, o);
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const TcGemmArgs g, const Geometry q) {
+                   const TcGemmArgs g, const Geometry q, long long* tr) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 16384 + q.b_bytes;
@@ -81,6 +153,7 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sps = (g.K + kBK - 1) / kBK;
   const int BN = q.BN, stages = q.stages;
+  if (threadIdx.x == 0) trace(tr, 0);
 
   if (warp == 1) {
     if (lane == 0) {
@@ -99,6 +172,7 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
+  if (threadIdx.x == 0) trace(tr, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one lane)
@@ -134,6 +208,7 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
         }
       }
+      trace(tr, 2);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -151,6 +226,7 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const int s = it % stages;
           mbar_wait(&sm->full[s], (it / stages) & 1);
           tc_fence_after();
+          if (it == 0) trace(tr, 3);
           const uint32_t a_base = smem_u32(ring + s * stage_bytes);
           const uint32_t b_base = a_base + 16384;
 #pragma unroll
@@ -163,11 +239,16 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         mma_commit(&sm->acc_full[buf]);
       }
+      trace(tr, 4);
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (TMEM lane quarter = warp % 4)
     const int quarter = warp & 3;
+    // which specialised store loop serves this launch (-1: only the element-wise one)
+    int fast_kind = -1;
+    if (g.mode == TC_STORE) fast_kind = (g.c_add && g.round_out) ? -1 : g.c_add ? 2 : g.round_out ? 1 : 0;
+    else if (!g.c_add && !g.round_out) fast_kind = g.mode == TC_ATOMIC ? 3 : 4;
     int tcount = 0;
     for (unsigned t = blockIdx.x; t < q.total_tiles; t += gridDim.x, ++tcount) {
       const Tile tl = decode_tile(g, q, t, sps);
@@ -176,7 +257,9 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const float* Cadd = g.c_add ? g.c_add + tl.z1 * g.s_add1 + tl.z2 * g.s_add2 : nullptr;
       mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1);
       tc_fence_after();
+      if (tcount == 0 && threadIdx.x == 64) trace(tr, 5);
       const bool c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (g.ldc % 4 == 0) && (tl.n0 % 4 == 0);
+      const bool add_vec = Cadd && ((reinterpret_cast<uintptr_t>(Cadd) & 15) == 0) && (g.ld_add % 4 == 0);
       const int row_tm = tl.m0 + quarter * 32 + lane;           // the accumulator row this thread reads from TMEM
       const float rs = (g.out_rowscale && row_tm < g.M) ? __ldg(g.out_rowscale + row_tm) : 1.f;
       const uint32_t acc = tmem + buf * BN + ((uint32_t)(quarter * 32) << 16);
@@ -201,49 +284,25 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               make_float4(v[i4 * 4] * rs, v[i4 * 4 + 1] * rs, v[i4 * 4 + 2] * rs, v[i4 * 4 + 3] * rs);
         __syncwarp();
         const int cc = (lane & 7) * 4;                       // 4 columns of this thread
+        const int r0 = lane >> 3;                            // first of its 8 rows (stride 4)
         const int n = tl.n0 + c0 + cc;
-        const bool col_ok = n < g.N && c0 + cc < BN;
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int r = rr * 4 + (lane >> 3);
-          if (r < warp_rows && col_ok) {
-            const int row = tl.m0 + quarter * 32 + r;
-            float4 o = *reinterpret_cast<const float4*>(stage + r * kEpiLd + cc);
-            const bool full = n + 3 < g.N;
-            if (Cadd) {
-              const float* ap = Cadd + (long long)row * g.ld_add + n;
-              o.x += __ldg(ap);
-              if (n + 1 < g.N) o.y += __ldg(ap + 1);
-              if (n + 2 < g.N) o.z += __ldg(ap + 2);
-              if (n + 3 < g.N) o.w += __ldg(ap + 3);
-            }
-            if (g.round_out) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
-            float* p = C + (long long)row * g.ldc + n;
-            if (g.mode == TC_STORE) {
-              if (c_vec && full) {
-                *reinterpret_cast<float4*>(p) = o;
-              } else {
-                p[0] = o.x;
-                if (n + 1 < g.N) p[1] = o.y;
-                if (n + 2 < g.N) p[2] = o.z;
-                if (n + 3 < g.N) p[3] = o.w;
-              }
-            } else if (g.mode == TC_ACCUM) {
-              p[0] += o.x;
-              if (n + 1 < g.N) p[1] += o.y;
-              if (n + 2 < g.N) p[2] += o.z;
-              if (n + 3 < g.N) p[3] += o.w;
-            } else {
-              if (c_vec && full) {
-                atomicAdd(reinterpret_cast<float4*>(p), o);
-              } else {
-                atomicAdd(p, o.x);
-                if (n + 1 < g.N) atomicAdd(p + 1, o.y);
-                if (n + 2 < g.N) atomicAdd(p + 2, o.z);
-                if (n + 3 < g.N) atomicAdd(p + 3, o.w);
-              }
-            }
+        const int nvalid = (c0 + cc < BN) ? max(0, min(4, g.N - n)) : 0;
+        const int rows_left = warp_rows - r0;
+        const long long row0 = tl.m0 + quarter * 32 + r0;
+        float* p = C + row0 * g.ldc + n;
+        const float* ap = Cadd ? Cadd + row0 * g.ld_add + n : nullptr;
+        const float* sp = stage + r0 * kEpiLd + cc;
+        const long long pstep = 4 * g.ldc, astep = 4 * g.ld_add;
+        if (nvalid == 4 && c_vec && fast_kind >= 0) {
+          switch (fast_kind) {
+            case 0: epi_store_vec<TC_STORE, false, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            case 1: epi_store_vec<TC_STORE, true, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            case 2: epi_store_vec<TC_STORE, false, true>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            case 3: epi_store_vec<TC_ATOMIC, false, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            default: epi_store_vec<TC_ACCUM, false, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
           }
+        } else if (nvalid > 0 && rows_left > 0) {
+          epi_store_scalar(sp, p, pstep, ap, astep, g.round_out != 0, rows_left, nvalid, g.mode);
         }
         __syncwarp();
       }
@@ -251,11 +310,13 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->acc_empty[buf]);
     }
+    if (threadIdx.x == 64) trace(tr, 6);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, q.tmem_cols);
+  if (threadIdx.x == 0) trace(tr, 7);
 }
 
 // ---- tf32 rounding / repacking pass --------------------------------------------------------
@@ -407,7 +468,7 @@ int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& a) {
   MMS_TRY(make_map(ctx, &mapB, a.B, a.ldb, a.b_mn != 0, a.N, a.K, a.b_mn ? 32 : BN, a.sB1, a.sB2, a.segB, a.nb1,
                    a.nb2, a.nseg));
 
-  typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const TcGemmArgs, const Geometry);
+  typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const TcGemmArgs, const Geometry, long long*);
   static const kernel_t kernels[4] = {tc_gemm_tma_kernel<false, false>, tc_gemm_tma_kernel<false, true>,
                                       tc_gemm_tma_kernel<true, false>, tc_gemm_tma_kernel<true, true>};
   static bool configured = false;
@@ -418,8 +479,35 @@ int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& a) {
   }
   const kernel_t kernel = kernels[(a.a_mn ? 2 : 0) + (a.b_mn ? 1 : 0)];
   const unsigned grid = (unsigned)mms_min<long long>(total, ctx->sm_count);
+  static const bool tracing = getenv("MMS_TC_TRACE") != nullptr;
+  long long* tr = nullptr;
+  if (tracing) {
+    MMS_CUDA(cudaMalloc(&tr, sizeof(long long) * 8 * grid));
+    MMS_CUDA(cudaMemset(tr, 0, sizeof(long long) * 8 * grid));
+  }
   { MmsKernelScope ks_(ctx, "tc_gemm_tma_kernel");
-    kernel<<<grid, kThreads, smem, ctx->stream>>>(mapA, mapB, a, q); }
+    kernel<<<grid, kThreads, smem, ctx->stream>>>(mapA, mapB, a, q, tr); }
   MMS_LAUNCH_CHECK();
+  if (tracing) {
+    std::vector<long long> h((size_t)8 * grid);
+    MMS_CUDA(cudaStreamSynchronize(ctx->stream));
+    MMS_CUDA(cudaMemcpy(h.data(), tr, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(tr);
+    long long t0 = h[0];
+    for (unsigned b = 0; b < grid; ++b) t0 = mms_min(t0, h[(size_t)b * 8]);
+    static const char* names[8] = {"entry", "setup", "tma_issued", "first_full", "mma_issued", "acc_ready",
+                                   "epi_done", "exit"};
+    fprintf(stderr, "[tc trace] M %d N %d K %d nseg %d batch %dx%d ksplit %d a_mn %d b_mn %d BN %d stages %d tiles %u grid %u | ns since first entry (min/avg/max over CTAs):",
+            a.M, a.N, a.K, a.nseg, a.nb1, a.nb2, a.ksplit, a.a_mn, a.b_mn, BN, stages, q.total_tiles, grid);
+    for (int s = 0; s < 8; ++s) {
+      long long mn = 1LL << 62, mx = 0; double sum = 0;
+      for (unsigned b = 0; b < grid; ++b) {
+        const long long v = h[(size_t)b * 8 + s] - t0;
+        mn = mms_min(mn, v); mx = mms_max(mx, v); sum += (double)v;
+      }
+      fprintf(stderr, " %s %lld/%.0f/%lld", names[s], mn, sum / grid, mx);
+    }
+    fprintf(stderr, "\n");
+  }
   return 0;
 }

@@ -17,6 +17,7 @@
 #include "caffe/layer_factory.hpp"
 #include "caffe/layers/pair_rank_loss_layer.hpp"
 
+#ifndef MMS_DROPIN
 namespace caffe {
 // pair_rank_loss_layer.cpp:86-87 has no STUB_GPU, so a CPU_ONLY link lacks the
 // Forward_gpu/Backward_gpu bodies its header declares; supply the stubs here.
@@ -24,6 +25,12 @@ STUB_GPU(PairRankLossLayer);
 template class PairRankLossLayer<float>;
 template class PairRankLossLayer<double>;
 }  // namespace caffe
+#else
+// Built a second time with -DMMS_DROPIN (no CPU_ONLY) into oracle/_ref/libmms_dropin.so: the same
+// harness then drives the PRODUCT's drop-in layers (mms_answer_selection_b200/caffe_layers/) through
+// the reference's Layer API in Caffe::GPU mode -- see dropin_runtime.cpp.
+#include <cuda_runtime.h>
+#endif
 
 namespace {
 
@@ -96,8 +103,17 @@ extern "C" {
 
 const char* mmsref_last_error() { return g_last_error.c_str(); }
 
+#ifndef MMS_DROPIN
 void mmsref_set_blas_threads(int n) { openblas_set_num_threads(n); }
 int mmsref_get_blas_threads() { return openblas_get_num_threads(); }
+int mmsref_is_dropin() { return 0; }
+#else
+void mmsref_set_blas_threads(int) {}
+int mmsref_get_blas_threads() { return 0; }
+int mmsref_is_dropin() { return 1; }
+// 0 = Caffe::CPU (every drop-in layer then aborts: there is no CPU path), 1 = Caffe::GPU
+void mmsref_set_mode(int gpu) { caffe::Caffe::set_mode(gpu ? caffe::Caffe::GPU : caffe::Caffe::CPU); }
+#endif
 
 void* mmsref_create(const char* type, int dtype) {
   SessionBase* s = dtype == 0 ? static_cast<SessionBase*>(new Session<float>())
@@ -273,6 +289,9 @@ int mmsref_time(void* h, int iters, int do_backward, const int* propagate_down, 
         S->layer->Forward(S->bottom, S->top);
         if (do_backward) S->layer->Backward(S->top, pd, S->bottom);
       }
+#ifdef MMS_DROPIN
+      cudaDeviceSynchronize();
+#endif
       auto t1 = std::chrono::steady_clock::now();
       *ms_out = std::chrono::duration<double, std::milli>(t1 - t0).count() / iters;
     });

@@ -19,22 +19,33 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libmms_ref.so")
+DROPIN_SO = os.path.join(_HERE, "_ref", "libmms_dropin.so")
+PRODUCT_SO = os.path.join(os.path.dirname(_HERE), "mms_answer_selection_b200", "libmms_b200.so")
 ORACLE_SO = os.path.join(_HERE, "_build", "libmms_oracle.so")
 
 _ref = None
+_dropin = None
 _oracle = None
 
 _NP = {0: np.float32, 1: np.float64}
 _KIND = {"bottom": 0, "top": 1, "blob": 2}
 
 
-def build(ref=True, oracle=True):
-    """Build the checkers (a no-op for ``_ref`` when /root/reference is absent)."""
+def build(ref=True, oracle=True, dropin=None):
+    """Build the checkers (a no-op for ``_ref`` when /root/reference is absent).
+
+    ``dropin`` (default: same as ``ref``, provided the product library has been built) also builds
+    ``_ref/libmms_dropin.so``: the reference's Layer API / Blob / SyncedMemory in GPU mode linked with
+    the product's C++ drop-in layers (mms_answer_selection_b200/caffe_layers/)."""
     targets = []
     if oracle:
         targets.append("oracle")
     if ref:
         targets.append("ref")
+    if dropin is None:
+        dropin = ref
+    if dropin and os.path.exists(PRODUCT_SO):
+        targets.append("dropin")
     subprocess.run(["make", "-C", _HERE, "-s"] + targets, check=True)
 
 
@@ -42,13 +53,12 @@ def ref_available():
     return os.path.exists(REF_SO)
 
 
-def ref_lib():
-    global _ref
-    if _ref is None:
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(
-                REF_SO + " missing: run `make -C oracle ref` where /root/reference exists")
-        L = ctypes.CDLL(REF_SO)
+def dropin_available():
+    return os.path.exists(DROPIN_SO)
+
+
+def _bind(path):
+        L = ctypes.CDLL(path)
         L.mmsref_last_error.restype = ctypes.c_char_p
         L.mmsref_create.restype = ctypes.c_void_p
         L.mmsref_create.argtypes = [ctypes.c_char_p, ctypes.c_int]
@@ -68,8 +78,29 @@ def ref_lib():
         L.mmsref_backward.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.mmsref_time.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.mmsref_set_blas_threads.argtypes = [ctypes.c_int]
-        _ref = L
+        return L
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(
+                REF_SO + " missing: run `make -C oracle ref` where /root/reference exists")
+        _ref = _bind(REF_SO)
     return _ref
+
+
+def dropin_lib():
+    """The reference's Layer API + Blob + SyncedMemory (GPU build) hosting the PRODUCT's layers."""
+    global _dropin
+    if _dropin is None:
+        if not os.path.exists(DROPIN_SO):
+            raise FileNotFoundError(
+                DROPIN_SO + " missing: run `make -C oracle dropin` where /root/reference exists")
+        _dropin = _bind(DROPIN_SO)
+        _dropin.mmsref_set_mode.argtypes = [ctypes.c_int]
+    return _dropin
 
 
 class RefError(RuntimeError):
@@ -86,8 +117,10 @@ class RefLayer(object):
     bias_filler.type, weight_source``.
     """
 
+    _lib = staticmethod(lambda: ref_lib())
+
     def __init__(self, type_, bottoms, params=None, dtype=np.float32, num_top=1, seed=1701):
-        self.L = ref_lib()
+        self.L = self._lib()
         self.np = np.dtype(dtype)
         self.dt = 0 if self.np == np.float32 else 1
         self.h = self.L.mmsref_create(type_.encode(), self.dt)
@@ -160,6 +193,12 @@ class RefLayer(object):
         ms = ctypes.c_double(0)
         self._ck(self.L.mmsref_time(self.h, iters, int(backward), arr, ctypes.byref(ms)))
         return ms.value
+
+
+class DropinLayer(RefLayer):
+    """Same driver, but the layer behind ``LayerRegistry::CreateLayer`` is the product's C++ drop-in
+    class running through libmms_b200.so on the GPU (Caffe::GPU mode)."""
+    _lib = staticmethod(lambda: dropin_lib())
 
 
 def set_ref_blas_threads(n):

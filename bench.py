@@ -5,10 +5,14 @@
 
 A "step" is one forward+backward pass of the hot path (Embed x2 -> SimCross mode 2 ->
 loss plumbing -> SimCross backward -> Embed scatter-add) over one batch of synthetic
-TREC-QA-shaped QA pairs.  Default workload: BASELINE.json configs[1] (C2: batch 50,
-q/a length 40, 300-d embeddings, mesure_count 4, V = 60002).  With N > 1 every rank runs
-its own batch (weak scaling, as each Caffe solver does) and the flat gradient buffer is
-all-reduced over NCCL and scaled by 1/N inside the step.
+TREC-QA-shaped QA pairs.  Workload by N, as BASELINE.json's configs assign them:
+  N = 1      configs[1] (C2): the reference's batch of 50 QA pairs per step, q/a length 40,
+             300-d embeddings, mesure_count 4, V = 60002 (an epoch is 1069 such steps);
+  N = 2,4,8  configs[2] (C3): a GLOBAL batch of 4096 QA pairs sharded over the ranks (strong
+             scaling), the flat gradient buffer all-reduced over NCCL and scaled by 1/N inside
+             the step.
+--workload overrides.  The line also carries `extra`: candidate scores/s (configs[3], candidates
+sharded over the ranks), and at N = 1 the C3 and C5 single-GPU figures.
 
 Prints ONE JSON line (rank 0).  `value` = QA pairs/s with inputs resident in HBM;
 `e2e` = the same through the public API with pinned-host inputs, H2D of the step's token
@@ -37,10 +41,20 @@ def flops_per_pair(L, D, mc):
     return mc * (6.0 * L * D * D + 8.0 * L * L * D)
 
 
-def workload_config(name):
+def workload_config(name, world=1):
+    """Per-rank configuration: C3 fixes the GLOBAL batch (4096), so a rank gets 4096 / world pairs."""
     from mms_answer_selection_b200 import synth
     c = dict(synth.CONFIGS[name])
+    c["global_N"] = c["N"]
+    if name == "c3":
+        c["N"] = max(1, c["N"] // world)
+    else:
+        c["global_N"] = c["N"] * world
     return c
+
+
+def pick_workload(args, world):
+    return args.workload or ("c2" if world == 1 else "c3")
 
 
 # ---------------------------------------------------------------------------- reference arm
@@ -115,13 +129,14 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = workload_config(args.workload)
+    wl = pick_workload(args, args.gpus)
+    cfg = workload_config(wl, args.gpus)
     r = time_reference(cfg, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, cfg), "pairs_per_step": r["pairs"]},
+        "scaling": "strong" if wl == "c3" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(wl, cfg), "pairs_per_step": r["pairs"]},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -132,9 +147,9 @@ def main_reference(args):
 
 
 def workload_name(name, cfg):
-    return ("%s: synthetic TREC-QA-shaped batch, %d QA pairs/step/GPU, q/a len %d, %d-d embeddings, "
+    return ("%s: synthetic TREC-QA-shaped batch, %d QA pairs/step/GPU (%d global), q/a len %d, %d-d embeddings, "
             "mesure_count %d, V=%d; Embed x2 -> SimCross(mode 2) fwd+bwd"
-            % (name.upper(), cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]))
+            % (name.upper(), cfg["N"], cfg["global_N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]))
 
 
 # ---------------------------------------------------------------------------- clocks
@@ -197,7 +212,8 @@ def main_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = workload_config(args.workload)
+    wl = pick_workload(args, world)
+    cfg = workload_config(wl, world)
     N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
 
     d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V, seed=synth.SEED + rank)
@@ -306,9 +322,10 @@ def main_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core contractions, fp32 accumulate)",
+        "scaling": "strong" if wl == "c3" else "weak", "vs_baseline": None,
+        "dtype": "f32 (TF32 tensor-core contractions, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, cfg), "parallelism": "dp%d" % world,
+        "config": {"workload": workload_name(wl, cfg), "parallelism": "dp%d" % world,
                    "l2": "256 MiB L2 flush between timed steps (inputs+table < L2)",
                    "launch": "step recorded as one CUDA graph (%d kernels of libmms_b200.so per step)" % launches_per_step,
                    "grad_exchange": "NCCL all-reduce of the flat gradient buffer + 1/N scale" if world > 1 else "none"},
@@ -320,6 +337,8 @@ def main_ours(args):
         "kernels_ms_per_step": {k: round(ms / prof_steps, 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
         "kernel_step_ms_sum": step_ms_prof,
     }
+    if not args.no_extra:
+        line["extra"] = extras(world, rank, flush)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = time_reference(cfg, steps=3, warmup=1, budget_s=20.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
@@ -329,6 +348,112 @@ def main_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _max_ms(ms, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _time_ms(fn, iters, flush, world):
+    """CUDA-event time of `iters` calls (L2 flushed before each, untimed), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = []
+    for _ in range(iters):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return _max_ms(sum(a.elapsed_time(b) for a, b in evs), world) / iters
+
+
+def extras(world, rank, flush):
+    """The other headline figures of BASELINE.json, measured briefly (a few iterations each)."""
+    import ctypes
+
+    import torch
+
+    import mms_answer_selection_b200 as mms
+    from mms_answer_selection_b200 import _lib, layers, synth
+    from mms_answer_selection_b200.blob import Blob
+    out = {}
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    # ---- configs[3]: reranking, 1k queries x 1M candidates, K = 1024, candidates sharded over the ranks
+    c4 = synth.CONFIGS["c4"]
+    Nq, K = c4["Nq"], c4["K"]
+    Nc_local = c4["Nc"] // world
+    g = torch.Generator(device="cuda").manual_seed(synth.SEED + rank)
+    Q = torch.randn((Nq, K), device="cuda", generator=g) / K ** 0.5
+    C = torch.randn((Nc_local, K), device="cuda", generator=g) / K ** 0.5
+    W = (torch.rand((K, K), device="cuda", generator=g) * 2 - 1) * (3.0 / K) ** 0.5
+    QW = torch.empty((Nq, K), device="cuda")
+    scores = torch.empty((Nq, Nc_local), device="cuda")
+    h = _lib.Handle()
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def rerank():
+        _lib.check(_lib.lib().mms_rerank_scores_f32(h.ptr, p(Q), p(C), p(W), p(QW), p(scores), Nq, Nc_local, K, K))
+    ms = _time_ms(rerank, 3, flush, world)
+    flops = 2.0 * Nq * K * K + 2.0 * Nq * Nc_local * K
+    out["candidate_scoring"] = {
+        "workload": "C4: %d queries x %d candidates (%d per GPU), K=%d, scores = (Q W) C^T, all scores written"
+                    % (Nq, Nc_local * world, Nc_local, K),
+        "candidate_scores_per_sec": Nq * Nc_local * world / (ms / 1e3), "ms": ms,
+        "tflops_per_gpu": flops / (ms / 1e3) / 1e12}
+    del C, scores, Q, QW, W
+    torch.cuda.empty_cache()
+    if world > 1:
+        return out
+    # ---- configs[2] on ONE GPU (the base of the strong-scaling series the N > 1 runs report)
+    c3 = synth.CONFIGS["c3"]
+    d = synth.make_qa_batch(N=c3["N"], L=c3["L"], D=c3["D"], mc=c3["mc"], V=c3["V"])
+    net = mms.MMSNet(c3["N"], c3["L"], c3["D"], c3["mc"], c3["V"])
+    net.set_params(d["W"], d["b"], d["M"], d["B"])
+    net.set_inputs(d["idx_q"], d["idx_a"])
+    net.set_upstream_gradient(d["dS"])
+    net.capture(with_loss=True, clear_diffs=True)
+    ms = _time_ms(lambda: net.replay(read_loss=False), 5, flush, 1)
+    fl = c3["N"] * flops_per_pair(c3["L"], c3["D"], c3["mc"])
+    out["c3_single_gpu"] = {"workload": "C3: 4096 QA pairs/step on one GPU, D=300, mc=4 (fwd+bwd, graph replay)",
+                            "qa_pairs_per_sec": c3["N"] / (ms / 1e3), "ms_per_step": ms,
+                            "algorithmic_tflops": fl / (ms / 1e3) / 1e12}
+    del net, d
+    torch.cuda.empty_cache()
+    # ---- configs[4]: 4 modalities, SimMatrix 1024 x 1024, batch 16384, PairRankLoss on (s+, s-)
+    c5 = synth.CONFIGS["c5"]
+    N5, K1, K2, nm = c5["N"], c5["K1"], c5["K2"], c5["modalities"]
+    mods = []
+    for m in range(nm):
+        qv, av, Wv = synth.make_sentence_vectors(N5, K1, K2, seed=synth.SEED + m)
+        lay = layers.SimMatrixLayer(layers.LayerParameter("SimMatrix", sim_matrix_param=dict(
+            weight_filler=dict(type="xavier"))))
+        bq, ba, top = Blob((N5, K1)), Blob((N5, K2)), Blob(())
+        bq.set_cpu_data(qv); ba.set_cpu_data(av)
+        lay.SetUp([bq, ba], [top])
+        lay.blobs[0].set_cpu_data(Wv)
+        top.diff.fill_(1.0 / N5)
+        mods.append((lay, bq, ba, top))
+
+    def c5_step():
+        for lay, bq, ba, top in mods:
+            lay.blobs[0].diff.zero_()
+            lay.Forward([bq, ba], [top])
+            lay.Backward([top], [True, True], [bq, ba])
+    ms = _time_ms(c5_step, 3, flush, 1)
+    out["c5_multimodal"] = {"workload": "C5: %d modalities x SimMatrix %dx%d, batch %d, fwd+bwd (dW, dq, da)" % (nm, K1, K2, N5),
+                            "qa_pairs_per_sec": N5 / (ms / 1e3), "ms_per_step": ms,
+                            "algorithmic_tflops": nm * 6.0 * N5 * K1 * K2 / (ms / 1e3) / 1e12}
+    return out
 
 
 def roofline_for(name, rec, prof, steps, cfg, peaks):
@@ -365,8 +490,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

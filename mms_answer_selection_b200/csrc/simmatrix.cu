@@ -62,36 +62,60 @@ inline int ew_grid(mms_context* ctx, long long n) {
 
 }  // namespace
 
-// float + MMS_MATH_TF32: the three contractions run on tcgen05 (tc/tc_gemm.cu); diag(ds) is fused
-// into the operand staging, so no scaled copies of q / a are materialised.
+// float + MMS_MATH_TF32: the three contractions run on the TMA-fed tcgen05 GEMM (tc/tc_gemm_tma.cu).
+// Its operands must be TF32-exact, so q, a and W pass through one rounding launch into the scratch
+// buffer (leading dimensions padded to 4 floats); diag(ds) is folded into that pass, so the scaled
+// copies ds o a and ds o q cost nothing extra.
 inline bool use_tc(mms_context* ctx, const float*) { return ctx->math == MMS_MATH_TF32; }
 inline bool use_tc(mms_context*, const double*) { return false; }
 
-inline int tc_T(mms_context* ctx, const float* q, const float* W, float* Tm, int N, int K1, int K2,
-                const float* rowscale) {
-  TcGemmArgs g = tc_gemm_args(q, K1, 0, W, K2, 1, Tm, K2, N, K2, K1);   // A K-major, B(n=c,k=t)=W[t][c] MN-major
-  g.a_rowscale = rowscale;
+inline int tc_forward(mms_context* ctx, const float* q, const float* W, float* Tm, int N, int K1, int K2) {
+  const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * ((size_t)N * K1p + (size_t)K1 * K2p), &sp));
+  float* qr = static_cast<float*>(sp);
+  float* Wr = qr + (size_t)N * K1p;
+  const RoundJob jobs[2] = {{q, qr, N, K1, K1, K1p, nullptr}, {W, Wr, K1, K2, K2, K2p, nullptr}};
+  MMS_TRY(mms_tf32_round(ctx, jobs, 2));
+  TcGemmArgs g = tc_gemm_args(qr, K1p, 0, Wr, K2p, 1, Tm, K2, N, K2, K1);   // B(n=c,k=t) = W[t][c]: MN-major
+  g.operands_tf32 = 1;
   return mms_tc_gemm(ctx, g);
 }
-inline int tc_T(mms_context*, const double*, const double*, double*, int, int, int, const double*) { return MMS_E_UNSUPPORTED; }
+inline int tc_forward(mms_context*, const double*, const double*, double*, int, int, int) { return MMS_E_UNSUPPORTED; }
 
-inline int tc_dW(mms_context* ctx, const float* q, const float* a, const float* ds, float* dW, int N, int K1, int K2) {
-  // dW[r][c] += sum_n q[n][r] * ds[n] * a[n][c]: both operands MN-major (rows = sample n = K index)
-  TcGemmArgs g = tc_gemm_args(q, K1, 1, a, K2, 1, dW, K2, K1, K2, N, TC_ATOMIC);
-  g.b_rowscale = ds;
-  const int tiles = mms_ceil_div(K1, 128) * mms_ceil_div(K2, 256);
-  g.ksplit = mms_max(1, mms_min(mms_ceil_div(ctx->sm_count, tiles), mms_ceil_div(N, 256)));
-  return mms_tc_gemm(ctx, g);
+inline int tc_backward(mms_context* ctx, const float* q, const float* a, const float* W, const float* ds, float* dW,
+                       float* dq, float* da, int N, int K1, int K2) {
+  const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * ((size_t)N * (2 * K1p + K2p) + (size_t)K1 * K2p), &sp));
+  float* qr = static_cast<float*>(sp);          // q
+  float* qs = qr + (size_t)N * K1p;             // ds o q
+  float* as = qs + (size_t)N * K1p;             // ds o a
+  float* Wr = as + (size_t)N * K2p;
+  const RoundJob jobs[4] = {{q, qr, N, K1, K1, K1p, nullptr}, {q, qs, N, K1, K1, K1p, ds},
+                            {a, as, N, K2, K2, K2p, ds}, {W, Wr, K1, K2, K2, K2p, nullptr}};
+  MMS_TRY(mms_tf32_round(ctx, jobs, 4));
+  if (dW) {   // dW[r][c] += sum_n q[n][r] (ds[n] a[n][c]): both operands MN-major (rows = sample n = K index)
+    TcGemmArgs g = tc_gemm_args(qr, K1p, 1, as, K2p, 1, dW, K2, K1, K2, N, TC_ATOMIC);
+    const int tiles = mms_ceil_div(K1, 128) * mms_ceil_div(K2, 256);
+    g.ksplit = mms_max(1, mms_min(ctx->sm_count / mms_max(tiles, 1), mms_ceil_div(N, 256)));   // one full wave
+    g.operands_tf32 = 1;
+    MMS_TRY(mms_tc_gemm(ctx, g));
+  }
+  if (dq) {   // dq[n][r] = sum_c (ds[n] a[n][c]) W[r][c]: A K-major, B(n=r,k=c) = W[r][c] K-major
+    TcGemmArgs g = tc_gemm_args(as, K2p, 0, Wr, K2p, 0, dq, K1, N, K1, K2);
+    g.operands_tf32 = 1;
+    MMS_TRY(mms_tc_gemm(ctx, g));
+  }
+  if (da) {   // da = (ds o q) W
+    TcGemmArgs g = tc_gemm_args(qs, K1p, 0, Wr, K2p, 1, da, K2, N, K2, K1);
+    g.operands_tf32 = 1;
+    MMS_TRY(mms_tc_gemm(ctx, g));
+  }
+  return 0;
 }
-inline int tc_dW(mms_context*, const double*, const double*, const double*, double*, int, int, int) { return MMS_E_UNSUPPORTED; }
-
-inline int tc_dq(mms_context* ctx, const float* a, const float* W, const float* ds, float* dq, int N, int K1, int K2) {
-  // dq[n][r] = ds[n] * sum_c a[n][c] W[r][c]: A = a K-major (row-scaled), B(n=r,k=c)=W[r][c] K-major
-  TcGemmArgs g = tc_gemm_args(a, K2, 0, W, K2, 0, dq, K1, N, K1, K2);
-  g.a_rowscale = ds;
-  return mms_tc_gemm(ctx, g);
-}
-inline int tc_dq(mms_context*, const double*, const double*, const double*, double*, int, int, int) { return MMS_E_UNSUPPORTED; }
+inline int tc_backward(mms_context*, const double*, const double*, const double*, const double*, double*, double*,
+                       double*, int, int, int) { return MMS_E_UNSUPPORTED; }
 
 template <typename T>
 int mms_simmatrix_forward_impl(mms_context* ctx, const T* q, const T* a, const T* W, T* s, T* Tm,
@@ -100,7 +124,7 @@ int mms_simmatrix_forward_impl(mms_context* ctx, const T* q, const T* a, const T
   MMS_REQUIRE(N >= 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
   if (N == 0) return 0;
   // T = q W   (gemm NoTrans,NoTrans M_ x K2 x K1, sim_matrix_layer.cpp:60-61)
-  if (use_tc(ctx, q)) MMS_TRY(tc_T(ctx, q, W, Tm, N, K1, K2, nullptr));
+  if (use_tc(ctx, q)) MMS_TRY(tc_forward(ctx, q, W, Tm, N, K1, K2));
   else MMS_TRY(gemm2d<T>(ctx, q, K1, 1, W, K2, 1, Tm, K2, N, K2, K1, T(0)));
   { MmsKernelScope ks_(ctx, "rowdot_kernel");
     rowdot_kernel<T><<<ew_grid(ctx, (long long)N * 32), 256, 0, ctx->stream>>>(a, Tm, s, N, K2); }
@@ -115,12 +139,9 @@ int mms_simmatrix_backward_impl(mms_context* ctx, const T* q, const T* a, const 
   MMS_REQUIRE(q && a && W && ds, MMS_E_INVALID, "null pointer");
   MMS_REQUIRE(N >= 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
   if (N == 0) return 0;
-  if (use_tc(ctx, q)) {
-    if (prop_w && dW) MMS_TRY(tc_dW(ctx, q, a, ds, dW, N, K1, K2));
-    if (prop0 && dq) MMS_TRY(tc_dq(ctx, a, W, ds, dq, N, K1, K2));
-    if (prop1 && da) MMS_TRY(tc_T(ctx, q, W, da, N, K1, K2, ds));     // da = (ds o q) W
-    return 0;
-  }
+  if (use_tc(ctx, q))
+    return tc_backward(ctx, q, a, W, ds, (prop_w && dW) ? dW : nullptr, (prop0 && dq) ? dq : nullptr,
+                       (prop1 && da) ? da : nullptr, N, K1, K2);
   const bool need_as = (prop_w && dW) || (prop0 && dq);
   const bool need_qs = (prop1 && da);
   void* sp = nullptr;
@@ -157,10 +178,35 @@ int mms_rerank_scores_impl(mms_context* ctx, const float* Q, const float* C, con
   MMS_REQUIRE(Nq > 0 && Nc > 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
   MMS_REQUIRE(Nc <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "candidate count exceeds int range");
   if (ctx->math == MMS_MATH_TF32) {
-    MMS_TRY(tc_T(ctx, Q, W, QW, Nq, K1, K2, nullptr));
-    // scores = QW C^T: both K-major
-    TcGemmArgs t = tc_gemm_args(QW, K2, 0, C, K2, 0, scores, Nc, Nq, (int)Nc, K2);
-    return mms_tc_gemm(ctx, t);
+    // QW = Q W (kept un-rounded for the caller), then scores = QW C^T slab by slab: the candidates of
+    // a slab are rounded to TF32 into the scratch buffer (they are read-once data, HBM-bound) and the
+    // slab GEMM is TMA-fed; Q W is rounded once.
+    const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
+    const size_t fixed = (size_t)Nq * K1p + (size_t)K1 * K2p + (size_t)Nq * K2p;
+    long long slab = ((long long)(ctx->scratch_cap / sizeof(float)) - (long long)fixed) / K2p;
+    slab = mms_max<long long>(1024, mms_min<long long>(slab, mms_min<long long>(Nc, 1 << 18)));
+    void* sp = nullptr;
+    MMS_TRY(mms_scratch(ctx, sizeof(float) * (fixed + (size_t)slab * K2p), &sp));
+    float* Qr = static_cast<float*>(sp);
+    float* Wr = Qr + (size_t)Nq * K1p;
+    float* QWr = Wr + (size_t)K1 * K2p;
+    float* Cr = QWr + (size_t)Nq * K2p;
+    const RoundJob j0[2] = {{Q, Qr, Nq, K1, K1, K1p, nullptr}, {W, Wr, K1, K2, K2, K2p, nullptr}};
+    MMS_TRY(mms_tf32_round(ctx, j0, 2));
+    TcGemmArgs t = tc_gemm_args(Qr, K1p, 0, Wr, K2p, 1, QW, K2, Nq, K2, K1);
+    t.operands_tf32 = 1;
+    MMS_TRY(mms_tc_gemm(ctx, t));
+    const RoundJob j1[1] = {{QW, QWr, Nq, K2, K2, K2p, nullptr}};
+    MMS_TRY(mms_tf32_round(ctx, j1, 1));
+    for (long long c0 = 0; c0 < Nc; c0 += slab) {
+      const long long nc = mms_min<long long>(slab, Nc - c0);
+      const RoundJob j2[1] = {{C + (size_t)c0 * K2, Cr, nc, K2, K2, K2p, nullptr}};
+      MMS_TRY(mms_tf32_round(ctx, j2, 1));
+      TcGemmArgs g = tc_gemm_args(QWr, K2p, 0, Cr, K2p, 0, scores + c0, Nc, Nq, (int)nc, K2);   // both K-major
+      g.operands_tf32 = 1;
+      MMS_TRY(mms_tc_gemm(ctx, g));
+    }
+    return 0;
   }
   MMS_TRY(gemm2d<float>(ctx, Q, K1, 1, W, K2, 1, QW, K2, Nq, K2, K1, 0.f));
   // scores[i][j] = sum_c QW[i][c] * C[j][c]; scores row stride = Nc

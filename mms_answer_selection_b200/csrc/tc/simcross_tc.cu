@@ -126,7 +126,8 @@ int mms_tc_simcross2_backward(mms_context* ctx, const float* q, const float* a, 
       TcGemmArgs g = tc_gemm_args(qr, Dp, 1, buf, Dp, 1, dM, D, D, D, kdim, TC_ATOMIC);
       g.nb1 = mc; g.sB1 = sU1; g.sC1 = (long long)D * D;
       const int tiles = mc * mms_ceil_div(D, 128) * mms_ceil_div(D, 256);
-      g.ksplit = mms_max(1, mms_min(mms_ceil_div(ctx->sm_count, tiles), mms_ceil_div(kdim, 128)));
+      // one full wave of CTAs: tiles * ksplit <= SM count (a 149th tile would double the kernel's time)
+      g.ksplit = mms_max(1, mms_min(ctx->sm_count / mms_max(tiles, 1), mms_ceil_div(kdim, 128)));
       g.operands_tf32 = 1;
       MMS_TRY(mms_tc_gemm(ctx, g));
     }

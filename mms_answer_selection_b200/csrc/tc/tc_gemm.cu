@@ -170,7 +170,9 @@ tc_gemm_kernel(const TcGemmArgs g, const int BN, const int stages, const int b_b
                const int m_tiles, const unsigned total_tiles, const uint32_t tmem_cols) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned operand ring first, barriers after it
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by an OFFSET from the __shared__ symbol (not by integer arithmetic on the pointer), so the
+  // compiler keeps the shared address space and emits STS/LDS instead of generic ST/LD for everything derived from it
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = 16384 + b_bytes;
   Smem* sm = reinterpret_cast<Smem*>(ring + stages * stage_bytes);
 

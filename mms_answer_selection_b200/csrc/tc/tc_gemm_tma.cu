@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const TcGemmArgs g, const Geometry q, long long* tr) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by an OFFSET from the __shared__ symbol (not by integer arithmetic on the pointer), so the
+  // compiler keeps the shared address space and emits STS/LDS instead of generic ST/LD for everything derived from it
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = 16384 + q.b_bytes;
   float* epi = reinterpret_cast<float*>(ring + q.stages * stage_bytes);
   Smem* sm = reinterpret_cast<Smem*>(ring + q.stages * stage_bytes + kEpiBytes);

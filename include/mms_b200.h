@@ -54,8 +54,17 @@ enum {
                                 pair_rank_loss_layer.cpp:76), 1 `ordered >= 0` (reference GPU,
                                 pair_rank_loss_layer.cu:51).  Default 0. */
   MMS_OPT_SCRATCH_BYTES = 3, /* cap for the per-call scratch chunk (default 4 GiB; grows on demand) */
-  MMS_OPT_EMBED_DETERMINISTIC = 4 /* Embed backward: 1 = order-independent segmented reduction
+  MMS_OPT_EMBED_DETERMINISTIC = 4, /* Embed backward: 1 = order-independent segmented reduction
                                 (bit-reproducible), 0 = block-aggregated atomics.  Default 0. */
+  MMS_OPT_REUSE_FORWARD = 5, /* SimCross mode 2, float: 1 = mms_simcross_backward may reuse the TF32-rounded
+                                operands and T = Q M_k that the LAST mms_simcross_forward on this handle left
+                                in the workspace, provided it was called with the same q / a / M pointers and
+                                sizes and no other call used the workspace since.  The caller promises that
+                                q, a and M are unchanged between that forward and this backward -- which is
+                                how Net::ForwardBackward and GradientChecker drive a layer.  Default 0
+                                (stateless: backward recomputes, like the reference, sim_cross_layer.cpp:296). */
+  MMS_OPT_CONCURRENCY = 6    /* 1 (default): independent contractions inside one call may run on private
+                                streams, joined back before the call's last launch on the handle's stream. */
 };
 
 typedef struct mms_context* mms_handle_t;

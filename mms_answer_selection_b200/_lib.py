@@ -12,6 +12,7 @@ c_f, c_d = ctypes.c_float, ctypes.c_double
 
 MMS_MATH_TF32, MMS_MATH_FP32 = 0, 1
 MMS_OPT_MATH, MMS_OPT_PRL_GE, MMS_OPT_SCRATCH_BYTES, MMS_OPT_EMBED_DETERMINISTIC = 1, 2, 3, 4
+MMS_OPT_REUSE_FORWARD, MMS_OPT_CONCURRENCY = 5, 6
 MMS_E_INVALID, MMS_E_UNSUPPORTED, MMS_E_NOMEM, MMS_E_FAULT = -1, -2, -3, -4
 
 

@@ -18,6 +18,7 @@ void mms_set_error(const char* fmt, ...) {
 }
 
 int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
+  ctx->fwd_cache.valid = false;        // whoever asks for the scratch buffer is about to overwrite it
   if (bytes > ctx->scratch_bytes) {
     if (ctx->scratch) {
       // earlier launches on the stream may still read the old buffer
@@ -39,6 +40,23 @@ int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
 }
 
 void mms_tc_destroy_state(mms_context* ctx);
+
+int mms_fork(mms_context* ctx, int i) {
+  if (!ctx->side[i]) {
+    MMS_CUDA(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+    MMS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming));
+    MMS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+  }
+  MMS_CUDA(cudaEventRecord(ctx->ev_fork[i], ctx->stream));
+  MMS_CUDA(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork[i], 0));
+  return 0;
+}
+
+int mms_join(mms_context* ctx, int i) {
+  MMS_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+  MMS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+  return 0;
+}
 
 // ---- per-launch CUDA-event profiler -----------------------------------------------------
 #include <map>
@@ -100,6 +118,7 @@ int mms_create(mms_handle_t* out) {
   ctx->sm_count = sms;
   cudaError_t e = cudaMalloc(&ctx->fault_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->fault_flag, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->partials, 1024 * sizeof(double));
   if (e != cudaSuccess) {
     mms_set_error("context allocation failed: %s", cudaGetErrorString(e));
     delete ctx;
@@ -117,6 +136,12 @@ int mms_destroy(mms_handle_t h) {
   delete static_cast<std::vector<ProfRecord>*>(h->prof);
   if (h->scratch) cudaFree(h->scratch);
   if (h->fault_flag) cudaFree(h->fault_flag);
+  if (h->partials) cudaFree(h->partials);
+  for (int i = 0; i < 2; ++i) {
+    if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
+    if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
   delete h;
   return 0;
 }
@@ -138,6 +163,8 @@ int mms_set_option(mms_handle_t h, int option, long long value) {
       MMS_REQUIRE(value >= (1 << 20), MMS_E_INVALID, "scratch cap below 1 MiB");
       h->scratch_cap = (size_t)value; return 0;
     case MMS_OPT_EMBED_DETERMINISTIC: h->embed_deterministic = value != 0; return 0;
+    case MMS_OPT_REUSE_FORWARD: h->reuse_forward = value != 0; h->fwd_cache.valid = false; return 0;
+    case MMS_OPT_CONCURRENCY: h->concurrency = value != 0; return 0;
     default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
   }
 }
@@ -149,6 +176,8 @@ int mms_get_option(mms_handle_t h, int option, long long* value) {
     case MMS_OPT_PRL_GE: *value = h->prl_ge; return 0;
     case MMS_OPT_SCRATCH_BYTES: *value = (long long)h->scratch_cap; return 0;
     case MMS_OPT_EMBED_DETERMINISTIC: *value = h->embed_deterministic; return 0;
+    case MMS_OPT_REUSE_FORWARD: *value = h->reuse_forward; return 0;
+    case MMS_OPT_CONCURRENCY: *value = h->concurrency; return 0;
     default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
   }
 }

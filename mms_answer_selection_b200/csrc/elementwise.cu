@@ -162,7 +162,7 @@ int mms_pairrankloss_forward_impl(mms_context* ctx, const T* a, const T* b, cons
   MMS_REQUIRE(a && b && y && loss && ordered && similar, MMS_E_INVALID, "null pointer");
   MMS_REQUIRE(count > 0, MMS_E_INVALID, "count must be positive");
   void* sp = nullptr;
-  MMS_TRY(mms_scratch(ctx, sizeof(T) * kMaxPartials, &sp));
+  sp = ctx->partials;     // a private buffer: the scratch buffer may hold SimCross's forward cache
   T* partials = static_cast<T*>(sp);
   const int grid = red_grid(ctx, count);
   { MmsKernelScope ks_(ctx, "prl_forward_kernel");
@@ -220,7 +220,7 @@ int mms_dot_impl(mms_context* ctx, const T* x, const T* y, long long n, T* out) 
   MMS_REQUIRE(x && out, MMS_E_INVALID, "null pointer");
   MMS_REQUIRE(n >= 0, MMS_E_INVALID, "bad size");
   void* sp = nullptr;
-  MMS_TRY(mms_scratch(ctx, sizeof(T) * kMaxPartials, &sp));
+  sp = ctx->partials;     // a private buffer: the scratch buffer may hold SimCross's forward cache
   T* partials = static_cast<T*>(sp);
   const int grid = red_grid(ctx, n);
   { MmsKernelScope ks_(ctx, "sum_kernel");

@@ -21,6 +21,31 @@ struct mms_context {
   unsigned long long launches = 0;   // kernels launched through this handle
   int profile = 0;               // 1: bracket every launch with CUDA events (mms_profile_*)
   void* prof = nullptr;          // std::vector<ProfRecord>*
+  void* partials = nullptr;      // 1024 doubles: block partial sums of the loss reductions
+  // fork/join inside one call: independent contractions of SimCross backward run on two private
+  // streams, ordered against the caller's stream with events (works under stream capture too)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr};
+  cudaEvent_t ev_join[2] = {nullptr, nullptr};
+  int concurrency = 1;           // MMS_OPT_CONCURRENCY
+  // SimCross forward leaves its rounded operands and T = Q M_k in the scratch buffer; backward reuses
+  // them when MMS_OPT_REUSE_FORWARD is set and nothing has touched the scratch buffer in between.
+  int reuse_forward = 0;
+  struct FwdCache {
+    bool valid = false;
+    const void *q = nullptr, *a = nullptr, *M = nullptr;
+    int N = 0, Lq = 0, La = 0, D = 0, mc = 0;
+  } fwd_cache;
+};
+
+// Runs the launches issued between fork(i) and join(i) on private stream i, after everything already
+// queued on the caller's stream; join(i) makes the caller's stream wait for them.
+int mms_fork(mms_context* ctx, int i);
+int mms_join(mms_context* ctx, int i);
+struct MmsStreamSwitch {          // RAII: ctx->stream = side stream i for the scope
+  mms_context* ctx; cudaStream_t saved;
+  MmsStreamSwitch(mms_context* c, int i) : ctx(c), saved(c->stream) { c->stream = c->side[i]; }
+  ~MmsStreamSwitch() { ctx->stream = saved; }
 };
 
 // Placed in front of every kernel launch: counts it and, when profiling is on, records a
@@ -141,6 +166,9 @@ int mms_rerank_scores_impl(mms_context*, const float* Q, const float* C, const f
 // handle; the caller then uses the SIMT path (still on the GPU).
 int mms_tc_simcross2_forward(mms_context*, const float* q, const float* a, const float* Mw,
                              const float* B, float* S, int N, int Lq, int La, int D, int mc);
+// fused forward over TF32-rounded, row-padded copies (tc/simcross_fused.cu)
+int mms_tc_simcross2_forward_fused(mms_context*, const float* qr, const float* ar, const float* Mr,
+                                   const float* B, float* S, int N, int Lq, int La, int D, int mc, int Dp);
 // (dq, da, dM overwritten; dB is accumulated by the caller)
 int mms_tc_simcross2_backward(mms_context*, const float* q, const float* a, const float* Mw,
                               const float* dS, float* dq, float* da, float* dM, int N, int Lq, int La,

@@ -1,0 +1,287 @@
+// SimCross mode 2 forward as ONE kernel: S[n,k] = (Q_n M_k) A_n^T + B_k with T = Q_n M_k never
+// leaving the SM (reference: src/caffe/layers/sim_cross_layer.cpp:146-160, two cblas_sgemm calls per
+// (pair, measure) with T in the layer's measure_temp0_ blob).
+//
+// One tile = P consecutive QA pairs (P*Lq <= 128 token rows) x one measure k:
+//   GEMM1  T[128 x N1]  = Qtile[128 x D] * M_k[D x D]     operands by TMA (Q K-major, M_k MN-major),
+//                                                          fp32 accumulator T in TMEM columns [0, N1)
+//   round  T -> tf32 (round to nearest) in place           tcgen05.ld -> cvt.rna -> tcgen05.st, 32 columns at a
+//                                                          time; tcgen05 would otherwise TRUNCATE the operand
+//   GEMM2  S[128 x N2]  = T * Atile[N2 x D]^T              A operand read straight from TMEM (tcgen05.mma
+//                                                          [tmem], smem-desc), Atile = the P pairs' answer rows;
+//                                                          accumulator S in TMEM columns [N1, N1 + N2)
+//   store  row (p, lq) keeps columns [p*La, (p+1)*La) of S, + B_k, -> S[n0+p][k][lq][:]
+// GEMM2 is block-diagonal (only the P diagonal Lq x La blocks are kept); it costs L/D of GEMM1, so
+// computing the off-diagonal blocks is cheaper than a second pass over T through HBM.
+//
+//   warp 0     TMA producer (one lane), one ring of stages shared by both GEMMs
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2-5  T rounding, then the S epilogue (TMEM lane quarter = warp % 4)
+// The epilogue of tile i overlaps GEMM1 of tile i+1 (S and T occupy different TMEM columns); GEMM2 starts on
+// a 32-column chunk of T as soon as that chunk is rounded.
+#include <cuda.h>
+
+#include <stdlib.h>
+
+#include "../mms_common.cuh"
+#include "tc_gemm.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+constexpr int kMaxChunks = 12;          // 32-column chunks of T (N1 <= 384)
+
+struct FwdGeom {
+  int N, Lq, La, D, mc;
+  int P;                 // pairs per tile
+  int N1, N2;            // accumulator widths of GEMM1 / GEMM2 (multiples of 16)
+  int nkb;               // 32-wide k-blocks over D (both GEMMs reduce over D)
+  int nboxes;            // 32-wide column boxes of M_k per k-block
+  int stages, stage_bytes;
+  unsigned total_tiles;
+  uint32_t tmem_cols;
+  int vec;               // S / B rows are 16-byte aligned
+};
+
+struct FwdSmem {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t t_full, s_full, s_empty;
+  uint64_t t_ready[kMaxChunks];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapM,
+                           const __grid_constant__ CUtensorMap mapA, const float* __restrict__ Bias,
+                           float* __restrict__ S, const FwdGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  FwdSmem* sm = reinterpret_cast<FwdSmem*>(ring + g.stages * g.stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stages = g.stages;
+  const int nch = (g.N1 + 31) >> 5;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+      mbar_init(&sm->t_full, 1); mbar_init(&sm->s_full, 1); mbar_init(&sm->s_empty, 4);
+      for (int c = 0; c < kMaxChunks; ++c) mbar_init(&sm->t_ready[c], 4);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm->tmem_base, g.tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapM);
+    tma_prefetch_desc(&mapA);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const uint32_t tmem_S = tmem + (uint32_t)g.N1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx1 = 16384u + (uint32_t)g.nboxes * 4096u;
+      const uint32_t tx2 = (uint32_t)g.N2 * 128u;
+      int it = 0;
+      for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+        const int k = (int)(t % (unsigned)g.mc);
+        const int n0 = (int)(t / (unsigned)g.mc) * g.P;
+        for (int b = 0; b < g.nkb; ++b, ++it) {                  // GEMM1: Q k-block + M_k k-block
+          const int s = it % stages;
+          if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
+          uint8_t* dst = ring + s * g.stage_bytes;
+          mbar_arrive_expect_tx(&sm->full[s], tx1);
+          tma_load_5d(dst, &mapQ, &sm->full[s], b * 32, n0 * g.Lq, 0, 0, 0);
+          for (int x = 0; x < g.nboxes; ++x)
+            tma_load_5d(dst + 16384 + x * 4096, &mapM, &sm->full[s], 32 * x, b * 32, 0, k, 0);
+        }
+        for (int b = 0; b < g.nkb; ++b, ++it) {                  // GEMM2: answer rows of the P pairs
+          const int s = it % stages;
+          if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
+          uint8_t* dst = ring + s * g.stage_bytes;
+          mbar_arrive_expect_tx(&sm->full[s], tx2);
+          tma_load_5d(dst, &mapA, &sm->full[s], b * 32, n0 * g.La, 0, 0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issue
+    if (lane == 0) {
+      const int np0 = min(g.N1, 256), np1 = g.N1 - np0;         // GEMM1 runs as one or two N parts (N <= 256 each)
+      const uint32_t idesc_p0 = idesc_tf32(128, np0, false, true);
+      const uint32_t idesc_p1 = idesc_tf32(128, np1 > 0 ? np1 : 16, false, true);
+      const uint32_t idesc_2 = idesc_tf32(128, g.N2, false, false);
+      int it = 0, tc = 0;
+      for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tc) {
+        for (int b = 0; b < g.nkb; ++b, ++it) {
+          const int s = it % stages;
+          mbar_wait(&sm->full[s], (it / stages) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(ring + s * g.stage_bytes);
+          const uint32_t b_base = a_base + 16384;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (b * 32 + ks * 8 < g.D) {
+              const uint32_t acc = (b > 0 || ks > 0) ? 1u : 0u;
+              const uint64_t da = desc_kmajor(a_base + ks * 32);
+              mma_tf32_ss(tmem, da, desc_mnmajor(b_base + ks * 1024, 4096), idesc_p0, acc);
+              if (np1 > 0)
+                mma_tf32_ss(tmem + 256, da, desc_mnmajor(b_base + 8 * 4096 + ks * 1024, 4096), idesc_p1, acc);
+            }
+          }
+          mma_commit(&sm->empty[s]);
+        }
+        mma_commit(&sm->t_full);
+        if (tc > 0) mbar_wait(&sm->s_empty, (tc - 1) & 1);       // the previous tile's S has been read out
+        for (int b = 0; b < g.nkb; ++b, ++it) {
+          const int s = it % stages;
+          mbar_wait(&sm->full[s], (it / stages) & 1);
+          mbar_wait(&sm->t_ready[b], tc & 1);                    // T columns [32 b, 32 b + 32) are rounded
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(ring + s * g.stage_bytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (b * 32 + ks * 8 < g.D)
+              mma_tf32_ts(tmem_S, tmem + b * 32 + ks * 8, desc_kmajor(b_base + ks * 32), idesc_2,
+                          (b > 0 || ks > 0) ? 1u : 0u);
+          }
+          mma_commit(&sm->empty[s]);
+        }
+        mma_commit(&sm->s_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ T rounding + S epilogue
+    const int quarter = warp & 3;
+    const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
+    const int row = quarter * 32 + lane;                         // token row of the tile = TMEM lane
+    const int p_lane = row / g.Lq, lq = row - p_lane * g.Lq;
+    const int p_lo = (quarter * 32) / g.Lq;
+    const int p_hi = min(g.P - 1, (quarter * 32 + 31) / g.Lq);
+    const int nc8 = (g.La + 7) >> 3;
+    int tc = 0;
+    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tc) {
+      const int k = (int)(t % (unsigned)g.mc);
+      const int n0 = (int)(t / (unsigned)g.mc) * g.P;
+      mbar_wait(&sm->t_full, tc & 1);
+      tc_fence_after();
+      for (int c = 0; c < nch; ++c) {
+        float v[32];
+        const uint32_t ta = tmem + lane_bits + (uint32_t)(c * 32);
+        if (c * 32 + 16 < g.N1) {
+          tmem_ld32(ta, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = to_tf32(v[i]);
+          tmem_st32(ta, v);
+        } else {
+          tmem_ld16(ta, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = to_tf32(v[i]);
+          tmem_st16(ta, v);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->t_ready[c]);
+      }
+      mbar_wait(&sm->s_full, tc & 1);
+      tc_fence_after();
+      for (int p = p_lo; p <= p_hi; ++p) {
+        const int n = n0 + p;
+        const bool active = (p_lane == p) && (n < g.N);
+        float* srow = S + (((size_t)n * g.mc + k) * g.Lq + lq) * g.La;
+        const float* brow = Bias ? Bias + ((size_t)k * g.Lq + lq) * g.La : nullptr;
+        for (int c8 = 0; c8 < nc8; ++c8) {
+          float v[8];
+          tmem_ld8(tmem_S + lane_bits + (uint32_t)(p * g.La + c8 * 8), v);
+          if (active) {
+            const int col = c8 * 8;
+            if (g.vec && col + 8 <= g.La) {
+              if (brow) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + col + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              *reinterpret_cast<float4*>(srow + col) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(srow + col + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col + j < g.La) srow[col + j] = v[j] + (brow ? __ldg(brow + col + j) : 0.f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->s_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, g.tmem_cols);
+}
+
+}  // namespace
+
+// qr (N*Lq x Dp), ar (N*La x Dp), Mr (mc x D x Dp): TF32-rounded copies with 16-byte-aligned rows.
+// Returns MMS_E_UNSUPPORTED for shapes the fused tile does not cover (the caller composes GEMMs instead).
+int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const float* ar, const float* Mr,
+                                   const float* B, float* S, int N, int Lq, int La, int D, int mc, int Dp) {
+  static const bool disabled = getenv("MMS_NO_FUSED") != nullptr;
+  if (disabled) return MMS_E_UNSUPPORTED;
+  if (Lq > 128 || La > 256) return MMS_E_UNSUPPORTED;
+  FwdGeom g;
+  g.N = N; g.Lq = Lq; g.La = La; g.D = D; g.mc = mc;
+  g.P = mms_max(1, mms_min(mms_min(128 / Lq, 256 / La), N));
+  g.N1 = mms_ceil_div(D, 16) * 16;
+  // the epilogue reads S in 8-column groups per pair: the last group may overhang the pair's La columns
+  g.N2 = mms_ceil_div((g.P - 1) * La + mms_ceil_div(La, 8) * 8, 16) * 16;
+  if (g.N1 > 32 * kMaxChunks || g.N2 > 256 || g.N1 + g.N2 > 512) return MMS_E_UNSUPPORTED;
+  g.nkb = mms_ceil_div(D, 32);
+  g.nboxes = mms_ceil_div(g.N1, 32);
+  g.stage_bytes = mms_ceil_div(mms_max(16384 + g.nboxes * 4096, g.N2 * 128), 1024) * 1024;
+  int stages = kMaxStages;
+  while (stages > 2 && (size_t)stages * g.stage_bytes + sizeof(FwdSmem) + 1024 > 226 * 1024) --stages;
+  if ((size_t)stages * g.stage_bytes + sizeof(FwdSmem) + 1024 > 226 * 1024) return MMS_E_UNSUPPORTED;
+  g.stages = stages;
+  const long long total = (long long)mms_ceil_div(N, g.P) * mc;
+  if (total > 0x7fffffffLL) return MMS_E_UNSUPPORTED;
+  g.total_tiles = (unsigned)total;
+  g.tmem_cols = umma::tmem_cols_pow2((uint32_t)(g.N1 + g.N2));
+  g.vec = (La % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) &&
+          (!B || (reinterpret_cast<uintptr_t>(B) & 15) == 0);
+
+  CUtensorMap mapQ, mapM, mapA;
+  MMS_TRY(mms_tc_make_map(ctx, &mapQ, qr, Dp, false, (long long)N * Lq, D, 128, 0, 0, 0, 1, 1, 1));
+  MMS_TRY(mms_tc_make_map(ctx, &mapM, Mr, Dp, true, D, D, 32, (long long)D * Dp, 0, 0, mc, 1, 1));
+  MMS_TRY(mms_tc_make_map(ctx, &mapA, ar, Dp, false, (long long)N * La, D, g.N2, 0, 0, 0, 1, 1, 1));
+
+  static bool configured = false;
+  if (!configured) {
+    MMS_CUDA(cudaFuncSetAttribute(simcross2_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
+    configured = true;
+  }
+  const size_t smem = (size_t)stages * g.stage_bytes + sizeof(FwdSmem) + 1024;
+  const unsigned grid = (unsigned)mms_min<long long>(total, ctx->sm_count);
+  { MmsKernelScope ks_(ctx, "simcross2_fwd_fused_kernel");
+    simcross2_fwd_fused_kernel<<<grid, kThreads, smem, ctx->stream>>>(mapQ, mapM, mapA, B, S, g); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}

@@ -72,6 +72,11 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
         {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
         {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
     MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
+    {  // one kernel for both contractions, T stays in tensor memory (tc/simcross_fused.cu)
+      const int rc = mms_tc_simcross2_forward_fused(ctx, qr, ar, Mr, B, Sc, nc, Lq, La, D, mc, Dp);
+      if (rc == 0) continue;
+      if (rc != MMS_E_UNSUPPORTED) return rc;
+    }
     MMS_TRY(gemm_T(ctx, qr, Mr, Tk, nc * Lq, D, Dp, mc));                  // sim_cross_layer.cpp:148-149
     TcGemmArgs g = tc_gemm_args(Tk, Dp, 0, ar, Dp, 0, Sc, La, Lq, La, D);  // :151-153
     g.nb1 = mc; g.nb2 = nc;

@@ -416,6 +416,13 @@ bool tma_ok(const float* p, long long ld, long long s1, long long s2, long long 
 
 }  // namespace
 
+int mms_tc_make_map(mms_context* ctx, void* out, const float* ptr, long long ld, bool mn_major, long long MN,
+                    long long K, int rows_box, long long s1, long long s2, long long sseg, int nb1, int nb2,
+                    int nseg) {
+  return make_map(ctx, static_cast<CUtensorMap*>(out), ptr, ld, mn_major, MN, K, rows_box, s1, s2, sseg, nb1, nb2,
+                  nseg);
+}
+
 void mms_tc_destroy_state(mms_context* ctx) {
   delete static_cast<TcState*>(ctx->tc_state);
   ctx->tc_state = nullptr;

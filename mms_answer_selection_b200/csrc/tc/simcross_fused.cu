@@ -16,7 +16,8 @@
 //
 //   warp 0     TMA producer (one lane), one ring of stages shared by both GEMMs
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5  T rounding, then the S epilogue (TMEM lane quarter = warp % 4)
+//   warps 2-9  T rounding, then the S epilogue (TMEM lane quarter = warp % 4, two warps per quarter
+//              taking alternate column chunks)
 // The epilogue of tile i overlaps GEMM1 of tile i+1 (S and T occupy different TMEM columns); GEMM2 starts on
 // a 32-column chunk of T as soon as that chunk is rounded.
 #include <cuda.h>
@@ -31,7 +32,7 @@ namespace {
 
 using namespace umma;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // TMA warp, MMA warp, 2 x 4 rounding / epilogue warps
 constexpr int kMaxStages = 6;
 constexpr int kMaxChunks = 12;          // 32-column chunks of T (N1 <= 384)
 
@@ -42,6 +43,7 @@ struct FwdGeom {
   int nkb;               // 32-wide k-blocks over D (both GEMMs reduce over D)
   int nboxes;            // 32-wide column boxes of M_k per k-block
   int stages, stage_bytes;
+  int kb2;               // k-blocks of the answer tile per ring stage in GEMM2
   unsigned total_tiles;
   uint32_t tmem_cols;
   int vec;               // S / B rows are 16-byte aligned
@@ -55,22 +57,32 @@ struct FwdSmem {
   uint32_t tmem_base;
 };
 
+// Optional per-CTA timeline (MMS_TC_TRACE=1): globaltimer stamps at 12 checkpoints.
+constexpr int kTraceSlots = 16;
+__device__ __forceinline__ void trace(long long* tr, int slot) {
+  if (!tr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  tr[(size_t)blockIdx.x * kTraceSlots + slot] = (long long)t;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapM,
                            const __grid_constant__ CUtensorMap mapA, const float* __restrict__ Bias,
-                           float* __restrict__ S, const FwdGeom g) {
+                           float* __restrict__ S, const FwdGeom g, long long* tr) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   FwdSmem* sm = reinterpret_cast<FwdSmem*>(ring + g.stages * g.stage_bytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
   const int stages = g.stages;
   const int nch = (g.N1 + 31) >> 5;
+  if (threadIdx.x == 0) { trace(tr, 0); if (tr) tr[(size_t)blockIdx.x * kTraceSlots + 15] = clock64(); }
 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
-      mbar_init(&sm->t_full, 1); mbar_init(&sm->s_full, 1); mbar_init(&sm->s_empty, 4);
+      mbar_init(&sm->t_full, 1); mbar_init(&sm->s_full, 1); mbar_init(&sm->s_empty, 8);
       for (int c = 0; c < kMaxChunks; ++c) mbar_init(&sm->t_ready[c], 4);
       fence_barrier_init();
     }
@@ -87,10 +99,11 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
   const uint32_t tmem_S = tmem + (uint32_t)g.N1;
+  if (threadIdx.x == 0) trace(tr, 1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp walks the loops,
+    {                                                            // one elected lane issues)
       const uint32_t tx1 = 16384u + (uint32_t)g.nboxes * 4096u;
       const uint32_t tx2 = (uint32_t)g.N2 * 128u;
       int it = 0;
@@ -101,25 +114,36 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
           const int s = it % stages;
           if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
           uint8_t* dst = ring + s * g.stage_bytes;
-          mbar_arrive_expect_tx(&sm->full[s], tx1);
-          tma_load_5d(dst, &mapQ, &sm->full[s], b * 32, n0 * g.Lq, 0, 0, 0);
-          for (int x = 0; x < g.nboxes; ++x)
-            tma_load_5d(dst + 16384 + x * 4096, &mapM, &sm->full[s], 32 * x, b * 32, 0, k, 0);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&sm->full[s], tx1);
+            tma_load_5d(dst, &mapQ, &sm->full[s], b * 32, n0 * g.Lq, 0, 0, 0);
+            for (int x = 0; x < g.nboxes; ++x)
+              tma_load_5d(dst + 16384 + x * 4096, &mapM, &sm->full[s], 32 * x, b * 32, 0, k, 0);
+          }
+          __syncwarp();
         }
-        for (int b = 0; b < g.nkb; ++b, ++it) {                  // GEMM2: answer rows of the P pairs
-          const int s = it % stages;
+        for (int b0 = 0; b0 < g.nkb; b0 += g.kb2, ++it) {        // GEMM2: answer rows of the P pairs, kb2 k-blocks
+          const int s = it % stages;                             // per stage (they are small: keep bytes in flight)
+          const int nb = min(g.kb2, g.nkb - b0);
           if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
           uint8_t* dst = ring + s * g.stage_bytes;
-          mbar_arrive_expect_tx(&sm->full[s], tx2);
-          tma_load_5d(dst, &mapA, &sm->full[s], b * 32, n0 * g.La, 0, 0, 0);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&sm->full[s], tx2 * (uint32_t)nb);
+            for (int j = 0; j < nb; ++j)
+              tma_load_5d(dst + j * tx2, &mapA, &sm->full[s], (b0 + j) * 32, n0 * g.La, 0, 0, 0);
+          }
+          __syncwarp();
         }
       }
+      if (lane == 0) trace(tr, 2);
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issue
-    if (lane == 0) {
-      const int np0 = min(g.N1, 256), np1 = g.N1 - np0;         // GEMM1 runs as one or two N parts (N <= 256 each)
+    // ------------------------------------------------------------ MMA issue (whole warp walks the loops,
+    {                                                            // one elected lane issues)
+      // GEMM1 runs as one MMA per k-step, or two of about equal N (N <= 256 each; the split is a multiple of the
+      // 32-column boxes of M_k; measured: 160 + 144 costs 152 cycles per k-step, 256 + 48 costs 171)
+      const int np0 = g.N1 <= 256 ? g.N1 : ((g.N1 / 2 + 31) & ~31), np1 = g.N1 - np0;
       const uint32_t idesc_p0 = idesc_tf32(128, np0, false, true);
       const uint32_t idesc_p1 = idesc_tf32(128, np1 > 0 ? np1 : 16, false, true);
       const uint32_t idesc_2 = idesc_tf32(128, g.N2, false, false);
@@ -129,43 +153,60 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
           const int s = it % stages;
           mbar_wait(&sm->full[s], (it / stages) & 1);
           tc_fence_after();
+          if (it == 0 && lane == 0) trace(tr, 3);
           const uint32_t a_base = smem_u32(ring + s * g.stage_bytes);
           const uint32_t b_base = a_base + 16384;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (b * 32 + ks * 8 < g.D) {
-              const uint32_t acc = (b > 0 || ks > 0) ? 1u : 0u;
-              const uint64_t da = desc_kmajor(a_base + ks * 32);
-              mma_tf32_ss(tmem, da, desc_mnmajor(b_base + ks * 1024, 4096), idesc_p0, acc);
-              if (np1 > 0)
-                mma_tf32_ss(tmem + 256, da, desc_mnmajor(b_base + 8 * 4096 + ks * 1024, 4096), idesc_p1, acc);
+            for (int ks = 0; ks < 4; ++ks) {
+              if (b * 32 + ks * 8 < g.D) {
+                const uint32_t acc = (b > 0 || ks > 0) ? 1u : 0u;
+                const uint64_t da = desc_kmajor(a_base + ks * 32);
+                mma_tf32_ss(tmem, da, desc_mnmajor(b_base + ks * 1024, 4096), idesc_p0, acc);
+                if (np1 > 0)
+                  mma_tf32_ss(tmem + np0, da, desc_mnmajor(b_base + (np0 >> 5) * 4096 + ks * 1024, 4096), idesc_p1, acc);
+              }
             }
+            mma_commit(&sm->empty[s]);
+            if (b == g.nkb - 1) mma_commit(&sm->t_full);
           }
-          mma_commit(&sm->empty[s]);
+          __syncwarp();
         }
-        mma_commit(&sm->t_full);
+        if (tc == 0 && lane == 0) trace(tr, 4);
         if (tc > 0) mbar_wait(&sm->s_empty, (tc - 1) & 1);       // the previous tile's S has been read out
-        for (int b = 0; b < g.nkb; ++b, ++it) {
+        for (int b0 = 0; b0 < g.nkb; b0 += g.kb2, ++it) {
           const int s = it % stages;
+          const int nb = min(g.kb2, g.nkb - b0);
+          if (tc == 0 && b0 == g.kb2 && lane == 0) trace(tr, 12);
+          if (tc == 0 && b0 == 2 * g.kb2 && lane == 0) trace(tr, 14);
           mbar_wait(&sm->full[s], (it / stages) & 1);
-          mbar_wait(&sm->t_ready[b], tc & 1);                    // T columns [32 b, 32 b + 32) are rounded
-          tc_fence_after();
-          const uint32_t b_base = smem_u32(ring + s * g.stage_bytes);
+          if (tc == 0 && b0 == g.kb2 && lane == 0) trace(tr, 13);
+          for (int j = 0; j < nb; ++j) {
+            const int b = b0 + j;
+            mbar_wait(&sm->t_ready[b], tc & 1);                  // T columns [32 b, 32 b + 32) are rounded
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(ring + s * g.stage_bytes) + (uint32_t)j * (uint32_t)g.N2 * 128u;
+            if (elect_one_sync()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (b * 32 + ks * 8 < g.D)
-              mma_tf32_ts(tmem_S, tmem + b * 32 + ks * 8, desc_kmajor(b_base + ks * 32), idesc_2,
-                          (b > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks) {
+                if (b * 32 + ks * 8 < g.D)
+                  mma_tf32_ts(tmem_S, tmem + b * 32 + ks * 8, desc_kmajor(b_base + ks * 32), idesc_2,
+                              (b > 0 || ks > 0) ? 1u : 0u);
+              }
+              if (j == nb - 1) mma_commit(&sm->empty[s]);
+              if (b == g.nkb - 1) mma_commit(&sm->s_full);
+            }
+            __syncwarp();
           }
-          mma_commit(&sm->empty[s]);
         }
-        mma_commit(&sm->s_full);
+        if (tc == 0 && lane == 0) trace(tr, 7);
       }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------ T rounding + S epilogue
     const int quarter = warp & 3;
+    const int set = (warp - 2) >> 2;                             // two warps per TMEM lane quarter share the columns
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
     const int row = quarter * 32 + lane;                         // token row of the tile = TMEM lane
     const int p_lane = row / g.Lq, lq = row - p_lane * g.Lq;
@@ -178,7 +219,8 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
       const int n0 = (int)(t / (unsigned)g.mc) * g.P;
       mbar_wait(&sm->t_full, tc & 1);
       tc_fence_after();
-      for (int c = 0; c < nch; ++c) {
+      if (tc == 0 && threadIdx.x == 64) trace(tr, 5);
+      for (int c = set; c < nch; c += 2) {
         float v[32];
         const uint32_t ta = tmem + lane_bits + (uint32_t)(c * 32);
         if (c * 32 + 16 < g.N1) {
@@ -197,14 +239,16 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->t_ready[c]);
       }
+      if (tc == 0 && threadIdx.x == 64) trace(tr, 6);
       mbar_wait(&sm->s_full, tc & 1);
       tc_fence_after();
+      if (tc == 0 && threadIdx.x == 64) trace(tr, 8);
       for (int p = p_lo; p <= p_hi; ++p) {
         const int n = n0 + p;
         const bool active = (p_lane == p) && (n < g.N);
         float* srow = S + (((size_t)n * g.mc + k) * g.Lq + lq) * g.La;
         const float* brow = Bias ? Bias + ((size_t)k * g.Lq + lq) * g.La : nullptr;
-        for (int c8 = 0; c8 < nc8; ++c8) {
+        for (int c8 = set; c8 < nc8; c8 += 2) {
           float v[8];
           tmem_ld8(tmem_S + lane_bits + (uint32_t)(p * g.La + c8 * 8), v);
           if (active) {
@@ -229,13 +273,59 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->s_empty);
+      if (tc == 0 && threadIdx.x == 64) trace(tr, 9);
     }
+    if (threadIdx.x == 64) trace(tr, 10);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, g.tmem_cols);
+  if (threadIdx.x == 0) {
+    trace(tr, 11);
+    if (tr) tr[(size_t)blockIdx.x * kTraceSlots + 15] = clock64() - tr[(size_t)blockIdx.x * kTraceSlots + 15];
+  }
 }
+
+// MMS_TC_TRACE: print min/avg/max over CTAs of every checkpoint, relative to the first CTA's entry
+struct TraceBuf {
+  long long* dev = nullptr;
+  unsigned grid = 0;
+  int begin(unsigned g) {
+    static const bool tracing = getenv("MMS_TC_TRACE") != nullptr;
+    if (!tracing) return 0;
+    grid = g;
+    MMS_CUDA(cudaMalloc(&dev, sizeof(long long) * kTraceSlots * grid));
+    MMS_CUDA(cudaMemset(dev, 0, sizeof(long long) * kTraceSlots * grid));
+    return 0;
+  }
+  int end(mms_context* ctx, const char* what, const char* const* names) {
+    if (!dev) return 0;
+    long long* h = (long long*)malloc(sizeof(long long) * kTraceSlots * grid);
+    MMS_CUDA(cudaStreamSynchronize(ctx->stream));
+    MMS_CUDA(cudaMemcpy(h, dev, sizeof(long long) * kTraceSlots * grid, cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    long long t0 = h[0];
+    for (unsigned b = 0; b < grid; ++b) t0 = mms_min(t0, h[(size_t)b * kTraceSlots]);
+    double mhz = 0;
+    for (unsigned b = 0; b < grid; ++b)
+      mhz += 1e3 * (double)h[(size_t)b * kTraceSlots + 15] /
+             (double)mms_max<long long>(1, h[(size_t)b * kTraceSlots + 11] - h[(size_t)b * kTraceSlots]);
+    fprintf(stderr, "[fused trace] %s grid %u SM clock %.0f MHz | ns since first entry (min/avg/max over CTAs):", what,
+            grid, mhz / grid);
+    for (int s = 0; s < kTraceSlots - 1; ++s) {
+      long long mn = 1LL << 62, mx = 0; double sum = 0;
+      for (unsigned b = 0; b < grid; ++b) {
+        const long long v = h[(size_t)b * kTraceSlots + s] - t0;
+        mn = mms_min(mn, v); mx = mms_max(mx, v); sum += (double)v;
+      }
+      fprintf(stderr, " %s %lld/%.0f/%lld", names[s], mn, sum / grid, mx);
+    }
+    fprintf(stderr, "\n");
+    free(h);
+    return 0;
+  }
+};
 
 }  // namespace
 
@@ -256,6 +346,7 @@ int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const floa
   g.nkb = mms_ceil_div(D, 32);
   g.nboxes = mms_ceil_div(g.N1, 32);
   g.stage_bytes = mms_ceil_div(mms_max(16384 + g.nboxes * 4096, g.N2 * 128), 1024) * 1024;
+  g.kb2 = mms_max(1, mms_min(4, g.stage_bytes / (g.N2 * 128)));
   int stages = kMaxStages;
   while (stages > 2 && (size_t)stages * g.stage_bytes + sizeof(FwdSmem) + 1024 > 226 * 1024) --stages;
   if ((size_t)stages * g.stage_bytes + sizeof(FwdSmem) + 1024 > 226 * 1024) return MMS_E_UNSUPPORTED;
@@ -280,8 +371,17 @@ int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const floa
   }
   const size_t smem = (size_t)stages * g.stage_bytes + sizeof(FwdSmem) + 1024;
   const unsigned grid = (unsigned)mms_min<long long>(total, ctx->sm_count);
+  TraceBuf tb;
+  MMS_TRY(tb.begin(grid));
   { MmsKernelScope ks_(ctx, "simcross2_fwd_fused_kernel");
-    simcross2_fwd_fused_kernel<<<grid, kThreads, smem, ctx->stream>>>(mapQ, mapM, mapA, B, S, g); }
+    simcross2_fwd_fused_kernel<<<grid, kThreads, smem, ctx->stream>>>(mapQ, mapM, mapA, B, S, g, tb.dev); }
   MMS_LAUNCH_CHECK();
+  static const char* const names[kTraceSlots] = {"entry", "setup", "tma_issued", "first_full", "g1_issued", "t_full",
+                                                 "rounded", "g2_issued", "s_full", "epi0_done", "epi_done", "exit",
+                                                 "g2_st1_prewait", "g2_st1_full", "g2_st2_prewait", "clk"};
+  char what[96];
+  snprintf(what, sizeof(what), "fwd N %d L %dx%d D %d mc %d P %d tiles %u stages %d", N, Lq, La, D, mc, g.P,
+           g.total_tiles, stages);
+  MMS_TRY(tb.end(ctx, what, names));
   return 0;
 }

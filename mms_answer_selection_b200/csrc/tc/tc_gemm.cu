@@ -176,7 +176,7 @@ tc_gemm_kernel(const TcGemmArgs g, const int BN, const int stages, const int b_b
   const int stage_bytes = 16384 + b_bytes;
   Smem* sm = reinterpret_cast<Smem*>(ring + stages * stage_bytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
   const int sps = (g.K + kBK - 1) / kBK;
 
   if (warp == kEpiWarps) {
@@ -231,8 +231,8 @@ tc_gemm_kernel(const TcGemmArgs g, const int BN, const int stages, const int b_b
       }
     }
   } else if (warp == kEpiWarps) {
-    // ------------------------------------------------------------ MMA issue (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issue (whole warp, one elected lane)
+    {
       const uint32_t idesc = idesc_tf32(kBM, BN, A_MN, B_MN);
       int it = 0, tcount = 0;
       for (unsigned t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
@@ -247,15 +247,22 @@ tc_gemm_kernel(const TcGemmArgs g, const int BN, const int stages, const int b_b
           tc_fence_after();
           const uint32_t a_base = smem_u32(ring + s * stage_bytes);
           const uint32_t b_base = a_base + 16384;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int ks = 0; ks < kBK / 8; ++ks) {
-            const uint64_t da = A_MN ? desc_mnmajor(a_base + ks * 1024, 4096) : desc_kmajor(a_base + ks * 32);
-            const uint64_t db = B_MN ? desc_mnmajor(b_base + ks * 1024, 4096) : desc_kmajor(b_base + ks * 32);
-            mma_tf32_ss(acc, da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kBK / 8; ++ks) {
+              const uint64_t da = A_MN ? desc_mnmajor(a_base + ks * 1024, 4096) : desc_kmajor(a_base + ks * 32);
+              const uint64_t db = B_MN ? desc_mnmajor(b_base + ks * 1024, 4096) : desc_kmajor(b_base + ks * 32);
+              mma_tf32_ss(acc, da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            }
+            mma_commit(&sm->empty[s]);
+            if (i == tl.nk - 1) mma_commit(&sm->acc_full[buf]);
           }
-          mma_commit(&sm->empty[s]);
+          __syncwarp();
         }
-        mma_commit(&sm->acc_full[buf]);
+        if (tl.nk == 0) {
+          if (elect_one_sync()) mma_commit(&sm->acc_full[buf]);
+          __syncwarp();
+        }
       }
     }
     __syncwarp();

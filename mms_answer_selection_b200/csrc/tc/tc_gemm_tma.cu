@@ -152,7 +152,7 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   float* epi = reinterpret_cast<float*>(ring + q.stages * stage_bytes);
   Smem* sm = reinterpret_cast<Smem*>(ring + q.stages * stage_bytes + kEpiBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
   const int sps = (g.K + kBK - 1) / kBK;
   const int BN = q.BN, stages = q.stages;
   if (threadIdx.x == 0) trace(tr, 0);
@@ -177,8 +177,8 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (threadIdx.x == 0) trace(tr, 1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer: the whole warp walks the
+    {                                                            // loops, one elected lane issues (umma.cuh)
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
       const int b_blocks = (BN + 31) >> 5;
       int it = 0;
@@ -194,28 +194,31 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
           uint8_t* a_dst = ring + s * stage_bytes;
           uint8_t* b_dst = a_dst + 16384;
-          mbar_arrive_expect_tx(&sm->full[s], tx_bytes);
-          if (!A_MN) {
-            tma_load_5d(a_dst, &mapA, &sm->full[s], k0, tl.m0, az2, az1, seg * q.a_seg);
-          } else {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&sm->full[s], tx_bytes);
+            if (!A_MN) {
+              tma_load_5d(a_dst, &mapA, &sm->full[s], k0, tl.m0, az2, az1, seg * q.a_seg);
+            } else {
 #pragma unroll
-            for (int b = 0; b < kBM / 32; ++b)
-              tma_load_5d(a_dst + b * 4096, &mapA, &sm->full[s], tl.m0 + 32 * b, k0, az2, az1, seg * q.a_seg);
+              for (int b = 0; b < kBM / 32; ++b)
+                tma_load_5d(a_dst + b * 4096, &mapA, &sm->full[s], tl.m0 + 32 * b, k0, az2, az1, seg * q.a_seg);
+            }
+            if (!B_MN) {
+              tma_load_5d(b_dst, &mapB, &sm->full[s], k0, tl.n0, bz2, bz1, seg * q.b_seg);
+            } else {
+              for (int b = 0; b < b_blocks; ++b)
+                tma_load_5d(b_dst + b * 4096, &mapB, &sm->full[s], tl.n0 + 32 * b, k0, bz2, bz1, seg * q.b_seg);
+            }
           }
-          if (!B_MN) {
-            tma_load_5d(b_dst, &mapB, &sm->full[s], k0, tl.n0, bz2, bz1, seg * q.b_seg);
-          } else {
-            for (int b = 0; b < b_blocks; ++b)
-              tma_load_5d(b_dst + b * 4096, &mapB, &sm->full[s], tl.n0 + 32 * b, k0, bz2, bz1, seg * q.b_seg);
-          }
+          __syncwarp();
         }
       }
-      trace(tr, 2);
+      if (lane == 0) trace(tr, 2);
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issue (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issue (whole warp, one elected lane)
+    {
       const uint32_t idesc = idesc_tf32(kBM, BN, A_MN, B_MN);
       int it = 0, tcount = 0;
       for (unsigned t = blockIdx.x; t < q.total_tiles; t += gridDim.x, ++tcount) {
@@ -228,20 +231,27 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const int s = it % stages;
           mbar_wait(&sm->full[s], (it / stages) & 1);
           tc_fence_after();
-          if (it == 0) trace(tr, 3);
+          if (it == 0 && lane == 0) trace(tr, 3);
           const uint32_t a_base = smem_u32(ring + s * stage_bytes);
           const uint32_t b_base = a_base + 16384;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int ks = 0; ks < kBK / 8; ++ks) {
-            const uint64_t da = A_MN ? desc_mnmajor(a_base + ks * 1024, 4096) : desc_kmajor(a_base + ks * 32);
-            const uint64_t db = B_MN ? desc_mnmajor(b_base + ks * 1024, 4096) : desc_kmajor(b_base + ks * 32);
-            mma_tf32_ss(acc, da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kBK / 8; ++ks) {
+              const uint64_t da = A_MN ? desc_mnmajor(a_base + ks * 1024, 4096) : desc_kmajor(a_base + ks * 32);
+              const uint64_t db = B_MN ? desc_mnmajor(b_base + ks * 1024, 4096) : desc_kmajor(b_base + ks * 32);
+              mma_tf32_ss(acc, da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            }
+            mma_commit(&sm->empty[s]);
+            if (i == tl.nk - 1) mma_commit(&sm->acc_full[buf]);
           }
-          mma_commit(&sm->empty[s]);
+          __syncwarp();
         }
-        mma_commit(&sm->acc_full[buf]);
+        if (tl.nk == 0) {                                        // nothing to reduce: hand over an untouched accumulator
+          if (elect_one_sync()) mma_commit(&sm->acc_full[buf]);
+          __syncwarp();
+        }
       }
-      trace(tr, 4);
+      if (lane == 0) trace(tr, 4);
     }
     __syncwarp();
   } else {

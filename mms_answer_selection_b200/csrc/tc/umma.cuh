@@ -26,6 +26,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (elect.sync).  Issue TMA / tcgen05.mma / tcgen05.commit under
+// `if (elect_one_sync())` with the surrounding loops executed by the WHOLE warp: ptxas then keeps the operands in
+// uniform registers.  Guarding with `lane == 0` instead makes it wrap every UTMALDG / UTCHMMA in a
+// per-thread "waterfall" loop (ELECT / R2UR / BRA.U.ANY), ~170 cycles per instruction issued.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ------------------------------------------------------------------ mbarrier -------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

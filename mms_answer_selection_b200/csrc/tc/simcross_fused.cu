@@ -27,6 +27,7 @@
 #include "../mms_common.cuh"
 #include "tc_gemm.cuh"
 #include "umma.cuh"
+#include "fused_trace.cuh"
 
 namespace {
 
@@ -57,15 +58,6 @@ struct FwdSmem {
   uint32_t tmem_base;
 };
 
-// Optional per-CTA timeline (MMS_TC_TRACE=1): globaltimer stamps at 12 checkpoints.
-constexpr int kTraceSlots = 16;
-__device__ __forceinline__ void trace(long long* tr, int slot) {
-  if (!tr) return;
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  tr[(size_t)blockIdx.x * kTraceSlots + slot] = (long long)t;
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapM,
                            const __grid_constant__ CUtensorMap mapA, const float* __restrict__ Bias,
@@ -77,7 +69,7 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
   const int stages = g.stages;
   const int nch = (g.N1 + 31) >> 5;
-  if (threadIdx.x == 0) { trace(tr, 0); if (tr) tr[(size_t)blockIdx.x * kTraceSlots + 15] = clock64(); }
+  if (threadIdx.x == 0) trace_begin(tr);
 
   if (warp == 1) {
     if (lane == 0) {
@@ -281,51 +273,8 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, g.tmem_cols);
-  if (threadIdx.x == 0) {
-    trace(tr, 11);
-    if (tr) tr[(size_t)blockIdx.x * kTraceSlots + 15] = clock64() - tr[(size_t)blockIdx.x * kTraceSlots + 15];
-  }
+  if (threadIdx.x == 0) trace_end(tr);
 }
-
-// MMS_TC_TRACE: print min/avg/max over CTAs of every checkpoint, relative to the first CTA's entry
-struct TraceBuf {
-  long long* dev = nullptr;
-  unsigned grid = 0;
-  int begin(unsigned g) {
-    static const bool tracing = getenv("MMS_TC_TRACE") != nullptr;
-    if (!tracing) return 0;
-    grid = g;
-    MMS_CUDA(cudaMalloc(&dev, sizeof(long long) * kTraceSlots * grid));
-    MMS_CUDA(cudaMemset(dev, 0, sizeof(long long) * kTraceSlots * grid));
-    return 0;
-  }
-  int end(mms_context* ctx, const char* what, const char* const* names) {
-    if (!dev) return 0;
-    long long* h = (long long*)malloc(sizeof(long long) * kTraceSlots * grid);
-    MMS_CUDA(cudaStreamSynchronize(ctx->stream));
-    MMS_CUDA(cudaMemcpy(h, dev, sizeof(long long) * kTraceSlots * grid, cudaMemcpyDeviceToHost));
-    cudaFree(dev);
-    long long t0 = h[0];
-    for (unsigned b = 0; b < grid; ++b) t0 = mms_min(t0, h[(size_t)b * kTraceSlots]);
-    double mhz = 0;
-    for (unsigned b = 0; b < grid; ++b)
-      mhz += 1e3 * (double)h[(size_t)b * kTraceSlots + 15] /
-             (double)mms_max<long long>(1, h[(size_t)b * kTraceSlots + 11] - h[(size_t)b * kTraceSlots]);
-    fprintf(stderr, "[fused trace] %s grid %u SM clock %.0f MHz | ns since first entry (min/avg/max over CTAs):", what,
-            grid, mhz / grid);
-    for (int s = 0; s < kTraceSlots - 1; ++s) {
-      long long mn = 1LL << 62, mx = 0; double sum = 0;
-      for (unsigned b = 0; b < grid; ++b) {
-        const long long v = h[(size_t)b * kTraceSlots + s] - t0;
-        mn = mms_min(mn, v); mx = mms_max(mx, v); sum += (double)v;
-      }
-      fprintf(stderr, " %s %lld/%.0f/%lld", names[s], mn, sum / grid, mx);
-    }
-    fprintf(stderr, "\n");
-    free(h);
-    return 0;
-  }
-};
 
 }  // namespace
 
@@ -378,7 +327,8 @@ int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const floa
   MMS_LAUNCH_CHECK();
   static const char* const names[kTraceSlots] = {"entry", "setup", "tma_issued", "first_full", "g1_issued", "t_full",
                                                  "rounded", "g2_issued", "s_full", "epi0_done", "epi_done", "exit",
-                                                 "g2_st1_prewait", "g2_st1_full", "g2_st2_prewait", "clk"};
+                                                 "g2_st1_prewait", "g2_st1_full", "g2_st2_prewait", nullptr,
+                                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char what[96];
   snprintf(what, sizeof(what), "fwd N %d L %dx%d D %d mc %d P %d tiles %u stages %d", N, Lq, La, D, mc, g.P,
            g.total_tiles, stages);

@@ -92,10 +92,70 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
   return 0;
 }
 
+namespace {
+
+// dM_k += Qall^T U[k]   (= sum_n Q_n^T G_nk A_n, sim_cross_layer.cpp:286-289): reduction over all token rows,
+// split over CTAs so that one full wave runs (a 149th tile would double the kernel's time)
+int gemm_dM(mms_context* ctx, const float* qr, const float* U, float* dM, int rows, int D, int Dp, int mc) {
+  TcGemmArgs g = tc_gemm_args(qr, Dp, 1, U, Dp, 1, dM, D, D, D, rows, TC_ATOMIC);
+  g.nb1 = mc; g.sB1 = (long long)rows * Dp; g.sC1 = (long long)D * D;
+  const int tiles = mc * mms_ceil_div(D, 128) * mms_ceil_div(D, 256);
+  g.ksplit = mms_max(1, mms_min(ctx->sm_count / mms_max(tiles, 1), mms_ceil_div(rows, 128)));
+  g.operands_tf32 = 1;
+  return mms_tc_gemm(ctx, g);
+}
+
+int backward_fused(mms_context* ctx, const float* q, const float* a, const float* Mw, const float* dS, float* dq,
+                   float* da, float* dM, int N, int Lq, int La, int D, int mc) {
+  const int Dp = (D + 31) & ~31;
+  // scratch per pair: rounded q and a rows + the exported U (mc x Lq x Dp)
+  const size_t per_pair = (size_t)(Lq + La) * Dp + (size_t)mc * Lq * Dp;
+  const size_t fixed = (size_t)mc * D * Dp;
+  const long long cap = ((long long)(ctx->scratch_cap / sizeof(float)) - (long long)fixed) / (long long)per_pair;
+  const int nc_max = (int)mms_max<long long>(1, mms_min<long long>(cap, N));
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * (fixed + per_pair * nc_max), &sp));
+  float* Mr = static_cast<float*>(sp);
+  float* qr = Mr + fixed;
+  float* ar = qr + (size_t)nc_max * Lq * Dp;
+  float* U = ar + (size_t)nc_max * La * Dp;
+  MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));   // :256
+  for (int n0 = 0; n0 < N; n0 += nc_max) {
+    const int nc = mms_min(nc_max, N - n0);
+    float* dqc = dq + (size_t)n0 * Lq * D;
+    float* dac = da + (size_t)n0 * La * D;
+    const float* dSc = dS + (size_t)n0 * mc * Lq * La;
+    const RoundJob jobs[3] = {
+        {q + (size_t)n0 * Lq * D, qr, (long long)nc * Lq, D, D, Dp, nullptr},
+        {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
+        {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
+    MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
+    int ksplit = 1;
+    MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctx->sm_count, &ksplit));
+    if (ksplit > 1) {   // the measures of one tile are spread over CTAs that add into the output
+      MMS_CUDA(cudaMemsetAsync(dqc, 0, sizeof(float) * (size_t)nc * Lq * D, ctx->stream));
+      MMS_CUDA(cudaMemsetAsync(dac, 0, sizeof(float) * (size_t)nc * La * D, ctx->stream));
+    }
+    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp));   // :291-294
+    MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));                                           // :286-289
+    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp));  // :296-299
+  }
+  return 0;
+}
+
+}  // namespace
+
 // Computes dq, da (overwritten) and dM (overwritten: zeroed here, :256).  dB is left to the caller.
 int mms_tc_simcross2_backward(mms_context* ctx, const float* q, const float* a, const float* Mw,
                               const float* dS, float* dq, float* da, float* dM, int N, int Lq, int La,
                               int D, int mc) {
+  {  // fused kernels for dq / da (tc/simcross_fused_bwd.cu) + one GEMM for dM, when the shape allows
+    int ksplit = 1;
+    if (mms_tc_simcross2_backward_fused_plan(0, N, Lq, La, D, mc, ctx->sm_count, &ksplit) == 0) {
+      const int rc = backward_fused(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
+      if (rc != MMS_E_UNSUPPORTED) return rc;
+    }
+  }
   const Plan p = make_plan(ctx, N, Lq, La, D, mc, true);
   const int Dp = p.Dp, Lap = p.Lap, Lmax = mms_max(Lq, La);
   void* sp = nullptr;

@@ -118,7 +118,9 @@ int mms_create(mms_handle_t* out) {
   ctx->sm_count = sms;
   cudaError_t e = cudaMalloc(&ctx->fault_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->fault_flag, 0, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->partials, 1024 * sizeof(double));
+  // 1024 block partials + one ticket word (zero between launches) for the single-launch reductions
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->partials, 1025 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(ctx->partials, 0, 1025 * sizeof(double));
   if (e != cudaSuccess) {
     mms_set_error("context allocation failed: %s", cudaGetErrorString(e));
     delete ctx;

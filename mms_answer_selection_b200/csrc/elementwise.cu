@@ -127,15 +127,31 @@ __global__ void fm_backward_kernel(const T* __restrict__ x, const T* __restrict_
   }
 }
 
+// out = sum_i x[i] * (yv ? yv[i] : 1) in ONE launch: every block leaves its partial sum, the block that draws the
+// last ticket adds the partials in index order (the result does not depend on which block that is) and re-arms
+// the ticket for the next launch on this handle.
 template <typename T>
 __global__ void __launch_bounds__(kRedThreads)
-sum_kernel(const T* __restrict__ x, const T* __restrict__ yv, long long n, T* __restrict__ partials) {
+sum_kernel(const T* __restrict__ x, const T* __restrict__ yv, long long n, T* __restrict__ partials,
+           unsigned int* __restrict__ ticket, T* __restrict__ out) {
   T acc = T(0);
   for (long long i = blockIdx.x * (long long)kRedThreads + threadIdx.x; i < n;
        i += (long long)gridDim.x * kRedThreads)
     acc += yv ? x[i] * yv[i] : x[i];
   acc = block_sum(acc);
-  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  T v = T(0);
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kRedThreads) v += __ldcg(partials + i);
+  v = block_sum(v);
+  if (threadIdx.x == 0) { *out = v; *ticket = 0u; }
 }
 
 template <typename T>
@@ -223,11 +239,9 @@ int mms_dot_impl(mms_context* ctx, const T* x, const T* y, long long n, T* out) 
   sp = ctx->partials;     // a private buffer: the scratch buffer may hold SimCross's forward cache
   T* partials = static_cast<T*>(sp);
   const int grid = red_grid(ctx, n);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(static_cast<double*>(ctx->partials) + 1024);
   { MmsKernelScope ks_(ctx, "sum_kernel");
-    sum_kernel<T><<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, partials); }
-  MMS_LAUNCH_CHECK();
-  { MmsKernelScope ks_(ctx, "finish_sum_kernel");
-    finish_sum_kernel<T><<<1, kRedThreads, 0, ctx->stream>>>(partials, grid, T(1), out); }
+    sum_kernel<T><<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, partials, ticket, out); }
   MMS_LAUNCH_CHECK();
   return 0;
 }

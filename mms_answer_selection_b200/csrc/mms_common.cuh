@@ -171,10 +171,10 @@ int mms_tc_simcross2_forward_fused(mms_context*, const float* qr, const float* a
                                    const float* B, float* S, int N, int Lq, int La, int D, int mc, int Dp);
 // fused bottom gradients (tc/simcross_fused_bwd.cu): which = 0 dq (xr = rounded answers; exports U = G A for the
 // dM contraction), which = 1 da (xr = rounded questions).  _plan tells whether the shape is covered and how many
-// CTAs share one tile's measures (> 1: `out` must be zeroed by the caller).
-int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int sm_count, int* ksplit);
+// of the `ctas` CTAs it may use share one tile's measures (> 1: `out` must be zeroed by the caller).
+int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int* ksplit);
 int mms_tc_simcross2_backward_fused(mms_context*, int which, const float* xr, const float* Mr, const float* dS,
-                                    float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp);
+                                    float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp, int ksplit);
 // (dq, da, dM overwritten; dB is accumulated by the caller)
 int mms_tc_simcross2_backward(mms_context*, const float* q, const float* a, const float* Mw,
                               const float* dS, float* dq, float* da, float* dM, int N, int Lq, int La,

@@ -405,7 +405,8 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
 // xr (rows x Dp) and Mr (mc x D x Dp) are TF32-rounded copies with 128-byte-aligned rows; dS is read as is.
 // ksplit > 1 accumulates with atomics: the caller must have zeroed `out`.  Returns MMS_E_UNSUPPORTED for shapes the
 // tile does not cover.
-int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int sm_count, int* ksplit) {
+int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int* ksplit) {
+  const int sm_count = ctas;
   static const bool disabled = getenv("MMS_NO_FUSED") != nullptr || getenv("MMS_NO_FUSED_BWD") != nullptr;
   if (disabled) return MMS_E_UNSUPPORTED;
   if (Lq > 128 || La > 128 || N < 1) return MMS_E_UNSUPPORTED;
@@ -424,10 +425,14 @@ int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D
 }
 
 int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr, const float* Mr, const float* dS,
-                                    float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp) {
+                                    float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp,
+                                    int ksplit) {
   BwdGeom g;
-  int ksplit = 1;
-  MMS_TRY(mms_tc_simcross2_backward_fused_plan(which, N, Lq, La, D, mc, ctx->sm_count, &ksplit));
+  {
+    int unused = 1;
+    MMS_TRY(mms_tc_simcross2_backward_fused_plan(which, N, Lq, La, D, mc, ctx->sm_count, &unused));
+    MMS_REQUIRE(ksplit >= 1 && ksplit <= mc, MMS_E_INVALID, "bad measure split");
+  }
   const bool DA = which != 0;
   g.N = N; g.Lq = Lq; g.La = La; g.D = D; g.mc = mc;
   g.Lr = DA ? La : Lq; g.Lk = DA ? Lq : La;

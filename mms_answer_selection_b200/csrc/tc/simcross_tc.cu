@@ -66,6 +66,11 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
   float* qr = Mr + p.fixed;
   float* ar = qr + (size_t)p.nc_max * Lq * Dp;
   float* Tk = ar + (size_t)p.nc_max * La * Dp;
+  // the rounded copies stay in the scratch buffer: a backward on the same handle may reuse them (MMS_OPT_REUSE_FORWARD)
+  struct CacheMark {
+    mms_context* c; bool ok;
+    ~CacheMark() { c->fwd_cache.valid = ok; }
+  } mark{ctx, false};
   for (int n0 = 0; n0 < N; n0 += p.nc_max) {
     const int nc = mms_min(p.nc_max, N - n0);
     float* Sc = S + (size_t)n0 * mc * Lq * La;
@@ -76,7 +81,14 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
     MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
     {  // one kernel for both contractions, T stays in tensor memory (tc/simcross_fused.cu)
       const int rc = mms_tc_simcross2_forward_fused(ctx, qr, ar, Mr, B, Sc, nc, Lq, La, D, mc, Dp);
-      if (rc == 0) continue;
+      if (rc == 0) {
+        if (nc == N) {
+          mms_context::FwdCache& fc = ctx->fwd_cache;
+          fc.q = q; fc.a = a; fc.M = Mw; fc.N = N; fc.Lq = Lq; fc.La = La; fc.D = D; fc.mc = mc;
+          mark.ok = true;
+        }
+        continue;
+      }
       if (rc != MMS_E_UNSUPPORTED) return rc;
     }
     MMS_TRY(gemm_T(ctx, qr, Mr, Tk, nc * Lq, D, Dp, mc));                  // sim_cross_layer.cpp:148-149
@@ -113,13 +125,22 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
   const size_t fixed = (size_t)mc * D * Dp;
   const long long cap = ((long long)(ctx->scratch_cap / sizeof(float)) - (long long)fixed) / (long long)per_pair;
   const int nc_max = (int)mms_max<long long>(1, mms_min<long long>(cap, N));
-  void* sp = nullptr;
-  MMS_TRY(mms_scratch(ctx, sizeof(float) * (fixed + per_pair * nc_max), &sp));
+  // MMS_OPT_REUSE_FORWARD: the last forward on this handle left the rounded q, a and M at the head of the scratch
+  // buffer (same layout: Mr | qr | ar | per-measure intermediate) and nothing has touched the buffer since
+  const mms_context::FwdCache& fc = ctx->fwd_cache;
+  const size_t need = sizeof(float) * (fixed + per_pair * nc_max);
+  const bool reuse = ctx->reuse_forward && fc.valid && fc.q == q && fc.a == a && fc.M == Mw && fc.N == N &&
+                     fc.Lq == Lq && fc.La == La && fc.D == D && fc.mc == mc && nc_max == N && need <= ctx->scratch_bytes;
+  void* sp = ctx->scratch;
+  if (!reuse) MMS_TRY(mms_scratch(ctx, need, &sp));
   float* Mr = static_cast<float*>(sp);
   float* qr = Mr + fixed;
   float* ar = qr + (size_t)nc_max * Lq * Dp;
   float* U = ar + (size_t)nc_max * La * Dp;
   MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));   // :256
+  // dq (+ U, dM) and da are independent: with MMS_OPT_CONCURRENCY the da kernel runs on a private stream and each
+  // kernel is sized for half of the SMs when the batch is too small to fill them
+  const bool conc = ctx->concurrency != 0;
   for (int n0 = 0; n0 < N; n0 += nc_max) {
     const int nc = mms_min(nc_max, N - n0);
     float* dqc = dq + (size_t)n0 * Lq * D;
@@ -129,16 +150,23 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
         {q + (size_t)n0 * Lq * D, qr, (long long)nc * Lq, D, D, Dp, nullptr},
         {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
         {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
-    MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
+    if (!reuse) MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
+    const int ctas = conc ? mms_max(1, ctx->sm_count / 2) : ctx->sm_count;
     int ksplit = 1;
-    MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctx->sm_count, &ksplit));
+    MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctas, &ksplit));
     if (ksplit > 1) {   // the measures of one tile are spread over CTAs that add into the output
       MMS_CUDA(cudaMemsetAsync(dqc, 0, sizeof(float) * (size_t)nc * Lq * D, ctx->stream));
       MMS_CUDA(cudaMemsetAsync(dac, 0, sizeof(float) * (size_t)nc * La * D, ctx->stream));
     }
-    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp));   // :291-294
-    MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));                                           // :286-289
-    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp));  // :296-299
+    if (conc) {
+      MMS_TRY(mms_fork(ctx, 0));
+      MmsStreamSwitch sw(ctx, 0);
+      MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit));  // :296-299
+    }
+    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp, ksplit));   // :291-294
+    MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));                                                   // :286-289
+    if (conc) MMS_TRY(mms_join(ctx, 0));
+    else MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit));
   }
   return 0;
 }

@@ -46,7 +46,12 @@ class MMSNet(object):
         self.sim.SetUp([self.q, self.a], [self.S])
         if math is not None:
             self.sim.set_math(math)
+        # Net::ForwardBackward drives Backward right after Forward on unchanged bottoms and weights, so SimCross
+        # backward may reuse the TF32-rounded operands its forward left in the workspace
+        from . import _lib
+        self.sim.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 1)
         self._pinned = None
+        self._side = None
 
     # learnable params in net order, shared blobs once (net.cpp:440-530)
     def params(self):
@@ -101,6 +106,47 @@ class MMSNet(object):
         self.Backward()
         return loss
 
+    def ForwardBackwardConcurrent(self, with_loss=True, clear_diffs=True):
+        """The same step with its independent pieces on forked streams (the reference's Net runs layers one
+        after the other on the legacy stream, net.cpp:535-591; the data dependencies are all that matters):
+
+            ClearParamDiffs ----------------------------\
+            Embed(q) --\                                 +--> SimCross bwd --> Embed(q) bwd --\
+            Embed(a) ---+--> SimCross fwd (+ loss dot) --/                \--> Embed(a) bwd ---+--> done
+
+        (SimCross backward forks its own da branch inside the library.)  Works eagerly and under stream
+        capture; every side stream is joined back into the current stream before returning."""
+        if self._side is None:
+            self._side = (torch.cuda.Stream(), torch.cuda.Stream())
+        main = torch.cuda.current_stream()
+        s1, s2 = self._side
+        s1.wait_stream(main)
+        s2.wait_stream(main)
+        if clear_diffs:
+            with torch.cuda.stream(s1):
+                self.ClearParamDiffs()
+        with torch.cuda.stream(s2):
+            self.embed_a.Forward([self.idx_a], [self.a])
+        self.embed_q.Forward([self.idx_q], [self.q])
+        main.wait_stream(s2)
+        if with_loss:
+            loss = self.sim.Forward([self.q, self.a], [self.S])
+        else:
+            saved, self.sim.loss_ = self.sim.loss_, []
+            try:
+                self.sim.Forward([self.q, self.a], [self.S])
+            finally:
+                self.sim.loss_ = saved
+            loss = 0.0
+        main.wait_stream(s1)                                   # diffs are cleared before anything accumulates
+        self.sim.Backward([self.S], [True, True], [self.q, self.a])
+        s2.wait_stream(main)
+        with torch.cuda.stream(s2):                            # both scatter-adds go into the shared dW with atomics
+            self.embed_a.Backward([self.a], [False], [self.idx_a])
+        self.embed_q.Backward([self.q], [False], [self.idx_q])
+        main.wait_stream(s2)
+        return loss
+
     # -- CUDA-graph replay of the whole step ----------------------------------------------
     # The step is ~15 short kernels; issued one by one from the host it is launch-bound
     # (the reference has the same problem in the small: 2*N*mc host BLAS calls).  Recording
@@ -113,16 +159,12 @@ class MMSNet(object):
         try:
             with torch.cuda.stream(side):
                 for _ in range(2):                      # sizes scratch, fills the tensor-map cache
-                    if clear_diffs:
-                        self.ClearParamDiffs()
-                    self.ForwardBackward(with_loss)
+                    self.ForwardBackwardConcurrent(with_loss, clear_diffs)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                if clear_diffs:
-                    self.ClearParamDiffs()
-                self.ForwardBackward(with_loss)
+                self.ForwardBackwardConcurrent(with_loss, clear_diffs)
         finally:
             self.sim.defer_loss_ = False
         self._graph = graph

@@ -41,6 +41,19 @@ def flops_per_pair(L, D, mc):
     return mc * (6.0 * L * D * D + 8.0 * L * L * D)
 
 
+def kernel_flop_shares(L, D, mc):
+    """How the algorithmic FLOPs of one (pair, measure) -- SURVEY.md 8(d): fwd 2LD(D+L), bwd minimum
+    2LD^2 (A M^T) + 3 * 2L^2D (dQ, dA, dS A) + 2LD^2 (dM) -- are attributed to the kernels that produce them
+    (DESIGN.md 3.1).  The dA kernel re-derives its D x D product instead of reading T from the forward, so it is
+    credited with the 2L^2D of dA only; the shares add up to 6LD^2 + 8L^2D."""
+    return {
+        "simcross2_fwd_fused_kernel": mc * 2.0 * L * D * (D + L),
+        "simcross2_bwd_fused_kernel<dQ>": mc * (2.0 * L * D * D + 4.0 * L * L * D),   # A M^T, dQ and U = dS A
+        "simcross2_bwd_fused_kernel<dA>": mc * 2.0 * L * L * D,
+        "tc_gemm_tma_kernel": mc * 2.0 * L * D * D,                                   # dM = Q^T U
+    }
+
+
 def workload_config(name, world=1):
     """Per-rank configuration: C3 fixes the GLOBAL batch (4096), so a rank gets 4096 / world pairs."""
     from mms_answer_selection_b200 import synth
@@ -293,6 +306,8 @@ def main_ours(args):
     # host launch latency.
     sim_state = net.sim.defer_loss_
     net.sim.defer_loss_ = True
+    from mms_answer_selection_b200 import _lib as _mmslib
+    net.sim.handle.set_option(_mmslib.MMS_OPT_CONCURRENCY, 0)     # one kernel at a time: the events bracket it alone
     for h in handles:
         h.profile_enable(True)
     prof_steps = min(args.steps, 20)
@@ -302,6 +317,7 @@ def main_ours(args):
         eager_step()
         torch.cuda.synchronize()
     net.sim.defer_loss_ = sim_state
+    net.sim.handle.set_option(_mmslib.MMS_OPT_CONCURRENCY, 1)
     prof = {}
     for h in handles:
         for k, (n, ms) in h.profile_report().items():
@@ -315,7 +331,7 @@ def main_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roof = roofline_for(dom[0], dom[1], prof, prof_steps, cfg, peaks)
+    roof = roofline_for(dom[0], dom[1], prof, prof_steps, cfg, peaks, wl)
 
     value = N * world * args.steps / (total_ms / 1e3)
     e2e_value = N * world * args.steps / (e2e_ms / 1e3)
@@ -456,25 +472,50 @@ def extras(world, rank, flush):
     return out
 
 
-def roofline_for(name, rec, prof, steps, cfg, peaks):
+def ncu_traffic(wl, name):
+    """DRAM bytes per launch of kernel `name` from the committed `ncu --set full` capture of this workload
+    (profiles/r01_ncu_full_<wl>_fused.json, tools/ncu_summary.py), or None."""
+    alias = {"simcross2_bwd_fused_kernel<dQ>": "simcross2_bwd_fused_kernel<0>",
+             "simcross2_bwd_fused_kernel<dA>": "simcross2_bwd_fused_kernel<1>"}
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_%s_fused.json" % wl)))
+    except Exception:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows:
+        if r.get("kernel") == alias.get(name, name):
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = r[k].split()
+                tot += float(v) * scale.get(u, 1.0)
+            return tot
+    return None
+
+
+def roofline_for(name, rec, prof, steps, cfg, peaks, wl):
     """Roofline entry for the dominant kernel `name` (launch count, total ms over `steps`)."""
     n, ms = rec
     per_launch_s = ms / n / 1e3
     N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
     launches_per_step = n / steps
+    shares = kernel_flop_shares(L, D, mc)
     tensor_kernels = ("simcross", "tc_", "simt_gemm")
     if any(t in name for t in tensor_kernels):
-        # the contraction kernels share the algorithmic FLOPs of the step in proportion to
-        # their launches; conservative: attribute the whole SimCross FLOPs to the dominant
-        # kernel family and divide by the family's total device time.
-        fam_ms = sum(m for k, (_, m) in prof.items() if any(t in k for t in tensor_kernels))
-        flops_step = N * flops_per_pair(L, D, mc)
-        achieved = flops_step * steps / (fam_ms / 1e3) / 1e12
         peak = peaks.get("bf16_tflops", 1590.0) / 2.0       # TF32 dense = half the bf16 rate
+        flops_launch = N * shares.get(name, 0.0) / max(launches_per_step, 1.0)
+        achieved = flops_launch / per_launch_s / 1e12
+        # the whole step: all algorithmic FLOPs over the summed device time of every contraction kernel
+        fam_ms = sum(m for k, (_, m) in prof.items() if any(t in k for t in tensor_kernels))
+        step_achieved = N * flops_per_pair(L, D, mc) * steps / (fam_ms / 1e3) / 1e12
         return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
-                "note": "algorithmic SimCross fwd+bwd FLOPs / summed device time of the contraction kernels; "
-                        "peak = measured cuBLAS bf16 burst / 2 (TF32), %s" % ("of measured" if peaks else "of fallback")}
+                "frac": achieved / peak, "traffic": ncu_traffic(wl, name),
+                "flops_per_launch": flops_launch, "ms_per_launch": per_launch_s * 1e3,
+                "step_contractions": {"achieved": step_achieved, "frac": step_achieved / peak,
+                                      "ms_per_step": fam_ms / steps},
+                "note": "algorithmic FLOPs attributed to this kernel (DESIGN.md 3.1) per launch / its mean launch time "
+                        "(CUDA events, one kernel at a time); step_contractions = all 6LD^2+8L^2D FLOPs / summed time of "
+                        "the contraction kernels; peak = measured cuBLAS bf16 burst / 2 (TF32), %s; traffic = DRAM "
+                        "bytes per launch from profiles/r01_ncu_full_%s_fused.json" % ("of measured" if peaks else "of fallback", wl)}
     rows = N * 2 * L
     bytes_launch = rows * (4 + 8 * D) / max(launches_per_step, 1) * 1.0
     achieved = bytes_launch / per_launch_s / 1e9

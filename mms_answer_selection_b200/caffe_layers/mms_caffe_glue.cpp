@@ -25,6 +25,11 @@ mms_handle_t handle() {
     th.device = dev;
     // legacy default stream 0: implicit ordering with every other Caffe layer
     MMS_CAFFE_CHECK(mms_set_stream(th.h, nullptr));
+    // Net::ForwardBackward / GradientChecker run a layer's Backward right after its Forward on unchanged bottoms
+    // and weights (net.cpp:535-591), so SimCross backward may reuse the TF32-rounded operands the forward left
+    // in the workspace.  The library checks pointers and sizes and re-rounds whenever another call touched the
+    // workspace in between (e.g. a second SimCross layer on this thread).
+    MMS_CAFFE_CHECK(mms_set_option(th.h, MMS_OPT_REUSE_FORWARD, 1));
   }
   return th.h;
 }

@@ -284,6 +284,17 @@ int mms_simcross_backward_impl(mms_context* ctx, int mode, const T* q, const T* 
   if (mode == 2) {
     MMS_REQUIRE(Mw && dM && mc > 0, MMS_E_INVALID, "mode 2 needs M, dM and mesure_count > 0");
     int rc = MMS_E_UNSUPPORTED;
+    // dB depends on dS only: with MMS_OPT_CONCURRENCY it is reduced on a private stream beside the contractions
+    const bool side_bias = dB && ctx->concurrency;
+    if (side_bias) {
+      MMS_TRY(mms_fork(ctx, 1));
+      MmsStreamSwitch sw(ctx, 1);
+      MMS_TRY(simcross2_bias_grad<T>(ctx, dS, dB, N, Lq, La, mc));
+    }
+    struct Join {                       // every exit path joins the side stream back
+      mms_context* c; bool on;
+      ~Join() { if (on) mms_join(c, 1); }
+    } join_bias{ctx, side_bias};
     if (IsFloat<T>::value && ctx->math == MMS_MATH_TF32)
       rc = tc_bwd(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
     if (rc == MMS_E_UNSUPPORTED) {
@@ -293,7 +304,7 @@ int mms_simcross_backward_impl(mms_context* ctx, int mode, const T* q, const T* 
       rc = simcross2_backward_simt<T>(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
     }
     MMS_TRY(rc);
-    if (dB) MMS_TRY(simcross2_bias_grad<T>(ctx, dS, dB, N, Lq, La, mc));
+    if (dB && !side_bias) MMS_TRY(simcross2_bias_grad<T>(ctx, dS, dB, N, Lq, La, mc));
     return 0;
   }
   MMS_REQUIRE(S, MMS_E_INVALID, "modes 0/1 read the forward output");

@@ -147,16 +147,17 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
           tc_fence_after();
           if (it == 0 && lane == 0) trace(tr, 3);
           const uint32_t a_base = smem_u32(ring + s * g.stage_bytes);
-          const uint32_t b_base = a_base + 16384;
+          const uint32_t a_lo = desc_lo_k(a_base), b_lo = desc_lo_mn(a_base + 16384, 4096);
+          const uint32_t b1_lo = b_lo + (uint32_t)(np0 >> 5) * (4096u >> 4);
           if (elect_one_sync()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               if (b * 32 + ks * 8 < g.D) {
                 const uint32_t acc = (b > 0 || ks > 0) ? 1u : 0u;
-                const uint64_t da = desc_kmajor(a_base + ks * 32);
-                mma_tf32_ss(tmem, da, desc_mnmajor(b_base + ks * 1024, 4096), idesc_p0, acc);
+                mma_tf32_ss_lh(tmem, a_lo + ks * kDescStepK, kDescHiK, b_lo + ks * kDescStepMN, kDescHiMN, idesc_p0, acc);
                 if (np1 > 0)
-                  mma_tf32_ss(tmem + np0, da, desc_mnmajor(b_base + (np0 >> 5) * 4096 + ks * 1024, 4096), idesc_p1, acc);
+                  mma_tf32_ss_lh(tmem + np0, a_lo + ks * kDescStepK, kDescHiK, b1_lo + ks * kDescStepMN, kDescHiMN,
+                                 idesc_p1, acc);
               }
             }
             mma_commit(&sm->empty[s]);
@@ -177,13 +178,13 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
             const int b = b0 + j;
             mbar_wait(&sm->t_ready[b], tc & 1);                  // T columns [32 b, 32 b + 32) are rounded
             tc_fence_after();
-            const uint32_t b_base = smem_u32(ring + s * g.stage_bytes) + (uint32_t)j * (uint32_t)g.N2 * 128u;
+            const uint32_t b_lo = desc_lo_k(smem_u32(ring + s * g.stage_bytes) + (uint32_t)j * (uint32_t)g.N2 * 128u);
             if (elect_one_sync()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 if (b * 32 + ks * 8 < g.D)
-                  mma_tf32_ts(tmem_S, tmem + b * 32 + ks * 8, desc_kmajor(b_base + ks * 32), idesc_2,
-                              (b > 0 || ks > 0) ? 1u : 0u);
+                  mma_tf32_ts_lh(tmem_S, tmem + b * 32 + ks * 8, b_lo + ks * kDescStepK, kDescHiK, idesc_2,
+                                 (b > 0 || ks > 0) ? 1u : 0u);
               }
               if (j == nb - 1) mma_commit(&sm->empty[s]);
               if (b == g.nkb - 1) mma_commit(&sm->s_full);

@@ -186,17 +186,18 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
           if (tr && lane == 0) trace_add(tr, 1, trace_now() - tw);
           tc_fence_after();
           if (it == 0 && lane == 0) trace(tr, 3);
-          const uint32_t b_base = smem_u32(ring + s * g.stage_bytes);
+          const uint32_t a_lo = desc_lo_k(gblk_base + kb * 16384);
+          const uint32_t b_lo = desc_lo_mn(smem_u32(ring + s * g.stage_bytes), 4096);
+          const uint32_t b1_lo = b_lo + (uint32_t)(g.np0 >> 5) * (4096u >> 4);
           if (elect_one_sync()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               if (kb * 32 + ks * 8 < PLk) {
                 const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-                const uint64_t da = desc_kmajor(gblk_base + kb * 16384 + ks * 32);
-                mma_tf32_ss(tmem, da, desc_mnmajor(b_base + ks * 1024, 4096), idesc_p0, acc);
+                mma_tf32_ss_lh(tmem, a_lo + ks * kDescStepK, kDescHiK, b_lo + ks * kDescStepMN, kDescHiMN, idesc_p0, acc);
                 if (np1 > 0)
-                  mma_tf32_ss(tmem + g.np0, da, desc_mnmajor(b_base + (g.np0 >> 5) * 4096 + ks * 1024, 4096), idesc_p1,
-                              acc);
+                  mma_tf32_ss_lh(tmem + g.np0, a_lo + ks * kDescStepK, kDescHiK, b1_lo + ks * kDescStepMN, kDescHiMN,
+                                 idesc_p1, acc);
               }
             }
             mma_commit(&sm->empty[s]);
@@ -221,13 +222,13 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
             if (tr && lane == 0) trace_add(tr, 4, trace_now() - tw);
             tc_fence_after();
             const uint32_t bb = smem_u32(ring + s * g.stage_bytes) + (uint32_t)(j * g.b2_bytes);
+            const uint32_t b_lo = DA ? desc_lo_mn(bb, 4096) : desc_lo_k(bb);
             if (elect_one_sync()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                if (b * 32 + ks * 8 < g.D) {
-                  const uint64_t db = DA ? desc_mnmajor(bb + ks * 1024, 4096) : desc_kmajor(bb + ks * 32);
-                  mma_tf32_ts(tmem_O, tmem + b * 32 + ks * 8, db, idesc_b, (k > k_lo || b > 0 || ks > 0) ? 1u : 0u);
-                }
+                if (b * 32 + ks * 8 < g.D)
+                  mma_tf32_ts_lh(tmem_O, tmem + b * 32 + ks * 8, b_lo + ks * (DA ? kDescStepMN : kDescStepK),
+                                 DA ? kDescHiMN : kDescHiK, idesc_b, (k > k_lo || b > 0 || ks > 0) ? 1u : 0u);
               }
               if (j == nb - 1) mma_commit(&sm->empty[s]);
               if (b == g.nkb - 1 && k == k_hi - 1) mma_commit(&sm->o_full);

@@ -140,7 +140,7 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
   MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));   // :256
   // dq (+ U, dM) and da are independent: with MMS_OPT_CONCURRENCY the da kernel runs on a private stream and each
   // kernel is sized for half of the SMs when the batch is too small to fill them
-  const bool conc = ctx->concurrency != 0;
+  const bool want_conc = ctx->concurrency != 0;
   for (int n0 = 0; n0 < N; n0 += nc_max) {
     const int nc = mms_min(nc_max, N - n0);
     float* dqc = dq + (size_t)n0 * Lq * D;
@@ -151,9 +151,11 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
         {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
         {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
     if (!reuse) MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
-    const int ctas = conc ? mms_max(1, ctx->sm_count / 2) : ctx->sm_count;
+    // two kernels side by side only pay when one of them cannot fill the GPU: then each gets half of the SMs
     int ksplit = 1;
-    MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctas, &ksplit));
+    MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctx->sm_count, &ksplit));
+    const bool conc = want_conc && ksplit > 1;
+    if (conc) MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, mms_max(1, ctx->sm_count / 2), &ksplit));
     if (ksplit > 1) {   // the measures of one tile are spread over CTAs that add into the output
       MMS_CUDA(cudaMemsetAsync(dqc, 0, sizeof(float) * (size_t)nc * Lq * D, ctx->stream));
       MMS_CUDA(cudaMemsetAsync(dac, 0, sizeof(float) * (size_t)nc * La * D, ctx->stream));

@@ -233,14 +233,14 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           tc_fence_after();
           if (it == 0 && lane == 0) trace(tr, 3);
           const uint32_t a_base = smem_u32(ring + s * stage_bytes);
-          const uint32_t b_base = a_base + 16384;
+          const uint32_t a_lo = A_MN ? desc_lo_mn(a_base, 4096) : desc_lo_k(a_base);
+          const uint32_t b_lo = B_MN ? desc_lo_mn(a_base + 16384, 4096) : desc_lo_k(a_base + 16384);
           if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < kBK / 8; ++ks) {
-              const uint64_t da = A_MN ? desc_mnmajor(a_base + ks * 1024, 4096) : desc_kmajor(a_base + ks * 32);
-              const uint64_t db = B_MN ? desc_mnmajor(b_base + ks * 1024, 4096) : desc_kmajor(b_base + ks * 32);
-              mma_tf32_ss(acc, da, db, idesc, (i > 0 || ks > 0) ? 1u : 0u);
-            }
+            for (int ks = 0; ks < kBK / 8; ++ks)
+              mma_tf32_ss_lh(acc, a_lo + ks * (A_MN ? kDescStepMN : kDescStepK), A_MN ? kDescHiMN : kDescHiK,
+                             b_lo + ks * (B_MN ? kDescStepMN : kDescStepK), B_MN ? kDescHiMN : kDescHiK, idesc,
+                             (i > 0 || ks > 0) ? 1u : 0u);
             mma_commit(&sm->empty[s]);
             if (i == tl.nk - 1) mma_commit(&sm->acc_full[buf]);
           }

@@ -248,6 +248,41 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same descriptors as two 32-bit halves: the high half is a constant per layout and the low half is
+// (address >> 4) | (LBO >> 4) << 16, so stepping through a tile is ONE 32-bit add on the low half (addresses stay
+// below 256 KB, so the add never carries out of the 14-bit address field).  The MMA issue loop is executed by a
+// single elected lane and is latency-bound on its own instruction stream: rebuilding 64-bit descriptors with
+// shifts and masks for every MMA costs more cycles than a small MMA takes to execute.
+constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (2u << 29);    // K-major, SWIZZLE_128B, SBO 1024
+constexpr uint32_t kDescHiMN = (512u >> 4) | (1u << 14) | (1u << 29);    // MN-major, SWIZZLE_128B_BASE32B, SBO 512
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+constexpr uint32_t kDescStepK = 32u >> 4;        // one k-step (8 tf32) inside a K-major block
+constexpr uint32_t kDescStepMN = 1024u >> 4;     // one k-step (8 k-rows) inside an MN-major block
+
+__device__ __forceinline__ void mma_tf32_ss_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on `bar` when every MMA issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -156,6 +156,11 @@ class Layer(object):
         self.Reshape(bottom, top)                    # layer.hpp:456
         self._bind_stream()
         self.Forward_gpu(bottom, top)
+        return self.ForwardLoss(top)
+
+    def ForwardLoss(self, top):
+        """The loss part of Layer::Forward: sum over loss tops of dot(top.data, top.diff)."""
+        self._bind_stream()
         loss = 0.0
         for i, t in enumerate(top):                  # layer.hpp:471-479
             if i < len(self.loss_) and self.loss_[i]:

@@ -107,7 +107,7 @@ class MMSNet(object):
         return loss
 
     def ForwardBackwardConcurrent(self, with_loss=True, clear_diffs=True):
-        """The same step with its independent pieces on forked streams (the reference's Net runs layers one
+        r"""The same step with its independent pieces on forked streams (the reference's Net runs layers one
         after the other on the legacy stream, net.cpp:535-591; the data dependencies are all that matters):
 
             ClearParamDiffs ----------------------------\
@@ -129,15 +129,16 @@ class MMSNet(object):
             self.embed_a.Forward([self.idx_a], [self.a])
         self.embed_q.Forward([self.idx_q], [self.q])
         main.wait_stream(s2)
+        saved, self.sim.loss_ = self.sim.loss_, []             # the loss dot (layer.hpp:471-479) goes on a side branch
+        try:
+            self.sim.Forward([self.q, self.a], [self.S])
+        finally:
+            self.sim.loss_ = saved
+        loss = 0.0
         if with_loss:
-            loss = self.sim.Forward([self.q, self.a], [self.S])
-        else:
-            saved, self.sim.loss_ = self.sim.loss_, []
-            try:
-                self.sim.Forward([self.q, self.a], [self.S])
-            finally:
-                self.sim.loss_ = saved
-            loss = 0.0
+            s2.wait_stream(main)
+            with torch.cuda.stream(s2):
+                loss = self.sim.ForwardLoss([self.S])
         main.wait_stream(s1)                                   # diffs are cleared before anything accumulates
         self.sim.Backward([self.S], [True, True], [self.q, self.a])
         s2.wait_stream(main)

@@ -217,6 +217,68 @@ def test_simcross_mode2_vs_oracle(dtype, shape, math):
         assert np.all(sg[:-1][clear] > sg[1:][clear])
 
 
+@pytest.mark.parametrize("shape", [(50, 40, 40, 300, 4), (7, 17, 23, 36, 3), (200, 40, 40, 50, 4)])
+def test_simcross_backward_options_agree(shape):
+    """MMS_OPT_REUSE_FORWARD (backward reuses the operands the forward rounded) and MMS_OPT_CONCURRENCY (the da
+    kernel on a private stream) change how the work is issued, not what is computed."""
+    N, Lq, La, D, mc = shape
+    rng = np.random.default_rng(11 + sum(shape))
+    q = rng.uniform(-0.08, 0.08, (N, Lq, D)).astype(np.float32)
+    a = rng.uniform(-0.08, 0.08, (N, La, D)).astype(np.float32)
+    Mw = rng.uniform(-0.1, 0.1, (mc, D, D)).astype(np.float32)
+    B = rng.uniform(-0.01, 0.01, (mc, Lq, La)).astype(np.float32)
+    dS = (rng.uniform(-1, 1, (N, mc, Lq, La)) / (N * mc * Lq * La)).astype(np.float32)
+    S, _, _ = cport.simcross_forward(2, q, a, Mw, B)
+    dq, da, dM, dB = cport.simcross_backward(2, q, a, Mw, S, dS)
+    outs = {}
+    for reuse in (0, 1):
+        for conc in (0, 1):
+            lay = mms.SimCrossLayer(mms.LayerParameter("SimCross", sim_cross_param=dict(
+                dist_mode=2, mesure_count=mc, bias_term=True)))
+            bq, ba, top = blob(q, np.float32), blob(a, np.float32), mms.Blob((), dtype=np.float32)
+            lay.SetUp([bq, ba], [top])
+            lay.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, reuse)
+            lay.handle.set_option(_lib.MMS_OPT_CONCURRENCY, conc)
+            lay.blobs[0].set_cpu_data(Mw); lay.blobs[1].set_cpu_data(B)
+            lay.Forward([bq, ba], [top])
+            top.set_cpu_diff(dS)
+            lay.Backward([top], [True, True], [bq, ba])
+            lay.Backward([top], [True, True], [bq, ba])          # a second backward on the same forward
+            torch.cuda.synchronize()
+            got = dict(dq=bq.cpu_diff(), da=ba.cpu_diff(), dM=lay.blobs[0].cpu_diff())
+            for k, ref in (("dq", dq), ("da", da), ("dM", dM)):
+                assert scaled_err(got[k], ref) <= TOL_TF32, (reuse, conc, k)
+            assert scaled_err(lay.blobs[1].cpu_diff(), 2 * dB) <= 10 * TOL_EXACT[np.float32]   # dB accumulates
+            outs[(reuse, conc)] = got
+    base = outs[(0, 0)]
+    for key, got in outs.items():
+        for k in ("dq", "da", "dM"):       # same rounded operands, same kernels: only atomic ordering may differ
+            assert scaled_err(got[k], base[k]) <= 1e-5, (key, k)
+
+
+def test_simcross_reuse_is_dropped_when_inputs_move():
+    """The forward cache is keyed on pointers and sizes: a backward with other bottoms re-rounds."""
+    N, L, D, mc = 9, 40, 300, 2
+    rng = np.random.default_rng(5)
+    mk = lambda: rng.uniform(-0.08, 0.08, (N, L, D)).astype(np.float32)
+    q1, a1, q2, a2 = mk(), mk(), mk(), mk()
+    Mw = rng.uniform(-0.1, 0.1, (mc, D, D)).astype(np.float32)
+    dS = (rng.uniform(-1, 1, (N, mc, L, L)) / (N * mc * L * L)).astype(np.float32)
+    lay = mms.SimCrossLayer(mms.LayerParameter("SimCross", sim_cross_param=dict(dist_mode=2, mesure_count=mc)))
+    b1, c1, b2, c2, top = (blob(x, np.float32) for x in (q1, a1, q2, a2, np.zeros((N, mc, L, L), np.float32)))
+    lay.SetUp([b1, c1], [top])
+    lay.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 1)
+    lay.blobs[0].set_cpu_data(Mw)
+    lay.Forward([b1, c1], [top])
+    top.set_cpu_diff(dS)
+    lay.Backward([top], [True, True], [b2, c2])                  # other bottoms than the forward saw
+    S2, _, _ = cport.simcross_forward(2, q2, a2, Mw, None)
+    dq, da, dM, _ = cport.simcross_backward(2, q2, a2, Mw, S2, dS)
+    assert scaled_err(b2.cpu_diff(), dq) <= TOL_TF32
+    assert scaled_err(c2.cpu_diff(), da) <= TOL_TF32
+    assert scaled_err(lay.blobs[0].cpu_diff(), dM) <= TOL_TF32
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_simcross_quirks(dtype):
     """zero-initialised M gives S == B exactly; no bias blob when bias_term is false; nothing

@@ -46,6 +46,7 @@ constexpr int kEpiBytes = kEpiWarps * 32 * kEpiLd * 4;        // one 32 x 32 tra
 
 struct Geometry {
   int BN, stages, b_bytes, n_tiles, m_tiles;
+  int m_fast;            // tile order: 1 = m-tile index fastest (few row panels, many column panels), 0 = n-tile fastest
   unsigned total_tiles;
   uint32_t tmem_cols;
   // 0/1 multipliers: a broadcast (stride 0) batch / segment dimension has extent 1 in the tensor map
@@ -66,8 +67,9 @@ __device__ __forceinline__ void trace(long long* tr, int slot) {
 
 __device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry& q, unsigned t, int sps) {
   Tile tl;
-  const int n_tile = t % q.n_tiles; t /= q.n_tiles;
-  const int m_tile = t % q.m_tiles; t /= q.m_tiles;
+  int n_tile, m_tile;
+  if (q.m_fast) { m_tile = t % q.m_tiles; t /= q.m_tiles; n_tile = t % q.n_tiles; t /= q.n_tiles; }
+  else { n_tile = t % q.n_tiles; t /= q.n_tiles; m_tile = t % q.m_tiles; t /= q.m_tiles; }
   const int split = t % g.ksplit;
   const int z = t / g.ksplit;
   tl.z1 = z / g.nb2; tl.z2 = z % g.nb2;
@@ -469,6 +471,11 @@ int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& a) {
   q.BN = BN;
   q.n_tiles = mms_ceil_div(a.N, BN);
   q.m_tiles = mms_ceil_div(a.M, kBM);
+  // The CTAs that run together take consecutive tiles.  With n fastest they share one row panel of A and stream
+  // distinct panels of B; when A has only a few row panels (candidate scoring: 1000 queries x 10^6 candidates) that
+  // re-reads all of B from HBM once per row panel -- walk the row panels first instead, so that each panel of B is
+  // fetched from HBM once and served to its m_tiles consumers from L2.
+  q.m_fast = (q.m_tiles < q.n_tiles && q.m_tiles <= ctx->sm_count) ? 1 : 0;
   q.b_bytes = a.b_mn ? mms_ceil_div(BN, 32) * 4096 : BN * 128;
   const int stage_bytes = 16384 + q.b_bytes;
   int stages = kMaxStages;

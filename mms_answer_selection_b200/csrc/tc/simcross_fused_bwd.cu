@@ -6,23 +6,34 @@
 //                                           gradients have the same shape: small product first, D x D product second)
 //
 // One kernel template serves both (DA = false: dQ, DA = true: dA).  One tile = P consecutive QA pairs (their
-// P*Lr output rows, Lr = Lq or La) x one column part h of the output x a range of measures:
-//   for k in the tile's measures:
-//     build  Gblk [128 x 128]: block-diagonal, block p = G_{n0+p,k} (dQ) or its transpose (dA), rounded to TF32,
-//            written into shared memory in the K-major UMMA layout by four builder warps straight from dS
-//     GEMM-A U [128 x N1] = Gblk * X      X = the P pairs' answer (dQ) / question (dA) rows, MN-major by TMA;
-//                                         accumulator U in TMEM columns [0, N1)
-//     round  U -> tf32 in place (tcgen05.ld / cvt.rna / tcgen05.st); the dQ kernel also writes U to global memory,
-//            where the dM contraction (dM_k = Q^T U_k, a reduction over ALL pairs) picks it up
-//     GEMM-B O [128 x Nh] += U * W_k      W_k = columns [h*Nh0, ..) of M_k^T (dQ, K-major boxes) or M_k (dA, MN-major
-//                                         boxes); A operand read from TMEM; O accumulates over k in TMEM
-//   store  O -> dq / da rows (plain stores; red.global.add when the measures of one tile are split over CTAs)
-// The output is split in column parts because U (N1 columns) and O share the 512 TMEM columns: D = 300 gives
-// N1 = 304 and two parts of 160 + 144 columns, with U recomputed for each part.
+// P*Lr output rows, Lr = Lq or La) x a range of measures; the full-width output O [128 x N1] accumulates over the
+// measures in TMEM columns [0, N1).  The intermediate U = Gblk * X never exists as a whole: it is produced, rounded
+// and consumed in column chunks of CW (64) columns that rotate through three TMEM buffers behind O,
 //
-//   warp 0       TMA producer        warp 1       tcgen05.mma issuer + TMEM allocator
-//   warps 2-9    rounding of U, U export, output epilogue (two warps per TMEM lane quarter)
-//   warps 10-13  Gblk builders
+//   chunk (tile, k, c):
+//     GEMM-A  U_c [128 x CW] = Gblk * X[:, chunk c]     Gblk [128 x 128]: block-diagonal, block p = G_{n0+p,k} (dQ) or
+//                                                       its transpose (dA), built in shared memory by four builder
+//                                                       warps straight from dS; X = the P pairs' answer (dQ) /
+//                                                       question (dA) rows, MN-major boxes of 32 columns x 128 rows
+//     round   U_c -> tf32 in place (tcgen05.ld / cvt.rna / tcgen05.st); the dQ kernel also writes U_c to global
+//             memory, where the dM contraction (dM_k = Q^T U_k, a reduction over ALL pairs) picks it up
+//     GEMM-B  O [128 x N1] += U_c * W_k[chunk c rows]   W_k = M_k^T (dQ, K-major boxes) or M_k (dA, MN-major boxes);
+//                                                       A operand read from TMEM
+//
+// and the MMA warp issues  A(0) A(1) | B(0) A(2) | B(1) A(3) | ...  across measure and tile boundaries: while the
+// rounding warps work on chunk c+1 the tensor pipe runs B(c-1), A(c+1) .. B(c), A(c+2), so neither the rounding
+// nor the Gblk build of the next measure leaves it idle.  (The previous version of this kernel kept a whole U in
+// TMEM, which forced two column parts of O with U recomputed for each, and serialised GEMM-A -> round -> GEMM-B
+// per measure: 35-41 % tensor-pipe activity.)
+//
+//   warp 0       TMA producer        warp 1       GEMM-A issuer + TMEM allocator        warp 14   GEMM-B issuer
+//   warps 2-9    rounding of U, U export (two warps per TMEM lane quarter)
+//   warps 10-13  Gblk builders        warps 15-18  output epilogue (one warp per TMEM lane quarter)
+//
+// The issue loops are written for the uniform datapath: every quantity an MMA needs besides the k-step offset is
+// hoisted out of the unrolled k-steps (tools/mma_rate.cu: the tensor pipe runs every shape used here at its ideal
+// N/2 cycles per K=8 step, but an issue loop that rebuilds descriptors from kernel parameters takes ~150 cycles per
+// iteration, more than the MMAs it issues).
 #include <cuda.h>
 
 #include <stdlib.h>
@@ -36,34 +47,35 @@ namespace {
 
 using namespace umma;
 
-constexpr int kThreads = 14 * 32;
-constexpr int kMaxStages = 5;
-constexpr int kMaxChunks = 12;          // 32-column chunks of U (N1 <= 384)
+constexpr int kThreads = 19 * 32;
+constexpr int kMaxStages = 6;
+constexpr int kUBufs = 3;               // TMEM buffers the chunks of U rotate through
 constexpr int kGblkBytes = 4 * 16384;   // 128 rows x 128 contraction columns, four 32-wide k-blocks
 
 struct BwdGeom {
   int N, Lq, La, D, mc;
   int Lr, Lk;            // output-row side / contraction side sentence length
   int P;                 // pairs per tile
-  int N1, np0;           // width of U; GEMM-A runs as MMAs of np0 and N1 - np0 columns
-  int nh, Nh0;           // column parts of the output: part h = [h*Nh0, min(N1, (h+1)*Nh0))
-  int nka, nkb;          // 32-wide k-blocks of GEMM-A (over P*Lk) / GEMM-B (over D)
-  int nboxes;            // 32-column boxes of X per GEMM-A stage
-  int kb2, b2_bytes;     // GEMM-B: k-blocks per ring slot, bytes per k-block
+  int nksA;              // k-steps (of 8) of GEMM-A: ceil(P*Lk / 8)
+  int N1, np0, np1;      // width of U and O; O is written by MMAs of np0 and np1 columns
+  int CW, nch, wl;       // chunk width, chunks per (tile, measure), width of the last chunk
+  int nbxB;              // dA: 32-column boxes of M_k per k-block
   int stages, stage_bytes;
-  int ksplit;            // CTAs that share the measures of one (group, part)
+  int ksplit;            // CTAs that share the measures of one pair group
   unsigned total_tiles;
   uint32_t tmem_cols;
   int vec_g, vec_out;
   int Dp;                // row pitch of the exported U
+  int dbg;               // MMS_BWD_DEBUG timing knobs (wrong results): 1 no rounding, 2 no output stores, 4 no U export,
+                         // 8 no dS loads, 16 no epilogue TMEM loads
   long long u_rows;      // rows of one measure slab of the exported U
 };
 
 struct BwdSmem {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t g_full, g_empty, u_full, o_full, o_empty;
-  uint64_t t_ready[kMaxChunks];
+  uint64_t g_full, g_empty, o_full, o_empty;
+  uint64_t u_full[kUBufs], u_ready[kUBufs], u_free[kUBufs];
   uint32_t tmem_base;
 };
 
@@ -74,7 +86,40 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
                : "memory");
 }
 
-template <bool DA>
+// Walks the chunks (tile, measure, chunk) of this CTA in issue order.  Every role keeps its own copy (the MMA warp
+// and the producer keep two: GEMM-A runs two chunks ahead of GEMM-B).
+struct ChunkIter {
+  unsigned t;
+  int n0, k, k_lo, k_hi, c;
+  bool live;
+  __device__ __forceinline__ void load(const BwdGeom& g) {
+    live = t < g.total_tiles;
+    c = 0;
+    if (live) {
+      const int ksp = (int)(t % (unsigned)g.ksplit);
+      n0 = (int)(t / (unsigned)g.ksplit) * g.P;
+      k_lo = ksp * g.mc / g.ksplit;
+      k_hi = (ksp + 1) * g.mc / g.ksplit;
+      k = k_lo;
+    }
+  }
+  __device__ __forceinline__ void start(const BwdGeom& g) { t = blockIdx.x; load(g); }
+  __device__ __forceinline__ void next(const BwdGeom& g) {
+    if (++c == g.nch) {
+      c = 0;
+      if (++k == k_hi) { t += gridDim.x; load(g); }
+    }
+  }
+};
+
+// ring slot / U buffer cursors: index and phase bit, advanced without divisions
+struct Cursor {
+  int i; uint32_t ph;
+  __device__ __forceinline__ void advance(int n) { if (++i == n) { i = 0; ph ^= 1u; } }
+  __device__ __forceinline__ void skip(int by, int n) { i += by; if (i >= n) { i -= n; ph ^= 1u; } }   // by < n
+};
+
+template <bool DA, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM,
                            const float* __restrict__ dS, float* __restrict__ out, float* __restrict__ Uexp,
@@ -85,17 +130,14 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
   BwdSmem* sm = reinterpret_cast<BwdSmem*>(ring + g.stages * g.stage_bytes);
 
   const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
-  const int stages = g.stages;
-  const int nch = (g.N1 + 31) >> 5;
-  const int PLk = g.P * g.Lk;
-  if (threadIdx.x == 0) trace_begin(tr);
+  if (TRACE && threadIdx.x == 0) trace_begin(tr);
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
-      mbar_init(&sm->g_full, 4); mbar_init(&sm->g_empty, 1); mbar_init(&sm->u_full, 1);
-      mbar_init(&sm->o_full, 1); mbar_init(&sm->o_empty, 8);
-      for (int c = 0; c < kMaxChunks; ++c) mbar_init(&sm->t_ready[c], 4);
+      for (int s = 0; s < g.stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+      mbar_init(&sm->g_full, 4); mbar_init(&sm->g_empty, 1);
+      mbar_init(&sm->o_full, 1); mbar_init(&sm->o_empty, 4);
+      for (int j = 0; j < kUBufs; ++j) { mbar_init(&sm->u_full[j], 1); mbar_init(&sm->u_ready[j], 8); mbar_init(&sm->u_free[j], 1); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -108,225 +150,336 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = sm->tmem_base;
-  const uint32_t tmem_O = tmem + (uint32_t)g.N1;
-  if (threadIdx.x == 0) trace(tr, 1);
-
-  // tile -> (pair group, column part, measure range)
-  auto decode = [&](unsigned t, int& n0, int& h, int& k_lo, int& k_hi) {
-    const int ksp = (int)(t % (unsigned)g.ksplit); t /= (unsigned)g.ksplit;
-    h = (int)(t % (unsigned)g.nh);
-    n0 = (int)(t / (unsigned)g.nh) * g.P;
-    k_lo = ksp * g.mc / g.ksplit;
-    k_hi = (ksp + 1) * g.mc / g.ksplit;
-  };
+  const uint32_t tmem_O = sm->tmem_base;
+  const uint32_t tmem_U = tmem_O + (uint32_t)g.N1;
+  if (TRACE && threadIdx.x == 0) trace(tr, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    const uint32_t txa = (uint32_t)g.nboxes * 4096u;
-    const int nbx2 = g.b2_bytes >> 12;                           // dA: 32-column boxes of M_k per k-block
-    int it = 0;
-    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-      int n0, h, k_lo, k_hi;
-      decode(t, n0, h, k_lo, k_hi);
-      for (int k = k_lo; k < k_hi; ++k) {
-        for (int kb = 0; kb < g.nka; ++kb, ++it) {               // GEMM-A: 32 contraction rows of X, all N1 columns
-          const int s = it % stages;
-          if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
-          uint8_t* dst = ring + s * g.stage_bytes;
-          if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&sm->full[s], txa);
-            for (int x = 0; x < g.nboxes; ++x)
-              tma_load_5d(dst + x * 4096, &mapX, &sm->full[s], 32 * x, n0 * g.Lk + 32 * kb, 0, 0, 0);
+    const int stages = g.stages, stage_bytes = g.stage_bytes, CW = g.CW, nch = g.nch, wl = g.wl;
+    const int Lk = g.Lk, np0 = g.np0, nbxB = g.nbxB;
+    const bool two = g.np1 > 0;
+    const uint32_t bytesB = DA ? (uint32_t)nbxB * 4096u : (uint32_t)(two ? 2 : 1) * (uint32_t)np0 * 128u;
+    Cursor slot = {0, 0};
+    auto load_a = [&](const ChunkIter& it) {               // X[:, chunk c]: 32-column x 128-row boxes
+      const int w = it.c == nch - 1 ? wl : CW;
+      const int nbx = (w + 31) >> 5;
+      mbar_wait(&sm->empty[slot.i], slot.ph ^ 1u);
+      uint8_t* dst = ring + slot.i * stage_bytes;
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&sm->full[slot.i], (uint32_t)nbx * 16384u);
+        for (int x = 0; x < nbx; ++x)
+          tma_load_5d(dst + x * 16384, &mapX, &sm->full[slot.i], it.c * CW + 32 * x, it.n0 * Lk, 0, 0, 0);
+        // the next tile's X rows come from HBM: pull them into L2 a whole tile ahead, so that the ring (which holds
+        // about 1 us of operands) only ever waits for L2
+        if (it.c == 0 && it.k == it.k_lo && (g.dbg & 32)) {
+          const unsigned tn = it.t + gridDim.x;
+          if (tn < g.total_tiles && (g.ksplit == 1 || tn / (unsigned)g.ksplit != it.t / (unsigned)g.ksplit)) {
+            const int n0n = (int)(tn / (unsigned)g.ksplit) * g.P;
+            for (int x = 0; x < nbxB; ++x) tma_prefetch_l2_5d(&mapX, 32 * x, n0n * Lk, 0, 0, 0);
           }
-          __syncwarp();
-        }
-        for (int b0 = 0; b0 < g.nkb; b0 += g.kb2, ++it) {        // GEMM-B: kb2 k-blocks of W_k per slot
-          const int s = it % stages;
-          const int nb = min(g.kb2, g.nkb - b0);
-          if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
-          uint8_t* dst = ring + s * g.stage_bytes;
-          if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&sm->full[s], (uint32_t)(nb * g.b2_bytes));
-            for (int j = 0; j < nb; ++j) {
-              if (!DA) {
-                tma_load_5d(dst + j * g.b2_bytes, &mapM, &sm->full[s], (b0 + j) * 32, h * g.Nh0, 0, k, 0);
-              } else {
-                for (int x = 0; x < nbx2; ++x)
-                  tma_load_5d(dst + j * g.b2_bytes + x * 4096, &mapM, &sm->full[s], h * g.Nh0 + 32 * x, (b0 + j) * 32,
-                              0, k, 0);
-              }
-            }
-          }
-          __syncwarp();
         }
       }
+      __syncwarp();
+      slot.advance(stages);
+    };
+    auto load_b = [&](const ChunkIter& it) {               // rows [chunk c] of W_k, one 32-row k-block per slot
+      const int w = it.c == nch - 1 ? wl : CW;
+      const int nkb = (w + 31) >> 5;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int e0 = it.c * CW + kb * 32;
+        mbar_wait(&sm->empty[slot.i], slot.ph ^ 1u);
+        uint8_t* dst = ring + slot.i * stage_bytes;
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&sm->full[slot.i], bytesB);
+          if (!DA) {
+            tma_load_5d(dst, &mapM, &sm->full[slot.i], e0, 0, 0, it.k, 0);
+            if (two) tma_load_5d(dst + np0 * 128, &mapM, &sm->full[slot.i], e0, np0, 0, it.k, 0);
+          } else {
+            for (int x = 0; x < nbxB; ++x)
+              tma_load_5d(dst + x * 4096, &mapM, &sm->full[slot.i], 32 * x, e0, 0, it.k, 0);
+          }
+        }
+        __syncwarp();
+        slot.advance(stages);
+      }
+    };
+    ChunkIter ia, ib;
+    ia.start(g); ib.start(g);
+    for (int i = 0; i < 2 && ia.live; ++i) { load_a(ia); ia.next(g); }
+    while (ib.live) {
+      load_b(ib); ib.next(g);
+      if (ia.live) { load_a(ia); ia.next(g); }
     }
-    if (lane == 0) trace(tr, 2);
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issue
-    const int np1 = g.N1 - g.np0;
-    const uint32_t idesc_p0 = idesc_tf32(128, g.np0, false, true);
-    const uint32_t idesc_p1 = idesc_tf32(128, np1 > 0 ? np1 : 16, false, true);
-    const uint32_t gblk_base = smem_u32(gblk);
-    int it = 0, tc = 0, itk = 0;
-    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tc) {
-      int n0, h, k_lo, k_hi;
-      decode(t, n0, h, k_lo, k_hi);
-      const int Nh = min(g.Nh0, g.N1 - h * g.Nh0);
-      const uint32_t idesc_b = idesc_tf32(128, Nh, false, DA);
-      for (int k = k_lo; k < k_hi; ++k, ++itk) {
-        long long tw = tr ? trace_now() : 0;
-        mbar_wait(&sm->g_full, itk & 1);                         // Gblk of (tile, k) is in shared memory
-        if (tr && lane == 0) { const long long n = trace_now(); trace_add(tr, 0, n - tw); tw = n; }
-        for (int kb = 0; kb < g.nka; ++kb, ++it) {
-          const int s = it % stages;
-          if (tr) tw = trace_now();
-          mbar_wait(&sm->full[s], (it / stages) & 1);
-          if (tr && lane == 0) trace_add(tr, 1, trace_now() - tw);
+    if (TRACE && lane == 0) trace(tr, 2);
+  } else if (warp == 1 || warp == 14) {
+    // ------------------------------------------------------------ MMA issue: warp 1 GEMM-A, warp 14 GEMM-B
+    // Two issuers because a lone warp retires one dependent uniform-datapath instruction every ~5 cycles: with one
+    // issuer the instruction stream of the 151 short MMAs of a (tile, measure) takes about as long as the MMAs
+    // themselves (ncu: the single issue warp was busy, not waiting, 55 % of the kernel).  Both warps walk the same
+    // static schedule  A(0) A(1) | B(0) A(2) | B(1) A(3) | ...  over the one TMA ring and act on their own items
+    // only; what the in-order issue of a single warp used to guarantee is now a barrier: u_free[j] (GEMM-B has
+    // read U buffer j) before GEMM-A overwrites it.
+    const bool is_a = warp == 1;
+    const int stages = g.stages, stage_bytes = g.stage_bytes, CW = g.CW, nch = g.nch, wl = g.wl;
+    const int nksA = g.nksA, D = g.D, np0 = g.np0;
+    const bool two = g.np1 > 0;
+    const uint32_t ring_base = smem_u32(ring);
+    const uint32_t stage_lo = (uint32_t)stage_bytes >> 4;
+    Cursor slot = {0, 0};
+    long long tw = 0;
+    ChunkIter ia, ib;
+    ia.start(g); ib.start(g);
+    if (is_a) {
+      const uint32_t idesc_a = idesc_tf32(128, CW, false, true);
+      const uint32_t idesc_al = idesc_tf32(128, wl, false, true);
+      const uint32_t gblk_lo = desc_lo_k(smem_u32(gblk));
+      const uint32_t ring_lo_mnA = desc_lo_mn(ring_base, 16384);
+      const int a_full = nksA >> 2, a_rem = nksA & 3;
+      Cursor ua = {0, 0};
+      uint32_t gph = 0;          // phase of g_full
+      auto issue_a = [&](const ChunkIter& it) {
+        if (it.c == 0) {
+          if (TRACE) tw = trace_now();
+          mbar_wait(&sm->g_full, gph);                       // Gblk of (tile, k) is in shared memory
+          gph ^= 1u;
+          if (TRACE && lane == 0) trace_add(tr, 0, trace_now() - tw);
+        }
+        if (TRACE) tw = trace_now();
+        mbar_wait(&sm->u_free[ua.i], ua.ph ^ 1u);            // GEMM-B of the chunk three back has read this buffer
+        if (TRACE && lane == 0) trace_add(tr, 5, trace_now() - tw);
+        if (TRACE) tw = trace_now();
+        mbar_wait(&sm->full[slot.i], slot.ph);
+        if (TRACE && lane == 0) trace_add(tr, 1, trace_now() - tw);
+        tc_fence_after();
+        const bool last = it.c == nch - 1;
+        const uint32_t d = tmem_U + (uint32_t)(ua.i * CW);
+        const uint32_t idesc = last ? idesc_al : idesc_a;
+        if (elect_one_sync()) {
+          uint32_t al = gblk_lo, bl = ring_lo_mnA + (uint32_t)slot.i * stage_lo;
+#pragma unroll 1
+          for (int kb = 0; kb < a_full; ++kb) {
+            mma_tf32_ss_lh(d, al, kDescHiK, bl, kDescHiMN, idesc, kb > 0 ? 1u : 0u);
+            mma_tf32_ss_lh(d, al + 1 * kDescStepK, kDescHiK, bl + 1 * kDescStepMN, kDescHiMN, idesc, 1u);
+            mma_tf32_ss_lh(d, al + 2 * kDescStepK, kDescHiK, bl + 2 * kDescStepMN, kDescHiMN, idesc, 1u);
+            mma_tf32_ss_lh(d, al + 3 * kDescStepK, kDescHiK, bl + 3 * kDescStepMN, kDescHiMN, idesc, 1u);
+            al += 16384u >> 4; bl += 4 * kDescStepMN;
+          }
+          if (a_rem > 0) mma_tf32_ss_lh(d, al, kDescHiK, bl, kDescHiMN, idesc, a_full > 0 ? 1u : 0u);
+          if (a_rem > 1) mma_tf32_ss_lh(d, al + 1 * kDescStepK, kDescHiK, bl + 1 * kDescStepMN, kDescHiMN, idesc, 1u);
+          if (a_rem > 2) mma_tf32_ss_lh(d, al + 2 * kDescStepK, kDescHiK, bl + 2 * kDescStepMN, kDescHiMN, idesc, 1u);
+          mma_commit(&sm->empty[slot.i]);
+          mma_commit(&sm->u_full[ua.i]);
+          if (last) mma_commit(&sm->g_empty);
+        }
+        __syncwarp();
+        slot.advance(stages);
+        ua.advance(kUBufs);
+      };
+      for (int i = 0; i < 2 && ia.live; ++i) { issue_a(ia); ia.next(g); }
+      if (TRACE && lane == 0) trace(tr, 4);
+      while (ib.live) {
+        slot.skip(((ib.c == nch - 1 ? wl : CW) + 31) >> 5, stages);     // the ring slots of B(c)
+        ib.next(g);
+        if (ia.live) { issue_a(ia); ia.next(g); }
+      }
+    } else {
+      const uint32_t idesc_b0 = idesc_tf32(128, np0, false, DA);
+      const uint32_t idesc_b1 = idesc_tf32(128, two ? g.np1 : 16, false, DA);
+      const uint32_t b1_off = DA ? (uint32_t)(np0 >> 5) * (4096u >> 4) : ((uint32_t)np0 * 128u) >> 4;
+      constexpr uint32_t kStepB = DA ? kDescStepMN : kDescStepK;
+      constexpr uint32_t kHiB = DA ? kDescHiMN : kDescHiK;
+      const uint32_t ring_lo_B = DA ? desc_lo_mn(ring_base, 4096) : desc_lo_k(ring_base);
+      const uint32_t tmem_O1 = tmem_O + (uint32_t)np0;
+      Cursor ub = {0, 0};
+      int tcb = 0;               // tiles whose GEMM-B has started
+      auto issue_b = [&](const ChunkIter& it) {
+        const bool tile_first = it.c == 0 && it.k == it.k_lo;
+        const bool tile_last = it.c == nch - 1 && it.k == it.k_hi - 1;
+        if (tile_first && tcb > 0) {
+          if (TRACE) tw = trace_now();
+          mbar_wait(&sm->o_empty, (uint32_t)(tcb - 1) & 1u);   // the previous tile's O has been read out
+          if (TRACE && lane == 0) trace_add(tr, 2, trace_now() - tw);
+        }
+        if (TRACE) tw = trace_now();
+        mbar_wait(&sm->u_ready[ub.i], ub.ph);                  // chunk c of U is rounded
+        if (TRACE && lane == 0) trace_add(tr, 4, trace_now() - tw);
+        const int w = it.c == nch - 1 ? wl : CW;
+        const int nkb = (w + 31) >> 5;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (TRACE) tw = trace_now();
+          mbar_wait(&sm->full[slot.i], slot.ph);
+          if (TRACE && lane == 0) trace_add(tr, 3, trace_now() - tw);
           tc_fence_after();
-          if (it == 0 && lane == 0) trace(tr, 3);
-          const uint32_t a_lo = desc_lo_k(gblk_base + kb * 16384);
-          const uint32_t b_lo = desc_lo_mn(smem_u32(ring + s * g.stage_bytes), 4096);
-          const uint32_t b1_lo = b_lo + (uint32_t)(g.np0 >> 5) * (4096u >> 4);
+          const uint32_t b_lo = ring_lo_B + (uint32_t)slot.i * stage_lo;
+          const uint32_t a_t = tmem_U + (uint32_t)(ub.i * CW + kb * 32);
+          const int left = D - (it.c * CW + kb * 32);          // valid contraction columns from this k-block on
+          const int nks = left >= 32 ? 4 : (left + 7) >> 3;
+          const uint32_t acc0 = (tile_first && kb == 0) ? 0u : 1u;
           if (elect_one_sync()) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (kb * 32 + ks * 8 < PLk) {
-                const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-                mma_tf32_ss_lh(tmem, a_lo + ks * kDescStepK, kDescHiK, b_lo + ks * kDescStepMN, kDescHiMN, idesc_p0, acc);
-                if (np1 > 0)
-                  mma_tf32_ss_lh(tmem + g.np0, a_lo + ks * kDescStepK, kDescHiK, b1_lo + ks * kDescStepMN, kDescHiMN,
-                                 idesc_p1, acc);
+            if (two) {
+              const uint32_t b1_lo = b_lo + b1_off;
+              mma_tf32_ts_lh(tmem_O, a_t, b_lo, kHiB, idesc_b0, acc0);
+              mma_tf32_ts_lh(tmem_O1, a_t, b1_lo, kHiB, idesc_b1, acc0);
+              if (nks > 1) {
+                mma_tf32_ts_lh(tmem_O, a_t + 8, b_lo + 1 * kStepB, kHiB, idesc_b0, 1u);
+                mma_tf32_ts_lh(tmem_O1, a_t + 8, b1_lo + 1 * kStepB, kHiB, idesc_b1, 1u);
               }
+              if (nks > 2) {
+                mma_tf32_ts_lh(tmem_O, a_t + 16, b_lo + 2 * kStepB, kHiB, idesc_b0, 1u);
+                mma_tf32_ts_lh(tmem_O1, a_t + 16, b1_lo + 2 * kStepB, kHiB, idesc_b1, 1u);
+              }
+              if (nks > 3) {
+                mma_tf32_ts_lh(tmem_O, a_t + 24, b_lo + 3 * kStepB, kHiB, idesc_b0, 1u);
+                mma_tf32_ts_lh(tmem_O1, a_t + 24, b1_lo + 3 * kStepB, kHiB, idesc_b1, 1u);
+              }
+            } else {
+              mma_tf32_ts_lh(tmem_O, a_t, b_lo, kHiB, idesc_b0, acc0);
+              if (nks > 1) mma_tf32_ts_lh(tmem_O, a_t + 8, b_lo + 1 * kStepB, kHiB, idesc_b0, 1u);
+              if (nks > 2) mma_tf32_ts_lh(tmem_O, a_t + 16, b_lo + 2 * kStepB, kHiB, idesc_b0, 1u);
+              if (nks > 3) mma_tf32_ts_lh(tmem_O, a_t + 24, b_lo + 3 * kStepB, kHiB, idesc_b0, 1u);
             }
-            mma_commit(&sm->empty[s]);
-            if (kb == g.nka - 1) { mma_commit(&sm->u_full); mma_commit(&sm->g_empty); }
+            mma_commit(&sm->empty[slot.i]);
+            if (kb == nkb - 1) {
+              mma_commit(&sm->u_free[ub.i]);
+              if (tile_last) mma_commit(&sm->o_full);
+            }
           }
           __syncwarp();
+          slot.advance(stages);
         }
-        if (itk == 0 && lane == 0) trace(tr, 4);
-        if (tr) tw = trace_now();
-        if (k == k_lo && tc > 0) mbar_wait(&sm->o_empty, (tc - 1) & 1);   // the previous tile's O has been read out
-        if (tr && lane == 0) trace_add(tr, 2, trace_now() - tw);
-        for (int b0 = 0; b0 < g.nkb; b0 += g.kb2, ++it) {
-          const int s = it % stages;
-          const int nb = min(g.kb2, g.nkb - b0);
-          if (tr) tw = trace_now();
-          mbar_wait(&sm->full[s], (it / stages) & 1);
-          if (tr && lane == 0) trace_add(tr, 3, trace_now() - tw);
-          for (int j = 0; j < nb; ++j) {
-            const int b = b0 + j;
-            if (tr) tw = trace_now();
-            mbar_wait(&sm->t_ready[b], itk & 1);                 // U columns [32 b, 32 b + 32) are rounded
-            if (tr && lane == 0) trace_add(tr, 4, trace_now() - tw);
-            tc_fence_after();
-            const uint32_t bb = smem_u32(ring + s * g.stage_bytes) + (uint32_t)(j * g.b2_bytes);
-            const uint32_t b_lo = DA ? desc_lo_mn(bb, 4096) : desc_lo_k(bb);
-            if (elect_one_sync()) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (b * 32 + ks * 8 < g.D)
-                  mma_tf32_ts_lh(tmem_O, tmem + b * 32 + ks * 8, b_lo + ks * (DA ? kDescStepMN : kDescStepK),
-                                 DA ? kDescHiMN : kDescHiK, idesc_b, (k > k_lo || b > 0 || ks > 0) ? 1u : 0u);
-              }
-              if (j == nb - 1) mma_commit(&sm->empty[s]);
-              if (b == g.nkb - 1 && k == k_hi - 1) mma_commit(&sm->o_full);
-            }
-            __syncwarp();
-          }
-        }
-        if (itk == 0 && lane == 0) trace(tr, 7);
+        ub.advance(kUBufs);
+        if (tile_last) ++tcb;
+      };
+      for (int i = 0; i < 2 && ia.live; ++i) { slot.advance(stages); ia.next(g); }   // the ring slots of A(0), A(1)
+      while (ib.live) {
+        issue_b(ib); ib.next(g);
+        if (ia.live) { slot.advance(stages); ia.next(g); }
       }
     }
   } else if (warp < 10) {
-    // ------------------------------------------------------------ U rounding / export, output epilogue
+    // ------------------------------------------------------------ U rounding / export
     const int quarter = warp & 3;
     const int set = (warp - 2) >> 2;
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
     const int row = quarter * 32 + lane;
     const int p_lane = row / g.Lr;
-    int tc = 0, itk = 0;
-    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tc) {
-      int n0, h, k_lo, k_hi;
-      decode(t, n0, h, k_lo, k_hi);
-      const bool valid = (p_lane < g.P) && (n0 + p_lane < g.N);
-      const long long grow = (long long)n0 * g.Lr + row;         // row of dq / da / U this thread owns
-      const bool exporting = !DA && Uexp != nullptr && h == 0 && valid;
-      for (int k = k_lo; k < k_hi; ++k, ++itk) {
-        mbar_wait(&sm->u_full, itk & 1);
-        tc_fence_after();
-        if (itk == 0 && threadIdx.x == 64) trace(tr, 5);
-        if (threadIdx.x == 64) trace(tr, 12);                    // keeps the LAST iteration's time
-        float* urow = exporting ? Uexp + ((size_t)k * g.u_rows + grow) * g.Dp : nullptr;
-        for (int c = set; c < nch; c += 2) {
-          float v[32];
-          const uint32_t ta = tmem + lane_bits + (uint32_t)(c * 32);
-          if (c * 32 + 16 < g.N1) {
-            tmem_ld32(ta, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = to_tf32(v[i]);
-            tmem_st32(ta, v);
-            if (urow) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) st_global_v8(urow + c * 32 + i * 8, v + 8 * i);
-            }
-          } else {
-            tmem_ld16(ta, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = to_tf32(v[i]);
-            tmem_st16(ta, v);
-            if (urow) {
-#pragma unroll
-              for (int i = 0; i < 2; ++i) st_global_v8(urow + c * 32 + i * 8, v + 8 * i);
-            }
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm->t_ready[c]);
-        }
-        if (itk == 0 && threadIdx.x == 64) trace(tr, 6);
-      }
-      mbar_wait(&sm->o_full, tc & 1);
+    const int CW = g.CW, nch = g.nch, wl = g.wl;
+    Cursor ur = {0, 0};
+    bool first = true;
+    ChunkIter it;
+    it.start(g);
+    while (it.live) {
+      const bool valid = (p_lane < g.P) && (it.n0 + p_lane < g.N);
+      const long long grow = (long long)it.n0 * g.Lr + row;      // row of U this thread owns
+      mbar_wait(&sm->u_full[ur.i], ur.ph);
       tc_fence_after();
-      if (tc == 0 && threadIdx.x == 64) trace(tr, 8);
-      const int Nh = min(g.Nh0, g.N1 - h * g.Nh0);
-      float* orow = out + grow * g.D + h * g.Nh0;
-      const int ncols = min(Nh, g.D - h * g.Nh0);                // columns of this part that exist in the output
-      for (int c = set; c * 32 < Nh; c += 2) {
+      if (TRACE && first && threadIdx.x == 64) trace(tr, 5);
+      const int w = it.c == nch - 1 ? wl : CW;
+      const int col0 = set * 32;                                  // this warp's 32 columns of the chunk
+      const bool mine = col0 < w && !(g.dbg & 1);
+      const bool wide = w - col0 > 16;
+      float v[32];
+      if (mine) {
+        const uint32_t ta = tmem_U + lane_bits + (uint32_t)(ur.i * CW + col0);
+        if (wide) {
+          tmem_ld32(ta, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = to_tf32(v[i]);
+          tmem_st32(ta, v);
+        } else {
+          tmem_ld16(ta, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = to_tf32(v[i]);
+          tmem_st16(ta, v);
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->u_ready[ur.i]);             // GEMM-B may start; the export below is off its path
+      if (!DA && mine && Uexp != nullptr && valid && !(g.dbg & 4)) {
+        float* urow = Uexp + ((size_t)it.k * g.u_rows + grow) * g.Dp + it.c * CW + col0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < 2 || wide) st_global_v8(urow + i * 8, v + 8 * i);
+      }
+      if (TRACE && first && threadIdx.x == 64) trace(tr, 6);
+      first = false;
+      ur.advance(kUBufs);
+      it.next(g);
+    }
+    if (TRACE && threadIdx.x == 64) trace(tr, 10);
+  } else if (warp >= 15) {
+    // ------------------------------------------------------------ output epilogue: O -> dq / da rows
+    // Row-per-thread stores are bound by the LSU (one 32-byte sector per lane and instruction): 32-byte stores where
+    // the row allows (rows of D = 300 floats are 32-byte aligned every other row; the others start with one 16-byte
+    // store) halve the instruction count of the 16-byte version.
+    const int quarter = warp & 3;
+    const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
+    const int row = quarter * 32 + lane;
+    const int p_lane = row / g.Lr;
+    const int N1 = g.N1, D = g.D;
+    int tc = 0;
+    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tc) {
+      const int n0 = (int)(t / (unsigned)g.ksplit) * g.P;
+      const bool valid = (p_lane < g.P) && (n0 + p_lane < g.N) && !(g.dbg & 2);
+      const long long grow = (long long)n0 * g.Lr + row;
+      float* orow = out + grow * D;
+      const bool shifted = (reinterpret_cast<uintptr_t>(orow) & 31) != 0;   // 16-byte aligned only
+      mbar_wait(&sm->o_full, (uint32_t)tc & 1u);
+      tc_fence_after();
+      if (TRACE && tc == 0 && lane == 0 && quarter == 0) trace(tr, 8);
+      for (int c = 0; c * 32 < N1; ++c) {
         float v[32];
         const uint32_t ta = tmem_O + lane_bits + (uint32_t)(c * 32);
-        const int w = (Nh - c * 32 > 16) ? 32 : 16;
-        if (w == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);
-        if (valid) {
+        const int wc = (N1 - c * 32 > 16) ? 32 : 16;
+        if (!(g.dbg & 16)) { if (wc == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v); }
+        if (!valid) continue;
+        const int ncols = mms_min(wc, D - c * 32);               // columns of this chunk that exist in the output
+        float* dst = orow + c * 32;
+        if (g.ksplit > 1 || !g.vec_out) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int col = c * 32 + i * 4;
-            if (i * 4 < w && col < ncols) {
-              if (g.vec_out && col + 4 <= ncols) {
-                float4* dst = reinterpret_cast<float4*>(orow + col);
+            if (i * 4 < ncols) {
+              if (g.vec_out && i * 4 + 4 <= ncols) {
                 const float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                if (g.ksplit > 1) atomicAdd(dst, o); else *dst = o;
+                if (g.ksplit > 1) atomicAdd(reinterpret_cast<float4*>(dst + 4 * i), o);
+                else *reinterpret_cast<float4*>(dst + 4 * i) = o;
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  if (col + j < ncols) {
-                    if (g.ksplit > 1) atomicAdd(orow + col + j, v[4 * i + j]); else orow[col + j] = v[4 * i + j];
+                  if (i * 4 + j < ncols) {
+                    if (g.ksplit > 1) atomicAdd(dst + 4 * i + j, v[4 * i + j]); else dst[4 * i + j] = v[4 * i + j];
                   }
                 }
               }
             }
+          }
+        } else if (!shifted) {          // D % 4 == 0: ncols is a multiple of 4
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i * 8 + 8 <= ncols) st_global_v8(dst + i * 8, v + i * 8);
+            else if (i * 8 + 4 <= ncols)
+              *reinterpret_cast<float4*>(dst + i * 8) = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+          }
+        } else {
+          if (ncols >= 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = 4 + i * 8;
+            if (c0 + 8 <= ncols) st_global_v8(dst + c0, v + c0);
+            else if (c0 + 4 <= ncols)
+              *reinterpret_cast<float4*>(dst + c0) = make_float4(v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->o_empty);
-      if (tc == 0 && threadIdx.x == 64) trace(tr, 9);
+      if (TRACE && tc == 0 && lane == 0 && quarter == 0) trace(tr, 9);
     }
-    if (threadIdx.x == 64) trace(tr, 10);
-  } else {
+  } else if (warp >= 10 && warp < 14) {
     // ------------------------------------------------------------ Gblk builders: thread r owns tile row r
     const int r = (warp - 10) * 32 + lane;
     const int p = r / g.Lr, l = r - p * g.Lr;
@@ -337,9 +490,10 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         *reinterpret_cast<float4*>(gblk + kb * 16384 + swz128(r, c4)) = make_float4(0.f, 0.f, 0.f, 0.f);
     int itk = 0;
     for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-      int n0, h, k_lo, k_hi;
-      decode(t, n0, h, k_lo, k_hi);
-      const bool valid = (p < g.P) && (n0 + p < g.N);
+      const int ksp = (int)(t % (unsigned)g.ksplit);
+      const int n0 = (int)(t / (unsigned)g.ksplit) * g.P;
+      const int k_lo = ksp * g.mc / g.ksplit, k_hi = (ksp + 1) * g.mc / g.ksplit;
+      const bool valid = (p < g.P) && (n0 + p < g.N) && !(g.dbg & 8);
       for (int k = k_lo; k < k_hi; ++k, ++itk) {
         // The G values of this row are loaded into registers BEFORE waiting for the tile to be free (the loads do
         // not touch shared memory), 64 at a time with all loads of a batch in flight together.
@@ -363,7 +517,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
                 if (e0 + i < g.Lk) v[i] = __ldg(src + (size_t)(e0 + i) * (DA ? g.La : 1));
             }
           }
-          if (e0 == 0 && itk > 0) mbar_wait(&sm->g_empty, (itk - 1) & 1);   // GEMM-A of the previous iteration has read Gblk
+          if (e0 == 0 && itk > 0) mbar_wait(&sm->g_empty, (uint32_t)(itk - 1) & 1u);   // every GEMM-A of the previous measure has read Gblk
           if (valid) {
             if (!DA && g.vec_g) {
 #pragma unroll
@@ -395,9 +549,12 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, g.tmem_cols);
-  if (threadIdx.x == 0) trace_end(tr);
+  if (warp == 1) tmem_dealloc(tmem_O, g.tmem_cols);
+  if (TRACE && threadIdx.x == 0) trace_end(tr);
 }
+
+// chunk width of U: three buffers behind O must fit the 512 TMEM columns
+int chunk_width(int N1) { return N1 + kUBufs * 64 <= 512 ? 64 : (N1 + kUBufs * 32 <= 512 ? 32 : 0); }
 
 }  // namespace
 
@@ -412,12 +569,9 @@ int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D
   if (disabled) return MMS_E_UNSUPPORTED;
   if (Lq > 128 || La > 128 || N < 1) return MMS_E_UNSUPPORTED;
   const int N1 = mms_ceil_div(D, 16) * 16;
-  if (N1 > 32 * kMaxChunks) return MMS_E_UNSUPPORTED;
-  const int nh = 2 * N1 <= 512 ? 1 : 2;
-  const int Nh0 = nh == 1 ? N1 : ((N1 / 2 + 31) & ~31);
-  if (N1 + Nh0 > 512 || Nh0 > 256) return MMS_E_UNSUPPORTED;
+  if (chunk_width(N1) == 0) return MMS_E_UNSUPPORTED;
   const int P = mms_max(1, mms_min(mms_min(128 / Lq, 128 / La), N));
-  const long long base = (long long)mms_ceil_div(N, P) * nh;
+  const long long base = mms_ceil_div(N, P);
   int ks = 1;
   if (base * 2 <= sm_count) ks = (int)mms_min<long long>(mc, sm_count / base);
   *ksplit = mms_max(1, ks);
@@ -438,41 +592,43 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   g.N = N; g.Lq = Lq; g.La = La; g.D = D; g.mc = mc;
   g.Lr = DA ? La : Lq; g.Lk = DA ? Lq : La;
   g.P = mms_max(1, mms_min(mms_min(128 / Lq, 128 / La), N));
+  g.nksA = mms_ceil_div(g.P * g.Lk, 8);
   g.N1 = mms_ceil_div(D, 16) * 16;
   g.np0 = g.N1 <= 256 ? g.N1 : ((g.N1 / 2 + 31) & ~31);
-  g.nh = 2 * g.N1 <= 512 ? 1 : 2;
-  g.Nh0 = g.nh == 1 ? g.N1 : ((g.N1 / 2 + 31) & ~31);
-  g.nka = mms_ceil_div(g.P * g.Lk, 32);
-  g.nkb = mms_ceil_div(D, 32);
-  g.nboxes = mms_ceil_div(g.N1, 32);
-  g.b2_bytes = DA ? mms_ceil_div(g.Nh0, 32) * 4096 : mms_ceil_div(g.Nh0 * 128, 1024) * 1024;
-  g.stage_bytes = mms_ceil_div(mms_max(g.nboxes * 4096, g.b2_bytes), 1024) * 1024;
-  g.kb2 = mms_max(1, mms_min(4, g.stage_bytes / g.b2_bytes));
+  g.np1 = g.N1 - g.np0;
+  g.CW = chunk_width(g.N1);
+  g.nch = mms_ceil_div(g.N1, g.CW);
+  g.wl = g.N1 - (g.nch - 1) * g.CW;
+  g.nbxB = mms_ceil_div(g.N1, 32);
+  const int a_bytes = mms_ceil_div(g.CW, 32) * 16384;
+  const int b_bytes = DA ? g.nbxB * 4096 : (g.np1 > 0 ? 2 : 1) * g.np0 * 128;
+  g.stage_bytes = mms_ceil_div(mms_max(a_bytes, b_bytes), 1024) * 1024;
   int stages = kMaxStages;
-  while (stages > 2 && (size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 226 * 1024) --stages;
-  if ((size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 226 * 1024) return MMS_E_UNSUPPORTED;
+  while (stages > 2 && (size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 227 * 1024) --stages;
+  if ((size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 227 * 1024) return MMS_E_UNSUPPORTED;
   g.stages = stages;
   g.ksplit = ksplit;
-  const long long total = (long long)mms_ceil_div(N, g.P) * g.nh * ksplit;
+  const long long total = (long long)mms_ceil_div(N, g.P) * ksplit;
   if (total > 0x7fffffffLL) return MMS_E_UNSUPPORTED;
   g.total_tiles = (unsigned)total;
-  g.tmem_cols = umma::tmem_cols_pow2((uint32_t)(g.N1 + g.Nh0));
+  g.tmem_cols = umma::tmem_cols_pow2((uint32_t)(g.N1 + kUBufs * g.CW));
   g.vec_g = (La % 4 == 0) && ((reinterpret_cast<uintptr_t>(dS) & 15) == 0);
-  g.vec_out = (D % 4 == 0) && (g.Nh0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  g.vec_out = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   g.Dp = Dp;
+  { static const char* e = getenv("MMS_BWD_DEBUG"); g.dbg = e ? atoi(e) : 0; }
   g.u_rows = (long long)N * g.Lr;
 
   CUtensorMap mapX, mapM;
-  MMS_TRY(mms_tc_make_map(ctx, &mapX, xr, Dp, true, D, (long long)N * g.Lk, 32, 0, 0, 0, 1, 1, 1));
-  if (!DA) MMS_TRY(mms_tc_make_map(ctx, &mapM, Mr, Dp, false, D, D, g.Nh0, (long long)D * Dp, 0, 0, mc, 1, 1));
+  MMS_TRY(mms_tc_make_map(ctx, &mapX, xr, Dp, true, D, (long long)N * g.Lk, 32, 0, 0, 0, 1, 1, 1, 128));
+  if (!DA) MMS_TRY(mms_tc_make_map(ctx, &mapM, Mr, Dp, false, D, D, g.np0, (long long)D * Dp, 0, 0, mc, 1, 1));
   else MMS_TRY(mms_tc_make_map(ctx, &mapM, Mr, Dp, true, D, D, 32, (long long)D * Dp, 0, 0, mc, 1, 1));
 
   static bool configured = false;
   if (!configured) {
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
+    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const size_t smem = (size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024;
@@ -480,17 +636,22 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   TraceBuf tb;
   MMS_TRY(tb.begin(grid));
   { MmsKernelScope ks_(ctx, DA ? "simcross2_bwd_fused_kernel<dA>" : "simcross2_bwd_fused_kernel<dQ>");
-    if (!DA) simcross2_bwd_fused_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(mapX, mapM, dS, out, Uexp, g, tb.dev);
-    else simcross2_bwd_fused_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(mapX, mapM, dS, out, nullptr, g, tb.dev); }
+    if (tb.dev) {
+      if (!DA) simcross2_bwd_fused_kernel<false, true><<<grid, kThreads, smem, ctx->stream>>>(mapX, mapM, dS, out, Uexp, g, tb.dev);
+      else simcross2_bwd_fused_kernel<true, true><<<grid, kThreads, smem, ctx->stream>>>(mapX, mapM, dS, out, nullptr, g, tb.dev);
+    } else {
+      if (!DA) simcross2_bwd_fused_kernel<false, false><<<grid, kThreads, smem, ctx->stream>>>(mapX, mapM, dS, out, Uexp, g, nullptr);
+      else simcross2_bwd_fused_kernel<true, false><<<grid, kThreads, smem, ctx->stream>>>(mapX, mapM, dS, out, nullptr, g, nullptr);
+    } }
   MMS_LAUNCH_CHECK();
-  static const char* const names[kTraceSlots] = {"entry", "setup", "tma_issued", "first_full", "gA_issued", "u_full",
-                                                 "rounded", "gB_issued", "o_full", "epi0_done", "epi_done", "exit",
-                                                 "last_u_full", nullptr, nullptr, nullptr,
-                                                 "W:g_full", "W:fullA", "W:o_empty", "W:fullB", "W:t_ready", nullptr, nullptr,
+  static const char* const names[kTraceSlots] = {"entry", "setup", "tma_issued", nullptr, "prologue_issued", "u_full",
+                                                 "rounded", nullptr, "o_full", "epi0_done", "epi_done", "exit",
+                                                 nullptr, nullptr, nullptr, nullptr,
+                                                 "W:g_full", "W:fullA", "W:o_empty", "W:fullB", "W:u_ready", "W:u_free", nullptr,
                                                  nullptr};
-  char what[112];
-  snprintf(what, sizeof(what), "bwd %s N %d L %dx%d D %d mc %d P %d nh %d ksplit %d tiles %u stages %d", DA ? "dA" : "dQ",
-           N, Lq, La, D, mc, g.P, g.nh, ksplit, g.total_tiles, stages);
+  char what[128];
+  snprintf(what, sizeof(what), "bwd %s N %d L %dx%d D %d mc %d P %d CW %d nch %d ksplit %d tiles %u stages %d", DA ? "dA" : "dQ",
+           N, Lq, La, D, mc, g.P, g.CW, g.nch, ksplit, g.total_tiles, stages);
   MMS_TRY(tb.end(ctx, what, names));
   return 0;
 }

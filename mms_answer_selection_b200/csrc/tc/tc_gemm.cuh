@@ -47,12 +47,12 @@ int mms_tc_gemm_staged(mms_context* ctx, const TcGemmArgs& args);
 int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& args);   // MMS_E_UNSUPPORTED if not eligible
 
 // Tensor map (cached per handle) over operand X(mn, k): K-major X[mn*ld + k] (box = rows_box x 32 k) or
-// MN-major X[k*ld + mn] (box = 32 k x 32 mn); batch strides s1 (extent nb1), s2 (nb2), segment stride sseg
+// MN-major X[k*ld + mn] (box = k_box k x 32 mn); batch strides s1 (extent nb1), s2 (nb2), segment stride sseg
 // (nseg) in elements, 0 = broadcast.  `out` points at a CUtensorMap.  TMA coordinates: K-major
 // (k, mn, z2, z1, seg), MN-major (mn, k, z2, z1, seg); out-of-range elements read as zero.
 int mms_tc_make_map(mms_context* ctx, void* out, const float* ptr, long long ld, bool mn_major, long long MN,
                     long long K, int rows_box, long long s1, long long s2, long long sseg, int nb1, int nb2,
-                    int nseg);
+                    int nseg, int k_box = 32);
 
 // dst[r*ldd + c] = tf32_rna(src[r*lds + c] * (scale ? scale[r] : 1)) for up to 4 matrices in one launch.
 struct RoundJob {

@@ -383,7 +383,8 @@ TcState* state_of(mms_context* ctx) {
 // Operand X(mn, k): K-major X[mn*ld + k] or MN-major X[k*ld + mn]; batch strides s1, s2 and segment
 // stride sseg in elements (0 = broadcast).  rows_box: rows per K-major box.
 int make_map(mms_context* ctx, CUtensorMap* out, const float* ptr, long long ld, bool mn_major, long long MN,
-             long long K, int rows_box, long long s1, long long s2, long long sseg, int nb1, int nb2, int nseg) {
+             long long K, int rows_box, long long s1, long long s2, long long sseg, int nb1, int nb2, int nseg,
+             int k_box = 32) {
   TcState* st = state_of(ctx);
   if (!st->encode) {
     void* fn = nullptr;
@@ -392,14 +393,14 @@ int make_map(mms_context* ctx, CUtensorMap* out, const float* ptr, long long ld,
     MMS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MMS_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
     st->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
   }
-  const MapKey key(ptr, ld, mn_major ? 1 : 0, MN, K, rows_box, s1, s2, sseg, nb1, nb2, nseg);
+  const MapKey key(ptr, ld, mn_major ? k_box : 0, MN, K, rows_box, s1, s2, sseg, nb1, nb2, nseg);
   auto hit = st->maps.find(key);
   if (hit != st->maps.end()) { *out = hit->second; return 0; }
   cuuint64_t dims[5], strides[4];
   cuuint32_t box[5] = {32, 32, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
   dims[0] = (cuuint64_t)(mn_major ? MN : K);
   dims[1] = (cuuint64_t)(mn_major ? K : MN);
-  if (!mn_major) box[1] = (cuuint32_t)rows_box;
+  box[1] = (cuuint32_t)(mn_major ? k_box : rows_box);
   strides[0] = (cuuint64_t)ld * 4;
   // broadcast / singleton dimensions get extent 1; their stride only has to be a legal value
   const cuuint64_t filler = strides[0] * dims[1];
@@ -430,9 +431,9 @@ bool tma_ok(const float* p, long long ld, long long s1, long long s2, long long 
 
 int mms_tc_make_map(mms_context* ctx, void* out, const float* ptr, long long ld, bool mn_major, long long MN,
                     long long K, int rows_box, long long s1, long long s2, long long sseg, int nb1, int nb2,
-                    int nseg) {
+                    int nseg, int k_box) {
   return make_map(ctx, static_cast<CUtensorMap*>(out), ptr, ld, mn_major, MN, K, rows_box, s1, s2, sseg, nb1, nb2,
-                  nseg);
+                  nseg, k_box);
 }
 
 void mms_tc_destroy_state(mms_context* ctx) {

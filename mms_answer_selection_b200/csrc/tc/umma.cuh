@@ -90,6 +90,12 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
       "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// the same box, fetched into L2 only (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_l2_5d(const void* tmap, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

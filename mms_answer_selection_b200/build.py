@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177",
-]
+] + os.environ.get("MMS_NVCC_EXTRA", "").split()
 
 
 def sources():

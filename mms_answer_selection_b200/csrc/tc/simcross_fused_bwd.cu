@@ -64,10 +64,11 @@ struct BwdGeom {
   int ksplit;            // CTAs that share the measures of one pair group
   unsigned total_tiles;
   uint32_t tmem_cols;
-  int vec_g, vec_out;
+  int vec_g, vec_s, vec_out;   // 16-byte dS loads (dQ) / 16-byte Gblk stores / 16-byte output stores
   int Dp;                // row pitch of the exported U
-  int dbg;               // MMS_BWD_DEBUG timing knobs (wrong results): 1 no rounding, 2 no output stores, 4 no U export,
-                         // 8 no dS loads, 16 no epilogue TMEM loads
+  int dbg;               // timing probes (MMS_BWD_PROBES builds only; WRONG results): 1 no rounding, 2 no output stores,
+                         // 4 no U export, 8 no Gblk build, 16 no epilogue TMEM loads, 32 L2 prefetch of the next tile's X,
+                         // 64 / 128 GEMM-B slots filled from private lines / with half of the bytes, 256 no dS loads
   long long u_rows;      // rows of one measure slab of the exported U
 };
 
@@ -137,7 +138,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
       for (int s = 0; s < g.stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
       mbar_init(&sm->g_full, 4); mbar_init(&sm->g_empty, 1);
       mbar_init(&sm->o_full, 1); mbar_init(&sm->o_empty, 4);
-      for (int j = 0; j < kUBufs; ++j) { mbar_init(&sm->u_full[j], 1); mbar_init(&sm->u_ready[j], 8); mbar_init(&sm->u_free[j], 1); }
+      for (int j = 0; j < kUBufs; ++j) { mbar_init(&sm->u_full[j], 1); mbar_init(&sm->u_ready[j], DA ? 8 : 4); mbar_init(&sm->u_free[j], DA ? 1 : 5); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -191,6 +192,15 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         mbar_wait(&sm->empty[slot.i], slot.ph ^ 1u);
         uint8_t* dst = ring + slot.i * stage_bytes;
         if (elect_one_sync()) {
+          if (g.dbg & 64) {            // timing probe: the same slot filled from this CTA's own X rows (no shared lines)
+            mbar_arrive_expect_tx(&sm->full[slot.i], 32768u);
+            tma_load_5d(dst, &mapX, &sm->full[slot.i], (e0 & 255), it.n0 * Lk, 0, 0, 0);
+            tma_load_5d(dst + 16384, &mapX, &sm->full[slot.i], ((e0 + 32) & 255), it.n0 * Lk, 0, 0, 0);
+          } else if (g.dbg & 128) {    // timing probe: half of the bytes
+            mbar_arrive_expect_tx(&sm->full[slot.i], DA ? 5u * 4096u : (uint32_t)np0 * 128u);
+            if (!DA) tma_load_5d(dst, &mapM, &sm->full[slot.i], e0, 0, 0, it.k, 0);
+            else for (int x = 0; x < 5; ++x) tma_load_5d(dst + x * 4096, &mapM, &sm->full[slot.i], 32 * x, e0, 0, it.k, 0);
+          } else {
           mbar_arrive_expect_tx(&sm->full[slot.i], bytesB);
           if (!DA) {
             tma_load_5d(dst, &mapM, &sm->full[slot.i], e0, 0, 0, it.k, 0);
@@ -198,6 +208,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
           } else {
             for (int x = 0; x < nbxB; ++x)
               tma_load_5d(dst + x * 4096, &mapM, &sm->full[slot.i], 32 * x, e0, 0, it.k, 0);
+          }
           }
         }
         __syncwarp();
@@ -359,6 +370,10 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------ U rounding / export
+    // dA: eight warps round (two per TMEM lane quarter, 32 columns of the chunk each).
+    // dQ: warps 2-5 round the whole chunk; warps 6-9 read the rounded chunk back and write it to global memory for the
+    //     dM contraction.  Row-per-thread stores cost one LSU wavefront per lane and instruction (~1000 cycles per
+    //     chunk for the CTA); issued by the rounding warps they sat on the round -> GEMM-B path of the NEXT chunk.
     const int quarter = warp & 3;
     const int set = (warp - 2) >> 2;
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
@@ -369,45 +384,64 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     bool first = true;
     ChunkIter it;
     it.start(g);
-    while (it.live) {
-      const bool valid = (p_lane < g.P) && (it.n0 + p_lane < g.N);
-      const long long grow = (long long)it.n0 * g.Lr + row;      // row of U this thread owns
-      mbar_wait(&sm->u_full[ur.i], ur.ph);
-      tc_fence_after();
-      if (TRACE && first && threadIdx.x == 64) trace(tr, 5);
-      const int w = it.c == nch - 1 ? wl : CW;
-      const int col0 = set * 32;                                  // this warp's 32 columns of the chunk
-      const bool mine = col0 < w && !(g.dbg & 1);
-      const bool wide = w - col0 > 16;
-      float v[32];
-      if (mine) {
-        const uint32_t ta = tmem_U + lane_bits + (uint32_t)(ur.i * CW + col0);
-        if (wide) {
-          tmem_ld32(ta, v);
+    if (!DA && set == 1) {
+      while (it.live) {
+        const bool valid = (p_lane < g.P) && (it.n0 + p_lane < g.N) && Uexp != nullptr && !(g.dbg & 4);
+        const long long grow = (long long)it.n0 * g.Lr + row;    // row of U this thread owns
+        mbar_wait(&sm->u_ready[ur.i], ur.ph);
+        tc_fence_after();
+        const int w = it.c == nch - 1 ? wl : CW;
+        float* urow = Uexp + ((size_t)it.k * g.u_rows + grow) * g.Dp + it.c * CW;
+        for (int c0 = 0; c0 < w; c0 += 32) {
+          float v[32];
+          const uint32_t ta = tmem_U + lane_bits + (uint32_t)(ur.i * CW + c0);
+          const bool wide = w - c0 > 16;
+          if (wide) tmem_ld32(ta, v); else tmem_ld16(ta, v);
+          if (valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = to_tf32(v[i]);
-          tmem_st32(ta, v);
-        } else {
-          tmem_ld16(ta, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = to_tf32(v[i]);
-          tmem_st16(ta, v);
+            for (int i = 0; i < 4; ++i)
+              if (i < 2 || wide) st_global_v8(urow + c0 + i * 8, v + 8 * i);
+          }
         }
-        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->u_free[ur.i]);
+        ur.advance(kUBufs);
+        it.next(g);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm->u_ready[ur.i]);             // GEMM-B may start; the export below is off its path
-      if (!DA && mine && Uexp != nullptr && valid && !(g.dbg & 4)) {
-        float* urow = Uexp + ((size_t)it.k * g.u_rows + grow) * g.Dp + it.c * CW + col0;
+    } else {
+      const int step = DA ? 64 : 32;                              // column stride between the pieces of one warp
+      while (it.live) {
+        mbar_wait(&sm->u_full[ur.i], ur.ph);
+        tc_fence_after();
+        if (TRACE && first && threadIdx.x == 64) trace(tr, 5);
+        const int w = it.c == nch - 1 ? wl : CW;
+        if (!(g.dbg & 1)) {
+          for (int c0 = DA ? set * 32 : 0; c0 < w; c0 += step) {
+            float v[32];
+            const uint32_t ta = tmem_U + lane_bits + (uint32_t)(ur.i * CW + c0);
+            if (w - c0 > 16) {
+              tmem_ld32(ta, v);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < 2 || wide) st_global_v8(urow + i * 8, v + 8 * i);
+              for (int i = 0; i < 32; ++i) v[i] = to_tf32(v[i]);
+              tmem_st32(ta, v);
+            } else {
+              tmem_ld16(ta, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = to_tf32(v[i]);
+              tmem_st16(ta, v);
+            }
+          }
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->u_ready[ur.i]);
+        if (TRACE && first && threadIdx.x == 64) trace(tr, 6);
+        first = false;
+        ur.advance(kUBufs);
+        it.next(g);
       }
-      if (TRACE && first && threadIdx.x == 64) trace(tr, 6);
-      first = false;
-      ur.advance(kUBufs);
-      it.next(g);
     }
     if (TRACE && threadIdx.x == 64) trace(tr, 10);
   } else if (warp >= 15) {
@@ -502,7 +536,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         const int col0 = p * g.Lk;
         float v[64];
         for (int e0 = 0; e0 < g.Lk; e0 += 64) {
-          if (valid) {
+          if (valid && !(g.dbg & 256)) {
             if (!DA && g.vec_g) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -518,8 +552,10 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
             }
           }
           if (e0 == 0 && itk > 0) mbar_wait(&sm->g_empty, (uint32_t)(itk - 1) & 1u);   // every GEMM-A of the previous measure has read Gblk
+          // a thread's values are consecutive contraction columns of its own Gblk row (dQ: a row of G, dA: a column
+          // of G): 16-byte stores whenever the pair blocks start on a multiple of four columns
           if (valid) {
-            if (!DA && g.vec_g) {
+            if (g.vec_s) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 if (e0 + 4 * i < g.Lk) {
@@ -606,6 +642,7 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   int stages = kMaxStages;
   while (stages > 2 && (size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 227 * 1024) --stages;
   if ((size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 227 * 1024) return MMS_E_UNSUPPORTED;
+  { static const char* e = getenv("MMS_BWD_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
   g.stages = stages;
   g.ksplit = ksplit;
   const long long total = (long long)mms_ceil_div(N, g.P) * ksplit;
@@ -613,9 +650,13 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   g.total_tiles = (unsigned)total;
   g.tmem_cols = umma::tmem_cols_pow2((uint32_t)(g.N1 + kUBufs * g.CW));
   g.vec_g = (La % 4 == 0) && ((reinterpret_cast<uintptr_t>(dS) & 15) == 0);
+  g.vec_s = g.Lk % 4 == 0;
   g.vec_out = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   g.Dp = Dp;
+  g.dbg = 0;
+#ifdef MMS_BWD_PROBES   // timing probes that skip parts of the kernel (WRONG results): MMS_NVCC_EXTRA=-DMMS_BWD_PROBES builds only
   { static const char* e = getenv("MMS_BWD_DEBUG"); g.dbg = e ? atoi(e) : 0; }
+#endif
   g.u_rows = (long long)N * g.Lr;
 
   CUtensorMap mapX, mapM;

@@ -248,6 +248,7 @@ def main_ours(args):
     l0 = sum(h.launch_count() for h in handles)
     net.capture(with_loss=True, clear_diffs=True)
     launches_per_step = (sum(h.launch_count() for h in handles) - l0) // 3      # 2 warm-up passes + the capture
+    net.capture(with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a))  # + H2D / D2H nodes for the e2e step
 
     def device_step():
         net.replay(read_loss=False)
@@ -255,12 +256,13 @@ def main_ours(args):
             exch.allreduce()
 
     def e2e_step():
+        if not exch:
+            # one graph launch: H2D of this step's inputs (pinned), the step, D2H of the loss (4 bytes), then a sync
+            return net.replay_from_host()
         net.set_inputs_from_pinned(host_q, host_a)      # H2D of this step's inputs
-        loss = net.replay(read_loss=not exch)           # D2H of the step's loss (4 bytes) + sync
-        if exch:
-            exch.allreduce()
-            loss = float(net.sim.loss_dev_[0].item())
-        return loss
+        net.replay(read_loss=False)
+        exch.allreduce()
+        return float(net.sim.loss_dev_[0].item())       # D2H of the step's loss (4 bytes) + sync
 
     def eager_step():
         net.ClearParamDiffs()          # Net::ClearParamDiffs (solver.cpp:203): zeroes the V x D diff too

@@ -174,7 +174,12 @@ int mms_tc_simcross2_forward_fused(mms_context*, const float* qr, const float* a
 // of the `ctas` CTAs it may use share one tile's measures (> 1: `out` must be zeroed by the caller).
 int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int* ksplit);
 int mms_tc_simcross2_backward_fused(mms_context*, int which, const float* xr, const float* Mr, const float* dS,
-                                    float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp, int ksplit);
+                                    float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp, int ksplit,
+                                    int u_blocked = 0);
+// weight gradient dM_k += Qall^T U_k from the blocked U export (tc/simcross_dm.cu); _plan: shape covered?
+int mms_tc_simcross2_dm_plan(int D);
+int mms_tc_simcross2_dm(mms_context*, const float* qr, const float* Ub, float* dM, long long rows, int D, int Dp, int mc,
+                        int blocked = 1);
 // (dq, da, dM overwritten; dB is accumulated by the caller)
 int mms_tc_simcross2_backward(mms_context*, const float* q, const float* a, const float* Mw,
                               const float* dS, float* dq, float* da, float* dM, int N, int Lq, int La,

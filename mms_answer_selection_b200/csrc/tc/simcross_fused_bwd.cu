@@ -70,6 +70,8 @@ struct BwdGeom {
                          // 4 no U export, 8 no Gblk build, 16 no epilogue TMEM loads, 32 L2 prefetch of the next tile's X,
                          // 64 / 128 GEMM-B slots filled from private lines / with half of the bytes, 256 no dS loads
   long long u_rows;      // rows of one measure slab of the exported U
+  int u_blocked;         // U export layout: 0 row-major (pitch Dp), 1 blocked (tc/simcross_dm.cu)
+  long long u_groups;    // blocked: 32-row groups per measure slab
 };
 
 struct BwdSmem {
@@ -385,22 +387,45 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     ChunkIter it;
     it.start(g);
     if (!DA && set == 1) {
+      if (g.u_blocked && Uexp != nullptr && blockIdx.x == 0) {
+        // rows past the last token row of the last 32-row group are read by the dM kernel: they must be zero
+        const int tail0 = (int)(g.u_rows & 31);
+        if (tail0 != 0) {
+          const int ntail = 32 - tail0, per_k = g.N1 * ntail;
+          for (int e = (warp - 6) * 32 + lane; e < g.mc * per_k; e += 128) {
+            const int kk = e / per_k, rem = e - kk * per_k;
+            const int col = rem / ntail, r = tail0 + rem - col * ntail;
+            Uexp[(((size_t)kk * g.u_groups + (size_t)(g.u_groups - 1)) * g.Dp + col) * 32 + r] = 0.f;
+          }
+        }
+      }
       while (it.live) {
         const bool valid = (p_lane < g.P) && (it.n0 + p_lane < g.N) && Uexp != nullptr && !(g.dbg & 4);
         const long long grow = (long long)it.n0 * g.Lr + row;    // row of U this thread owns
         mbar_wait(&sm->u_ready[ur.i], ur.ph);
         tc_fence_after();
         const int w = it.c == nch - 1 ? wl : CW;
-        float* urow = Uexp + ((size_t)it.k * g.u_rows + grow) * g.Dp + it.c * CW;
+        // row-major: this row's 32 bytes every 8 columns (a different 128-byte line per lane: 32 LSU wavefronts per
+        // instruction); blocked (tc/simcross_dm.cu): the 32 rows of a group are contiguous per column, so one 4-byte
+        // store per column writes 128 consecutive bytes per warp
+        float* urow = g.u_blocked
+            ? Uexp + (((size_t)it.k * g.u_groups + (size_t)(grow >> 5)) * g.Dp + (size_t)(it.c * CW)) * 32 + (size_t)(grow & 31)
+            : Uexp + ((size_t)it.k * g.u_rows + grow) * g.Dp + it.c * CW;
         for (int c0 = 0; c0 < w; c0 += 32) {
           float v[32];
           const uint32_t ta = tmem_U + lane_bits + (uint32_t)(ur.i * CW + c0);
           const bool wide = w - c0 > 16;
           if (wide) tmem_ld32(ta, v); else tmem_ld16(ta, v);
           if (valid) {
+            if (g.u_blocked) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i < 2 || wide) st_global_v8(urow + c0 + i * 8, v + 8 * i);
+              for (int i = 0; i < 32; ++i)
+                if (i < 16 || wide) urow[(size_t)(c0 + i) * 32] = v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < 2 || wide) st_global_v8(urow + c0 + i * 8, v + 8 * i);
+            }
           }
         }
         tc_fence_before();
@@ -617,7 +642,7 @@ int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D
 
 int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr, const float* Mr, const float* dS,
                                     float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp,
-                                    int ksplit) {
+                                    int ksplit, int u_blocked) {
   BwdGeom g;
   {
     int unused = 1;
@@ -658,6 +683,8 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   { static const char* e = getenv("MMS_BWD_DEBUG"); g.dbg = e ? atoi(e) : 0; }
 #endif
   g.u_rows = (long long)N * g.Lr;
+  g.u_blocked = u_blocked;
+  g.u_groups = (g.u_rows + 31) / 32;
 
   CUtensorMap mapX, mapM;
   MMS_TRY(mms_tc_make_map(ctx, &mapX, xr, Dp, true, D, (long long)N * g.Lk, 32, 0, 0, 0, 1, 1, 1, 128));

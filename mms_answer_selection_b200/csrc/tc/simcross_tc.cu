@@ -17,6 +17,8 @@
 // No operand is ever transposed in memory: the UMMA descriptors take K-major and MN-major
 // tiles alike (tc_gemm.cu).  T / U live in the handle's scratch buffer; N is processed in
 // chunks when mc*N*L*D floats exceed MMS_OPT_SCRATCH_BYTES.
+#include <stdlib.h>
+
 #include "../mms_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -61,7 +63,8 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
   const Plan p = make_plan(ctx, N, Lq, La, D, mc, false);
   const int Dp = p.Dp;
   void* sp = nullptr;
-  MMS_TRY(mms_scratch(ctx, sizeof(float) * (p.fixed + p.per_pair * p.nc_max), &sp));
+  // (+ room for the blocked U export of a later backward: up to 31 padding rows per measure)
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * (p.fixed + p.per_pair * p.nc_max + (size_t)mc * 32 * Dp), &sp));
   float* Mr = static_cast<float*>(sp);
   float* qr = Mr + p.fixed;
   float* ar = qr + (size_t)p.nc_max * Lq * Dp;
@@ -128,7 +131,7 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
   // MMS_OPT_REUSE_FORWARD: the last forward on this handle left the rounded q, a and M at the head of the scratch
   // buffer (same layout: Mr | qr | ar | per-measure intermediate) and nothing has touched the buffer since
   const mms_context::FwdCache& fc = ctx->fwd_cache;
-  const size_t need = sizeof(float) * (fixed + per_pair * nc_max);
+  const size_t need = sizeof(float) * (fixed + per_pair * nc_max + (size_t)mc * 32 * Dp);   // blocked U: padded to 32-row groups
   const bool reuse = ctx->reuse_forward && fc.valid && fc.q == q && fc.a == a && fc.M == Mw && fc.N == N &&
                      fc.Lq == Lq && fc.La == La && fc.D == D && fc.mc == mc && nc_max == N && need <= ctx->scratch_bytes;
   void* sp = ctx->scratch;
@@ -165,8 +168,14 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
       MmsStreamSwitch sw(ctx, 0);
       MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit));  // :296-299
     }
-    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp, ksplit));   // :291-294
-    MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));                                                   // :286-289
+    // dedicated dM kernel (tc/simcross_dm.cu) over the blocked U export; small batches are latency-bound and do
+    // better with the 32-byte row-major export and the many small tiles of the generic engine (measured at 50 pairs)
+    const int use_dm = mms_tc_simcross2_dm_plan(D) == 0 && (long long)nc * Lq >= 16384;
+    static const bool rowmajor_u = getenv("MMS_DM_ROWMAJOR") != nullptr;
+    const int blocked = use_dm && !rowmajor_u;                // U in the blocked layout that kernel reads best
+    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp, ksplit, blocked));   // :291-294
+    if (use_dm) MMS_TRY(mms_tc_simcross2_dm(ctx, qr, U, dM, (long long)nc * Lq, D, Dp, mc, blocked));        // :286-289
+    else MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));
     if (conc) MMS_TRY(mms_join(ctx, 0));
     else MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit));
   }

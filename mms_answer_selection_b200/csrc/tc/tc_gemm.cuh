@@ -54,6 +54,9 @@ int mms_tc_make_map(mms_context* ctx, void* out, const float* ptr, long long ld,
                     long long K, int rows_box, long long s1, long long s2, long long sseg, int nb1, int nb2,
                     int nseg, int k_box = 32);
 
+int mms_tc_make_map_raw(mms_context* ctx, void* out, const float* ptr, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box, bool atom32b);
+
 // dst[r*ldd + c] = tf32_rna(src[r*lds + c] * (scale ? scale[r] : 1)) for up to 4 matrices in one launch.
 struct RoundJob {
   const float* src; float* dst; long long rows; int cols; long long lds, ldd; const float* scale;

@@ -436,6 +436,34 @@ int mms_tc_make_map(mms_context* ctx, void* out, const float* ptr, long long ld,
                   nseg, k_box);
 }
 
+// A tensor map given dimension by dimension (fp32 elements, strides in bytes for dimensions 1..rank-1, 128-byte
+// swizzle: the 32-byte-atom variant the MN-major UMMA layout needs, or the plain one).  Not cached.
+int mms_tc_make_map_raw(mms_context* ctx, void* out, const float* ptr, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box, bool atom32b) {
+  TcState* st = state_of(ctx);
+  if (!st->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MMS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    MMS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, MMS_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+    st->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  }
+  MMS_REQUIRE(rank >= 1 && rank <= 5, MMS_E_INVALID, "tensor map rank");
+  cuuint64_t d[5], sb[4];
+  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) sb[i] = strides_bytes[i];
+  const CUresult r = st->encode(static_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                                const_cast<float*>(ptr), d, sb, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mms_set_error("cuTensorMapEncodeTiled (raw, rank %d) failed with CUresult %d", rank, (int)r);
+    return MMS_E_UNSUPPORTED;
+  }
+  return 0;
+}
+
 void mms_tc_destroy_state(mms_context* ctx) {
   delete static_cast<TcState*>(ctx->tc_state);
   ctx->tc_state = nullptr;

@@ -153,7 +153,11 @@ class MMSNet(object):
     # (the reference has the same problem in the small: 2*N*mc host BLAS calls).  Recording
     # ClearParamDiffs + Forward + Backward once and replaying the graph removes the host from
     # the loop.  Blob storage must not be re-allocated between capture and replay.
-    def capture(self, with_loss=True, clear_diffs=True):
+    def capture(self, with_loss=True, clear_diffs=True, host_inputs=None):
+        """Records one step.  With `host_inputs=(host_q, host_a)` (pinned tensors) a second graph is recorded
+        that also contains the H2D copies of the two id tensors and the D2H copy of the loss scalar into a pinned
+        buffer, so that an end-to-end step is ONE graph launch and one stream synchronisation
+        (`replay_from_host`)."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         self.sim.defer_loss_ = True
@@ -170,7 +174,30 @@ class MMSNet(object):
             self.sim.defer_loss_ = False
         self._graph = graph
         self._graph_with_loss = with_loss
+        self._graph_host = None
+        if host_inputs is not None:
+            host_q, host_a = host_inputs
+            assert host_q.is_pinned() and host_a.is_pinned()
+            self._host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.sim.defer_loss_ = True
+            try:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=side):
+                    self.set_inputs_from_pinned(host_q, host_a)
+                    self.ForwardBackwardConcurrent(with_loss, clear_diffs)
+                    if with_loss:
+                        self._host_loss.copy_(self.sim.loss_dev_[0], non_blocking=True)
+            finally:
+                self.sim.defer_loss_ = False
+            self._graph_host = g2
+            self._graph_stream = side
         return graph
+
+    def replay_from_host(self):
+        """One recorded end-to-end step: H2D of the pinned inputs given to `capture`, the step, D2H of the loss."""
+        self._graph_host.replay()
+        torch.cuda.current_stream().synchronize()
+        return float(self._host_loss[0]) if self._graph_with_loss else 0.0
 
     def replay(self, read_loss=True):
         """One recorded step.  Returns the loss (D2H of one scalar + sync) when asked to."""

@@ -485,6 +485,37 @@ def test_simcross_full_size_properties():
     assert (ba.diff.double() - da_ref).abs().max().item() <= TOL_TF32 * da_ref.abs().max().item()
 
 
+@pytest.mark.parametrize("shape", [(411, 40, 40, 300, 2), (530, 33, 31, 130, 3)])
+def test_simcross_backward_blocked_export_ragged(shape):
+    """Large-batch backward (dedicated dM kernel over the blocked U export, tc/simcross_dm.cu) with a token-row
+    count that is not a multiple of the 32-row groups of that layout: the rows past the end must read as zero."""
+    N, Lq, La, D, mc = shape
+    assert (N * Lq) % 32 != 0 and N * Lq >= 16384
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    lay = mms.SimCrossLayer(mms.LayerParameter("SimCross", sim_cross_param=dict(dist_mode=2, mesure_count=mc)))
+    Mw = (torch.rand((mc, D, D), device="cuda", generator=gen) - 0.5) * 0.2
+    # a slightly larger batch first: it leaves non-zero U rows in the handle's scratch buffer exactly where the
+    # ragged batch's padding rows will be
+    for n in (N + 3, N):
+        q = (torch.rand((n, Lq, D), device="cuda", generator=gen) - 0.5) * 0.16
+        a = (torch.rand((n, La, D), device="cuda", generator=gen) - 0.5) * 0.16
+        bq, ba, top = mms.Blob((n, Lq, D)), mms.Blob((n, La, D)), mms.Blob(())
+        if n == N + 3:
+            lay.SetUp([bq, ba], [top])
+            lay.blobs[0].data.copy_(Mw)
+        bq.data.copy_(q); ba.data.copy_(a)
+        lay.Forward([bq, ba], [top])
+        dS = (torch.rand(top.shape, device="cuda", generator=gen) - 0.5)
+        top.diff.copy_(dS)
+        lay.Backward([top], [True, True], [bq, ba])
+    dM_ref = torch.einsum("nld,nklm,nme->kde", q.double(), dS.double(), a.double())
+    assert (lay.blobs[0].diff.double() - dM_ref).abs().max().item() <= TOL_TF32 * dM_ref.abs().max().item()
+    dq_ref = torch.einsum("nklm,nme,kde->nld", dS.double(), a.double(), Mw.double())
+    assert (bq.diff.double() - dq_ref).abs().max().item() <= TOL_TF32 * dq_ref.abs().max().item()
+    da_ref = torch.einsum("nklm,nld,kde->nme", dS.double(), q.double(), Mw.double())
+    assert (ba.diff.double() - da_ref).abs().max().item() <= TOL_TF32 * da_ref.abs().max().item()
+
+
 def test_rerank_scores_vs_simmatrix_form():
     """candidate scoring: scores[i,j] = q_i^T W c_j, checked against the SimMatrix oracle."""
     import ctypes

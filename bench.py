@@ -50,7 +50,8 @@ def kernel_flop_shares(L, D, mc):
         "simcross2_fwd_fused_kernel": mc * 2.0 * L * D * (D + L),
         "simcross2_bwd_fused_kernel<dQ>": mc * (2.0 * L * D * D + 4.0 * L * L * D),   # A M^T, dQ and U = dS A
         "simcross2_bwd_fused_kernel<dA>": mc * 2.0 * L * L * D,
-        "tc_gemm_tma_kernel": mc * 2.0 * L * D * D,                                   # dM = Q^T U
+        "tc_gemm_tma_kernel": mc * 2.0 * L * D * D,                                   # dM = Q^T U (small batches)
+        "simcross2_dm_kernel": mc * 2.0 * L * D * D,                                  # dM = Q^T U (tc/simcross_dm.cu)
     }
 
 
@@ -474,24 +475,41 @@ def extras(world, rank, flush):
     return out
 
 
-def ncu_traffic(wl, name):
-    """DRAM bytes per launch of kernel `name` from the committed `ncu --set full` capture of this workload
-    (profiles/r01_ncu_full_<wl>_fused.json, tools/ncu_summary.py), or None."""
-    alias = {"simcross2_bwd_fused_kernel<dQ>": "simcross2_bwd_fused_kernel<0>",
-             "simcross2_bwd_fused_kernel<dA>": "simcross2_bwd_fused_kernel<1>"}
+def _ncu_row(wl, name):
+    """The row of kernel `name` in the committed `ncu --set full` summary of this workload
+    (profiles/r01_ncu_full_<wl>_fused.json, written by tools/ncu_summary.py), or None."""
+    alias = {"simcross2_bwd_fused_kernel<dQ>": "simcross2_bwd_fused_kernel<0, 0>",
+             "simcross2_bwd_fused_kernel<dA>": "simcross2_bwd_fused_kernel<1, 0>"}
     try:
         rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_%s_fused.json" % wl)))
     except Exception:
         return None
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows:
         if r.get("kernel") == alias.get(name, name):
-            tot = 0.0
-            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                v, u = r[k].split()
-                tot += float(v) * scale.get(u, 1.0)
-            return tot
+            return r
     return None
+
+
+def ncu_traffic(wl, name):
+    """DRAM bytes per launch of kernel `name` from the committed ncu capture of this workload, or None."""
+    r = _ncu_row(wl, name)
+    if not r:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        v, u = r[k].split()
+        tot += float(v) * scale.get(u, 1.0)
+    return tot
+
+
+def ncu_tensor_pipe(wl, name):
+    """sm__pipe_tensor_cycles_active (% of peak, ncu) of kernel `name` from the committed capture, or None."""
+    r = _ncu_row(wl, name)
+    try:
+        return float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"].split()[0])
+    except Exception:
+        return None
 
 
 def roofline_for(name, rec, prof, steps, cfg, peaks, wl):
@@ -511,6 +529,7 @@ def roofline_for(name, rec, prof, steps, cfg, peaks, wl):
         step_achieved = N * flops_per_pair(L, D, mc) * steps / (fam_ms / 1e3) / 1e12
         return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(wl, name),
+                "tensor_pipe_active_pct_ncu": ncu_tensor_pipe(wl, name),
                 "flops_per_launch": flops_launch, "ms_per_launch": per_launch_s * 1e3,
                 "step_contractions": {"achieved": step_achieved, "frac": step_achieved / peak,
                                       "ms_per_step": fam_ms / steps},

@@ -58,6 +58,7 @@ struct FwdSmem {
   uint32_t tmem_base;
 };
 
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapM,
                            const __grid_constant__ CUtensorMap mapA, const float* __restrict__ Bias,
@@ -69,7 +70,7 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
   const int stages = g.stages;
   const int nch = (g.N1 + 31) >> 5;
-  if (threadIdx.x == 0) trace_begin(tr);
+  if (TRACE && threadIdx.x == 0) trace_begin(tr);
 
   if (warp == 1) {
     if (lane == 0) {
@@ -91,7 +92,7 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
   const uint32_t tmem_S = tmem + (uint32_t)g.N1;
-  if (threadIdx.x == 0) trace(tr, 1);
+  if (TRACE && threadIdx.x == 0) trace(tr, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp walks the loops,
@@ -127,72 +128,97 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
           __syncwarp();
         }
       }
-      if (lane == 0) trace(tr, 2);
+      if (TRACE && lane == 0) trace(tr, 2);
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issue (whole warp walks the loops,
     {                                                            // one elected lane issues)
       // GEMM1 runs as one MMA per k-step, or two of about equal N (N <= 256 each; the split is a multiple of the
-      // 32-column boxes of M_k; measured: 160 + 144 costs 152 cycles per k-step, 256 + 48 costs 171)
+      // 32-column boxes of M_k; measured: 160 + 144 costs 152 cycles per k-step, 256 + 48 costs 171).
+      // The blocks below keep the uniform-datapath work per MMA small (one elect per block, descriptors advanced by
+      // immediates from a per-stage base, no per-MMA predicates): a lone warp retires a dependent instruction
+      // every ~5 cycles, and at 16 instructions per MMA the issue stream was slower than the MMAs.
       const int np0 = g.N1 <= 256 ? g.N1 : ((g.N1 / 2 + 31) & ~31), np1 = g.N1 - np0;
+      const bool two = np1 > 0;
       const uint32_t idesc_p0 = idesc_tf32(128, np0, false, true);
-      const uint32_t idesc_p1 = idesc_tf32(128, np1 > 0 ? np1 : 16, false, true);
+      const uint32_t idesc_p1 = idesc_tf32(128, two ? np1 : 16, false, true);
       const uint32_t idesc_2 = idesc_tf32(128, g.N2, false, false);
-      int it = 0, tc = 0;
+      const uint32_t ring_base = smem_u32(ring);
+      const uint32_t ring_lo_a = desc_lo_k(ring_base), ring_lo_b = desc_lo_mn(ring_base + 16384, 4096);
+      const uint32_t ring_lo_2 = desc_lo_k(ring_base);
+      const uint32_t stage_lo = (uint32_t)g.stage_bytes >> 4;
+      const uint32_t b1_off = (uint32_t)(np0 >> 5) * (4096u >> 4);
+      const uint32_t tmem_T1 = tmem + (uint32_t)np0;
+      const uint32_t n2_lo = ((uint32_t)g.N2 * 128u) >> 4;
+      const int nkb = g.nkb, D = g.D, kb2 = g.kb2;
+      int s = 0; uint32_t ph = 0;
+      int tc = 0;
       for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tc) {
-        for (int b = 0; b < g.nkb; ++b, ++it) {
-          const int s = it % stages;
-          mbar_wait(&sm->full[s], (it / stages) & 1);
+        for (int b = 0; b < nkb; ++b) {
+          mbar_wait(&sm->full[s], ph);
           tc_fence_after();
-          if (it == 0 && lane == 0) trace(tr, 3);
-          const uint32_t a_base = smem_u32(ring + s * g.stage_bytes);
-          const uint32_t a_lo = desc_lo_k(a_base), b_lo = desc_lo_mn(a_base + 16384, 4096);
-          const uint32_t b1_lo = b_lo + (uint32_t)(np0 >> 5) * (4096u >> 4);
+          if (TRACE && tc == 0 && b == 0 && lane == 0) trace(tr, 3);
+          const uint32_t a_lo = ring_lo_a + (uint32_t)s * stage_lo, b_lo = ring_lo_b + (uint32_t)s * stage_lo;
+          const int left = D - b * 32;
+          const int nks = left >= 32 ? 4 : (left + 7) >> 3;
+          const uint32_t acc0 = b > 0 ? 1u : 0u;
           if (elect_one_sync()) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (b * 32 + ks * 8 < g.D) {
-                const uint32_t acc = (b > 0 || ks > 0) ? 1u : 0u;
-                mma_tf32_ss_lh(tmem, a_lo + ks * kDescStepK, kDescHiK, b_lo + ks * kDescStepMN, kDescHiMN, idesc_p0, acc);
-                if (np1 > 0)
-                  mma_tf32_ss_lh(tmem + np0, a_lo + ks * kDescStepK, kDescHiK, b1_lo + ks * kDescStepMN, kDescHiMN,
-                                 idesc_p1, acc);
+            if (two) {
+              const uint32_t b1_lo = b_lo + b1_off;
+              mma_tf32_ss_lh(tmem, a_lo, kDescHiK, b_lo, kDescHiMN, idesc_p0, acc0);
+              mma_tf32_ss_lh(tmem_T1, a_lo, kDescHiK, b1_lo, kDescHiMN, idesc_p1, acc0);
+              if (nks > 1) {
+                mma_tf32_ss_lh(tmem, a_lo + 1 * kDescStepK, kDescHiK, b_lo + 1 * kDescStepMN, kDescHiMN, idesc_p0, 1u);
+                mma_tf32_ss_lh(tmem_T1, a_lo + 1 * kDescStepK, kDescHiK, b1_lo + 1 * kDescStepMN, kDescHiMN, idesc_p1, 1u);
               }
+              if (nks > 2) {
+                mma_tf32_ss_lh(tmem, a_lo + 2 * kDescStepK, kDescHiK, b_lo + 2 * kDescStepMN, kDescHiMN, idesc_p0, 1u);
+                mma_tf32_ss_lh(tmem_T1, a_lo + 2 * kDescStepK, kDescHiK, b1_lo + 2 * kDescStepMN, kDescHiMN, idesc_p1, 1u);
+              }
+              if (nks > 3) {
+                mma_tf32_ss_lh(tmem, a_lo + 3 * kDescStepK, kDescHiK, b_lo + 3 * kDescStepMN, kDescHiMN, idesc_p0, 1u);
+                mma_tf32_ss_lh(tmem_T1, a_lo + 3 * kDescStepK, kDescHiK, b1_lo + 3 * kDescStepMN, kDescHiMN, idesc_p1, 1u);
+              }
+            } else {
+              mma_tf32_ss_lh(tmem, a_lo, kDescHiK, b_lo, kDescHiMN, idesc_p0, acc0);
+              if (nks > 1) mma_tf32_ss_lh(tmem, a_lo + 1 * kDescStepK, kDescHiK, b_lo + 1 * kDescStepMN, kDescHiMN, idesc_p0, 1u);
+              if (nks > 2) mma_tf32_ss_lh(tmem, a_lo + 2 * kDescStepK, kDescHiK, b_lo + 2 * kDescStepMN, kDescHiMN, idesc_p0, 1u);
+              if (nks > 3) mma_tf32_ss_lh(tmem, a_lo + 3 * kDescStepK, kDescHiK, b_lo + 3 * kDescStepMN, kDescHiMN, idesc_p0, 1u);
             }
             mma_commit(&sm->empty[s]);
-            if (b == g.nkb - 1) mma_commit(&sm->t_full);
+            if (b == nkb - 1) mma_commit(&sm->t_full);
           }
           __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        if (tc == 0 && lane == 0) trace(tr, 4);
-        if (tc > 0) mbar_wait(&sm->s_empty, (tc - 1) & 1);       // the previous tile's S has been read out
-        for (int b0 = 0; b0 < g.nkb; b0 += g.kb2, ++it) {
-          const int s = it % stages;
-          const int nb = min(g.kb2, g.nkb - b0);
-          if (tc == 0 && b0 == g.kb2 && lane == 0) trace(tr, 12);
-          if (tc == 0 && b0 == 2 * g.kb2 && lane == 0) trace(tr, 14);
-          mbar_wait(&sm->full[s], (it / stages) & 1);
-          if (tc == 0 && b0 == g.kb2 && lane == 0) trace(tr, 13);
+        if (TRACE && tc == 0 && lane == 0) trace(tr, 4);
+        if (tc > 0) mbar_wait(&sm->s_empty, (uint32_t)(tc - 1) & 1u);       // the previous tile's S has been read out
+        for (int b0 = 0; b0 < nkb; b0 += kb2) {
+          const int nb = min(kb2, nkb - b0);
+          mbar_wait(&sm->full[s], ph);
+          const uint32_t base2 = ring_lo_2 + (uint32_t)s * stage_lo;
           for (int j = 0; j < nb; ++j) {
             const int b = b0 + j;
-            mbar_wait(&sm->t_ready[b], tc & 1);                  // T columns [32 b, 32 b + 32) are rounded
+            mbar_wait(&sm->t_ready[b], (uint32_t)tc & 1u);                  // T columns [32 b, 32 b + 32) are rounded
             tc_fence_after();
-            const uint32_t b_lo = desc_lo_k(smem_u32(ring + s * g.stage_bytes) + (uint32_t)j * (uint32_t)g.N2 * 128u);
+            const uint32_t b_lo = base2 + (uint32_t)j * n2_lo;
+            const uint32_t a_t = tmem + (uint32_t)(b * 32);
+            const int left = D - b * 32;
+            const int nks = left >= 32 ? 4 : (left + 7) >> 3;
             if (elect_one_sync()) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (b * 32 + ks * 8 < g.D)
-                  mma_tf32_ts_lh(tmem_S, tmem + b * 32 + ks * 8, b_lo + ks * kDescStepK, kDescHiK, idesc_2,
-                                 (b > 0 || ks > 0) ? 1u : 0u);
-              }
+              mma_tf32_ts_lh(tmem_S, a_t, b_lo, kDescHiK, idesc_2, b > 0 ? 1u : 0u);
+              if (nks > 1) mma_tf32_ts_lh(tmem_S, a_t + 8, b_lo + 1 * kDescStepK, kDescHiK, idesc_2, 1u);
+              if (nks > 2) mma_tf32_ts_lh(tmem_S, a_t + 16, b_lo + 2 * kDescStepK, kDescHiK, idesc_2, 1u);
+              if (nks > 3) mma_tf32_ts_lh(tmem_S, a_t + 24, b_lo + 3 * kDescStepK, kDescHiK, idesc_2, 1u);
               if (j == nb - 1) mma_commit(&sm->empty[s]);
-              if (b == g.nkb - 1) mma_commit(&sm->s_full);
+              if (b == nkb - 1) mma_commit(&sm->s_full);
             }
             __syncwarp();
           }
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        if (tc == 0 && lane == 0) trace(tr, 7);
+        if (TRACE && tc == 0 && lane == 0) trace(tr, 7);
       }
     }
     __syncwarp();
@@ -212,7 +238,7 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
       const int n0 = (int)(t / (unsigned)g.mc) * g.P;
       mbar_wait(&sm->t_full, tc & 1);
       tc_fence_after();
-      if (tc == 0 && threadIdx.x == 64) trace(tr, 5);
+      if (TRACE && tc == 0 && threadIdx.x == 64) trace(tr, 5);
       for (int c = set; c < nch; c += 2) {
         float v[32];
         const uint32_t ta = tmem + lane_bits + (uint32_t)(c * 32);
@@ -232,10 +258,10 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->t_ready[c]);
       }
-      if (tc == 0 && threadIdx.x == 64) trace(tr, 6);
+      if (TRACE && tc == 0 && threadIdx.x == 64) trace(tr, 6);
       mbar_wait(&sm->s_full, tc & 1);
       tc_fence_after();
-      if (tc == 0 && threadIdx.x == 64) trace(tr, 8);
+      if (TRACE && tc == 0 && threadIdx.x == 64) trace(tr, 8);
       for (int p = p_lo; p <= p_hi; ++p) {
         const int n = n0 + p;
         const bool active = (p_lane == p) && (n < g.N);
@@ -266,15 +292,15 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->s_empty);
-      if (tc == 0 && threadIdx.x == 64) trace(tr, 9);
+      if (TRACE && tc == 0 && threadIdx.x == 64) trace(tr, 9);
     }
-    if (threadIdx.x == 64) trace(tr, 10);
+    if (TRACE && threadIdx.x == 64) trace(tr, 10);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, g.tmem_cols);
-  if (threadIdx.x == 0) trace_end(tr);
+  if (TRACE && threadIdx.x == 0) trace_end(tr);
 }
 
 }  // namespace
@@ -315,7 +341,9 @@ int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const floa
 
   static bool configured = false;
   if (!configured) {
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MMS_CUDA(cudaFuncSetAttribute(simcross2_fwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
+    MMS_CUDA(cudaFuncSetAttribute(simcross2_fwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   227 * 1024));
     configured = true;
   }
@@ -324,11 +352,12 @@ int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const floa
   TraceBuf tb;
   MMS_TRY(tb.begin(grid));
   { MmsKernelScope ks_(ctx, "simcross2_fwd_fused_kernel");
-    simcross2_fwd_fused_kernel<<<grid, kThreads, smem, ctx->stream>>>(mapQ, mapM, mapA, B, S, g, tb.dev); }
+    if (tb.dev) simcross2_fwd_fused_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(mapQ, mapM, mapA, B, S, g, tb.dev);
+    else simcross2_fwd_fused_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(mapQ, mapM, mapA, B, S, g, nullptr); }
   MMS_LAUNCH_CHECK();
   static const char* const names[kTraceSlots] = {"entry", "setup", "tma_issued", "first_full", "g1_issued", "t_full",
                                                  "rounded", "g2_issued", "s_full", "epi0_done", "epi_done", "exit",
-                                                 "g2_st1_prewait", "g2_st1_full", "g2_st2_prewait", nullptr,
+                                                 nullptr, nullptr, nullptr, nullptr,
                                                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char what[96];
   snprintf(what, sizeof(what), "fwd N %d L %dx%d D %d mc %d P %d tiles %u stages %d", N, Lq, La, D, mc, g.P,

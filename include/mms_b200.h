@@ -204,6 +204,29 @@ int mms_dot_f64(mms_handle_t h, const double* data, const double* diff, long lon
 int mms_scale_f32(mms_handle_t h, float* x, long long count, float alpha);
 int mms_scale_f64(mms_handle_t h, double* x, long long count, double alpha);
 
+/* ------------------------------------------------------------ optimizer step ---
+ * mms_adadelta_update_* has the argument meaning of the reference's
+ * adadelta_update_gpu(N, g, h, h2, momentum, delta, local_rate) (src/caffe/solvers/adadelta_solver.cu:6-26,
+ * called from AdaDeltaSolver::ComputeUpdateValue, adadelta_solver.cpp:96-101): g (the blob's diff) becomes the
+ * update, hist_g / hist_u are the two history blobs of the parameter.
+ * mms_adadelta_step_* is the whole SGDSolver::ApplyUpdate of one learnable blob (sgd_solver.cpp:102-116) in ONE pass:
+ *   diff *= grad_scale              Normalize (:118-141) and the 1/solver_count of P2PSync (parallel.cpp:377)
+ *   diff += local_decay * data      Regularize, L2 (:181-185); local_decay = weight_decay * decay_mult
+ *   AdaDelta update of diff         as above; local_rate = base_lr * lr_mult
+ *   data -= diff                    Net::Update -> Blob::Update
+ *   diff = 0 if clear_diff          Net::ClearParamDiffs of the next iteration (solver.cpp:203)
+ * data may be NULL (then only the first three). */
+int mms_adadelta_update_f32(mms_handle_t h, float* g, float* hist_g, float* hist_u, long long count,
+                            float momentum, float delta, float local_rate);
+int mms_adadelta_update_f64(mms_handle_t h, double* g, double* hist_g, double* hist_u, long long count,
+                            double momentum, double delta, double local_rate);
+int mms_adadelta_step_f32(mms_handle_t h, float* data, float* diff, float* hist_g, float* hist_u,
+                          long long count, float grad_scale, float local_decay, float momentum,
+                          float delta, float local_rate, int clear_diff);
+int mms_adadelta_step_f64(mms_handle_t h, double* data, double* diff, double* hist_g, double* hist_u,
+                          long long count, double grad_scale, double local_decay, double momentum,
+                          double delta, double local_rate, int clear_diff);
+
 /* ------------------------------------------------------ candidate scoring ---
  * Reranking with the SimMatrix bilinear form (BASELINE config "1k queries x 1M candidates"):
  * scores[i,j] = q_i^T W c_j.  Q (Nq,K1), C (Nc,K2), W (K1,K2), scores (Nq,Nc) row-major.

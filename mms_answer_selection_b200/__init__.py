@@ -15,6 +15,7 @@ from .blob import Blob  # noqa: F401
 from .layers import (EmbedLayer, FMLayer, Layer, LayerParameter, PairRankLossLayer,  # noqa: F401
                      SimCrossLayer, SimMatrixLayer, create_layer)
 from .net import MMSNet  # noqa: F401
+from .solver import AdaDeltaSolver  # noqa: F401
 
 __all__ = ["MMSError", "lib", "lib_path", "Blob", "Layer", "LayerParameter", "EmbedLayer",
-           "SimCrossLayer", "SimMatrixLayer", "PairRankLossLayer", "FMLayer", "create_layer", "MMSNet"]
+           "SimCrossLayer", "SimMatrixLayer", "PairRankLossLayer", "FMLayer", "create_layer", "MMSNet", "AdaDeltaSolver"]

@@ -42,6 +42,8 @@ def _typed(real):
         "mms_fm_backward": [p, p, p, p, p, c_int, c_int, c_int, c_int],
         "mms_dot": [p, p, p, c_ll, p],
         "mms_scale": [p, p, c_ll, real],
+        "mms_adadelta_update": [p, p, p, p, c_ll, real, real, real],
+        "mms_adadelta_step": [p, p, p, p, p, c_ll, real, real, real, real, real, c_int],
     }
 
 

@@ -287,6 +287,17 @@ int mms_check_faults(mms_handle_t h) {
   }                                                                                                \
   int mms_scale_##SUF(mms_handle_t h, T* x, long long count, T alpha) {                            \
     H; return mms_scale_impl<T>(h, x, count, alpha);                                               \
+  }                                                                                                \
+  int mms_adadelta_step_##SUF(mms_handle_t h, T* data, T* diff, T* hist_g, T* hist_u,              \
+                              long long count, T grad_scale, T local_decay, T momentum, T delta,   \
+                              T local_rate, int clear_diff) {                                      \
+    H; return mms_adadelta_step_impl<T>(h, data, diff, hist_g, hist_u, count, grad_scale,          \
+                                        local_decay, momentum, delta, local_rate, clear_diff);     \
+  }                                                                                                \
+  int mms_adadelta_update_##SUF(mms_handle_t h, T* g, T* hist_g, T* hist_u, long long count,       \
+                                T momentum, T delta, T local_rate) {                               \
+    H; return mms_adadelta_step_impl<T>(h, nullptr, g, hist_g, hist_u, count, T(1), T(0), momentum,\
+                                        delta, local_rate, 0);                                     \
   }
 
 MMS_DEFINE_TYPED(float, f32)

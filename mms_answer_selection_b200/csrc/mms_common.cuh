@@ -157,6 +157,9 @@ template <typename T>
 int mms_dot_impl(mms_context*, const T* x, const T* y, long long n, T* out);
 template <typename T>
 int mms_scale_impl(mms_context*, T* x, long long n, T alpha);
+template <typename T>
+int mms_adadelta_step_impl(mms_context*, T* data, T* diff, T* hist_g, T* hist_u, long long n, T grad_scale, T local_decay,
+                           T momentum, T delta, T local_rate, int clear_diff);
 
 int mms_rerank_scores_impl(mms_context*, const float* Q, const float* C, const float* W, float* QW,
                            float* scores, int Nq, long long Nc, int K1, int K2);

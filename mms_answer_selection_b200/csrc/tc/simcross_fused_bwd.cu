@@ -82,9 +82,11 @@ struct BwdSmem {
   uint32_t tmem_base;
 };
 
-// one full 32-byte sector per thread and instruction (row-per-thread stores of the U export)
+// one full 32-byte sector per thread and instruction (row-per-thread stores of the U export); streaming (evict-first)
+// like every store of these kernels: U, dq and da are written once and read by a LATER kernel, and must not push the
+// M_k / X lines that the TMA ring keeps re-reading out of L2
 __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+  asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
@@ -420,7 +422,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
             if (g.u_blocked) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < 16 || wide) urow[(size_t)(c0 + i) * 32] = v[i];
+                if (i < 16 || wide) __stcs(urow + (size_t)(c0 + i) * 32, v[i]);
             } else {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -504,7 +506,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
               if (g.vec_out && i * 4 + 4 <= ncols) {
                 const float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 if (g.ksplit > 1) atomicAdd(reinterpret_cast<float4*>(dst + 4 * i), o);
-                else *reinterpret_cast<float4*>(dst + 4 * i) = o;
+                else __stcs(reinterpret_cast<float4*>(dst + 4 * i), o);
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -520,16 +522,16 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
           for (int i = 0; i < 4; ++i) {
             if (i * 8 + 8 <= ncols) st_global_v8(dst + i * 8, v + i * 8);
             else if (i * 8 + 4 <= ncols)
-              *reinterpret_cast<float4*>(dst + i * 8) = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+              __stcs(reinterpret_cast<float4*>(dst + i * 8), make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]));
           }
         } else {
-          if (ncols >= 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          if (ncols >= 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c0 = 4 + i * 8;
             if (c0 + 8 <= ncols) st_global_v8(dst + c0, v + c0);
             else if (c0 + 4 <= ncols)
-              *reinterpret_cast<float4*>(dst + c0) = make_float4(v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3]);
+              __stcs(reinterpret_cast<float4*>(dst + c0), make_float4(v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3]));
           }
         }
       }
@@ -566,14 +568,14 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 if (e0 + 4 * i < g.Lk) {
-                  const float4 x = __ldg(reinterpret_cast<const float4*>(src + e0 + 4 * i));
+                  const float4 x = __ldcs(reinterpret_cast<const float4*>(src + e0 + 4 * i));
                   v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
                 }
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 64; ++i)
-                if (e0 + i < g.Lk) v[i] = __ldg(src + (size_t)(e0 + i) * (DA ? g.La : 1));
+                if (e0 + i < g.Lk) v[i] = __ldcs(src + (size_t)(e0 + i) * (DA ? g.La : 1));
             }
           }
           if (e0 == 0 && itk > 0) mbar_wait(&sm->g_empty, (uint32_t)(itk - 1) & 1u);   // every GEMM-A of the previous measure has read Gblk

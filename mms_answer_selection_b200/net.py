@@ -153,6 +153,32 @@ class MMSNet(object):
     # (the reference has the same problem in the small: 2*N*mc host BLAS calls).  Recording
     # ClearParamDiffs + Forward + Backward once and replaying the graph removes the host from
     # the loop.  Blob storage must not be re-allocated between capture and replay.
+    def capture_train_step(self, solver, with_loss=True):
+        """Records a whole solver iteration: Forward + Backward + ``solver.ApplyUpdate(clear_diffs=True)`` -- the
+        fused optimizer launch also zeroes every diff for the next iteration, so the step contains no separate
+        ClearParamDiffs pass (Solver::Step, solver.cpp:195-260).  Diffs must be zero when the first replay starts."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        self.sim.defer_loss_ = True
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.ForwardBackwardConcurrent(with_loss, clear_diffs=False)
+                    solver.ApplyUpdate(clear_diffs=True)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.ForwardBackwardConcurrent(with_loss, clear_diffs=False)
+                solver.ApplyUpdate(clear_diffs=True)
+        finally:
+            self.sim.defer_loss_ = False
+        self._graph_train = graph
+        return graph
+
+    def replay_train_step(self):
+        self._graph_train.replay()
+
     def capture(self, with_loss=True, clear_diffs=True, host_inputs=None):
         """Records one step.  With `host_inputs=(host_q, host_a)` (pinned tensors) a second graph is recorded
         that also contains the H2D copies of the two id tensors and the D2H copy of the loss scalar into a pinned

@@ -157,3 +157,15 @@ def fm_backward(x, dy, bias_term=True, prop0=True):
     db = np.zeros(1, dtype=dt) if bias_term else None
     _call("mmso_fm_backward", dt, _ptr(x_c), _ptr(g), _ptr(dx), _ptr(db), N, C, Dm, int(prop0))
     return dx, db
+
+
+def adadelta_step(data, diff, hist_g, hist_u, grad_scale=1.0, local_decay=0.0, momentum=0.95, delta=5e-7,
+                  local_rate=1.0):
+    """In place on contiguous arrays of one dtype (data may be None: the bare adadelta_update)."""
+    dtype = diff.dtype
+    _, real = _suffix(dtype)
+    for x in (data, diff, hist_g, hist_u):
+        assert x is None or (x.dtype == dtype and x.flags["C_CONTIGUOUS"])
+    _call("mmso_adadelta_step", dtype, _ptr(data), _ptr(diff), _ptr(hist_g), _ptr(hist_u),
+          ctypes.c_longlong(diff.size), real(grad_scale), real(local_decay), real(momentum), real(delta),
+          real(local_rate))

@@ -23,12 +23,16 @@
 
 #define REAL float
 #define FN(name) MMS_CAT(name, _f32)
+#define MMSO_POW(x, y) powf(x, y)
 #include "mms_oracle_impl.h"
 #undef REAL
 #undef FN
+#undef MMSO_POW
 
 #define REAL double
 #define FN(name) MMS_CAT(name, _f64)
+#define MMSO_POW(x, y) pow(x, y)
 #include "mms_oracle_impl.h"
 #undef REAL
 #undef FN
+#undef MMSO_POW

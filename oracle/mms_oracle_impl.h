@@ -375,3 +375,37 @@ int FN(mmso_fm_backward)(const REAL* x, const REAL* dy, REAL* dx, REAL* dbias,
   }
   return 0;
 }
+
+/* One AdaDelta step of one learnable blob, in the order SGDSolver::ApplyUpdate makes its passes
+ * (src/caffe/solvers/sgd_solver.cpp:102-116):
+ *   Normalize      :118-141 (caffe_scal by 1/iter_size) -- here the general gradient scale, which also carries the
+ *                  1/solver_count of P2PSync::on_gradients_ready (src/caffe/parallel.cpp:377)
+ *   Regularize     :143-161, L2 only: diff += local_decay * data   (local_decay = weight_decay * decay_mult)
+ *   ComputeUpdateValue  src/caffe/solvers/adadelta_solver.cpp:33-94 (CPU branch), pass by pass: powx 2, axpby into the
+ *                  gradient history, (delta + update history) / (delta + gradient history), powx 0.5, mul, powx 2,
+ *                  axpby into the update history, scale by local_rate (= base_lr * lr_mult)
+ *   Net::Update    -> Blob::Update (src/caffe/blob.cpp): data -= diff
+ * diff is left holding the applied update, as in the reference.  data == NULL skips Net::Update (the bare
+ * adadelta_update of adadelta_solver.cu:6-26).  caffe_powx is pow() per element (mkl_alternate.hpp vsPowx). */
+int FN(mmso_adadelta_step)(REAL* data, REAL* diff, REAL* hist_g, REAL* hist_u, long long n, REAL grad_scale,
+                           REAL local_decay, REAL momentum, REAL delta, REAL local_rate) {
+  for (long long i = 0; i < n; ++i) {
+    REAL g = diff[i];
+    if (grad_scale != (REAL)1) g *= grad_scale;
+    if (local_decay != (REAL)0 && data) g += local_decay * data[i];
+    REAL upd = MMSO_POW(g, (REAL)2);
+    hist_g[i] = ((REAL)1 - momentum) * upd + momentum * hist_g[i];
+    REAL tmp = delta;
+    upd = tmp + hist_u[i];
+    tmp = tmp + hist_g[i];
+    upd = upd / tmp;
+    upd = MMSO_POW(upd, (REAL)0.5);
+    g = g * upd;
+    upd = MMSO_POW(g, (REAL)2);
+    hist_u[i] = ((REAL)1 - momentum) * upd + momentum * hist_u[i];
+    g = local_rate * g;
+    diff[i] = g;
+    if (data) data[i] = data[i] - g;
+  }
+  return 0;
+}

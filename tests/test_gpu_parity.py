@@ -516,6 +516,72 @@ def test_simcross_backward_blocked_export_ragged(shape):
     assert (ba.diff.double() - da_ref).abs().max().item() <= TOL_TF32 * da_ref.abs().max().item()
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,decay,scale,clear", [(1000, 5e-4, 1.0, 0), (4099, 0.0, 0.125, 1), (18_000_900, 5e-4, 0.5, 1)])
+def test_adadelta_step_vs_oracle(dtype, n, decay, scale, clear):
+    """mms_adadelta_step_* (scale + L2 decay + AdaDelta + Net::Update + ClearParamDiffs in one pass) against the
+    oracle's pass-by-pass restatement of the reference solver, three iterations; n = 18 000 900 is the size of the
+    V x D embedding table of the path."""
+    import ctypes
+    if n > 10**7 and dtype == np.float64:
+        pytest.skip("the table-sized case runs in float32 only")
+    rng = np.random.default_rng(n % 1000)
+    h = _lib.Handle()
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    real = ctypes.c_float if dtype == np.float32 else ctypes.c_double
+    fn = _lib.lib().mms_adadelta_step_f32 if dtype == np.float32 else _lib.lib().mms_adadelta_step_f64
+    w = rng.uniform(-0.08, 0.08, n).astype(dtype); hg = np.zeros(n, dtype); hu = np.zeros(n, dtype)
+    tw, thg, thu = (torch.from_numpy(x.copy()).cuda() for x in (w, hg, hu))
+    for it in range(3):
+        g = rng.normal(0, 1e-3, n).astype(dtype)
+        tg = torch.from_numpy(g.copy()).cuda()
+        _lib.check(fn(h.ptr, *(ctypes.c_void_p(t.data_ptr()) for t in (tw, tg, thg, thu)), n, real(scale),
+                      real(decay), real(0.95), real(5e-7), real(1.0), clear))
+        cport.adadelta_step(w, g, hg, hu, grad_scale=scale, local_decay=decay, momentum=0.95, delta=5e-7,
+                            local_rate=1.0)
+        tol = 2e-6 if dtype == np.float32 else 1e-12
+        assert scaled_err(tw.cpu().numpy(), w) <= tol
+        assert scaled_err(thg.cpu().numpy(), hg) <= tol and scaled_err(thu.cpu().numpy(), hu) <= tol
+        if clear:
+            assert not tg.any().item()
+        else:
+            assert scaled_err(tg.cpu().numpy(), g) <= tol
+    assert tdt == tw.dtype
+
+
+def test_adadelta_solver_on_the_net():
+    """AdaDeltaSolver.ApplyUpdate on MMSNet's learnable blobs (multipliers of do_trec_qa_clean.py:461-468) against the
+    oracle step applied blob by blob, two iterations, gradients from a real ForwardBackward."""
+    N, L, D, mc, V = 12, 40, 52, 2, 400
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    net = mms.MMSNet(N, L, D, mc, V)
+    net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
+    net.set_upstream_gradient(d["dS"])
+    params = net.params()                                        # W, b (shared Embed), M, B
+    lr, dec = [1.0, 2.0, 1.0, 1.0], [0.0, 0.0, 1.0, 1.0]
+    sol = mms.AdaDeltaSolver(params, lr_mult=lr, decay_mult=dec)
+    ref_w = [p.cpu_data().astype(np.float32).copy() for p in params]
+    ref_h = [[np.zeros_like(x), np.zeros_like(x)] for x in ref_w]
+    for it in range(2):
+        net.ClearParamDiffs(); net.ForwardBackward()
+        grads = [p.cpu_diff().astype(np.float32).copy() for p in params]
+        sol.ApplyUpdate(grad_scale=0.5, clear_diffs=(it == 1))
+        torch.cuda.synchronize()
+        for i, p in enumerate(params):
+            g = np.ascontiguousarray(grads[i].reshape(-1)); w = ref_w[i].reshape(-1)
+            cport.adadelta_step(w, g, ref_h[i][0].reshape(-1), ref_h[i][1].reshape(-1), grad_scale=0.5,
+                                local_decay=5e-4 * dec[i], momentum=0.95, delta=5e-7, local_rate=1.0 * lr[i])
+            assert scaled_err(p.cpu_data(), ref_w[i]) <= 2e-6, (it, i)
+            if it == 1:
+                assert not p.cpu_diff().any()
+            else:
+                assert scaled_err(p.cpu_diff().reshape(-1), g) <= 2e-6
+        # the next iteration's forward uses the updated weights: keep the reference copies in sync bit for bit
+        ref_w = [p.cpu_data().astype(np.float32).copy() for p in params]
+        for i in range(len(params)):
+            ref_h[i][0] = sol.history[i].cpu().numpy().copy(); ref_h[i][1] = sol.history[len(params) + i].cpu().numpy().copy()
+
+
 def test_rerank_scores_vs_simmatrix_form():
     """candidate scoring: scores[i,j] = q_i^T W c_j, checked against the SimMatrix oracle."""
     import ctypes

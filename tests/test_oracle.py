@@ -263,3 +263,50 @@ def test_pairrankloss_label_table():
                           (-1, 0.0, 2.0, 0.0 + 2 * 2.0), (-1, 2.0, 0.0, 3.0 + 4.0)]:
         loss, _, _ = cport.pairrankloss_forward(np.array([a]), np.array([b]), np.array([float(y)]), 1.0)
         assert loss == pytest.approx(want)
+
+
+# ---------------------------------------------------------------- AdaDelta step
+def _adadelta_numpy(w, g, h, h2, scale, decay, mom, delta, rate):
+    """The update as the reference's GPU kernel states it (adadelta_solver.cu:7-16), in float64, with the passes
+    SGDSolver::ApplyUpdate makes around it."""
+    g = g * scale + decay * w
+    h = mom * h + (1 - mom) * g * g
+    g = g * np.sqrt((h2 + delta) / (h + delta))
+    h2 = mom * h2 + (1 - mom) * g * g
+    g = rate * g
+    return w - g, g, h, h2
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_adadelta_oracle_matches_the_kernel_formula(dtype):
+    """The oracle follows the CPU branch pass by pass (adadelta_solver.cpp:33-94); the reference's GPU branch is the
+    closed form above -- the two must agree (the reference's own test_gradient_based_solver.cpp checks its solvers
+    against such a re-derivation, not against golden vectors)."""
+    rng = np.random.default_rng(3)
+    n = 1000
+    w = rng.uniform(-0.1, 0.1, n)
+    hist = [np.zeros(n), np.zeros(n)]
+    wo = w.astype(dtype); ho = [np.zeros(n, dtype), np.zeros(n, dtype)]
+    for step in range(4):
+        g = rng.normal(0, 1e-2, n)
+        w, upd, hist[0], hist[1] = _adadelta_numpy(w, g, hist[0], hist[1], 0.5, 5e-4, 0.95, 5e-7, 1.0)
+        go = g.astype(dtype)
+        cport.adadelta_step(wo, go, ho[0], ho[1], grad_scale=0.5, local_decay=5e-4, momentum=0.95, delta=5e-7,
+                            local_rate=1.0)
+        tol = 1e-5 if dtype == np.float32 else 1e-12
+        assert scaled_err(go, upd) <= tol and scaled_err(wo, w) <= tol
+        assert scaled_err(ho[0], hist[0]) <= tol and scaled_err(ho[1], hist[1]) <= tol
+
+
+def test_adadelta_oracle_known_answer():
+    """First iteration from zero histories, g = 1, no decay: h = 0.05, update = sqrt(delta / (0.05 + delta)),
+    h2 = 0.05 * update^2 (hand-computed)."""
+    g = np.ones(3); w = np.zeros(3); h = np.zeros(3); h2 = np.zeros(3)
+    cport.adadelta_step(w, g, h, h2, momentum=0.95, delta=5e-7, local_rate=2.0)
+    u = np.sqrt(5e-7 / (0.05 + 5e-7))
+    assert np.allclose(h, 0.05, rtol=1e-12) and np.allclose(h2, 0.05 * u * u, rtol=1e-12)
+    assert np.allclose(g, 2.0 * u, rtol=1e-12) and np.allclose(w, -2.0 * u, rtol=1e-12)
+    # data = None: the bare adadelta_update (no Net::Update, no decay)
+    g2 = np.ones(3); h = np.zeros(3); h2 = np.zeros(3)
+    cport.adadelta_step(None, g2, h, h2, local_decay=1.0, momentum=0.95, delta=5e-7, local_rate=2.0)
+    assert np.allclose(g2, 2.0 * u, rtol=1e-12)

@@ -65,7 +65,7 @@ __device__ __forceinline__ void trace(long long* tr, int slot) {
   tr[(size_t)blockIdx.x * 8 + slot] = (long long)t;
 }
 
-__device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry& q, unsigned t, int sps) {
+__device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry& q, unsigned t, int sps, int bm = kBM) {
   Tile tl;
   int n_tile, m_tile;
   if (q.m_fast) { m_tile = t % q.m_tiles; t /= q.m_tiles; n_tile = t % q.n_tiles; t /= q.n_tiles; }
@@ -73,7 +73,7 @@ __device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry&
   const int split = t % g.ksplit;
   const int z = t / g.ksplit;
   tl.z1 = z / g.nb2; tl.z2 = z % g.nb2;
-  tl.m0 = m_tile * kBM; tl.n0 = n_tile * q.BN;
+  tl.m0 = m_tile * bm; tl.n0 = n_tile * q.BN;
   const int total_stages = g.nseg * sps;
   const int per_split = (total_stages + g.ksplit - 1) / g.ksplit;
   tl.ibeg = split * per_split;
@@ -333,6 +333,203 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (threadIdx.x == 0) trace(tr, 7);
 }
 
+// ---- CTA-pair variant: 256 x BN tiles on two SMs (tcgen05 cta_group::2) -----------------------------------
+// Same contract and the same roles as tc_gemm_tma_kernel, launched as clusters of two CTAs.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile (16 KB + BN * 64 B per k-block instead of 16 KB + BN * 128 B), keeps its
+// 128 x BN half of the accumulator in its own TMEM and stores it; the leader CTA (rank 0) issues one M = 256 MMA
+// per k-step for both.  What it buys: the 128 x 256 tile of the single-CTA kernel needs 94 B of TMA ingest per
+// tensor-pipe cycle per SM and runs at the ~55-60 B/clk the SMs sustain (candidate scoring: 447 TFLOP/s); the pair
+// needs 64.
+//   full[s]      lives in the leader; both producers arrive on it (expect_tx of their own bytes) and both CTAs'
+//                TMA loads complete_tx on it
+//   empty[s], acc_full[b]   per CTA; the leader's tcgen05.commit multicasts its arrival to both
+//   acc_empty[b] lives in the leader; the epilogue warps of both CTAs arrive on it
+constexpr int kBM2 = 256;
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_gemm_tma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const TcGemmArgs g, const Geometry q) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int BN = q.BN, stages = q.stages, BNh = BN >> 1;
+  const int stage_bytes = 16384 + q.b_bytes;                     // q.b_bytes: this CTA's half of the B tile
+  float* epi = reinterpret_cast<float*>(ring + stages * stage_bytes);
+  Smem* sm = reinterpret_cast<Smem*>(ring + stages * stage_bytes + kEpiBytes);
+
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int sps = (g.K + kBK - 1) / kBK;
+  const unsigned cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) { mbar_init(&sm->full[s], 2); mbar_init(&sm->empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], 2 * kEpiWarps); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta(&sm->tmem_base, q.tmem_cols);
+    tmem_relinquish_2cta();
+  } else if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                            // the peer's barriers exist before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    const uint32_t tx_bytes = (uint32_t)stage_bytes;
+    const int b_blocks = (BNh + 31) >> 5;
+    int it = 0;
+    for (unsigned t = cluster_id; t < q.total_tiles; t += n_clusters) {
+      const Tile tl = decode_tile(g, q, t, sps, kBM2);
+      const int az1 = tl.z1 * q.a_z1, az2 = tl.z2 * q.a_z2;
+      const int bz1 = tl.z1 * q.b_z1, bz2 = tl.z2 * q.b_z2;
+      const int m0 = tl.m0 + (int)rank * kBM, n0 = tl.n0 + (int)rank * BNh;
+      for (int i = 0; i < tl.nk; ++i, ++it) {
+        const int s = it % stages;
+        const int gi = tl.ibeg + i;
+        const int seg = gi / sps;
+        const int k0 = (gi - seg * sps) * kBK;
+        if (it >= stages) mbar_wait(&sm->empty[s], ((it / stages) - 1) & 1);
+        uint8_t* a_dst = ring + s * stage_bytes;
+        uint8_t* b_dst = a_dst + 16384;
+        const uint32_t full_leader = mapa_shared(smem_u32(&sm->full[s]), 0);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx_cluster(full_leader, tx_bytes);
+          if (!A_MN) {
+            tma_load_5d_2cta(a_dst, &mapA, full_leader, k0, m0, az2, az1, seg * q.a_seg);
+          } else {
+#pragma unroll
+            for (int b = 0; b < kBM / 32; ++b)
+              tma_load_5d_2cta(a_dst + b * 4096, &mapA, full_leader, m0 + 32 * b, k0, az2, az1, seg * q.a_seg);
+          }
+          if (!B_MN) {
+            tma_load_5d_2cta(b_dst, &mapB, full_leader, k0, n0, bz2, bz1, seg * q.b_seg);
+          } else {
+            for (int b = 0; b < b_blocks; ++b)
+              tma_load_5d_2cta(b_dst + b * 4096, &mapB, full_leader, n0 + 32 * b, k0, bz2, bz1, seg * q.b_seg);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issue: the leader, for both CTAs
+    if (leader) {
+      const uint32_t idesc = idesc_tf32(kBM2, BN, A_MN, B_MN);
+      const uint32_t ring_base = smem_u32(ring);
+      const uint32_t ring_a = A_MN ? desc_lo_mn(ring_base, 4096) : desc_lo_k(ring_base);
+      const uint32_t ring_b = B_MN ? desc_lo_mn(ring_base + 16384, 4096) : desc_lo_k(ring_base + 16384);
+      const uint32_t stage_lo = (uint32_t)stage_bytes >> 4;
+      constexpr uint32_t a_step = A_MN ? kDescStepMN : kDescStepK, a_hi = A_MN ? kDescHiMN : kDescHiK;
+      constexpr uint32_t b_step = B_MN ? kDescStepMN : kDescStepK, b_hi = B_MN ? kDescHiMN : kDescHiK;
+      int it = 0, tcount = 0;
+      for (unsigned t = cluster_id; t < q.total_tiles; t += n_clusters, ++tcount) {
+        const Tile tl = decode_tile(g, q, t, sps, kBM2);
+        const int buf = tcount & 1;
+        if (tcount >= 2) mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem + buf * BN;
+        for (int i = 0; i < tl.nk; ++i, ++it) {
+          const int s = it % stages;
+          mbar_wait(&sm->full[s], (it / stages) & 1);
+          tc_fence_after();
+          const uint32_t a_lo = ring_a + (uint32_t)s * stage_lo, b_lo = ring_b + (uint32_t)s * stage_lo;
+          if (elect_one_sync()) {
+            mma_tf32_ss_lh_2cta(acc, a_lo, a_hi, b_lo, b_hi, idesc, i > 0 ? 1u : 0u);
+            mma_tf32_ss_lh_2cta(acc, a_lo + 1 * a_step, a_hi, b_lo + 1 * b_step, b_hi, idesc, 1u);
+            mma_tf32_ss_lh_2cta(acc, a_lo + 2 * a_step, a_hi, b_lo + 2 * b_step, b_hi, idesc, 1u);
+            mma_tf32_ss_lh_2cta(acc, a_lo + 3 * a_step, a_hi, b_lo + 3 * b_step, b_hi, idesc, 1u);
+            mma_commit_2cta(&sm->empty[s]);
+            if (i == tl.nk - 1) mma_commit_2cta(&sm->acc_full[buf]);
+          }
+          __syncwarp();
+        }
+        if (tl.nk == 0) {
+          if (elect_one_sync()) mma_commit_2cta(&sm->acc_full[buf]);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: each CTA its own 128 rows
+    const int quarter = warp & 3;
+    int fast_kind = -1;
+    if (g.mode == TC_STORE) fast_kind = (g.c_add && g.round_out) ? -1 : g.c_add ? 2 : g.round_out ? 1 : 0;
+    else if (!g.c_add && !g.round_out) fast_kind = g.mode == TC_ATOMIC ? 3 : 4;
+    int tcount = 0;
+    for (unsigned t = cluster_id; t < q.total_tiles; t += n_clusters, ++tcount) {
+      const Tile tl = decode_tile(g, q, t, sps, kBM2);
+      const int m0 = tl.m0 + (int)rank * kBM;
+      const int buf = tcount & 1;
+      float* C = g.C + tl.z1 * g.sC1 + tl.z2 * g.sC2;
+      const float* Cadd = g.c_add ? g.c_add + tl.z1 * g.s_add1 + tl.z2 * g.s_add2 : nullptr;
+      mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const bool c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (g.ldc % 4 == 0) && (tl.n0 % 4 == 0);
+      const bool add_vec = Cadd && ((reinterpret_cast<uintptr_t>(Cadd) & 15) == 0) && (g.ld_add % 4 == 0);
+      const int row_tm = m0 + quarter * 32 + lane;
+      const float rs = (g.out_rowscale && row_tm < g.M) ? __ldg(g.out_rowscale + row_tm) : 1.f;
+      const uint32_t acc = tmem + buf * BN + ((uint32_t)(quarter * 32) << 16);
+      const int ncols = min(BN, g.N - tl.n0);
+      float* stage = epi + quarter * (32 * kEpiLd);
+      const int warp_rows = min(32, g.M - (m0 + quarter * 32));
+      for (int c0 = 0; warp_rows > 0 && c0 < ncols; c0 += 32) {
+        float v[32];
+        if (tl.nk > 0) {
+          if (c0 + 16 < BN) tmem_ld32(acc + c0, v);
+          else tmem_ld16(acc + c0, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4)
+          *reinterpret_cast<float4*>(stage + lane * kEpiLd + i4 * 4) =
+              make_float4(v[i4 * 4] * rs, v[i4 * 4 + 1] * rs, v[i4 * 4 + 2] * rs, v[i4 * 4 + 3] * rs);
+        __syncwarp();
+        const int cc = (lane & 7) * 4;
+        const int r0 = lane >> 3;
+        const int n = tl.n0 + c0 + cc;
+        const int nvalid = (c0 + cc < BN) ? max(0, min(4, g.N - n)) : 0;
+        const int rows_left = warp_rows - r0;
+        const long long row0 = m0 + quarter * 32 + r0;
+        float* p = C + row0 * g.ldc + n;
+        const float* ap = Cadd ? Cadd + row0 * g.ld_add + n : nullptr;
+        const float* sp = stage + r0 * kEpiLd + cc;
+        const long long pstep = 4 * g.ldc, astep = 4 * g.ld_add;
+        if (nvalid == 4 && c_vec && fast_kind >= 0) {
+          switch (fast_kind) {
+            case 0: epi_store_vec<TC_STORE, false, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            case 1: epi_store_vec<TC_STORE, true, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            case 2: epi_store_vec<TC_STORE, false, true>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            case 3: epi_store_vec<TC_ATOMIC, false, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+            default: epi_store_vec<TC_ACCUM, false, false>(sp, p, pstep, ap, astep, add_vec, rows_left); break;
+          }
+        } else if (nvalid > 0 && rows_left > 0) {
+          epi_store_scalar(sp, p, pstep, ap, astep, g.round_out != 0, rows_left, nvalid, g.mode);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&sm->acc_empty[buf]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                            // no CTA frees TMEM or exits while its peer still works
+  if (warp == 1) tmem_dealloc_2cta(tmem, q.tmem_cols);
+}
+
 // ---- tf32 rounding / repacking pass --------------------------------------------------------
 struct RoundJobs {
   RoundJob j[4];
@@ -485,6 +682,58 @@ int mms_tf32_round(mms_context* ctx, const RoundJob* jobs, int njobs) {
   return 0;
 }
 
+namespace {
+
+// The CTA-pair kernel pays when the tile is wide (the B half it saves is large) and there are enough 256-row tiles
+// to fill the 74 pairs; otherwise the single-CTA kernel's smaller tiles spread better.
+int gemm_tma_pair(mms_context* ctx, const TcGemmArgs& a) {
+  static const bool disabled = getenv("MMS_NO_2CTA") != nullptr;
+  if (disabled || a.M <= 128 || a.N < 256) return MMS_E_UNSUPPORTED;
+  Geometry q;
+  const int BN = 256;
+  q.BN = BN;
+  q.n_tiles = mms_ceil_div(a.N, BN);
+  q.m_tiles = mms_ceil_div(a.M, kBM2);
+  const long long total = (long long)q.n_tiles * q.m_tiles * a.ksplit * a.nb1 * a.nb2;
+  const int pairs = ctx->sm_count / 2;
+  // rows wasted by the 256-row tiles vs the 128-row tiles, and enough tiles for every pair
+  if (total < pairs || total > 0x7fffffffLL) return MMS_E_UNSUPPORTED;
+  if ((long long)q.m_tiles * kBM2 > (long long)mms_ceil_div(a.M, kBM) * kBM + 64) return MMS_E_UNSUPPORTED;
+  q.m_fast = (q.m_tiles < q.n_tiles && q.m_tiles <= pairs) ? 1 : 0;
+  q.b_bytes = a.b_mn ? mms_ceil_div(BN / 2, 32) * 4096 : (BN / 2) * 128;
+  const int stage_bytes = 16384 + q.b_bytes;
+  int stages = 8;
+  while (stages > 2 && (size_t)stages * stage_bytes + kEpiBytes + sizeof(Smem) + 1024 > 220 * 1024) --stages;
+  if (stages > kMaxStages) stages = kMaxStages;
+  q.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + kEpiBytes + sizeof(Smem) + 1024;
+  q.total_tiles = (unsigned)total;
+  q.tmem_cols = umma::tmem_cols_pow2(2 * BN);
+  q.a_z1 = a.sA1 != 0; q.a_z2 = a.sA2 != 0; q.a_seg = a.segA != 0;
+  q.b_z1 = a.sB1 != 0; q.b_z2 = a.sB2 != 0; q.b_seg = a.segB != 0;
+  CUtensorMap mapA, mapB;
+  MMS_TRY(make_map(ctx, &mapA, a.A, a.lda, a.a_mn != 0, a.M, a.K, kBM, a.sA1, a.sA2, a.segA, a.nb1, a.nb2, a.nseg));
+  MMS_TRY(make_map(ctx, &mapB, a.B, a.ldb, a.b_mn != 0, a.N, a.K, a.b_mn ? 32 : BN / 2, a.sB1, a.sB2, a.segB, a.nb1,
+                   a.nb2, a.nseg));
+  typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const TcGemmArgs, const Geometry);
+  static const kernel_t kernels[4] = {tc_gemm_tma2_kernel<false, false>, tc_gemm_tma2_kernel<false, true>,
+                                      tc_gemm_tma2_kernel<true, false>, tc_gemm_tma2_kernel<true, true>};
+  static bool configured = false;
+  if (!configured) {
+    for (int i = 0; i < 4; ++i)
+      MMS_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+    configured = true;
+  }
+  const kernel_t kernel = kernels[(a.a_mn ? 2 : 0) + (a.b_mn ? 1 : 0)];
+  const unsigned grid = 2u * (unsigned)mms_min<long long>(total, pairs);
+  { MmsKernelScope ks_(ctx, "tc_gemm_tma2_kernel");
+    kernel<<<grid, kThreads, smem, ctx->stream>>>(mapA, mapB, a, q); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
 int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& a) {
   MMS_REQUIRE(a.A && a.B && a.C, MMS_E_INVALID, "null pointer");
   MMS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.nb1 > 0 && a.nb2 > 0 && a.ksplit > 0 && a.nseg > 0,
@@ -493,6 +742,10 @@ int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& a) {
   if (a.a_rowscale || a.b_rowscale) return MMS_E_UNSUPPORTED;     // row scaling needs the register pass
   if (!tma_ok(a.A, a.lda, a.sA1, a.sA2, a.segA) || !tma_ok(a.B, a.ldb, a.sB1, a.sB2, a.segB))
     return MMS_E_UNSUPPORTED;
+  {
+    const int rc = gemm_tma_pair(ctx, a);
+    if (rc != MMS_E_UNSUPPORTED) return rc;
+  }
   Geometry q;
   const int ntiles = mms_ceil_div(a.N, 256);
   int BN = mms_ceil_div(mms_ceil_div(a.N, ntiles), 16) * 16;

@@ -93,3 +93,19 @@ def test_tc_gemm_tma_split_k_and_accumulate():
 def test_tc_gemm_tma_unaligned_falls_back_to_staged_kernel():
     # leading dimensions that are not 16-byte multiples cannot be described to TMA
     assert run(150, 90, 50, 0, 0, pad=1, tma=True) <= 1e-5
+
+
+# ---- the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles): taken when M > 128, N >= 256 and there are at
+# ---- least 74 such tiles; TF32-exact operands, so the result must match fp64 to fp32 rounding
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("shape", [(2304, 2304, 160), (2000, 2500, 100), (1000, 20000, 1024), (129 + 256 * 3, 256 * 20, 36)])
+def test_tc_gemm_pair_majorness(shape, a_mn, b_mn):
+    M, N, K = shape
+    assert run(M, N, K, a_mn, b_mn, tma=True) <= 1e-5
+
+
+def test_tc_gemm_pair_split_k_and_accumulate():
+    assert run(1024, 1024, 4096, 1, 1, ksplit=5, mode=2, tma=True) <= 1e-4
+    assert run(1024, 1024, 4100, 0, 0, ksplit=6, mode=2, tma=True) <= 1e-4
+    assert run(2304, 2304, 200, 0, 1, ksplit=1, mode=1, tma=True) <= 1e-4

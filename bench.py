@@ -156,7 +156,7 @@ def main_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -201,7 +201,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -297,11 +297,11 @@ def main_ours(args):
     sampler.start()
     total_ms = timed(device_step, args.steps)
     launches = launches_per_step * args.steps
-    clocks = sampler.stop()
 
     for _ in range(3):
         e2e_step()
     e2e_ms = timed(e2e_step, args.steps)
+    clocks = sampler.stop()          # sampled every 5 ms over both timed regions (device-resident and end-to-end)
 
     # roofline of the dominant kernel, measured live with CUDA events around each launch of an
     # eagerly issued step.  The GPU is first given ~0.5 ms of other work (L2 flushes) so that every
@@ -363,7 +363,7 @@ def main_ours(args):
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                 "sample": r["sample"]}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -482,6 +482,25 @@ def extras(world, rank, flush):
     out["c5_multimodal"] = {"workload": "C5: %d modalities x SimMatrix %dx%d, batch %d, fwd+bwd (dW, dq, da)" % (nm, K1, K2, N5),
                             "qa_pairs_per_sec": N5 / (ms / 1e3), "ms_per_step": ms,
                             "algorithmic_tflops": nm * 6.0 * N5 * K1 * K2 / (ms / 1e3) / 1e12}
+    del mods
+    torch.cuda.empty_cache()
+    # ---- ranking metrics on the device: MAP + MRR over a reranking score slab, grouped by query
+    nq, nc = 1000, 32768
+    n = nq * nc
+    gm = torch.Generator(device="cuda").manual_seed(synth.SEED)
+    prob = torch.rand((n, 2), device="cuda", generator=gm)
+    label = (torch.rand((n,), device="cuda", generator=gm) < 0.01).float()
+    group = torch.randint(0, nq, (n,), device="cuda", generator=gm).float()
+    res = torch.empty((2,), device="cuda")
+
+    def rank_metrics():
+        _lib.check(_lib.lib().mms_rank_map_mrr_f32(h.ptr, p(prob), 2, 1, p(label), p(group), n, p(res),
+                                                   ctypes.c_void_p(res.data_ptr() + 4)))
+    ms = _time_ms(rank_metrics, 3, flush, 1)
+    out["ranking_metrics"] = {"workload": "MAP + MRR of %d scores in %d query groups (segmented sort + scans on the device, "
+                                          "one call)" % (n, nq),
+                              "scores_per_sec": n / (ms / 1e3), "ms": ms, "map": float(res[0]), "mrr": float(res[1]),
+                              "input_gbs": 16.0 * n / (ms / 1e3) / 1e9}
     return out
 
 
@@ -566,9 +585,27 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints its version banner to
+    # stdout when NCCL_DEBUG is set): route fd 1 to stderr for the run and keep the real stdout for the result line.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 
 if __name__ == "__main__":

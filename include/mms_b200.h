@@ -227,6 +227,35 @@ int mms_adadelta_step_f64(mms_handle_t h, double* data, double* diff, double* hi
                           long long count, double grad_scale, double local_decay, double momentum,
                           double delta, double local_rate, int clear_diff);
 
+/* ------------------------------------------------------------ ranking metrics ---
+ * The reference's evaluation layers are CPU-only (Forward_cpu; the scores are pulled to the host, bucketed in a
+ * std::map and std::sort-ed per bucket).  Here: device in, device scalar out (a pointer to one T in device memory).
+ * The score of sample i is data[i * stride + offset] -- the reference's bottom_data[i * (fixed_axis + 1) + fixed_axis]
+ * (map_layer.cpp:50, mrr_layer.cpp:49) / bottom_data[i * dim + fixed_axis] (auc_layer.cpp:76): stride = number of
+ * classes, offset = fixed_axis.  labels and group ids are float-encoded integers as in the reference's blobs.
+ *   mms_rank_map_mrr  MAPLayer::Forward_cpu (map_layer.cpp:41-100) and MRRLayer::Forward_cpu (mrr_layer.cpp:38-79) in
+ *                     one pass (either output may be NULL): groups without a positive (label 1) or without a negative
+ *                     (MAP: any other label; MRR: label 0) are skipped, mean over the rest
+ *   mms_rank_auc      AUCLayer::Forward_cpu (auc_layer.cpp:47-136) for (N, C) predictions
+ *   mms_rank_accuracy RankAccuracyLayer::Forward_cpu (rank_accuracy_layer.cpp:36-50)
+ * Samples with EQUAL scores keep their input order (the reference's std::sort leaves their order unspecified). */
+int mms_rank_map_mrr_f32(mms_handle_t h, const float* data, long long stride, long long offset,
+                         const float* label, const float* group, long long count, float* map_out,
+                         float* mrr_out);
+int mms_rank_map_mrr_f64(mms_handle_t h, const double* data, long long stride, long long offset,
+                         const double* label, const double* group, long long count, double* map_out,
+                         double* mrr_out);
+int mms_rank_auc_f32(mms_handle_t h, const float* data, long long stride, long long offset,
+                     const float* label, long long count, int has_ignore_label, int ignore_label,
+                     float* out);
+int mms_rank_auc_f64(mms_handle_t h, const double* data, long long stride, long long offset,
+                     const double* label, long long count, int has_ignore_label, int ignore_label,
+                     double* out);
+int mms_rank_accuracy_f32(mms_handle_t h, const float* a, const float* b, const float* label,
+                          long long count, float* out);
+int mms_rank_accuracy_f64(mms_handle_t h, const double* a, const double* b, const double* label,
+                          long long count, double* out);
+
 /* ------------------------------------------------------ candidate scoring ---
  * Reranking with the SimMatrix bilinear form (BASELINE config "1k queries x 1M candidates"):
  * scores[i,j] = q_i^T W c_j.  Q (Nq,K1), C (Nc,K2), W (K1,K2), scores (Nq,Nc) row-major.

@@ -12,10 +12,11 @@ library or without a B200 the layers raise.
 """
 from ._lib import MMSError, lib, lib_path  # noqa: F401
 from .blob import Blob  # noqa: F401
-from .layers import (EmbedLayer, FMLayer, Layer, LayerParameter, PairRankLossLayer,  # noqa: F401
-                     SimCrossLayer, SimMatrixLayer, create_layer)
+from .layers import (AUCLayer, EmbedLayer, FMLayer, Layer, LayerParameter, MAPLayer, MRRLayer,  # noqa: F401
+                     PairRankLossLayer, RankAccuracyLayer, SimCrossLayer, SimMatrixLayer, create_layer)
 from .net import MMSNet  # noqa: F401
 from .solver import AdaDeltaSolver  # noqa: F401
 
 __all__ = ["MMSError", "lib", "lib_path", "Blob", "Layer", "LayerParameter", "EmbedLayer",
-           "SimCrossLayer", "SimMatrixLayer", "PairRankLossLayer", "FMLayer", "create_layer", "MMSNet", "AdaDeltaSolver"]
+           "SimCrossLayer", "SimMatrixLayer", "PairRankLossLayer", "FMLayer", "create_layer", "MMSNet", "AdaDeltaSolver",
+           "MAPLayer", "MRRLayer", "AUCLayer", "RankAccuracyLayer"]

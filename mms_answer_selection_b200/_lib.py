@@ -43,6 +43,9 @@ def _typed(real):
         "mms_dot": [p, p, p, c_ll, p],
         "mms_scale": [p, p, c_ll, real],
         "mms_adadelta_update": [p, p, p, p, c_ll, real, real, real],
+        "mms_rank_map_mrr": [p, p, c_ll, c_ll, p, p, c_ll, p, p],
+        "mms_rank_auc": [p, p, c_ll, c_ll, p, c_ll, c_int, c_int, p],
+        "mms_rank_accuracy": [p, p, p, p, c_ll, p],
         "mms_adadelta_step": [p, p, p, p, p, c_ll, real, real, real, real, real, c_int],
     }
 

@@ -1,7 +1,7 @@
 // Glue between Caffe's Layer API and the C-ABI of libmms_b200.so (include/mms_b200.h).
 //
-// The five TUs in this directory REPLACE src/caffe/layers/{embed,sim_cross,sim_matrix,
-// pair_rank_loss,fm}_layer.{cpp,cu} of the reference in the link (a layer type can be registered
+// The TUs in this directory REPLACE src/caffe/layers/{embed,sim_cross,sim_matrix,
+// pair_rank_loss,fm}_layer.{cpp,cu} and {map,mrr,auc,rank_accuracy}_layer.cpp of the reference in the link (a layer type can be registered
 // once, include/caffe/layer_factory.hpp:69-70).  They are compiled against the reference's own,
 // unmodified headers, so the class declarations -- members included -- are the reference's; the
 // per-thread workspace handle therefore lives here, not in the classes.
@@ -91,6 +91,22 @@ MMS_OVERLOAD(fm_backward,
              (mms_handle_t h, const float* x, const float* dy, float* dx, float* db, int N, int C, int Dm, int p0),
              (mms_handle_t h, const double* x, const double* dy, double* dx, double* db, int N, int C, int Dm, int p0),
              (h, x, dy, dx, db, N, C, Dm, p0))
+MMS_OVERLOAD(rank_map_mrr,
+             (mms_handle_t h, const float* d, long long st, long long off, const float* l, const float* g, long long n,
+              float* map, float* mrr),
+             (mms_handle_t h, const double* d, long long st, long long off, const double* l, const double* g,
+              long long n, double* map, double* mrr),
+             (h, d, st, off, l, g, n, map, mrr))
+MMS_OVERLOAD(rank_auc,
+             (mms_handle_t h, const float* d, long long st, long long off, const float* l, long long n, int hi, int il,
+              float* out),
+             (mms_handle_t h, const double* d, long long st, long long off, const double* l, long long n, int hi,
+              int il, double* out),
+             (h, d, st, off, l, n, hi, il, out))
+MMS_OVERLOAD(rank_accuracy,
+             (mms_handle_t h, const float* a, const float* b, const float* y, long long n, float* out),
+             (mms_handle_t h, const double* a, const double* b, const double* y, long long n, double* out),
+             (h, a, b, y, n, out))
 #undef MMS_OVERLOAD
 
 }  // namespace mms

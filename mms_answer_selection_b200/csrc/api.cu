@@ -294,6 +294,22 @@ int mms_check_faults(mms_handle_t h) {
     H; return mms_adadelta_step_impl<T>(h, data, diff, hist_g, hist_u, count, grad_scale,          \
                                         local_decay, momentum, delta, local_rate, clear_diff);     \
   }                                                                                                \
+  int mms_rank_map_mrr_##SUF(mms_handle_t h, const T* data, long long stride, long long offset,    \
+                             const T* label, const T* group, long long count, T* map_out,          \
+                             T* mrr_out) {                                                         \
+    H; return mms_rank_map_mrr_impl<T>(h, data, stride, offset, label, group, count, map_out,      \
+                                       mrr_out);                                                   \
+  }                                                                                                \
+  int mms_rank_auc_##SUF(mms_handle_t h, const T* data, long long stride, long long offset,        \
+                         const T* label, long long count, int has_ignore_label, int ignore_label,  \
+                         T* out) {                                                                 \
+    H; return mms_rank_auc_impl<T>(h, data, stride, offset, label, count, has_ignore_label,        \
+                                   ignore_label, out);                                             \
+  }                                                                                                \
+  int mms_rank_accuracy_##SUF(mms_handle_t h, const T* a, const T* b, const T* label,              \
+                              long long count, T* out) {                                           \
+    H; return mms_rank_accuracy_impl<T>(h, a, b, label, count, out);                               \
+  }                                                                                                \
   int mms_adadelta_update_##SUF(mms_handle_t h, T* g, T* hist_g, T* hist_u, long long count,       \
                                 T momentum, T delta, T local_rate) {                               \
     H; return mms_adadelta_step_impl<T>(h, nullptr, g, hist_g, hist_u, count, T(1), T(0), momentum,\

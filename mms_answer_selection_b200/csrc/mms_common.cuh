@@ -158,6 +158,14 @@ int mms_dot_impl(mms_context*, const T* x, const T* y, long long n, T* out);
 template <typename T>
 int mms_scale_impl(mms_context*, T* x, long long n, T alpha);
 template <typename T>
+int mms_rank_map_mrr_impl(mms_context*, const T* data, long long stride, long long offset, const T* label, const T* group,
+                          long long n, T* map_out, T* mrr_out);
+template <typename T>
+int mms_rank_auc_impl(mms_context*, const T* data, long long stride, long long offset, const T* label, long long n,
+                      int has_ignore, int ignore_label, T* out);
+template <typename T>
+int mms_rank_accuracy_impl(mms_context*, const T* a, const T* b, const T* label, long long n, T* out);
+template <typename T>
 int mms_adadelta_step_impl(mms_context*, T* data, T* diff, T* hist_g, T* hist_u, long long n, T grad_scale, T local_decay,
                            T momentum, T delta, T local_rate, int clear_diff);
 

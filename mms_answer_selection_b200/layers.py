@@ -54,6 +54,9 @@ _DEFAULTS = {
     "fm_param": dict(bias_term=True),                                   # caffe.proto:418-420
     "embed_param": dict(num_output=0, input_dim=0, bias_term=True, weight_filler=None,   # :790-803
                         bias_filler=None, weight_source=""),
+    "map_param": dict(fixed_axis=1),                                    # caffe.proto:422-424
+    "mrr_param": dict(fixed_axis=1),                                    # caffe.proto:426-428
+    "auc_param": dict(fixed_axis=1, axis=1, ignore_label=None),         # caffe.proto:465-469
 }
 
 
@@ -378,8 +381,95 @@ class FMLayer(Layer):
                    bottom[0].num(), bottom[0].channels(), bottom[0].height(), int(propagate_down[0]))
 
 
+# ------------------------------------------------------------------------- ranking metrics
+class _GroupedRankLayer(Layer):
+    """MAPLayer / MRRLayer (include/caffe/layers/{map,mrr}_layer.hpp): bottoms (predictions (N, C), labels (N),
+    group ids (N)), a scalar top.  The reference implements Forward_cpu only; here the scores never leave the
+    device."""
+    exact_num_bottom = 3
+    _param = None
+    _which = 0
+
+    def LayerSetUp(self, bottom, top):
+        self.fixed_axis_ = int(getattr(self.layer_param_, self._param)["fixed_axis"])
+
+    def Reshape(self, bottom, top):
+        _check(self.fixed_axis_ <= bottom[0].count() // max(bottom[1].count(), 1),
+               "top_k must be less than or equal to the number of classes.")           # map_layer.cpp:19-20
+        outer, inner = bottom[0].count(0, 1), bottom[0].count(2)
+        _check(outer * inner == bottom[1].count(), "Number of labels must match number of predictions; ")
+        _check(outer * inner == bottom[2].count(), "Number of group ids must match number of predictions")
+        top[0].Reshape((1,))                                   # scalar top (0 axes in the reference)
+
+    def Forward_gpu(self, bottom, top):
+        out = c_p(top[0].gpu_data())
+        null = c_p(0)
+        # the reference reads bottom_data[i * (fixed_axis + 1) + fixed_axis] (map_layer.cpp:50, mrr_layer.cpp:49)
+        self._call("mms_rank_map_mrr", _p(bottom[0]), self.fixed_axis_ + 1, self.fixed_axis_, _p(bottom[1]),
+                   _p(bottom[2]), bottom[0].num(), out if self._which == 0 else null, out if self._which == 1 else null)
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        _check(not any(propagate_down), "%s Layer cannot backpropagate." % self.type())   # map_layer.hpp: NOT_IMPLEMENTED
+
+
+class MAPLayer(_GroupedRankLayer):
+    _param, _which = "map_param", 0
+
+
+class MRRLayer(_GroupedRankLayer):
+    _param, _which = "mrr_param", 1
+
+
+class AUCLayer(Layer):
+    """AUCLayer (auc_layer.cpp:11-136) for (N, C) predictions and N labels."""
+    exact_num_bottom = 2
+
+    def LayerSetUp(self, bottom, top):
+        ap = self.layer_param_.auc_param
+        self.fixed_axis_ = int(ap["fixed_axis"])
+        self.has_ignore_label_ = ap["ignore_label"] is not None
+        self.ignore_label_ = int(ap["ignore_label"] or 0)
+
+    def Reshape(self, bottom, top):
+        _check(self.fixed_axis_ <= bottom[0].count() // max(bottom[1].count(), 1),
+               "top_k must be less than or equal to the number of classes.")
+        axis = int(self.layer_param_.auc_param["axis"])
+        _check(axis == 1 and bottom[0].count(2) == 1,
+               "AUC on the device takes (N, C) predictions (label axis 1, no inner dimensions)")
+        _check(bottom[0].count(0, 1) == bottom[1].count(), "Number of labels must match number of predictions; ")
+        top[0].Reshape((1,))                                   # scalar top (0 axes in the reference)
+
+    def Forward_gpu(self, bottom, top):
+        self._call("mms_rank_auc", _p(bottom[0]), bottom[0].count(1), self.fixed_axis_, _p(bottom[1]),
+                   bottom[0].num(), int(self.has_ignore_label_), self.ignore_label_, c_p(top[0].gpu_data()))
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        _check(not any(propagate_down), "AUC Layer cannot backpropagate.")
+
+
+class RankAccuracyLayer(Layer):
+    """RankAccuracyLayer (rank_accuracy_layer.cpp:17-50): fraction of pairs with label * (a - b) > 0."""
+    exact_num_bottom = 3
+
+    def LayerSetUp(self, bottom, top):
+        pass
+
+    def Reshape(self, bottom, top):
+        _check(bottom[0].count() == bottom[1].count(), "two pairs have the same dimension!.")
+        _check(bottom[0].count() == bottom[2].count(), "pair should have the same dimension with the label!.")
+        top[0].Reshape((1,))                                   # scalar top (0 axes in the reference)
+
+    def Forward_gpu(self, bottom, top):
+        self._call("mms_rank_accuracy", _p(bottom[0]), _p(bottom[1]), _p(bottom[2]), bottom[0].count(),
+                   c_p(top[0].gpu_data()))
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        _check(not any(propagate_down), "RankAccuracy Layer cannot backpropagate.")
+
+
 _REGISTRY = {"Embed": EmbedLayer, "SimCross": SimCrossLayer, "SimMatrix": SimMatrixLayer,
-             "PairRankLoss": PairRankLossLayer, "FM": FMLayer}
+             "PairRankLoss": PairRankLossLayer, "FM": FMLayer, "MAP": MAPLayer, "MRR": MRRLayer, "AUC": AUCLayer,
+             "RankAccuracy": RankAccuracyLayer}
 
 
 def create_layer(param):

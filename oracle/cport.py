@@ -169,3 +169,30 @@ def adadelta_step(data, diff, hist_g, hist_u, grad_scale=1.0, local_decay=0.0, m
     _call("mmso_adadelta_step", dtype, _ptr(data), _ptr(diff), _ptr(hist_g), _ptr(hist_u),
           ctypes.c_longlong(diff.size), real(grad_scale), real(local_decay), real(momentum), real(delta),
           real(local_rate))
+
+
+def map_mrr(data, label, group, fixed_axis=1):
+    """(MAP, MRR) of MAPLayer / MRRLayer; data (N, fixed_axis + 1)."""
+    dtype = data.dtype
+    d, l, g = _c(data, dtype), _c(label, dtype), _c(group, dtype)
+    out = np.zeros(2, dtype)
+    _call("mmso_map_mrr", dtype, _ptr(d), _ptr(l), _ptr(g), int(l.size), int(fixed_axis),
+          ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(out.ctypes.data + out.itemsize))
+    return out[0], out[1]
+
+
+def auc(data, label, fixed_axis=1, ignore_label=None):
+    dtype = data.dtype
+    d, l = _c(data, dtype), _c(label, dtype)
+    out = np.zeros(1, dtype)
+    _call("mmso_auc", dtype, _ptr(d), _ptr(l), int(l.size), int(d.size // l.size), int(fixed_axis),
+          int(ignore_label is not None), int(ignore_label or 0), _ptr(out))
+    return out[0]
+
+
+def rank_accuracy(a, b, label):
+    dtype = a.dtype
+    out = np.zeros(1, dtype)
+    _call("mmso_rank_accuracy", dtype, _ptr(_c(a, dtype)), _ptr(_c(b, dtype)), _ptr(_c(label, dtype)), int(a.size),
+          _ptr(out))
+    return out[0]

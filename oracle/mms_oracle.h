@@ -17,6 +17,9 @@ int mmso_pairrankloss_forward_f32(const float* a, const float* b, const float* y
 int mmso_pairrankloss_backward_f32(const float* y, const float* ordered, const float* similar, float top_diff, int count, int ge, float* da, float* db);
 int mmso_fm_forward_f32(const float* x, const float* bias, float* y, int N, int C, int Dm);
 int mmso_fm_backward_f32(const float* x, const float* dy, float* dx, float* dbias, int N, int C, int Dm, int prop0);
+int mmso_map_mrr_f32(const float* data, const float* label, const float* group, int n, int fixed_axis, float* map_out, float* mrr_out);
+int mmso_auc_f32(const float* data, const float* label, int n, int dim, int fixed_axis, int has_ignore, int ignore_label, float* out);
+int mmso_rank_accuracy_f32(const float* a, const float* b, const float* label, int n, float* out);
 int mmso_adadelta_step_f32(float* data, float* diff, float* hist_g, float* hist_u, long long n, float grad_scale, float local_decay, float momentum, float delta, float local_rate);
 
 int mmso_embed_forward_f64(const double* idx, const double* W, const double* bias, double* top, int M, int D, int V);
@@ -29,6 +32,9 @@ int mmso_pairrankloss_forward_f64(const double* a, const double* b, const double
 int mmso_pairrankloss_backward_f64(const double* y, const double* ordered, const double* similar, double top_diff, int count, int ge, double* da, double* db);
 int mmso_fm_forward_f64(const double* x, const double* bias, double* y, int N, int C, int Dm);
 int mmso_fm_backward_f64(const double* x, const double* dy, double* dx, double* dbias, int N, int C, int Dm, int prop0);
+int mmso_map_mrr_f64(const double* data, const double* label, const double* group, int n, int fixed_axis, double* map_out, double* mrr_out);
+int mmso_auc_f64(const double* data, const double* label, int n, int dim, int fixed_axis, int has_ignore, int ignore_label, double* out);
+int mmso_rank_accuracy_f64(const double* a, const double* b, const double* label, int n, double* out);
 int mmso_adadelta_step_f64(double* data, double* diff, double* hist_g, double* hist_u, long long n, double grad_scale, double local_decay, double momentum, double delta, double local_rate);
 
 #ifdef __cplusplus

@@ -409,3 +409,90 @@ int FN(mmso_adadelta_step)(REAL* data, REAL* diff, REAL* hist_g, REAL* hist_u, l
   }
   return 0;
 }
+
+/* ---- ranking metrics (evaluation layers) -------------------------------------------------
+ * Shared by MAP and MRR: samples are bucketed by int(group) into a std::map (ascending key), each bucket holds
+ * (float score, int label) pairs in input order and is sorted by score, descending, with std::sort
+ * (map_layer.cpp:47-51,72; mrr_layer.cpp:47-50,57).  std::sort is not stable: the order of EQUAL scores is
+ * unspecified in the reference; this restatement (and the GPU implementation) keeps input order among equals. */
+#ifndef MMSO_RANK_HELPERS
+#define MMSO_RANK_HELPERS
+typedef struct { int group; float score; int label; int index; } mmso_rank_item;
+static int mmso_rank_cmp(const void* pa, const void* pb) {
+  const mmso_rank_item* a = (const mmso_rank_item*)pa; const mmso_rank_item* b = (const mmso_rank_item*)pb;
+  if (a->group != b->group) return a->group < b->group ? -1 : 1;
+  if (a->score != b->score) return a->score > b->score ? -1 : 1;
+  return a->index < b->index ? -1 : (a->index > b->index ? 1 : 0);
+}
+#endif
+
+/* MAPLayer::Forward_cpu, map_layer.cpp:41-100 and MRRLayer::Forward_cpu, mrr_layer.cpp:38-79.  The score of sample i
+ * is data[i * (fixed_axis + 1) + fixed_axis] (:50 / :49).  MAP counts label == 1 as positive and anything else as a
+ * negative (:78-85); MRR needs a label == 0 for its negative (:64-66).  Groups without a positive or without a
+ * negative are skipped; the mean is over the remaining groups (0/0 if there is none, as in the reference). */
+int FN(mmso_map_mrr)(const REAL* data, const REAL* label, const REAL* group, int n, int fixed_axis, REAL* map_out,
+                     REAL* mrr_out) {
+  mmso_rank_item* it = (mmso_rank_item*)malloc(sizeof(mmso_rank_item) * (size_t)(n > 0 ? n : 1));
+  if (!it) return 1;
+  for (int i = 0; i < n; ++i) {
+    it[i].group = (int)group[i];
+    it[i].score = (float)data[(size_t)i * (fixed_axis + 1) + fixed_axis];
+    it[i].label = (int)label[i];
+    it[i].index = i;
+  }
+  qsort(it, (size_t)n, sizeof(mmso_rank_item), mmso_rank_cmp);
+  REAL map_ = 0, mrr = 0;
+  int eff_map = 0, eff_mrr = 0;
+  for (int s = 0; s < n;) {
+    int e = s;
+    while (e < n && it[e].group == it[s].group) ++e;
+    REAL ap = 0;
+    int map_rank = 0, neg_any = 0, mrr_rank = -1, neg_zero = 0;
+    for (int i = s; i < e; ++i) {
+      if (it[i].label == 1) { ap += (REAL)(++map_rank) / (REAL)(i - s + 1); if (mrr_rank < 0) mrr_rank = i - s; }
+      else neg_any = 1;
+      if (it[i].label == 0) neg_zero = 1;
+    }
+    if (map_rank >= 1 && neg_any) { ++eff_map; map_ += ap / map_rank; }
+    if (mrr_rank >= 0 && neg_zero) { ++eff_mrr; mrr = (REAL)((double)mrr + 1.0 / (mrr_rank + 1)); }   /* :75: Dtype += double */
+    s = e;
+  }
+  if (map_out) *map_out = map_ / (REAL)eff_map;
+  if (mrr_out) *mrr_out = mrr / (REAL)eff_mrr;
+  free(it);
+  return 0;
+}
+
+/* AUCLayer::Forward_cpu, auc_layer.cpp:47-136, for the 2-D (N, C) bottom the reference net feeds it
+ * (label axis 1, inner_num 1): score of sample i = data[i * dim + fixed_axis]; sorted by score, descending (compared
+ * as float, :43-45); auc = sum over samples of high * (1 - label), high = positives so far; / high / (count - high). */
+int FN(mmso_auc)(const REAL* data, const REAL* label, int n, int dim, int fixed_axis, int has_ignore, int ignore_label,
+                 REAL* out) {
+  mmso_rank_item* it = (mmso_rank_item*)malloc(sizeof(mmso_rank_item) * (size_t)(n > 0 ? n : 1));
+  if (!it) return 1;
+  int count = 0;
+  for (int i = 0; i < n; ++i) {
+    const int lv = (int)label[i];
+    if (has_ignore && lv == ignore_label) continue;
+    it[count].group = 0;
+    it[count].score = (float)data[(size_t)i * dim + fixed_axis];
+    it[count].label = lv;
+    it[count].index = count;
+    ++count;
+  }
+  qsort(it, (size_t)count, sizeof(mmso_rank_item), mmso_rank_cmp);
+  int high = 0;
+  REAL auc = 0;
+  for (int i = 0; i < count; ++i) { high += it[i].label; auc += (REAL)(high * (1 - it[i].label)); }
+  *out = high > 0 ? auc / high / (count - high) : (REAL)0;
+  free(it);
+  return 0;
+}
+
+/* RankAccuracyLayer::Forward_cpu, rank_accuracy_layer.cpp:36-50. */
+int FN(mmso_rank_accuracy)(const REAL* a, const REAL* b, const REAL* label, int n, REAL* out) {
+  REAL acc = 0;
+  for (int i = 0; i < n; ++i) acc += (label[i] * (a[i] - b[i])) > 0 ? 1 : 0;
+  *out = acc / n;
+  return 0;
+}

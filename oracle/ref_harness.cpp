@@ -138,6 +138,11 @@ int mmsref_set_i(void* h, const char* key, long long v) {
   else if (k == "embed.bias_term") s->param.mutable_embed_param()->set_bias_term(v != 0);
   else if (k == "fm.bias_term") s->param.mutable_fm_param()->set_bias_term(v != 0);
   else if (k == "phase") s->param.set_phase(v ? caffe::TEST : caffe::TRAIN);
+  else if (k == "map.fixed_axis") s->param.mutable_map_param()->set_fixed_axis(static_cast<int>(v));
+  else if (k == "mrr.fixed_axis") s->param.mutable_mrr_param()->set_fixed_axis(static_cast<int>(v));
+  else if (k == "auc.fixed_axis") s->param.mutable_auc_param()->set_fixed_axis(static_cast<int>(v));
+  else if (k == "auc.axis") s->param.mutable_auc_param()->set_axis(static_cast<int>(v));
+  else if (k == "auc.ignore_label") s->param.mutable_auc_param()->set_ignore_label(static_cast<int>(v));
   else return 2;
   return 0;
 }

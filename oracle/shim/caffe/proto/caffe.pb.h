@@ -129,6 +129,21 @@ class FMParameter {
   MMS_PB_OPTIONAL(bool, bias_term, true)
 };
 
+// caffe.proto:422-428
+class MAPParameter {
+  MMS_PB_OPTIONAL(int, fixed_axis, 1)
+};
+class MRRParameter {
+  MMS_PB_OPTIONAL(int, fixed_axis, 1)
+};
+
+// caffe.proto:465-469
+class AUCParameter {
+  MMS_PB_OPTIONAL(int, fixed_axis, 1)
+  MMS_PB_OPTIONAL(int, axis, 1)
+  MMS_PB_OPTIONAL(int, ignore_label, 0)
+};
+
 // caffe.proto (LossParameter): ignore_label, normalize
 class LossParameter {
   MMS_PB_OPTIONAL(int, ignore_label, 0)
@@ -148,6 +163,9 @@ class LayerParameter {
   MMS_PB_MESSAGE(EmbedParameter, embed_param)
   MMS_PB_MESSAGE(FMParameter, fm_param)
   MMS_PB_MESSAGE(LossParameter, loss_param)
+  MMS_PB_MESSAGE(MAPParameter, map_param)
+  MMS_PB_MESSAGE(MRRParameter, mrr_param)
+  MMS_PB_MESSAGE(AUCParameter, auc_param)
  private:
   std::vector<BlobProto> blobs_;
  public:

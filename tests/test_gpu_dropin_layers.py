@@ -148,6 +148,34 @@ def test_fm(dtype):
     assert scaled_err(new.read("blob", 0, diff=True), ref.read("blob", 0, diff=True)) <= 1e-5
 
 
+@needs_dropin
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_ranking_metric_layers(dtype):
+    """MAP / MRR / AUC / RankAccuracy: the reference's layers on the CPU vs the drop-in classes in Caffe::GPU mode
+    (distinct scores: equal scores have no specified order in the reference).  The device sums in double and rounds
+    once, the reference accumulates in Dtype."""
+    rng = np.random.default_rng(17)
+    n = 1517
+    prob = np.zeros((n, 2), dtype)
+    prob[:, 1] = (rng.permutation(n) + 0.5) / n
+    prob[:, 0] = 1 - prob[:, 1]
+    label = (rng.uniform(0, 1, n) < 0.17).astype(dtype)
+    group = rng.integers(-2, 66, n).astype(dtype)
+    b = rng.uniform(0, 1, n).astype(dtype)
+    y = np.where(rng.uniform(0, 1, n) < 0.5, 1.0, -1.0).astype(dtype)
+    tol = 2e-6 if dtype == np.float32 else 1e-12
+    for typ, params, bots in (("MAP", {"map.fixed_axis": 1}, [prob, label, group]),
+                              ("MRR", {"mrr.fixed_axis": 1}, [prob, label, group]),
+                              ("AUC", {"auc.fixed_axis": 1}, [prob, label]),
+                              ("AUC", {"auc.fixed_axis": 1, "auc.ignore_label": 3}, [prob, label]),
+                              ("RankAccuracy", {}, [np.ascontiguousarray(prob[:, 1]), b, y])):
+        ref, new = pair(typ, bots, params, dtype)
+        ref.forward(); new.forward()
+        r, g = float(ref.read("top", 0).reshape(-1)[0]), float(new.read("top", 0).reshape(-1)[0])
+        assert 0.0 < r <= 1.0 and abs(g - r) <= tol * abs(r), (typ, r, g)
+
+
 # ---- no GPU needed: the drop-in library registers the five types and has no CPU path -----------
 @needs_dropin
 def test_dropin_registers_the_reference_layer_types_and_refuses_cpu_mode():
@@ -157,7 +185,11 @@ def test_dropin_registers_the_reference_layer_types_and_refuses_cpu_mode():
         shapes = {"Embed": ([np.zeros((2, 3), np.float32)], {"num_output": 4, "input_dim": 5}),
                   "SimCross": ([x, x], {"dist_mode": 2, "mesure_count": 2}),
                   "SimMatrix": ([x, x], {}), "FM": ([x], {}),
-                  "PairRankLoss": ([np.zeros((2, 1), np.float32)] * 3, {})}
+                  "PairRankLoss": ([np.zeros((2, 1), np.float32)] * 3, {}),
+                  "MAP": ([np.zeros((2, 2), np.float32)] + [np.zeros((2,), np.float32)] * 2, {}),
+                  "MRR": ([np.zeros((2, 2), np.float32)] + [np.zeros((2,), np.float32)] * 2, {}),
+                  "AUC": ([np.zeros((2, 2), np.float32), np.zeros((2,), np.float32)], {}),
+                  "RankAccuracy": ([np.zeros((2,), np.float32)] * 3, {})}
         for type_, (bottoms, params) in shapes.items():
             layer = refbind.DropinLayer(type_, bottoms, params)
             with pytest.raises(refbind.RefError, match="runs on the GPU only"):

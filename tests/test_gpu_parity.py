@@ -8,6 +8,8 @@ Tolerances (scaled error |got-ref| / max(|got|,|ref|,max|ref|), the GradientChec
   * float32 TF32 tensor-core contractions (SimCross mode 2, SimMatrix): 1e-3, the
     tolerance BASELINE.json's north_star states for fp32/TF32 scores and gradients.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -598,3 +600,67 @@ def test_rerank_scores_vs_simmatrix_form():
     # one row through the SimMatrix oracle (q_i paired with every candidate)
     s, _ = cport.simmatrix_forward(np.repeat(Q[:1], 64, 0), C[:64], W)
     assert scaled_err(got[0, :64], s.reshape(-1)) <= TOL_TF32
+
+
+# ---------------------------------------------------------------- ranking metrics on the device
+def _metric_layers(prob, label, group, dtype, fa):
+    out = {}
+    bp, bl, bg = blob(prob, dtype), blob(label, dtype), blob(group, dtype)
+    for typ, key, bots in (("MAP", "map_param", [bp, bl, bg]), ("MRR", "mrr_param", [bp, bl, bg])):
+        lay = mms.create_layer(mms.LayerParameter(typ, dtype=dtype, **{key: dict(fixed_axis=fa)}))
+        top = mms.Blob((), dtype=dtype)
+        lay.SetUp(bots, [top]); lay.Forward(bots, [top])
+        out[typ] = top.cpu_data().reshape(-1)[0]
+    return out
+
+
+@pytest.mark.parametrize("tag,dtype", [("f32", np.float32), ("f64", np.float64)])
+@pytest.mark.parametrize("case", ["trec", "small", "one_group", "no_pos_groups", "three_class"])
+def test_rank_metrics_golden(case, tag, dtype):
+    """MAP / MRR / AUC / RankAccuracy on the device against fixtures from the reference's own CPU layers
+    (tests/golden/metrics_golden.npz; distinct scores, so the ranking is fully determined).  The device sums in
+    double and rounds once; the reference accumulates in Dtype: 2e-6 / 1e-12 relative."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_golden.npz"))
+    k = "%s_%s/" % (case, tag)
+    prob, label, group = g[k + "prob"], g[k + "label"], g[k + "group"]
+    fa = prob.shape[1] - 1
+    tol = 2e-6 if dtype == np.float32 else 1e-12
+    close = lambda x, y: (np.isnan(x) and np.isnan(y)) or abs(float(x) - float(y)) <= tol * max(abs(float(y)), 1e-30)
+    got = _metric_layers(prob, label, group, dtype, fa)
+    assert close(got["MAP"], g[k + "map"]) and close(got["MRR"], g[k + "mrr"])
+    if prob.shape[1] == 2:
+        for ign, key in ((None, "auc"), (0, "auc_ignore")):
+            lay = mms.create_layer(mms.LayerParameter("AUC", dtype=dtype, auc_param=dict(fixed_axis=fa, ignore_label=ign)))
+            bots, top = [blob(prob, dtype), blob(label, dtype)], mms.Blob((), dtype=dtype)
+            lay.SetUp(bots, [top]); lay.Forward(bots, [top])
+            assert close(top.cpu_data().reshape(-1)[0], g[k + key]), key
+    lay = mms.create_layer(mms.LayerParameter("RankAccuracy", dtype=dtype))
+    bots = [blob(np.ascontiguousarray(prob[:, fa]), dtype), blob(g[k + "ra_b"], dtype), blob(g[k + "ra_y"], dtype)]
+    top = mms.Blob((), dtype=dtype)
+    lay.SetUp(bots, [top]); lay.Forward(bots, [top])
+    assert close(top.cpu_data().reshape(-1)[0], g[k + "rank_accuracy"])
+
+
+@pytest.mark.parametrize("n,ngroups", [(1, 1), (5000, 400), (300_000, 3), (200_000, 20_000)])
+def test_rank_metrics_vs_oracle_with_ties(n, ngroups):
+    """Quantised scores (many ties) and every group-size regime, against the oracle restatement, which breaks ties
+    the same way (input order); includes groups with no positive / no negative and a single-sample input."""
+    rng = np.random.default_rng(n + ngroups)
+    prob = np.zeros((n, 2), np.float32)
+    prob[:, 1] = rng.integers(0, 50, n) / 50.0
+    prob[:, 0] = 1 - prob[:, 1]
+    label = (rng.uniform(0, 1, n) < 0.2).astype(np.float32)
+    group = rng.integers(0, ngroups, n).astype(np.float32)
+    got = _metric_layers(prob, label, group, np.float32, 1)
+    # the reference accumulates AP / RR / the AUC sum in Dtype (float: ~1e-5 of rounding noise over 10^5-sample
+    # groups); the device sums in double and rounds once, so the yardstick is the oracle evaluated in float64
+    m, r = cport.map_mrr(prob.astype(np.float64), label.astype(np.float64), group.astype(np.float64))
+    m32, r32 = cport.map_mrr(prob, label, group)
+    close = lambda x, y, t=5e-6: (np.isnan(x) and np.isnan(y)) or abs(float(x) - float(y)) <= t * max(abs(float(y)), 1e-30)
+    assert close(m32, m, 1e-4) and close(r32, r, 1e-4)
+    assert close(got["MAP"], m) and close(got["MRR"], r)
+    lay = mms.create_layer(mms.LayerParameter("AUC"))
+    bots, top = [blob(prob, np.float32), blob(label, np.float32)], mms.Blob(())
+    lay.SetUp(bots, [top]); lay.Forward(bots, [top])
+    ref = float(cport.auc(prob.astype(np.float64), label.astype(np.float64)))
+    assert close(top.cpu_data().reshape(-1)[0], np.float32(ref))

@@ -8,6 +8,8 @@ Three anchors, per the parity contract:
  3. the reference itself (oracle/_ref) on fresh random inputs, when it is present.
 plus GradientChecker-style finite differences (test_gradient_check_util.hpp:148-175).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -310,3 +312,51 @@ def test_adadelta_oracle_known_answer():
     g2 = np.ones(3); h = np.zeros(3); h2 = np.zeros(3)
     cport.adadelta_step(None, g2, h, h2, local_decay=1.0, momentum=0.95, delta=5e-7, local_rate=2.0)
     assert np.allclose(g2, 2.0 * u, rtol=1e-12)
+
+
+# ---------------------------------------------------------------- ranking metrics
+METRIC_CASES = ["trec", "small", "one_group", "no_pos_groups", "three_class"]
+
+
+def _metrics_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_golden.npz"))
+
+
+@pytest.mark.parametrize("tag,dtype", [("f32", np.float32), ("f64", np.float64)])
+@pytest.mark.parametrize("case", METRIC_CASES)
+def test_metric_oracles_match_reference_fixtures(case, tag, dtype):
+    """The plain-C restatements of MAP / MRR / AUC / RankAccuracy against fixtures produced by the reference's own
+    layers (tests/golden/make_metrics_golden.py): bit-exact -- same order of operations, same accumulation type."""
+    g = _metrics_golden()
+    k = "%s_%s/" % (case, tag)
+    prob, label, group = g[k + "prob"], g[k + "label"], g[k + "group"]
+    fa = prob.shape[1] - 1
+    m, r = cport.map_mrr(prob, label, group, fixed_axis=fa)
+    assert m == g[k + "map"] or (np.isnan(m) and np.isnan(g[k + "map"]))
+    assert r == g[k + "mrr"] or (np.isnan(r) and np.isnan(g[k + "mrr"]))
+    if prob.shape[1] == 2:
+        same = lambda x, y: x == y or (np.isnan(x) and np.isnan(y))
+        assert same(cport.auc(prob, label, fixed_axis=fa), g[k + "auc"])
+        # ignoring label 0 leaves no negative: 0/0, in the reference and here
+        assert same(cport.auc(prob, label, fixed_axis=fa, ignore_label=0), g[k + "auc_ignore"])
+    a = np.ascontiguousarray(prob[:, fa])
+    assert cport.rank_accuracy(a, g[k + "ra_b"], g[k + "ra_y"]) == g[k + "rank_accuracy"]
+
+
+@pytest.mark.skipif(not os.path.exists(refbind.REF_SO), reason="compiled reference not present")
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_metric_oracles_match_compiled_reference(dtype):
+    rng = np.random.default_rng(8)
+    for _ in range(10):
+        n = int(rng.integers(2, 600))
+        prob = rng.uniform(0, 1, (n, 2)).astype(dtype)
+        label = (rng.uniform(0, 1, n) < 0.3).astype(dtype)
+        group = rng.integers(-3, 30, n).astype(dtype)
+        m, r = cport.map_mrr(prob, label, group)
+        for typ, params, bots, ours in (("MAP", {"map.fixed_axis": 1}, [prob, label, group], m),
+                                        ("MRR", {"mrr.fixed_axis": 1}, [prob, label, group], r),
+                                        ("AUC", {"auc.fixed_axis": 1}, [prob, label], cport.auc(prob, label))):
+            lay = refbind.RefLayer(typ, bots, params, dtype=dtype)
+            lay.forward()
+            ref = lay.read("top", 0).reshape(-1)[0]
+            assert ours == ref or (np.isnan(ours) and np.isnan(ref)), typ

@@ -355,6 +355,7 @@ def main_ours(args):
         "roofline": roof,
         "kernels_ms_per_step": {k: round(ms / prof_steps, 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
         "kernel_step_ms_sum": step_ms_prof,
+        "hbm_kernels": hbm_kernel_table(prof, prof_steps, cfg, peaks),
     }
     if not args.no_extra:
         line["extra"] = extras(world, rank, flush)
@@ -539,6 +540,29 @@ def ncu_tensor_pipe(wl, name):
         return float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"].split()[0])
     except Exception:
         return None
+
+
+def hbm_kernel_table(prof, steps, cfg, peaks):
+    """Achieved HBM GB/s of the gather / scatter / reduce kernels of the step against the measured copy bandwidth:
+    algorithmic bytes per step / the kernel's summed device time per step."""
+    N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
+    rows = N * 2 * L                                   # token rows of q and a
+    Dp = (D + 31) // 32 * 32                           # rounded copies: rows padded to 128-byte lines
+    alg = {
+        "embed_forward_vec": rows * (4 + 8 * D),                       # id + table row in, row out
+        "embed_backward_runs": rows * (4 + 4 * D) + rows * 8 * D,      # id + dtop in, <= one RMW of the dW row
+        "tf32_round_kernel": rows * 4 * (D + Dp) + mc * D * 4 * (D + Dp),
+        "sum_kernel": 2 * 4 * N * mc * L * L,                          # loss = dot(S, dS)
+        "bias_grad_kernel": 4 * N * mc * L * L,                        # dB += sum_n dS[n]
+    }
+    peak = peaks.get("hbm_gbs", 6650.0)
+    out = {}
+    for k, b in alg.items():
+        if k in prof and prof[k][1] > 0:
+            gbs = b / (prof[k][1] / steps / 1e3) / 1e9
+            out[k] = {"algorithmic_bytes_per_step": int(b), "achieved_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 3)}
+    out["peak_gbs"] = peak
+    return out
 
 
 def roofline_for(name, rec, prof, steps, cfg, peaks, wl):

@@ -264,6 +264,21 @@ int mms_rank_accuracy_f64(mms_handle_t h, const double* a, const double* b, cons
 int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W,
                           float* QW, float* scores, int Nq, long long Nc, int K1, int K2);
 
+/* ------------------------------------------------- input formats (host) ---
+ * embed_param.weight_source: the pre-trained word-vector file EmbedLayer::LayerSetUp reads into blobs_[0]
+ * (embed_layer.cpp:46-113).  HOST memory: table_host is the (input_dim, num_output) table as the weight filler left
+ * it (blobs_[0]->mutable_cpu_data()); records overwrite rows 0.. in file order, the other rows keep their values.
+ * Format by file-name suffix as in the reference: "txt" GloVe text, "all" the fork's id/vector/word dump (header
+ * must say input_dim-1, num_output-1), anything else word2vec binary (its dimension must equal num_output).
+ * Values are stored as 32-bit floats into the first four bytes of each element -- for _f64 that is the reference's
+ * `(float*)(weight_data + w_index)` behaviour, kept for identical results.  Unlike the reference, a missing file, a
+ * malformed record or more records than rows is an error (MMS_E_INVALID), not undefined behaviour.
+ * rows_loaded (may be NULL) receives the number of records read.  No GPU is touched. */
+int mms_load_weight_source_f32(const char* path, float* table_host, long long input_dim, long long num_output,
+                               long long* rows_loaded);
+int mms_load_weight_source_f64(const char* path, double* table_host, long long input_dim, long long num_output,
+                               long long* rows_loaded);
+
 /* --------------------------------------------------------- diagnostics ------
  * The tcgen05 TF32 GEMM building block, exposed for tests and profiling:
  * C (+)= op(A) op(B), M x N x K.  a_mn = 0: A(m,k) = A[m*lda + k] (K-major), 1: A[k*lda + m]

@@ -74,6 +74,10 @@ def lib():
                 fn = getattr(L, name + suffix)
                 fn.argtypes = args
                 fn.restype = c_int
+        for suffix in ("_f32", "_f64"):
+            fn = getattr(L, "mms_load_weight_source" + suffix)
+            fn.argtypes = [ctypes.c_char_p, c_p, c_ll, c_ll, ctypes.POINTER(c_ll)]
+            fn.restype = c_int
         L.mms_rerank_scores_f32.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_ll, c_int, c_int]
         L.mms_tc_gemm_f32.argtypes = [c_p, c_p, c_ll, c_int, c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int,
                                       c_int, c_int]

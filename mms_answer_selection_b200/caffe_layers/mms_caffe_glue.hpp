@@ -107,6 +107,10 @@ MMS_OVERLOAD(rank_accuracy,
              (mms_handle_t h, const float* a, const float* b, const float* y, long long n, float* out),
              (mms_handle_t h, const double* a, const double* b, const double* y, long long n, double* out),
              (h, a, b, y, n, out))
+MMS_OVERLOAD(load_weight_source,
+             (const char* path, float* t, long long K, long long N, long long* n),
+             (const char* path, double* t, long long K, long long N, long long* n),
+             (path, t, K, N, n))
 #undef MMS_OVERLOAD
 
 }  // namespace mms

@@ -34,11 +34,16 @@ void EmbedLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vec
       shared_ptr<Filler<Dtype> > bf(GetFiller<Dtype>(ep.bias_filler()));
       bf->Fill(this->blobs_[1].get());
     }
-    // embed_param.weight_source (the fork's pre-trained-vector loader, embed_layer.cpp:46-113) is a
-    // file-format concern outside the GPU path; DESIGN.md lists it under "next".
-    CHECK(!ep.has_weight_source() || ep.weight_source().empty())
-        << "mms_b200 EmbedLayer: weight_source is not loaded by the drop-in layer; copy the vectors "
-           "into blobs()[0] (e.g. from a .caffemodel) instead.";
+    // embed_param.weight_source: pre-trained vectors over the filler's values (embed_layer.cpp:46-113); the loader is
+    // host code of the library and writes the blob's CPU copy, the table reaches the GPU through the blob's own sync
+    if (ep.has_weight_source() && !ep.weight_source().empty()) {
+      long long loaded = 0;
+      MMS_CAFFE_CHECK(mms::load_weight_source(ep.weight_source().c_str(), this->blobs_[0]->mutable_cpu_data(), K_, N_,
+                                              &loaded));
+      LOG(INFO) << "loaded " << loaded << " words from " << ep.weight_source();
+    } else {
+      LOG(INFO) << "Not loading word embeddings";
+    }
   }
   this->param_propagate_down_.resize(this->blobs_.size(), true);
 }

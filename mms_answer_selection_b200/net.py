@@ -67,6 +67,22 @@ class MMSNet(object):
         if B is not None and len(self.sim.blobs) > 1:
             self.sim.blobs[1].set_cpu_data(B)
 
+    # snapshots: Net::CopyTrainedLayersFrom (net.cpp:741-776) / Net::ToProto (:847-856) over .caffemodel files
+    def layers(self):
+        return [self.embed_q, self.embed_a, self.sim]
+
+    def CopyTrainedLayersFrom(self, source):
+        from . import formats
+        return formats.copy_trained_layers_from(self.layers(), source)
+
+    def ToProto(self, write_diff=False):
+        from . import formats
+        return formats.net_to_proto(self.layers(), name="mms", write_diff=write_diff)
+
+    def Snapshot(self, path, write_diff=False):
+        from . import formats
+        formats.write_caffemodel(path, self.ToProto(write_diff))
+
     def set_upstream_gradient(self, dS):
         """top.diff of the loss top = per-element loss weights = dLoss/dS."""
         self.S.set_cpu_diff(dS)

@@ -58,6 +58,31 @@ def test_embed(dtype, bias):
 @needs_dropin
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_embed_weight_source(dtype, tmp_path):
+    """embed_param.weight_source through LayerSetUp of the reference layer and of the drop-in layer: the same table,
+    bit for bit (embed_layer.cpp:46-113), and the same gather from it."""
+    rng = np.random.default_rng(19)
+    V, D = 31, 10
+    path = tmp_path / "vectors.bin"
+    vecs = rng.uniform(-1, 1, (V - 2, D)).astype("<f4")
+    with open(path, "wb") as f:
+        f.write(b"%d %d\n" % vecs.shape)
+        for i, v in enumerate(vecs):
+            f.write(b"w%d " % i + v.tobytes() + b"\n")
+    idx = rng.integers(0, V, size=(4, 9)).astype(dtype)
+    params = {"num_output": D, "input_dim": V, "embed.bias_term": 0, "weight_filler.type": "constant",
+              "weight_filler.value": 0.125, "weight_source": str(path)}
+    ref = refbind.RefLayer("Embed", [idx], params, dtype=dtype)
+    refbind.dropin_lib().mmsref_set_mode(1)
+    new = refbind.DropinLayer("Embed", [idx], params, dtype=dtype)
+    assert new.read("blob", 0).tobytes() == ref.read("blob", 0).tobytes()
+    ref.forward(); new.forward()
+    assert np.array_equal(ref.read("top", 0), new.read("top", 0))
+
+
+@needs_dropin
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_simcross(dtype, mode):
     rng = np.random.default_rng(5 + mode)

@@ -664,3 +664,43 @@ def test_rank_metrics_vs_oracle_with_ties(n, ngroups):
     lay.SetUp(bots, [top]); lay.Forward(bots, [top])
     ref = float(cport.auc(prob.astype(np.float64), label.astype(np.float64)))
     assert close(top.cpu_data().reshape(-1)[0], np.float32(ref))
+
+
+# ---------------------------------------------------------------- formats through the layers
+def test_embed_weight_source_and_caffemodel_round_trip(tmp_path):
+    """embed_param.weight_source fills the table in LayerSetUp (embed_layer.cpp:46-113); Net::ToProto ->
+    .caffemodel -> Net::CopyTrainedLayersFrom carries W, b, M, B into a second net, whose step is then identical."""
+    V, D, L, N, mc = 40, 12, 8, 5, 2
+    rng = np.random.default_rng(4)
+    vecs = rng.uniform(-1, 1, (V - 2, D)).astype(np.float32)
+    path = tmp_path / "glove.txt"
+    with open(path, "w") as f:
+        for i, v in enumerate(vecs):
+            f.write("w%d " % i + " ".join("%.9g" % x for x in v) + "\n")
+    lay = mms.EmbedLayer(mms.LayerParameter("Embed", embed_param=dict(
+        num_output=D, input_dim=V, bias_term=False, weight_filler=dict(type="constant", value=0.5),
+        weight_source=str(path))))
+    idx = rng.integers(0, V, (N, L)).astype(np.float32)
+    bottom, top = blob(idx, np.float32), mms.Blob(())
+    lay.SetUp([bottom], [top])
+    table = lay.blobs[0].cpu_data()
+    assert np.array_equal(table[:V - 2], vecs) and np.all(table[V - 2:] == 0.5)
+    lay.Forward([bottom], [top])
+    assert np.array_equal(top.cpu_data(), table[idx.astype(int)])
+
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    a = mms.MMSNet(N, L, D, mc, V)
+    a.set_params(d["W"], d["b"], d["M"], d["B"])
+    snap = str(tmp_path / "iter_1.caffemodel")
+    a.Snapshot(snap)
+    b = mms.MMSNet(N, L, D, mc, V)
+    assert b.CopyTrainedLayersFrom(snap) == ["embed_q", "embed_a", "sim_cross"]
+    for pa, pb in zip(a.params(), b.params()):
+        assert np.array_equal(pa.cpu_data(), pb.cpu_data())
+    for net in (a, b):
+        net.set_inputs(d["idx_q"], d["idx_a"])
+        net.set_upstream_gradient(d["dS"])
+        net.ClearParamDiffs()
+        net.ForwardBackward()
+    assert np.array_equal(a.S.cpu_data(), b.S.cpu_data())
+    assert np.array_equal(a.params()[2].cpu_diff(), b.params()[2].cpu_diff())

@@ -264,6 +264,55 @@ int mms_rank_accuracy_f64(mms_handle_t h, const double* a, const double* b, cons
 int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W,
                           float* QW, float* scores, int Nq, long long Nc, int K1, int K2);
 
+/* ------------------------------------------------------ sentence encoder ---
+ * The sentence-vector variant of the net (examples/trec_qa_w2v_mms/do_trec_qa_clean.py:352-375, 412-422):
+ * Convolution(kernel kh x D over the (N,1,L,D) embedded sentence) -> BN -> Pooling(MAX over time) -> TanH -> SimMatrix.
+ *
+ * mms_sentconv_*: ConvolutionLayer (conv_layer.cpp:25-73, base_conv_layer.cpp:257-321) for ONE input channel and a
+ *   kernel as wide as the input (kernel_w = D, stride 1, pad 0, group 1): x (N,1,L,D), W (C,1,kh,D), bias (C) or
+ *   NULL, top (N,C,L-kh+1,1).  No im2col buffer: the windows are overlapping views of x.  backward: dW and dbias
+ *   ACCUMULATE (gemm/gemv beta 1), dx is OVERWRITTEN; any of the three may be NULL (param_propagate_down /
+ *   propagate_down false).
+ * mms_pool_*: PoolingLayer (pooling_layer.cpp:80-227), method 0 MAX / 1 AVE over (NC, H, W) planes, NC = num*channels;
+ *   PH, PW are the pooled sizes the caller computed in Reshape (:80-110).  mask (NC,PH,PW) int32 is the reference's
+ *   max_idx_ (argmax as h*W+w; first maximum in scan order), required for MAX.  backward OVERWRITES dx.
+ * mms_tanh_*: TanHLayer (tanh_layer.cpp:11-37); backward takes the forward OUTPUT y.  In place is allowed.
+ * mms_bn_*: the fork's BNLayer (type "BN", bn_layer.cpp:121-257 forward, :261-384 backward) over (N,C,HW):
+ *   train != 0: batch statistics (var = E[x^2] - E[x]^2), running mean/var <- (1-bn_memory)*batch + bn_memory*running;
+ *   train == 0: the running statistics.  x_norm (N,C,HW), batch_mean (C) and batch_std (C) = sqrt(var + var_eps) are
+ *   outputs the backward reads (the reference keeps them in buffer_blob_.diff / batch_variance_; var_eps is 1e-9
+ *   there).  backward OVERWRITES dscale, dshift (may be NULL) and dx (may be NULL). */
+int mms_sentconv_forward_f32(mms_handle_t h, const float* x, const float* W, const float* bias, float* top, int N, int L,
+                             int D, int C, int kh);
+int mms_sentconv_forward_f64(mms_handle_t h, const double* x, const double* W, const double* bias, double* top, int N,
+                             int L, int D, int C, int kh);
+int mms_sentconv_backward_f32(mms_handle_t h, const float* x, const float* W, const float* dtop, float* dW, float* dbias,
+                              float* dx, int N, int L, int D, int C, int kh);
+int mms_sentconv_backward_f64(mms_handle_t h, const double* x, const double* W, const double* dtop, double* dW,
+                              double* dbias, double* dx, int N, int L, int D, int C, int kh);
+int mms_pool_forward_f32(mms_handle_t h, const float* x, float* top, int* mask, long long NC, int H, int W, int PH, int PW,
+                         int kh, int kw, int sh, int sw, int pad_h, int pad_w, int method);
+int mms_pool_forward_f64(mms_handle_t h, const double* x, double* top, int* mask, long long NC, int H, int W, int PH,
+                         int PW, int kh, int kw, int sh, int sw, int pad_h, int pad_w, int method);
+int mms_pool_backward_f32(mms_handle_t h, const float* dtop, const int* mask, float* dx, long long NC, int H, int W, int PH,
+                          int PW, int kh, int kw, int sh, int sw, int pad_h, int pad_w, int method);
+int mms_pool_backward_f64(mms_handle_t h, const double* dtop, const int* mask, double* dx, long long NC, int H, int W,
+                          int PH, int PW, int kh, int kw, int sh, int sw, int pad_h, int pad_w, int method);
+int mms_tanh_forward_f32(mms_handle_t h, const float* x, float* y, long long count);
+int mms_tanh_forward_f64(mms_handle_t h, const double* x, double* y, long long count);
+int mms_tanh_backward_f32(mms_handle_t h, const float* y, const float* dy, float* dx, long long count);
+int mms_tanh_backward_f64(mms_handle_t h, const double* y, const double* dy, double* dx, long long count);
+int mms_bn_forward_f32(mms_handle_t h, const float* x, const float* scale, const float* shift, float* run_mean,
+                       float* run_var, float* top, float* x_norm, float* batch_mean, float* batch_std, int N, int C, int HW,
+                       int train, float bn_memory, float var_eps);
+int mms_bn_forward_f64(mms_handle_t h, const double* x, const double* scale, const double* shift, double* run_mean,
+                       double* run_var, double* top, double* x_norm, double* batch_mean, double* batch_std, int N, int C,
+                       int HW, int train, double bn_memory, double var_eps);
+int mms_bn_backward_f32(mms_handle_t h, const float* dtop, const float* x_norm, const float* scale, const float* batch_std,
+                        float* dscale, float* dshift, float* dx, int N, int C, int HW);
+int mms_bn_backward_f64(mms_handle_t h, const double* dtop, const double* x_norm, const double* scale,
+                        const double* batch_std, double* dscale, double* dshift, double* dx, int N, int C, int HW);
+
 /* ------------------------------------------------- input formats (host) ---
  * embed_param.weight_source: the pre-trained word-vector file EmbedLayer::LayerSetUp reads into blobs_[0]
  * (embed_layer.cpp:46-113).  HOST memory: table_host is the (input_dim, num_output) table as the weight filler left

@@ -46,6 +46,14 @@ def _typed(real):
         "mms_rank_map_mrr": [p, p, c_ll, c_ll, p, p, c_ll, p, p],
         "mms_rank_auc": [p, p, c_ll, c_ll, p, c_ll, c_int, c_int, p],
         "mms_rank_accuracy": [p, p, p, p, c_ll, p],
+        "mms_sentconv_forward": [p, p, p, p, p, c_int, c_int, c_int, c_int, c_int],
+        "mms_sentconv_backward": [p, p, p, p, p, p, p, c_int, c_int, c_int, c_int, c_int],
+        "mms_pool_forward": [p, p, p, p, c_ll] + [c_int] * 11,
+        "mms_pool_backward": [p, p, p, p, c_ll] + [c_int] * 11,
+        "mms_tanh_forward": [p, p, p, c_ll],
+        "mms_tanh_backward": [p, p, p, p, c_ll],
+        "mms_bn_forward": [p, p, p, p, p, p, p, p, p, p, c_int, c_int, c_int, c_int, real, real],
+        "mms_bn_backward": [p, p, p, p, p, p, p, p, c_int, c_int, c_int],
         "mms_adadelta_step": [p, p, p, p, p, c_ll, real, real, real, real, real, c_int],
     }
 

@@ -310,6 +310,44 @@ int mms_check_faults(mms_handle_t h) {
                               long long count, T* out) {                                           \
     H; return mms_rank_accuracy_impl<T>(h, a, b, label, count, out);                               \
   }                                                                                                \
+  int mms_sentconv_forward_##SUF(mms_handle_t h, const T* x, const T* W, const T* bias, T* top,    \
+                                 int N, int L, int D, int C, int kh) {                             \
+    H; return mms_sentconv_forward_impl<T>(h, x, W, bias, top, N, L, D, C, kh);                    \
+  }                                                                                                \
+  int mms_sentconv_backward_##SUF(mms_handle_t h, const T* x, const T* W, const T* dtop, T* dW,    \
+                                  T* dbias, T* dx, int N, int L, int D, int C, int kh) {           \
+    H; return mms_sentconv_backward_impl<T>(h, x, W, dtop, dW, dbias, dx, N, L, D, C, kh);         \
+  }                                                                                                \
+  int mms_pool_forward_##SUF(mms_handle_t h, const T* x, T* top, int* mask, long long NC, int H_,  \
+                             int W_, int PH, int PW, int kh, int kw, int sh, int sw, int pad_h,    \
+                             int pad_w, int method) {                                              \
+    H; return mms_pool_forward_impl<T>(h, x, top, mask, NC, H_, W_, PH, PW, kh, kw, sh, sw, pad_h, \
+                                       pad_w, method);                                             \
+  }                                                                                                \
+  int mms_pool_backward_##SUF(mms_handle_t h, const T* dtop, const int* mask, T* dx, long long NC, \
+                              int H_, int W_, int PH, int PW, int kh, int kw, int sh, int sw,      \
+                              int pad_h, int pad_w, int method) {                                  \
+    H; return mms_pool_backward_impl<T>(h, dtop, mask, dx, NC, H_, W_, PH, PW, kh, kw, sh, sw,     \
+                                        pad_h, pad_w, method);                                     \
+  }                                                                                                \
+  int mms_tanh_forward_##SUF(mms_handle_t h, const T* x, T* y, long long count) {                  \
+    H; return mms_tanh_forward_impl<T>(h, x, y, count);                                            \
+  }                                                                                                \
+  int mms_tanh_backward_##SUF(mms_handle_t h, const T* y, const T* dy, T* dx, long long count) {   \
+    H; return mms_tanh_backward_impl<T>(h, y, dy, dx, count);                                      \
+  }                                                                                                \
+  int mms_bn_forward_##SUF(mms_handle_t h, const T* x, const T* scale, const T* shift,             \
+                           T* run_mean, T* run_var, T* top, T* x_norm, T* batch_mean,              \
+                           T* batch_std, int N, int C, int HW, int train, T bn_memory, T var_eps) {\
+    H; return mms_bn_forward_impl<T>(h, x, scale, shift, run_mean, run_var, top, x_norm,           \
+                                     batch_mean, batch_std, N, C, HW, train, bn_memory, var_eps);  \
+  }                                                                                                \
+  int mms_bn_backward_##SUF(mms_handle_t h, const T* dtop, const T* x_norm, const T* scale,        \
+                            const T* batch_std, T* dscale, T* dshift, T* dx, int N, int C,         \
+                            int HW) {                                                              \
+    H; return mms_bn_backward_impl<T>(h, dtop, x_norm, scale, batch_std, dscale, dshift, dx, N, C, \
+                                      HW);                                                         \
+  }                                                                                                \
   int mms_adadelta_update_##SUF(mms_handle_t h, T* g, T* hist_g, T* hist_u, long long count,       \
                                 T momentum, T delta, T local_rate) {                               \
     H; return mms_adadelta_step_impl<T>(h, nullptr, g, hist_g, hist_u, count, T(1), T(0), momentum,\

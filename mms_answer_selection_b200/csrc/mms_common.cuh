@@ -166,6 +166,27 @@ int mms_rank_auc_impl(mms_context*, const T* data, long long stride, long long o
 template <typename T>
 int mms_rank_accuracy_impl(mms_context*, const T* a, const T* b, const T* label, long long n, T* out);
 template <typename T>
+int mms_sentconv_forward_impl(mms_context*, const T* x, const T* W, const T* bias, T* top, int N, int L, int D, int C, int kh);
+template <typename T>
+int mms_sentconv_backward_impl(mms_context*, const T* x, const T* W, const T* dtop, T* dW, T* dbias, T* dx, int N, int L,
+                               int D, int C, int kh);
+template <typename T>
+int mms_pool_forward_impl(mms_context*, const T* x, T* top, int* mask, long long NC, int H, int W, int PH, int PW, int kh,
+                          int kw, int sh, int sw, int pad_h, int pad_w, int method);
+template <typename T>
+int mms_pool_backward_impl(mms_context*, const T* dtop, const int* mask, T* dx, long long NC, int H, int W, int PH, int PW,
+                           int kh, int kw, int sh, int sw, int pad_h, int pad_w, int method);
+template <typename T>
+int mms_tanh_forward_impl(mms_context*, const T* x, T* y, long long n);
+template <typename T>
+int mms_tanh_backward_impl(mms_context*, const T* y, const T* dy, T* dx, long long n);
+template <typename T>
+int mms_bn_forward_impl(mms_context*, const T* x, const T* scale, const T* shift, T* run_mean, T* run_var, T* top,
+                        T* x_norm, T* batch_mean, T* batch_std, int N, int C, int HW, int train, T memory, T eps);
+template <typename T>
+int mms_bn_backward_impl(mms_context*, const T* dtop, const T* x_norm, const T* scale, const T* batch_std, T* dscale,
+                         T* dshift, T* dx, int N, int C, int HW);
+template <typename T>
 int mms_adadelta_step_impl(mms_context*, T* data, T* diff, T* hist_g, T* hist_u, long long n, T grad_scale, T local_decay,
                            T momentum, T delta, T local_rate, int clear_diff);
 

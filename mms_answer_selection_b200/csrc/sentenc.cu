@@ -1,0 +1,567 @@
+// Sentence encoder of the sentence-vector variant of the net (reference examples/trec_qa_w2v_mms/do_trec_qa_clean.py:
+// 352-375, 412-422): Convolution(kernel 5 x D over the (N,1,L,D) embedded sentence) -> BN -> max-over-time Pooling ->
+// TanH, whose (N,K) outputs feed SimMatrix.  Reference layers: src/caffe/layers/{base_conv,conv,bn,pooling,tanh}_layer.cpp
+// (the stock Caffe classes plus the fork's own "BN").
+//
+// Sentence convolution = three contractions on the GEMM engines, with NO im2col buffer.  A window of kh token rows of a
+// sentence is kh*D consecutive floats of x, so the im2col matrix the reference materialises per sample
+// (base_conv_layer.cpp:257-321, util/im2col.cpp) is an overlapping view of x itself: row r = n*L + t starts at x + r*D.
+//   forward   Y[r][c]  = sum_i sum_d x[(r+i)*D + d] W[c][i][d]             kh reduction segments, A base + i*D
+//   dW        dW[c][i][d] += sum_r G[r][c] x[(r+i)*D + d]                   kh batches, B base + i*D, split over r
+//   dx        dx[r][d] = sum_i' sum_c G[r - (kh-1) + i'][c] W[c][kh-1-i'][d] kh reduction segments over the padded G
+// Rows r whose window crosses a sentence boundary (t > L-kh) are junk in Y and are dropped by the kernel that
+// transposes Y into Caffe's (N,C,T,1) top and adds the bias; G (the top gradient, transposed back to rows, TF32
+// rounded) holds zeros there, which is exactly the zero padding dx needs.  float blobs run on the TMA-fed tcgen05
+// engine (tc/tc_gemm_tma.cu), double blobs and MMS_MATH_FP32 on the SIMT GEMM with the same views.
+//
+// BN, pooling and TanH are HBM-bound passes: per-channel double accumulators (split over CTAs) for the statistics,
+// one thread per output for pooling, gather (no atomics) for the pooling gradients.
+#include <cfloat>
+
+#include "mms_common.cuh"
+#include "tc/tc_gemm.cuh"
+
+namespace {
+
+__device__ __forceinline__ float round_operand(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ double round_operand(double v) { return v; }
+
+inline int ew_grid(mms_context* ctx, long long n) {
+  return (int)mms_max<long long>(1, mms_min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16));
+}
+
+// top[n][c][t] = Y[(n*L + t)*ldy + c] + bias[c], t < T.  One sample per CTA pass: the T x C tile of Y goes through
+// shared memory so that both the reads (along c) and the writes (along t) are coalesced.
+template <typename T>
+__global__ void sentconv_unpack_kernel(const T* __restrict__ Y, const T* __restrict__ bias, T* __restrict__ top, int N,
+                                       int L, int Tn, int C, int ldy) {
+  extern __shared__ unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);                 // [Tn][C + 1]
+  const int ldt = C + 1;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const T* src = Y + (size_t)n * L * ldy;
+    for (int e = threadIdx.x; e < Tn * C; e += blockDim.x) {
+      const int t = e / C, c = e - t * C;
+      tile[t * ldt + c] = src[(size_t)t * ldy + c];
+    }
+    __syncthreads();
+    T* dst = top + (size_t)n * C * Tn;
+    for (int e = threadIdx.x; e < C * Tn; e += blockDim.x) {
+      const int c = e / Tn, t = e - c * Tn;
+      dst[e] = tile[t * ldt + c] + (bias ? bias[c] : T(0));
+    }
+    __syncthreads();
+  }
+}
+
+// G[(n*L + t)*ldg + c] = round(dtop[n][c][t]) for t < T, 0 for the other rows and the pad columns; and
+// dbias[c] += sum_{n,t} dtop[n][c][t] (conv_layer.cpp:47-52, accumulating) with one atomic per channel and CTA.
+template <typename T>
+__global__ void sentconv_pack_kernel(const T* __restrict__ dtop, T* __restrict__ G, T* __restrict__ dbias, int N, int L,
+                                     int Tn, int C, int ldg, int do_round) {
+  extern __shared__ unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);                 // [C][Tn + 1]
+  T* bsum = tile + (size_t)C * (Tn + 1);                     // [C]
+  const int ldt = Tn + 1;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) bsum[c] = T(0);
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    const T* src = dtop + (size_t)n * C * Tn;
+    for (int e = threadIdx.x; e < C * Tn; e += blockDim.x) {
+      const int c = e / Tn, t = e - c * Tn;
+      tile[c * ldt + t] = src[e];
+    }
+    __syncthreads();
+    if (dbias)
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        T s = T(0);
+        for (int t = 0; t < Tn; ++t) s += tile[c * ldt + t];
+        bsum[c] += s;
+      }
+    if (G) {
+      T* dst = G + (size_t)n * L * ldg;
+      for (int e = threadIdx.x; e < L * ldg; e += blockDim.x) {
+        const int t = e / ldg, c = e - t * ldg;
+        T v = (t < Tn && c < C) ? tile[c * ldt + t] : T(0);
+        dst[e] = do_round ? round_operand(v) : v;
+      }
+    }
+  }
+  __syncthreads();
+  if (dbias)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, bsum[c]);
+}
+
+// Wf[(i'*C + c)*D + d] = round(W[c][kh-1-i'][d]): the kernel rows in reverse order, channel-minor, for dx
+template <typename T>
+__global__ void sentconv_flip_weights_kernel(const T* __restrict__ W, T* __restrict__ Wf, int C, int kh, int D,
+                                             int do_round) {
+  const long long total = (long long)kh * C * D;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const int c = (int)((e / D) % C);
+    const int ip = (int)(e / ((long long)D * C));
+    const T v = W[((size_t)c * kh + (kh - 1 - ip)) * D + d];
+    Wf[e] = do_round ? round_operand(v) : v;
+  }
+}
+
+template <typename T>
+int simt_gemm(mms_context* ctx, const T* A, long long sAm, long long sAk, const T* B, long long sBk, long long sBn, T* C,
+              int ldc, long long M, int N, int K, T beta, int ksplit) {
+  SimtGemmArgs<T> g;
+  g.B = B; g.N = N; g.K = K; g.sAm = sAm; g.sAk = sAk; g.sBk = sBk; g.sBn = sBn; g.ldc = ldc;
+  g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0;
+  g.nb1 = g.nb2 = 1; g.alpha = T(1); g.beta = beta; g.ksplit = ksplit;
+  const long long step = 65535LL * 64;                      // grid.y limit of the SIMT kernel (row tiles of 64)
+  for (long long m0 = 0; m0 < M; m0 += step) {
+    g.A = A + m0 * sAm; g.C = C + m0 * ldc; g.M = (int)mms_min<long long>(step, M - m0);
+    MMS_TRY(mms_simt_gemm<T>(ctx, g));
+  }
+  return 0;
+}
+
+inline bool tensor_path(mms_context* ctx, const float*, int D) { return ctx->math == MMS_MATH_TF32 && D % 4 == 0; }
+inline bool tensor_path(mms_context*, const double*, int) { return false; }
+
+// ---- tensor-core legs (float only; the double overloads exist to keep the templates well-formed)
+int tc_conv_forward(mms_context* ctx, const float* xr, const float* Wr, float* Y, long long rows, int D, int C, int kh,
+                    int ldy) {
+  TcGemmArgs g = tc_gemm_args(xr, D, 0, Wr, (long long)kh * D, 0, Y, ldy, (int)rows, C, D);
+  g.nseg = kh; g.segA = D; g.segB = D;                       // segment i: window row i of x against W[:, i, :]
+  g.operands_tf32 = 1;
+  return mms_tc_gemm(ctx, g);
+}
+int tc_conv_forward(mms_context*, const double*, const double*, double*, long long, int, int, int, int) {
+  return MMS_E_UNSUPPORTED;
+}
+
+int tc_conv_dw(mms_context* ctx, const float* G, int ldg, const float* xr, float* dW, long long rows, int D, int C, int kh) {
+  // dW[c][i*D + d] += sum_r G[r][c] xr[(r+i)*D + d]: both operands MN-major (the reduction index r is the row), the
+  // kernel row i is a batch (B and C move by D per batch, A is shared), the reduction is split over CTAs
+  TcGemmArgs g = tc_gemm_args(G, ldg, 1, xr, D, 1, dW, (long long)kh * D, C, D, (int)rows, TC_ATOMIC);
+  g.nb2 = kh; g.sA2 = 0; g.sB2 = D; g.sC2 = D;
+  const int tiles = mms_ceil_div(C, 128) * mms_ceil_div(D, 256) * kh;
+  g.ksplit = (int)mms_max<long long>(1, mms_min<long long>(mms_ceil_div(ctx->sm_count, tiles), (rows + 511) / 512));
+  g.operands_tf32 = 1;
+  return mms_tc_gemm(ctx, g);
+}
+int tc_conv_dw(mms_context*, const double*, int, const double*, double*, long long, int, int, int) { return MMS_E_UNSUPPORTED; }
+
+int tc_conv_dx(mms_context* ctx, const float* Gpad, int ldg, const float* Wf, float* dx, long long rows, int D, int C,
+               int kh) {
+  TcGemmArgs g = tc_gemm_args(Gpad, ldg, 0, Wf, D, 1, dx, D, (int)rows, D, C);
+  g.nseg = kh; g.segA = ldg; g.segB = (long long)C * D;      // segment i': G row r - (kh-1) + i' against W[:, kh-1-i', :]
+  g.operands_tf32 = 1;
+  return mms_tc_gemm(ctx, g);
+}
+int tc_conv_dx(mms_context*, const double*, int, const double*, double*, long long, int, int, int) { return MMS_E_UNSUPPORTED; }
+
+int round_copies(mms_context* ctx, const float* x, float* xr, long long rows, int D, const float* W, float* Wr, int C,
+                 int kh) {
+  const RoundJob jobs[2] = {{x, xr, rows, D, D, D, nullptr}, {W, Wr, C, kh * D, (long long)kh * D, (long long)kh * D, nullptr}};
+  return mms_tf32_round(ctx, jobs, Wr ? 2 : 1);
+}
+int round_copies(mms_context*, const double*, double*, long long, int, const double*, double*, int, int) {
+  return MMS_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ sentence convolution
+template <typename T>
+int mms_sentconv_forward_impl(mms_context* ctx, const T* x, const T* W, const T* bias, T* top, int N, int L, int D, int C,
+                              int kh) {
+  MMS_REQUIRE(x && W && top, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && L > 0 && D > 0 && C > 0 && kh > 0 && kh <= L, MMS_E_INVALID, "bad size");
+  if (N == 0) return 0;
+  const int Tn = L - kh + 1;
+  const long long rows = (long long)N * L;
+  const long long mrows = rows - (kh - 1);                   // windows that stay inside x
+  MMS_REQUIRE(rows <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "more than 2^31 token rows");
+  const bool tc = tensor_path(ctx, x, D);
+  const int ldy = tc ? (int)tc_pad4(C) : C;
+  void* sp = nullptr;
+  const size_t n_y = (size_t)rows * ldy, n_xr = tc ? (size_t)rows * D : 0, n_wr = tc ? (size_t)C * kh * D : 0;
+  MMS_TRY(mms_scratch(ctx, sizeof(T) * (n_y + n_xr + n_wr), &sp));
+  T* Y = static_cast<T*>(sp);
+  if (tc) {
+    T* xr = Y + n_y;
+    T* Wr = xr + n_xr;
+    MMS_TRY(round_copies(ctx, x, xr, rows, D, W, Wr, C, kh));
+    MMS_TRY(tc_conv_forward(ctx, xr, Wr, Y, mrows, D, C, kh, ldy));
+  } else {
+    // Y[r][c] = sum_k x[r*D + k] W[c*kh*D + k], k < kh*D
+    MMS_TRY(simt_gemm<T>(ctx, x, D, 1, W, 1, (long long)kh * D, Y, ldy, mrows, C, kh * D, T(0), 1));
+  }
+  const size_t smem = sizeof(T) * (size_t)Tn * (C + 1);
+  MMS_REQUIRE(smem <= 200 * 1024, MMS_E_UNSUPPORTED, "output tile of one sentence exceeds shared memory");
+  static bool configured[2] = {false, false};
+  if (!configured[sizeof(T) == 8]) {
+    MMS_CUDA(cudaFuncSetAttribute(sentconv_unpack_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[sizeof(T) == 8] = true;
+  }
+  { MmsKernelScope ks_(ctx, "sentconv_unpack_kernel");
+    sentconv_unpack_kernel<T><<<mms_min(N, ctx->sm_count * 8), 256, smem, ctx->stream>>>(Y, bias, top, N, L, Tn, C, ldy); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T* dtop, T* dW, T* dbias, T* dx, int N,
+                               int L, int D, int C, int kh) {
+  MMS_REQUIRE(x && W && dtop, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && L > 0 && D > 0 && C > 0 && kh > 0 && kh <= L, MMS_E_INVALID, "bad size");
+  if (N == 0 || !(dW || dbias || dx)) return 0;
+  const int Tn = L - kh + 1;
+  const long long rows = (long long)N * L;
+  MMS_REQUIRE(rows <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "more than 2^31 token rows");
+  const bool tc = tensor_path(ctx, x, D);
+  const int ldg = tc ? (int)tc_pad4(C) : C;
+  const bool need_g = dW || dx;
+  // Gpad: kh-1 zero rows, the N*L gradient rows (row n*L + t holds dtop[n][:, t], zero for t >= T), kh-1 zero rows.
+  // G = Gpad + (kh-1) rows is the row-aligned view dW uses; Gpad itself is the shifted, zero-padded view dx uses.
+  const size_t n_g = need_g ? (size_t)(rows + 2 * (kh - 1)) * ldg : 0;
+  const size_t n_xr = (tc && dW) ? (size_t)rows * D : 0, n_wf = dx ? (size_t)kh * C * D : 0;
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(T) * (n_g + n_xr + n_wf + 4), &sp));
+  T* Gpad = static_cast<T*>(sp);
+  T* G = Gpad + (size_t)(kh - 1) * ldg;
+  T* xr = Gpad + n_g;
+  T* Wf = xr + n_xr;
+  if (need_g && kh > 1) {
+    MMS_CUDA(cudaMemsetAsync(Gpad, 0, sizeof(T) * (size_t)(kh - 1) * ldg, ctx->stream));
+    MMS_CUDA(cudaMemsetAsync(G + (size_t)rows * ldg, 0, sizeof(T) * (size_t)(kh - 1) * ldg, ctx->stream));
+  }
+  const size_t smem = sizeof(T) * ((size_t)C * (Tn + 1) + C);
+  MMS_REQUIRE(smem <= 200 * 1024, MMS_E_UNSUPPORTED, "gradient tile of one sentence exceeds shared memory");
+  static bool configured[2] = {false, false};
+  if (!configured[sizeof(T) == 8]) {
+    MMS_CUDA(cudaFuncSetAttribute(sentconv_pack_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[sizeof(T) == 8] = true;
+  }
+  { MmsKernelScope ks_(ctx, "sentconv_pack_kernel");
+    sentconv_pack_kernel<T><<<mms_min(N, ctx->sm_count * 4), 256, smem, ctx->stream>>>(
+        dtop, need_g ? G : nullptr, dbias, N, L, Tn, C, ldg, tc ? 1 : 0); }
+  MMS_LAUNCH_CHECK();
+  const long long mrows = rows - (kh - 1);
+  if (dW) {                                                  // accumulates (weight_cpu_gemm, beta = 1; conv_layer.cpp:57-60)
+    if (tc) {
+      MMS_TRY(round_copies(ctx, x, xr, rows, D, nullptr, nullptr, C, kh));
+      MMS_TRY(tc_conv_dw(ctx, G, ldg, xr, dW, mrows, D, C, kh));
+    } else {
+      const int tiles = mms_ceil_div(C, 64) * mms_ceil_div(kh * D, 64);
+      const int ksplit = (int)mms_max<long long>(1, mms_min<long long>(mms_ceil_div(2 * ctx->sm_count, tiles), (mrows + 255) / 256));
+      MMS_TRY(simt_gemm<T>(ctx, G, 1, ldg, x, D, 1, dW, kh * D, C, kh * D, (int)mrows, T(1), ksplit));
+    }
+  }
+  if (dx) {                                                  // overwrites (backward_cpu_gemm + col2im; conv_layer.cpp:62-65)
+    { MmsKernelScope ks_(ctx, "sentconv_flip_weights_kernel");
+      sentconv_flip_weights_kernel<T><<<ew_grid(ctx, (long long)kh * C * D), 256, 0, ctx->stream>>>(W, Wf, C, kh, D, tc ? 1 : 0); }
+    MMS_LAUNCH_CHECK();
+    if (tc) MMS_TRY(tc_conv_dx(ctx, Gpad, ldg, Wf, dx, rows, D, C, kh));
+    else MMS_TRY(simt_gemm<T>(ctx, Gpad, ldg, 1, Wf, D, 1, dx, D, rows, D, kh * C, T(0), 1));   // ldg == C here
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ pooling (pooling_layer.cpp)
+namespace {
+
+template <typename T>
+__global__ void pool_forward_kernel(const T* __restrict__ x, T* __restrict__ top, int* __restrict__ mask, long long total,
+                                    int H, int W, int PH, int PW, int kh, int kw, int sh, int sw, int ph_, int pw_,
+                                    int method) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int pw = (int)(e % PW), ph = (int)((e / PW) % PH);
+    const long long nc = e / ((long long)PW * PH);
+    const T* src = x + nc * H * W;
+    int hs = ph * sh - ph_, ws = pw * sw - pw_;
+    if (method == 0) {                                       // MAX: first maximum in scan order wins (:150-163)
+      const int he = min(hs + kh, H), we = min(ws + kw, W);
+      hs = max(hs, 0); ws = max(ws, 0);
+      T best = -FLT_MAX;
+      int arg = -1;
+      for (int h = hs; h < he; ++h)
+        for (int w = ws; w < we; ++w)
+          if (src[h * W + w] > best) { best = src[h * W + w]; arg = h * W + w; }
+      top[e] = best;
+      if (mask) mask[e] = arg;
+    } else {                                                 // AVE: the divisor counts the padding (:186-203)
+      int he = min(hs + kh, H + ph_), we = min(ws + kw, W + pw_);
+      const int pool_size = (he - hs) * (we - ws);
+      hs = max(hs, 0); ws = max(ws, 0); he = min(he, H); we = min(we, W);
+      T s = T(0);
+      for (int h = hs; h < he; ++h)
+        for (int w = ws; w < we; ++w) s += src[h * W + w];
+      top[e] = s / pool_size;
+    }
+  }
+}
+
+template <typename T>
+__global__ void pool_backward_kernel(const T* __restrict__ dtop, const int* __restrict__ mask, T* __restrict__ dx,
+                                     long long total, int H, int W, int PH, int PW, int kh, int kw, int sh, int sw, int ph_,
+                                     int pw_, int method) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(e % W), h = (int)((e / W) % H);
+    const long long nc = e / ((long long)W * H);
+    const int phs = (h + ph_ < kh) ? 0 : (h + ph_ - kh) / sh + 1, phe = min((h + ph_) / sh + 1, PH);
+    const int pws = (w + pw_ < kw) ? 0 : (w + pw_ - kw) / sw + 1, pwe = min((w + pw_) / sw + 1, PW);
+    const T* g = dtop + nc * PH * PW;
+    T s = T(0);
+    if (method == 0) {
+      const int* m = mask + nc * PH * PW;
+      for (int ph = phs; ph < phe; ++ph)
+        for (int pw = pws; pw < pwe; ++pw)
+          if (m[ph * PW + pw] == h * W + w) s += g[ph * PW + pw];
+    } else {
+      for (int ph = phs; ph < phe; ++ph)
+        for (int pw = pws; pw < pwe; ++pw) {
+          const int hs = ph * sh - ph_, ws = pw * sw - pw_;
+          const int he = min(hs + kh, H + ph_), we = min(ws + kw, W + pw_);
+          s += g[ph * PW + pw] / ((he - hs) * (we - ws));
+        }
+    }
+    dx[e] = s;
+  }
+}
+
+}  // namespace
+
+template <typename T>
+int mms_pool_forward_impl(mms_context* ctx, const T* x, T* top, int* mask, long long NC, int H, int W, int PH, int PW,
+                          int kh, int kw, int sh, int sw, int pad_h, int pad_w, int method) {
+  MMS_REQUIRE(x && top && (method == 1 || mask), MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(NC >= 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && pad_h >= 0 &&
+              pad_w >= 0 && (method == 0 || method == 1), MMS_E_INVALID, "bad argument");
+  const long long total = NC * PH * PW;
+  if (total == 0) return 0;
+  { MmsKernelScope ks_(ctx, "pool_forward_kernel");
+    pool_forward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, top, mask, total, H, W, PH, PW, kh, kw, sh, sw,
+                                                                       pad_h, pad_w, method); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_pool_backward_impl(mms_context* ctx, const T* dtop, const int* mask, T* dx, long long NC, int H, int W, int PH,
+                           int PW, int kh, int kw, int sh, int sw, int pad_h, int pad_w, int method) {
+  MMS_REQUIRE(dtop && dx && (method == 1 || mask), MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(NC >= 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && pad_h >= 0 &&
+              pad_w >= 0 && (method == 0 || method == 1), MMS_E_INVALID, "bad argument");
+  const long long total = NC * H * W;
+  if (total == 0) return 0;
+  { MmsKernelScope ks_(ctx, "pool_backward_kernel");
+    pool_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, mask, dx, total, H, W, PH, PW, kh, kw, sh,
+                                                                        sw, pad_h, pad_w, method); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ TanH (tanh_layer.cpp)
+namespace {
+template <typename T>
+__global__ void tanh_forward_kernel(const T* __restrict__ x, T* __restrict__ y, long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    y[e] = tanh(x[e]);
+}
+template <typename T>
+__global__ void tanh_backward_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const T t = y[e];
+    dx[e] = dy[e] * (T(1) - t * t);                          // tanh_layer.cpp:27-33
+  }
+}
+}  // namespace
+
+template <typename T>
+int mms_tanh_forward_impl(mms_context* ctx, const T* x, T* y, long long n) {
+  MMS_REQUIRE(n >= 0 && (n == 0 || (x && y)), MMS_E_INVALID, "bad argument");
+  if (n == 0) return 0;
+  { MmsKernelScope ks_(ctx, "tanh_forward_kernel");
+    tanh_forward_kernel<T><<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(x, y, n); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T>
+int mms_tanh_backward_impl(mms_context* ctx, const T* y, const T* dy, T* dx, long long n) {
+  MMS_REQUIRE(n >= 0 && (n == 0 || (y && dy && dx)), MMS_E_INVALID, "bad argument");
+  if (n == 0) return 0;
+  { MmsKernelScope ks_(ctx, "tanh_backward_kernel");
+    tanh_backward_kernel<T><<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(y, dy, dx, n); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ BN (the fork's bn_layer.cpp)
+namespace {
+
+// acc[c] += sum a, acc[C + c] += sum b over a slice of the N*HW elements of channel c; a/b chosen by MODE:
+//   0: (x, x^2)   forward statistics        1: (g, g * xn)   backward sums
+template <typename T, int MODE>
+__global__ void bn_channel_sums_kernel(const T* __restrict__ p, const T* __restrict__ q, double* __restrict__ acc, int N,
+                                       int C, int HW, int slices) {
+  const int c = blockIdx.x / slices, slice = blockIdx.x - c * slices;
+  const long long per = (long long)N * HW;
+  double s0 = 0, s1 = 0;
+  for (long long e = slice * (long long)blockDim.x + threadIdx.x; e < per; e += (long long)slices * blockDim.x) {
+    const long long n = e / HW, i = e - n * HW;
+    const size_t at = ((size_t)n * C + c) * HW + i;
+    const double a = (double)p[at];
+    s0 += a;
+    s1 += MODE == 0 ? a * a : a * (double)q[at];
+  }
+  __shared__ double red[2][32];
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    s0 = threadIdx.x < nw ? red[0][threadIdx.x] : 0.0;
+    s1 = threadIdx.x < nw ? red[1][threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (threadIdx.x == 0) { atomicAdd(acc + c, s0); atomicAdd(acc + C + c, s1); }
+  }
+}
+
+// TRAIN: mean / variance of the batch (var = E[x^2] - E[x]^2, :131-165), running statistics blended with bn_memory
+// (:168-172);  TEST: the running statistics (:177-182).  stat[c] = mean, stat[C + c] = sqrt(var + eps) (:206-210).
+template <typename T>
+__global__ void bn_finalize_stats_kernel(const double* __restrict__ acc, T* __restrict__ run_mean, T* __restrict__ run_var,
+                                         T* __restrict__ mean_out, T* __restrict__ std_out, int C, double count, int train,
+                                         T memory, T eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  T mean, var;
+  if (train) {
+    mean = static_cast<T>(acc[c] / count);
+    const T ex2 = static_cast<T>(acc[C + c] / count);
+    var = ex2 - mean * mean;
+    run_mean[c] = (T(1) - memory) * mean + memory * run_mean[c];
+    run_var[c] = (T(1) - memory) * var + memory * run_var[c];
+  } else {
+    mean = run_mean[c];
+    var = run_var[c];
+  }
+  mean_out[c] = mean;
+  std_out[c] = static_cast<T>(pow(var + eps, T(0.5)));
+}
+
+template <typename T>
+__global__ void bn_normalize_kernel(const T* __restrict__ x, const T* __restrict__ mean, const T* __restrict__ stdv,
+                                    const T* __restrict__ scale, const T* __restrict__ shift, T* __restrict__ xn,
+                                    T* __restrict__ top, long long total, int C, int HW) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((e / HW) % C);
+    const T v = (x[e] - mean[c]) / stdv[c];
+    xn[e] = v;                                               // "Saving x_norm" :225-227
+    top[e] = v * scale[c] + shift[c];
+  }
+}
+
+// dscale = sum g xn, dshift = sum g (both OVERWRITTEN, gemv beta 0, :271-292)
+template <typename T>
+__global__ void bn_param_grads_kernel(const double* __restrict__ acc, T* __restrict__ dscale, T* __restrict__ dshift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dshift) dshift[c] = static_cast<T>(acc[c]);
+  if (dscale) dscale[c] = static_cast<T>(acc[C + c]);
+}
+
+// dx = (t - (xn * sum(xn t) + sum(t)) / m) / std with t = g * scale  (:296-384)
+template <typename T>
+__global__ void bn_backward_kernel(const T* __restrict__ g, const T* __restrict__ xn, const T* __restrict__ scale,
+                                   const T* __restrict__ stdv, const double* __restrict__ acc, T* __restrict__ dx,
+                                   long long total, int C, int HW, double count) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((e / HW) % C);
+    const T sc = scale[c];
+    const T sum_t = static_cast<T>(acc[c]) * sc, sum_xt = static_cast<T>(acc[C + c]) * sc;
+    const T t = g[e] * sc;
+    dx[e] = (t - (xn[e] * sum_xt + sum_t) / static_cast<T>(count)) / stdv[c];
+  }
+}
+
+inline int bn_slices(mms_context* ctx, int C, long long per_channel) {
+  const long long want = mms_max<long long>(1, (4LL * ctx->sm_count + C - 1) / C);
+  return (int)mms_max<long long>(1, mms_min<long long>(want, (per_channel + 1023) / 1024));
+}
+
+}  // namespace
+
+template <typename T>
+int mms_bn_forward_impl(mms_context* ctx, const T* x, const T* scale, const T* shift, T* run_mean, T* run_var, T* top,
+                        T* x_norm, T* batch_mean, T* batch_std, int N, int C, int HW, int train, T memory, T eps) {
+  MMS_REQUIRE(x && scale && shift && run_mean && run_var && top && x_norm && batch_mean && batch_std, MMS_E_INVALID,
+              "null pointer");
+  MMS_REQUIRE(N > 0 && C > 0 && HW > 0, MMS_E_INVALID, "bad size");
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(double) * 2 * C, &sp));
+  double* acc = static_cast<double*>(sp);
+  if (train) {
+    MMS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, ctx->stream));
+    const int slices = bn_slices(ctx, C, (long long)N * HW);
+    { MmsKernelScope ks_(ctx, "bn_channel_sums_kernel");
+      bn_channel_sums_kernel<T, 0><<<C * slices, 256, 0, ctx->stream>>>(x, nullptr, acc, N, C, HW, slices); }
+    MMS_LAUNCH_CHECK();
+  }
+  { MmsKernelScope ks_(ctx, "bn_finalize_stats_kernel");
+    bn_finalize_stats_kernel<T><<<mms_ceil_div(C, 128), 128, 0, ctx->stream>>>(acc, run_mean, run_var, batch_mean, batch_std,
+                                                                             C, (double)N * HW, train, memory, eps); }
+  MMS_LAUNCH_CHECK();
+  const long long total = (long long)N * C * HW;
+  { MmsKernelScope ks_(ctx, "bn_normalize_kernel");
+    bn_normalize_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, batch_mean, batch_std, scale, shift, x_norm, top,
+                                                                       total, C, HW); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_bn_backward_impl(mms_context* ctx, const T* dtop, const T* x_norm, const T* scale, const T* batch_std, T* dscale,
+                         T* dshift, T* dx, int N, int C, int HW) {
+  MMS_REQUIRE(dtop && x_norm && scale && batch_std, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N > 0 && C > 0 && HW > 0, MMS_E_INVALID, "bad size");
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(double) * 2 * C, &sp));
+  double* acc = static_cast<double*>(sp);
+  MMS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, ctx->stream));
+  const int slices = bn_slices(ctx, C, (long long)N * HW);
+  { MmsKernelScope ks_(ctx, "bn_channel_sums_kernel");
+    bn_channel_sums_kernel<T, 1><<<C * slices, 256, 0, ctx->stream>>>(dtop, x_norm, acc, N, C, HW, slices); }
+  MMS_LAUNCH_CHECK();
+  if (dscale || dshift) {
+    { MmsKernelScope ks_(ctx, "bn_param_grads_kernel");
+      bn_param_grads_kernel<T><<<mms_ceil_div(C, 128), 128, 0, ctx->stream>>>(acc, dscale, dshift, C); }
+    MMS_LAUNCH_CHECK();
+  }
+  if (dx) {
+    const long long total = (long long)N * C * HW;
+    { MmsKernelScope ks_(ctx, "bn_backward_kernel");
+      bn_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, x_norm, scale, batch_std, acc, dx, total, C,
+                                                                        HW, (double)N * HW); }
+    MMS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+#define INST(T)                                                                                                       \
+  template int mms_sentconv_forward_impl<T>(mms_context*, const T*, const T*, const T*, T*, int, int, int, int, int); \
+  template int mms_sentconv_backward_impl<T>(mms_context*, const T*, const T*, const T*, T*, T*, T*, int, int, int,   \
+                                             int, int);                                                              \
+  template int mms_pool_forward_impl<T>(mms_context*, const T*, T*, int*, long long, int, int, int, int, int, int,    \
+                                        int, int, int, int, int);                                                    \
+  template int mms_pool_backward_impl<T>(mms_context*, const T*, const int*, T*, long long, int, int, int, int, int,  \
+                                         int, int, int, int, int, int);                                              \
+  template int mms_tanh_forward_impl<T>(mms_context*, const T*, T*, long long);                                       \
+  template int mms_tanh_backward_impl<T>(mms_context*, const T*, const T*, T*, long long);                            \
+  template int mms_bn_forward_impl<T>(mms_context*, const T*, const T*, const T*, T*, T*, T*, T*, T*, T*, int, int,   \
+                                      int, int, T, T);                                                               \
+  template int mms_bn_backward_impl<T>(mms_context*, const T*, const T*, const T*, const T*, T*, T*, T*, int, int, int);
+INST(float)
+INST(double)

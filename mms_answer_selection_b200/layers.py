@@ -54,6 +54,11 @@ _DEFAULTS = {
     "fm_param": dict(bias_term=True),                                   # caffe.proto:418-420
     "embed_param": dict(num_output=0, input_dim=0, bias_term=True, weight_filler=None,   # :790-803
                         bias_filler=None, weight_source=""),
+    "convolution_param": dict(num_output=0, bias_term=True, kernel_h=0, kernel_w=0, kernel_size=0, stride=1, pad=0,
+                              group=1, weight_filler=None, bias_filler=None),   # caffe.proto ConvolutionParameter
+    "pooling_param": dict(pool="MAX", kernel_h=0, kernel_w=0, kernel_size=0, stride=1, stride_h=0, stride_w=0,
+                          pad=0, pad_h=0, pad_w=0, global_pooling=False),       # caffe.proto PoolingParameter
+    "bn_param": dict(bn_memory=0.9, scale_filler=None, shift_filler=None),      # caffe.proto:484-488
     "map_param": dict(fixed_axis=1),                                    # caffe.proto:422-424
     "mrr_param": dict(fixed_axis=1),                                    # caffe.proto:426-428
     "auc_param": dict(fixed_axis=1, axis=1, ignore_label=None),         # caffe.proto:465-469
@@ -76,7 +81,7 @@ class LayerParameter(object):
             if unknown:
                 raise KeyError("unknown field(s) %s in %s" % (sorted(unknown), key))
             vals.update(given)
-            for f in ("weight_filler", "bias_filler"):
+            for f in ("weight_filler", "bias_filler", "scale_filler", "shift_filler"):
                 if f in vals:
                     vals[f] = FillerParameter(**(vals[f] or {}))
             setattr(self, key, vals)
@@ -381,6 +386,165 @@ class FMLayer(Layer):
                    bottom[0].num(), bottom[0].channels(), bottom[0].height(), int(propagate_down[0]))
 
 
+# ------------------------------------------------------------------------- sentence encoder
+class ConvolutionLayer(Layer):
+    """ConvolutionLayer (conv_layer.cpp, base_conv_layer.cpp) for the sentence convolution of the reference net
+    (do_trec_qa_clean.py:352-358, 412-416): one input channel, kernel (kernel_h x input width), stride 1, pad 0,
+    group 1.  Other geometries are the stock Caffe layer's business and are refused."""
+    exact_num_bottom = 1
+
+    def LayerSetUp(self, bottom, top):
+        cp = self.layer_param_.convolution_param
+        self.kernel_h_ = int(cp["kernel_h"] or cp["kernel_size"])
+        self.kernel_w_ = int(cp["kernel_w"] or cp["kernel_size"])
+        _check(self.kernel_h_ > 0 and self.kernel_w_ > 0, "Filter dimensions must be nonzero.")   # base_conv_layer.cpp:52-54
+        self.num_output_ = int(cp["num_output"])
+        _check(self.num_output_ > 0, "num_output must be positive")
+        self.bias_term_ = bool(cp["bias_term"])
+        _check(bottom[0].num_axes() == 4, "sentence convolution takes (N, 1, L, D) bottoms")
+        _check(bottom[0].channels() == 1 and int(cp["group"]) == 1 and int(cp["stride"]) == 1 and int(cp["pad"]) == 0
+               and self.kernel_w_ == bottom[0].width(),
+               "Convolution (mms_b200): only the sentence convolution (1 channel, kernel_w = input width, stride 1, "
+               "pad 0, group 1) runs here")
+        if not self.blobs_:                                   # base_conv_layer.cpp:137-160
+            self.blobs_.append(self._new_blob((self.num_output_, 1, self.kernel_h_, self.kernel_w_), bottom[0]))
+            _fill(self.blobs_[0], cp["weight_filler"], self.rng)
+            if self.bias_term_:
+                self.blobs_.append(self._new_blob((self.num_output_,), bottom[0]))
+                _fill(self.blobs_[1], cp["bias_filler"], self.rng)
+        self.param_propagate_down_ = [True] * len(self.blobs_)
+
+    def Reshape(self, bottom, top):
+        _check(bottom[0].height() >= self.kernel_h_, "kernel taller than the input")
+        top[0].Reshape((bottom[0].num(), self.num_output_, bottom[0].height() - self.kernel_h_ + 1, 1))
+
+    def Forward_gpu(self, bottom, top):
+        self._call("mms_sentconv_forward", _p(bottom[0]), _p(self.blobs_[0]), _p(self.blobs_[1] if self.bias_term_ else None),
+                   _p(top[0]), bottom[0].num(), bottom[0].height(), bottom[0].width(), self.num_output_, self.kernel_h_)
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        dW = self.blobs_[0] if self.param_propagate_down_[0] else None
+        db = self.blobs_[1] if (self.bias_term_ and self.param_propagate_down_[1]) else None
+        self._call("mms_sentconv_backward", _p(bottom[0]), _p(self.blobs_[0]), _p(top[0], True), _p(dW, True), _p(db, True),
+                   _p(bottom[0] if propagate_down[0] else None, True), bottom[0].num(), bottom[0].height(),
+                   bottom[0].width(), self.num_output_, self.kernel_h_)
+
+
+class PoolingLayer(Layer):
+    """PoolingLayer (pooling_layer.cpp:17-227), MAX and AVE, one top."""
+    exact_num_bottom = 1
+
+    def LayerSetUp(self, bottom, top):
+        pp = self.layer_param_.pooling_param
+        self.method_ = {"MAX": 0, "AVE": 1}.get(pp["pool"])
+        _check(self.method_ is not None, "Unknown pooling method.")           # STOCHASTIC has no CPU path in the reference
+        self.global_pooling_ = bool(pp["global_pooling"])
+        if self.global_pooling_:
+            self.kernel_h_, self.kernel_w_ = bottom[0].height(), bottom[0].width()
+        else:
+            self.kernel_h_ = int(pp["kernel_h"] or pp["kernel_size"])
+            self.kernel_w_ = int(pp["kernel_w"] or pp["kernel_size"])
+        _check(self.kernel_h_ > 0 and self.kernel_w_ > 0, "Filter dimensions cannot be zero.")
+        self.pad_h_ = int(pp["pad_h"] or pp["pad"])
+        self.pad_w_ = int(pp["pad_w"] or pp["pad"])
+        self.stride_h_ = int(pp["stride_h"] or pp["stride"])
+        self.stride_w_ = int(pp["stride_w"] or pp["stride"])
+        _check(self.pad_h_ < self.kernel_h_ and self.pad_w_ < self.kernel_w_, "pad must be smaller than the kernel")
+        self.max_idx_ = None
+
+    def Reshape(self, bottom, top):
+        _check(bottom[0].num_axes() == 4, "Input must have 4 axes, corresponding to (num, channels, height, width)")
+        H, W = bottom[0].height(), bottom[0].width()
+        if self.global_pooling_:
+            self.kernel_h_, self.kernel_w_ = H, W
+        ceil_div = lambda a, b: -(-a // b)
+        self.pooled_height_ = ceil_div(H + 2 * self.pad_h_ - self.kernel_h_, self.stride_h_) + 1   # :88-91
+        self.pooled_width_ = ceil_div(W + 2 * self.pad_w_ - self.kernel_w_, self.stride_w_) + 1
+        if self.pad_h_ or self.pad_w_:                                        # :92-103
+            if (self.pooled_height_ - 1) * self.stride_h_ >= H + self.pad_h_:
+                self.pooled_height_ -= 1
+            if (self.pooled_width_ - 1) * self.stride_w_ >= W + self.pad_w_:
+                self.pooled_width_ -= 1
+        shape = (bottom[0].num(), bottom[0].channels(), self.pooled_height_, self.pooled_width_)
+        top[0].Reshape(shape)
+        if self.method_ == 0 and (self.max_idx_ is None or tuple(self.max_idx_.shape) != shape):
+            self.max_idx_ = torch.zeros(shape, dtype=torch.int32, device=bottom[0].device)       # Blob<int> max_idx_
+
+    def _geom(self, bottom):
+        return (bottom[0].num() * bottom[0].channels(), bottom[0].height(), bottom[0].width(), self.pooled_height_,
+                self.pooled_width_, self.kernel_h_, self.kernel_w_, self.stride_h_, self.stride_w_, self.pad_h_,
+                self.pad_w_, self.method_)
+
+    def Forward_gpu(self, bottom, top):
+        mask = c_p(self.max_idx_.data_ptr()) if self.method_ == 0 else c_p(0)
+        self._call("mms_pool_forward", _p(bottom[0]), _p(top[0]), mask, *self._geom(bottom))
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        if not propagate_down[0]:
+            return
+        mask = c_p(self.max_idx_.data_ptr()) if self.method_ == 0 else c_p(0)
+        self._call("mms_pool_backward", _p(top[0], True), mask, _p(bottom[0], True), *self._geom(bottom))
+
+
+class TanHLayer(Layer):
+    """TanHLayer (tanh_layer.cpp:11-37); in place (top[0] is bottom[0]) is allowed, as in the reference."""
+    exact_num_bottom = 1
+
+    def LayerSetUp(self, bottom, top):
+        pass
+
+    def Reshape(self, bottom, top):
+        if top[0] is not bottom[0]:
+            top[0].Reshape(bottom[0].shape)                                    # NeuronLayer::Reshape
+
+    def Forward_gpu(self, bottom, top):
+        self._call("mms_tanh_forward", _p(bottom[0]), _p(top[0]), bottom[0].count())
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        if propagate_down[0]:
+            self._call("mms_tanh_backward", _p(top[0]), _p(top[0], True), _p(bottom[0], True), bottom[0].count())
+
+
+class BNLayer(Layer):
+    """The fork's batch normalisation (type "BN", bn_layer.cpp): blobs scale, shift, running mean, running variance,
+    each (1, C, 1, 1)."""
+    exact_num_bottom = 1
+
+    def LayerSetUp(self, bottom, top):
+        _check(top[0] is not bottom[0], "BN Layer does not allow in-place computation.")           # bn_layer.cpp:52-53
+        bp = self.layer_param_.bn_param
+        self.bn_memory_ = float(np.float32(bp["bn_memory"]))          # a float field of BNParameter (caffe.proto:485)
+        self.var_eps_ = 1e-9                                                                        # :63
+        C = bottom[0].channels()
+        if not self.blobs_:                                                                         # :95-117
+            for filler in (bp["scale_filler"], bp["shift_filler"]):
+                self.blobs_.append(self._new_blob((1, C, 1, 1), bottom[0]))
+                _fill(self.blobs_[-1], filler, self.rng)
+            self.blobs_.append(self._new_blob((1, C, 1, 1), bottom[0]))
+            self.blobs_.append(self._new_blob((1, C, 1, 1), bottom[0]))
+            self.blobs_[2].data.zero_(); self.blobs_[3].data.zero_()
+        self.param_propagate_down_ = [True] * len(self.blobs_)
+
+    def Reshape(self, bottom, top):
+        shape = (bottom[0].num(), bottom[0].channels(), bottom[0].height(), bottom[0].width())
+        top[0].Reshape(shape)
+        if getattr(self, "x_norm_", None) is None or tuple(self.x_norm_.shape) != shape:
+            self.x_norm_ = self._new_blob(shape, bottom[0])                    # buffer_blob_.diff in the reference
+            self.batch_mean_ = self._new_blob((shape[1],), bottom[0])
+            self.batch_std_ = self._new_blob((shape[1],), bottom[0])           # batch_variance_ after the sqrt
+
+    def Forward_gpu(self, bottom, top):
+        N, C, HW = bottom[0].num(), bottom[0].channels(), bottom[0].height() * bottom[0].width()
+        self._call("mms_bn_forward", _p(bottom[0]), _p(self.blobs_[0]), _p(self.blobs_[1]), _p(self.blobs_[2]),
+                   _p(self.blobs_[3]), _p(top[0]), _p(self.x_norm_), _p(self.batch_mean_), _p(self.batch_std_), N, C, HW,
+                   int(self.layer_param_.phase == "TRAIN"), self.real(self.bn_memory_), self.real(self.var_eps_))
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        N, C, HW = bottom[0].num(), bottom[0].channels(), bottom[0].height() * bottom[0].width()
+        self._call("mms_bn_backward", _p(top[0], True), _p(self.x_norm_), _p(self.blobs_[0]), _p(self.batch_std_),
+                   _p(self.blobs_[0], True), _p(self.blobs_[1], True), _p(bottom[0], True), N, C, HW)
+
+
 # ------------------------------------------------------------------------- ranking metrics
 class _GroupedRankLayer(Layer):
     """MAPLayer / MRRLayer (include/caffe/layers/{map,mrr}_layer.hpp): bottoms (predictions (N, C), labels (N),
@@ -469,7 +633,8 @@ class RankAccuracyLayer(Layer):
 
 _REGISTRY = {"Embed": EmbedLayer, "SimCross": SimCrossLayer, "SimMatrix": SimMatrixLayer,
              "PairRankLoss": PairRankLossLayer, "FM": FMLayer, "MAP": MAPLayer, "MRR": MRRLayer, "AUC": AUCLayer,
-             "RankAccuracy": RankAccuracyLayer}
+             "RankAccuracy": RankAccuracyLayer, "Convolution": ConvolutionLayer, "Pooling": PoolingLayer,
+             "TanH": TanHLayer, "BN": BNLayer}
 
 
 def create_layer(param):

@@ -18,7 +18,24 @@
 #include "caffe/layers/pair_rank_loss_layer.hpp"
 
 #ifndef MMS_DROPIN
+#include "caffe/layers/conv_layer.hpp"
+#include "caffe/layers/pooling_layer.hpp"
+#include "caffe/layers/tanh_layer.hpp"
 namespace caffe {
+// Convolution / Pooling / TanH are registered by creator functions in layer_factory.cpp (engine selection,
+// :38-110, :220-239), which is not compiled here (cuDNN, Python layers): register the CAFFE-engine classes directly.
+template <typename Dtype> shared_ptr<Layer<Dtype> > MmsRefConv(const LayerParameter& p) {
+  return shared_ptr<Layer<Dtype> >(new ConvolutionLayer<Dtype>(p));
+}
+template <typename Dtype> shared_ptr<Layer<Dtype> > MmsRefPool(const LayerParameter& p) {
+  return shared_ptr<Layer<Dtype> >(new PoolingLayer<Dtype>(p));
+}
+template <typename Dtype> shared_ptr<Layer<Dtype> > MmsRefTanH(const LayerParameter& p) {
+  return shared_ptr<Layer<Dtype> >(new TanHLayer<Dtype>(p));
+}
+REGISTER_LAYER_CREATOR(Convolution, MmsRefConv);
+REGISTER_LAYER_CREATOR(Pooling, MmsRefPool);
+REGISTER_LAYER_CREATOR(TanH, MmsRefTanH);
 // pair_rank_loss_layer.cpp:86-87 has no STUB_GPU, so a CPU_ONLY link lacks the
 // Forward_gpu/Backward_gpu bodies its header declares; supply the stubs here.
 STUB_GPU(PairRankLossLayer);
@@ -75,6 +92,12 @@ caffe::FillerParameter* filler_of(LayerParameter* p, const std::string& which) {
                                     : p->mutable_sim_cross_param()->mutable_bias_filler();
   } else if (t == "SimMatrix") {
     return p->mutable_sim_matrix_param()->mutable_weight_filler();
+  } else if (t == "Convolution") {
+    return which == "weight_filler" ? p->mutable_convolution_param()->mutable_weight_filler()
+                                    : p->mutable_convolution_param()->mutable_bias_filler();
+  } else if (t == "BN") {
+    return which == "scale_filler" ? p->mutable_bn_param()->mutable_scale_filler()
+                                   : p->mutable_bn_param()->mutable_shift_filler();
   } else if (t == "Embed") {
     return which == "weight_filler" ? p->mutable_embed_param()->mutable_weight_filler()
                                     : p->mutable_embed_param()->mutable_bias_filler();
@@ -138,6 +161,18 @@ int mmsref_set_i(void* h, const char* key, long long v) {
   else if (k == "embed.bias_term") s->param.mutable_embed_param()->set_bias_term(v != 0);
   else if (k == "fm.bias_term") s->param.mutable_fm_param()->set_bias_term(v != 0);
   else if (k == "phase") s->param.set_phase(v ? caffe::TEST : caffe::TRAIN);
+  else if (k == "conv.num_output") s->param.mutable_convolution_param()->set_num_output(static_cast<unsigned>(v));
+  else if (k == "conv.kernel_h") s->param.mutable_convolution_param()->set_kernel_h(static_cast<unsigned>(v));
+  else if (k == "conv.kernel_w") s->param.mutable_convolution_param()->set_kernel_w(static_cast<unsigned>(v));
+  else if (k == "conv.stride") s->param.mutable_convolution_param()->add_stride(static_cast<unsigned>(v));
+  else if (k == "conv.pad") s->param.mutable_convolution_param()->add_pad(static_cast<unsigned>(v));
+  else if (k == "conv.group") s->param.mutable_convolution_param()->set_group(static_cast<unsigned>(v));
+  else if (k == "conv.bias_term") s->param.mutable_convolution_param()->set_bias_term(v != 0);
+  else if (k == "pool.method") s->param.mutable_pooling_param()->set_pool(static_cast<caffe::PoolingParameter_PoolMethod>(v));
+  else if (k == "pool.kernel_h") s->param.mutable_pooling_param()->set_kernel_h(static_cast<unsigned>(v));
+  else if (k == "pool.kernel_w") s->param.mutable_pooling_param()->set_kernel_w(static_cast<unsigned>(v));
+  else if (k == "pool.stride_h") s->param.mutable_pooling_param()->set_stride_h(static_cast<unsigned>(v));
+  else if (k == "pool.stride_w") s->param.mutable_pooling_param()->set_stride_w(static_cast<unsigned>(v));
   else if (k == "map.fixed_axis") s->param.mutable_map_param()->set_fixed_axis(static_cast<int>(v));
   else if (k == "mrr.fixed_axis") s->param.mutable_mrr_param()->set_fixed_axis(static_cast<int>(v));
   else if (k == "auc.fixed_axis") s->param.mutable_auc_param()->set_fixed_axis(static_cast<int>(v));
@@ -153,6 +188,7 @@ int mmsref_set_f(void* h, const char* key, double v) {
   const std::string k(key);
   if (k == "margin") { s->param.mutable_pair_rank_loss_param()->set_margin(static_cast<float>(v)); return 0; }
   if (k == "loss_weight") { s->param.add_loss_weight(static_cast<float>(v)); return 0; }
+  if (k == "bn_memory") { s->param.mutable_bn_param()->set_bn_memory(static_cast<float>(v)); return 0; }
   const size_t dot = k.find('.');
   if (dot == std::string::npos) return 2;
   caffe::FillerParameter* f = filler_of(&s->param, k.substr(0, dot));

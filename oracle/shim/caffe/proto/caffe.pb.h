@@ -144,6 +144,61 @@ class AUCParameter {
   MMS_PB_OPTIONAL(int, ignore_label, 0)
 };
 
+// caffe.proto (ConvolutionParameter): the fields base_conv_layer.cpp reads
+enum ConvolutionParameter_Engine { ConvolutionParameter_Engine_DEFAULT = 0, ConvolutionParameter_Engine_CAFFE = 1,
+                                   ConvolutionParameter_Engine_CUDNN = 2 };
+class ConvolutionParameter {
+  MMS_PB_OPTIONAL(unsigned, num_output, 0u)
+  MMS_PB_OPTIONAL(bool, bias_term, true)
+  MMS_PB_REPEATED(unsigned, pad)
+  MMS_PB_REPEATED(unsigned, kernel_size)
+  MMS_PB_REPEATED(unsigned, stride)
+  MMS_PB_REPEATED(unsigned, dilation)
+  MMS_PB_OPTIONAL(unsigned, pad_h, 0u)
+  MMS_PB_OPTIONAL(unsigned, pad_w, 0u)
+  MMS_PB_OPTIONAL(unsigned, kernel_h, 0u)
+  MMS_PB_OPTIONAL(unsigned, kernel_w, 0u)
+  MMS_PB_OPTIONAL(unsigned, stride_h, 0u)
+  MMS_PB_OPTIONAL(unsigned, stride_w, 0u)
+  MMS_PB_OPTIONAL(unsigned, group, 1u)
+  MMS_PB_MESSAGE(FillerParameter, weight_filler)
+  MMS_PB_MESSAGE(FillerParameter, bias_filler)
+  MMS_PB_OPTIONAL(ConvolutionParameter_Engine, engine, ConvolutionParameter_Engine_DEFAULT)
+  MMS_PB_OPTIONAL(int, axis, 1)
+  MMS_PB_OPTIONAL(bool, force_nd_im2col, false)
+};
+
+// caffe.proto (PoolingParameter)
+enum PoolingParameter_PoolMethod { PoolingParameter_PoolMethod_MAX = 0, PoolingParameter_PoolMethod_AVE = 1,
+                                   PoolingParameter_PoolMethod_STOCHASTIC = 2 };
+class PoolingParameter {
+ public:
+  typedef PoolingParameter_PoolMethod PoolMethod;
+  MMS_PB_OPTIONAL(PoolingParameter_PoolMethod, pool, PoolingParameter_PoolMethod_MAX)
+  MMS_PB_OPTIONAL(unsigned, pad, 0u)
+  MMS_PB_OPTIONAL(unsigned, pad_h, 0u)
+  MMS_PB_OPTIONAL(unsigned, pad_w, 0u)
+  MMS_PB_OPTIONAL(unsigned, kernel_size, 0u)
+  MMS_PB_OPTIONAL(unsigned, kernel_h, 0u)
+  MMS_PB_OPTIONAL(unsigned, kernel_w, 0u)
+  MMS_PB_OPTIONAL(unsigned, stride, 1u)
+  MMS_PB_OPTIONAL(unsigned, stride_h, 0u)
+  MMS_PB_OPTIONAL(unsigned, stride_w, 0u)
+  MMS_PB_OPTIONAL(bool, global_pooling, false)
+};
+
+// caffe.proto:484-488
+class BNParameter {
+  MMS_PB_OPTIONAL(float, bn_memory, 0.9f)
+  MMS_PB_MESSAGE(FillerParameter, scale_filler)
+  MMS_PB_MESSAGE(FillerParameter, shift_filler)
+};
+
+// caffe.proto:1216-1223
+class TanHParameter {
+  MMS_PB_OPTIONAL(int, engine, 0)
+};
+
 // caffe.proto (LossParameter): ignore_label, normalize
 class LossParameter {
   MMS_PB_OPTIONAL(int, ignore_label, 0)
@@ -166,6 +221,10 @@ class LayerParameter {
   MMS_PB_MESSAGE(MAPParameter, map_param)
   MMS_PB_MESSAGE(MRRParameter, mrr_param)
   MMS_PB_MESSAGE(AUCParameter, auc_param)
+  MMS_PB_MESSAGE(ConvolutionParameter, convolution_param)
+  MMS_PB_MESSAGE(PoolingParameter, pooling_param)
+  MMS_PB_MESSAGE(BNParameter, bn_param)
+  MMS_PB_MESSAGE(TanHParameter, tanh_param)
  private:
   std::vector<BlobProto> blobs_;
  public:

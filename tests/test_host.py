@@ -32,7 +32,7 @@ def test_layer_parameter_defaults_match_caffe_proto():
     with pytest.raises(KeyError):
         LayerParameter("SimCross", sim_cross_param=dict(measure_count=2))  # the reference spells it mesure_count
     with pytest.raises(CheckError, match="Unknown layer type"):
-        create_layer(LayerParameter("Convolution"))
+        create_layer(LayerParameter("InnerProduct"))
 
 
 def test_synthetic_batch_follows_the_reference_padding():

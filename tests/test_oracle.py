@@ -360,3 +360,45 @@ def test_metric_oracles_match_compiled_reference(dtype):
             lay.forward()
             ref = lay.read("top", 0).reshape(-1)[0]
             assert ours == ref or (np.isnan(ours) and np.isnan(ref)), typ
+
+
+# ---------------------------------------------------------------- sentence encoder (conv 5xD / BN / pooling / TanH)
+def _sentenc_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sentenc_golden.npz"))
+
+
+@pytest.mark.parametrize("tag,tol", [("f32", 2e-5), ("f64", 1e-12)])
+def test_sentence_encoder_restatement_matches_reference_fixtures(tag, tol):
+    """oracle/sentenc_np.py against fixtures produced by the reference's own Convolution / BN / Pooling / TanH layers
+    (tests/golden/make_sentenc_golden.py).  Summation order differs from BLAS: 2e-5 / 1e-12 of the largest magnitude."""
+    from oracle import sentenc_np as snp
+    g = _sentenc_golden()
+    k = tag + "/"
+    err = lambda got, ref: float(np.abs(np.asarray(got, np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+    x, W, b = g[k + "conv/x"], g[k + "conv/W"], g[k + "conv/b"]
+    assert err(snp.conv_forward(x, W, b), g[k + "conv/top"]) <= tol
+    dW, db, dx = snp.conv_backward(x.astype(np.float64), W.astype(np.float64), g[k + "conv/dtop"].astype(np.float64))
+    assert err(dW + 0.5, g[k + "conv/dW"]) <= tol and err(db + 0.5, g[k + "conv/db"]) <= tol      # param diffs accumulate
+    assert err(dx, g[k + "conv/dx"]) <= tol
+    sc, sh = g[k + "bn/scale"], g[k + "bn/shift"]
+    f64 = lambda a: a.astype(np.float64)
+    mem = float(np.float32(0.9))                              # BNParameter.bn_memory is a float field (caffe.proto:485)
+    _, _, _, rm, rv = snp.bn_forward(f64(g[k + "bn/x0"]), f64(sc), f64(sh), np.zeros(sc.size), np.zeros(sc.size), memory=mem)
+    top, xn, std, rm, rv = snp.bn_forward(f64(g[k + "bn/x1"]), f64(sc), f64(sh), rm, rv, memory=mem)
+    assert err(top, g[k + "bn/top"]) <= 10 * tol
+    assert err(rm, g[k + "bn/run_mean"].reshape(-1)) <= 10 * tol and err(rv, g[k + "bn/run_var"].reshape(-1)) <= 10 * tol
+    dsc, dsh, dxb = snp.bn_backward(f64(g[k + "bn/dtop"]), xn, f64(sc), std)
+    assert err(dsc, g[k + "bn/dscale"].reshape(-1)) <= 10 * tol and err(dsh, g[k + "bn/dshift"].reshape(-1)) <= 10 * tol
+    assert err(dxb, g[k + "bn/dx"]) <= 20 * tol
+    ttop, _, _, _, _ = snp.bn_forward(f64(g[k + "bn/x0"]), f64(sc), f64(sh), rm, rv, train=False)
+    assert err(ttop, g[k + "bn/top_test"]) <= 10 * tol
+    L = x.shape[2]
+    for name, geom in (("pool_time", dict(kh=L - 4, kw=1, method="MAX")),
+                       ("pool_ave2d", dict(kh=4, kw=3, sh=2, sw=2, method="AVE")),
+                       ("pool_max2d", dict(kh=3, kw=3, sh=2, sw=1, method="MAX"))):
+        src = g[k + name + "/x"]
+        top, mask = snp.pool_forward(src, **geom)
+        assert top.shape == g[k + name + "/top"].shape and err(top, g[k + name + "/top"]) <= tol
+        assert err(snp.pool_backward(g[k + name + "/dtop"], mask, src.shape, **geom), g[k + name + "/dx"]) <= tol
+    assert err(snp.tanh_forward(g[k + "pool_time/top"]), g[k + "tanh/top"]) <= tol
+    assert err(snp.tanh_backward(g[k + "tanh/top"], g[k + "tanh/dtop"]), g[k + "tanh/dx"]) <= tol

@@ -36,6 +36,14 @@ struct mms_context {
     const void *q = nullptr, *a = nullptr, *M = nullptr;
     int N = 0, Lq = 0, La = 0, D = 0, mc = 0;
   } fwd_cache;
+  // Sentence convolution: the forward leaves the TF32-rounded copy of x at the head of the scratch buffer; with
+  // MMS_OPT_REUSE_FORWARD the backward on the same handle reads it instead of rounding x again.
+  struct SentCache {
+    bool valid = false;
+    const void* x = nullptr;
+    long long rows = 0;
+    int D = 0;
+  } sent_cache;
 };
 
 // Runs the launches issued between fork(i) and join(i) on private stream i, after everything already

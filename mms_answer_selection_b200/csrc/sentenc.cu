@@ -14,8 +14,10 @@
 // rounded) holds zeros there, which is exactly the zero padding dx needs.  float blobs run on the TMA-fed tcgen05
 // engine (tc/tc_gemm_tma.cu), double blobs and MMS_MATH_FP32 on the SIMT GEMM with the same views.
 //
-// BN, pooling and TanH are HBM-bound passes: per-channel double accumulators (split over CTAs) for the statistics,
-// one thread per output for pooling, gather (no atomics) for the pooling gradients.
+// BN, pooling and TanH are HBM-bound passes.  BN statistics: CTAs walk whole samples with coalesced reads and keep
+// per-thread double accumulators (the channel of a thread's elements is the same in every sample); the elementwise
+// passes and the max over time take one warp per (n, c) plane; general pooling is one thread per output, and gather
+// (no atomics) for its gradients.
 #include <cfloat>
 
 #include "mms_common.cuh"
@@ -185,15 +187,19 @@ int mms_sentconv_forward_impl(mms_context* ctx, const T* x, const T* W, const T*
   MMS_REQUIRE(rows <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "more than 2^31 token rows");
   const bool tc = tensor_path(ctx, x, D);
   const int ldy = tc ? (int)tc_pad4(C) : C;
+  // scratch: [xr | Y | Wr].  xr sits at the head and the request already covers what the backward needs
+  // ([xr | Gpad | Wf]), so that a backward on this handle finds the rounded x where the forward left it.
   void* sp = nullptr;
   const size_t n_y = (size_t)rows * ldy, n_xr = tc ? (size_t)rows * D : 0, n_wr = tc ? (size_t)C * kh * D : 0;
-  MMS_TRY(mms_scratch(ctx, sizeof(T) * (n_y + n_xr + n_wr), &sp));
-  T* Y = static_cast<T*>(sp);
+  const size_t n_bwd = n_xr + (size_t)(rows + 2 * (kh - 1)) * ldy + (size_t)kh * C * D + 4;
+  MMS_TRY(mms_scratch(ctx, sizeof(T) * mms_max(n_xr + n_y + n_wr, n_bwd), &sp));
+  T* xr = static_cast<T*>(sp);
+  T* Y = xr + n_xr;
   if (tc) {
-    T* xr = Y + n_y;
-    T* Wr = xr + n_xr;
+    T* Wr = Y + n_y;
     MMS_TRY(round_copies(ctx, x, xr, rows, D, W, Wr, C, kh));
     MMS_TRY(tc_conv_forward(ctx, xr, Wr, Y, mrows, D, C, kh, ldy));
+    ctx->sent_cache.valid = true; ctx->sent_cache.x = x; ctx->sent_cache.rows = rows; ctx->sent_cache.D = D;
   } else {
     // Y[r][c] = sum_k x[r*D + k] W[c*kh*D + k], k < kh*D
     MMS_TRY(simt_gemm<T>(ctx, x, D, 1, W, 1, (long long)kh * D, Y, ldy, mrows, C, kh * D, T(0), 1));
@@ -227,12 +233,16 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
   // G = Gpad + (kh-1) rows is the row-aligned view dW uses; Gpad itself is the shifted, zero-padded view dx uses.
   const size_t n_g = need_g ? (size_t)(rows + 2 * (kh - 1)) * ldg : 0;
   const size_t n_xr = (tc && dW) ? (size_t)rows * D : 0, n_wf = dx ? (size_t)kh * C * D : 0;
+  const bool cached = ctx->reuse_forward && ctx->sent_cache.valid && ctx->sent_cache.x == x &&
+                      ctx->sent_cache.rows == rows && ctx->sent_cache.D == D;
+  const void* before = ctx->scratch;
   void* sp = nullptr;
-  MMS_TRY(mms_scratch(ctx, sizeof(T) * (n_g + n_xr + n_wf + 4), &sp));
-  T* Gpad = static_cast<T*>(sp);
+  MMS_TRY(mms_scratch(ctx, sizeof(T) * (n_xr + n_g + n_wf + 4), &sp));
+  const bool have_xr = cached && sp == before && n_xr > 0;   // the forward's rounded x is still at the head
+  T* xr = static_cast<T*>(sp);
+  T* Gpad = xr + n_xr;
   T* G = Gpad + (size_t)(kh - 1) * ldg;
-  T* xr = Gpad + n_g;
-  T* Wf = xr + n_xr;
+  T* Wf = Gpad + n_g;
   if (need_g && kh > 1) {
     MMS_CUDA(cudaMemsetAsync(Gpad, 0, sizeof(T) * (size_t)(kh - 1) * ldg, ctx->stream));
     MMS_CUDA(cudaMemsetAsync(G + (size_t)rows * ldg, 0, sizeof(T) * (size_t)(kh - 1) * ldg, ctx->stream));
@@ -251,7 +261,7 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
   const long long mrows = rows - (kh - 1);
   if (dW) {                                                  // accumulates (weight_cpu_gemm, beta = 1; conv_layer.cpp:57-60)
     if (tc) {
-      MMS_TRY(round_copies(ctx, x, xr, rows, D, nullptr, nullptr, C, kh));
+      if (!have_xr) MMS_TRY(round_copies(ctx, x, xr, rows, D, nullptr, nullptr, C, kh));
       MMS_TRY(tc_conv_dw(ctx, G, ldg, xr, dW, mrows, D, C, kh));
     } else {
       const int tiles = mms_ceil_div(C, 64) * mms_ceil_div(kh * D, 64);
@@ -331,6 +341,63 @@ __global__ void pool_backward_kernel(const T* __restrict__ dtop, const int* __re
   }
 }
 
+// One window covering the whole (H, W) plane (max over time: kernel (L-kh+1) x 1): one WARP per plane, coalesced
+// reads, shuffle arg-max in which the smaller index wins a tie (= the first maximum of the reference's scan).
+template <typename T>
+__global__ void pool_plane_max_kernel(const T* __restrict__ x, T* __restrict__ top, int* __restrict__ mask, long long NC,
+                                      int HW) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < NC; p += nwarps) {
+    const T* src = x + p * HW;
+    T best = -FLT_MAX;
+    int arg = 0x7fffffff;
+    for (int i = lane; i < HW; i += 32) {
+      const T v = src[i];
+      if (v > best) { best = v; arg = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) { top[p] = best; mask[p] = arg == 0x7fffffff ? -1 : arg; }
+  }
+}
+// The same for planes whose size is a multiple of the 16-byte vector: one THREAD per plane, all of its loads in flight
+// at once (a warp-per-plane pass over 36 elements is latency-bound: two dependent loads and a shuffle chain per plane).
+template <typename T, typename V, int VL>
+__global__ void pool_plane_max_vec_kernel(const T* __restrict__ x, T* __restrict__ top, int* __restrict__ mask, long long NC,
+                                          int HW) {
+  const int nv = HW / VL;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < NC; p += (long long)gridDim.x * blockDim.x) {
+    const V* src = reinterpret_cast<const V*>(x + p * HW);
+    T best = -FLT_MAX;
+    int arg = -1;
+#pragma unroll 4
+    for (int v = 0; v < nv; ++v) {
+      const V q = src[v];
+      const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int j = 0; j < VL; ++j)
+        if (e[j] > best) { best = e[j]; arg = v * VL + j; }
+    }
+    top[p] = best;
+    mask[p] = arg;
+  }
+}
+
+template <typename T>
+__global__ void pool_plane_max_backward_kernel(const T* __restrict__ dtop, const int* __restrict__ mask, T* __restrict__ dx,
+                                               long long total, int HW) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / HW;
+    dx[e] = mask[p] == (int)(e - p * HW) ? dtop[p] : T(0);
+  }
+}
+
 }  // namespace
 
 template <typename T>
@@ -341,6 +408,21 @@ int mms_pool_forward_impl(mms_context* ctx, const T* x, T* top, int* mask, long 
               pad_w >= 0 && (method == 0 || method == 1), MMS_E_INVALID, "bad argument");
   const long long total = NC * PH * PW;
   if (total == 0) return 0;
+  if (method == 0 && PH == 1 && PW == 1 && pad_h == 0 && pad_w == 0 && kh >= H && kw >= W) {
+    const int HW = H * W, VL = 16 / (int)sizeof(T);
+    if (HW % VL == 0 && HW <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      MmsKernelScope ks_(ctx, "pool_plane_max_vec_kernel");
+      if (sizeof(T) == 4)
+        pool_plane_max_vec_kernel<T, float4, 16 / sizeof(T)><<<ew_grid(ctx, NC), 128, 0, ctx->stream>>>(x, top, mask, NC, HW);
+      else
+        pool_plane_max_vec_kernel<T, double2, 16 / sizeof(T)><<<ew_grid(ctx, NC), 128, 0, ctx->stream>>>(x, top, mask, NC, HW);
+    } else {
+      MmsKernelScope ks_(ctx, "pool_plane_max_kernel");
+      pool_plane_max_kernel<T><<<ew_grid(ctx, NC * 32), 256, 0, ctx->stream>>>(x, top, mask, NC, HW);
+    }
+    MMS_LAUNCH_CHECK();
+    return 0;
+  }
   { MmsKernelScope ks_(ctx, "pool_forward_kernel");
     pool_forward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, top, mask, total, H, W, PH, PW, kh, kw, sh, sw,
                                                                        pad_h, pad_w, method); }
@@ -356,6 +438,12 @@ int mms_pool_backward_impl(mms_context* ctx, const T* dtop, const int* mask, T* 
               pad_w >= 0 && (method == 0 || method == 1), MMS_E_INVALID, "bad argument");
   const long long total = NC * H * W;
   if (total == 0) return 0;
+  if (method == 0 && PH == 1 && PW == 1 && pad_h == 0 && pad_w == 0 && kh >= H && kw >= W) {
+    { MmsKernelScope ks_(ctx, "pool_plane_max_backward_kernel");
+      pool_plane_max_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, mask, dx, total, H * W); }
+    MMS_LAUNCH_CHECK();
+    return 0;
+  }
   { MmsKernelScope ks_(ctx, "pool_backward_kernel");
     pool_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, mask, dx, total, H, W, PH, PW, kh, kw, sh,
                                                                         sw, pad_h, pad_w, method); }
@@ -429,6 +517,51 @@ __global__ void bn_channel_sums_kernel(const T* __restrict__ p, const T* __restr
   }
 }
 
+// The same sums with coalesced reads, for C*HW <= 16 * 1024: a CTA walks whole samples (C*HW contiguous elements each);
+// element j + k*blockDim of every sample belongs to the same channel, so thread j keeps one pair of register
+// accumulators per k and the channel reduction happens once, at the end, through shared memory.
+template <typename T, int MODE>
+__global__ void bn_channel_sums_rows_kernel(const T* __restrict__ p, const T* __restrict__ q, double* __restrict__ acc, int N,
+                                            int C, int HW) {
+  extern __shared__ unsigned char bn_smem_raw[];
+  T* part = reinterpret_cast<T*>(bn_smem_raw);              // [C*HW]: the per-thread partial sums, one pass per sum
+  const int per = C * HW;
+  // per-thread partial sums over this CTA's share of the samples (a few dozen values each) stay in the blob's own
+  // type -- no FP64 or conversions in the streaming loop; everything across threads and CTAs is summed in double
+  T d0[16], d1[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) d0[k] = d1[k] = T(0);
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const size_t base = (size_t)n * per;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int e = threadIdx.x + k * blockDim.x;
+      if (e < per) {
+        const T a = p[base + e];
+        d0[k] += a;
+        d1[k] += MODE == 0 ? a * a : a * q[base + e];
+      }
+    }
+  }
+  // channel reduction without atomics on shared memory (a 36-way same-address CAS loop per element is slower than
+  // the whole streaming pass): park the partials, then thread c adds up the HW entries of channel c
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int e = threadIdx.x + k * blockDim.x;
+      if (e < per) part[e] = pass == 0 ? d0[k] : d1[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double s = 0.0;
+      for (int i = 0; i < HW; ++i) s += (double)part[c * HW + i];
+      atomicAdd(acc + pass * C + c, s);
+    }
+  }
+}
+
 // TRAIN: mean / variance of the batch (var = E[x^2] - E[x]^2, :131-165), running statistics blended with bn_memory
 // (:168-172);  TEST: the running statistics (:177-182).  stat[c] = mean, stat[C + c] = sqrt(var + eps) (:206-210).
 template <typename T>
@@ -450,6 +583,45 @@ __global__ void bn_finalize_stats_kernel(const double* __restrict__ acc, T* __re
   }
   mean_out[c] = mean;
   std_out[c] = static_cast<T>(pow(var + eps, T(0.5)));
+}
+
+// Elementwise passes walk whole (n, c) planes so that the channel -- and with it mean, std, scale, shift and the two
+// backward sums -- is fixed per plane instead of being re-derived per element: one warp per plane, lanes across HW.
+template <typename T>
+__global__ void bn_normalize_planes_kernel(const T* __restrict__ x, const T* __restrict__ mean, const T* __restrict__ stdv,
+                                           const T* __restrict__ scale, const T* __restrict__ shift, T* __restrict__ xn,
+                                           T* __restrict__ top, long long planes, int C, int HW) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < planes; p += nwarps) {
+    const int c = (int)(p % C);
+    const T m = mean[c], sd = stdv[c], sc = scale[c], sh = shift[c];
+    const size_t base = (size_t)p * HW;
+    for (int i = lane; i < HW; i += 32) {
+      const T v = (x[base + i] - m) / sd;
+      xn[base + i] = v;
+      top[base + i] = v * sc + sh;
+    }
+  }
+}
+template <typename T>
+__global__ void bn_backward_planes_kernel(const T* __restrict__ g, const T* __restrict__ xn, const T* __restrict__ scale,
+                                          const T* __restrict__ stdv, const double* __restrict__ acc, T* __restrict__ dx,
+                                          long long planes, int C, int HW, double count) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < planes; p += nwarps) {
+    const int c = (int)(p % C);
+    const T sc = scale[c], sd = stdv[c];
+    const T sum_t = static_cast<T>(acc[c]) * sc, sum_xt = static_cast<T>(acc[C + c]) * sc, cnt = static_cast<T>(count);
+    const size_t base = (size_t)p * HW;
+    for (int i = lane; i < HW; i += 32) {
+      const T t = g[base + i] * sc;
+      dx[base + i] = (t - (xn[base + i] * sum_xt + sum_t) / cnt) / sd;
+    }
+  }
 }
 
 template <typename T>
@@ -487,9 +659,23 @@ __global__ void bn_backward_kernel(const T* __restrict__ g, const T* __restrict_
   }
 }
 
-inline int bn_slices(mms_context* ctx, int C, long long per_channel) {
+template <typename T, int MODE>
+int bn_channel_sums(mms_context* ctx, const T* p, const T* q, double* acc, int N, int C, int HW) {
+  const long long per = (long long)C * HW;
+  if (per * sizeof(T) <= 48 * 1024) {
+    const int threads = (int)mms_min<long long>(1024, mms_max<long long>(128, ((per + 15) / 16 + 31) / 32 * 32));
+    { MmsKernelScope ks_(ctx, "bn_channel_sums_rows_kernel");
+      bn_channel_sums_rows_kernel<T, MODE><<<mms_min(N, ctx->sm_count * 4), threads, per * sizeof(T), ctx->stream>>>(
+          p, q, acc, N, C, HW); }
+    MMS_LAUNCH_CHECK();
+    return 0;
+  }
   const long long want = mms_max<long long>(1, (4LL * ctx->sm_count + C - 1) / C);
-  return (int)mms_max<long long>(1, mms_min<long long>(want, (per_channel + 1023) / 1024));
+  const int slices = (int)mms_max<long long>(1, mms_min<long long>(want, ((long long)N * HW + 1023) / 1024));
+  { MmsKernelScope ks_(ctx, "bn_channel_sums_kernel");
+    bn_channel_sums_kernel<T, MODE><<<C * slices, 256, 0, ctx->stream>>>(p, q, acc, N, C, HW, slices); }
+  MMS_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace
@@ -505,19 +691,22 @@ int mms_bn_forward_impl(mms_context* ctx, const T* x, const T* scale, const T* s
   double* acc = static_cast<double*>(sp);
   if (train) {
     MMS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, ctx->stream));
-    const int slices = bn_slices(ctx, C, (long long)N * HW);
-    { MmsKernelScope ks_(ctx, "bn_channel_sums_kernel");
-      bn_channel_sums_kernel<T, 0><<<C * slices, 256, 0, ctx->stream>>>(x, nullptr, acc, N, C, HW, slices); }
-    MMS_LAUNCH_CHECK();
+    MMS_TRY((bn_channel_sums<T, 0>(ctx, x, nullptr, acc, N, C, HW)));
   }
   { MmsKernelScope ks_(ctx, "bn_finalize_stats_kernel");
     bn_finalize_stats_kernel<T><<<mms_ceil_div(C, 128), 128, 0, ctx->stream>>>(acc, run_mean, run_var, batch_mean, batch_std,
                                                                              C, (double)N * HW, train, memory, eps); }
   MMS_LAUNCH_CHECK();
   const long long total = (long long)N * C * HW;
-  { MmsKernelScope ks_(ctx, "bn_normalize_kernel");
-    bn_normalize_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, batch_mean, batch_std, scale, shift, x_norm, top,
-                                                                       total, C, HW); }
+  if (HW >= 16) {
+    { MmsKernelScope ks_(ctx, "bn_normalize_planes_kernel");
+      bn_normalize_planes_kernel<T><<<ew_grid(ctx, (long long)N * C * 32), 256, 0, ctx->stream>>>(
+          x, batch_mean, batch_std, scale, shift, x_norm, top, (long long)N * C, C, HW); }
+  } else {
+    { MmsKernelScope ks_(ctx, "bn_normalize_kernel");
+      bn_normalize_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, batch_mean, batch_std, scale, shift, x_norm,
+                                                                         top, total, C, HW); }
+  }
   MMS_LAUNCH_CHECK();
   return 0;
 }
@@ -531,10 +720,7 @@ int mms_bn_backward_impl(mms_context* ctx, const T* dtop, const T* x_norm, const
   MMS_TRY(mms_scratch(ctx, sizeof(double) * 2 * C, &sp));
   double* acc = static_cast<double*>(sp);
   MMS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, ctx->stream));
-  const int slices = bn_slices(ctx, C, (long long)N * HW);
-  { MmsKernelScope ks_(ctx, "bn_channel_sums_kernel");
-    bn_channel_sums_kernel<T, 1><<<C * slices, 256, 0, ctx->stream>>>(dtop, x_norm, acc, N, C, HW, slices); }
-  MMS_LAUNCH_CHECK();
+  MMS_TRY((bn_channel_sums<T, 1>(ctx, dtop, x_norm, acc, N, C, HW)));
   if (dscale || dshift) {
     { MmsKernelScope ks_(ctx, "bn_param_grads_kernel");
       bn_param_grads_kernel<T><<<mms_ceil_div(C, 128), 128, 0, ctx->stream>>>(acc, dscale, dshift, C); }
@@ -542,9 +728,15 @@ int mms_bn_backward_impl(mms_context* ctx, const T* dtop, const T* x_norm, const
   }
   if (dx) {
     const long long total = (long long)N * C * HW;
-    { MmsKernelScope ks_(ctx, "bn_backward_kernel");
-      bn_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, x_norm, scale, batch_std, acc, dx, total, C,
-                                                                        HW, (double)N * HW); }
+    if (HW >= 16) {
+      { MmsKernelScope ks_(ctx, "bn_backward_planes_kernel");
+        bn_backward_planes_kernel<T><<<ew_grid(ctx, (long long)N * C * 32), 256, 0, ctx->stream>>>(
+            dtop, x_norm, scale, batch_std, acc, dx, (long long)N * C, C, HW, (double)N * HW); }
+    } else {
+      { MmsKernelScope ks_(ctx, "bn_backward_kernel");
+        bn_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, x_norm, scale, batch_std, acc, dx, total,
+                                                                          C, HW, (double)N * HW); }
+    }
     MMS_LAUNCH_CHECK();
   }
   return 0;

@@ -43,11 +43,13 @@ def conv_layer(dtype, C, kh, D, W, b, math=None):
     return lay
 
 
-def run_conv(dtype, x, W, b, dtop, math=None, dW0=0.5):
+def run_conv(dtype, x, W, b, dtop, math=None, dW0=0.5, reuse=False):
     C, _, kh, D = W.shape
     lay = conv_layer(dtype, C, kh, D, W, b)
     bottom, top = blob(x, dtype), mms.Blob((), dtype=dtype)
     lay.SetUp([bottom], [top])
+    if reuse:                                                # backward reads the rounded x the forward left behind
+        lay.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 1)
     if math is not None:
         lay.set_math(math)
     lay.blobs[0].set_cpu_data(W)
@@ -90,6 +92,19 @@ def test_conv_vs_restatement(N, L, D, C, kh, math, tol):
     assert err(y, snp.conv_forward(f64(x), f64(W), f64(b))) <= tol
     rW, rb, rx = snp.conv_backward(f64(x), f64(W), f64(dtop))
     assert err(dW, rW) <= tol and err(dx, rx) <= tol and err(db, rb) <= 2e-5
+
+
+def test_conv_backward_reusing_the_forward_copy_is_identical():
+    rng = np.random.default_rng(12)
+    N, L, D, C, kh = 19, 40, 300, 100, 5
+    x = rng.uniform(-1, 1, (N, 1, L, D)).astype(np.float32)
+    W = (rng.uniform(-1, 1, (C, 1, kh, D)) * 0.05).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, C).astype(np.float32)
+    dtop = rng.uniform(-1, 1, (N, C, L - kh + 1, 1)).astype(np.float32)
+    plain = run_conv(np.float32, x, W, b, dtop, dW0=0.0)
+    reused = run_conv(np.float32, x, W, b, dtop, dW0=0.0, reuse=True)
+    assert np.array_equal(plain[0], reused[0]) and np.array_equal(plain[3], reused[3])
+    assert err(reused[1], plain[1]) <= 1e-6                   # split-K atomics: order only
 
 
 def test_conv_without_bias_and_partial_propagation():
@@ -206,6 +221,26 @@ def test_pooling_padded_vs_restatement():
         top.set_cpu_diff(dtop)
         lay.Backward([top], [True], [bottom])
         assert err(bottom.cpu_diff(), snp.pool_backward(dtop, mask, x.shape, 3, 3, 2, 2, 1, 1, method)) <= 1e-14
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("H,W", [(7, 1), (36, 1), (33, 1), (5, 3)])
+def test_global_max_pooling_with_ties(dtype, H, W):
+    """One window over the whole plane (max over time), quantised values: the first maximum wins, in the warp-per-plane
+    kernel (odd plane sizes) and in the vectorised thread-per-plane kernel alike."""
+    rng = np.random.default_rng(H * 10 + W)
+    x = (np.round(rng.uniform(-1, 1, (37, 11, H, W)) * 3) / 3).astype(dtype)
+    lay = mms.create_layer(mms.LayerParameter("Pooling", dtype=dtype, pooling_param=dict(pool="MAX", kernel_h=H, kernel_w=W)))
+    bottom, top = blob(x, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bottom], [top])
+    lay.Forward([bottom], [top])
+    ref, mask = snp.pool_forward(x, H, W)
+    assert np.array_equal(top.cpu_data(), ref)
+    assert np.array_equal(lay.max_idx_.cpu().numpy().astype(np.int64), mask)
+    dtop = rng.uniform(-1, 1, ref.shape).astype(dtype)
+    top.set_cpu_diff(dtop)
+    lay.Backward([top], [True], [bottom])
+    assert np.array_equal(bottom.cpu_diff(), snp.pool_backward(dtop, mask, x.shape, H, W))
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

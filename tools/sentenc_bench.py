@@ -25,6 +25,8 @@ def run(N=8192, L=40, D=300, C=100, kh=5, iters=5):
     x, y, z, p = mms.Blob((N, 1, L, D)), mms.Blob(()), mms.Blob(()), mms.Blob(())
     x.data.copy_(torch.rand((N, 1, L, D), device="cuda", generator=g) * 0.16 - 0.08)
     conv.SetUp([x], [y]); bn.SetUp([y], [z]); pool.SetUp([z], [p]); tanh.SetUp([p], [p])
+    from mms_answer_selection_b200 import _lib
+    conv.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 1)     # Backward right after Forward on an unchanged bottom
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
@@ -63,8 +65,15 @@ def run(N=8192, L=40, D=300, C=100, kh=5, iters=5):
         "ms_per_step": step_ms, "sentences_per_sec": N / (step_ms / 1e3),
         "conv_algorithmic_tflops": flops / (conv_ms / 1e3) / 1e12 if conv_ms else None,
         "conv_gemm_only_tflops": flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None,
-        "bn_gbs": {"forward": (3 * act_bytes + act_bytes) / 1e9 / max(1e-9, sum(
-            v["ms_per_step"] for k, v in prof.items() if k in ("bn/bn_normalize_kernel",)) / 1e3)},
+        "hbm_gbs": {name: round(nbytes / 1e9 / (prof[key]["ms_per_step"] / 1e3), 1) for name, key, nbytes in (
+            ("bn_statistics (2 launches: x; dtop and x_norm)", "bn/bn_channel_sums_rows_kernel", 3 * act_bytes),
+            ("bn_normalize (x in; x_norm, top out)", "bn/bn_normalize_planes_kernel", 3 * act_bytes),
+            ("bn_backward (dtop, x_norm in; dx out)", "bn/bn_backward_planes_kernel", 3 * act_bytes),
+            ("max_over_time forward", "pool/pool_plane_max_vec_kernel", act_bytes),
+            ("max_over_time backward", "pool/pool_plane_max_backward_kernel", act_bytes),
+            ("conv top transpose + bias", "conv/sentconv_unpack_kernel", 4.0 * N * L * 104 + act_bytes),
+            ("conv gradient transpose + bias grad", "conv/sentconv_pack_kernel", 4.0 * N * L * 104 + act_bytes),
+            ("TF32 rounding of x", "conv/tf32_round_kernel", 8.0 * N * L * D)) if key in prof},
         "kernels": prof,
     }
     return out

@@ -180,6 +180,31 @@ def test_bn_golden(gold, dtype):
         mms.create_layer(mms.LayerParameter("BN", dtype=dtype)).SetUp([tb], [tb])
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-4), (np.float64, 1e-10)])
+@pytest.mark.parametrize("shape", [(5, 7, 17, 1), (4, 3, 7, 1), (3, 5, 6, 6), (300, 100, 36, 1), (2, 700, 5, 5)])
+def test_bn_vs_restatement(dtype, tol, shape):
+    """Every kernel variant (vectorised planes, warp per plane, per element; coalesced and strided statistics)."""
+    rng = np.random.default_rng(sum(shape))
+    C = shape[1]
+    x = (rng.standard_normal(shape) * rng.uniform(0.5, 2.0, (1, C, 1, 1)) + rng.uniform(-1, 1, (1, C, 1, 1))).astype(dtype)
+    sc, sh = rng.uniform(0.5, 1.5, C).astype(dtype), rng.uniform(-0.5, 0.5, C).astype(dtype)
+    dtop = rng.uniform(-1, 1, shape).astype(dtype)
+    lay = mms.create_layer(mms.LayerParameter("BN", dtype=dtype))
+    bottom, top = blob(x, dtype), mms.Blob((), dtype=dtype)
+    lay.SetUp([bottom], [top])
+    lay.blobs[0].set_cpu_data(sc.reshape(1, C, 1, 1)); lay.blobs[1].set_cpu_data(sh.reshape(1, C, 1, 1))
+    lay.Forward([bottom], [top])
+    f64 = lambda a: a.astype(np.float64)
+    rt, xn, std, rm, rv = snp.bn_forward(f64(x), f64(sc), f64(sh), np.zeros(C), np.zeros(C), memory=float(np.float32(0.9)))
+    assert err(top.cpu_data(), rt) <= tol and err(lay.blobs[2].cpu_data().reshape(-1), rm) <= tol
+    assert err(lay.blobs[3].cpu_data().reshape(-1), rv) <= tol
+    top.set_cpu_diff(dtop)
+    lay.Backward([top], [True], [bottom])
+    dsc, dsh, dx = snp.bn_backward(f64(dtop), xn, f64(sc), std)
+    assert err(lay.blobs[0].cpu_diff().reshape(-1), dsc) <= tol and err(lay.blobs[1].cpu_diff().reshape(-1), dsh) <= tol
+    assert err(bottom.cpu_diff(), dx) <= 10 * tol
+
+
 POOLS = {"pool_time": dict(pool="MAX", kernel_w=1), "pool_ave2d": dict(pool="AVE", kernel_h=4, kernel_w=3, stride=2),
          "pool_max2d": dict(pool="MAX", kernel_size=3, stride_h=2, stride_w=1)}
 

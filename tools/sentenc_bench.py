@@ -67,8 +67,8 @@ def run(N=8192, L=40, D=300, C=100, kh=5, iters=5):
         "conv_gemm_only_tflops": flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None,
         "hbm_gbs": {name: round(nbytes / 1e9 / (prof[key]["ms_per_step"] / 1e3), 1) for name, key, nbytes in (
             ("bn_statistics (2 launches: x; dtop and x_norm)", "bn/bn_channel_sums_rows_kernel", 3 * act_bytes),
-            ("bn_normalize (x in; x_norm, top out)", "bn/bn_normalize_planes_kernel", 3 * act_bytes),
-            ("bn_backward (dtop, x_norm in; dx out)", "bn/bn_backward_planes_kernel", 3 * act_bytes),
+            ("bn_normalize (x in; x_norm, top out)", "bn/bn_normalize_vec_kernel", 3 * act_bytes),
+            ("bn_backward (dtop, x_norm in; dx out)", "bn/bn_backward_vec_kernel", 3 * act_bytes),
             ("max_over_time forward", "pool/pool_plane_max_vec_kernel", act_bytes),
             ("max_over_time backward", "pool/pool_plane_max_backward_kernel", act_bytes),
             ("conv top transpose + bias", "conv/sentconv_unpack_kernel", 4.0 * N * L * 104 + act_bytes),

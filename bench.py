@@ -502,6 +502,15 @@ def extras(world, rank, flush):
                                           "one call)" % (n, nq),
                               "scores_per_sec": n / (ms / 1e3), "ms": ms, "map": float(res[0]), "mrr": float(res[1]),
                               "input_gbs": 16.0 * n / (ms / 1e3) / 1e9}
+    del prob, label, group
+    torch.cuda.empty_cache()
+    # ---- sentence encoder (sentence-vector variant): Convolution(5 x D) -> BN -> MAX over time ->
+    #      TanH, forward + backward, with per-kernel device times (tools/sentenc_bench.py)
+    import tools.sentenc_bench as sentenc_bench
+    r = sentenc_bench.run(N=8192, iters=3)
+    out["sentence_encoder"] = {k: r[k] for k in ("workload", "ms_per_step", "sentences_per_sec", "conv_algorithmic_tflops",
+                                                 "conv_gemm_only_tflops", "hbm_gbs")}
+    out["sentence_encoder"]["kernels_ms_per_step"] = {k: v["ms_per_step"] for k, v in r["kernels"].items()}
     return out
 
 

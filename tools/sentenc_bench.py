@@ -70,7 +70,7 @@ def run(N=8192, L=40, D=300, C=100, kh=5, iters=5):
             ("bn_normalize (x in; x_norm, top out)", "bn/bn_normalize_vec_kernel", 3 * act_bytes),
             ("bn_backward (dtop, x_norm in; dx out)", "bn/bn_backward_vec_kernel", 3 * act_bytes),
             ("max_over_time forward", "pool/pool_plane_max_vec_kernel", act_bytes),
-            ("max_over_time backward", "pool/pool_plane_max_backward_kernel", act_bytes),
+            ("max_over_time backward", "pool/pool_plane_max_backward_vec_kernel", act_bytes),
             ("conv top transpose + bias", "conv/sentconv_unpack_kernel", 4.0 * N * L * 104 + act_bytes),
             ("conv gradient transpose + bias grad", "conv/sentconv_pack_kernel", 4.0 * N * L * 104 + act_bytes),
             ("TF32 rounding of x", "conv/tf32_round_kernel", 8.0 * N * L * D)) if key in prof},
@@ -82,4 +82,5 @@ def run(N=8192, L=40, D=300, C=100, kh=5, iters=5):
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     C = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-    print(json.dumps(run(N=N, C=C), indent=1))
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    print(json.dumps(run(N=N, C=C, iters=iters), indent=1))

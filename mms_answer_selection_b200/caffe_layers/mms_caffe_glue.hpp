@@ -1,7 +1,7 @@
 // Glue between Caffe's Layer API and the C-ABI of libmms_b200.so (include/mms_b200.h).
 //
 // The TUs in this directory REPLACE src/caffe/layers/{embed,sim_cross,sim_matrix,
-// pair_rank_loss,fm}_layer.{cpp,cu} and {map,mrr,auc,rank_accuracy}_layer.cpp of the reference in the link (a layer type can be registered
+// pair_rank_loss,fm,bn}_layer.{cpp,cu} and {map,mrr,auc,rank_accuracy}_layer.cpp of the reference in the link (a layer type can be registered
 // once, include/caffe/layer_factory.hpp:69-70).  They are compiled against the reference's own,
 // unmodified headers, so the class declarations -- members included -- are the reference's; the
 // per-thread workspace handle therefore lives here, not in the classes.
@@ -107,6 +107,18 @@ MMS_OVERLOAD(rank_accuracy,
              (mms_handle_t h, const float* a, const float* b, const float* y, long long n, float* out),
              (mms_handle_t h, const double* a, const double* b, const double* y, long long n, double* out),
              (h, a, b, y, n, out))
+MMS_OVERLOAD(bn_forward,
+             (mms_handle_t h, const float* x, const float* sc, const float* sh, float* rm, float* rv, float* top, float* xn,
+              float* bm, float* bs, int N, int C, int HW, int train, float mem, float eps),
+             (mms_handle_t h, const double* x, const double* sc, const double* sh, double* rm, double* rv, double* top,
+              double* xn, double* bm, double* bs, int N, int C, int HW, int train, double mem, double eps),
+             (h, x, sc, sh, rm, rv, top, xn, bm, bs, N, C, HW, train, mem, eps))
+MMS_OVERLOAD(bn_backward,
+             (mms_handle_t h, const float* g, const float* xn, const float* sc, const float* bs, float* dsc, float* dsh,
+              float* dx, int N, int C, int HW),
+             (mms_handle_t h, const double* g, const double* xn, const double* sc, const double* bs, double* dsc,
+              double* dsh, double* dx, int N, int C, int HW),
+             (h, g, xn, sc, bs, dsc, dsh, dx, N, C, HW))
 MMS_OVERLOAD(load_weight_source,
              (const char* path, float* t, long long K, long long N, long long* n),
              (const char* path, double* t, long long K, long long N, long long* n),

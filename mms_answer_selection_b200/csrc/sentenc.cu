@@ -60,6 +60,27 @@ __global__ void sentconv_unpack_kernel(const T* __restrict__ Y, const T* __restr
   }
 }
 
+// Channel-major variant for the tensor-core forward, which computes Yt[c][r] (the weights on the 128-row side of the
+// MMA, 256 sentence rows per tile): top[n][c][t] = Yt[c*ldyt + n*L + t] + bias[c] is a copy of T-element runs.
+template <typename T, int VL>
+__global__ void sentconv_unpack_t_kernel(const T* __restrict__ Yt, const T* __restrict__ bias, T* __restrict__ top,
+                                         long long nvec, int L, int Tn, int C, long long ldyt) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    const long long e = v * VL, plane = e / Tn;              // plane = n*C + c; a vector never straddles two planes
+    const int t = (int)(e - plane * Tn), c = (int)(plane % C);
+    const long long n = plane / C;
+    const T b = bias ? bias[c] : T(0);
+    const T* src = Yt + (size_t)c * ldyt + n * L + t;
+    if (VL == 4) {
+      float4 q = *reinterpret_cast<const float4*>(src);
+      q.x += b; q.y += b; q.z += b; q.w += b;
+      *reinterpret_cast<float4*>(top + e) = q;
+    } else {
+      top[e] = src[0] + b;
+    }
+  }
+}
+
 // G[(n*L + t)*ldg + c] = round(dtop[n][c][t]) for t < T, 0 for the other rows and the pad columns; and
 // dbias[c] += sum_{n,t} dtop[n][c][t] (conv_layer.cpp:47-52, accumulating) with one atomic per channel and CTA.
 template <typename T>
@@ -141,6 +162,19 @@ int tc_conv_forward(mms_context* ctx, const float* xr, const float* Wr, float* Y
 int tc_conv_forward(mms_context*, const double*, const double*, double*, long long, int, int, int, int) {
   return MMS_E_UNSUPPORTED;
 }
+// The same product with the operands' roles swapped: Yt[c][r], the C filters on the MMA's 128-row side and 256
+// sentence rows per tile -- 48 KB of operands per 512 tensor-pipe cycles instead of 30 KB per 224 (the kernel is
+// bound by what an SM ingests, not by the tensor pipe), and the top then needs no transpose.
+int tc_conv_forward_t(mms_context* ctx, const float* xr, const float* Wr, float* Yt, long long rows, int D, int C, int kh,
+                      long long ldyt) {
+  TcGemmArgs g = tc_gemm_args(Wr, (long long)kh * D, 0, xr, D, 0, Yt, ldyt, C, (int)rows, D);
+  g.nseg = kh; g.segA = D; g.segB = D;
+  g.operands_tf32 = 1;
+  return mms_tc_gemm(ctx, g);
+}
+int tc_conv_forward_t(mms_context*, const double*, const double*, double*, long long, int, int, int, long long) {
+  return MMS_E_UNSUPPORTED;
+}
 
 int tc_conv_dw(mms_context* ctx, const float* G, int ldg, const float* xr, float* dW, long long rows, int D, int C, int kh) {
   // dW[c][i*D + d] += sum_r G[r][c] xr[(r+i)*D + d]: both operands MN-major (the reduction index r is the row), the
@@ -188,10 +222,12 @@ int mms_sentconv_forward_impl(mms_context* ctx, const T* x, const T* W, const T*
   MMS_REQUIRE(rows <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "more than 2^31 token rows");
   const bool tc = tensor_path(ctx, x, D);
   const int ldy = tc ? (int)tc_pad4(C) : C;
+  const long long ldyt = tc_pad4(rows);                      // tensor path: Yt[c][r], C rows of ldyt
   // scratch: [xr | Y | Wr].  xr sits at the head and the request already covers what the backward needs
   // ([xr | Gpad | Wf]), so that a backward on this handle finds the rounded x where the forward left it.
   void* sp = nullptr;
-  const size_t n_y = (size_t)rows * ldy, n_xr = tc ? (size_t)rows * D : 0, n_wr = tc ? (size_t)C * kh * D : 0;
+  const size_t n_y = tc ? (size_t)C * ldyt : (size_t)rows * ldy, n_xr = tc ? (size_t)rows * D : 0,
+               n_wr = tc ? (size_t)C * kh * D : 0;
   const size_t n_bwd = n_xr + (size_t)(rows + 2 * (kh - 1)) * ldy + (size_t)kh * C * D + 4;
   MMS_TRY(mms_scratch(ctx, sizeof(T) * mms_max(n_xr + n_y + n_wr, n_bwd), &sp));
   T* xr = static_cast<T*>(sp);
@@ -199,8 +235,15 @@ int mms_sentconv_forward_impl(mms_context* ctx, const T* x, const T* W, const T*
   if (tc) {
     T* Wr = Y + n_y;
     MMS_TRY(round_copies(ctx, x, xr, rows, D, W, Wr, C, kh));
-    MMS_TRY(tc_conv_forward(ctx, xr, Wr, Y, mrows, D, C, kh, ldy));
+    MMS_TRY(tc_conv_forward_t(ctx, xr, Wr, Y, mrows, D, C, kh, ldyt));
     ctx->sent_cache.valid = true; ctx->sent_cache.x = x; ctx->sent_cache.rows = rows; ctx->sent_cache.D = D;
+    const long long total = (long long)N * C * Tn;
+    const bool vec = sizeof(T) == 4 && Tn % 4 == 0 && L % 4 == 0 && (reinterpret_cast<uintptr_t>(top) & 15) == 0;
+    { MmsKernelScope ks_(ctx, "sentconv_unpack_t_kernel");
+      if (vec) sentconv_unpack_t_kernel<T, 4><<<ew_grid(ctx, total / 4), 256, 0, ctx->stream>>>(Y, bias, top, total / 4, L, Tn, C, ldyt);
+      else sentconv_unpack_t_kernel<T, 1><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(Y, bias, top, total, L, Tn, C, ldyt); }
+    MMS_LAUNCH_CHECK();
+    return 0;
   } else {
     // Y[r][c] = sum_k x[r*D + k] W[c*kh*D + k], k < kh*D
     MMS_TRY(simt_gemm<T>(ctx, x, D, 1, W, 1, (long long)kh * D, Y, ldy, mrows, C, kh * D, T(0), 1));

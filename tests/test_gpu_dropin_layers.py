@@ -201,6 +201,36 @@ def test_ranking_metric_layers(dtype):
         assert 0.0 < r <= 1.0 and abs(g - r) <= tol * abs(r), (typ, r, g)
 
 
+@needs_dropin
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bn(dtype):
+    """The fork's BN layer: two TRAIN forwards (running statistics blend twice), backward, against the reference's
+    own layer; float 1e-4 (var = E[x^2] - E[x]^2 cancels), double 1e-10."""
+    rng = np.random.default_rng(23)
+    x0 = (rng.standard_normal((9, 6, 12, 1)) * 0.7 + 0.3).astype(dtype)
+    x1 = (x0 * 1.5 - 0.2).astype(dtype)
+    params = {"scale_filler.type": "uniform", "scale_filler.min": 0.5, "scale_filler.max": 1.5,
+              "shift_filler.type": "uniform", "shift_filler.min": -0.2, "shift_filler.max": 0.2, "bn_memory": 0.9}
+    ref, new = pair("BN", [x0], params, dtype)
+    tol = 1e-4 if dtype == np.float32 else 1e-10
+    dz = rng.uniform(-1, 1, x0.shape).astype(dtype)
+    for l in (ref, new):
+        l.forward()
+        l.write("bottom", 0, x1)
+        l.forward()
+        l.write("top", 0, dz, diff=True)
+        for i in range(2):
+            l.write("blob", i, np.full(l.shape("blob", i), 3.0), diff=True)      # overwritten by Backward
+        l.backward([True])
+    assert scaled_err(new.read("top", 0), ref.read("top", 0)) <= tol
+    for i in (2, 3):
+        assert scaled_err(new.read("blob", i), ref.read("blob", i)) <= tol        # running mean / variance
+    for i in (0, 1):
+        assert scaled_err(new.read("blob", i, diff=True), ref.read("blob", i, diff=True)) <= tol
+    assert scaled_err(new.read("bottom", 0, diff=True), ref.read("bottom", 0, diff=True)) <= 10 * tol
+
+
 # ---- no GPU needed: the drop-in library registers the five types and has no CPU path -----------
 @needs_dropin
 def test_dropin_registers_the_reference_layer_types_and_refuses_cpu_mode():
@@ -214,7 +244,8 @@ def test_dropin_registers_the_reference_layer_types_and_refuses_cpu_mode():
                   "MAP": ([np.zeros((2, 2), np.float32)] + [np.zeros((2,), np.float32)] * 2, {}),
                   "MRR": ([np.zeros((2, 2), np.float32)] + [np.zeros((2,), np.float32)] * 2, {}),
                   "AUC": ([np.zeros((2, 2), np.float32), np.zeros((2,), np.float32)], {}),
-                  "RankAccuracy": ([np.zeros((2,), np.float32)] * 3, {})}
+                  "RankAccuracy": ([np.zeros((2,), np.float32)] * 3, {}),
+                  "BN": ([np.zeros((2, 3, 4, 1), np.float32)], {})}
         for type_, (bottoms, params) in shapes.items():
             layer = refbind.DropinLayer(type_, bottoms, params)
             with pytest.raises(refbind.RefError, match="runs on the GPU only"):

@@ -119,6 +119,46 @@ __global__ void sentconv_pack_kernel(const T* __restrict__ dtop, T* __restrict__
     for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, bsum[c]);
 }
 
+// The same with no block-wide barrier: one WARP per (sample, block of 32 channels).  A warp keeps its channel block for
+// all the samples it visits, so the bias-gradient partial sums live in registers (lane = channel) and cost one atomic
+// per lane at the end; the 32 x T tile is transposed through a private slice of shared memory under __syncwarp.
+template <typename T>
+__global__ void sentconv_pack_warp_kernel(const T* __restrict__ dtop, T* __restrict__ G, T* __restrict__ dbias, int N, int L,
+                                          int Tn, int C, int ldg, int do_round) {
+  extern __shared__ unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, ldt = Tn + 1;
+  T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)wib * 32 * ldt;      // [32][Tn + 1]
+  const int cblocks = (ldg + 31) / 32;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int stride = nwarps / cblocks;                       // samples advance by the number of complete warp groups
+  if (warp >= stride * cblocks) return;                      // leftover warps (no block-wide barrier below)
+  const int cb = warp % cblocks, c0 = cb * 32, nc = max(0, min(32, C - c0));
+  const int col = c0 + lane;
+  T bsum = T(0);
+  for (int n = warp / cblocks; n < N; n += stride) {
+    const T* src = dtop + ((size_t)n * C + c0) * Tn;          // channels c0 .. c0+nc of sample n: nc*Tn contiguous values
+    for (int e = lane; e < nc * Tn; e += 32) {
+      const int c = e / Tn;
+      tile[c * ldt + (e - c * Tn)] = src[e];
+    }
+    __syncwarp();
+    if (dbias && lane < nc) {
+      T s_ = T(0);
+      for (int t = 0; t < Tn; ++t) s_ += tile[lane * ldt + t];
+      bsum += s_;
+    }
+    if (G && col < ldg) {
+      T* dst = G + (size_t)n * L * ldg + col;
+      for (int t = 0; t < L; ++t) {
+        const T v = (t < Tn && lane < nc) ? tile[lane * ldt + t] : T(0);
+        dst[(size_t)t * ldg] = do_round ? round_operand(v) : v;
+      }
+    }
+    __syncwarp();
+  }
+  if (dbias && lane < nc) atomicAdd(dbias + col, bsum);
+}
+
 // Wf[(i'*C + c)*D + d] = round(W[c][kh-1-i'][d]): the kernel rows in reverse order, channel-minor, for dx
 template <typename T>
 __global__ void sentconv_flip_weights_kernel(const T* __restrict__ W, T* __restrict__ Wf, int C, int kh, int D,
@@ -291,6 +331,18 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
     MMS_CUDA(cudaMemsetAsync(Gpad, 0, sizeof(T) * (size_t)(kh - 1) * ldg, ctx->stream));
     MMS_CUDA(cudaMemsetAsync(G + (size_t)rows * ldg, 0, sizeof(T) * (size_t)(kh - 1) * ldg, ctx->stream));
   }
+  const int cblocks = (ldg + 31) / 32;
+  const size_t wsmem = sizeof(T) * 8 * 32 * (size_t)(Tn + 1);           // 8 warps, a 32 x (T+1) tile each
+  if (wsmem <= 48 * 1024 && (long long)ctx->sm_count * 4 * 8 >= 2 * cblocks) {
+    // every warp keeps one channel block: the warp count must be a multiple of the number of channel blocks
+    long long warps = mms_min<long long>((long long)N * cblocks, (long long)ctx->sm_count * 4 * 8);
+    warps = mms_max<long long>(cblocks, warps / cblocks * cblocks);
+    const int blocks = (int)((warps + 7) / 8);
+    { MmsKernelScope ks_(ctx, "sentconv_pack_warp_kernel");
+      sentconv_pack_warp_kernel<T><<<blocks, 256, wsmem, ctx->stream>>>(dtop, need_g ? G : nullptr, dbias, N, L, Tn, C, ldg,
+                                                                        tc ? 1 : 0); }
+    MMS_LAUNCH_CHECK();
+  } else {
   const size_t smem = sizeof(T) * ((size_t)C * (Tn + 1) + C);
   MMS_REQUIRE(smem <= 200 * 1024, MMS_E_UNSUPPORTED, "gradient tile of one sentence exceeds shared memory");
   static bool configured[2] = {false, false};
@@ -302,6 +354,7 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
     sentconv_pack_kernel<T><<<mms_min(N, ctx->sm_count * 4), 256, smem, ctx->stream>>>(
         dtop, need_g ? G : nullptr, dbias, N, L, Tn, C, ldg, tc ? 1 : 0); }
   MMS_LAUNCH_CHECK();
+  }
   const long long mrows = rows - (kh - 1);
   if (dW) {                                                  // accumulates (weight_cpu_gemm, beta = 1; conv_layer.cpp:57-60)
     if (tc) {

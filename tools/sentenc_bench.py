@@ -72,7 +72,7 @@ def run(N=8192, L=40, D=300, C=100, kh=5, iters=5):
             ("max_over_time forward", "pool/pool_plane_max_vec_kernel", act_bytes),
             ("max_over_time backward", "pool/pool_plane_max_backward_vec_kernel", act_bytes),
             ("conv top copy + bias", "conv/sentconv_unpack_t_kernel", 2 * act_bytes),
-            ("conv gradient transpose + bias grad", "conv/sentconv_pack_kernel", 4.0 * N * L * 104 + act_bytes),
+            ("conv gradient transpose + bias grad", "conv/sentconv_pack_warp_kernel", 4.0 * N * L * 104 + act_bytes),
             ("TF32 rounding of x", "conv/tf32_round_kernel", 8.0 * N * L * D)) if key in prof},
         "kernels": prof,
     }

@@ -6,9 +6,10 @@
 // Sentence convolution = three contractions on the GEMM engines, with NO im2col buffer.  A window of kh token rows of a
 // sentence is kh*D consecutive floats of x, so the im2col matrix the reference materialises per sample
 // (base_conv_layer.cpp:257-321, util/im2col.cpp) is an overlapping view of x itself: row r = n*L + t starts at x + r*D.
-//   forward   Y[r][c]  = sum_i sum_d x[(r+i)*D + d] W[c][i][d]             kh reduction segments, A base + i*D
-//   dW        dW[c][i][d] += sum_r G[r][c] x[(r+i)*D + d]                   kh batches, B base + i*D, split over r
-//   dx        dx[r][d] = sum_i' sum_c G[r - (kh-1) + i'][c] W[c][kh-1-i'][d] kh reduction segments over the padded G
+//   forward   Yt[c][r] = sum_k W[c][k] x[r*D + k],  k < kh*D          rows of the x operand overlap (ld D < kh*D)
+//   dW        dW[c][k] += sum_r G[r][c] x[r*D + k]                     the same view as the MN-major operand, split over r
+//   dx        dx[r][d] = sum_k Gpad[r*ldg + k] Wf[k][d],  k < kh*ldg    kh consecutive rows of the padded gradient
+// TMA tensor maps take overlapping rows as they are (tools/tma_overlap_test.py), so each product is ONE plain GEMM.
 // Rows r whose window crosses a sentence boundary (t > L-kh) are junk in Y and are dropped by the kernel that
 // transposes Y into Caffe's (N,C,T,1) top and adds the bias; G (the top gradient, transposed back to rows, TF32
 // rounded) holds zeros there, which is exactly the zero padding dx needs.  float blobs run on the TMA-fed tcgen05
@@ -159,16 +160,16 @@ __global__ void sentconv_pack_warp_kernel(const T* __restrict__ dtop, T* __restr
   if (dbias && lane < nc) atomicAdd(dbias + col, bsum);
 }
 
-// Wf[(i'*C + c)*D + d] = round(W[c][kh-1-i'][d]): the kernel rows in reverse order, channel-minor, for dx
+// Wf[(i'*Cp + c)*D + d] = round(W[c][kh-1-i'][d]): the kernel rows in reverse order, channel-minor, for dx
 template <typename T>
-__global__ void sentconv_flip_weights_kernel(const T* __restrict__ W, T* __restrict__ Wf, int C, int kh, int D,
+__global__ void sentconv_flip_weights_kernel(const T* __restrict__ W, T* __restrict__ Wf, int C, int Cp, int kh, int D,
                                              int do_round) {
-  const long long total = (long long)kh * C * D;
+  const long long total = (long long)kh * Cp * D;            // Cp >= C rows per kernel row, the extra ones zero
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int d = (int)(e % D);
-    const int c = (int)((e / D) % C);
-    const int ip = (int)(e / ((long long)D * C));
-    const T v = W[((size_t)c * kh + (kh - 1 - ip)) * D + d];
+    const int c = (int)((e / D) % Cp);
+    const int ip = (int)(e / ((long long)D * Cp));
+    const T v = c < C ? W[((size_t)c * kh + (kh - 1 - ip)) * D + d] : T(0);
     Wf[e] = do_round ? round_operand(v) : v;
   }
 }
@@ -207,8 +208,9 @@ int tc_conv_forward(mms_context*, const double*, const double*, double*, long lo
 // bound by what an SM ingests, not by the tensor pipe), and the top then needs no transpose.
 int tc_conv_forward_t(mms_context* ctx, const float* xr, const float* Wr, float* Yt, long long rows, int D, int C, int kh,
                       long long ldyt) {
-  TcGemmArgs g = tc_gemm_args(Wr, (long long)kh * D, 0, xr, D, 0, Yt, ldyt, C, (int)rows, D);
-  g.nseg = kh; g.segA = D; g.segB = D;
+  // B(n = r, k) = xr[r*D + k], k < kh*D: rows of the operand overlap (leading dimension D, row length kh*D) -- the
+  // tensor map takes that as it is (tools/tma_overlap_test.py), so the kh window rows are one contiguous reduction
+  TcGemmArgs g = tc_gemm_args(Wr, (long long)kh * D, 0, xr, D, 0, Yt, ldyt, C, (int)rows, kh * D);
   g.operands_tf32 = 1;
   return mms_tc_gemm(ctx, g);
 }
@@ -218,10 +220,10 @@ int tc_conv_forward_t(mms_context*, const double*, const double*, double*, long 
 
 int tc_conv_dw(mms_context* ctx, const float* G, int ldg, const float* xr, float* dW, long long rows, int D, int C, int kh) {
   // dW[c][i*D + d] += sum_r G[r][c] xr[(r+i)*D + d]: both operands MN-major (the reduction index r is the row), the
-  // kernel row i is a batch (B and C move by D per batch, A is shared), the reduction is split over CTAs
-  TcGemmArgs g = tc_gemm_args(G, ldg, 1, xr, D, 1, dW, (long long)kh * D, C, D, (int)rows, TC_ATOMIC);
-  g.nb2 = kh; g.sA2 = 0; g.sB2 = D; g.sC2 = D;
-  const int tiles = mms_ceil_div(C, 128) * mms_ceil_div(D, 256) * kh;
+  // reduction is split over CTAs
+  // B(n, k = r) = xr[r*D + n], n < kh*D: the overlapping view again, so all kh kernel rows are columns of ONE product
+  TcGemmArgs g = tc_gemm_args(G, ldg, 1, xr, D, 1, dW, (long long)kh * D, C, kh * D, (int)rows, TC_ATOMIC);
+  const int tiles = mms_ceil_div(C, 128) * mms_ceil_div(kh * D, 256);
   // one full wave and no more: 150 tiles on 148 persistent CTAs take as long as 296 (measured: 0.64 ms with 15 splits)
   g.ksplit = (int)mms_max<long long>(1, mms_min<long long>(ctx->sm_count / tiles, (rows + 511) / 512));
   g.operands_tf32 = 1;
@@ -231,8 +233,9 @@ int tc_conv_dw(mms_context*, const double*, int, const double*, double*, long lo
 
 int tc_conv_dx(mms_context* ctx, const float* Gpad, int ldg, const float* Wf, float* dx, long long rows, int D, int C,
                int kh) {
-  TcGemmArgs g = tc_gemm_args(Gpad, ldg, 0, Wf, D, 1, dx, D, (int)rows, D, C);
-  g.nseg = kh; g.segA = ldg; g.segB = (long long)C * D;      // segment i': G row r - (kh-1) + i' against W[:, kh-1-i', :]
+  // A(m = r, k) = Gpad[r*ldg + k], k < kh*ldg: kh consecutive gradient rows are one contiguous reduction (overlapping
+  // rows again); Wf holds ldg rows per kernel row, the pad rows zero like G's pad columns
+  TcGemmArgs g = tc_gemm_args(Gpad, ldg, 0, Wf, D, 1, dx, D, (int)rows, D, kh * ldg);
   g.operands_tf32 = 1;
   return mms_tc_gemm(ctx, g);
 }
@@ -268,7 +271,7 @@ int mms_sentconv_forward_impl(mms_context* ctx, const T* x, const T* W, const T*
   void* sp = nullptr;
   const size_t n_y = tc ? (size_t)C * ldyt : (size_t)rows * ldy, n_xr = tc ? (size_t)rows * D : 0,
                n_wr = tc ? (size_t)C * kh * D : 0;
-  const size_t n_bwd = n_xr + (size_t)(rows + 2 * (kh - 1)) * ldy + (size_t)kh * C * D + 4;
+  const size_t n_bwd = n_xr + (size_t)(rows + 2 * (kh - 1)) * ldy + (size_t)kh * ldy * D + 4;
   MMS_TRY(mms_scratch(ctx, sizeof(T) * mms_max(n_xr + n_y + n_wr, n_bwd), &sp));
   T* xr = static_cast<T*>(sp);
   T* Y = xr + n_xr;
@@ -316,7 +319,7 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
   // Gpad: kh-1 zero rows, the N*L gradient rows (row n*L + t holds dtop[n][:, t], zero for t >= T), kh-1 zero rows.
   // G = Gpad + (kh-1) rows is the row-aligned view dW uses; Gpad itself is the shifted, zero-padded view dx uses.
   const size_t n_g = need_g ? (size_t)(rows + 2 * (kh - 1)) * ldg : 0;
-  const size_t n_xr = (tc && dW) ? (size_t)rows * D : 0, n_wf = dx ? (size_t)kh * C * D : 0;
+  const size_t n_xr = (tc && dW) ? (size_t)rows * D : 0, n_wf = dx ? (size_t)kh * ldg * D : 0;
   const bool cached = ctx->reuse_forward && ctx->sent_cache.valid && ctx->sent_cache.x == x &&
                       ctx->sent_cache.rows == rows && ctx->sent_cache.D == D;
   const void* before = ctx->scratch;
@@ -368,7 +371,8 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
   }
   if (dx) {                                                  // overwrites (backward_cpu_gemm + col2im; conv_layer.cpp:62-65)
     { MmsKernelScope ks_(ctx, "sentconv_flip_weights_kernel");
-      sentconv_flip_weights_kernel<T><<<ew_grid(ctx, (long long)kh * C * D), 256, 0, ctx->stream>>>(W, Wf, C, kh, D, tc ? 1 : 0); }
+      sentconv_flip_weights_kernel<T><<<ew_grid(ctx, (long long)kh * ldg * D), 256, 0, ctx->stream>>>(W, Wf, C, ldg, kh, D,
+                                                                                                 tc ? 1 : 0); }
     MMS_LAUNCH_CHECK();
     if (tc) MMS_TRY(tc_conv_dx(ctx, Gpad, ldg, Wf, dx, rows, D, C, kh));
     else MMS_TRY(simt_gemm<T>(ctx, Gpad, ldg, 1, Wf, D, 1, dx, D, rows, D, kh * C, T(0), 1));   // ldg == C here

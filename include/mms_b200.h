@@ -62,7 +62,9 @@ enum {
                                 sizes and no other call used the workspace since.  The caller promises that
                                 q, a and M are unchanged between that forward and this backward -- which is
                                 how Net::ForwardBackward and GradientChecker drive a layer.  Default 0
-                                (stateless: backward recomputes, like the reference, sim_cross_layer.cpp:296). */
+                                (stateless: backward recomputes, like the reference, sim_cross_layer.cpp:296).
+                                The same promise lets mms_simmatrix_backward reuse the rounded q and W, and
+                                mms_sentconv_backward the rounded x, of the last forward on the handle. */
   MMS_OPT_CONCURRENCY = 6    /* 1 (default): independent contractions inside one call may run on private
                                 streams, joined back before the call's last launch on the handle's stream. */
 };

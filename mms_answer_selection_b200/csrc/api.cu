@@ -20,6 +20,7 @@ void mms_set_error(const char* fmt, ...) {
 int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
   ctx->fwd_cache.valid = false;        // whoever asks for the scratch buffer is about to overwrite it
   ctx->sent_cache.valid = false;
+  ctx->simmat_cache.valid = false;
   if (bytes > ctx->scratch_bytes) {
     if (ctx->scratch) {
       // earlier launches on the stream may still read the old buffer

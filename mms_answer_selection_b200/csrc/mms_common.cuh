@@ -44,6 +44,12 @@ struct mms_context {
     long long rows = 0;
     int D = 0;
   } sent_cache;
+  // SimMatrix: likewise the rounded q and W ([qr | Wr] at the head of the scratch buffer)
+  struct SimMatCache {
+    bool valid = false;
+    const void *q = nullptr, *W = nullptr;
+    int N = 0, K1 = 0, K2 = 0;
+  } simmat_cache;
 };
 
 // Runs the launches issued between fork(i) and join(i) on private stream i, after everything already

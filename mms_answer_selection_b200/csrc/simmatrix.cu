@@ -69,32 +69,54 @@ inline int ew_grid(mms_context* ctx, long long n) {
 inline bool use_tc(mms_context* ctx, const float*) { return ctx->math == MMS_MATH_TF32; }
 inline bool use_tc(mms_context*, const double*) { return false; }
 
+// scratch layout shared by forward and backward: [qr | Wr | ar | as]; the forward already asks for all of it, so a
+// backward on the same handle finds qr and Wr in place (MMS_OPT_REUSE_FORWARD) and rounds only the answer side
+inline size_t tc_scratch_floats(int N, long long K1p, long long K2p, int K1) {
+  return (size_t)N * K1p + (size_t)K1 * K2p + 2 * (size_t)N * K2p;
+}
+
 inline int tc_forward(mms_context* ctx, const float* q, const float* W, float* Tm, int N, int K1, int K2) {
   const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
   void* sp = nullptr;
-  MMS_TRY(mms_scratch(ctx, sizeof(float) * ((size_t)N * K1p + (size_t)K1 * K2p), &sp));
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * tc_scratch_floats(N, K1p, K2p, K1), &sp));
   float* qr = static_cast<float*>(sp);
   float* Wr = qr + (size_t)N * K1p;
   const RoundJob jobs[2] = {{q, qr, N, K1, K1, K1p, nullptr}, {W, Wr, K1, K2, K2, K2p, nullptr}};
   MMS_TRY(mms_tf32_round(ctx, jobs, 2));
   TcGemmArgs g = tc_gemm_args(qr, K1p, 0, Wr, K2p, 1, Tm, K2, N, K2, K1);   // B(n=c,k=t) = W[t][c]: MN-major
   g.operands_tf32 = 1;
-  return mms_tc_gemm(ctx, g);
+  MMS_TRY(mms_tc_gemm(ctx, g));
+  ctx->simmat_cache.valid = true; ctx->simmat_cache.q = q; ctx->simmat_cache.W = W;
+  ctx->simmat_cache.N = N; ctx->simmat_cache.K1 = K1; ctx->simmat_cache.K2 = K2;
+  return 0;
 }
 inline int tc_forward(mms_context*, const double*, const double*, double*, int, int, int) { return MMS_E_UNSUPPORTED; }
 
 inline int tc_backward(mms_context* ctx, const float* q, const float* a, const float* W, const float* ds, float* dW,
                        float* dq, float* da, int N, int K1, int K2) {
   const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
+  const bool cached = ctx->reuse_forward && ctx->simmat_cache.valid && ctx->simmat_cache.q == q &&
+                      ctx->simmat_cache.W == W && ctx->simmat_cache.N == N && ctx->simmat_cache.K1 == K1 &&
+                      ctx->simmat_cache.K2 == K2;
+  const void* before = ctx->scratch;
   void* sp = nullptr;
-  MMS_TRY(mms_scratch(ctx, sizeof(float) * ((size_t)N * (2 * K1p + K2p) + (size_t)K1 * K2p), &sp));
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * tc_scratch_floats(N, K1p, K2p, K1), &sp));
+  const bool have_qw = cached && sp == before;
   float* qr = static_cast<float*>(sp);          // q
-  float* qs = qr + (size_t)N * K1p;             // ds o q
-  float* as = qs + (size_t)N * K1p;             // ds o a
-  float* Wr = as + (size_t)N * K2p;
-  const RoundJob jobs[4] = {{q, qr, N, K1, K1, K1p, nullptr}, {q, qs, N, K1, K1, K1p, ds},
-                            {a, as, N, K2, K2, K2p, ds}, {W, Wr, K1, K2, K2, K2p, nullptr}};
-  MMS_TRY(mms_tf32_round(ctx, jobs, 4));
+  float* Wr = qr + (size_t)N * K1p;
+  float* ar = Wr + (size_t)K1 * K2p;            // a
+  float* as = ar + (size_t)N * K2p;             // ds o a
+  // diag(ds) is applied where it is free: folded into the rounding pass for dW's operand (ds o a), and as the
+  // epilogue's row scale for dq = diag(ds) (a W^T) and da = diag(ds) (q W) -- no scaled copy of q is made
+  RoundJob jobs[4];
+  int nj = 0;
+  if (!have_qw) {
+    jobs[nj++] = RoundJob{q, qr, N, K1, K1, K1p, nullptr};
+    jobs[nj++] = RoundJob{W, Wr, K1, K2, K2, K2p, nullptr};
+  }
+  if (dq) jobs[nj++] = RoundJob{a, ar, N, K2, K2, K2p, nullptr};
+  if (dW) jobs[nj++] = RoundJob{a, as, N, K2, K2, K2p, ds};
+  if (nj) MMS_TRY(mms_tf32_round(ctx, jobs, nj));
   if (dW) {   // dW[r][c] += sum_n q[n][r] (ds[n] a[n][c]): both operands MN-major (rows = sample n = K index)
     TcGemmArgs g = tc_gemm_args(qr, K1p, 1, as, K2p, 1, dW, K2, K1, K2, N, TC_ATOMIC);
     const int tiles = mms_ceil_div(K1, 128) * mms_ceil_div(K2, 256);
@@ -102,14 +124,16 @@ inline int tc_backward(mms_context* ctx, const float* q, const float* a, const f
     g.operands_tf32 = 1;
     MMS_TRY(mms_tc_gemm(ctx, g));
   }
-  if (dq) {   // dq[n][r] = sum_c (ds[n] a[n][c]) W[r][c]: A K-major, B(n=r,k=c) = W[r][c] K-major
-    TcGemmArgs g = tc_gemm_args(as, K2p, 0, Wr, K2p, 0, dq, K1, N, K1, K2);
+  if (dq) {   // dq[n][r] = ds[n] sum_c a[n][c] W[r][c]: A K-major, B(n=r,k=c) = W[r][c] K-major
+    TcGemmArgs g = tc_gemm_args(ar, K2p, 0, Wr, K2p, 0, dq, K1, N, K1, K2);
     g.operands_tf32 = 1;
+    g.out_rowscale = ds;
     MMS_TRY(mms_tc_gemm(ctx, g));
   }
-  if (da) {   // da = (ds o q) W
-    TcGemmArgs g = tc_gemm_args(qs, K1p, 0, Wr, K2p, 1, da, K2, N, K2, K1);
+  if (da) {   // da = diag(ds) (q W)
+    TcGemmArgs g = tc_gemm_args(qr, K1p, 0, Wr, K2p, 1, da, K2, N, K2, K1);
     g.operands_tf32 = 1;
+    g.out_rowscale = ds;
     MMS_TRY(mms_tc_gemm(ctx, g));
   }
   return 0;

@@ -332,8 +332,9 @@ def test_simmatrix_golden(golden, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("reuse", [False, True])
 @pytest.mark.parametrize("shape", [(64, 100, 100), (33, 70, 45), (256, 1024, 1024)])
-def test_simmatrix_vs_oracle(dtype, shape):
+def test_simmatrix_vs_oracle(dtype, shape, reuse):
     N, K1, K2 = shape
     q, a, W = synth.make_sentence_vectors(N, K1, K2, seed=N, dtype=dtype)
     rng = np.random.default_rng(N)
@@ -341,6 +342,8 @@ def test_simmatrix_vs_oracle(dtype, shape):
     lay = mms.SimMatrixLayer(mms.LayerParameter("SimMatrix", dtype=dtype))
     bq, ba, top = blob(q, dtype), blob(a, dtype), mms.Blob((), dtype=dtype)
     lay.SetUp([bq, ba], [top])
+    if reuse:                                                # backward reads the rounded q and W the forward left behind
+        lay.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 1)
     lay.blobs[0].set_cpu_data(W)
     lay.Forward([bq, ba], [top])
     s, T = cport.simmatrix_forward(q, a, W)

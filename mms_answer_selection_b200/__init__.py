@@ -15,9 +15,10 @@ from .blob import Blob  # noqa: F401
 from .layers import (AUCLayer, BNLayer, ConvolutionLayer, EmbedLayer, PoolingLayer, TanHLayer, FMLayer, Layer, LayerParameter, MAPLayer, MRRLayer,  # noqa: F401
                      PairRankLossLayer, RankAccuracyLayer, SimCrossLayer, SimMatrixLayer, create_layer)
 from .net import MMSNet  # noqa: F401
+from .sentnet import SentenceVectorNet  # noqa: F401
 from .solver import AdaDeltaSolver  # noqa: F401
 
 __all__ = ["MMSError", "lib", "lib_path", "Blob", "Layer", "LayerParameter", "EmbedLayer",
            "SimCrossLayer", "SimMatrixLayer", "PairRankLossLayer", "FMLayer", "create_layer", "MMSNet", "AdaDeltaSolver",
            "MAPLayer", "MRRLayer", "AUCLayer", "RankAccuracyLayer",
-           "ConvolutionLayer", "BNLayer", "PoolingLayer", "TanHLayer"]
+           "ConvolutionLayer", "BNLayer", "PoolingLayer", "TanHLayer", "SentenceVectorNet"]

@@ -355,7 +355,10 @@ class PairRankLossLayer(Layer):
     def Backward_gpu(self, top, propagate_down, bottom):
         if propagate_down[2]:
             raise CheckError(self.type() + " Layer cannot backpropagate to label inputs.")
-        top_diff = float(top[0].diff.reshape(-1)[0].item())    # top[0]->cpu_diff()[0]
+        if self.defer_loss_:                                   # recording a graph: no host read; the loss weight
+            top_diff = float(self.loss_[0])                    # SetLossWeights put into top.diff (layer.hpp:414-428)
+        else:
+            top_diff = float(top[0].diff.reshape(-1)[0].item())    # top[0]->cpu_diff()[0]
         self._call("mms_pairrankloss_backward", _p(bottom[2]), _p(self.ordered_diff_), _p(self.similar_diff_),
                    self.real(top_diff), bottom[0].count(),
                    _p(bottom[0] if propagate_down[0] else None, True),

@@ -340,3 +340,84 @@ def test_sentence_encoder_chain_feeds_simmatrix():
         # the bias gradient behind a BN layer is a sum that cancels to zero: absolute, against the size of its terms
         assert np.abs(conv.blobs[1].cpu_diff() - rb).max() <= 1e-12 * np.abs(dy).sum()
         assert err(bx.cpu_diff(), rx) <= 1e-9
+
+
+# ---------------------------------------------------------------- the whole sentence-vector variant of the net
+def _sentence_net_reference(idx_q, idx_a, label, P, margin, L, D, C, kh):
+    """The step on the CPU restatements (float64): Embed -> Convolution -> BN -> MAX over time -> TanH per branch
+    (shared parameters, running statistics blended by the question branch first), SimMatrix, PairRankLoss on the two
+    halves of the score column; backward in the reverse layer order."""
+    from oracle import cport
+    N = idx_q.shape[0]
+    h = N // 2
+    mem = float(np.float32(0.9))
+    rm, rv = np.zeros(C), np.zeros(C)
+    br = []
+    for idx in (idx_q, idx_a):
+        e = cport.embed_forward(idx.astype(np.float64), P["W"], P["b"]).reshape(N, 1, L, D)
+        y = snp.conv_forward(e, P["cW"], P["cb"])
+        z, xn, std, rm, rv = snp.bn_forward(y, P["scale"].reshape(-1), P["shift"].reshape(-1), rm, rv, memory=mem)
+        p, mask = snp.pool_forward(z, L - kh + 1, 1)
+        br.append(dict(idx=idx, e=e, y=y, xn=xn, std=std, mask=mask, v=np.tanh(p), zshape=z.shape))
+    vq, va = br[0]["v"].reshape(N, C), br[1]["v"].reshape(N, C)
+    s, _ = cport.simmatrix_forward(vq, va, P["Wm"])
+    s = s.reshape(N, 1)
+    loss, ordered, similar = cport.pairrankloss_forward(s[:h].copy(), s[h:].copy(), label.reshape(h, 1).astype(np.float64), margin)
+    da, db = cport.pairrankloss_backward(label.reshape(h, 1).astype(np.float64), ordered, similar, 1.0)
+    ds = np.concatenate([da, db], axis=0)
+    dWm, dvq, dva = cport.simmatrix_backward(vq, va, P["Wm"], ds, np.zeros_like(P["Wm"]))
+    out = dict(loss=float(loss), dWm=dWm, dcW=np.zeros_like(P["cW"]), dcb=np.zeros_like(P["cb"]),
+               dW=np.zeros_like(P["W"]), db=np.zeros_like(P["b"]), run_mean=rm, run_var=rv)
+    for b, dv in ((br[1], dva), (br[0], dvq)):                # answer branch first: the question branch's BN diffs survive
+        dp = snp.tanh_backward(b["v"], dv.reshape(N, C, 1, 1))
+        dz = snp.pool_backward(dp, b["mask"], b["zshape"], L - kh + 1, 1)
+        out["dscale"], out["dshift"], dy = snp.bn_backward(dz, b["xn"], P["scale"].reshape(-1), b["std"])
+        dW_, db_, dx = snp.conv_backward(b["e"], P["cW"], dy)
+        out["dcW"] += dW_; out["dcb"] += db_
+        cport.embed_backward(b["idx"].astype(np.float64), dx.reshape(N * L, D), out["dW"], out["db"])
+    return out
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-3)])
+def test_sentence_vector_net_step(dtype, tol):
+    """The north-star path as one net (Embed -> sentence encoder -> SimMatrix -> PairRankLoss) against the chained CPU
+    restatements; float runs the TF32 contractions (1e-3 per contraction, 2e-3 through the chain), double is exact to
+    summation order.  The CUDA-graph replay of the step reproduces the eager step."""
+    N, L, D, C, kh, V, margin = 12, 16, 20, 9, 5, 50, 0.7
+    rng = np.random.default_rng(31)
+    net = mms.SentenceVectorNet(N, L, D, C, kh, V, dtype=dtype, margin=margin)
+    bq = net.branches[0]
+    P = dict(W=rng.uniform(-0.5, 0.5, (V, D)), b=rng.uniform(-0.1, 0.1, D), cW=rng.uniform(-0.3, 0.3, (C, 1, kh, D)),
+             cb=rng.uniform(-0.1, 0.1, C), scale=rng.uniform(0.5, 1.5, (1, C, 1, 1)), shift=rng.uniform(-0.2, 0.2, (1, C, 1, 1)),
+             Wm=rng.uniform(-0.5, 0.5, (C, C)))
+    for blob_, key in ((bq["embed"].blobs[0], "W"), (bq["embed"].blobs[1], "b"), (bq["conv"].blobs[0], "cW"),
+                       (bq["conv"].blobs[1], "cb"), (bq["bn"].blobs[0], "scale"), (bq["bn"].blobs[1], "shift"),
+                       (net.sim.blobs[0], "Wm")):
+        blob_.set_cpu_data(P[key])
+        P[key] = blob_.cpu_data().astype(np.float64)          # what the net holds (float32-rounded in the float run)
+    idx_q = rng.integers(0, V, (N, L)); idx_a = rng.integers(0, V, (N, L))
+    idx_q[:, :3] = V - 1                                      # pad ids, as centre-padded sentences have
+    label = rng.choice([1.0, 0.0, -1.0], N // 2)
+    net.set_inputs(idx_q, idx_a, label)
+    net.ClearParamDiffs()
+    loss = net.ForwardBackward()
+    ref = _sentence_net_reference(idx_q, idx_a, label, P, margin, L, D, C, kh)
+    assert abs(loss - ref["loss"]) <= tol * max(abs(ref["loss"]), 1.0)
+    got = dict(dWm=net.sim.blobs[0], dcW=bq["conv"].blobs[0], dcb=bq["conv"].blobs[1], dW=bq["embed"].blobs[0],
+               db=bq["embed"].blobs[1], dscale=bq["bn"].blobs[0], dshift=bq["bn"].blobs[1])
+    for key, blob_ in got.items():
+        r = ref[key].reshape(blob_.shape)
+        scale = max(np.abs(r).max(), 1e-6 if dtype == np.float64 else 1e-3)
+        if key == "db":       # behind BN a constant added to every token cancels: the sum is ~0, judge it by its terms
+            scale = np.abs(ref["dW"]).sum(axis=0).max()
+        assert np.abs(blob_.cpu_diff() - r).max() <= tol * scale, key
+    assert err(bq["bn"].blobs[2].cpu_data().reshape(-1), ref["run_mean"]) <= max(tol, 1e-4)
+    # the step as one CUDA graph: identical parameter gradients (the running statistics blend once more)
+    eager = {k: b_.cpu_diff().copy() for k, b_ in got.items()}
+    net.capture(clear_diffs=True)
+    net.replay()
+    torch.cuda.synchronize()
+    assert abs(net.loss_value() - ref["loss"]) <= 5 * tol * max(abs(ref["loss"]), 1.0)
+    for key, blob_ in got.items():
+        scale = np.abs(eager["dW"]).sum(axis=0).max() if key == "db" else max(np.abs(eager[key]).max(), 1e-3)
+        assert np.abs(blob_.cpu_diff() - eager[key]).max() <= 5 * tol * scale, key

@@ -524,6 +524,22 @@ def extras(world, rank, flush):
     out["sentence_encoder"] = {k: r[k] for k in ("workload", "ms_per_step", "sentences_per_sec", "conv_algorithmic_tflops",
                                                  "conv_gemm_only_tflops", "hbm_gbs")}
     out["sentence_encoder"]["kernels_ms_per_step"] = {k: v["ms_per_step"] for k, v in r["kernels"].items()}
+    torch.cuda.empty_cache()
+    # ---- the whole sentence-vector variant as one net (north_star's path end to end): Embed x2 -> sentence encoder x2
+    #      (shared parameters) -> SimMatrix -> PairRankLoss, forward + backward into W, the filters, BN and the table
+    Ns = c3["N"]
+    ds_ = synth.make_qa_batch(N=Ns, L=c3["L"], D=c3["D"], mc=1, V=c3["V"])
+    snet = mms.SentenceVectorNet(Ns, c3["L"], c3["D"], 100, 5, c3["V"])
+    snet.branches[0]["embed"].blobs[0].set_cpu_data(ds_["W"])
+    lab = (np.random.default_rng(synth.SEED).uniform(0, 1, Ns // 2) < 0.5).astype(np.float32)
+    snet.set_inputs(ds_["idx_q"], ds_["idx_a"], lab)
+    snet.capture(clear_diffs=True)
+    ms = _time_ms(snet.replay, 5, flush, 1)
+    out["sentence_variant_step"] = {
+        "workload": "sentence-vector variant, %d QA pairs/step: Embed x2 -> Convolution(5 x %d, 100) -> BN -> MAX over time -> "
+                    "TanH (shared parameters) -> SimMatrix -> PairRankLoss, fwd+bwd incl. ClearParamDiffs, one CUDA graph"
+                    % (Ns, c3["D"]),
+        "qa_pairs_per_sec": Ns / (ms / 1e3), "ms_per_step": ms, "loss": snet.loss_value()}
     return out
 
 
@@ -536,8 +552,9 @@ def _ncu_row(wl, name):
         rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_%s_fused.json" % wl)))
     except Exception:
         return None
+    want = alias.get(name, name)
     for r in rows:
-        if r.get("kernel") == alias.get(name, name):
+        if r.get("kernel") == want or r.get("kernel", "").startswith(want + "<"):
             return r
     return None
 

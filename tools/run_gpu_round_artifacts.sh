@@ -17,5 +17,7 @@ for f in ("bench_c2", "bench_c3"):
 PY
 # ---- profiler passes (never a source of bench values)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_sentenc.csv python tools/sentenc_bench.py 8192 100 1 > gpurun_out/ncu_sentenc.log 2>&1; echo "launch list sentenc rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_tma|bn_|pool_plane|sentconv" -s 34 -c 17 -o gpurun_out/prof_sentenc -f python tools/sentenc_bench.py 8192 100 1 > gpurun_out/ncu_sentenc_full.log 2>&1; echo "full sentenc rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_tma|bn_|pool_plane|sentconv|tf32_round" -s 30 -c 15 -o gpurun_out/prof_sentenc -f python tools/sentenc_bench.py 8192 100 1 > gpurun_out/ncu_sentenc_full.log 2>&1; echo "full sentenc rc=$?"
 ls -la gpurun_out/*.ncu-rep | tail -3
+# ---- the main path: launch lists and full captures of the fused kernels (C2: 50 pairs, C3: 4096 pairs)
+bash tools/run_gpu_ncu.sh

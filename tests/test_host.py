@@ -57,3 +57,29 @@ def test_blob_reshape_keeps_storage_when_count_is_unchanged():
     assert b.diff.reshape(-1)[0].item() == 2.0
     b.Reshape((3,))
     assert not b.diff.any()
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (plain runs on a B200) carry every key the driver's contract names."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("r01_bench_c2_n1.json", "r01_bench_c3_n4.json"):
+        d = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert k in d, (name, k)
+        assert d["metric"] == "qa_pairs_per_sec_fwd_bwd" and d["higher_is_better"] is True and d["data"] == "synthetic"
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+        assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
+        assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+        assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+        if d["n_gpus"] == 1:
+            assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_ref_c2.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["cpu_baseline"]["kind"] in ("reference", "port")
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]

@@ -605,6 +605,41 @@ def test_rerank_scores_vs_simmatrix_form():
     assert scaled_err(got[0, :64], s.reshape(-1)) <= TOL_TF32
 
 
+@pytest.mark.parametrize("Nq,Nc,K,offset", [
+    (300, 20000, 128, 0),       # CTA-pair kernel
+    (1000, 40000, 1024, 0),     # the C4 shape (a slice of the candidate set)
+    (257, 19001, 96, 0),        # ragged tiles in both directions
+    (300, 20000, 128, 1),       # candidates that are not 16-byte aligned
+])
+def test_rerank_scores_large(Nq, Nc, K, offset):
+    """Candidate scoring on shapes that reach the CTA-pair kernel: agreement with the float64 product to the TF32
+    tolerance, and with an explicitly rounded evaluation closely (operands are rounded to nearest, not truncated)."""
+    import ctypes
+    g = torch.Generator(device="cuda").manual_seed(Nq + Nc)
+    Q = torch.randn((Nq, K), device="cuda", generator=g) / K ** 0.5
+    Cbuf = torch.randn((Nc * K + 4,), device="cuda", generator=g) / K ** 0.5
+    C = Cbuf[offset:offset + Nc * K].view(Nc, K)
+    W = (torch.rand((K, K), device="cuda", generator=g) * 2 - 1) * (3.0 / K) ** 0.5
+    QW = torch.empty((Nq, K), device="cuda"); sc = torch.empty((Nq, Nc), device="cuda")
+    h = _lib.Handle()
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    l0 = h.launch_count()
+    _lib.check(_lib.lib().mms_rerank_scores_f32(h.ptr, *(ctypes.c_void_p(t.data_ptr()) for t in (Q, C, W, QW, sc)),
+                                                Nq, Nc, K, K))
+    torch.cuda.synchronize()
+    assert h.launch_count() > l0
+    ref = (Q.double() @ W.double()) @ C.double().T
+    err = float((sc.double() - ref).abs().max() / ref.abs().max())
+    assert err <= TOL_TF32, err
+    # a few rows against an explicitly rounded evaluation: round(QW) . round(C) in float64 (truncating the operands
+    # instead of rounding them to nearest would show as a bias of ~7e-4)
+    def rna(t):
+        b = t.contiguous().view(torch.int32)
+        return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+    exact = rna(QW[:8]).double() @ rna(C).double().T
+    assert float((sc[:8].double() - exact).abs().max() / exact.abs().max()) <= 2e-5
+
+
 # ---------------------------------------------------------------- ranking metrics on the device
 def _metric_layers(prob, label, group, dtype, fa):
     out = {}

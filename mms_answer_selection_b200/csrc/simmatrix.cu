@@ -212,6 +212,8 @@ int mms_rerank_scores_impl(mms_context* ctx, const float* Q, const float* C, con
     // (Slabs small enough to stay dirty in L2 between the rounding pass and the GEMM -- 2 x 40 MB -- were tried: the
     // rounded copy then never reaches HBM, but 106 two-tile GEMM launches cost more than that saves: 5.0 ms vs 4.1 ms.)
     const bool pipelined = ctx->concurrency != 0 && slab < Nc;   // two slab buffers: round slab i+1 beside the GEMM of slab i
+    if (pipelined) slab = mms_max<long long>(1024, mms_min<long long>(slab, (((long long)(ctx->scratch_cap / sizeof(float)) - (long long)fixed) / K2p) / 2));
+    void* sp = nullptr;
     MMS_TRY(mms_scratch(ctx, sizeof(float) * (fixed + (size_t)slab * K2p * (pipelined ? 2 : 1)), &sp));
     float* Qr = static_cast<float*>(sp);
     float* Wr = Qr + (size_t)Nq * K1p;

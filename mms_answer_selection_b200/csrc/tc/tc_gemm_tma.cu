@@ -690,7 +690,9 @@ int gemm_tma_pair(mms_context* ctx, const TcGemmArgs& a) {
   static const bool disabled = getenv("MMS_NO_2CTA") != nullptr;
   if (disabled || a.M <= 128 || a.N < 256) return MMS_E_UNSUPPORTED;
   Geometry q;
-  const int BN = 256;
+  // column tiles of equal width, each CTA's half a multiple of 32 columns: N = 300 runs as 2 x 192 (78 % of the MMA
+  // columns useful) instead of 256 + 44 (59 %)
+  const int BN = mms_min(256, mms_ceil_div(mms_ceil_div(a.N, mms_ceil_div(a.N, 256)), 64) * 64);
   q.BN = BN;
   q.n_tiles = mms_ceil_div(a.N, BN);
   q.m_tiles = mms_ceil_div(a.M, kBM2);

@@ -106,6 +106,32 @@ __global__ void bias_grad_kernel(const T* __restrict__ dS, T* __restrict__ dB, i
   if (ne > nb) atomicAdd(dB + e, acc);
 }
 
+// float blobs with 16-byte rows: one float4 column group per thread, eight samples' loads in flight per trip
+__global__ void bias_grad_vec_kernel(const float* __restrict__ dS, float* __restrict__ dB, int N, int per4) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= per4) return;
+  const int chunk = (N + gridDim.y - 1) / gridDim.y;
+  const int nb = blockIdx.y * chunk, ne = min(N, nb + chunk);
+  const float4* src = reinterpret_cast<const float4*>(dS) + e;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int n = nb;
+  for (; n + 8 <= ne; n += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldcs(src + (size_t)(n + j) * per4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+  }
+  for (; n < ne; ++n) {
+    const float4 v = __ldcs(src + (size_t)n * per4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (ne > nb) {
+    float* d = dB + 4 * (size_t)e;
+    atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+  }
+}
+
 inline int ew_grid(mms_context* ctx, long long n) {
   return (int)mms_min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
 }
@@ -206,6 +232,14 @@ int simcross2_backward_simt(mms_context* ctx, const T* q, const T* a, const T* M
 template <typename T>
 int simcross2_bias_grad(mms_context* ctx, const T* dS, T* dB, int N, int Lq, int La, int mc) {
   const int per = mc * Lq * La;
+  if (sizeof(T) == 4 && per % 4 == 0 && (reinterpret_cast<uintptr_t>(dS) & 15) == 0) {
+    const int per4 = per / 4, gx = mms_ceil_div(per4, 128);
+    dim3 grid(gx, max(1, min(mms_ceil_div(N, 8), mms_ceil_div(8 * ctx->sm_count, gx))));
+    { MmsKernelScope ks_(ctx, "bias_grad_kernel");
+      bias_grad_vec_kernel<<<grid, 128, 0, ctx->stream>>>(reinterpret_cast<const float*>(dS), reinterpret_cast<float*>(dB), N, per4); }
+    MMS_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(mms_ceil_div(per, 256), max(1, min(N, mms_ceil_div(4 * ctx->sm_count, mms_ceil_div(per, 256)))));
   { MmsKernelScope ks_(ctx, "bias_grad_kernel");
     bias_grad_kernel<T><<<grid, 256, 0, ctx->stream>>>(dS, dB, N, per); }

@@ -287,3 +287,38 @@ def test_copy_trained_layers_from_follows_the_reference_rules(tmp_path):
 def test_v1_layers_are_refused():
     with pytest.raises(ValueError, match="V1LayerParameter"):
         formats.NetProto.parse(bytes([0x12, 0x00]))             # field 2 (`layers`), empty message
+
+
+def test_caffemodel_random_round_trips():
+    """Random nets (shapes incl. 0-axis and 5-axis blobs, float and double blobs, with and without diffs) through our
+    writer -> protobuf parser and protobuf writer -> our parser."""
+    Net, _ = caffe_messages(True)
+    rng = np.random.default_rng(99)
+    for _ in range(25):
+        layers = []
+        for li in range(int(rng.integers(1, 5))):
+            blobs = []
+            for _b in range(int(rng.integers(0, 4))):
+                shape = tuple(int(d) for d in rng.integers(1, 5, int(rng.integers(0, 6))))
+                dt = np.float64 if rng.uniform() < 0.3 else np.float32
+                data = rng.standard_normal(shape).astype(dt)
+                diff = rng.standard_normal(shape).astype(dt) if rng.uniform() < 0.5 else None
+                blobs.append((data, diff))
+            layers.append(("layer%d" % li, "Type%d" % li, blobs))
+        ours = formats.NetProto("net", [formats.LayerProto(n, t, [formats.BlobProto.from_array(d, g) for d, g in bl])
+                                        for n, t, bl in layers])
+        back = Net()
+        back.ParseFromString(ours.serialize())
+        again = formats.NetProto.parse(back.SerializeToString())
+        assert [l.name for l in back.layer] == [n for n, _, _ in layers]
+        for (n, t, bl), lp, lo in zip(layers, back.layer, again.layers):
+            assert lp.type == t and len(lp.blobs) == len(bl) == len(lo.blobs)
+            for (data, diff), bp, bo in zip(bl, lp.blobs, lo.blobs):
+                assert tuple(bp.shape.dim) == data.shape == bo.blob_shape()
+                field = bp.double_data if data.dtype == np.float64 else bp.data
+                assert np.array_equal(np.array(field, data.dtype).reshape(data.shape), data)
+                assert np.array_equal(bo.values(data.dtype).reshape(data.shape), data)
+                if diff is not None:
+                    assert np.array_equal(bo.values(data.dtype, diff=True).reshape(data.shape), diff)
+                else:
+                    assert len(bo.diff) == 0 and len(bo.double_diff) == 0

@@ -421,3 +421,27 @@ def test_sentence_vector_net_step(dtype, tol):
     for key, blob_ in got.items():
         scale = np.abs(eager["dW"]).sum(axis=0).max() if key == "db" else max(np.abs(eager[key]).max(), 1e-3)
         assert np.abs(blob_.cpu_diff() - eager[key]).max() <= 5 * tol * scale, key
+
+
+def test_empty_and_degenerate_calls_through_the_c_abi():
+    """Zero-sized batches are no-ops that return 0; bad arguments are refused with MMS_E_INVALID and a message."""
+    import ctypes
+    L_ = _lib.lib()
+    h = _lib.Handle()
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    x = torch.zeros(64, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    null = ctypes.c_void_p(0)
+    assert L_.mms_sentconv_forward_f32(h.ptr, p(x), p(x), null, p(x), 0, 8, 4, 2, 5) == 0
+    assert L_.mms_sentconv_backward_f32(h.ptr, p(x), p(x), p(x), p(x), null, p(x), 0, 8, 4, 2, 5) == 0
+    assert L_.mms_pool_forward_f32(h.ptr, p(x), p(x), p(x), 0, 4, 4, 1, 1, 4, 4, 1, 1, 0, 0, 0) == 0
+    assert L_.mms_tanh_forward_f32(h.ptr, null, null, 0) == 0
+    assert L_.mms_sentconv_forward_f32(h.ptr, p(x), p(x), null, p(x), 2, 4, 4, 2, 5) == _lib.MMS_E_INVALID   # kernel taller than L
+    assert b"bad size" in L_.mms_last_error()
+    assert L_.mms_pool_forward_f32(h.ptr, p(x), p(x), null, 2, 4, 4, 1, 1, 4, 4, 1, 1, 0, 0, 0) == _lib.MMS_E_INVALID  # MAX needs a mask
+    assert L_.mms_bn_forward_f32(h.ptr, p(x), p(x), p(x), p(x), p(x), p(x), p(x), p(x), p(x), 0, 2, 4, 1,
+                                 ctypes.c_float(0.9), ctypes.c_float(1e-9)) == _lib.MMS_E_INVALID
+    out = torch.zeros(2, device="cuda")
+    assert L_.mms_rank_map_mrr_f32(h.ptr, p(x), 2, 1, p(x), p(x), 0, p(out), ctypes.c_void_p(out.data_ptr() + 4)) == 0
+    torch.cuda.synchronize()
+    assert torch.isnan(out).all()                             # no group qualifies: 0/0, as in the reference

@@ -266,6 +266,14 @@ int mms_rank_accuracy_f64(mms_handle_t h, const double* a, const double* b, cons
 int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W,
                           float* QW, float* scores, int Nq, long long Nc, int K1, int K2);
 
+/* The same against a candidate set that is scored repeatedly (a static index): mms_rerank_prepare writes the
+ * TF32-rounded copy the contraction reads -- (Nc, pad4(K2)) floats, rows padded to a multiple of 4 -- into C_tf32
+ * once; mms_rerank_scores_prepared then scores any number of query batches against it without re-reading and
+ * re-writing the candidates (16 -> 8 GB per call at 10^6 x 1024).  Results are identical to mms_rerank_scores. */
+int mms_rerank_prepare_f32(mms_handle_t h, const float* C, float* C_tf32, long long Nc, int K2);
+int mms_rerank_scores_prepared_f32(mms_handle_t h, const float* Q, const float* C_tf32, const float* W, float* QW,
+                                   float* scores, int Nq, long long Nc, int K1, int K2);
+
 /* ------------------------------------------------------ sentence encoder ---
  * The sentence-vector variant of the net (examples/trec_qa_w2v_mms/do_trec_qa_clean.py:352-375, 412-422):
  * Convolution(kernel kh x D over the (N,1,L,D) embedded sentence) -> BN -> Pooling(MAX over time) -> TanH -> SimMatrix.

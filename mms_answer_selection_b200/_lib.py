@@ -87,6 +87,8 @@ def lib():
             fn.argtypes = [ctypes.c_char_p, c_p, c_ll, c_ll, ctypes.POINTER(c_ll)]
             fn.restype = c_int
         L.mms_rerank_scores_f32.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_ll, c_int, c_int]
+        L.mms_rerank_prepare_f32.argtypes = [c_p, c_p, c_p, c_ll, c_int]
+        L.mms_rerank_scores_prepared_f32.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_ll, c_int, c_int]
         L.mms_tc_gemm_f32.argtypes = [c_p, c_p, c_ll, c_int, c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int,
                                       c_int, c_int]
         _lib = L

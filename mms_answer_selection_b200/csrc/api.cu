@@ -364,6 +364,14 @@ int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const 
   H; return mms_rerank_scores_impl(h, Q, C, W, QW, scores, Nq, Nc, K1, K2);
 }
 
+int mms_rerank_prepare_f32(mms_handle_t h, const float* C, float* C_tf32, long long Nc, int K2) {
+  H; return mms_rerank_prepare_impl(h, C, C_tf32, Nc, K2);
+}
+int mms_rerank_scores_prepared_f32(mms_handle_t h, const float* Q, const float* C_tf32, const float* W, float* QW,
+                                   float* scores, int Nq, long long Nc, int K1, int K2) {
+  H; return mms_rerank_scores_prepared_impl(h, Q, C_tf32, W, QW, scores, Nq, Nc, K1, K2);
+}
+
 // Test/diagnostic entry: C (+)= op(A) op(B) on the tcgen05 TF32 GEMM (see tc/tc_gemm.cuh).
 int mms_tc_gemm_f32(mms_handle_t h, const float* A, long long lda, int a_mn, const float* B, long long ldb,
                     int b_mn, float* C, long long ldc, int M, int N, int K, int ksplit, int mode) {

@@ -179,6 +179,9 @@ int mms_rank_auc_impl(mms_context*, const T* data, long long stride, long long o
                       int has_ignore, int ignore_label, T* out);
 template <typename T>
 int mms_rank_accuracy_impl(mms_context*, const T* a, const T* b, const T* label, long long n, T* out);
+int mms_rerank_prepare_impl(mms_context*, const float* C, float* Cr, long long Nc, int K2);
+int mms_rerank_scores_prepared_impl(mms_context*, const float* Q, const float* Cr, const float* W, float* QW,
+                                    float* scores, int Nq, long long Nc, int K1, int K2);
 template <typename T>
 int mms_sentconv_forward_impl(mms_context*, const T* x, const T* W, const T* bias, T* top, int N, int L, int D, int C, int kh);
 template <typename T>

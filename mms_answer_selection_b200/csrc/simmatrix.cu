@@ -272,6 +272,39 @@ int mms_rerank_scores_impl(mms_context* ctx, const float* Q, const float* C, con
   return mms_simt_gemm<float>(ctx, g);
 }
 
+// A candidate set that is scored again and again (a static index) is rounded once: mms_rerank_prepare writes the
+// TF32-rounded copy the GEMM reads (rows padded to 4 floats) into a buffer the caller keeps, and
+// mms_rerank_scores_prepared scores against it -- the per-call traffic drops from 16 to 8 GB at 10^6 x 1024.
+int mms_rerank_prepare_impl(mms_context* ctx, const float* C, float* Cr, long long Nc, int K2) {
+  MMS_REQUIRE(C && Cr && Nc > 0 && K2 > 0, MMS_E_INVALID, "bad argument");
+  const RoundJob j[1] = {{C, Cr, Nc, K2, K2, tc_pad4(K2), nullptr}};
+  return mms_tf32_round(ctx, j, 1);
+}
+
+int mms_rerank_scores_prepared_impl(mms_context* ctx, const float* Q, const float* Cr, const float* W, float* QW,
+                                    float* scores, int Nq, long long Nc, int K1, int K2) {
+  MMS_REQUIRE(Q && Cr && W && QW && scores, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(Nq > 0 && Nc > 0 && K1 > 0 && K2 > 0, MMS_E_INVALID, "bad size");
+  MMS_REQUIRE(Nc <= 0x7fffffffLL, MMS_E_UNSUPPORTED, "candidate count exceeds int range");
+  MMS_REQUIRE(ctx->math == MMS_MATH_TF32, MMS_E_UNSUPPORTED, "prepared candidates are a TF32 operand");
+  const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
+  void* sp = nullptr;
+  MMS_TRY(mms_scratch(ctx, sizeof(float) * ((size_t)Nq * K1p + (size_t)K1 * K2p + (size_t)Nq * K2p), &sp));
+  float* Qr = static_cast<float*>(sp);
+  float* Wr = Qr + (size_t)Nq * K1p;
+  float* QWr = Wr + (size_t)K1 * K2p;
+  const RoundJob j0[2] = {{Q, Qr, Nq, K1, K1, K1p, nullptr}, {W, Wr, K1, K2, K2, K2p, nullptr}};
+  MMS_TRY(mms_tf32_round(ctx, j0, 2));
+  TcGemmArgs t = tc_gemm_args(Qr, K1p, 0, Wr, K2p, 1, QW, K2, Nq, K2, K1);
+  t.operands_tf32 = 1;
+  MMS_TRY(mms_tc_gemm(ctx, t));
+  const RoundJob j1[1] = {{QW, QWr, Nq, K2, K2, K2p, nullptr}};
+  MMS_TRY(mms_tf32_round(ctx, j1, 1));
+  TcGemmArgs g = tc_gemm_args(QWr, K2p, 0, Cr, K2p, 0, scores, Nc, Nq, (int)Nc, K2);   // both K-major
+  g.operands_tf32 = 1;
+  return mms_tc_gemm(ctx, g);
+}
+
 template int mms_simmatrix_forward_impl<float>(mms_context*, const float*, const float*, const float*, float*, float*, int, int, int);
 template int mms_simmatrix_forward_impl<double>(mms_context*, const double*, const double*, const double*, double*, double*, int, int, int);
 template int mms_simmatrix_backward_impl<float>(mms_context*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int);

@@ -638,6 +638,14 @@ def test_rerank_scores_large(Nq, Nc, K, offset):
         return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
     exact = rna(QW[:8]).double() @ rna(C).double().T
     assert float((sc[:8].double() - exact).abs().max() / exact.abs().max()) <= 2e-5
+    # the prepared-candidates form (round the candidate set once, score against the copy): identical scores
+    Cr = torch.empty((Nc, (K + 3) // 4 * 4), device="cuda")
+    sc2 = torch.empty_like(sc)
+    p_ = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib().mms_rerank_prepare_f32(h.ptr, p_(C), p_(Cr), Nc, K))
+    _lib.check(_lib.lib().mms_rerank_scores_prepared_f32(h.ptr, p_(Q), p_(Cr), p_(W), p_(QW), p_(sc2), Nq, Nc, K, K))
+    torch.cuda.synchronize()
+    assert torch.equal(sc, sc2)
 
 
 # ---------------------------------------------------------------- ranking metrics on the device

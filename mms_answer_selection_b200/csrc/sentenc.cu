@@ -208,6 +208,10 @@ int tc_conv_forward(mms_context*, const double*, const double*, double*, long lo
 // bound by what an SM ingests, not by the tensor pipe), and the top then needs no transpose.
 int tc_conv_forward_t(mms_context* ctx, const float* xr, const float* Wr, float* Yt, long long rows, int D, int C, int kh,
                       long long ldyt) {
+  {  // the dedicated kernel that stages every slab of token rows once for all kh kernel rows (tc/sentconv_fwd.cu)
+    const int rc = mms_tc_sentconv_forward(ctx, xr, rows + kh - 1, Wr, Yt, rows, D, C, kh, ldyt);
+    if (rc != MMS_E_UNSUPPORTED) return rc;
+  }
   // B(n = r, k) = xr[r*D + k], k < kh*D: rows of the operand overlap (leading dimension D, row length kh*D) -- the
   // tensor map takes that as it is (tools/tma_overlap_test.py), so the kh window rows are one contiguous reduction
   TcGemmArgs g = tc_gemm_args(Wr, (long long)kh * D, 0, xr, D, 0, Yt, ldyt, C, (int)rows, kh * D);

@@ -1,0 +1,211 @@
+// Sentence convolution, forward, as ONE dedicated tcgen05 kernel:  Yt[c][r] = sum_i sum_d W[c][i][d] x[r + i][d]
+// (reference ConvolutionLayer::Forward_cpu for a kernel as wide as the input, conv_layer.cpp:25-43).
+//
+// The generic GEMM treats the kh shifted windows as one long reduction and fetches every 32-column slab of token rows
+// kh times (48 KB of operands per 512 tensor-pipe cycles: ingest-bound at 47 % tensor pipe).  Here a slab of
+// 256 + 8 token rows is staged ONCE per 32 columns and the kh MMAs of that slab read it at row offsets 0 .. kh-1:
+// a K-major, 128-byte-swizzled tile can be read by tcgen05.mma from any row -- start address + i * 128 B with the
+// descriptor's base-offset field 0 (tools/smem_row_shift_test.cu).  Per slab: 33 KB of x + kh blocks of filters
+// (C rows each) for 4 * kh MMAs of N = 256.
+//   warp 0: TMA producer (x slab in two boxes, kh filter blocks)   warp 1: MMA issue   warps 2-5: epilogue
+//   two stages of 34 KB + kh * Cb * 128 B, two accumulators of 256 TMEM columns (epilogue of tile t beside tile t+1)
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "../mms_common.cuh"
+#include "tc_gemm.cuh"
+#include "umma.cuh"
+
+using namespace umma;
+
+namespace {
+
+constexpr int kRowsTile = 256;                 // sentence rows (MMA N) per tile
+constexpr int kSlabBytes = 34 * 1024;          // (256 + 8) rows x 128 B, padded to a multiple of 1024
+constexpr int kStages = 2;
+constexpr int kEpiLd = 36;
+constexpr int kThreads = 6 * 32;
+
+// 2-D tiled bulk tensor load global -> shared, completion signalled on `bar`
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+struct ConvSmem {
+  uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct ConvGeom {
+  int kh, D, C, Cb, wblock_bytes, stage_bytes, kblocks;
+  long long rows, ldyt;                        // rows = windows to compute (N*L - kh + 1)
+  unsigned tiles;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapX8,
+                    const __grid_constant__ CUtensorMap mapW, float* __restrict__ Yt, const ConvGeom q) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* epi = reinterpret_cast<float*>(ring + kStages * q.stage_bytes);
+  ConvSmem* sm = reinterpret_cast<ConvSmem*>(ring + kStages * q.stage_bytes + 4 * 32 * kEpiLd * 4);
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm->tmem_base, 512);
+    tmem_relinquish();
+  } else if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapX8); tma_prefetch_desc(&mapW);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    const uint32_t tx = (uint32_t)((kRowsTile + 8) * 128 + q.kh * q.Cb * 128);
+    int it = 0;
+    for (unsigned t = blockIdx.x; t < q.tiles; t += gridDim.x) {
+      const int r0 = (int)t * kRowsTile;
+      for (int kb = 0; kb < q.kblocks; ++kb, ++it) {
+        const int s = it % kStages;
+        if (it >= kStages) mbar_wait(&sm->empty[s], ((it / kStages) - 1) & 1);
+        uint8_t* xs = ring + s * q.stage_bytes;
+        uint8_t* ws = xs + kSlabBytes;
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&sm->full[s], tx);
+          tma_load_2d(xs, &mapX, &sm->full[s], kb * 32, r0);                                  // rows r0 .. r0+255
+          tma_load_2d(xs + kRowsTile * 128, &mapX8, &sm->full[s], kb * 32, r0 + kRowsTile);   // .. r0+263
+          for (int i = 0; i < q.kh; ++i)
+            tma_load_2d(ws + i * q.wblock_bytes, &mapW, &sm->full[s], i * q.D + kb * 32, 0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issue
+    const uint32_t idesc = idesc_tf32(128, kRowsTile, false, false);
+    int it = 0, tcount = 0;
+    for (unsigned t = blockIdx.x; t < q.tiles; t += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      if (tcount >= 2) mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * kRowsTile;
+      for (int kb = 0; kb < q.kblocks; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&sm->full[s], (it / kStages) & 1);
+        tc_fence_after();
+        const uint32_t xbase = smem_u32(ring + s * q.stage_bytes), wbase = xbase + kSlabBytes;
+        if (elect_one_sync()) {
+          for (int i = 0; i < q.kh; ++i) {
+            const uint32_t a_lo = desc_lo_k(wbase + i * q.wblock_bytes);     // filters of kernel row i: the MMA's M side
+            const uint32_t b_lo = desc_lo_k(xbase + i * 128);                // the slab, read from token row i on
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_tf32_ss_lh(acc, a_lo + ks * kDescStepK, kDescHiK, b_lo + ks * kDescStepK, kDescHiK, idesc,
+                             (kb > 0 || i > 0 || ks > 0) ? 1u : 0u);
+          }
+          mma_commit(&sm->empty[s]);
+          if (kb == q.kblocks - 1) mma_commit(&sm->acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: lane = filter, columns = sentence rows
+    const int quarter = warp & 3;
+    float* stage = epi + quarter * (32 * kEpiLd);
+    int tcount = 0;
+    for (unsigned t = blockIdx.x; t < q.tiles; t += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      const long long r0 = (long long)t * kRowsTile;
+      mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * kRowsTile + ((uint32_t)(quarter * 32) << 16);
+      const int c_first = quarter * 32;
+      if (c_first < q.C) {
+        for (int c0 = 0; c0 < kRowsTile && r0 + c0 < q.rows; c0 += 32) {
+          float v[32];
+          tmem_ld32(acc + c0, v);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4)
+            *reinterpret_cast<float4*>(stage + lane * kEpiLd + i4 * 4) =
+                make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
+          __syncwarp();
+          const int cc = (lane & 7) * 4, rr0 = lane >> 3;
+          const long long col = r0 + c0 + cc;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int row = rr0 + rr * 4, c = c_first + row;
+            if (c < q.C && col < q.rows) {
+              const float4 o = *reinterpret_cast<const float4*>(stage + row * kEpiLd + cc);
+              float* p = Yt + (size_t)c * q.ldyt + col;
+              if (col + 3 < q.rows) *reinterpret_cast<float4*>(p) = o;
+              else { p[0] = o.x; if (col + 1 < q.rows) p[1] = o.y; if (col + 2 < q.rows) p[2] = o.z; }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+// xr: (rows_total, D) TF32-rounded token rows; Wr: (C, kh*D) rounded filters; Yt: (C, ldyt), Yt[c][r] for r < rows.
+int mms_tc_sentconv_forward(mms_context* ctx, const float* xr, long long rows_total, const float* Wr, float* Yt,
+                            long long rows, int D, int C, int kh, long long ldyt) {
+  static const bool disabled = getenv("MMS_NO_SENTCONV_KERNEL") != nullptr;
+  if (disabled || C > 128 || kh > 8 || kh < 1 || D % 4 != 0 || rows < 1 || ldyt % 4 != 0) return MMS_E_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(Wr) | reinterpret_cast<uintptr_t>(Yt)) & 15) != 0)
+    return MMS_E_UNSUPPORTED;
+  ConvGeom q;
+  q.kh = kh; q.D = D; q.C = C; q.Cb = (C + 7) & ~7;
+  q.wblock_bytes = q.Cb * 128;
+  q.stage_bytes = kSlabBytes + kh * q.wblock_bytes;
+  q.kblocks = (D + 31) / 32;
+  q.rows = rows; q.ldyt = ldyt;
+  q.tiles = (unsigned)((rows + kRowsTile - 1) / kRowsTile);
+  // (the MMA reads 128 rows of every filter block whatever Cb is: the rows past Cb are the next block, or the epilogue
+  // staging behind the last one -- garbage that only reaches accumulator lanes >= Cb, which are never stored)
+  const size_t smem = (size_t)kStages * q.stage_bytes + 4 * 32 * kEpiLd * 4 + sizeof(ConvSmem) + 1024;
+  if (smem > 227 * 1024) return MMS_E_UNSUPPORTED;
+  CUtensorMap mapX, mapX8, mapW;
+  const unsigned long long dx[2] = {(unsigned long long)D, (unsigned long long)rows_total};
+  const unsigned long long sx[1] = {(unsigned long long)D * 4};
+  const unsigned bx[2] = {32, (unsigned)kRowsTile}, bx8[2] = {32, 8};
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapX, xr, 2, dx, sx, bx, false));
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapX8, xr, 2, dx, sx, bx8, false));
+  const unsigned long long dw[2] = {(unsigned long long)kh * D, (unsigned long long)C};
+  const unsigned long long sw[1] = {(unsigned long long)kh * D * 4};
+  const unsigned bw[2] = {32, (unsigned)q.Cb};
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapW, Wr, 2, dw, sw, bw, false));
+  static bool configured = false;
+  if (!configured) {
+    MMS_CUDA(cudaFuncSetAttribute(sentconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const unsigned grid = mms_min<unsigned>(q.tiles, (unsigned)ctx->sm_count);
+  { MmsKernelScope ks_(ctx, "sentconv_fwd_kernel");
+    sentconv_fwd_kernel<<<grid, kThreads, smem, ctx->stream>>>(mapX, mapX8, mapW, Yt, q); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}

@@ -57,6 +57,11 @@ int mms_tc_make_map(mms_context* ctx, void* out, const float* ptr, long long ld,
 int mms_tc_make_map_raw(mms_context* ctx, void* out, const float* ptr, int rank, const unsigned long long* dims,
                         const unsigned long long* strides_bytes, const unsigned* box, bool atom32b);
 
+// Sentence convolution forward as a dedicated kernel (tc/sentconv_fwd.cu): Yt[c][r] = sum_i sum_d Wr[c][i*D + d] *
+// xr[(r + i)*D + d] for r < rows; MMS_E_UNSUPPORTED when the shape does not fit it (C > 128, kh > 8, D % 4).
+int mms_tc_sentconv_forward(mms_context* ctx, const float* xr, long long rows_total, const float* Wr, float* Yt,
+                            long long rows, int D, int C, int kh, long long ldyt);
+
 // dst[r*ldd + c] = tf32_rna(src[r*lds + c] * (scale ? scale[r] : 1)) for up to 4 matrices in one launch.
 struct RoundJob {
   const float* src; float* dst; long long rows; int cols; long long lds, ldd; const float* scale;

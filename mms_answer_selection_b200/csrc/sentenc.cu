@@ -174,6 +174,22 @@ __global__ void sentconv_flip_weights_kernel(const T* __restrict__ W, T* __restr
   }
 }
 
+// Wt[(d*kh + i')*Cp + c] = round(W[c][kh-1-i'][d]): the same filters with the OUTPUT index d outermost -- K-major rows for
+// the dedicated shifted-window kernel (tc/sentconv_fwd.cu), which then computes dx exactly like a forward pass over
+// the padded gradient rows
+template <typename T>
+__global__ void sentconv_flip_weights_t_kernel(const T* __restrict__ W, T* __restrict__ Wt, int C, int Cp, int kh, int D,
+                                               int do_round) {
+  const long long total = (long long)D * kh * Cp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Cp);
+    const int ip = (int)((e / Cp) % kh);
+    const int d = (int)(e / ((long long)Cp * kh));
+    const T v = c < C ? W[((size_t)c * kh + (kh - 1 - ip)) * D + d] : T(0);
+    Wt[e] = do_round ? round_operand(v) : v;
+  }
+}
+
 template <typename T>
 int simt_gemm(mms_context* ctx, const T* A, long long sAm, long long sAk, const T* B, long long sBk, long long sBn, T* C,
               int ldc, long long M, int N, int K, T beta, int ksplit) {
@@ -244,6 +260,16 @@ int tc_conv_dx(mms_context* ctx, const float* Gpad, int ldg, const float* Wf, fl
   return mms_tc_gemm(ctx, g);
 }
 int tc_conv_dx(mms_context*, const double*, int, const double*, double*, long long, int, int, int) { return MMS_E_UNSUPPORTED; }
+
+// dx on the dedicated shifted-window kernel: out(m = d, r) = sum_i' sum_c Wt[d][i'*ldg + c] Gpad[(r + i')*ldg + c]
+int tc_conv_dx_shifted(mms_context* ctx, const float* Gpad, int ldg, const float* Wt, float* dx, long long rows, int D, int C,
+                       int kh, int dry_run) {
+  return mms_tc_sentconv_shifted(ctx, Gpad, rows + 2 * (kh - 1), ldg, C, Wt, (long long)kh * ldg, ldg, D, kh, dx, D, rows, 1,
+                                 dry_run);
+}
+int tc_conv_dx_shifted(mms_context*, const double*, int, const double*, double*, long long, int, int, int, int) {
+  return MMS_E_UNSUPPORTED;
+}
 
 int round_copies(mms_context* ctx, const float* x, float* xr, long long rows, int D, const float* W, float* Wr, int C,
                  int kh) {
@@ -374,11 +400,16 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
     }
   }
   if (dx) {                                                  // overwrites (backward_cpu_gemm + col2im; conv_layer.cpp:62-65)
+    const bool shifted = tc && tc_conv_dx_shifted(ctx, Gpad, ldg, Wf, dx, rows, D, C, kh, /*dry_run=*/1) == 0;
     { MmsKernelScope ks_(ctx, "sentconv_flip_weights_kernel");
-      sentconv_flip_weights_kernel<T><<<ew_grid(ctx, (long long)kh * ldg * D), 256, 0, ctx->stream>>>(W, Wf, C, ldg, kh, D,
-                                                                                                 tc ? 1 : 0); }
+      if (shifted)
+        sentconv_flip_weights_t_kernel<T><<<ew_grid(ctx, (long long)kh * ldg * D), 256, 0, ctx->stream>>>(W, Wf, C, ldg, kh, D, 1);
+      else
+        sentconv_flip_weights_kernel<T><<<ew_grid(ctx, (long long)kh * ldg * D), 256, 0, ctx->stream>>>(W, Wf, C, ldg, kh, D,
+                                                                                                   tc ? 1 : 0); }
     MMS_LAUNCH_CHECK();
-    if (tc) MMS_TRY(tc_conv_dx(ctx, Gpad, ldg, Wf, dx, rows, D, C, kh));
+    if (shifted) MMS_TRY(tc_conv_dx_shifted(ctx, Gpad, ldg, Wf, dx, rows, D, C, kh, 0));
+    else if (tc) MMS_TRY(tc_conv_dx(ctx, Gpad, ldg, Wf, dx, rows, D, C, kh));
     else MMS_TRY(simt_gemm<T>(ctx, Gpad, ldg, 1, Wf, D, 1, dx, D, rows, D, kh * C, T(0), 1));   // ldg == C here
   }
   return 0;

@@ -40,15 +40,16 @@ struct ConvSmem {
   uint32_t tmem_base;
 };
 
+// out(m, r) = sum_i sum_k F[m][i*Kdf + k] * X[(r + i)*ldx + k],  m < Mtot, r < rows, k < Kd
 struct ConvGeom {
-  int kh, D, C, Cb, wblock_bytes, stage_bytes, kblocks;
-  long long rows, ldyt;                        // rows = windows to compute (N*L - kh + 1)
-  unsigned tiles;
+  int kh, Kdf, Mtot, Mper, Cb, m_tiles, wblock_bytes, stage_bytes, kblocks, row_major_out;
+  long long rows, ld_out;                      // rows = output rows r to compute
+  unsigned tiles;                              // row tiles x m_tiles, m fastest (the tiles of a slab run together)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapX8,
-                    const __grid_constant__ CUtensorMap mapW, float* __restrict__ Yt, const ConvGeom q) {
+                    const __grid_constant__ CUtensorMap mapW, float* __restrict__ out, const ConvGeom q) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* epi = reinterpret_cast<float*>(ring + kStages * q.stage_bytes);
@@ -77,7 +78,7 @@ sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     const uint32_t tx = (uint32_t)((kRowsTile + 8) * 128 + q.kh * q.Cb * 128);
     int it = 0;
     for (unsigned t = blockIdx.x; t < q.tiles; t += gridDim.x) {
-      const int r0 = (int)t * kRowsTile;
+      const int r0 = (int)(t / q.m_tiles) * kRowsTile, m0 = (int)(t % q.m_tiles) * q.Mper;
       for (int kb = 0; kb < q.kblocks; ++kb, ++it) {
         const int s = it % kStages;
         if (it >= kStages) mbar_wait(&sm->empty[s], ((it / kStages) - 1) & 1);
@@ -88,7 +89,7 @@ sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
           tma_load_2d(xs, &mapX, &sm->full[s], kb * 32, r0);                                  // rows r0 .. r0+255
           tma_load_2d(xs + kRowsTile * 128, &mapX8, &sm->full[s], kb * 32, r0 + kRowsTile);   // .. r0+263
           for (int i = 0; i < q.kh; ++i)
-            tma_load_2d(ws + i * q.wblock_bytes, &mapW, &sm->full[s], i * q.D + kb * 32, 0);
+            tma_load_2d(ws + i * q.wblock_bytes, &mapW, &sm->full[s], i * q.Kdf + kb * 32, m0);
         }
         __syncwarp();
       }
@@ -129,15 +130,26 @@ sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     int tcount = 0;
     for (unsigned t = blockIdx.x; t < q.tiles; t += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
-      const long long r0 = (long long)t * kRowsTile;
+      const long long r0 = (long long)(t / q.m_tiles) * kRowsTile;
+      const int m0 = (int)(t % q.m_tiles) * q.Mper, m_end = min(q.Mtot, m0 + q.Mper);
       mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem + buf * kRowsTile + ((uint32_t)(quarter * 32) << 16);
-      const int c_first = quarter * 32;
-      if (c_first < q.C) {
+      const int c_first = m0 + quarter * 32;
+      if (c_first < m_end) {
         for (int c0 = 0; c0 < kRowsTile && r0 + c0 < q.rows; c0 += 32) {
           float v[32];
           tmem_ld32(acc + c0, v);
+          if (q.row_major_out) {                               // out[r][m]: the 32 lanes of a warp are 32 consecutive m
+            const int m = c_first + lane;
+            if (m < m_end) {
+              float* p = out + (size_t)(r0 + c0) * q.ld_out + m;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (r0 + c0 + j < q.rows) p[(size_t)j * q.ld_out] = v[j];
+            }
+            continue;
+          }
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4)
             *reinterpret_cast<float4*>(stage + lane * kEpiLd + i4 * 4) =
@@ -148,9 +160,9 @@ sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr) {
             const int row = rr0 + rr * 4, c = c_first + row;
-            if (c < q.C && col < q.rows) {
+            if (c < m_end && col < q.rows) {
               const float4 o = *reinterpret_cast<const float4*>(stage + row * kEpiLd + cc);
-              float* p = Yt + (size_t)c * q.ldyt + col;
+              float* p = out + (size_t)c * q.ld_out + col;
               if (col + 3 < q.rows) *reinterpret_cast<float4*>(p) = o;
               else { p[0] = o.x; if (col + 1 < q.rows) p[1] = o.y; if (col + 2 < q.rows) p[2] = o.z; }
             }
@@ -170,42 +182,59 @@ sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
 
 }  // namespace
 
-// xr: (rows_total, D) TF32-rounded token rows; Wr: (C, kh*D) rounded filters; Yt: (C, ldyt), Yt[c][r] for r < rows.
-int mms_tc_sentconv_forward(mms_context* ctx, const float* xr, long long rows_total, const float* Wr, float* Yt,
-                            long long rows, int D, int C, int kh, long long ldyt) {
+// out(m, r) = sum_{i < kh} sum_{k < Kd} F[m*ldf + i*Kdf + k] * X[(r + i)*ldx + k]   for m < Mtot, r < rows.
+//   X: (rows_total, ldx) TF32-exact rows (rows past rows_total read as zero), F: (Mtot, ldf) TF32-exact.
+//   row_major_out 0: out[m*ld_out + r] (channel-major, the forward's Yt)   1: out[r*ld_out + m] (the backward's dx)
+// dry_run != 0 only answers whether the shape is served (0) or not (MMS_E_UNSUPPORTED).
+int mms_tc_sentconv_shifted(mms_context* ctx, const float* X, long long rows_total, long long ldx, int Kd, const float* F,
+                            long long ldf, int Kdf, int Mtot, int kh, float* out, long long ld_out, long long rows,
+                            int row_major_out, int dry_run) {
   static const bool disabled = getenv("MMS_NO_SENTCONV_KERNEL") != nullptr;
-  if (disabled || C > 128 || kh > 8 || kh < 1 || D % 4 != 0 || rows < 1 || ldyt % 4 != 0) return MMS_E_UNSUPPORTED;
-  if (((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(Wr) | reinterpret_cast<uintptr_t>(Yt)) & 15) != 0)
-    return MMS_E_UNSUPPORTED;
+  if (disabled || kh > 8 || kh < 1 || ldx % 4 != 0 || ldf % 4 != 0 || rows < 1 || Mtot < 1 || Kd < 1) return MMS_E_UNSUPPORTED;
+  if (!row_major_out && ld_out % 4 != 0) return MMS_E_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(F)) & 15) != 0) return MMS_E_UNSUPPORTED;
+  if (!row_major_out && (reinterpret_cast<uintptr_t>(out) & 15) != 0) return MMS_E_UNSUPPORTED;
   ConvGeom q;
-  q.kh = kh; q.D = D; q.C = C; q.Cb = (C + 7) & ~7;
+  q.kh = kh; q.Kdf = Kdf; q.Mtot = Mtot;
+  q.m_tiles = (Mtot + 127) / 128;
+  q.Mper = (Mtot + q.m_tiles - 1) / q.m_tiles;               // outputs per tile, <= 128
+  q.Cb = (q.Mper + 7) & ~7;
   q.wblock_bytes = q.Cb * 128;
   q.stage_bytes = kSlabBytes + kh * q.wblock_bytes;
-  q.kblocks = (D + 31) / 32;
-  q.rows = rows; q.ldyt = ldyt;
-  q.tiles = (unsigned)((rows + kRowsTile - 1) / kRowsTile);
+  q.kblocks = (Kd + 31) / 32;
+  q.rows = rows; q.ld_out = ld_out; q.row_major_out = row_major_out;
+  const long long row_tiles = (rows + kRowsTile - 1) / kRowsTile;
+  if (row_tiles * q.m_tiles > 0x7fffffffLL) return MMS_E_UNSUPPORTED;
+  q.tiles = (unsigned)(row_tiles * q.m_tiles);
   // (the MMA reads 128 rows of every filter block whatever Cb is: the rows past Cb are the next block, or the epilogue
   // staging behind the last one -- garbage that only reaches accumulator lanes >= Cb, which are never stored)
   const size_t smem = (size_t)kStages * q.stage_bytes + 4 * 32 * kEpiLd * 4 + sizeof(ConvSmem) + 1024;
   if (smem > 227 * 1024) return MMS_E_UNSUPPORTED;
+  if (dry_run) return 0;
   CUtensorMap mapX, mapX8, mapW;
-  const unsigned long long dx[2] = {(unsigned long long)D, (unsigned long long)rows_total};
-  const unsigned long long sx[1] = {(unsigned long long)D * 4};
+  const unsigned long long dx[2] = {(unsigned long long)Kd, (unsigned long long)rows_total};
+  const unsigned long long sx[1] = {(unsigned long long)ldx * 4};
   const unsigned bx[2] = {32, (unsigned)kRowsTile}, bx8[2] = {32, 8};
-  MMS_TRY(mms_tc_make_map_raw(ctx, &mapX, xr, 2, dx, sx, bx, false));
-  MMS_TRY(mms_tc_make_map_raw(ctx, &mapX8, xr, 2, dx, sx, bx8, false));
-  const unsigned long long dw[2] = {(unsigned long long)kh * D, (unsigned long long)C};
-  const unsigned long long sw[1] = {(unsigned long long)kh * D * 4};
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapX, X, 2, dx, sx, bx, false));
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapX8, X, 2, dx, sx, bx8, false));
+  const unsigned long long dw[2] = {(unsigned long long)ldf, (unsigned long long)Mtot};
+  const unsigned long long sw[1] = {(unsigned long long)ldf * 4};
   const unsigned bw[2] = {32, (unsigned)q.Cb};
-  MMS_TRY(mms_tc_make_map_raw(ctx, &mapW, Wr, 2, dw, sw, bw, false));
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapW, F, 2, dw, sw, bw, false));
   static bool configured = false;
   if (!configured) {
     MMS_CUDA(cudaFuncSetAttribute(sentconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const unsigned grid = mms_min<unsigned>(q.tiles, (unsigned)ctx->sm_count);
-  { MmsKernelScope ks_(ctx, "sentconv_fwd_kernel");
-    sentconv_fwd_kernel<<<grid, kThreads, smem, ctx->stream>>>(mapX, mapX8, mapW, Yt, q); }
+  { MmsKernelScope ks_(ctx, row_major_out ? "sentconv_dx_kernel" : "sentconv_fwd_kernel");
+    sentconv_fwd_kernel<<<grid, kThreads, smem, ctx->stream>>>(mapX, mapX8, mapW, out, q); }
   MMS_LAUNCH_CHECK();
   return 0;
+}
+
+// forward: xr (rows_total, D), Wr (C, kh*D) -> Yt[c][r], r < rows
+int mms_tc_sentconv_forward(mms_context* ctx, const float* xr, long long rows_total, const float* Wr, float* Yt,
+                            long long rows, int D, int C, int kh, long long ldyt) {
+  return mms_tc_sentconv_shifted(ctx, xr, rows_total, D, D, Wr, (long long)kh * D, D, C, kh, Yt, ldyt, rows, 0, 0);
 }

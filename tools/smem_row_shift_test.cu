@@ -66,6 +66,57 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const float* __restrict__
   if (warp == 0) tmem_dealloc(tmem, 32);
 }
 
+// The same question for an MN-major operand (the reduction index k is the row of the tile): B(n, k) = Xmn[k + shift][n],
+// one block of 32 n-columns x 48 k-rows, 128 B per k-row, SWIZZLE_128B_BASE32B.
+__global__ void __launch_bounds__(128, 1) shift_mn_kernel(const float* __restrict__ A, const float* __restrict__ Xmn,
+                                                          float* __restrict__ D, int shift) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* at = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // A: 128 rows x 128 B, K-major
+  uint8_t* bt = at + 16384;                                                    // Xmn: 48 k-rows x 128 B, MN-major
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
+  for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
+    const int r = e >> 3, c4 = e & 7;
+    *reinterpret_cast<float4*>(at + swz128(r, c4)) = *reinterpret_cast<const float4*>(A + r * kK + c4 * 4);
+  }
+  for (int e = threadIdx.x; e < 48 * 8; e += blockDim.x) {
+    const int r = e >> 3, c4 = e & 7;
+    *reinterpret_cast<float4*>(bt + swz128_mn(r, c4)) = *reinterpret_cast<const float4*>(Xmn + r * 32 + c4 * 4);
+  }
+  if (warp == 0) {
+    if (lane == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(&tmem_base, 32);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (warp == 0) {
+    const uint32_t idesc = idesc_tf32(128, kN, false, true);
+    if (elect_one_sync()) {
+      for (int ks = 0; ks < kK / 8; ++ks) {
+        const uint64_t da = desc_kmajor(smem_u32(at) + ks * 32);
+        const uint64_t db = desc_mnmajor(smem_u32(bt) + shift * 128 + ks * 1024, 4096);
+        mma_tf32_ss(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+      }
+      mma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  float v[32];
+  tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+  for (int j = 0; j < kN; ++j) D[(warp * 32 + lane) * kN + j] = v[j];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
 static float tf32(float x) {
   unsigned u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; memcpy(&x, &u, 4); return x;
 }
@@ -98,5 +149,30 @@ int main() {
       printf("shift %2d rows  base_offset field %s : max |err| / max |ref| = %.2e  %s\n", s, ubo ? "= shift & 7" : "= 0       ",
              err / ref_max, err / ref_max < 1e-5 ? "OK" : "WRONG");
     }
+  // ---- MN-major operand shifted along the reduction index
+  std::vector<float> A(128 * kK), Xmn(48 * 32);
+  for (auto& v : A) v = tf32((rand() % 2001 - 1000) / 1000.f);
+  for (auto& v : Xmn) v = tf32((rand() % 2001 - 1000) / 1000.f);
+  float *dA, *dXmn;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dXmn, Xmn.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dXmn, Xmn.data(), Xmn.size() * 4, cudaMemcpyHostToDevice);
+  cudaFuncSetAttribute(shift_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int s : {0, 1, 2, 3, 4, 5, 8, 9}) {
+    cudaMemset(dD, 0, D.size() * 4);
+    shift_mn_kernel<<<1, 128, 64 * 1024>>>(dA, dXmn, dD, s);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("MN shift %d: %s\n", s, cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    double err = 0, ref_max = 0;
+    for (int r = 0; r < 128; ++r)
+      for (int n = 0; n < kN; ++n) {
+        double acc = 0;
+        for (int k = 0; k < kK; ++k) acc += (double)A[r * kK + k] * Xmn[(k + s) * 32 + n];
+        err = fmax(err, fabs(acc - D[r * kN + n])); ref_max = fmax(ref_max, fabs(acc));
+      }
+    printf("MN-major operand, shift %2d k-rows (base offset 0) : max |err| / max |ref| = %.2e  %s\n", s, err / ref_max,
+           err / ref_max < 1e-5 ? "OK" : "WRONG");
+  }
   return 0;
 }

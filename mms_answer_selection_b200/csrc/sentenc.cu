@@ -250,6 +250,16 @@ int tc_conv_dw(mms_context* ctx, const float* G, int ldg, const float* xr, float
   return mms_tc_gemm(ctx, g);
 }
 int tc_conv_dw(mms_context*, const double*, int, const double*, double*, long long, int, int, int) { return MMS_E_UNSUPPORTED; }
+// the dedicated kernel (tc/sentconv_fwd.cu) when the shape fits it, else the generic engine
+int tc_conv_dw_any(mms_context* ctx, const float* G, int ldg, const float* xr, float* dW, long long mrows, long long rows,
+                   int D, int C, int kh) {
+  const int rc = mms_tc_sentconv_dw(ctx, G, mrows, ldg, xr, rows, dW, D, C, kh);
+  if (rc != MMS_E_UNSUPPORTED) return rc;
+  return tc_conv_dw(ctx, G, ldg, xr, dW, mrows, D, C, kh);
+}
+int tc_conv_dw_any(mms_context*, const double*, int, const double*, double*, long long, long long, int, int, int) {
+  return MMS_E_UNSUPPORTED;
+}
 
 int tc_conv_dx(mms_context* ctx, const float* Gpad, int ldg, const float* Wf, float* dx, long long rows, int D, int C,
                int kh) {
@@ -392,7 +402,7 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
   if (dW) {                                                  // accumulates (weight_cpu_gemm, beta = 1; conv_layer.cpp:57-60)
     if (tc) {
       if (!have_xr) MMS_TRY(round_copies(ctx, x, xr, rows, D, nullptr, nullptr, C, kh));
-      MMS_TRY(tc_conv_dw(ctx, G, ldg, xr, dW, mrows, D, C, kh));
+      MMS_TRY(tc_conv_dw_any(ctx, G, ldg, xr, dW, mrows, rows, D, C, kh));
     } else {
       const int tiles = mms_ceil_div(C, 64) * mms_ceil_div(kh * D, 64);
       const int ksplit = (int)mms_max<long long>(1, mms_min<long long>(mms_ceil_div(2 * ctx->sm_count, tiles), (mrows + 255) / 256));

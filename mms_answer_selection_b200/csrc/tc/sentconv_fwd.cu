@@ -182,6 +182,156 @@ sentconv_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient on the same idea:  dW[c][i][d] += sum_r G[r][c] * x[(r + i)*D + d]   (conv_layer.cpp:57-60).
+// The reduction index r is the row of both tiles (MN-major operands); a slab of 32 + 8 token rows of x serves the
+// kh accumulators dW[:, i, d-range] by being read from k-row i on (MN-major tiles can be read from any k-row too:
+// tools/smem_row_shift_test.cu).  One CTA = one range of 96 d-columns x one slice of the token rows; kh accumulators
+// of 96 TMEM columns; per 32-row k-block 16 KB of G + 15 KB of x feed 4 * kh MMAs of N = 96 (960 tensor-pipe
+// cycles: 33 B/clk).  The slices add into dW with red.global.add (dW accumulates across calls anyway).
+namespace {
+
+constexpr int kDwN = 96, kDwStages = 6, kDwSlabRows = 40;
+constexpr int kDwABytes = 4 * 4096, kDwBBlock = kDwSlabRows * 128, kDwBBytes = (kDwN / 32) * kDwBBlock;
+
+struct DwSmem {
+  uint64_t full[kDwStages], empty[kDwStages], acc_full;
+  uint32_t tmem_base;
+};
+struct DwGeom {
+  int kh, D, C, n_dr, ksplit;
+  long long kblocks;                          // 32-row blocks of the reduction
+  long long ldw;                              // kh * D
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+sentconv_dw_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapX,
+                   float* __restrict__ dW, const DwGeom q) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kStageB = 32768;                               // 16 KB of G + 15 KB of x, padded to 32 KB
+  DwSmem* sm = reinterpret_cast<DwSmem*>(ring + kDwStages * kStageB);
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
+  const int dr = blockIdx.x % q.n_dr, slice = blockIdx.x / q.n_dr;
+  const int d0 = dr * kDwN;
+  const long long per = (q.kblocks + q.ksplit - 1) / q.ksplit;
+  const long long kb0 = slice * per, kb1 = min(q.kblocks, kb0 + per);
+  const int nkb = (int)max(0LL, kb1 - kb0);
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kDwStages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+      mbar_init(&sm->acc_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm->tmem_base, 512);
+    tmem_relinquish();
+  } else if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapG); tma_prefetch_desc(&mapX);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 0) {
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % kDwStages;
+      if (it >= kDwStages) mbar_wait(&sm->empty[s], ((it / kDwStages) - 1) & 1);
+      uint8_t* a_dst = ring + s * kStageB;
+      uint8_t* b_dst = a_dst + kDwABytes;
+      const int r0 = (int)((kb0 + it) * 32);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&sm->full[s], (uint32_t)(kDwABytes + kDwBBytes));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(a_dst + b * 4096, &mapG, &sm->full[s], 32 * b, r0);        // c block b
+#pragma unroll
+        for (int b = 0; b < kDwN / 32; ++b) tma_load_2d(b_dst + b * kDwBBlock, &mapX, &sm->full[s], d0 + 32 * b, r0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_tf32(128, kDwN, true, true);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % kDwStages;
+      mbar_wait(&sm->full[s], (it / kDwStages) & 1);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(ring + s * kStageB), b_base = a_base + kDwABytes;
+      const uint32_t a_lo = desc_lo_mn(a_base, 4096);
+      if (elect_one_sync()) {
+        for (int i = 0; i < q.kh; ++i) {
+          const uint32_t b_lo = desc_lo_mn(b_base + i * 128, kDwBBlock);       // the slab from token row i on
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_tf32_ss_lh(tmem + i * kDwN, a_lo + ks * kDescStepMN, kDescHiMN, b_lo + ks * kDescStepMN, kDescHiMN, idesc,
+                           (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(&sm->empty[s]);
+        if (it == nkb - 1) mma_commit(&sm->acc_full);
+      }
+      __syncwarp();
+    }
+  } else if (nkb > 0) {
+    // ------------------------------------------------------------ epilogue: lane = filter c, columns = d; adds into dW
+    const int quarter = warp & 3, c = quarter * 32 + lane;
+    mbar_wait(&sm->acc_full, 0);
+    tc_fence_after();
+    for (int i = 0; i < q.kh; ++i) {
+      for (int c0 = 0; c0 < kDwN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + i * kDwN + c0 + ((uint32_t)(quarter * 32) << 16), v);
+        if (c < q.C) {
+          float* p = dW + (size_t)c * q.ldw + (size_t)i * q.D + d0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {                   // red.global.add.v4.f32: D % 4 == 0, dW 16-byte aligned
+            if (d0 + c0 + j + 3 < q.D) atomicAdd(reinterpret_cast<float4*>(p + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+// G: (rows, ldg) TF32-exact gradient rows (zero where no window starts), xr: (rows_total, D) TF32-exact token rows.
+int mms_tc_sentconv_dw(mms_context* ctx, const float* G, long long rows, int ldg, const float* xr, long long rows_total,
+                       float* dW, int D, int C, int kh) {
+  static const bool disabled = getenv("MMS_NO_SENTCONV_KERNEL") != nullptr || getenv("MMS_NO_SENTCONV_DW") != nullptr;
+  if (disabled || C > 128 || kh > 5 || kh < 1 || D % 4 != 0 || ldg % 4 != 0 || rows < 1) return MMS_E_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(dW)) & 15) != 0)
+    return MMS_E_UNSUPPORTED;
+  DwGeom q;
+  q.kh = kh; q.D = D; q.C = C;
+  q.n_dr = (D + kDwN - 1) / kDwN;
+  q.kblocks = (rows + 31) / 32;
+  q.ksplit = (int)mms_max<long long>(1, mms_min<long long>(ctx->sm_count / q.n_dr, q.kblocks));
+  q.ldw = (long long)kh * D;
+  CUtensorMap mapG, mapX;
+  const unsigned long long dg[2] = {(unsigned long long)ldg, (unsigned long long)rows};
+  const unsigned long long sg[1] = {(unsigned long long)ldg * 4};
+  const unsigned bg[2] = {32, 32};
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapG, G, 2, dg, sg, bg, true));
+  const unsigned long long dx[2] = {(unsigned long long)D, (unsigned long long)rows_total};
+  const unsigned long long sx[1] = {(unsigned long long)D * 4};
+  const unsigned bx[2] = {32, (unsigned)kDwSlabRows};
+  MMS_TRY(mms_tc_make_map_raw(ctx, &mapX, xr, 2, dx, sx, bx, true));
+  const size_t smem = (size_t)kDwStages * 32768 + sizeof(DwSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MMS_CUDA(cudaFuncSetAttribute(sentconv_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  { MmsKernelScope ks_(ctx, "sentconv_dw_kernel");
+    sentconv_dw_kernel<<<q.n_dr * q.ksplit, kThreads, smem, ctx->stream>>>(mapG, mapX, dW, q); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
 // out(m, r) = sum_{i < kh} sum_{k < Kd} F[m*ldf + i*Kdf + k] * X[(r + i)*ldx + k]   for m < Mtot, r < rows.
 //   X: (rows_total, ldx) TF32-exact rows (rows past rows_total read as zero), F: (Mtot, ldf) TF32-exact.
 //   row_major_out 0: out[m*ld_out + r] (channel-major, the forward's Yt)   1: out[r*ld_out + m] (the backward's dx)

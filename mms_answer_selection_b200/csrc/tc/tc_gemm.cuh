@@ -61,6 +61,9 @@ int mms_tc_make_map_raw(mms_context* ctx, void* out, const float* ptr, int rank,
 // xr[(r + i)*D + d] for r < rows; MMS_E_UNSUPPORTED when the shape does not fit it (C > 128, kh > 8, D % 4).
 int mms_tc_sentconv_forward(mms_context* ctx, const float* xr, long long rows_total, const float* Wr, float* Yt,
                             long long rows, int D, int C, int kh, long long ldyt);
+// dW[c][i*D + d] += sum_r G[r*ldg + c] * xr[(r + i)*D + d] on a dedicated kernel (MMS_E_UNSUPPORTED: C > 128, kh > 5, ...)
+int mms_tc_sentconv_dw(mms_context* ctx, const float* G, long long rows, int ldg, const float* xr, long long rows_total,
+                       float* dW, int D, int C, int kh);
 // The general form (also the backward's dx): out(m, r) = sum_{i<kh} sum_{k<Kd} F[m*ldf + i*Kdf + k] * X[(r+i)*ldx + k].
 int mms_tc_sentconv_shifted(mms_context* ctx, const float* X, long long rows_total, long long ldx, int Kd, const float* F,
                             long long ldf, int Kdf, int Mtot, int kh, float* out, long long ld_out, long long rows,

@@ -56,7 +56,7 @@ def run(N=8192, L=40, D=300, C=100, kh=5, iters=5):
         l.handle.profile_enable(False)
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / iters
     conv_ms = sum(v["ms_per_step"] for k, v in prof.items() if k.startswith("conv/"))
-    gemm_ms = sum(v["ms_per_step"] for k, v in prof.items() if k.startswith("conv/tc_gemm") or k in ("conv/sentconv_fwd_kernel", "conv/sentconv_dx_kernel"))
+    gemm_ms = sum(v["ms_per_step"] for k, v in prof.items() if k.startswith("conv/tc_gemm") or k in ("conv/sentconv_fwd_kernel", "conv/sentconv_dx_kernel", "conv/sentconv_dw_kernel"))
     flops = 6.0 * N * T * kh * D * C
     act_bytes = 4.0 * N * C * T
     out = {

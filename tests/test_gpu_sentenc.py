@@ -80,6 +80,10 @@ def test_conv_golden(gold, dtype):
     (9, 23, 50, 17, 3, _lib.MMS_MATH_TF32, 2e-5),        # D % 4 != 0: no 16-byte rows for TMA -> SIMT
     (5, 12, 64, 130, 12, _lib.MMS_MATH_TF32, 1e-3),      # kernel as tall as the sentence (T = 1), C > 128
     (1, 5, 8, 1, 5, _lib.MMS_MATH_TF32, 1e-3),           # one sentence, one window, one channel
+    (70, 30, 128, 128, 3, _lib.MMS_MATH_TF32, 1e-3),     # dedicated kernels: 128 filters, 3 kernel rows
+    (513, 40, 300, 64, 5, _lib.MMS_MATH_TF32, 1e-3),     # dedicated kernels: many row tiles, ragged last tile
+    (3, 19, 36, 7, 8, _lib.MMS_MATH_TF32, 1e-3),         # 8 kernel rows: forward / dx dedicated, dW on the generic engine
+    (40, 40, 300, 120, 5, _lib.MMS_MATH_TF32, 1e-3),     # 120 filters: filter blocks of 120 rows still fit two stages
 ])
 def test_conv_vs_restatement(N, L, D, C, kh, math, tol):
     rng = np.random.default_rng(N * 1000 + D)

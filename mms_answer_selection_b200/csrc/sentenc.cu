@@ -138,9 +138,20 @@ __global__ void sentconv_pack_warp_kernel(const T* __restrict__ dtop, T* __restr
   T bsum = T(0);
   for (int n = warp / cblocks; n < N; n += stride) {
     const T* src = dtop + ((size_t)n * C + c0) * Tn;          // channels c0 .. c0+nc of sample n: nc*Tn contiguous values
-    for (int e = lane; e < nc * Tn; e += 32) {
-      const int c = e / Tn;
-      tile[c * ldt + (e - c * Tn)] = src[e];
+    if (sizeof(T) == 4 && (Tn & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const float4* src4 = reinterpret_cast<const float4*>(src);   // 16-byte loads; a vector never straddles two channels
+      const int tn4 = Tn >> 2;
+      for (int e = lane; e < nc * tn4; e += 32) {
+        const int c = e / tn4, t = (e - c * tn4) * 4;
+        const float4 v = src4[e];
+        T* d = tile + c * ldt + t;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      for (int e = lane; e < nc * Tn; e += 32) {
+        const int c = e / Tn;
+        tile[c * ldt + (e - c * Tn)] = src[e];
+      }
     }
     __syncwarp();
     if (dbias && lane < nc) {

@@ -61,7 +61,10 @@ enum {
                                 in the workspace, provided it was called with the same q / a / M pointers and
                                 sizes and no other call used the workspace since.  The caller promises that
                                 q, a and M are unchanged between that forward and this backward -- which is
-                                how Net::ForwardBackward and GradientChecker drive a layer.  Default 0
+                                how Net::ForwardBackward and GradientChecker drive a layer; writes made through
+                                this library (optimizer step, gradient exchange, forwards refilling a bottom)
+                                are detected and drop the cache, other in-place writes need
+                                mms_invalidate_caches().  Default 0
                                 (stateless: backward recomputes, like the reference, sim_cross_layer.cpp:296).
                                 The same promise lets mms_simmatrix_backward reuse the rounded q and W, and
                                 mms_sentconv_backward the rounded x, of the last forward on the handle. */
@@ -79,6 +82,17 @@ int mms_destroy(mms_handle_t h);
 int mms_set_stream(mms_handle_t h, void* cuda_stream /* cudaStream_t */);
 int mms_set_option(mms_handle_t h, int option, long long value);
 int mms_get_option(mms_handle_t h, int option, long long* value);
+/* Grows the handle's workspace to at least `bytes` now.  The workspace otherwise grows on demand with
+ * cudaStreamSynchronize + cudaFree + cudaMalloc, which is illegal while the handle's stream is being captured into a
+ * CUDA graph: a call that would have to grow it during a capture fails with MMS_E_INVALID instead of invalidating
+ * the capture.  Run the step once eagerly, or reserve here, before capturing. */
+int mms_reserve_scratch(mms_handle_t h, long long bytes);
+/* MMS_OPT_REUSE_FORWARD bookkeeping.  The library logs the byte ranges its own entry points rewrite behind
+ * unchanged pointers (tops of the forwards, weights in the optimizer step and the gradient exchange) and a backward
+ * only reuses what its forward left in the workspace if none of them overlaps the forward's operands.  A caller that
+ * changes q / a / weights IN PLACE by other means between a Forward and a later Backward (pycaffe assigning
+ * net.params[...], a cudaMemcpy into a blob, a foreign in-place layer) calls this to drop every such cache. */
+int mms_invalidate_caches(void);
 /* Synchronises the handle's stream and reports (then clears) kernel-flagged data
  * faults: returns MMS_E_FAULT if any Embed index was outside [0, V). */
 int mms_check_faults(mms_handle_t h);

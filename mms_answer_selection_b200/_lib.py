@@ -72,6 +72,8 @@ def lib():
         L.mms_set_stream.argtypes = [c_p, c_p]
         L.mms_set_option.argtypes = [c_p, c_int, c_ll]
         L.mms_get_option.argtypes = [c_p, c_int, ctypes.POINTER(c_ll)]
+        L.mms_reserve_scratch.argtypes = [c_p, c_ll]
+        L.mms_invalidate_caches.argtypes = []
         L.mms_check_faults.argtypes = [c_p]
         L.mms_launch_count.argtypes = [c_p]
         L.mms_launch_count.restype = ctypes.c_ulonglong
@@ -116,6 +118,9 @@ class Handle(object):
 
     def set_option(self, opt, value):
         check(lib().mms_set_option(self._h, opt, int(value)))
+
+    def reserve_scratch(self, nbytes):
+        check(lib().mms_reserve_scratch(self._h, int(nbytes)))
 
     def launch_count(self):
         return int(lib().mms_launch_count(self._h))

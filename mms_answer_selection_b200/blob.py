@@ -19,6 +19,12 @@ class Blob(object):
         self._shape = ()
         self._data = None
         self._diff = None
+        # parameter sharing (net.cpp:944-950): caffe::Blob::ShareData makes two blobs hold the SAME SyncedMemory
+        # object, so re-pointing that memory (P2PSync's Params rebinding the learnable blobs to a flat buffer,
+        # parallel.cpp:110-115) is seen by every sharer.  Here a sharer keeps a reference to the owning Blob and
+        # resolves data/diff through it on every access instead of snapshotting a tensor.
+        self._data_owner = None
+        self._diff_owner = None
         self.Reshape(shape)
 
     # -- shape ------------------------------------------------------------------
@@ -30,6 +36,8 @@ class Blob(object):
         if n != self.count():
             self._data = None   # reallocated lazily, like blob.cpp:40-44
             self._diff = None
+            self._data_owner = None
+            self._diff_owner = None
         self._shape = shape
         view = shape if shape else (0,)
         if self._data is not None:
@@ -73,12 +81,16 @@ class Blob(object):
 
     @property
     def data(self):
+        if self._data_owner is not None:
+            return self._data_owner.data.view(self._shape if self._shape else (0,))
         if self._data is None:
             self._data = self._alloc()
         return self._data
 
     @property
     def diff(self):
+        if self._diff_owner is not None:
+            return self._diff_owner.diff.view(self._shape if self._shape else (0,))
         if self._diff is None:
             self._diff = self._alloc()
         return self._diff
@@ -93,10 +105,16 @@ class Blob(object):
         """Adopt an existing device tensor as data (no copy); used to build flat
         parameter buffers for the data-parallel exchange (cf. parallel.cpp:110-115)."""
         assert t.numel() == max(self.count(), 0) and t.dtype == _TORCH[self.dtype]
+        if self._data_owner is not None:          # the shared storage is re-pointed, for every sharer
+            self._data_owner.set_data(t)
+            return
         self._data = t.view(self._shape)
 
     def set_diff(self, t):
         assert t.numel() == max(self.count(), 0) and t.dtype == _TORCH[self.dtype]
+        if self._diff_owner is not None:
+            self._diff_owner.set_diff(t)
+            return
         self._diff = t.view(self._shape)
 
     def set_cpu_data(self, arr, non_blocking=False):
@@ -113,8 +131,27 @@ class Blob(object):
     def cpu_diff(self):
         return self.diff.detach().cpu().numpy()
 
+    def _root(self, attr):
+        b = self
+        while getattr(b, attr) is not None:
+            b = getattr(b, attr)
+        return b
+
     def ShareData(self, other):
-        self._data = other.data   # net.cpp:944-950 parameter sharing
+        """blob.cpp:148-151 (CHECK_EQ(count_, other.count())); net.cpp:944-950 parameter sharing."""
+        if other.count() != self.count():
+            raise ValueError("ShareData: count mismatch (%d vs %d)" % (self.count(), other.count()))
+        root = other._root("_data_owner")
+        self._data_owner = None if root is self else root
+        self._data = None
 
     def ShareDiff(self, other):
-        self._diff = other.diff
+        if other.count() != self.count():
+            raise ValueError("ShareDiff: count mismatch (%d vs %d)" % (self.count(), other.count()))
+        root = other._root("_diff_owner")
+        self._diff_owner = None if root is self else root
+        self._diff = None
+
+    def shares_storage_with(self, other):
+        return (self._root("_data_owner") is other._root("_data_owner") and
+                self._root("_diff_owner") is other._root("_diff_owner"))

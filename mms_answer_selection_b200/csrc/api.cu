@@ -17,14 +17,55 @@ void mms_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+#include <mutex>
+namespace {
+struct WriteNote { uintptr_t lo, hi; unsigned long long clock; };
+constexpr int kWriteLog = 256;
+WriteNote g_writes[kWriteLog];
+unsigned long long g_write_clock = 1;      // clock of the next note; notes [clock - kWriteLog, clock) are retained
+std::mutex g_write_mu;
+}  // namespace
+unsigned long long mms_write_clock() {
+  std::lock_guard<std::mutex> lk(g_write_mu);
+  return g_write_clock;
+}
+void mms_note_write(const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_write_mu);
+  WriteNote& w = g_writes[g_write_clock % kWriteLog];
+  w.lo = p ? reinterpret_cast<uintptr_t>(p) : 0;
+  w.hi = p ? w.lo + bytes : ~(uintptr_t)0;
+  w.clock = g_write_clock++;
+}
+bool mms_unchanged_since(unsigned long long clock, const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_write_mu);
+  if (g_write_clock - clock > (unsigned long long)kWriteLog) return false;     // older notes are gone: assume changed
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes;
+  for (unsigned long long c = clock; c < g_write_clock; ++c) {
+    const WriteNote& w = g_writes[c % kWriteLog];
+    if (w.lo < hi && lo < w.hi) return false;
+  }
+  return true;
+}
+
 int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
   ctx->fwd_cache.valid = false;        // whoever asks for the scratch buffer is about to overwrite it
   ctx->sent_cache.valid = false;
   ctx->simmat_cache.valid = false;
   if (bytes > ctx->scratch_bytes) {
+    // growing means cudaStreamSynchronize + cudaFree + cudaMalloc, none of which is legal while the stream is being
+    // captured into a CUDA graph: the workspace must have its size before the capture starts (run the step once
+    // eagerly, or call mms_reserve_scratch)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+      mms_set_error("workspace of %zu bytes needed but only %zu reserved while the stream is being captured: "
+                    "pre-size it with mms_reserve_scratch or one eager call before the capture", bytes, ctx->scratch_bytes);
+      return MMS_E_INVALID;
+    }
     if (ctx->scratch) {
-      // earlier launches on the stream may still read the old buffer
+      // earlier launches on the stream and on the private streams may still read the old buffer
       MMS_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int i = 0; i < 2; ++i)
+        if (ctx->side[i]) MMS_CUDA(cudaStreamSynchronize(ctx->side[i]));
       MMS_CUDA(cudaFree(ctx->scratch));
       ctx->scratch = nullptr;
       ctx->scratch_bytes = 0;
@@ -173,6 +214,19 @@ int mms_set_option(mms_handle_t h, int option, long long value) {
   }
 }
 
+int mms_reserve_scratch(mms_handle_t h, long long bytes) {
+  MMS_REQUIRE(h, MMS_E_INVALID, "null handle");
+  MMS_REQUIRE(bytes >= 0, MMS_E_INVALID, "negative size");
+  if ((size_t)bytes <= h->scratch_bytes) return 0;
+  void* p = nullptr;
+  return mms_scratch(h, (size_t)bytes, &p);
+}
+
+int mms_invalidate_caches(void) {
+  mms_note_write(nullptr, 0);      // "everything may have changed"
+  return 0;
+}
+
 int mms_get_option(mms_handle_t h, int option, long long* value) {
   MMS_REQUIRE(h && value, MMS_E_INVALID, "null argument");
   switch (option) {
@@ -240,7 +294,8 @@ int mms_check_faults(mms_handle_t h) {
 #define MMS_DEFINE_TYPED(T, SUF)                                                                   \
   int mms_embed_forward_##SUF(mms_handle_t h, const T* idx, const T* W, const T* bias, T* top,     \
                               long long M, int D, int V) {                                         \
-    H; return mms_embed_forward_impl<T>(h, idx, W, bias, top, M, D, V);                            \
+    H; mms_note_write(top, sizeof(T) * (size_t)(M > 0 ? M : 0) * (size_t)(D > 0 ? D : 0));         \
+    return mms_embed_forward_impl<T>(h, idx, W, bias, top, M, D, V);                               \
   }                                                                                                \
   int mms_embed_backward_##SUF(mms_handle_t h, const T* idx, const T* dtop, T* dW, T* dbias,       \
                                long long M, int D, int V) {                                        \
@@ -293,7 +348,8 @@ int mms_check_faults(mms_handle_t h) {
   int mms_adadelta_step_##SUF(mms_handle_t h, T* data, T* diff, T* hist_g, T* hist_u,              \
                               long long count, T grad_scale, T local_decay, T momentum, T delta,   \
                               T local_rate, int clear_diff) {                                      \
-    H; return mms_adadelta_step_impl<T>(h, data, diff, hist_g, hist_u, count, grad_scale,          \
+    H; if (data) mms_note_write(data, sizeof(T) * (size_t)(count > 0 ? count : 0));                \
+    return mms_adadelta_step_impl<T>(h, data, diff, hist_g, hist_u, count, grad_scale,             \
                                         local_decay, momentum, delta, local_rate, clear_diff);     \
   }                                                                                                \
   int mms_rank_map_mrr_##SUF(mms_handle_t h, const T* data, long long stride, long long offset,    \
@@ -323,8 +379,9 @@ int mms_check_faults(mms_handle_t h) {
   int mms_pool_forward_##SUF(mms_handle_t h, const T* x, T* top, int* mask, long long NC, int H_,  \
                              int W_, int PH, int PW, int kh, int kw, int sh, int sw, int pad_h,    \
                              int pad_w, int method) {                                              \
-    H; return mms_pool_forward_impl<T>(h, x, top, mask, NC, H_, W_, PH, PW, kh, kw, sh, sw, pad_h, \
-                                       pad_w, method);                                             \
+    H; mms_note_write(top, sizeof(T) * (size_t)(NC > 0 ? NC : 0) * (size_t)(PH > 0 ? PH : 0) * (size_t)(PW > 0 ? PW : 0)); \
+    return mms_pool_forward_impl<T>(h, x, top, mask, NC, H_, W_, PH, PW, kh, kw, sh, sw, pad_h,    \
+                                    pad_w, method);                                             \
   }                                                                                                \
   int mms_pool_backward_##SUF(mms_handle_t h, const T* dtop, const int* mask, T* dx, long long NC, \
                               int H_, int W_, int PH, int PW, int kh, int kw, int sh, int sw,      \
@@ -333,7 +390,8 @@ int mms_check_faults(mms_handle_t h) {
                                         pad_h, pad_w, method);                                     \
   }                                                                                                \
   int mms_tanh_forward_##SUF(mms_handle_t h, const T* x, T* y, long long count) {                  \
-    H; return mms_tanh_forward_impl<T>(h, x, y, count);                                            \
+    H; mms_note_write(y, sizeof(T) * (size_t)(count > 0 ? count : 0));                             \
+    return mms_tanh_forward_impl<T>(h, x, y, count);                                            \
   }                                                                                                \
   int mms_tanh_backward_##SUF(mms_handle_t h, const T* y, const T* dy, T* dx, long long count) {   \
     H; return mms_tanh_backward_impl<T>(h, y, dy, dx, count);                                      \
@@ -341,7 +399,8 @@ int mms_check_faults(mms_handle_t h) {
   int mms_bn_forward_##SUF(mms_handle_t h, const T* x, const T* scale, const T* shift,             \
                            T* run_mean, T* run_var, T* top, T* x_norm, T* batch_mean,              \
                            T* batch_std, int N, int C, int HW, int train, T bn_memory, T var_eps) {\
-    H; return mms_bn_forward_impl<T>(h, x, scale, shift, run_mean, run_var, top, x_norm,           \
+    H; mms_note_write(top, sizeof(T) * (size_t)(N > 0 ? N : 0) * (size_t)(C > 0 ? C : 0) * (size_t)(HW > 0 ? HW : 0)); \
+    return mms_bn_forward_impl<T>(h, x, scale, shift, run_mean, run_var, top, x_norm,              \
                                      batch_mean, batch_std, N, C, HW, train, bn_memory, var_eps);  \
   }                                                                                                \
   int mms_bn_backward_##SUF(mms_handle_t h, const T* dtop, const T* x_norm, const T* scale,        \

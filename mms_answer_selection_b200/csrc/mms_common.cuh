@@ -35,6 +35,7 @@ struct mms_context {
     bool valid = false;
     const void *q = nullptr, *a = nullptr, *M = nullptr;
     int N = 0, Lq = 0, La = 0, D = 0, mc = 0;
+    unsigned long long generation = 0;   // mms_content_generation() when the forward ran
   } fwd_cache;
   // Sentence convolution: the forward leaves the TF32-rounded copy of x at the head of the scratch buffer; with
   // MMS_OPT_REUSE_FORWARD the backward on the same handle reads it instead of rounding x again.
@@ -43,14 +44,26 @@ struct mms_context {
     const void* x = nullptr;
     long long rows = 0;
     int D = 0;
+    unsigned long long generation = 0;
   } sent_cache;
   // SimMatrix: likewise the rounded q and W ([qr | Wr] at the head of the scratch buffer)
   struct SimMatCache {
     bool valid = false;
     const void *q = nullptr, *W = nullptr;
     int N = 0, K1 = 0, K2 = 0;
+    unsigned long long generation = 0;
   } simmat_cache;
 };
+
+// Process-wide write log behind the MMS_OPT_REUSE_FORWARD caches.  Every entry point that rewrites blob CONTENTS
+// behind unchanged pointers -- the tops written by the forwards, the weights written by the optimizer step and the
+// gradient exchange -- notes the byte range it writes (mms_note_write); mms_invalidate_caches() notes "everything".
+// A cache records mms_write_clock() when its forward ran and is honoured by a later backward only if no range noted
+// since then overlaps the operands it was built from (mms_unchanged_since): a weight update, an in-place layer or a
+// refilled bottom between a Forward and a later Backward can therefore never be paired with stale rounded copies.
+unsigned long long mms_write_clock();
+void mms_note_write(const void* p, size_t bytes);
+bool mms_unchanged_since(unsigned long long clock, const void* p, size_t bytes);
 
 // Runs the launches issued between fork(i) and join(i) on private stream i, after everything already
 // queued on the caller's stream; join(i) makes the caller's stream wait for them.

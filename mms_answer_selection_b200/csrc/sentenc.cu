@@ -330,7 +330,7 @@ int mms_sentconv_forward_impl(mms_context* ctx, const T* x, const T* W, const T*
     T* Wr = Y + n_y;
     MMS_TRY(round_copies(ctx, x, xr, rows, D, W, Wr, C, kh));
     MMS_TRY(tc_conv_forward_t(ctx, xr, Wr, Y, mrows, D, C, kh, ldyt));
-    ctx->sent_cache.valid = true; ctx->sent_cache.x = x; ctx->sent_cache.rows = rows; ctx->sent_cache.D = D;
+    ctx->sent_cache.valid = true; ctx->sent_cache.generation = mms_write_clock(); ctx->sent_cache.x = x; ctx->sent_cache.rows = rows; ctx->sent_cache.D = D;
     const long long total = (long long)N * C * Tn;
     const bool vec = sizeof(T) == 4 && Tn % 4 == 0 && L % 4 == 0 && (reinterpret_cast<uintptr_t>(top) & 15) == 0;
     { MmsKernelScope ks_(ctx, "sentconv_unpack_t_kernel");
@@ -371,7 +371,9 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
   // G = Gpad + (kh-1) rows is the row-aligned view dW uses; Gpad itself is the shifted, zero-padded view dx uses.
   const size_t n_g = need_g ? (size_t)(rows + 2 * (kh - 1)) * ldg : 0;
   const size_t n_xr = (tc && dW) ? (size_t)rows * D : 0, n_wf = dx ? (size_t)kh * ldg * D : 0;
-  const bool cached = ctx->reuse_forward && ctx->sent_cache.valid && ctx->sent_cache.x == x &&
+  const bool cached = ctx->reuse_forward && ctx->sent_cache.valid &&
+                      mms_unchanged_since(ctx->sent_cache.generation, x, sizeof(T) * (size_t)rows * D) &&
+                      ctx->sent_cache.x == x &&
                       ctx->sent_cache.rows == rows && ctx->sent_cache.D == D;
   const void* before = ctx->scratch;
   void* sp = nullptr;

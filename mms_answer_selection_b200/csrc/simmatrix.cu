@@ -86,7 +86,7 @@ inline int tc_forward(mms_context* ctx, const float* q, const float* W, float* T
   TcGemmArgs g = tc_gemm_args(qr, K1p, 0, Wr, K2p, 1, Tm, K2, N, K2, K1);   // B(n=c,k=t) = W[t][c]: MN-major
   g.operands_tf32 = 1;
   MMS_TRY(mms_tc_gemm(ctx, g));
-  ctx->simmat_cache.valid = true; ctx->simmat_cache.q = q; ctx->simmat_cache.W = W;
+  ctx->simmat_cache.valid = true; ctx->simmat_cache.generation = mms_write_clock(); ctx->simmat_cache.q = q; ctx->simmat_cache.W = W;
   ctx->simmat_cache.N = N; ctx->simmat_cache.K1 = K1; ctx->simmat_cache.K2 = K2;
   return 0;
 }
@@ -95,7 +95,10 @@ inline int tc_forward(mms_context*, const double*, const double*, double*, int, 
 inline int tc_backward(mms_context* ctx, const float* q, const float* a, const float* W, const float* ds, float* dW,
                        float* dq, float* da, int N, int K1, int K2) {
   const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
-  const bool cached = ctx->reuse_forward && ctx->simmat_cache.valid && ctx->simmat_cache.q == q &&
+  const bool cached = ctx->reuse_forward && ctx->simmat_cache.valid &&
+                      mms_unchanged_since(ctx->simmat_cache.generation, q, sizeof(float) * (size_t)N * K1) &&
+                      mms_unchanged_since(ctx->simmat_cache.generation, W, sizeof(float) * (size_t)K1 * K2) &&
+                      ctx->simmat_cache.q == q &&
                       ctx->simmat_cache.W == W && ctx->simmat_cache.N == N && ctx->simmat_cache.K1 == K1 &&
                       ctx->simmat_cache.K2 == K2;
   const void* before = ctx->scratch;

@@ -11,14 +11,13 @@
 //   backward  U[k][n] = dS[n,k] A_n            (Lq x D x La,   batch (k, n))
 //             dM_k   += Qall^T U[k]            (D x D x N*Lq,  batch k, split-K, atomics)
 //             dQall   = sum_k U[k] M_k^T       (N*Lq x D x mc*D, k as reduction segments)
-//             T[k]    = Qall M_k               (recomputed: the C-ABI is stateless)
+//             T[k]    = Qall M_k               (recomputed unless MMS_OPT_REUSE_FORWARD lets the backward
+//                                               read what the last forward left in the workspace)
 //             dA_n    = sum_k dS[n,k]^T T[k][n] (La x D x mc*Lq, batch n, k as segments)
 //
 // No operand is ever transposed in memory: the UMMA descriptors take K-major and MN-major
 // tiles alike (tc_gemm.cu).  T / U live in the handle's scratch buffer; N is processed in
 // chunks when mc*N*L*D floats exceed MMS_OPT_SCRATCH_BYTES.
-#include <stdlib.h>
-
 #include "../mms_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -88,6 +87,7 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
         if (nc == N) {
           mms_context::FwdCache& fc = ctx->fwd_cache;
           fc.q = q; fc.a = a; fc.M = Mw; fc.N = N; fc.Lq = Lq; fc.La = La; fc.D = D; fc.mc = mc;
+          fc.generation = mms_write_clock();
           mark.ok = true;
         }
         continue;
@@ -132,7 +132,10 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
   // buffer (same layout: Mr | qr | ar | per-measure intermediate) and nothing has touched the buffer since
   const mms_context::FwdCache& fc = ctx->fwd_cache;
   const size_t need = sizeof(float) * (fixed + per_pair * nc_max + (size_t)mc * 32 * Dp);   // blocked U: padded to 32-row groups
-  const bool reuse = ctx->reuse_forward && fc.valid && fc.q == q && fc.a == a && fc.M == Mw && fc.N == N &&
+  const bool unchanged = fc.valid && mms_unchanged_since(fc.generation, q, sizeof(float) * (size_t)N * Lq * D) &&
+                         mms_unchanged_since(fc.generation, a, sizeof(float) * (size_t)N * La * D) &&
+                         mms_unchanged_since(fc.generation, Mw, sizeof(float) * (size_t)mc * D * D);
+  const bool reuse = ctx->reuse_forward && unchanged && fc.q == q && fc.a == a && fc.M == Mw && fc.N == N &&
                      fc.Lq == Lq && fc.La == La && fc.D == D && fc.mc == mc && nc_max == N && need <= ctx->scratch_bytes;
   void* sp = ctx->scratch;
   if (!reuse) MMS_TRY(mms_scratch(ctx, need, &sp));
@@ -171,8 +174,7 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
     // dedicated dM kernel (tc/simcross_dm.cu) over the blocked U export; small batches are latency-bound and do
     // better with the 32-byte row-major export and the many small tiles of the generic engine (measured at 50 pairs)
     const int use_dm = mms_tc_simcross2_dm_plan(D) == 0 && (long long)nc * Lq >= 16384;
-    static const bool rowmajor_u = getenv("MMS_DM_ROWMAJOR") != nullptr;
-    const int blocked = use_dm && !rowmajor_u;                // U in the blocked layout that kernel reads best
+    const int blocked = use_dm;                               // U in the blocked layout that kernel reads best
     MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp, ksplit, blocked));   // :291-294
     if (use_dm) MMS_TRY(mms_tc_simcross2_dm(ctx, qr, U, dM, (long long)nc * Lq, D, Dp, mc, blocked));        // :286-289
     else MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));

@@ -20,6 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libmms_ref.so")
 DROPIN_SO = os.path.join(_HERE, "_ref", "libmms_dropin.so")
+REFCUDA_SO = os.path.join(_HERE, "_ref", "libmms_refcuda.so")
 PRODUCT_SO = os.path.join(os.path.dirname(_HERE), "mms_answer_selection_b200", "libmms_b200.so")
 ORACLE_SO = os.path.join(_HERE, "_build", "libmms_oracle.so")
 
@@ -46,6 +47,8 @@ def build(ref=True, oracle=True, dropin=None):
         dropin = ref
     if dropin and os.path.exists(PRODUCT_SO):
         targets.append("dropin")
+    if ref:
+        targets.append("refcuda")
     subprocess.run(["make", "-C", _HERE, "-s"] + targets, check=True)
 
 
@@ -101,6 +104,39 @@ def dropin_lib():
         _dropin = _bind(DROPIN_SO)
         _dropin.mmsref_set_mode.argtypes = [ctypes.c_int]
     return _dropin
+
+
+_refcuda = None
+
+
+def refcuda_available():
+    return os.path.exists(REFCUDA_SO)
+
+
+def refcuda_lib():
+    """The reference's own adadelta_solver.cu + math_functions.cu (nvcc, sm_100a): the GPU-side solver step."""
+    global _refcuda
+    if _refcuda is None:
+        if not os.path.exists(REFCUDA_SO):
+            raise FileNotFoundError(REFCUDA_SO + " missing: run `make -C oracle refcuda` where /root/reference exists")
+        L = ctypes.CDLL(REFCUDA_SO)
+        L.mmsrefcu_apply_update.argtypes = [ctypes.c_int, ctypes.c_longlong] + [ctypes.c_void_p] * 4 + [ctypes.c_double] * 5
+        _refcuda = L
+    return _refcuda
+
+
+def ref_apply_update(data, diff, h, h2, accum_normalization=1.0, local_decay=0.0, momentum=0.95, delta=5e-7,
+                     local_rate=1.0):
+    """One blob's SGDSolver::ApplyUpdate (GPU mode) through the reference's own CUDA routines, in place on torch CUDA
+    tensors (float32 or float64); ``data=None`` runs the bare adadelta_update_gpu."""
+    import torch
+    dt = 0 if diff.dtype == torch.float32 else 1
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    torch.cuda.synchronize()
+    rc = refcuda_lib().mmsrefcu_apply_update(dt, diff.numel(), p(data), p(diff), p(h), p(h2), accum_normalization,
+                                             local_decay, momentum, delta, local_rate)
+    if rc != 0:
+        raise RuntimeError("mmsrefcu_apply_update failed: %d" % rc)
 
 
 class RefError(RuntimeError):

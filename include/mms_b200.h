@@ -152,6 +152,20 @@ int mms_simcross_backward_f64(mms_handle_t h, int mode, const double* q, const d
                               double* dM, double* dB, int N, int Lq, int La, int D, int mc,
                               int prop0, int prop1);
 
+/* The same mode-2 backward in two calls, for a host that orders the step by data dependencies rather than layer by
+ * layer (data-parallel training: the embedding scatter-add and the exchange of the table gradient only need dq / da,
+ * so they can run while the weight gradient dM is still being computed):
+ *   _bottoms  dq, da OVERWRITTEN (sim_cross_layer.cpp:291-299); U = dS A stays in the handle's workspace.  Float /
+ *             TF32 only; MMS_E_UNSUPPORTED when the shape is outside the fused kernels or the batch does not fit
+ *             the workspace in one piece -- call mms_simcross_backward_f32 then.
+ *   _params   dM OVERWRITTEN (:256, :286-289) from that workspace -- it must be the next call on the handle after
+ *             the matching _bottoms -- and dB ACCUMULATES (:301-304; NULL without bias_term). */
+int mms_simcross_backward_bottoms_f32(mms_handle_t h, const float* q, const float* a, const float* Mw,
+                                      const float* dS, float* dq, float* da, int N, int Lq, int La, int D,
+                                      int mc);
+int mms_simcross_backward_params_f32(mms_handle_t h, const float* dS, float* dM, float* dB, int N, int Lq,
+                                     int La, int D, int mc);
+
 /* -------------------------------------------------------------- SimMatrix --
  * Replaces SimMatrixLayer::Forward_gpu (src/caffe/layers/sim_matrix_layer.cu:20-40):
  * T = q W (N,K2), written to `T` -- the reference keeps it in bottom[1]'s diff buffer
@@ -215,10 +229,75 @@ int mms_dot_f64(mms_handle_t h, const double* data, const double* diff, long lon
 
 /* ------------------------------------------------- data-parallel exchange ---
  * Replaces the root's 1/solver_count scaling of the summed gradient buffer in
- * P2PSync::on_gradients_ready (src/caffe/parallel.cpp:377, caffe_gpu_scal): x *= alpha.
- * The cross-GPU sum itself is an NCCL all-reduce issued by the host layer. */
+ * P2PSync::on_gradients_ready (src/caffe/parallel.cpp:377, caffe_gpu_scal): x *= alpha. */
 int mms_scale_f32(mms_handle_t h, float* x, long long count, float alpha);
 int mms_scale_f64(mms_handle_t h, double* x, long long count, double alpha);
+
+/* The exchange itself: replaces Params / GPUParams (parallel.cpp:60-115: all learnable blobs re-bound to one flat
+ * data and one flat diff buffer per solver) and P2PSync::on_start / on_gradients_ready (parallel.cpp:287-322 weight
+ * broadcast down the tree, :325-380 gradient sum up the tree + 1/solver_count scale on the root), one rank per GPU
+ * -- a process (torchrun) or a thread (P2PSync::InternalThreadEntry, :271-284).  Every rank owns ONE allocation
+ * [flags | data | diff] that all peers map over NVLink; one kernel launch per rank exchanges a range of the flat
+ * buffer by reading the rank's 1/world slice from every peer (fixed order: identical bits on every rank), and
+ * writing the result into every peer -- with an NVSwitch multicast mapping as multimem.ld_reduce / multimem.st.
+ * Calls are stream-ordered and capturable into CUDA graphs; cross-rank waits are bounded
+ * (MMS_EXCHANGE_OPT_TIMEOUT_MS) and reported by mms_exchange_check, never a hang.
+ *
+ *   mms_exchange_bytes        size of one rank's allocation for `count` elements of 4 / 8 bytes
+ *   mms_exchange_create       external_base NULL: the library cudaMalloc's the allocation (exportable by IPC);
+ *                             otherwise the caller's allocation of mms_exchange_bytes() (e.g. symmetric memory)
+ *   mms_exchange_buffers      this rank's flat data / diff buffers (count elements each) to re-bind the blobs to;
+ *                             blob offsets inside them must be multiples of 16 bytes
+ *   mms_exchange_export_ipc / _attach_ipc   one process per GPU: every rank exports 64 bytes, the host gathers the
+ *                             world x 64 bytes by any means (torch.distributed, MPI, a file) and attaches
+ *   mms_exchange_attach_ptrs  peers' allocations as plain pointers (threads of one process -- peer access is
+ *                             enabled here -- or symmetric memory), plus the multicast address of the same
+ *                             allocations or NULL
+ *   mms_exchange_allreduce    diff[begin, end) <- scale * sum over ranks, on every rank          (:325-380, :377)
+ *   mms_exchange_adadelta     the same sum, then the owner of each slice applies SGDSolver::ApplyUpdate with the
+ *                             AdaDelta rule (see mms_adadelta_step; history sharded over the ranks) and stores the
+ *                             new weights into every rank's data: all-reduce + replicated optimizer + the next
+ *                             on_start broadcast in one pass.  seg_end[s] (element offsets, ascending, last = end of
+ *                             the buffer) delimits blobs with local_rate seg_rate[s] and local_decay seg_decay[s].
+ *                             clear_diff: this rank's gradient range is left zeroed (Net::ClearParamDiffs).
+ *   mms_exchange_broadcast    data <- root's data on every rank                                   (:287-322)
+ * `channel` (0..MMS_EXCHANGE_CHANNELS-1) selects an independent set of flags: calls that may overlap in time (two
+ * buckets on two streams) use different channels; every rank issues the same calls in the same order per channel. */
+#define MMS_EXCHANGE_MAX_WORLD 8
+#define MMS_EXCHANGE_CHANNELS 4
+#define MMS_EXCHANGE_IPC_BYTES 64
+enum {
+  MMS_EXCHANGE_OPT_CTAS = 1,       /* CTAs per exchange kernel (0 = one per SM) */
+  MMS_EXCHANGE_OPT_TIMEOUT_MS = 2, /* bound of every cross-rank wait (default 10000) */
+  MMS_EXCHANGE_OPT_MULTICAST = 3   /* 0: ignore the multicast mapping (plain peer loads / stores) */
+};
+typedef struct mms_exchange* mms_exchange_t;
+long long mms_exchange_bytes(long long count, int elem_bytes);
+int mms_exchange_create(mms_exchange_t* out, int rank, int world, long long count, int elem_bytes,
+                        void* external_base);
+int mms_exchange_destroy(mms_exchange_t x);
+int mms_exchange_buffers(mms_exchange_t x, void** data, void** diff);
+int mms_exchange_base(mms_exchange_t x, void** base);
+int mms_exchange_export_ipc(mms_exchange_t x, void* handle64);
+int mms_exchange_attach_ipc(mms_exchange_t x, const void* handles /* world x 64 bytes, rank order */);
+int mms_exchange_attach_ptrs(mms_exchange_t x, void* const* peer_bases, void* multicast_base);
+int mms_exchange_set_option(mms_exchange_t x, int option, long long value);
+int mms_exchange_allreduce_f32(mms_exchange_t x, void* cuda_stream, int channel, long long begin, long long end,
+                               float scale);
+int mms_exchange_allreduce_f64(mms_exchange_t x, void* cuda_stream, int channel, long long begin, long long end,
+                               double scale);
+int mms_exchange_adadelta_f32(mms_exchange_t x, void* cuda_stream, int channel, long long begin, long long end,
+                              float grad_scale, const long long* seg_end, const double* seg_rate,
+                              const double* seg_decay, int nseg, float momentum, float delta, int clear_diff);
+int mms_exchange_adadelta_f64(mms_exchange_t x, void* cuda_stream, int channel, long long begin, long long end,
+                              double grad_scale, const long long* seg_end, const double* seg_rate,
+                              const double* seg_decay, int nseg, double momentum, double delta, int clear_diff);
+int mms_exchange_broadcast(mms_exchange_t x, void* cuda_stream, int channel, int root);
+/* this rank's history arrays of the fused solver step (count elements each; NULL before the first step) */
+int mms_exchange_history(mms_exchange_t x, void** hist_g, void** hist_u);
+/* synchronises the stream; MMS_E_FAULT if a cross-rank wait timed out since the last check */
+int mms_exchange_check(mms_exchange_t x, void* cuda_stream);
+unsigned long long mms_exchange_launch_count(mms_exchange_t x);
 
 /* ------------------------------------------------------------ optimizer step ---
  * mms_adadelta_update_* has the argument meaning of the reference's

@@ -14,6 +14,8 @@ MMS_MATH_TF32, MMS_MATH_FP32 = 0, 1
 MMS_OPT_MATH, MMS_OPT_PRL_GE, MMS_OPT_SCRATCH_BYTES, MMS_OPT_EMBED_DETERMINISTIC = 1, 2, 3, 4
 MMS_OPT_REUSE_FORWARD, MMS_OPT_CONCURRENCY = 5, 6
 MMS_E_INVALID, MMS_E_UNSUPPORTED, MMS_E_NOMEM, MMS_E_FAULT = -1, -2, -3, -4
+MMS_EXCHANGE_OPT_CTAS, MMS_EXCHANGE_OPT_TIMEOUT_MS, MMS_EXCHANGE_OPT_MULTICAST = 1, 2, 3
+MMS_EXCHANGE_MAX_WORLD, MMS_EXCHANGE_CHANNELS, MMS_EXCHANGE_IPC_BYTES = 8, 4, 64
 
 
 class MMSError(RuntimeError):
@@ -91,6 +93,29 @@ def lib():
         L.mms_rerank_scores_f32.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_ll, c_int, c_int]
         L.mms_rerank_prepare_f32.argtypes = [c_p, c_p, c_p, c_ll, c_int]
         L.mms_rerank_scores_prepared_f32.argtypes = [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_ll, c_int, c_int]
+        c_pp = ctypes.POINTER(c_p)
+        L.mms_exchange_bytes.argtypes = [c_ll, c_int]
+        L.mms_exchange_bytes.restype = c_ll
+        L.mms_exchange_create.argtypes = [c_pp, c_int, c_int, c_ll, c_int, c_p]
+        L.mms_exchange_destroy.argtypes = [c_p]
+        L.mms_exchange_buffers.argtypes = [c_p, c_pp, c_pp]
+        L.mms_exchange_base.argtypes = [c_p, c_pp]
+        L.mms_exchange_export_ipc.argtypes = [c_p, c_p]
+        L.mms_exchange_attach_ipc.argtypes = [c_p, c_p]
+        L.mms_exchange_attach_ptrs.argtypes = [c_p, c_pp, c_p]
+        L.mms_exchange_set_option.argtypes = [c_p, c_int, c_ll]
+        L.mms_exchange_allreduce_f32.argtypes = [c_p, c_p, c_int, c_ll, c_ll, c_f]
+        L.mms_exchange_allreduce_f64.argtypes = [c_p, c_p, c_int, c_ll, c_ll, c_d]
+        seg = [ctypes.POINTER(c_ll), ctypes.POINTER(c_d), ctypes.POINTER(c_d), c_int]
+        L.mms_exchange_adadelta_f32.argtypes = [c_p, c_p, c_int, c_ll, c_ll, c_f] + seg + [c_f, c_f, c_int]
+        L.mms_exchange_adadelta_f64.argtypes = [c_p, c_p, c_int, c_ll, c_ll, c_d] + seg + [c_d, c_d, c_int]
+        L.mms_exchange_broadcast.argtypes = [c_p, c_p, c_int, c_int]
+        L.mms_exchange_history.argtypes = [c_p, c_pp, c_pp]
+        L.mms_exchange_check.argtypes = [c_p, c_p]
+        L.mms_exchange_launch_count.argtypes = [c_p]
+        L.mms_exchange_launch_count.restype = ctypes.c_ulonglong
+        L.mms_simcross_backward_bottoms_f32.argtypes = [c_p] * 7 + [c_int] * 5
+        L.mms_simcross_backward_params_f32.argtypes = [c_p] * 4 + [c_int] * 5
         L.mms_tc_gemm_f32.argtypes = [c_p, c_p, c_ll, c_int, c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int,
                                       c_int, c_int]
         _lib = L

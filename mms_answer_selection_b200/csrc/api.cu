@@ -51,6 +51,7 @@ int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
   ctx->fwd_cache.valid = false;        // whoever asks for the scratch buffer is about to overwrite it
   ctx->sent_cache.valid = false;
   ctx->simmat_cache.valid = false;
+  ctx->dm_pending.valid = false;
   if (bytes > ctx->scratch_bytes) {
     // growing means cudaStreamSynchronize + cudaFree + cudaMalloc, none of which is legal while the stream is being
     // captured into a CUDA graph: the workspace must have its size before the capture starts (run the step once
@@ -417,6 +418,23 @@ int mms_check_faults(mms_handle_t h) {
 
 MMS_DEFINE_TYPED(float, f32)
 MMS_DEFINE_TYPED(double, f64)
+
+int mms_simcross_backward_bottoms_f32(mms_handle_t h, const float* q, const float* a, const float* Mw, const float* dS,
+                                      float* dq, float* da, int N, int Lq, int La, int D, int mc) {
+  H;
+  MMS_REQUIRE(q && a && Mw && dS && dq && da, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N > 0 && Lq > 0 && La > 0 && D > 0 && mc > 0, MMS_E_INVALID, "bad size");
+  if (h->math != MMS_MATH_TF32) return MMS_E_UNSUPPORTED;
+  return mms_tc_simcross2_backward_bottoms(h, q, a, Mw, dS, dq, da, N, Lq, La, D, mc);
+}
+int mms_simcross_backward_params_f32(mms_handle_t h, const float* dS, float* dM, float* dB, int N, int Lq, int La, int D,
+                                     int mc) {
+  H;
+  MMS_REQUIRE(dS && dM, MMS_E_INVALID, "null pointer");
+  MMS_TRY(mms_tc_simcross2_backward_params(h, dM, N, Lq, La, D, mc));
+  if (dB) MMS_TRY(mms_simcross2_bias_grad<float>(h, dS, dB, N, Lq, La, mc));
+  return 0;
+}
 
 int mms_rerank_scores_f32(mms_handle_t h, const float* Q, const float* C, const float* W, float* QW,
                           float* scores, int Nq, long long Nc, int K1, int K2) {

@@ -5,6 +5,7 @@
 #include <type_traits>
 
 #include "mms_common.cuh"
+#include "adadelta.cuh"
 
 namespace {
 
@@ -167,25 +168,6 @@ __global__ void scale_kernel(T* __restrict__ x, long long n, T alpha) {
 // parameter instead of ~20 passes): gradient scale (parallel.cpp:377 / sgd_solver.cpp:131), L2 weight decay
 // (sgd_solver.cpp:181-185), AdaDeltaUpdate (adadelta_solver.cu:7-16), Blob::Update (data -= diff) and, optionally,
 // Net::ClearParamDiffs for the next iteration (solver.cpp:203).
-// The update itself is written the way the reference's kernel is (adadelta_solver.cu:9-13), INCLUDING its quirk: gi
-// and hi are `float` locals there whatever Dtype is, so for double blobs the gradient and the refreshed gradient
-// history are narrowed to float before they enter the square root, and the update that reaches g / h2 carries float
-// precision.  Results are pinned by execution against that kernel compiled verbatim (oracle/_ref/libmms_refcuda.so).
-template <typename T>
-__device__ __forceinline__ void adadelta_one(T& w, T& g, T& h, T& h2, bool has_w, T grad_scale, T local_decay,
-                                             T momentum, T delta, T local_rate, bool clear) {
-  T gd = g;
-  if (grad_scale != T(1)) gd = gd * grad_scale;      // caffe_gpu_scal (Normalize / P2PSync's 1/n)
-  if (has_w && local_decay != T(0)) gd = local_decay * w + gd;   // caffe_gpu_axpy (Regularize, L2)
-  float gi = gd;
-  float hi = h = momentum * h + (1 - momentum) * gi * gi;
-  gi = gi * sqrt((h2 + delta) / (hi + delta));
-  h2 = momentum * h2 + (1 - momentum) * gi * gi;
-  const T upd = local_rate * gi;
-  if (has_w) w = T(-1) * upd + w;                    // Blob::Update: caffe_gpu_axpy(count, -1, diff, data)
-  g = clear ? T(0) : upd;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 adadelta_step_kernel(T* __restrict__ data, T* __restrict__ diff, T* __restrict__ hg, T* __restrict__ hu, long long n,

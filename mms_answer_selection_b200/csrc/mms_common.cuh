@@ -37,6 +37,11 @@ struct mms_context {
     int N = 0, Lq = 0, La = 0, D = 0, mc = 0;
     unsigned long long generation = 0;   // mms_content_generation() when the forward ran
   } fwd_cache;
+  // mms_simcross_backward_bottoms left U = dS A (and the rounded q) in the workspace for mms_simcross_backward_params
+  struct DmPending {
+    bool valid = false;
+    int N = 0, Lq = 0, La = 0, D = 0, mc = 0;
+  } dm_pending;
   // Sentence convolution: the forward leaves the TF32-rounded copy of x at the head of the scratch buffer; with
   // MMS_OPT_REUSE_FORWARD the backward on the same handle reads it instead of rounding x again.
   struct SentCache {
@@ -246,3 +251,9 @@ int mms_tc_simcross2_dm(mms_context*, const float* qr, const float* Ub, float* d
 int mms_tc_simcross2_backward(mms_context*, const float* q, const float* a, const float* Mw,
                               const float* dS, float* dq, float* da, float* dM, int N, int Lq, int La,
                               int D, int mc);
+// the same in two calls: bottoms (dq, da; U stays in the workspace) and, later, the weight gradient from it
+int mms_tc_simcross2_backward_bottoms(mms_context*, const float* q, const float* a, const float* Mw, const float* dS,
+                                      float* dq, float* da, int N, int Lq, int La, int D, int mc);
+int mms_tc_simcross2_backward_params(mms_context*, float* dM, int N, int Lq, int La, int D, int mc);
+template <typename T>
+int mms_simcross2_bias_grad(mms_context*, const T* dS, T* dB, int N, int Lq, int La, int mc);

@@ -247,6 +247,15 @@ int simcross2_bias_grad(mms_context* ctx, const T* dS, T* dB, int N, int Lq, int
   return 0;
 }
 
+}  // namespace
+template <typename T>
+int mms_simcross2_bias_grad(mms_context* ctx, const T* dS, T* dB, int N, int Lq, int La, int mc) {
+  return simcross2_bias_grad<T>(ctx, dS, dB, N, Lq, La, mc);
+}
+template int mms_simcross2_bias_grad<float>(mms_context*, const float*, float*, int, int, int, int);
+template int mms_simcross2_bias_grad<double>(mms_context*, const double*, double*, int, int, int, int);
+namespace {
+
 template <typename T> struct IsFloat { static constexpr bool value = false; };
 template <> struct IsFloat<float> { static constexpr bool value = true; };
 

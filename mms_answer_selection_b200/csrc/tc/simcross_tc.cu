@@ -120,8 +120,10 @@ int gemm_dM(mms_context* ctx, const float* qr, const float* U, float* dM, int ro
   return mms_tc_gemm(ctx, g);
 }
 
+// phase 0: the whole backward; 1: the bottom gradients only (dq, da; U = dS A stays in the workspace and
+// ctx->dm_pending remembers where); 2: the weight gradient from that workspace
 int backward_fused(mms_context* ctx, const float* q, const float* a, const float* Mw, const float* dS, float* dq,
-                   float* da, float* dM, int N, int Lq, int La, int D, int mc) {
+                   float* da, float* dM, int N, int Lq, int La, int D, int mc, int phase = 0) {
   const int Dp = (D + 31) & ~31;
   // scratch per pair: rounded q and a rows + the exported U (mc x Lq x Dp)
   const size_t per_pair = (size_t)(Lq + La) * Dp + (size_t)mc * Lq * Dp;
@@ -138,12 +140,27 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
   const bool reuse = ctx->reuse_forward && unchanged && fc.q == q && fc.a == a && fc.M == Mw && fc.N == N &&
                      fc.Lq == Lq && fc.La == La && fc.D == D && fc.mc == mc && nc_max == N && need <= ctx->scratch_bytes;
   void* sp = ctx->scratch;
-  if (!reuse) MMS_TRY(mms_scratch(ctx, need, &sp));
+  if (phase != 0 && nc_max != N) return MMS_E_UNSUPPORTED;      // the split form keeps U of the whole batch
+  if (phase == 2) {
+    const mms_context::DmPending& dp = ctx->dm_pending;
+    MMS_REQUIRE(dp.valid && dp.N == N && dp.Lq == Lq && dp.La == La && dp.D == D && dp.mc == mc, MMS_E_INVALID,
+                "mms_simcross_backward_params must directly follow the matching mms_simcross_backward_bottoms on this handle");
+  } else if (!reuse) {
+    MMS_TRY(mms_scratch(ctx, need, &sp));
+  }
   float* Mr = static_cast<float*>(sp);
   float* qr = Mr + fixed;
   float* ar = qr + (size_t)nc_max * Lq * Dp;
   float* U = ar + (size_t)nc_max * La * Dp;
-  MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));   // :256
+  if (phase == 2) {
+    MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));   // :256
+    const int use_dm = mms_tc_simcross2_dm_plan(D) == 0 && (long long)N * Lq >= 16384;
+    if (use_dm) MMS_TRY(mms_tc_simcross2_dm(ctx, qr, U, dM, (long long)N * Lq, D, Dp, mc, 1));        // :286-289
+    else MMS_TRY(gemm_dM(ctx, qr, U, dM, N * Lq, D, Dp, mc));
+    ctx->dm_pending.valid = false;
+    return 0;
+  }
+  if (phase == 0) MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));   // :256
   // dq (+ U, dM) and da are independent: with MMS_OPT_CONCURRENCY the da kernel runs on a private stream and each
   // kernel is sized for half of the SMs when the batch is too small to fill them
   const bool want_conc = ctx->concurrency != 0;
@@ -176,15 +193,32 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
     const int use_dm = mms_tc_simcross2_dm_plan(D) == 0 && (long long)nc * Lq >= 16384;
     const int blocked = use_dm;                               // U in the blocked layout that kernel reads best
     MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp, ksplit, blocked));   // :291-294
-    if (use_dm) MMS_TRY(mms_tc_simcross2_dm(ctx, qr, U, dM, (long long)nc * Lq, D, Dp, mc, blocked));        // :286-289
-    else MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));
+    if (phase == 0) {
+      if (use_dm) MMS_TRY(mms_tc_simcross2_dm(ctx, qr, U, dM, (long long)nc * Lq, D, Dp, mc, blocked));        // :286-289
+      else MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));
+    }
     if (conc) MMS_TRY(mms_join(ctx, 0));
     else MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit));
+  }
+  if (phase == 1) {
+    mms_context::DmPending& dp = ctx->dm_pending;
+    dp.valid = true; dp.N = N; dp.Lq = Lq; dp.La = La; dp.D = D; dp.mc = mc;
   }
   return 0;
 }
 
 }  // namespace
+
+int mms_tc_simcross2_backward_bottoms(mms_context* ctx, const float* q, const float* a, const float* Mw, const float* dS,
+                                      float* dq, float* da, int N, int Lq, int La, int D, int mc) {
+  int ksplit = 1;
+  if (mms_tc_simcross2_backward_fused_plan(0, N, Lq, La, D, mc, ctx->sm_count, &ksplit) != 0) return MMS_E_UNSUPPORTED;
+  return backward_fused(ctx, q, a, Mw, dS, dq, da, nullptr, N, Lq, La, D, mc, 1);
+}
+
+int mms_tc_simcross2_backward_params(mms_context* ctx, float* dM, int N, int Lq, int La, int D, int mc) {
+  return backward_fused(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dM, N, Lq, La, D, mc, 2);
+}
 
 // Computes dq, da (overwritten) and dM (overwritten: zeroed here, :256).  dB is left to the caller.
 int mms_tc_simcross2_backward(mms_context* ctx, const float* q, const float* a, const float* Mw,

@@ -295,6 +295,34 @@ class SimCrossLayer(Layer):
                    _p(top[0]), _p(top[0], True), _p(n0), _p(n1), _p(bottom[0], True), _p(bottom[1], True),
                    _p(Mw, True), _p(B, True), N, Lq, La, D, mc, int(propagate_down[0]), int(propagate_down[1]))
 
+    # -- the same backward in two calls (include/mms_b200.h: mms_simcross_backward_bottoms / _params) -------------
+    def BackwardBottoms(self, top, bottom):
+        """dq, da only; the weight gradient follows in BackwardParams.  Falls back to the whole Backward when the
+        library does not take the shape in split form (BackwardParams is then a no-op)."""
+        self._bind_stream()
+        self._split_pending = False
+        if self.dist_mode_ == 2 and self.dtype == np.float32:
+            N, Lq, La, D, mc = self._dims(bottom)
+            rc = lib().mms_simcross_backward_bottoms_f32(
+                self.handle.ptr, _p(bottom[0]), _p(bottom[1]), _p(self.blobs_[0]), _p(top[0], True),
+                _p(bottom[0], True), _p(bottom[1], True), N, Lq, La, D, mc)
+            if rc == 0:
+                self._split_pending = True
+                return
+            if rc != _lib.MMS_E_UNSUPPORTED:
+                check(rc)
+        self.Backward_gpu(top, [True, True], bottom)
+
+    def BackwardParams(self, top, bottom):
+        if not getattr(self, "_split_pending", False):
+            return
+        self._bind_stream()
+        N, Lq, La, D, mc = self._dims(bottom)
+        B = self.blobs_[1] if self.bias_term_ else None
+        check(lib().mms_simcross_backward_params_f32(self.handle.ptr, _p(top[0], True), _p(self.blobs_[0], True),
+                                                     _p(B, True), N, Lq, La, D, mc))
+        self._split_pending = False
+
 
 # ------------------------------------------------------------------------- SimMatrix
 class SimMatrixLayer(Layer):

@@ -164,6 +164,100 @@ class MMSNet(object):
         main.wait_stream(s2)
         return loss
 
+    def ForwardBackwardExchange(self, exch, with_loss=True, clear_diffs=True, solver=None):
+        r"""One data-parallel step ordered by its data dependencies (the reference runs Backward layer by layer and
+        only then P2PSync::on_gradients_ready, parallel.cpp:325-380): the embedding scatter-add needs dq / da only, so
+        SimCross backward is split (mms_simcross_backward_bottoms / _params) and the exchange of the table gradient --
+        73.5 of the 75 MB -- crosses NVLink on a private stream while dM and dB are still being computed:
+
+            ClearParamDiffs --------------------------------\
+            Embed(q) --\                                     +-> SimCross dq ‖ da --> Embed bwd (q ‖ a) --> exchange{W, b} --\
+            Embed(a) ---+--> SimCross fwd (+ loss dot) -----/                     \--> SimCross dM, dB --> exchange{M, B} --+--> done
+
+        ``exch``: GradientExchange over ``self.params()`` (peer-memory backend).  With ``solver`` (an
+        AdaDeltaSolver holding the hyper-parameters) the two exchanges are the fused reduce + solver step + weight
+        publication (mms_exchange_adadelta) and leave the gradients zeroed: a whole Solver::Step.  Works eagerly and
+        under stream capture."""
+        if self._side is None:
+            self._side = (torch.cuda.Stream(), torch.cuda.Stream())
+        if getattr(self, "_side3", None) is None:
+            self._side3 = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        s1, s2 = self._side
+        s3 = self._side3
+        s1.wait_stream(main)
+        s2.wait_stream(main)
+        if clear_diffs and solver is None:
+            with torch.cuda.stream(s1):
+                self.ClearParamDiffs()
+        with torch.cuda.stream(s2):
+            self.embed_a.Forward([self.idx_a], [self.a])
+        self.embed_q.Forward([self.idx_q], [self.q])
+        main.wait_stream(s2)
+        saved, self.sim.loss_ = self.sim.loss_, []
+        try:
+            self.sim.Forward([self.q, self.a], [self.S])
+        finally:
+            self.sim.loss_ = saved
+        loss = 0.0
+        if with_loss:
+            s2.wait_stream(main)
+            with torch.cuda.stream(s2):
+                loss = self.sim.ForwardLoss([self.S])
+        main.wait_stream(s1)
+        self.sim.BackwardBottoms([self.S], [self.q, self.a])
+        s2.wait_stream(main)
+        with torch.cuda.stream(s2):
+            self.embed_a.Backward([self.a], [False], [self.idx_a])
+        self.embed_q.Backward([self.q], [False], [self.idx_q])
+        main.wait_stream(s2)
+        ne = len(self.embed_q.blobs)                           # params() = Embed blobs, then SimCross blobs
+        s3.wait_stream(main)
+        with torch.cuda.stream(s3):
+            self._exchange(exch, solver, 0, ne, channel=0)
+        self.sim.BackwardParams([self.S], [self.q, self.a])
+        self._exchange(exch, solver, ne, len(self.params()), channel=1)
+        main.wait_stream(s3)
+        return loss
+
+    @staticmethod
+    def _exchange(exch, solver, first, last, channel):
+        if solver is None:
+            exch.allreduce(bucket=exch.bucket(first, last), channel=channel)
+        else:
+            exch.adadelta_step(lr_mult=solver.lr_mult, decay_mult=solver.decay_mult, base_lr=solver.GetLearningRate(),
+                               momentum=solver.momentum, delta=solver.delta, weight_decay=solver.weight_decay,
+                               iter_size=solver.iter_size, bucket_blobs=(first, last), channel=channel, clear_diffs=True)
+
+    def capture_exchange_step(self, exch, with_loss=True, clear_diffs=True, solver=None, host_inputs=None):
+        """Records ForwardBackwardExchange as ONE CUDA graph (the exchange kernels keep their epoch in device memory,
+        so a replay is a new exchange).  Two eager passes first: they size the workspaces, fill the tensor-map cache
+        and, with ``solver``, allocate the history -- and they are REAL steps, so every rank must call this the same
+        number of times.  ``host_inputs=(host_q, host_a)`` adds the H2D copies of the pinned id tensors and the D2H
+        copy of the loss to the graph (replay_exchange_from_host)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        self.sim.defer_loss_ = True
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.ForwardBackwardExchange(exch, with_loss, clear_diffs, solver)
+                exch.check()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                if host_inputs is not None:
+                    self.set_inputs_from_pinned(*host_inputs)
+                self.ForwardBackwardExchange(exch, with_loss, clear_diffs, solver)
+                if host_inputs is not None and with_loss:
+                    if getattr(self, "_host_loss", None) is None:
+                        self._host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+                    self._host_loss.copy_(self.sim.loss_dev_[0], non_blocking=True)
+        finally:
+            self.sim.defer_loss_ = False
+        return graph
+
     # -- CUDA-graph replay of the whole step ----------------------------------------------
     # The step is ~15 short kernels; issued one by one from the host it is launch-bound
     # (the reference has the same problem in the small: 2*N*mc host BLAS calls).  Recording
@@ -178,22 +272,28 @@ class MMSNet(object):
         self.sim.defer_loss_ = True
         try:
             with torch.cuda.stream(side):
+                # warm-up without the optimizer (sizes the workspaces, fills the tensor-map cache): weights, history
+                # and the iteration count are exactly what they were when the first replay runs
                 for _ in range(2):
                     self.ForwardBackwardConcurrent(with_loss, clear_diffs=False)
-                    solver.ApplyUpdate(clear_diffs=True)
+                    self.ClearParamDiffs()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            it = solver.iter
             with torch.cuda.graph(graph, stream=side):
                 self.ForwardBackwardConcurrent(with_loss, clear_diffs=False)
                 solver.ApplyUpdate(clear_diffs=True)
+            solver.iter = it                                # recording is not an iteration
         finally:
             self.sim.defer_loss_ = False
         self._graph_train = graph
         return graph
 
-    def replay_train_step(self):
+    def replay_train_step(self, solver=None):
         self._graph_train.replay()
+        if solver is not None:
+            solver.iter += 1
 
     def capture(self, with_loss=True, clear_diffs=True, host_inputs=None):
         """Records one step.  With `host_inputs=(host_q, host_a)` (pinned tensors) a second graph is recorded

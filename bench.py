@@ -1,22 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the MMS hot path on B200 (see the contract in DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+                    [--exchange p2p|p2p-multicast|nccl]
 
-A "step" is one forward+backward pass of the hot path (Embed x2 -> SimCross mode 2 ->
-loss plumbing -> SimCross backward -> Embed scatter-add) over one batch of synthetic
-TREC-QA-shaped QA pairs.  Workload by N, as BASELINE.json's configs assign them:
-  N = 1      configs[1] (C2): the reference's batch of 50 QA pairs per step, q/a length 40,
-             300-d embeddings, mesure_count 4, V = 60002 (an epoch is 1069 such steps);
-  N = 2,4,8  configs[2] (C3): a GLOBAL batch of 4096 QA pairs sharded over the ranks (strong
-             scaling), the flat gradient buffer all-reduced over NCCL and scaled by 1/N inside
-             the step.
---workload overrides.  The line also carries `extra`: candidate scores/s (configs[3], candidates
-sharded over the ranks), and at N = 1 the C3 and C5 single-GPU figures.
+A "step" is one forward+backward pass of the hot path (Embed x2 -> SimCross mode 2 -> loss plumbing -> SimCross backward
+-> Embed scatter-add, and at N > 1 the exchange of the parameter gradients) over one batch of synthetic TREC-QA-shaped
+QA pairs.  The workload is the SAME at every N -- BASELINE.json's configs[2] (C3): a GLOBAL batch of 4096 QA pairs,
+q/a length 40, 300-d embeddings, mesure_count 4, V = 60002 -- on one GPU at N = 1 and sharded 4096/N pairs per rank at
+N = 2, 4, 8 (strong scaling), so the N = 1 line is the base of the 1 -> 8 series.  --workload overrides (c2 = the
+reference's own batch of 50 pairs, c1 = its 50-d configuration); both are also measured in `extra` at N = 1, with the
+other configurations of BASELINE.json: candidate scoring (configs[3], candidates sharded over the ranks) and the
+multi-modal net (configs[4]).
 
-Prints ONE JSON line (rank 0).  `value` = QA pairs/s with inputs resident in HBM;
-`e2e` = the same through the public API with pinned-host inputs, H2D of the step's token
-ids and D2H of the step's loss inside the timed region.
+Prints ONE JSON line (rank 0).  `value` = QA pairs/s with inputs resident in HBM; `e2e` = the same through the public
+API with pinned-host inputs, H2D of the step's token ids and D2H of the step's loss inside the timed region.  At N > 1
+the line also carries `comm` (the exchange timed alone, beside a plain NCCL all-reduce of the same buffer) and `parity`
+(the exchanged gradient against rank 0 recomputing the whole 4096-pair batch alone).
 """
 import argparse
 import json
@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 METRIC = "qa_pairs_per_sec_fwd_bwd"
 UNIT = "QA pairs/s"
+NVLINK5_GBS_PER_DIRECTION = 900.0
 
 
 def flops_per_pair(L, D, mc):
@@ -56,19 +57,25 @@ def kernel_flop_shares(L, D, mc):
 
 
 def workload_config(name, world=1):
-    """Per-rank configuration: C3 fixes the GLOBAL batch (4096), so a rank gets 4096 / world pairs."""
+    """Per-rank configuration: the GLOBAL batch is fixed, a rank gets N / world pairs."""
     from mms_answer_selection_b200 import synth
     c = dict(synth.CONFIGS[name])
     c["global_N"] = c["N"]
-    if name == "c3":
-        c["N"] = max(1, c["N"] // world)
-    else:
-        c["global_N"] = c["N"] * world
+    c["N"] = max(1, c["N"] // world)
     return c
 
 
 def pick_workload(args, world):
-    return args.workload or ("c2" if world == 1 else "c3")
+    return args.workload or "c3"
+
+
+def bench_config(name, cfg, world):
+    """The `config` object of the JSON line -- built by BOTH arms from the same arguments, so the driver sees identical
+    dictionaries; anything arm-specific goes under `run`."""
+    return {"workload": workload_name(name, cfg), "name": name, "global_batch": cfg["global_N"],
+            "pairs_per_gpu": cfg["N"], "q_a_len": cfg["L"], "embedding_dim": cfg["D"], "mesure_count": cfg["mc"],
+            "vocab_rows": cfg["V"], "parallelism": "dp%d" % world,
+            "l2": "256 MiB L2 flush between timed steps (inputs + table < the 126 MB L2)"}
 
 
 # ---------------------------------------------------------------------------- reference arm
@@ -149,8 +156,10 @@ def main_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong" if wl == "c3" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(wl, cfg), "pairs_per_step": r["pairs"]},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(wl, cfg, args.gpus),
+        "run": {"pairs_per_step": r["pairs"], "note": "rank 0's share of the global batch on the host cores; each "
+                "step is a bounded sample of it"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,12 +221,77 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------- our arm
+def build_net(cfg, world, rank):
+    """MMSNet over this rank's slice of the GLOBAL synthetic batch (same seed on every rank: the global batch is
+    identical everywhere, rank r takes pairs [r N/n, (r+1) N/n)).  Each worker normalises its loss by ITS pair count, as
+    every Caffe worker does: dS of the global batch times `world`; the exchange's 1/n (parallel.cpp:377) turns the
+    sum of the per-rank means into the global-batch mean."""
+    import mms_answer_selection_b200 as mms
+    from mms_answer_selection_b200 import synth
+    N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
+    full = synth.make_qa_batch(N=cfg["global_N"], L=L, D=D, mc=mc, V=V, seed=synth.SEED)
+    sl = slice(rank * N, (rank + 1) * N)
+    net = mms.MMSNet(N, L, D, mc, V)
+    net.set_params(full["W"], full["b"], full["M"], full["B"])
+    net.set_inputs(full["idx_q"][sl], full["idx_a"][sl])
+    net.set_upstream_gradient(full["dS"][sl] * world)
+    return net, full, sl
+
+
+def elementwise_error_stats(got, ref, tol=1e-3, floor_frac=0.01):
+    """Normwise AND element-wise error of `got` against `ref` (both numpy): max |got-ref| / max|ref| (the
+    GradientChecker-style figure the tests bound), and among the elements with |ref| >= floor_frac * max|ref| the
+    largest relative error and the fraction above `tol`."""
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    m = float(np.abs(ref).max()) if ref.size else 0.0
+    if m == 0.0:
+        return {"max_scaled_err": float(np.abs(got).max()) if got.size else 0.0, "elements_checked": 0}
+    big = np.abs(ref) >= floor_frac * m
+    rel = np.abs(got[big] - ref[big]) / np.abs(ref[big])
+    return {"max_scaled_err": float(np.abs(got - ref).max() / m),
+            "max_rel_err_above_%g_of_max" % floor_frac: float(rel.max()) if rel.size else 0.0,
+            "frac_rel_err_gt_%g" % tol: float((rel > tol).mean()) if rel.size else 0.0,
+            "elements_checked": int(big.sum())}
+
+
+def measure_tf32_peak(seconds=1.5):
+    """cuBLAS TF32 8192^3 through torch.matmul (allow_tf32), measured the way MEASURED_PEAKS.json measures bf16: best
+    of 10 single launches (burst) and back-to-back launches for `seconds` (sustained)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn((n, n), device="cuda"); b = torch.randn((n, n), device="cuda"); c = torch.empty((n, n), device="cuda")
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record(); torch.cuda.synchronize()
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops_burst": fl / (best / 1e3) / 1e12, "tf32_tflops_sustained": fl * reps / (e0.elapsed_time(e1) / 1e3) / 1e12,
+                "how": "torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS TF32): best of 10 (burst), back to back for "
+                       "%.1f s (sustained), CUDA events" % seconds}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
 
     import mms_answer_selection_b200 as mms
-    from mms_answer_selection_b200 import synth
+    from mms_answer_selection_b200 import _lib as _mmslib
     from mms_answer_selection_b200.parallel import GradientExchange
 
     rank = int(os.environ.get("RANK", "0"))
@@ -230,35 +304,46 @@ def main_ours(args):
     cfg = workload_config(wl, world)
     N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
 
-    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V, seed=synth.SEED + rank)
-    net = mms.MMSNet(N, L, D, mc, V)
-    w = synth.make_qa_batch(N=1, L=L, D=D, mc=mc, V=V, seed=synth.SEED)      # same weights on every rank
-    net.set_params(w["W"], w["b"], w["M"], w["B"])
-    net.set_inputs(d["idx_q"], d["idx_a"])
-    net.set_upstream_gradient(d["dS"])
-    exch = GradientExchange(net.params()) if world > 1 else None
-    if exch:
+    net, full, sl = build_net(cfg, world, rank)
+    exch, exch_note = None, "none"
+    if world > 1:
+        exch, exch_note = make_exchange(net.params(), args.exchange)
         exch.broadcast_params(0)
-    host_q = torch.from_numpy(d["idx_q"]).pin_memory()
-    host_a = torch.from_numpy(d["idx_a"]).pin_memory()
+        exch.check()
+    host_q = torch.from_numpy(np.ascontiguousarray(full["idx_q"][sl])).pin_memory()
+    host_a = torch.from_numpy(np.ascontiguousarray(full["idx_a"][sl])).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     handles = [net.embed_q.handle, net.embed_a.handle, net.sim.handle]
+    count_launches = lambda: sum(h.launch_count() for h in handles) + (exch.launch_count() if exch else 0)
 
-    # The whole step (ClearParamDiffs + Forward + loss + Backward) is recorded once as a CUDA graph and
+    # The whole step (ClearParamDiffs + Forward + loss + Backward [+ exchange]) is recorded once as a CUDA graph and
     # replayed: issued launch by launch from the host the ~15 short kernels are launch-bound.
-    l0 = sum(h.launch_count() for h in handles)
-    net.capture(with_loss=True, clear_diffs=True)
-    launches_per_step = (sum(h.launch_count() for h in handles) - l0) // 3      # 2 warm-up passes + the capture
-    net.capture(with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a))  # + H2D / D2H nodes for the e2e step
+    in_graph = exch is not None and exch.backend == "p2p"
+    l0 = count_launches()
+    if in_graph:
+        graph = net.capture_exchange_step(exch, with_loss=True, clear_diffs=True)
+        launches_per_step = (count_launches() - l0) // 3                      # 2 warm-up passes + the capture
+        graph_host = net.capture_exchange_step(exch, with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a))
+    else:
+        net.capture(with_loss=True, clear_diffs=True)
+        launches_per_step = (count_launches() - l0) // 3 + (1 if exch else 0)
+        net.capture(with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a))  # + H2D / D2H nodes for the e2e step
 
     def device_step():
+        if in_graph:
+            graph.replay()
+            return
         net.replay(read_loss=False)
         if exch:
             exch.allreduce()
 
     def e2e_step():
+        if in_graph:
+            # one graph launch: H2D of this step's inputs (pinned), the step incl. the exchange, D2H of the loss, a sync
+            graph_host.replay()
+            torch.cuda.current_stream().synchronize()
+            return float(net._host_loss[0])
         if not exch:
-            # one graph launch: H2D of this step's inputs (pinned), the step, D2H of the loss (4 bytes), then a sync
             return net.replay_from_host()
         net.set_inputs_from_pinned(host_q, host_a)      # H2D of this step's inputs
         net.replay(read_loss=False)
@@ -285,10 +370,7 @@ def main_ours(args):
             e1.record()
         barrier()
         ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_ms(ms, world)
 
     for _ in range(max(args.warmup, 3)):
         device_step()
@@ -302,6 +384,18 @@ def main_ours(args):
         e2e_step()
     e2e_ms = timed(e2e_step, args.steps)
     clocks = sampler.stop()          # sampled every 5 ms over both timed regions (device-resident and end-to-end)
+    if exch:
+        exch.check()
+
+    # ---- parity of the exchanged gradient (N > 1): one more step, then rank 0 recomputes the GLOBAL batch alone
+    parity = None
+    if exch:
+        device_step()
+        torch.cuda.synchronize()
+        parity = exchange_parity(net, exch, cfg, full, world, rank)
+
+    # ---- the exchange alone (N > 1)
+    comm = comm_benchmark(exch, world, rank, flush, args) if exch else None
 
     # roofline of the dominant kernel, measured live with CUDA events around each launch of an
     # eagerly issued step.  The GPU is first given ~0.5 ms of other work (L2 flushes) so that every
@@ -309,7 +403,6 @@ def main_ours(args):
     # host launch latency.
     sim_state = net.sim.defer_loss_
     net.sim.defer_loss_ = True
-    from mms_answer_selection_b200 import _lib as _mmslib
     net.sim.handle.set_option(_mmslib.MMS_OPT_CONCURRENCY, 0)     # one kernel at a time: the events bracket it alone
     for h in handles:
         h.profile_enable(True)
@@ -334,20 +427,21 @@ def main_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roof = roofline_for(dom[0], dom[1], prof, prof_steps, cfg, peaks, wl)
+    tf32 = measure_tf32_peak() if (rank == 0 and world == 1 and not args.no_extra) else None
+    roof = roofline_for(dom[0], dom[1], prof, prof_steps, cfg, peaks, wl, tf32)
 
     value = N * world * args.steps / (total_ms / 1e3)
     e2e_value = N * world * args.steps / (e2e_ms / 1e3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if wl == "c3" else "weak", "vs_baseline": None,
+        "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (TF32 tensor-core contractions, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": workload_name(wl, cfg), "parallelism": "dp%d" % world,
-                   "l2": "256 MiB L2 flush between timed steps (inputs+table < L2)",
-                   "launch": "step recorded as one CUDA graph (%d kernels of libmms_b200.so per step)" % launches_per_step,
-                   "grad_exchange": "one NCCL all-reduce (ncclAvg) of the flat gradient buffer" if world > 1 else "none"},
+        "config": bench_config(wl, cfg, world),
+        "run": {"launch": "step recorded as one CUDA graph (%d kernels of libmms_b200.so per step)" % launches_per_step,
+                "grad_exchange": exch_note,
+                "algorithmic_tflops_per_gpu": N * flops_per_pair(L, D, mc) / (total_ms / args.steps / 1e3) / 1e12},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(host_q.numel() * 4 + host_a.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
@@ -357,8 +451,14 @@ def main_ours(args):
         "kernel_step_ms_sum": step_ms_prof,
         "hbm_kernels": hbm_kernel_table(prof, prof_steps, cfg, peaks),
     }
+    if tf32:
+        line["peaks"] = dict(tf32, bf16_tflops_burst_driver=peaks.get("bf16_tflops"), hbm_gbs_driver=peaks.get("hbm_gbs"))
+    if comm is not None:
+        line["comm"] = comm
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_extra:
-        line["extra"] = extras(world, rank, flush)
+        line["extra"] = extras(world, rank, flush, args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = time_reference(cfg, steps=3, warmup=1, budget_s=20.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
@@ -366,8 +466,139 @@ def main_ours(args):
     if rank == 0:
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def make_exchange(params, mode):
+    """GradientExchange over the net's learnable blobs.  "p2p": csrc/exchange.cu over cudaIpc-mapped peer memory;
+    "p2p-multicast": the same kernel over torch symmetric memory with the NVSwitch multicast mapping; "nccl": the
+    library all-reduce (baseline).  A peer-memory set-up that fails on this box falls back to NCCL -- loudly, in the
+    line's `run.grad_exchange` -- so that a scaling series is never lost to a mapping problem."""
+    import torch.distributed as dist
+    from mms_answer_selection_b200.parallel import GradientExchange
+    if mode == "nccl":
+        return GradientExchange(params, backend="nccl"), "one NCCL all-reduce (ncclAvg) of the flat gradient buffer after the graph"
+    ok = 1
+    ex = None
+    try:
+        ex = GradientExchange(params, backend="p2p", symmetric=(mode == "p2p-multicast"))
+    except Exception as e:          # noqa: BLE001
+        ok = 0
+        sys.stderr.write("peer-memory exchange unavailable on this rank: %r\n" % (e,))
+    import torch
+    t = torch.tensor([ok], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 1:
+        how = "multimem.ld_reduce/st over the NVSwitch multicast mapping" if ex.multicast else "peer loads/stores"
+        return ex, ("csrc/exchange.cu (%s): table bucket on a private stream overlapping dM/dB, SimCross bucket after; "
+                    "both inside the step's CUDA graph" % how)
+    if ex is not None:
+        raise RuntimeError("peer-memory exchange came up on some ranks only; blobs are already re-bound -- aborting")
+    return GradientExchange(params, backend="nccl"), "FALLBACK: peer-memory mapping failed here; one NCCL all-reduce (ncclAvg) after the graph"
+
+
+def exchange_parity(net, exch, cfg, full, world, rank):
+    """The exchanged (averaged) flat gradient of the sharded step against ONE GPU computing the global batch (rank 0
+    recomputes it alone), plus: are the replicas bit-identical?"""
+    import torch
+    import torch.distributed as dist
+
+    import mms_answer_selection_b200 as mms
+    flat = exch.flat_diff
+    h = flat.view(torch.int32).to(torch.int64).sum().reshape(1)
+    lo, hi = h.clone(), h.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out = {"replicas_bit_identical": bool(lo.item() == hi.item())}
+    if rank == 0:
+        L, D, mc, V = cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
+        ref = mms.MMSNet(cfg["global_N"], L, D, mc, V)
+        ref.set_params(full["W"], full["b"], full["M"], full["B"])
+        ref.set_inputs(full["idx_q"], full["idx_a"])
+        ref.set_upstream_gradient(full["dS"])
+        ref.ClearParamDiffs(); ref.ForwardBackward()
+        torch.cuda.synchronize()
+        names = ["dW_embed", "db_embed", "dM", "dB"]
+        worst = 0.0
+        for name, p, q in zip(names, net.params(), ref.params()):
+            st = elementwise_error_stats(p.cpu_diff(), q.cpu_diff())
+            out[name] = st
+            worst = max(worst, st["max_scaled_err"])
+        out["max_scaled_err"] = worst
+        out["tolerance"] = 1e-3
+        out["ok"] = bool(worst <= 1e-3 and out["replicas_bit_identical"])
+        out["what"] = ("flat gradient after the exchange (mean over %d ranks of per-rank means) vs one GPU on the whole "
+                       "%d-pair batch, TF32 contractions on both sides" % (world, cfg["global_N"]))
+        del ref
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
+
+def comm_benchmark(exch, world, rank, flush, args):
+    """The gradient exchange timed ALONE on a scratch buffer of the step's size: our kernel (whole buffer in one launch;
+    fused with the AdaDelta step), and a plain NCCL all-reduce of the same bytes for comparison.  busbw is NCCL's
+    convention 2 (n-1)/n x bytes / time, against NVLink 5's 900 GB/s per direction."""
+    import torch
+    import torch.distributed as dist
+
+    from mms_answer_selection_b200.blob import Blob
+    from mms_answer_selection_b200.parallel import GradientExchange
+    count = exch.count
+    nbytes = count * exch.elem
+    out = {"bytes": int(nbytes), "nvlink5_gbs_per_direction": NVLINK5_GBS_PER_DIRECTION}
+    iters = 20
+
+    def busbw(ms):
+        return 2.0 * (world - 1) / world * nbytes / (ms / 1e3) / 1e9
+
+    def entry(ms):
+        return {"ms": ms, "algbw_gbs": nbytes / (ms / 1e3) / 1e9, "busbw_gbs": busbw(ms),
+                "busbw_frac_of_nvlink5": busbw(ms) / NVLINK5_GBS_PER_DIRECTION}
+
+    buf = torch.ones(count, dtype=exch.flat_diff.dtype, device="cuda")
+    out["nccl_allreduce_avg"] = entry(_time_ms(lambda: dist.all_reduce(buf, op=dist.ReduceOp.AVG), iters, flush, world))
+    del buf
+    if exch.backend != "p2p":
+        return out
+    variants = [("p2p", False)]
+    if args.try_multicast:          # opt-in: a symmetric-memory rendezvous that fails on some ranks only would stall the run
+        variants.append(("p2p_multicast", True))
+    for name, symmetric in variants:
+        try:
+            b = Blob((count,))
+            ok = 1
+            try:
+                x2 = GradientExchange([b], backend="p2p", symmetric=symmetric)
+            except Exception as e:      # noqa: BLE001
+                ok = 0
+                err = repr(e)[:300]
+            t = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                out[name] = {"unavailable": err if not ok else "failed on another rank"}
+                continue
+            if symmetric and not x2.multicast:
+                out[name] = {"unavailable": "no multicast support reported for this allocation"}
+                continue
+            x2.flat_diff.fill_(1.0)
+            key = "allreduce" + ("_multimem" if x2.multicast else "")
+            r = {key: entry(_time_ms(lambda: x2.allreduce(), iters, flush, world))}
+            x2.check()
+            for ctas in (32, 64):
+                x2.set_option(1, ctas)
+                r["%s_%dctas" % (key, ctas)] = entry(_time_ms(lambda: x2.allreduce(), iters, flush, world))
+            x2.set_option(1, 0)
+            x2.adadelta_step()                           # allocates the history outside the timed loop
+            x2.check()
+            r["fused_adadelta_step"] = entry(_time_ms(lambda: x2.adadelta_step(), iters, flush, world))
+            x2.check()
+            out[name] = r
+            x2.close()
+        except Exception as e:          # noqa: BLE001
+            out[name] = {"error": repr(e)[:300]}
+    return out
 
 
 def _max_ms(ms, world):
@@ -397,71 +628,124 @@ def _time_ms(fn, iters, flush, world):
     return _max_ms(sum(a.elapsed_time(b) for a, b in evs), world) / iters
 
 
-def extras(world, rank, flush):
+def small_batch_line(name, flush, steps=30):
+    """One of the reference's own small configurations (C1: 50 pairs, D = 50; C2: 50 pairs, D = 300) on one GPU:
+    device-resident and end-to-end step times, graph replay, L2 flushed between steps."""
+    import torch
+    cfg = workload_config(name, 1)
+    net, full, sl = build_net(cfg, 1, 0)
+    host_q = torch.from_numpy(np.ascontiguousarray(full["idx_q"])).pin_memory()
+    host_a = torch.from_numpy(np.ascontiguousarray(full["idx_a"])).pin_memory()
+    handles = [net.embed_q.handle, net.embed_a.handle, net.sim.handle]
+    l0 = sum(h.launch_count() for h in handles)
+    net.capture(with_loss=True, clear_diffs=True)
+    per_step = (sum(h.launch_count() for h in handles) - l0) // 3
+    net.capture(with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a))
+    ms = _time_ms(lambda: net.replay(read_loss=False), steps, flush, 1)
+    ms_e2e = _time_ms(net.replay_from_host, steps, flush, 1)
+    N, L, D, mc = cfg["N"], cfg["L"], cfg["D"], cfg["mc"]
+    return {"workload": workload_name(name, cfg), "steps": steps, "qa_pairs_per_sec": N / (ms / 1e3), "ms_per_step": ms,
+            "e2e_qa_pairs_per_sec": N / (ms_e2e / 1e3), "e2e_ms_per_step": ms_e2e, "kernels_per_step": per_step,
+            "algorithmic_tflops": N * flops_per_pair(L, D, mc) / (ms / 1e3) / 1e12}
+
+
+def multimodal_line(world, rank, flush, exchange_mode):
+    """configs[4] (C5): 4 modalities x SimMatrix 1024 x 1024 -> Concat -> FM -> Slice -> PairRankLoss, batch 16384 (global;
+    16384 / N per rank), forward + backward into every W_m, the FM bias and the bottoms, ClearParamDiffs and -- at
+    N > 1 -- the exchange of the 16.8 MB of parameter gradients, recorded as one CUDA graph."""
+    import torch
+
+    from mms_answer_selection_b200 import synth
+    from mms_answer_selection_b200.multimodal import MultiModalNet
+    c5 = synth.CONFIGS["c5"]
+    Ng, K1, K2, nm = c5["N"], c5["K1"], c5["K2"], c5["modalities"]
+    n = Ng // world
+    net = MultiModalNet(n, K1, K2, nm)
+    g = torch.Generator(device="cuda").manual_seed(synth.SEED + rank)
+    for m in range(nm):
+        # q^, a^ ~ tanh(N(0,1)), W ~ xavier (SURVEY.md 8(d)); generated on the device (16384 x 1024 x 8 tensors)
+        net.q[m].data.copy_(torch.tanh(torch.randn((n, K1), device="cuda", generator=g)))
+        net.a[m].data.copy_(torch.tanh(torch.randn((n, K2), device="cuda", generator=g)))
+        gw = torch.Generator(device="cuda").manual_seed(synth.SEED + 100 + m)          # same weights on every rank
+        net.sim[m].blobs[0].data.copy_((torch.rand((K1, K2), device="cuda", generator=gw) * 2 - 1) * (3.0 / K1) ** 0.5)
+    net.label.data.copy_((torch.rand((n // 2, 1), device="cuda", generator=g) < 0.5).float())
+    exch, note = None, "none"
+    if world > 1:
+        exch, note = make_exchange(net.params(), exchange_mode)
+    net.capture(exch)
+    ms = _time_ms(net.replay, 10, flush, world)
+    if exch:
+        exch.check()
+    out = {"workload": "C5: %d modalities x SimMatrix %dx%d -> Concat -> FM -> Slice -> PairRankLoss(margin 1), global batch "
+                       "%d (%d per GPU), fwd+bwd (dW_m, db, dq, da) + ClearParamDiffs%s, one CUDA graph"
+                       % (nm, K1, K2, Ng, n, " + gradient exchange" if exch else ""),
+           "qa_pairs_per_sec": Ng / (ms / 1e3), "ms_per_step": ms, "loss": net.loss_value(), "grad_exchange": note,
+           "algorithmic_tflops_per_gpu": nm * 6.0 * n * K1 * K2 / (ms / 1e3) / 1e12}
+    return out
+
+
+def extras(world, rank, flush, args):
     """The other headline figures of BASELINE.json, measured briefly (a few iterations each)."""
     import ctypes
 
     import torch
 
     import mms_answer_selection_b200 as mms
-    from mms_answer_selection_b200 import _lib, layers, synth
-    from mms_answer_selection_b200.blob import Blob
+    from mms_answer_selection_b200 import _lib, synth
     out = {}
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    # ---- configs[3]: reranking, 1k queries x 1M candidates, K = 1024, candidates sharded over the ranks
+    # ---- configs[3]: reranking, 1k queries x 1M candidates, candidates sharded over the ranks; K = 1024 (C5's M) and K = 300
     c4 = synth.CONFIGS["c4"]
-    Nq, K = c4["Nq"], c4["K"]
-    Nc_local = c4["Nc"] // world
-    g = torch.Generator(device="cuda").manual_seed(synth.SEED + rank)
-    Q = torch.randn((Nq, K), device="cuda", generator=g) / K ** 0.5
-    C = torch.randn((Nc_local, K), device="cuda", generator=g) / K ** 0.5
-    W = (torch.rand((K, K), device="cuda", generator=g) * 2 - 1) * (3.0 / K) ** 0.5
-    QW = torch.empty((Nq, K), device="cuda")
-    scores = torch.empty((Nq, Nc_local), device="cuda")
     h = _lib.Handle()
     h.set_stream(torch.cuda.current_stream().cuda_stream)
+    for K, key in ((c4["K"], "candidate_scoring"), (300, "candidate_scoring_k300")):
+        Nq = c4["Nq"]
+        Nc_local = c4["Nc"] // world
+        g = torch.Generator(device="cuda").manual_seed(synth.SEED + rank)
+        Q = torch.randn((Nq, K), device="cuda", generator=g) / K ** 0.5
+        C = torch.randn((Nc_local, K), device="cuda", generator=g) / K ** 0.5
+        W = (torch.rand((K, K), device="cuda", generator=g) * 2 - 1) * (3.0 / K) ** 0.5
+        QW = torch.empty((Nq, K), device="cuda")
+        scores = torch.empty((Nq, Nc_local), device="cuda")
 
-    def rerank():
-        _lib.check(_lib.lib().mms_rerank_scores_f32(h.ptr, p(Q), p(C), p(W), p(QW), p(scores), Nq, Nc_local, K, K))
-    ms = _time_ms(rerank, 3, flush, world)
-    flops = 2.0 * Nq * K * K + 2.0 * Nq * Nc_local * K
-    out["candidate_scoring"] = {
-        "workload": "C4: %d queries x %d candidates (%d per GPU), K=%d, scores = (Q W) C^T, all scores written"
-                    % (Nq, Nc_local * world, Nc_local, K),
-        "candidate_scores_per_sec": Nq * Nc_local * world / (ms / 1e3), "ms": ms,
-        "tflops_per_gpu": flops / (ms / 1e3) / 1e12}
-    # the same against PREPARED candidates: a static candidate set is rounded to TF32 once (outside the timed call, as a
-    # static index would be) and every query batch is scored against that copy -- reported beside, never instead of,
-    # the figure above, which pays for the rounded copy inside every call
-    Cr = torch.empty((Nc_local, (K + 3) // 4 * 4), device="cuda")
-    _lib.check(_lib.lib().mms_rerank_prepare_f32(h.ptr, p(C), p(Cr), Nc_local, K))
+        def rerank():
+            _lib.check(_lib.lib().mms_rerank_scores_f32(h.ptr, p(Q), p(C), p(W), p(QW), p(scores), Nq, Nc_local, K, K))
+        ms = _time_ms(rerank, 3, flush, world)
+        flops = 2.0 * Nq * K * K + 2.0 * Nq * Nc_local * K
+        out[key] = {
+            "workload": "C4: %d queries x %d candidates (%d per GPU), K=%d, scores = (Q W) C^T, all scores written"
+                        % (Nq, Nc_local * world, Nc_local, K),
+            "candidate_scores_per_sec": Nq * Nc_local * world / (ms / 1e3), "ms": ms,
+            "tflops_per_gpu": flops / (ms / 1e3) / 1e12}
+        # the same against PREPARED candidates: a static candidate set is rounded to TF32 once (outside the timed call, as
+        # a static index would be) and every query batch is scored against that copy -- reported beside, never instead
+        # of, the figure above, which pays for the rounded copy inside every call
+        Cr = torch.empty((Nc_local, (K + 3) // 4 * 4), device="cuda")
+        _lib.check(_lib.lib().mms_rerank_prepare_f32(h.ptr, p(C), p(Cr), Nc_local, K))
 
-    def rerank_prepared():
-        _lib.check(_lib.lib().mms_rerank_scores_prepared_f32(h.ptr, p(Q), p(Cr), p(W), p(QW), p(scores), Nq, Nc_local, K, K))
-    ms_p = _time_ms(rerank_prepared, 3, flush, world)
-    out["candidate_scoring"]["prepared_candidates"] = {
-        "note": "candidate set rounded to TF32 once before the timed calls (mms_rerank_prepare), scores identical",
-        "candidate_scores_per_sec": Nq * Nc_local * world / (ms_p / 1e3), "ms": ms_p,
-        "tflops_per_gpu": flops / (ms_p / 1e3) / 1e12}
-    del C, Cr, scores, Q, QW, W
+        def rerank_prepared():
+            _lib.check(_lib.lib().mms_rerank_scores_prepared_f32(h.ptr, p(Q), p(Cr), p(W), p(QW), p(scores), Nq, Nc_local, K, K))
+        ms_p = _time_ms(rerank_prepared, 3, flush, world)
+        out[key]["prepared_candidates"] = {
+            "note": "candidate set rounded to TF32 once before the timed calls (mms_rerank_prepare), scores identical",
+            "candidate_scores_per_sec": Nq * Nc_local * world / (ms_p / 1e3), "ms": ms_p,
+            "tflops_per_gpu": flops / (ms_p / 1e3) / 1e12}
+        del C, Cr, scores, Q, QW, W
+        torch.cuda.empty_cache()
+    # ---- configs[4]: the multi-modal net, at every N
+    out["c5_multimodal"] = multimodal_line(world, rank, flush, args.exchange)
     torch.cuda.empty_cache()
     if world > 1:
         return out
-    # ---- configs[2] on ONE GPU (the base of the strong-scaling series the N > 1 runs report)
+    # ---- the reference's own small configurations on one GPU (C1: D = 50; C2: D = 300; 50 pairs per step)
+    out["c1_reference_config"] = small_batch_line("c1", flush)
+    out["c2_reference_batch"] = small_batch_line("c2", flush)
+    torch.cuda.empty_cache()
+    # ---- the C3 step as a whole solver iteration: + the fused AdaDelta update of all 18.4 M parameters (scale, weight
+    #      decay, update, Net::Update and the next iteration's ClearParamDiffs in one launch per blob)
     c3 = synth.CONFIGS["c3"]
-    d = synth.make_qa_batch(N=c3["N"], L=c3["L"], D=c3["D"], mc=c3["mc"], V=c3["V"])
-    net = mms.MMSNet(c3["N"], c3["L"], c3["D"], c3["mc"], c3["V"])
-    net.set_params(d["W"], d["b"], d["M"], d["B"])
-    net.set_inputs(d["idx_q"], d["idx_a"])
-    net.set_upstream_gradient(d["dS"])
-    net.capture(with_loss=True, clear_diffs=True)
-    ms = _time_ms(lambda: net.replay(read_loss=False), 5, flush, 1)
-    fl = c3["N"] * flops_per_pair(c3["L"], c3["D"], c3["mc"])
-    out["c3_single_gpu"] = {"workload": "C3: 4096 QA pairs/step on one GPU, D=300, mc=4 (fwd+bwd, graph replay)",
-                            "qa_pairs_per_sec": c3["N"] / (ms / 1e3), "ms_per_step": ms,
-                            "algorithmic_tflops": fl / (ms / 1e3) / 1e12}
-    # the same step as a whole solver iteration: + the fused AdaDelta update of all 18.4 M parameters (scale,
-    # weight decay, update, Net::Update and the next iteration's ClearParamDiffs in one launch per blob)
+    cfg3 = workload_config("c3", 1)
+    net, full, sl = build_net(cfg3, 1, 0)
     net.ClearParamDiffs()
     solver = mms.AdaDeltaSolver(net.params(), lr_mult=[1.0, 2.0, 1.0, 1.0][:len(net.params())],
                                 decay_mult=[0.0, 0.0, 1.0, 1.0][:len(net.params())])
@@ -470,46 +754,7 @@ def extras(world, rank, flush):
     out["c3_train_step_adadelta"] = {
         "workload": "C3 step + AdaDelta update of every learnable blob (fused optimizer launch replaces ClearParamDiffs)",
         "qa_pairs_per_sec": c3["N"] / (ms_t / 1e3), "ms_per_step": ms_t}
-    del net, d, solver
-    torch.cuda.empty_cache()
-    # ---- configs[4]: 4 modalities, SimMatrix 1024 x 1024, batch 16384, PairRankLoss on (s+, s-)
-    c5 = synth.CONFIGS["c5"]
-    N5, K1, K2, nm = c5["N"], c5["K1"], c5["K2"], c5["modalities"]
-    mods = []
-    for m in range(nm):
-        qv, av, Wv = synth.make_sentence_vectors(N5, K1, K2, seed=synth.SEED + m)
-        lay = layers.SimMatrixLayer(layers.LayerParameter("SimMatrix", sim_matrix_param=dict(
-            weight_filler=dict(type="xavier"))))
-        bq, ba, top = Blob((N5, K1)), Blob((N5, K2)), Blob(())
-        bq.set_cpu_data(qv); ba.set_cpu_data(av)
-        lay.SetUp([bq, ba], [top])
-        lay.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 1)      # Backward right after Forward on unchanged bottoms
-        lay.blobs[0].set_cpu_data(Wv)
-        top.diff.fill_(1.0 / N5)
-        mods.append((lay, bq, ba, top))
-
-    def c5_step():
-        for lay, bq, ba, top in mods:
-            lay.blobs[0].diff.zero_()
-            lay.Forward([bq, ba], [top])
-            lay.Backward([top], [True, True], [bq, ba])
-    ms_eager = _time_ms(c5_step, 3, flush, 1)
-    # the ~50 launches of the step issued from Python are host-bound; record them once and replay (as MMSNet.capture does)
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        c5_step()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    c5_graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(c5_graph, stream=side):
-        c5_step()
-    ms = _time_ms(c5_graph.replay, 5, flush, 1)
-    out["c5_multimodal"] = {"workload": "C5: %d modalities x SimMatrix %dx%d, batch %d, fwd+bwd (dW, dq, da), step replayed "
-                                        "as one CUDA graph (eager launches from Python: %.3f ms)" % (nm, K1, K2, N5, ms_eager),
-                            "qa_pairs_per_sec": N5 / (ms / 1e3), "ms_per_step": ms,
-                            "algorithmic_tflops": nm * 6.0 * N5 * K1 * K2 / (ms / 1e3) / 1e12}
-    del mods, c5_graph
+    del net, full, solver
     torch.cuda.empty_cache()
     # ---- ranking metrics on the device: MAP + MRR over a reranking score slab, grouped by query
     nq, nc = 1000, 32768
@@ -561,9 +806,14 @@ def _ncu_row(wl, name):
     (profiles/r01_ncu_full_<wl>_fused.json, written by tools/ncu_summary.py), or None."""
     alias = {"simcross2_bwd_fused_kernel<dQ>": "simcross2_bwd_fused_kernel<0, 0>",
              "simcross2_bwd_fused_kernel<dA>": "simcross2_bwd_fused_kernel<1, 0>"}
-    try:
-        rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_%s_fused.json" % wl)))
-    except Exception:
+    rows = None
+    for rnd in ("r02", "r01"):          # the newest committed capture of this workload
+        try:
+            rows = json.load(open(os.path.join(ROOT, "profiles", "%s_ncu_full_%s_fused.json" % (rnd, wl))))
+            break
+        except Exception:
+            continue
+    if rows is None:
         return None
     want = alias.get(name, name)
     for r in rows:
@@ -617,7 +867,7 @@ def hbm_kernel_table(prof, steps, cfg, peaks):
     return out
 
 
-def roofline_for(name, rec, prof, steps, cfg, peaks, wl):
+def roofline_for(name, rec, prof, steps, cfg, peaks, wl, tf32=None):
     """Roofline entry for the dominant kernel `name` (launch count, total ms over `steps`)."""
     n, ms = rec
     per_launch_s = ms / n / 1e3
@@ -632,16 +882,23 @@ def roofline_for(name, rec, prof, steps, cfg, peaks, wl):
         # the whole step: all algorithmic FLOPs over the summed device time of every contraction kernel
         fam_ms = sum(m for k, (_, m) in prof.items() if any(t in k for t in tensor_kernels))
         step_achieved = N * flops_per_pair(L, D, mc) * steps / (fam_ms / 1e3) / 1e12
+        extra_peak = {}
+        if tf32:
+            extra_peak = {"peak_cublas_tf32_burst": tf32["tf32_tflops_burst"],
+                          "peak_cublas_tf32_sustained": tf32["tf32_tflops_sustained"],
+                          "frac_of_cublas_tf32_burst": achieved / tf32["tf32_tflops_burst"]}
         return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(wl, name),
+                "frac": achieved / peak, "traffic": ncu_traffic(wl, name), **extra_peak,
                 "tensor_pipe_active_pct_ncu": ncu_tensor_pipe(wl, name),
                 "flops_per_launch": flops_launch, "ms_per_launch": per_launch_s * 1e3,
                 "step_contractions": {"achieved": step_achieved, "frac": step_achieved / peak,
                                       "ms_per_step": fam_ms / steps},
                 "note": "algorithmic FLOPs attributed to this kernel (DESIGN.md 3.1) per launch / its mean launch time "
                         "(CUDA events, one kernel at a time); step_contractions = all 6LD^2+8L^2D FLOPs / summed time of "
-                        "the contraction kernels; peak = measured cuBLAS bf16 burst / 2 (TF32), %s; traffic = DRAM "
-                        "bytes per launch from profiles/r01_ncu_full_%s_fused.json" % ("of measured" if peaks else "of fallback", wl)}
+                        "the contraction kernels; peak = driver-measured cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 "
+                        "rate), %s -- the cuBLAS TF32 8192^3 figure measured in this run is given beside it; traffic = DRAM "
+                        "bytes per launch from the committed ncu capture profiles/r0x_ncu_full_%s_fused.json"
+                        % ("of measured" if peaks else "of fallback", wl)}
     rows = N * 2 * L
     bytes_launch = rows * (4 + 8 * D) / max(launches_per_step, 1) * 1.0
     achieved = bytes_launch / per_launch_s / 1e9
@@ -658,6 +915,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-multicast", "nccl"])
+    ap.add_argument("--try-multicast", action="store_true", help="comm: also time the symmetric-memory / multimem variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

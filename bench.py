@@ -472,25 +472,44 @@ def main_ours(args):
 
 
 def make_exchange(params, mode):
-    """GradientExchange over the net's learnable blobs.  "p2p": csrc/exchange.cu over cudaIpc-mapped peer memory;
-    "p2p-multicast": the same kernel over torch symmetric memory with the NVSwitch multicast mapping; "nccl": the
-    library all-reduce (baseline).  A peer-memory set-up that fails on this box falls back to NCCL -- loudly, in the
-    line's `run.grad_exchange` -- so that a scaling series is never lost to a mapping problem."""
+    """GradientExchange over the net's learnable blobs.  "auto" (default): csrc/exchange.cu over torch symmetric memory
+    with the NVSwitch multicast mapping (multimem.ld_reduce / multimem.st) when a small probe allocation shows that
+    every rank can set it up, else the same kernel over cudaIpc-mapped peer memory (plain peer loads / stores);
+    "p2p" / "p2p-multicast" force one of the two; "nccl": the library all-reduce (baseline).  A peer-memory set-up that
+    fails on this box falls back to NCCL -- loudly, in the line's `run.grad_exchange` -- so that a scaling series is
+    never lost to a mapping problem."""
+    import torch
     import torch.distributed as dist
+    from mms_answer_selection_b200.blob import Blob
     from mms_answer_selection_b200.parallel import GradientExchange
+
+    def all_ok(flag):
+        t = torch.tensor([1 if flag else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item()) == 1
+
     if mode == "nccl":
         return GradientExchange(params, backend="nccl"), "one NCCL all-reduce (ncclAvg) of the flat gradient buffer after the graph"
-    ok = 1
-    ex = None
+    symmetric = mode == "p2p-multicast"
+    if mode == "auto":
+        ok = True
+        try:
+            probe = GradientExchange([Blob((4096,))], backend="p2p", symmetric=True)
+            ok = probe.multicast
+            probe.allreduce(); probe.check(); probe.close()
+        except Exception as e:          # noqa: BLE001
+            ok = False
+            sys.stderr.write("symmetric-memory / multicast probe failed on this rank: %r\n" % (e,))
+        symmetric = all_ok(ok)
+    ok, ex = True, None
     try:
-        ex = GradientExchange(params, backend="p2p", symmetric=(mode == "p2p-multicast"))
+        ex = GradientExchange(params, backend="p2p", symmetric=symmetric)
     except Exception as e:          # noqa: BLE001
-        ok = 0
+        ok = False
         sys.stderr.write("peer-memory exchange unavailable on this rank: %r\n" % (e,))
-    import torch
-    t = torch.tensor([ok], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    if int(t.item()) == 1:
+    if all_ok(ok):
+        if ex.multicast:
+            ex.set_option(1, 32)        # the NVSwitch does the adding: 32 CTAs saturate it and leave the SMs to dM / dB
         how = "multimem.ld_reduce/st over the NVSwitch multicast mapping" if ex.multicast else "peer loads/stores"
         return ex, ("csrc/exchange.cu (%s): table bucket on a private stream overlapping dM/dB, SimCross bucket after; "
                     "both inside the step's CUDA graph" % how)
@@ -563,7 +582,7 @@ def comm_benchmark(exch, world, rank, flush, args):
     if exch.backend != "p2p":
         return out
     variants = [("p2p", False)]
-    if args.try_multicast:          # opt-in: a symmetric-memory rendezvous that fails on some ranks only would stall the run
+    if exch.multicast or args.try_multicast:     # the symmetric-memory rendezvous is known to work here when the step uses it
         variants.append(("p2p_multicast", True))
     for name, symmetric in variants:
         try:
@@ -586,7 +605,7 @@ def comm_benchmark(exch, world, rank, flush, args):
             key = "allreduce" + ("_multimem" if x2.multicast else "")
             r = {key: entry(_time_ms(lambda: x2.allreduce(), iters, flush, world))}
             x2.check()
-            for ctas in (32, 64):
+            for ctas in ((16, 32) if x2.multicast else (74, 296)):
                 x2.set_option(1, ctas)
                 r["%s_%dctas" % (key, ctas)] = entry(_time_ms(lambda: x2.allreduce(), iters, flush, world))
             x2.set_option(1, 0)
@@ -915,7 +934,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3"])
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-multicast", "nccl"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-multicast", "nccl"])
     ap.add_argument("--try-multicast", action="store_true", help="comm: also time the symmetric-memory / multimem variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

@@ -83,6 +83,17 @@ int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
   return 0;
 }
 
+#include <set>
+int mms_prefer_max_shared(const void* func) {
+  static std::mutex mu;
+  static std::set<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(func)) return 0;
+  MMS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  done.insert(func);
+  return 0;
+}
+
 void mms_tc_destroy_state(mms_context* ctx);
 
 int mms_fork(mms_context* ctx, int i) {

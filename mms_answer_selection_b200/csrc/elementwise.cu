@@ -281,6 +281,7 @@ int mms_dot_impl(mms_context* ctx, const T* x, const T* y, long long n, T* out) 
   const int grid = red_grid(ctx, n);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(static_cast<double*>(ctx->partials) + 1024);
   { MmsKernelScope ks_(ctx, "sum_kernel");
+    MMS_CARVEOUT(sum_kernel<T>);
     sum_kernel<T><<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, partials, ticket, out); }
   MMS_LAUNCH_CHECK();
   return 0;

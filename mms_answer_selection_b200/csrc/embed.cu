@@ -185,6 +185,7 @@ inline bool launch_backward_v4<float>(mms_context* ctx, const float* idx, const 
   if (!ok) return false;
   const int threads = mms_min(128, mms_ceil_div(D / 4, 32) * 32);
   MmsKernelScope ks_(ctx, "embed_backward_runs");
+  if (mms_prefer_max_shared(reinterpret_cast<const void*>(embed_backward_runs_v4)) != 0) return false;
   embed_backward_runs_v4<<<(unsigned)grid, threads, 0, ctx->stream>>>(idx, dtop, dW, dbias, M, D, V, rows_per_cta,
                                                                       ctx->fault_flag);
   return true;
@@ -203,6 +204,7 @@ int mms_embed_forward_impl(mms_context* ctx, const T* idx, const T* W, const T* 
   const bool vec_ok = (D % VEC == 0) && aligned16(W) && aligned16(top) && (!bias || aligned16(bias));
   if (vec_ok) {
     { MmsKernelScope ks_(ctx, "embed_forward_vec");
+      MMS_CARVEOUT((embed_forward_vec<T, VEC>));
       embed_forward_vec<T, VEC><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, top, M, D, V,
                                                                            ctx->fault_flag); }
   } else {

@@ -173,11 +173,14 @@ __device__ __forceinline__ void done_round(const XDev& d, XChan* my, int channel
   }
 }
 
-template <typename T, int MODE, bool MC>
+// U = 16-byte units per thread and trip: U x world peer loads are in flight per thread (latency, not bandwidth, is what a
+// thread waits for on NVLink), so U is chosen as 16 / world by the host
+template <typename T, int MODE, bool MC, int U>
 __global__ void __launch_bounds__(kThreads)
 exchange_kernel(const XDev d, const XArgs<T> a, const XSegs segs) {
   typedef typename V16<T>::type VT;
   constexpr int VN = V16<T>::n;
+  constexpr int W = MC ? 1 : 16 / U;          // peers this instantiation walks (world <= W)
   XChan* my = chan_of(d.base[d.rank], a.channel);
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&my->epoch) + 1u;
   const bool ok = ready_round(d, my, a.channel, epoch);
@@ -194,29 +197,29 @@ exchange_kernel(const XDev d, const XArgs<T> a, const XSegs segs) {
       // slice of this rank, in 16-byte units of the range
       const long long lo = n16 * d.rank / d.world, hi = n16 * (d.rank + 1) / d.world;
       const VT* mc_diff = reinterpret_cast<const VT*>(d.mc + d.diff_off) + b16;
-      for (long long i0 = lo + blockIdx.x * (long long)kThreads * 2; i0 < hi; i0 += (long long)gridDim.x * kThreads * 2) {
-        VT acc[2];
-        bool live[2];
+      for (long long i0 = lo + blockIdx.x * (long long)kThreads * U; i0 < hi; i0 += (long long)gridDim.x * kThreads * U) {
+        VT acc[U];
+        bool live[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {                    // two independent 16-byte columns per thread: 2 x world loads in flight
+        for (int u = 0; u < U; ++u) {                    // U independent 16-byte columns per thread
           const long long i = i0 + u * kThreads + threadIdx.x;
           live[u] = i < hi;
           if (!live[u]) continue;
           if (MC) {
             acc[u] = mc_ld_reduce(mc_diff + i);
           } else {
-            VT part[kMaxWorld];
+            VT part[W];
 #pragma unroll
-            for (int q = 0; q < kMaxWorld; ++q)
+            for (int q = 0; q < W; ++q)
               if (q < d.world) part[q] = ld16(reinterpret_cast<const VT*>(d.base[q] + d.diff_off) + b16 + i);
             acc[u] = part[0];
 #pragma unroll
-            for (int q = 1; q < kMaxWorld; ++q)
+            for (int q = 1; q < W; ++q)
               if (q < d.world) vacc(acc[u], part[q]);      // fixed order 0..world-1: the same bits on every rank
           }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (!live[u]) continue;
           const long long i = i0 + u * kThreads + threadIdx.x;
           if (MODE == kAllreduce) {
@@ -225,7 +228,7 @@ exchange_kernel(const XDev d, const XArgs<T> a, const XSegs segs) {
               mc_st(reinterpret_cast<VT*>(d.mc + d.diff_off) + b16 + i, acc[u]);
             } else {
 #pragma unroll
-              for (int q = 0; q < kMaxWorld; ++q)
+              for (int q = 0; q < W; ++q)
                 if (q < d.world) st16(reinterpret_cast<VT*>(d.base[q] + d.diff_off) + b16 + i, acc[u]);
             }
           } else {   // kAdadelta: the owner updates its slice of the weights and publishes the new weights
@@ -247,7 +250,7 @@ exchange_kernel(const XDev d, const XArgs<T> a, const XSegs segs) {
               mc_st(reinterpret_cast<VT*>(d.mc + d.data_off) + b16 + i, w);
             } else {
 #pragma unroll
-              for (int q = 0; q < kMaxWorld; ++q)
+              for (int q = 0; q < W; ++q)
                 if (q < d.world) st16(reinterpret_cast<VT*>(d.base[q] + d.data_off) + b16 + i, w);
             }
           }
@@ -308,8 +311,8 @@ int check_range(const mms_exchange* x, long long begin, long long end, int chann
   return 0;
 }
 
-int grid_for(const mms_exchange* x, long long units) {
-  const long long want = (units + kThreads * 2 - 1) / (kThreads * 2);
+int grid_for(const mms_exchange* x, long long units, int U) {
+  const long long want = (units + kThreads * U - 1) / (kThreads * U);
   const int cap = x->ctas > 0 ? x->ctas : x->sm_count;
   return (int)mms_max<long long>(1, mms_min<long long>(want, cap));
 }
@@ -322,18 +325,27 @@ int launch(mms_exchange* x, cudaStream_t st, int mode, XArgs<T> a, const XSegs& 
   const long long n16 = (a.end - a.begin) / vn;
   if (n16 <= 0) return 0;
   const long long units = mode == kBroadcast ? n16 : (n16 + x->world - 1) / x->world;
-  const int grid = grid_for(x, units);
   const bool mc = x->mc != nullptr && sizeof(T) == 4;
+  const int U = (mc || x->world <= 2) ? 8 : (x->world <= 4 ? 4 : 2);      // world <= 16 / U
+  const int grid = grid_for(x, units, mode == kBroadcast ? 2 : U);
   x->launches++;
-  if (mode == kAllreduce) {
-    if (mc) exchange_kernel<T, kAllreduce, true><<<grid, kThreads, 0, st>>>(d, a, segs);
-    else exchange_kernel<T, kAllreduce, false><<<grid, kThreads, 0, st>>>(d, a, segs);
-  } else if (mode == kAdadelta) {
-    if (mc) exchange_kernel<T, kAdadelta, true><<<grid, kThreads, 0, st>>>(d, a, segs);
-    else exchange_kernel<T, kAdadelta, false><<<grid, kThreads, 0, st>>>(d, a, segs);
-  } else {
-    exchange_kernel<T, kBroadcast, false><<<grid, kThreads, 0, st>>>(d, a, segs);
-  }
+#define MMS_X_LAUNCH(MODE, MCF, UU)                                                   \
+  do {                                                                                \
+    MMS_CARVEOUT((exchange_kernel<T, MODE, MCF, UU>));                                 \
+    exchange_kernel<T, MODE, MCF, UU><<<grid, kThreads, 0, st>>>(d, a, segs);          \
+  } while (0)
+#define MMS_X_BY_U(MODE)                                                             \
+  do {                                                                               \
+    if (mc) MMS_X_LAUNCH(MODE, true, 8);                                             \
+    else if (U == 8) MMS_X_LAUNCH(MODE, false, 8);                                   \
+    else if (U == 4) MMS_X_LAUNCH(MODE, false, 4);                                   \
+    else MMS_X_LAUNCH(MODE, false, 2);                                               \
+  } while (0)
+  if (mode == kAllreduce) MMS_X_BY_U(kAllreduce);
+  else if (mode == kAdadelta) MMS_X_BY_U(kAdadelta);
+  else MMS_X_LAUNCH(kBroadcast, false, 2);
+#undef MMS_X_BY_U
+#undef MMS_X_LAUNCH
   MMS_LAUNCH_CHECK();
   return 0;
 }

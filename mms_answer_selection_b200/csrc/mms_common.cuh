@@ -109,6 +109,20 @@ void mms_set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
+// Opt-in to `bytes` of dynamic shared memory AND pin the kernel's shared-memory carveout to the maximum.  Kernels whose
+// carveouts differ cannot be resident on one SM at the same time (the SM drains before it is re-partitioned), which
+// silently serialises the branches of the step graph -- the contraction kernels, the HBM-bound kernels beside them
+// and the gradient exchange all ask for the same (largest) carveout, so they do co-reside (measured: the table
+// exchange did not overlap the dM kernel at all before this).
+#define MMS_MAX_SMEM(func, bytes)                                                                                  \
+  do {                                                                                                             \
+    MMS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));                      \
+    MMS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+  } while (0)
+// the same pin for kernels that need no opt-in (small static shared memory), once per kernel
+int mms_prefer_max_shared(const void* func);
+#define MMS_CARVEOUT(func) MMS_TRY(mms_prefer_max_shared(reinterpret_cast<const void*>(func)))
+
 #define MMS_REQUIRE(cond, code, msg)                                                    \
   do {                                                                                  \
     if (!(cond)) {                                                                      \

@@ -346,7 +346,7 @@ int mms_sentconv_forward_impl(mms_context* ctx, const T* x, const T* W, const T*
   MMS_REQUIRE(smem <= 200 * 1024, MMS_E_UNSUPPORTED, "output tile of one sentence exceeds shared memory");
   static bool configured[2] = {false, false};
   if (!configured[sizeof(T) == 8]) {
-    MMS_CUDA(cudaFuncSetAttribute(sentconv_unpack_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MMS_MAX_SMEM(sentconv_unpack_kernel<T>, 200 * 1024);
     configured[sizeof(T) == 8] = true;
   }
   { MmsKernelScope ks_(ctx, "sentconv_unpack_kernel");
@@ -403,7 +403,7 @@ int mms_sentconv_backward_impl(mms_context* ctx, const T* x, const T* W, const T
   MMS_REQUIRE(smem <= 200 * 1024, MMS_E_UNSUPPORTED, "gradient tile of one sentence exceeds shared memory");
   static bool configured[2] = {false, false};
   if (!configured[sizeof(T) == 8]) {
-    MMS_CUDA(cudaFuncSetAttribute(sentconv_pack_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MMS_MAX_SMEM(sentconv_pack_kernel<T>, 200 * 1024);
     configured[sizeof(T) == 8] = true;
   }
   { MmsKernelScope ks_(ctx, "sentconv_pack_kernel");

@@ -236,6 +236,7 @@ int simcross2_bias_grad(mms_context* ctx, const T* dS, T* dB, int N, int Lq, int
     const int per4 = per / 4, gx = mms_ceil_div(per4, 128);
     dim3 grid(gx, max(1, min(mms_ceil_div(N, 8), mms_ceil_div(8 * ctx->sm_count, gx))));
     { MmsKernelScope ks_(ctx, "bias_grad_kernel");
+      MMS_CARVEOUT(bias_grad_vec_kernel);
       bias_grad_vec_kernel<<<grid, 128, 0, ctx->stream>>>(reinterpret_cast<const float*>(dS), reinterpret_cast<float*>(dB), N, per4); }
     MMS_LAUNCH_CHECK();
     return 0;

@@ -323,7 +323,7 @@ int mms_tc_sentconv_dw(mms_context* ctx, const float* G, long long rows, int ldg
   const size_t smem = (size_t)kDwStages * 32768 + sizeof(DwSmem) + 1024;
   static bool configured = false;
   if (!configured) {
-    MMS_CUDA(cudaFuncSetAttribute(sentconv_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MMS_MAX_SMEM(sentconv_dw_kernel, 227 * 1024);
     configured = true;
   }
   { MmsKernelScope ks_(ctx, "sentconv_dw_kernel");
@@ -373,7 +373,7 @@ int mms_tc_sentconv_shifted(mms_context* ctx, const float* X, long long rows_tot
   MMS_TRY(mms_tc_make_map_raw(ctx, &mapW, F, 2, dw, sw, bw, false));
   static bool configured = false;
   if (!configured) {
-    MMS_CUDA(cudaFuncSetAttribute(sentconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MMS_MAX_SMEM(sentconv_fwd_kernel, 227 * 1024);
     configured = true;
   }
   const unsigned grid = mms_min<unsigned>(q.tiles, (unsigned)ctx->sm_count);

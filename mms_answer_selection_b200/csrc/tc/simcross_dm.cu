@@ -241,7 +241,7 @@ int mms_tc_simcross2_dm(mms_context* ctx, const float* qr, const float* Ub, floa
   }
   static bool configured = false;
   if (!configured) {
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_dm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MMS_MAX_SMEM(simcross2_dm_kernel, 227 * 1024);
     configured = true;
   }
   const size_t smem = (size_t)stages * g.stage_bytes + sizeof(DmSmem) + 1024;

@@ -341,10 +341,8 @@ int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const floa
 
   static bool configured = false;
   if (!configured) {
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_fwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_fwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
+    MMS_MAX_SMEM(simcross2_fwd_fused_kernel<false>, 227 * 1024);
+    MMS_MAX_SMEM(simcross2_fwd_fused_kernel<true>, 227 * 1024);
     configured = true;
   }
   const size_t smem = (size_t)stages * g.stage_bytes + sizeof(FwdSmem) + 1024;

@@ -695,10 +695,10 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
 
   static bool configured = false;
   if (!configured) {
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MMS_CUDA(cudaFuncSetAttribute(simcross2_bwd_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MMS_MAX_SMEM((simcross2_bwd_fused_kernel<false, false>), 227 * 1024);
+    MMS_MAX_SMEM((simcross2_bwd_fused_kernel<true, false>), 227 * 1024);
+    MMS_MAX_SMEM((simcross2_bwd_fused_kernel<false, true>), 227 * 1024);
+    MMS_MAX_SMEM((simcross2_bwd_fused_kernel<true, true>), 227 * 1024);
     configured = true;
   }
   const size_t smem = (size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024;

@@ -369,7 +369,7 @@ int mms_tc_gemm_staged(mms_context* ctx, const TcGemmArgs& a) {
   static bool configured = false;
   if (!configured) {
     for (int i = 0; i < 4; ++i)
-      MMS_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+      MMS_MAX_SMEM(kernels[i], 201 * 1024);
     configured = true;
   }
   const kernel_t kernel = kernels[(a.a_mn ? 2 : 0) + (a.b_mn ? 1 : 0)];

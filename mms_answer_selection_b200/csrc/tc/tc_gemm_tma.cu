@@ -677,6 +677,7 @@ int mms_tf32_round(mms_context* ctx, const RoundJob* jobs, int njobs) {
   if (biggest == 0) return 0;
   const int gx = (int)mms_min<long long>((biggest / 4 + 255) / 256 + 1, (long long)ctx->sm_count * 8);
   { MmsKernelScope ks_(ctx, "tf32_round_kernel");
+    MMS_CARVEOUT(tf32_round_kernel);
     tf32_round_kernel<<<dim3(gx, njobs), 256, 0, ctx->stream>>>(js); }
   MMS_LAUNCH_CHECK();
   return 0;
@@ -723,7 +724,7 @@ int gemm_tma_pair(mms_context* ctx, const TcGemmArgs& a) {
   static bool configured = false;
   if (!configured) {
     for (int i = 0; i < 4; ++i)
-      MMS_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+      MMS_MAX_SMEM(kernels[i], 221 * 1024);
     configured = true;
   }
   const kernel_t kernel = kernels[(a.a_mn ? 2 : 0) + (a.b_mn ? 1 : 0)];
@@ -784,7 +785,7 @@ int mms_tc_gemm_tma(mms_context* ctx, const TcGemmArgs& a) {
   static bool configured = false;
   if (!configured) {
     for (int i = 0; i < 4; ++i)
-      MMS_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+      MMS_MAX_SMEM(kernels[i], 221 * 1024);
     configured = true;
   }
   const kernel_t kernel = kernels[(a.a_mn ? 2 : 0) + (a.b_mn ? 1 : 0)];

@@ -164,7 +164,7 @@ class MMSNet(object):
         main.wait_stream(s2)
         return loss
 
-    def ForwardBackwardExchange(self, exch, with_loss=True, clear_diffs=True, solver=None):
+    def ForwardBackwardExchange(self, exch, with_loss=True, clear_diffs=True, solver=None, overlap=True):
         r"""One data-parallel step ordered by its data dependencies (the reference runs Backward layer by layer and
         only then P2PSync::on_gradients_ready, parallel.cpp:325-380): the embedding scatter-add needs dq / da only, so
         SimCross backward is split (mms_simcross_backward_bottoms / _params) and the exchange of the table gradient --
@@ -212,6 +212,10 @@ class MMSNet(object):
         self.embed_q.Backward([self.q], [False], [self.idx_q])
         main.wait_stream(s2)
         ne = len(self.embed_q.blobs)                           # params() = Embed blobs, then SimCross blobs
+        if not overlap:                                        # the reference's order: all of Backward, then one exchange
+            self.sim.BackwardParams([self.S], [self.q, self.a])
+            self._exchange(exch, solver, 0, len(self.params()), channel=0)
+            return loss
         s3.wait_stream(main)
         with torch.cuda.stream(s3):
             self._exchange(exch, solver, 0, ne, channel=0)
@@ -229,7 +233,7 @@ class MMSNet(object):
                                momentum=solver.momentum, delta=solver.delta, weight_decay=solver.weight_decay,
                                iter_size=solver.iter_size, bucket_blobs=(first, last), channel=channel, clear_diffs=True)
 
-    def capture_exchange_step(self, exch, with_loss=True, clear_diffs=True, solver=None, host_inputs=None):
+    def capture_exchange_step(self, exch, with_loss=True, clear_diffs=True, solver=None, host_inputs=None, overlap=True):
         """Records ForwardBackwardExchange as ONE CUDA graph (the exchange kernels keep their epoch in device memory,
         so a replay is a new exchange).  Two eager passes first: they size the workspaces, fill the tensor-map cache
         and, with ``solver``, allocate the history -- and they are REAL steps, so every rank must call this the same
@@ -241,7 +245,7 @@ class MMSNet(object):
         try:
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self.ForwardBackwardExchange(exch, with_loss, clear_diffs, solver)
+                    self.ForwardBackwardExchange(exch, with_loss, clear_diffs, solver, overlap)
                 exch.check()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
@@ -249,7 +253,7 @@ class MMSNet(object):
             with torch.cuda.graph(graph, stream=side):
                 if host_inputs is not None:
                     self.set_inputs_from_pinned(*host_inputs)
-                self.ForwardBackwardExchange(exch, with_loss, clear_diffs, solver)
+                self.ForwardBackwardExchange(exch, with_loss, clear_diffs, solver, overlap)
                 if host_inputs is not None and with_loss:
                     if getattr(self, "_host_loss", None) is None:
                         self._host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()

@@ -138,7 +138,7 @@ class GradientExchange(object):
         name = (self.group or dist.group.WORLD).group_name
         hdl = symm_mem.rendezvous(t, group=name)
         self._symm = (t, hdl)
-        mc = int(hdl.multicast_ptr) if hdl.has_multicast_support(dev.type, dev.index) else 0
+        mc = int(hdl.multicast_ptr or 0)                  # 0 when the allocation has no NVSwitch multicast object
         return int(t.data_ptr()), [int(p) for p in hdl.buffer_ptrs], mc
 
     def close(self):

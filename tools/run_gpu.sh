@@ -39,7 +39,7 @@ for stage in "$@"; do
       timeout 600 python -m pytest tests -q -m gpu -rs -k "multigpu" > gpurun_out/pytest_multigpu_n$N.log 2>&1
       echo "pytest multigpu rc=$?"; tail -4 gpurun_out/pytest_multigpu_n$N.log
       NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL,TUNING timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-        --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n$N.log 2> gpurun_out/bench_n$N.err
+        --master-port 29511 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_n$N.log 2> gpurun_out/bench_n$N.err
       echo "bench N=$N rc=$?"; grep -v NCCL gpurun_out/bench_n$N.err | tail -3; summ gpurun_out/bench_n$N.log
       grep -E "NCCL INFO (Connected|Channel 00/|.*NVLS|.*Algo|comm .* rank 0 )" gpurun_out/bench_n$N.err | head -40 > gpurun_out/nccl_info_n$N.log
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \

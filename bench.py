@@ -703,6 +703,31 @@ def multimodal_line(world, rank, flush, exchange_mode):
     return out
 
 
+def embed_backward_modes(flush):
+    """One Embed backward of the C3 step (163 840 token rows x 300, V = 60002, centre-padded ids) in both modes."""
+    import ctypes
+
+    import torch
+
+    from mms_answer_selection_b200 import _lib, synth
+    c3 = synth.CONFIGS["c3"]
+    M, D, V = c3["N"] * c3["L"], c3["D"], c3["V"]
+    rng = np.random.default_rng(synth.SEED)
+    idx = torch.from_numpy(synth.make_indices(rng, c3["N"], c3["L"], V, 5, 40).reshape(-1)).cuda()
+    g = torch.randn((M, D), device="cuda") * 1e-6
+    dW = torch.zeros((V, D), device="cuda"); db = torch.zeros(D, device="cuda")
+    h = _lib.Handle()
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    out = {"workload": "Embed backward, %d token rows x %d floats into a %d-row table (one of the two calls of a C3 step)" % (M, D, V)}
+    for name, det in (("atomic", 0), ("deterministic", 1)):
+        h.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, det)
+        fn = lambda: _lib.check(_lib.lib().mms_embed_backward_f32(h.ptr, p(idx), p(g), p(dW), p(db), M, D, V))
+        ms = _time_ms(fn, 10, flush, 1)
+        out[name] = {"ms": ms, "algorithmic_gbs": (M * (4 + 4 * D) + M * 8 * D) / (ms / 1e3) / 1e9}
+    return out
+
+
 def extras(world, rank, flush, args):
     """The other headline figures of BASELINE.json, measured briefly (a few iterations each)."""
     import ctypes
@@ -775,6 +800,8 @@ def extras(world, rank, flush, args):
         "qa_pairs_per_sec": c3["N"] / (ms_t / 1e3), "ms_per_step": ms_t}
     del net, full, solver
     torch.cuda.empty_cache()
+    # ---- Embed backward: run-merged float atomics (default) beside the order-independent path (MMS_OPT_EMBED_DETERMINISTIC)
+    out["embed_backward_modes"] = embed_backward_modes(flush)
     # ---- ranking metrics on the device: MAP + MRR over a reranking score slab, grouped by query
     nq, nc = 1000, 32768
     n = nq * nc
@@ -870,9 +897,10 @@ def hbm_kernel_table(prof, steps, cfg, peaks):
     rows = N * 2 * L                                   # token rows of q and a
     Dp = (D + 31) // 32 * 32                           # rounded copies: rows padded to 128-byte lines
     alg = {
-        "embed_forward_vec": rows * (4 + 8 * D),                       # id + table row in, row out
+        # id + table row in, row out, and (MMS_OPT_STAGE_TF32, what MMSNet runs) the rounded operand copy out as well
+        "embed_forward_vec": rows * (4 + 8 * D + 4 * Dp),
         "embed_backward_runs": rows * (4 + 4 * D) + rows * 8 * D,      # id + dtop in, <= one RMW of the dW row
-        "tf32_round_kernel": rows * 4 * (D + Dp) + mc * D * 4 * (D + Dp),
+        "tf32_round_kernel": mc * D * 4 * (D + Dp),                    # only M: q and a arrive staged by the gather
         "sum_kernel": 2 * 4 * N * mc * L * L,                          # loss = dot(S, dS)
         "bias_grad_kernel": 4 * N * mc * L * L,                        # dB += sum_n dS[n]
     }

@@ -54,8 +54,11 @@ enum {
                                 pair_rank_loss_layer.cpp:76), 1 `ordered >= 0` (reference GPU,
                                 pair_rank_loss_layer.cu:51).  Default 0. */
   MMS_OPT_SCRATCH_BYTES = 3, /* cap for the per-call scratch chunk (default 4 GiB; grows on demand) */
-  MMS_OPT_EMBED_DETERMINISTIC = 4, /* Embed backward: 1 = order-independent segmented reduction
-                                (bit-reproducible), 0 = block-aggregated atomics.  Default 0. */
+  MMS_OPT_EMBED_DETERMINISTIC = 4, /* Embed backward: 1 = order-independent reduction: rows are sorted by id and every
+                                table row is summed in 64-bit fixed point by one writer, so dW / dbias are bit-identical
+                                from run to run and under any permutation of the token rows (needs D a multiple of
+                                16 bytes and 16-byte aligned blobs, else MMS_E_UNSUPPORTED); 0 = run-merged float
+                                atomics (arrival order, like the reference's kernel).  Default 0. */
   MMS_OPT_REUSE_FORWARD = 5, /* SimCross mode 2, float: 1 = mms_simcross_backward may reuse the TF32-rounded
                                 operands and T = Q M_k that the LAST mms_simcross_forward on this handle left
                                 in the workspace, provided it was called with the same q / a / M pointers and
@@ -68,8 +71,17 @@ enum {
                                 (stateless: backward recomputes, like the reference, sim_cross_layer.cpp:296).
                                 The same promise lets mms_simmatrix_backward reuse the rounded q and W, and
                                 mms_sentconv_backward the rounded x, of the last forward on the handle. */
-  MMS_OPT_CONCURRENCY = 6    /* 1 (default): independent contractions inside one call may run on private
+  MMS_OPT_CONCURRENCY = 6,   /* 1 (default): independent contractions inside one call may run on private
                                 streams, joined back before the call's last launch on the handle's stream. */
+  MMS_OPT_STAGE_TF32 = 7     /* Embed forward, float: 1 = the gather also writes the operand copy the tensor-core
+                                contractions read (TF32 round-to-nearest, rows padded to 128-byte lines) into a
+                                buffer owned by this handle, and publishes it under the top's address.  A later
+                                mms_simcross_forward / _backward whose q or a IS that top (same pointer, shape) reads
+                                the staged copy instead of re-reading and rounding the top in a pass of its own
+                                (q and a then cross HBM twice per forward instead of three times).  The copy is
+                                dropped when the library itself rewrites the top; a caller that lets a foreign
+                                in-place layer modify the top between this Embed and its consumer must not set the
+                                option (or call mms_invalidate_caches).  Default 0. */
 };
 
 typedef struct mms_context* mms_handle_t;

@@ -83,6 +83,33 @@ int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
   return 0;
 }
 
+#include <unordered_map>
+namespace {
+struct StageEntry { mms_context* owner; const float* staged; long long rows; int cols, ld; unsigned long long clock; };
+std::unordered_map<const void*, StageEntry> g_stage;
+std::mutex g_stage_mu;
+}  // namespace
+void mms_stage_publish(mms_context* owner, const void* src, const float* staged, long long rows, int cols, int ld) {
+  const unsigned long long clock = mms_write_clock();
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  g_stage[src] = StageEntry{owner, staged, rows, cols, ld, clock};
+}
+const float* mms_stage_lookup(const void* src, long long rows, int cols, int ld) {
+  StageEntry e;
+  {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    auto it = g_stage.find(src);
+    if (it == g_stage.end()) return nullptr;
+    e = it->second;
+  }
+  if (e.rows != rows || e.cols != cols || e.ld != ld) return nullptr;
+  return mms_unchanged_since(e.clock, src, sizeof(float) * (size_t)rows * cols) ? e.staged : nullptr;
+}
+void mms_stage_drop_owner(mms_context* owner) {
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  for (auto it = g_stage.begin(); it != g_stage.end();) it = it->second.owner == owner ? g_stage.erase(it) : ++it;
+}
+
 #include <set>
 int mms_prefer_max_shared(const void* func) {
   static std::mutex mu;
@@ -191,6 +218,8 @@ int mms_destroy(mms_handle_t h) {
   mms_tc_destroy_state(h);
   prof_clear(h);
   delete static_cast<std::vector<ProfRecord>*>(h->prof);
+  mms_stage_drop_owner(h);
+  if (h->stage_buf) cudaFree(h->stage_buf);
   if (h->scratch) cudaFree(h->scratch);
   if (h->fault_flag) cudaFree(h->fault_flag);
   if (h->partials) cudaFree(h->partials);
@@ -222,6 +251,10 @@ int mms_set_option(mms_handle_t h, int option, long long value) {
     case MMS_OPT_EMBED_DETERMINISTIC: h->embed_deterministic = value != 0; return 0;
     case MMS_OPT_REUSE_FORWARD: h->reuse_forward = value != 0; h->fwd_cache.valid = false; return 0;
     case MMS_OPT_CONCURRENCY: h->concurrency = value != 0; return 0;
+    case MMS_OPT_STAGE_TF32:
+      h->stage_tf32 = value != 0;
+      if (!h->stage_tf32) mms_stage_drop_owner(h);
+      return 0;
     default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
   }
 }
@@ -248,6 +281,7 @@ int mms_get_option(mms_handle_t h, int option, long long* value) {
     case MMS_OPT_EMBED_DETERMINISTIC: *value = h->embed_deterministic; return 0;
     case MMS_OPT_REUSE_FORWARD: *value = h->reuse_forward; return 0;
     case MMS_OPT_CONCURRENCY: *value = h->concurrency; return 0;
+    case MMS_OPT_STAGE_TF32: *value = h->stage_tf32; return 0;
     default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
   }
 }

@@ -31,10 +31,21 @@ __device__ __forceinline__ double2 vadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void vzero(double2& a) { a = make_double2(0., 0.); }
 
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 tf32_rn(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+__device__ __forceinline__ double2 tf32_rn(double2 v) { return v; }   // staging is float only
+
+// `staged` (MMS_OPT_STAGE_TF32, float): the same rows once more, rounded to TF32 (round to nearest, what the tensor-core
+// contractions read) with a row pitch of `lds` floats -- written here, while the row is in registers, instead of by a
+// rounding pass that would read the top back from HBM.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 embed_forward_vec(const T* __restrict__ idx, const T* __restrict__ W, const T* __restrict__ bias,
-                  T* __restrict__ top, long long M, int D, int V, int* fault) {
+                  T* __restrict__ top, long long M, int D, int V, int* fault, T* __restrict__ staged, int lds) {
   typedef typename Vec<T, VEC>::type VT;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -51,6 +62,7 @@ embed_forward_vec(const T* __restrict__ idx, const T* __restrict__ W, const T* _
       if (ok) v = __ldg(src + c); else vzero(v);
       if (bias) v = vadd(v, __ldg(reinterpret_cast<const VT*>(bias) + c));
       __stcs(dst + c, v);   // streaming store: the gathered rows are consumed once
+      if (staged) reinterpret_cast<VT*>(staged + (size_t)row * lds)[c] = tf32_rn(v);
     }
   }
 }
@@ -203,10 +215,27 @@ int mms_embed_forward_impl(mms_context* ctx, const T* idx, const T* W, const T* 
   const int grid = (int)mms_min<long long>((M + kWarpsPerCta - 1) / kWarpsPerCta, (long long)ctx->sm_count * 16);
   const bool vec_ok = (D % VEC == 0) && aligned16(W) && aligned16(top) && (!bias || aligned16(bias));
   if (vec_ok) {
+    T* staged = nullptr;
+    const int lds = (D + 31) & ~31;                       // rows on 128-byte lines, the pitch the contractions use
+    if (ctx->stage_tf32 && sizeof(T) == 4) {
+      const size_t need = sizeof(float) * (size_t)M * lds;
+      if (need > ctx->stage_bytes) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        MMS_REQUIRE(cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone,
+                    MMS_E_INVALID, "the staging buffer must have its size before a capture: run the step once eagerly");
+        mms_stage_drop_owner(ctx);
+        if (ctx->stage_buf) { MMS_CUDA(cudaStreamSynchronize(ctx->stream)); MMS_CUDA(cudaFree(ctx->stage_buf)); }
+        ctx->stage_buf = nullptr; ctx->stage_bytes = 0;
+        MMS_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->stage_buf), need));
+        ctx->stage_bytes = need;
+      }
+      staged = reinterpret_cast<T*>(ctx->stage_buf);
+    }
     { MmsKernelScope ks_(ctx, "embed_forward_vec");
       MMS_CARVEOUT((embed_forward_vec<T, VEC>));
       embed_forward_vec<T, VEC><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, top, M, D, V,
-                                                                           ctx->fault_flag); }
+                                                                           ctx->fault_flag, staged, lds); }
+    if (staged) mms_stage_publish(ctx, top, ctx->stage_buf, M, D, lds);
   } else {
     { MmsKernelScope ks_(ctx, "embed_forward_scalar");
       embed_forward_scalar<T><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, top, M, D, V,
@@ -222,6 +251,8 @@ int mms_embed_backward_impl(mms_context* ctx, const T* idx, const T* dtop, T* dW
   MMS_REQUIRE(M >= 0 && D > 0 && V > 0, MMS_E_INVALID, "bad size");
   if (M == 0 || (!dW && !dbias)) return 0;
   MMS_REQUIRE(idx && dtop, MMS_E_INVALID, "null pointer");
+  if (ctx->embed_deterministic)      // order-independent 64-bit fixed-point sums (embed_det.cu); never the atomic path
+    return mms_embed_backward_deterministic<T>(ctx, idx, dtop, dW, dbias, M, D, V);
   // enough CTAs to cover the machine about four times over, 8..64 rows each
   const long long want = mms_ceil_div(M, 4LL * ctx->sm_count);
   const int rows_per_cta = (int)mms_min<long long>(kBwdMaxRows, mms_max<long long>(8, (want + 7) / 8 * 8));

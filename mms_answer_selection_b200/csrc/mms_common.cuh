@@ -28,6 +28,9 @@ struct mms_context {
   cudaEvent_t ev_fork[2] = {nullptr, nullptr};
   cudaEvent_t ev_join[2] = {nullptr, nullptr};
   int concurrency = 1;           // MMS_OPT_CONCURRENCY
+  int stage_tf32 = 0;            // MMS_OPT_STAGE_TF32: Embed forward also writes the TF32-rounded, row-padded copy
+  float* stage_buf = nullptr;    // ... into this buffer (owned by the handle, published in the staging registry)
+  size_t stage_bytes = 0;
   // SimCross forward leaves its rounded operands and T = Q M_k in the scratch buffer; backward reuses
   // them when MMS_OPT_REUSE_FORWARD is set and nothing has touched the scratch buffer in between.
   int reuse_forward = 0;
@@ -35,12 +38,14 @@ struct mms_context {
     bool valid = false;
     const void *q = nullptr, *a = nullptr, *M = nullptr;
     int N = 0, Lq = 0, La = 0, D = 0, mc = 0;
-    unsigned long long generation = 0;   // mms_content_generation() when the forward ran
+    unsigned long long generation = 0;   // mms_write_clock() when the forward ran
+    const float *qr = nullptr, *ar = nullptr;   // the rounded operands it used (workspace or a staged copy)
   } fwd_cache;
   // mms_simcross_backward_bottoms left U = dS A (and the rounded q) in the workspace for mms_simcross_backward_params
   struct DmPending {
     bool valid = false;
     int N = 0, Lq = 0, La = 0, D = 0, mc = 0;
+    const float* qr = nullptr;                  // the rounded questions _bottoms used
   } dm_pending;
   // Sentence convolution: the forward leaves the TF32-rounded copy of x at the head of the scratch buffer; with
   // MMS_OPT_REUSE_FORWARD the backward on the same handle reads it instead of rounding x again.
@@ -66,6 +71,12 @@ struct mms_context {
 // A cache records mms_write_clock() when its forward ran and is honoured by a later backward only if no range noted
 // since then overlaps the operands it was built from (mms_unchanged_since): a weight update, an in-place layer or a
 // refilled bottom between a Forward and a later Backward can therefore never be paired with stale rounded copies.
+// Staging registry (MMS_OPT_STAGE_TF32): producer kernels that know their top will be a tensor-core operand write the
+// rounded, padded copy themselves and publish it under the top's address; consumers look the address up.  An entry is
+// honoured only while no logged write overlaps the top.
+void mms_stage_publish(struct mms_context* owner, const void* src, const float* staged, long long rows, int cols, int ld);
+const float* mms_stage_lookup(const void* src, long long rows, int cols, int ld);
+void mms_stage_drop_owner(struct mms_context* owner);
 unsigned long long mms_write_clock();
 void mms_note_write(const void* p, size_t bytes);
 bool mms_unchanged_since(unsigned long long clock, const void* p, size_t bytes);
@@ -172,6 +183,8 @@ int mms_embed_forward_impl(mms_context*, const T* idx, const T* W, const T* bias
 template <typename T>
 int mms_embed_backward_impl(mms_context*, const T* idx, const T* dtop, T* dW, T* dbias,
                             long long M, int D, int V);
+template <typename T>
+int mms_embed_backward_deterministic(mms_context*, const T* idx, const T* dtop, T* dW, T* dbias, long long M, int D, int V);
 template <typename T>
 int mms_simcross_forward_impl(mms_context*, int mode, const T* q, const T* a, const T* Mw,
                               const T* B, T* S, T* norm0, T* norm1, int N, int Lq, int La, int D,

@@ -65,9 +65,14 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
   // (+ room for the blocked U export of a later backward: up to 31 padding rows per measure)
   MMS_TRY(mms_scratch(ctx, sizeof(float) * (p.fixed + p.per_pair * p.nc_max + (size_t)mc * 32 * Dp), &sp));
   float* Mr = static_cast<float*>(sp);
-  float* qr = Mr + p.fixed;
-  float* ar = qr + (size_t)p.nc_max * Lq * Dp;
-  float* Tk = ar + (size_t)p.nc_max * La * Dp;
+  float* qr_ws = Mr + p.fixed;
+  float* ar_ws = qr_ws + (size_t)p.nc_max * Lq * Dp;
+  float* Tk = ar_ws + (size_t)p.nc_max * La * Dp;
+  // operands a producer already staged (MMS_OPT_STAGE_TF32 on the Embed handle): read in place, no rounding pass
+  const float* qs = p.nc_max == N ? mms_stage_lookup(q, (long long)N * Lq, D, Dp) : nullptr;
+  const float* as = p.nc_max == N ? mms_stage_lookup(a, (long long)N * La, D, Dp) : nullptr;
+  const float* qr = qs ? qs : qr_ws;
+  const float* ar = as ? as : ar_ws;
   // the rounded copies stay in the scratch buffer: a backward on the same handle may reuse them (MMS_OPT_REUSE_FORWARD)
   struct CacheMark {
     mms_context* c; bool ok;
@@ -76,11 +81,12 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
   for (int n0 = 0; n0 < N; n0 += p.nc_max) {
     const int nc = mms_min(p.nc_max, N - n0);
     float* Sc = S + (size_t)n0 * mc * Lq * La;
-    const RoundJob jobs[3] = {
-        {q + (size_t)n0 * Lq * D, qr, (long long)nc * Lq, D, D, Dp, nullptr},
-        {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
-        {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
-    MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
+    RoundJob jobs[3];
+    int nj = 0;
+    if (!qs) jobs[nj++] = RoundJob{q + (size_t)n0 * Lq * D, qr_ws, (long long)nc * Lq, D, D, Dp, nullptr};
+    if (!as) jobs[nj++] = RoundJob{a + (size_t)n0 * La * D, ar_ws, (long long)nc * La, D, D, Dp, nullptr};
+    if (n0 == 0) jobs[nj++] = RoundJob{Mw, Mr, (long long)mc * D, D, D, Dp, nullptr};
+    if (nj) MMS_TRY(mms_tf32_round(ctx, jobs, nj));
     {  // one kernel for both contractions, T stays in tensor memory (tc/simcross_fused.cu)
       const int rc = mms_tc_simcross2_forward_fused(ctx, qr, ar, Mr, B, Sc, nc, Lq, La, D, mc, Dp);
       if (rc == 0) {
@@ -88,6 +94,7 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
           mms_context::FwdCache& fc = ctx->fwd_cache;
           fc.q = q; fc.a = a; fc.M = Mw; fc.N = N; fc.Lq = Lq; fc.La = La; fc.D = D; fc.mc = mc;
           fc.generation = mms_write_clock();
+          fc.qr = qr; fc.ar = ar;
           mark.ok = true;
         }
         continue;
@@ -149,9 +156,16 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
     MMS_TRY(mms_scratch(ctx, need, &sp));
   }
   float* Mr = static_cast<float*>(sp);
-  float* qr = Mr + fixed;
-  float* ar = qr + (size_t)nc_max * Lq * Dp;
-  float* U = ar + (size_t)nc_max * La * Dp;
+  float* qr_ws = Mr + fixed;
+  float* ar_ws = qr_ws + (size_t)nc_max * Lq * Dp;
+  float* U = ar_ws + (size_t)nc_max * La * Dp;
+  // where the rounded operands are: what the forward used (reuse), a producer's staged copy, or the workspace
+  const float* qs = nullptr; const float* as = nullptr;
+  if (phase == 2) { qs = ctx->dm_pending.qr; }
+  else if (reuse) { qs = fc.qr; as = fc.ar; }
+  else if (nc_max == N) { qs = mms_stage_lookup(q, (long long)N * Lq, D, Dp); as = mms_stage_lookup(a, (long long)N * La, D, Dp); }
+  const float* qr = qs ? qs : qr_ws;
+  const float* ar = as ? as : ar_ws;
   if (phase == 2) {
     MMS_CUDA(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)mc * D * D, ctx->stream));   // :256
     const int use_dm = mms_tc_simcross2_dm_plan(D) == 0 && (long long)N * Lq >= 16384;
@@ -169,11 +183,14 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
     float* dqc = dq + (size_t)n0 * Lq * D;
     float* dac = da + (size_t)n0 * La * D;
     const float* dSc = dS + (size_t)n0 * mc * Lq * La;
-    const RoundJob jobs[3] = {
-        {q + (size_t)n0 * Lq * D, qr, (long long)nc * Lq, D, D, Dp, nullptr},
-        {a + (size_t)n0 * La * D, ar, (long long)nc * La, D, D, Dp, nullptr},
-        {Mw, Mr, (long long)mc * D, D, D, Dp, nullptr}};
-    if (!reuse) MMS_TRY(mms_tf32_round(ctx, jobs, n0 == 0 ? 3 : 2));
+    if (!reuse) {
+      RoundJob jobs[3];
+      int nj = 0;
+      if (!qs) jobs[nj++] = RoundJob{q + (size_t)n0 * Lq * D, qr_ws, (long long)nc * Lq, D, D, Dp, nullptr};
+      if (!as) jobs[nj++] = RoundJob{a + (size_t)n0 * La * D, ar_ws, (long long)nc * La, D, D, Dp, nullptr};
+      if (n0 == 0) jobs[nj++] = RoundJob{Mw, Mr, (long long)mc * D, D, D, Dp, nullptr};
+      if (nj) MMS_TRY(mms_tf32_round(ctx, jobs, nj));
+    }
     // two kernels side by side only pay when one of them cannot fill the GPU: then each gets half of the SMs
     int ksplit = 1;
     MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctx->sm_count, &ksplit));
@@ -202,7 +219,7 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
   }
   if (phase == 1) {
     mms_context::DmPending& dp = ctx->dm_pending;
-    dp.valid = true; dp.N = N; dp.Lq = Lq; dp.La = La; dp.D = D; dp.mc = mc;
+    dp.valid = true; dp.N = N; dp.Lq = Lq; dp.La = La; dp.D = D; dp.mc = mc; dp.qr = qr;
   }
   return 0;
 }

@@ -21,7 +21,7 @@ from .layers import EmbedLayer, LayerParameter, SimCrossLayer
 
 class MMSNet(object):
     def __init__(self, N, L=40, D=300, mc=4, V=60002, dtype=np.float32, device="cuda", bias_term=True,
-                 embed_bias=True, math=None):
+                 embed_bias=True, math=None, stage_tf32=True, deterministic=False):
         self.N, self.L, self.D, self.mc, self.V = N, L, D, mc, V
         self.dtype = np.dtype(dtype)
         self.device = torch.device(device)
@@ -50,6 +50,17 @@ class MMSNet(object):
         # backward may reuse the TF32-rounded operands its forward left in the workspace
         from . import _lib
         self.sim.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 1)
+        # the Embed tops go straight into SimCross (do_trec_qa_clean.py:461-468: no layer in between), so the gather
+        # also writes the TF32 operand copy the contractions read (MMS_OPT_STAGE_TF32): no separate rounding pass
+        if self.dtype == np.float32 and stage_tf32:
+            self.embed_q.handle.set_option(_lib.MMS_OPT_STAGE_TF32, 1)
+            self.embed_a.handle.set_option(_lib.MMS_OPT_STAGE_TF32, 1)
+        # MMS_OPT_EMBED_DETERMINISTIC: order-independent scatter-add; the two Embed backwards then run one after the
+        # other (each is the single writer of the table rows it touches)
+        self.deterministic = bool(deterministic)
+        if self.deterministic:
+            self.embed_q.handle.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1)
+            self.embed_a.handle.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1)
         self._pinned = None
         self._side = None
 
@@ -157,12 +168,21 @@ class MMSNet(object):
                 loss = self.sim.ForwardLoss([self.S])
         main.wait_stream(s1)                                   # diffs are cleared before anything accumulates
         self.sim.Backward([self.S], [True, True], [self.q, self.a])
+        self._embed_backward_pair(main, s2)
+        return loss
+
+    def _embed_backward_pair(self, main, s2):
+        """Both scatter-adds into the shared dW: side by side with float atomics, or -- deterministic mode -- one after
+        the other, in the order MMSNet.Backward uses."""
+        if self.deterministic:                                 # the order of MMSNet.Backward
+            self.embed_q.Backward([self.q], [False], [self.idx_q])
+            self.embed_a.Backward([self.a], [False], [self.idx_a])
+            return
         s2.wait_stream(main)
-        with torch.cuda.stream(s2):                            # both scatter-adds go into the shared dW with atomics
+        with torch.cuda.stream(s2):
             self.embed_a.Backward([self.a], [False], [self.idx_a])
         self.embed_q.Backward([self.q], [False], [self.idx_q])
         main.wait_stream(s2)
-        return loss
 
     def ForwardBackwardExchange(self, exch, with_loss=True, clear_diffs=True, solver=None, overlap=True):
         r"""One data-parallel step ordered by its data dependencies (the reference runs Backward layer by layer and
@@ -206,11 +226,7 @@ class MMSNet(object):
                 loss = self.sim.ForwardLoss([self.S])
         main.wait_stream(s1)
         self.sim.BackwardBottoms([self.S], [self.q, self.a])
-        s2.wait_stream(main)
-        with torch.cuda.stream(s2):
-            self.embed_a.Backward([self.a], [False], [self.idx_a])
-        self.embed_q.Backward([self.q], [False], [self.idx_q])
-        main.wait_stream(s2)
+        self._embed_backward_pair(main, s2)
         ne = len(self.embed_q.blobs)                           # params() = Embed blobs, then SimCross blobs
         if not overlap:                                        # the reference's order: all of Backward, then one exchange
             self.sim.BackwardParams([self.S], [self.q, self.a])

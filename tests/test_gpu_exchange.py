@@ -336,3 +336,33 @@ def test_multigpu_exchanged_gradient_equals_single_gpu_batch(symmetric):
         err = np.abs(out[0]["diff"][j] - w).max() / max(np.abs(w).max(), 1e-30)
         assert err <= 1e-3, (j, err)                                                 # TF32 contractions, other split
     print("multigpu exchange ok; multicast=%s" % out[0]["multicast"])
+
+
+def test_staged_tf32_operands_change_nothing():
+    """MMS_OPT_STAGE_TF32: the gather writes the rounded operand copy SimCross reads; every result is bit-identical to
+    the path that rounds q / a in a pass of its own, and the rounding kernel no longer sees q / a."""
+    N, L, D, mc, V = 384, 40, 300, 4, 4000
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    outs, rounds = [], []
+    for stage in (False, True):
+        net = mms.MMSNet(N, L, D, mc, V, stage_tf32=stage)
+        net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
+        net.set_upstream_gradient(d["dS"])
+        net.sim.handle.profile_enable(True)
+        net.ClearParamDiffs(); net.ForwardBackward()
+        torch.cuda.synchronize()
+        rounds.append(net.sim.handle.profile_report().get("tf32_round_kernel", (0, 0.0))[1])
+        outs.append([net.q.cpu_data(), net.S.cpu_data(), net.q.cpu_diff(), net.a.cpu_diff()])
+        # a refilled bottom drops the staged copy: new ids, forward again, compare with a fresh net
+        if stage:
+            d2 = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V, seed=5)
+            net.set_inputs(d2["idx_q"], d2["idx_a"])
+            net.Forward()
+            ref = mms.MMSNet(N, L, D, mc, V, stage_tf32=False)
+            ref.set_params(d["W"], d["b"], d["M"], d["B"]); ref.set_inputs(d2["idx_q"], d2["idx_a"])
+            ref.Forward()
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(net.S.cpu_data(), ref.S.cpu_data())
+    for a, b, name in zip(outs[0], outs[1], ("q", "S", "dq", "da")):
+        np.testing.assert_array_equal(a, b, err_msg=name)
+    assert rounds[1] < 0.5 * rounds[0]          # only M is rounded when q / a arrive staged

@@ -804,3 +804,76 @@ def test_embed_weight_source_and_caffemodel_round_trip(tmp_path):
         net.ForwardBackward()
     assert np.array_equal(a.S.cpu_data(), b.S.cpu_data())
     assert np.array_equal(a.params()[2].cpu_diff(), b.params()[2].cpu_diff())
+
+
+# ---------------------------------------------------------------------------------------------- deterministic Embed backward
+def _embed_bwd(h, idx, dtop, dW0, db0, V, deterministic):
+    import ctypes
+    M, D = dtop.shape
+    dt = dtop.dtype
+    fn = _lib.lib().mms_embed_backward_f32 if dt == np.float32 else _lib.lib().mms_embed_backward_f64
+    h.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1 if deterministic else 0)
+    t_idx, t_g = torch.from_numpy(idx.astype(dt)).cuda(), torch.from_numpy(dtop).cuda()
+    t_dW, t_db = torch.from_numpy(dW0.copy()).cuda(), torch.from_numpy(db0.copy()).cuda()
+    _lib.check(fn(h.ptr, *(ctypes.c_void_p(t.data_ptr()) for t in (t_idx, t_g, t_dW, t_db)), M, D, V))
+    torch.cuda.synchronize()
+    return t_dW.cpu().numpy(), t_db.cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,D,V", [(4000, 300, 700), (163840, 300, 60002), (33, 52, 9), (2, 4, 5)])
+def test_embed_backward_deterministic(dtype, M, D, V):
+    """MMS_OPT_EMBED_DETERMINISTIC (reference op embed_layer.cu:29-39; SURVEY.md 7 hard parts): same sums as the oracle,
+    accumulate semantics kept, bit-identical across 10 runs AND across permutations of the token rows (64-bit fixed-point
+    sums are order-free), with a centre-padded id stream whose pad id owns about half of the rows."""
+    if M > 100000 and dtype == np.float64:
+        pytest.skip("the C3-sized case runs in float32 only")
+    rng = np.random.default_rng(M + D)
+    idx = rng.integers(0, V - 1, M).astype(np.int64)
+    idx[rng.random(M) < 0.55] = V - 1                               # the pad row: one run of ~0.55 M rows
+    mag = 10.0 ** rng.integers(-9, 1, (M, 1))                       # rows of very different magnitudes
+    dtop = (rng.normal(0, 1, (M, D)) * mag).astype(dtype)
+    dW0 = rng.normal(0, 1e-3, (V, D)).astype(dtype); db0 = rng.normal(0, 1e-3, D).astype(dtype)
+    h = _lib.Handle()
+    dW, db = _embed_bwd(h, idx, dtop, dW0, db0, V, True)
+    ref_W, ref_b = dW0.astype(np.float64), db0.astype(np.float64)
+    np.add.at(ref_W, idx, dtop.astype(np.float64)); ref_b += dtop.astype(np.float64).sum(0)
+    tol = 2e-6 if dtype == np.float32 else 1e-12
+    assert scaled_err(dW, ref_W) <= tol and scaled_err(db, ref_b) <= tol
+    # row by row: a run of tiny gradients keeps ITS relative precision next to runs of large ones (per-run scales)
+    touched = np.unique(idx)
+    num = np.abs(dW[touched].astype(np.float64) - ref_W[touched]).max(1)
+    den = np.abs(ref_W[touched] - dW0[touched].astype(np.float64)).max(1) + np.abs(dW0[touched]).max(1)
+    assert (num / den).max() <= (1e-6 if dtype == np.float32 else 1e-12)
+    for rep in range(10):
+        dW2, db2 = _embed_bwd(h, idx, dtop, dW0, db0, V, True)
+        assert np.array_equal(dW, dW2) and np.array_equal(db, db2), rep
+    for rep in range(3):
+        perm = rng.permutation(M)
+        dW3, db3 = _embed_bwd(h, idx[perm], np.ascontiguousarray(dtop[perm]), dW0, db0, V, True)
+        assert np.array_equal(dW, dW3) and np.array_equal(db, db3), ("permutation", rep)
+    # the atomic path agrees to rounding and an out-of-range id is flagged, not written
+    dW4, db4 = _embed_bwd(h, idx, dtop, dW0, db0, V, False)
+    assert scaled_err(dW4, ref_W) <= (2e-5 if dtype == np.float32 else 1e-11)
+    bad = idx.copy(); bad[0] = V + 3
+    _embed_bwd(h, bad, dtop, dW0, db0, V, True)
+    with pytest.raises(mms.MMSError):
+        h.check_faults()
+
+
+def test_deterministic_net_step_is_reproducible():
+    N, L, D, mc, V = 96, 40, 300, 4, 900
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    outs = []
+    for rep in range(3):
+        net = mms.MMSNet(N, L, D, mc, V, deterministic=True)
+        net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
+        net.set_upstream_gradient(d["dS"])
+        net.sim.handle.set_option(_lib.MMS_OPT_CONCURRENCY, 0)
+        if rep == 2:
+            net.capture(); net.replay(read_loss=False)
+        else:
+            net.ClearParamDiffs(); net.ForwardBackward()
+        torch.cuda.synchronize()
+        outs.append(net.embed_q.blobs[0].cpu_diff().copy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])

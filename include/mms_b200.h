@@ -379,6 +379,23 @@ int mms_rerank_prepare_f32(mms_handle_t h, const float* C, float* C_tf32, long l
 int mms_rerank_scores_prepared_f32(mms_handle_t h, const float* Q, const float* C_tf32, const float* W, float* QW,
                                    float* scores, int Nq, long long Nc, int K1, int K2);
 
+/* Per-query top-k instead of the full score matrix (the consumer ranks each query's candidates by
+ * score: do_trec_qa_clean.py:617-650, map_layer.cpp:41-100).  top_scores / top_idx (Nq, k): the k best candidates of
+ * every query, score descending, ties by candidate index ascending (NaN scores are never listed; unused slots hold
+ * -inf / INT64_MAX); indices are idx_base + the candidate's row in C, so that a shard of a larger candidate set
+ * reports global indices.  The scores are folded into the lists slab by slab while they are in L2 -- the Nq x Nc
+ * matrix is never written.  k <= 1024.  _prepared takes the mms_rerank_prepare copy of the candidates.
+ * mms_topk_merge_f32: merges lists of several shards: row q of `scores` / `idx` holds n candidate (score, index)
+ * pairs of query q (the all-gathered per-shard lists, ld elements apart); out_* as above.  The result does not depend
+ * on how the candidates were sharded. */
+int mms_rerank_topk_f32(mms_handle_t h, const float* Q, const float* C, const float* W, float* QW, float* top_scores,
+                        long long* top_idx, int Nq, long long Nc, int K1, int K2, int k, long long idx_base);
+int mms_rerank_topk_prepared_f32(mms_handle_t h, const float* Q, const float* C_tf32, const float* W, float* QW,
+                                 float* top_scores, long long* top_idx, int Nq, long long Nc, int K1, int K2, int k,
+                                 long long idx_base);
+int mms_topk_merge_f32(mms_handle_t h, const float* scores, const long long* idx, long long ld, long long n,
+                       float* out_scores, long long* out_idx, int Nq, int k);
+
 /* ------------------------------------------------------ sentence encoder ---
  * The sentence-vector variant of the net (examples/trec_qa_w2v_mms/do_trec_qa_clean.py:352-375, 412-422):
  * Convolution(kernel kh x D over the (N,1,L,D) embedded sentence) -> BN -> Pooling(MAX over time) -> TanH -> SimMatrix.

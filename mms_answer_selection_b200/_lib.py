@@ -116,6 +116,9 @@ def lib():
         L.mms_exchange_launch_count.restype = ctypes.c_ulonglong
         L.mms_simcross_backward_bottoms_f32.argtypes = [c_p] * 7 + [c_int] * 5
         L.mms_simcross_backward_params_f32.argtypes = [c_p] * 4 + [c_int] * 5
+        L.mms_rerank_topk_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
+        L.mms_rerank_topk_prepared_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
+        L.mms_topk_merge_f32.argtypes = [c_p, c_p, c_p, c_ll, c_ll, c_p, c_p, c_int, c_int]
         L.mms_tc_gemm_f32.argtypes = [c_p, c_p, c_ll, c_int, c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int,
                                       c_int, c_int]
         _lib = L

@@ -494,6 +494,24 @@ int mms_rerank_scores_prepared_f32(mms_handle_t h, const float* Q, const float* 
   H; return mms_rerank_scores_prepared_impl(h, Q, C_tf32, W, QW, scores, Nq, Nc, K1, K2);
 }
 
+int mms_rerank_topk_f32(mms_handle_t h, const float* Q, const float* C, const float* W, float* QW, float* top_scores,
+                        long long* top_idx, int Nq, long long Nc, int K1, int K2, int k, long long idx_base) {
+  H; return mms_rerank_topk_impl(h, Q, C, W, QW, top_scores, top_idx, Nq, Nc, K1, K2, k, idx_base, 0);
+}
+int mms_rerank_topk_prepared_f32(mms_handle_t h, const float* Q, const float* C_tf32, const float* W, float* QW,
+                                 float* top_scores, long long* top_idx, int Nq, long long Nc, int K1, int K2, int k,
+                                 long long idx_base) {
+  H; return mms_rerank_topk_impl(h, Q, C_tf32, W, QW, top_scores, top_idx, Nq, Nc, K1, K2, k, idx_base, 1);
+}
+int mms_topk_merge_f32(mms_handle_t h, const float* scores, const long long* idx, long long ld, long long n,
+                       float* out_scores, long long* out_idx, int Nq, int k) {
+  H;
+  MMS_REQUIRE(scores && idx && out_scores && out_idx, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(Nq > 0 && k > 0 && k <= 1024, MMS_E_INVALID, "bad size (k <= 1024)");
+  MMS_TRY(mms_topk_init(h, out_scores, out_idx, Nq, k));
+  return mms_topk_update(h, scores, idx, ld, n, 0, out_scores, out_idx, Nq, k);
+}
+
 // Test/diagnostic entry: C (+)= op(A) op(B) on the tcgen05 TF32 GEMM (see tc/tc_gemm.cuh).
 int mms_tc_gemm_f32(mms_handle_t h, const float* A, long long lda, int a_mn, const float* B, long long ldb,
                     int b_mn, float* C, long long ldc, int M, int N, int K, int ksplit, int mode) {

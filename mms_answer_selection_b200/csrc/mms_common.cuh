@@ -224,6 +224,11 @@ int mms_rank_auc_impl(mms_context*, const T* data, long long stride, long long o
                       int has_ignore, int ignore_label, T* out);
 template <typename T>
 int mms_rank_accuracy_impl(mms_context*, const T* a, const T* b, const T* label, long long n, T* out);
+int mms_rerank_topk_impl(mms_context*, const float* Q, const float* C, const float* W, float* QW, float* top_s,
+                         long long* top_i, int Nq, long long Nc, int K1, int K2, int k, long long idx_base, int prepared);
+int mms_topk_init(mms_context*, float* run_s, long long* run_i, int Nq, int k);
+int mms_topk_update(mms_context*, const float* scores, const long long* idx, long long ld, long long n, long long idx_base,
+                    float* run_s, long long* run_i, int Nq, int k);
 int mms_rerank_prepare_impl(mms_context*, const float* C, float* Cr, long long Nc, int K2);
 int mms_rerank_scores_prepared_impl(mms_context*, const float* Q, const float* Cr, const float* W, float* QW,
                                     float* scores, int Nq, long long Nc, int K1, int K2);

@@ -177,6 +177,7 @@ class MMSNet(object):
         if self.deterministic:                                 # the order of MMSNet.Backward
             self.embed_q.Backward([self.q], [False], [self.idx_q])
             self.embed_a.Backward([self.a], [False], [self.idx_a])
+            main.wait_stream(s2)                               # the loss branch still joins here
             return
         s2.wait_stream(main)
         with torch.cuda.stream(s2):

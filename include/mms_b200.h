@@ -445,6 +445,32 @@ int mms_bn_backward_f32(mms_handle_t h, const float* dtop, const float* x_norm, 
 int mms_bn_backward_f64(mms_handle_t h, const double* dtop, const double* x_norm, const double* scale,
                         const double* batch_std, double* dscale, double* dshift, double* dx, int N, int C, int HW);
 
+/* ------------------------------------------------ the CNN over the similarity tensor ---
+ * network_v4 (examples/trec_qa_w2v_mms/do_trec_qa_clean.py:470-477): Dropout(0.1) -> Convolution(5x5, 32) + BN ->
+ * Pooling(AVE 4, stride 4) -> TanH -> Convolution(5x5, 64) + BN -> Pooling(AVE 5) -> TanH over S (N, mc, Lq, La).  BN,
+ * Pooling and TanH are the entry points above (BN takes (N, C, H*W)).
+ * mms_conv2d_*: ConvolutionLayer (conv_layer.cpp:25-73, base_conv_layer.cpp:257-321) for stride 1, pad 0, group 1:
+ *   x (N,C,H,W), W (Co,C,kh,kw), bias (Co) or NULL, top (N,Co,H-kh+1,W-kw+1).  Implicit GEMMs on the tensor cores for
+ *   float (no im2col buffer); direct sums for double / MMS_MATH_FP32.  backward: dW and dbias ACCUMULATE, dx is
+ *   OVERWRITTEN; any of the three may be NULL.
+ * mms_dropout_*: DropoutLayer::Forward_gpu / Backward_gpu (dropout_layer.cu:10-45): y = x * (mask > threshold) * scale
+ *   with one random 32-bit word per element, threshold = UINT_MAX * dropout_ratio, scale = 1 / (1 - dropout_ratio);
+ *   the backward is the same call on the top gradient.  mms_dropout_mask fills `mask` from a counter-based generator
+ *   (the reference draws it with cuRAND, dropout_layer.cu:27; any source of uniform words is equivalent). */
+int mms_conv2d_forward_f32(mms_handle_t h, const float* x, const float* W, const float* bias, float* top, int N, int C,
+                           int H, int Wd, int Co, int kh, int kw);
+int mms_conv2d_forward_f64(mms_handle_t h, const double* x, const double* W, const double* bias, double* top, int N,
+                           int C, int H, int Wd, int Co, int kh, int kw);
+int mms_conv2d_backward_f32(mms_handle_t h, const float* x, const float* W, const float* dtop, float* dW, float* dbias,
+                            float* dx, int N, int C, int H, int Wd, int Co, int kh, int kw);
+int mms_conv2d_backward_f64(mms_handle_t h, const double* x, const double* W, const double* dtop, double* dW,
+                            double* dbias, double* dx, int N, int C, int H, int Wd, int Co, int kh, int kw);
+int mms_dropout_f32(mms_handle_t h, const float* x, const unsigned* mask, float* y, long long count,
+                    unsigned threshold, float scale);
+int mms_dropout_f64(mms_handle_t h, const double* x, const unsigned* mask, double* y, long long count,
+                    unsigned threshold, double scale);
+int mms_dropout_mask(mms_handle_t h, unsigned* mask, long long count, unsigned long long seed);
+
 /* ------------------------------------------------- input formats (host) ---
  * embed_param.weight_source: the pre-trained word-vector file EmbedLayer::LayerSetUp reads into blobs_[0]
  * (embed_layer.cpp:46-113).  HOST memory: table_host is the (input_dim, num_output) table as the weight filler left

@@ -12,7 +12,7 @@ library or without a B200 the layers raise.
 """
 from ._lib import MMSError, lib, lib_path  # noqa: F401
 from .blob import Blob  # noqa: F401
-from .layers import (AUCLayer, BNLayer, ConvolutionLayer, EmbedLayer, PoolingLayer, TanHLayer, FMLayer, Layer, LayerParameter, MAPLayer, MRRLayer,  # noqa: F401
+from .layers import (AUCLayer, BNLayer, ConvolutionLayer, DropoutLayer, EmbedLayer, PoolingLayer, TanHLayer, FMLayer, Layer, LayerParameter, MAPLayer, MRRLayer,  # noqa: F401
                      PairRankLossLayer, RankAccuracyLayer, SimCrossLayer, SimMatrixLayer, create_layer)
 from . import parallel  # noqa: F401
 from .net import MMSNet  # noqa: F401
@@ -23,4 +23,4 @@ from .solver import AdaDeltaSolver  # noqa: F401
 __all__ = ["MMSError", "lib", "lib_path", "Blob", "Layer", "LayerParameter", "EmbedLayer",
            "SimCrossLayer", "SimMatrixLayer", "PairRankLossLayer", "FMLayer", "create_layer", "MMSNet", "AdaDeltaSolver", "GradientExchange",
            "MAPLayer", "MRRLayer", "AUCLayer", "RankAccuracyLayer",
-           "ConvolutionLayer", "BNLayer", "PoolingLayer", "TanHLayer", "SentenceVectorNet"]
+           "ConvolutionLayer", "DropoutLayer", "BNLayer", "PoolingLayer", "TanHLayer", "SentenceVectorNet"]

@@ -57,6 +57,9 @@ def _typed(real):
         "mms_bn_forward": [p, p, p, p, p, p, p, p, p, p, c_int, c_int, c_int, c_int, real, real],
         "mms_bn_backward": [p, p, p, p, p, p, p, p, c_int, c_int, c_int],
         "mms_adadelta_step": [p, p, p, p, p, c_ll, real, real, real, real, real, c_int],
+        "mms_conv2d_forward": [p, p, p, p, p] + [c_int] * 7,
+        "mms_conv2d_backward": [p, p, p, p, p, p, p] + [c_int] * 7,
+        "mms_dropout": [p, p, p, p, c_ll, ctypes.c_uint, real],
     }
 
 
@@ -119,6 +122,7 @@ def lib():
         L.mms_rerank_topk_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
         L.mms_rerank_topk_prepared_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
         L.mms_topk_merge_f32.argtypes = [c_p, c_p, c_p, c_ll, c_ll, c_p, c_p, c_int, c_int]
+        L.mms_dropout_mask.argtypes = [c_p, c_p, c_ll, ctypes.c_ulonglong]
         L.mms_tc_gemm_f32.argtypes = [c_p, c_p, c_ll, c_int, c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int,
                                       c_int, c_int]
         _lib = L

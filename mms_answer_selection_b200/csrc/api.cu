@@ -422,6 +422,22 @@ int mms_check_faults(mms_handle_t h) {
                                   T* dbias, T* dx, int N, int L, int D, int C, int kh) {           \
     H; return mms_sentconv_backward_impl<T>(h, x, W, dtop, dW, dbias, dx, N, L, D, C, kh);         \
   }                                                                                                \
+  int mms_conv2d_forward_##SUF(mms_handle_t h, const T* x, const T* W, const T* bias, T* top, int N,  \
+                               int C, int H_, int W_, int Co, int kh, int kw) {                     \
+    H; mms_note_write(top, sizeof(T) * (size_t)(N > 0 ? N : 0) * Co * (size_t)((H_ - kh + 1) > 0 ? (H_ - kh + 1) : 0) * \
+                               (size_t)((W_ - kw + 1) > 0 ? (W_ - kw + 1) : 0));                   \
+    return mms_conv2d_forward_impl<T>(h, x, W, bias, top, N, C, H_, W_, Co, kh, kw);                \
+  }                                                                                                \
+  int mms_conv2d_backward_##SUF(mms_handle_t h, const T* x, const T* W, const T* dtop, T* dW,       \
+                                T* dbias, T* dx, int N, int C, int H_, int W_, int Co, int kh,      \
+                                int kw) {                                                          \
+    H; return mms_conv2d_backward_impl<T>(h, x, W, dtop, dW, dbias, dx, N, C, H_, W_, Co, kh, kw);  \
+  }                                                                                                \
+  int mms_dropout_##SUF(mms_handle_t h, const T* x, const unsigned* mask, T* y, long long count,    \
+                        unsigned threshold, T scale) {                                             \
+    H; mms_note_write(y, sizeof(T) * (size_t)(count > 0 ? count : 0));                             \
+    return mms_dropout_impl<T>(h, x, mask, y, count, threshold, scale);                            \
+  }                                                                                                \
   int mms_pool_forward_##SUF(mms_handle_t h, const T* x, T* top, int* mask, long long NC, int H_,  \
                              int W_, int PH, int PW, int kh, int kw, int sh, int sw, int pad_h,    \
                              int pad_w, int method) {                                              \
@@ -492,6 +508,10 @@ int mms_rerank_prepare_f32(mms_handle_t h, const float* C, float* C_tf32, long l
 int mms_rerank_scores_prepared_f32(mms_handle_t h, const float* Q, const float* C_tf32, const float* W, float* QW,
                                    float* scores, int Nq, long long Nc, int K1, int K2) {
   H; return mms_rerank_scores_prepared_impl(h, Q, C_tf32, W, QW, scores, Nq, Nc, K1, K2);
+}
+
+int mms_dropout_mask(mms_handle_t h, unsigned* mask, long long count, unsigned long long seed) {
+  H; return mms_dropout_mask_impl(h, mask, count, seed);
 }
 
 int mms_rerank_topk_f32(mms_handle_t h, const float* Q, const float* C, const float* W, float* QW, float* top_scores,

@@ -312,6 +312,45 @@ int mms_adadelta_step_impl(mms_context* ctx, T* data, T* diff, T* hist_g, T* his
   return 0;
 }
 
+// ---- Dropout (dropout_layer.cu:10-45): y = x * (mask > threshold) * scale, mask = one random 32-bit word per element
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(const T* __restrict__ x, const unsigned* __restrict__ mask, T* __restrict__ y, long long n, unsigned threshold,
+               T scale) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    y[i] = x[i] * static_cast<T>(mask[i] > threshold) * scale;
+}
+// counter-based generator (splitmix64 of seed and element index): the same words whatever the launch geometry
+__global__ void __launch_bounds__(256) dropout_mask_kernel(unsigned* __restrict__ mask, long long n, unsigned long long seed) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    mask[i] = (unsigned)((z ^ (z >> 31)) >> 32);
+  }
+}
+template <typename T>
+int mms_dropout_impl(mms_context* ctx, const T* x, const unsigned* mask, T* y, long long n, unsigned threshold, T scale) {
+  MMS_REQUIRE(n >= 0, MMS_E_INVALID, "bad size");
+  if (n == 0) return 0;
+  MMS_REQUIRE(x && mask && y, MMS_E_INVALID, "null pointer");
+  { MmsKernelScope ks_(ctx, "dropout_kernel");
+    dropout_kernel<T><<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(x, mask, y, n, threshold, scale); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+int mms_dropout_mask_impl(mms_context* ctx, unsigned* mask, long long n, unsigned long long seed) {
+  MMS_REQUIRE(n >= 0, MMS_E_INVALID, "bad size");
+  if (n == 0) return 0;
+  MMS_REQUIRE(mask, MMS_E_INVALID, "null pointer");
+  { MmsKernelScope ks_(ctx, "dropout_mask_kernel");
+    dropout_mask_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(mask, n, seed); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+template int mms_dropout_impl<float>(mms_context*, const float*, const unsigned*, float*, long long, unsigned, float);
+template int mms_dropout_impl<double>(mms_context*, const double*, const unsigned*, double*, long long, unsigned, double);
+
 #define INST(T)                                                                                        \
   template int mms_pairrankloss_forward_impl<T>(mms_context*, const T*, const T*, const T*, T, long long, T*, T*, T*); \
   template int mms_pairrankloss_backward_impl<T>(mms_context*, const T*, const T*, const T*, T, long long, T*, T*);    \

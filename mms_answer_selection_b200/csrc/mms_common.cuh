@@ -238,6 +238,15 @@ template <typename T>
 int mms_sentconv_backward_impl(mms_context*, const T* x, const T* W, const T* dtop, T* dW, T* dbias, T* dx, int N, int L,
                                int D, int C, int kh);
 template <typename T>
+int mms_conv2d_forward_impl(mms_context*, const T* x, const T* W, const T* bias, T* top, int N, int C, int H, int Wd, int Co,
+                            int kh, int kw);
+template <typename T>
+int mms_conv2d_backward_impl(mms_context*, const T* x, const T* W, const T* dtop, T* dW, T* dbias, T* dx, int N, int C, int H,
+                             int Wd, int Co, int kh, int kw);
+template <typename T>
+int mms_dropout_impl(mms_context*, const T* x, const unsigned* mask, T* y, long long n, unsigned threshold, T scale);
+int mms_dropout_mask_impl(mms_context*, unsigned* mask, long long n, unsigned long long seed);
+template <typename T>
 int mms_pool_forward_impl(mms_context*, const T* x, T* top, int* mask, long long NC, int H, int W, int PH, int PW, int kh,
                           int kw, int sh, int sw, int pad_h, int pad_w, int method);
 template <typename T>

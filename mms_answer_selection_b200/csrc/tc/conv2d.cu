@@ -1,0 +1,541 @@
+// 2-D convolution of the CNN that consumes the similarity tensor S in the reference's net
+// (examples/trec_qa_w2v_mms/do_trec_qa_clean.py:470-477: Conv 5x5 (mc -> 32) + BN -> AvePool 4 -> TanH -> Conv 5x5
+// (32 -> 64) + BN -> AvePool 5 -> TanH), as implicit GEMMs on tcgen05 (TF32 multiply, fp32 accumulate in TMEM).
+// Reference layer: ConvolutionLayer (conv_layer.cpp:25-73) over BaseConvolutionLayer's im2col + gemm
+// (base_conv_layer.cpp:257-321), stride 1, pad 0, group 1 -- the geometry of the net; other geometries are refused.
+//
+// The reference materialises the im2col matrix per sample (kh*kw = 25 copies of every input value) and calls one gemm
+// per sample.  Here the im2col matrix never exists: its elements are gathered straight from the NCHW tensor into the
+// shared-memory operand tile (separable addressing: element (row, k) of the matrix is src[f(row) + g(k)], g from a
+// small table), rounded to TF32 on the way, in the canonical 128-byte-swizzled K-major UMMA layout:
+//
+//   forward  Y[(n,oy,ox)][o] = sum_k A[(n,oy,ox)][k] Wm[o][k] + b[o]     A gathered from x,  k = (c,ky,kx)   M = N*OH*OW
+//   dx       dX[(n,y,x)][c]  = sum_k G[(n,y,x)][k]  Wt[c][k]             G gathered from dY with (y-ky, x-kx) and zero
+//                                                                         padding, k = (o,ky,kx), Wt = weights re-laid out
+//   dW       dW[o][k]       += sum_(n,p) dY[n][o][p] A[(n,p)][k]         the reduction runs over positions: dY is the
+//                                                                         K-major A operand as it lies in memory, the
+//                                                                         gathered matrix is the B operand; images are
+//                                                                         split over CTAs, red.global.add into dW
+// One persistent kernel (warps 0-3 epilogue, warp 4 MMA issue, warps 5-12 operand staging; mbarrier ring; double-
+// buffered TMEM accumulator), three modes.  The outputs leave in NCHW directly from the accumulator rows (a warp's 32
+// lanes are 32 consecutive positions of one channel plane: 128 contiguous bytes per store).
+#include "../mms_common.cuh"
+#include "tc_gemm.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;
+constexpr int kEpiWarps = 4;
+constexpr int kLoadWarps = 8;
+constexpr int kLoadThreads = kLoadWarps * 32;
+constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps) * 32;
+constexpr int kMaxStages = 6;
+constexpr int kMaxKc = 2048;            // entries of the k-offset table
+
+enum { kFwd = 0, kDx = 1, kDw = 2 };
+
+struct ConvArgs {
+  const float* src;        // gathered tensor: x (fwd, dW) or dY (dx): (Nimg, Cs, Hs, Ws)
+  int Cs, Hs, Ws;
+  int Hg, Wg;              // grid the gathered rows walk, per image: OH x OW (fwd, dW) or H x W (dx)
+  int sgn;                 // +1: (y + ky, x + kx);  -1: (y - ky, x - kx) with zero padding
+  int kh, kw, Kc;          // Kc = Cs * kh * kw
+  int Nimg;
+  const float* dense;      // fwd / dx: weight matrix [Ncols][Kc];  dW: dY (Nimg, Co, P)
+  int Ncols;               // fwd: C_out, dx: C_in
+  float* out;              // fwd / dx: (Nimg, Ncols, Hg, Wg);  dW: [Co][Kc], accumulated
+  const float* bias;       // fwd: [C_out] or null
+  int Co;                  // dW: rows of dW (= channels of dY)
+  int BN, n_tiles, isplit, stages;
+  long long Mtot;          // fwd / dx: Nimg * Hg * Wg
+  unsigned total_tiles;
+  uint32_t tmem_cols;
+};
+
+struct Smem {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct Tile { long long m0; int n0, img0, img1, nk; };
+
+__device__ __forceinline__ Tile decode(const ConvArgs& g, unsigned t, int mode, int sps) {
+  Tile tl;
+  if (mode != kDw) {
+    tl.m0 = (long long)t * kBM; tl.n0 = 0; tl.img0 = tl.img1 = 0; tl.nk = sps;
+  } else {
+    const int nt = t % g.n_tiles, sp = t / g.n_tiles;
+    const int per = (g.Nimg + g.isplit - 1) / g.isplit;
+    tl.m0 = 0; tl.n0 = nt * g.BN;
+    tl.img0 = min(g.Nimg, sp * per); tl.img1 = min(g.Nimg, tl.img0 + per);
+    tl.nk = (tl.img1 - tl.img0) * sps;
+  }
+  return tl;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv2d_kernel(const ConvArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int b_bytes = g.BN * 128;
+  const int stage_bytes = 16384 + b_bytes;
+  Smem* sm = reinterpret_cast<Smem*>(ring + g.stages * stage_bytes);
+  int* koff = reinterpret_cast<int*>(sm + 1);              // g(k): offset of gathered column k
+  int* kyx = koff + g.Kc;                                  // (ky << 16) | kx, for the zero padding of dx
+
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
+  const int plane_g = g.Hg * g.Wg;
+  // stages per reduction unit: fwd / dx: k blocks of the gathered matrix; dW: position blocks of one image
+  const int sps = MODE == kDw ? (plane_g + kBK - 1) / kBK : (g.Kc + kBK - 1) / kBK;
+  for (int k = threadIdx.x; k < g.Kc; k += kThreads) {
+    const int c = k / (g.kh * g.kw), r = k - c * g.kh * g.kw, ky = r / g.kw, kx = r - ky * g.kw;
+    koff[k] = c * g.Hs * g.Ws + g.sgn * (ky * g.Ws + kx);
+    kyx[k] = (ky << 16) | kx;
+  }
+  if (warp == kEpiWarps) {
+    if (lane == 0) {
+      for (int s = 0; s < g.stages; ++s) { mbar_init(&sm->full[s], kLoadWarps); mbar_init(&sm->empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], kEpiWarps); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm->tmem_base, g.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const long long src_img = (long long)g.Cs * g.Hs * g.Ws;
+
+  if (warp > kEpiWarps) {
+    // ------------------------------------------------------------ operand staging
+    const int tid = threadIdx.x - (kEpiWarps + 1) * 32;
+    const int r0 = tid >> 3, c4 = tid & 7;
+    const uint32_t soff0 = swz128(r0, c4);                 // chunk j of this thread: + j * 4096 (32 rows further down)
+    int it = 0;
+    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+      const Tile tl = decode(g, t, MODE, sps);
+      // per-tile row geometry of the gathered operand
+      long long gbase[8]; int gy[8], gx[8]; bool gok[8];
+      if (MODE != kDw) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long m = tl.m0 + r0 + 32 * j;
+          gok[j] = m < g.Mtot;
+          const long long n = gok[j] ? m / plane_g : 0;
+          const int p = gok[j] ? (int)(m - n * plane_g) : 0;
+          gy[j] = p / g.Wg; gx[j] = p - gy[j] * g.Wg;
+          gbase[j] = n * src_img + (long long)gy[j] * g.Ws + gx[j];
+        }
+      }
+      for (int i = 0; i < tl.nk; ++i, ++it) {
+        const int s = it % g.stages;
+        float4 va[4], vb[8];
+        if (MODE != kDw) {
+          const int k0 = i * kBK + c4 * 4;
+          // gathered A: rows = positions, 4 consecutive gathered columns per chunk
+          int ko[4], kq[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const int k = k0 + e; ko[e] = k < g.Kc ? koff[k] : 0; kq[e] = k < g.Kc ? kyx[k] : -1; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              bool ok = gok[j] && kq[e] >= 0;
+              if (MODE == kDx && ok) {
+                const int yy = gy[j] - (kq[e] >> 16), xx = gx[j] - (kq[e] & 0xffff);
+                ok = yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws;
+              }
+              v[e] = ok ? __ldg(g.src + gbase[j] + ko[e]) : 0.f;
+            }
+            va[j] = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          // dense B: weight matrix rows (output columns), 4 consecutive k
+          const int nb = g.BN / 32 + ((g.BN & 31) ? 1 : 0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int row = r0 + 32 * j;
+            if (j < nb && row < g.Ncols) {
+              const float* p = g.dense + (long long)row * g.Kc + k0;
+              if (k0 + 3 < g.Kc && (g.Kc & 3) == 0) vb[j] = __ldg(reinterpret_cast<const float4*>(p));
+              else {
+                if (k0 < g.Kc) vb[j].x = __ldg(p);
+                if (k0 + 1 < g.Kc) vb[j].y = __ldg(p + 1);
+                if (k0 + 2 < g.Kc) vb[j].z = __ldg(p + 2);
+                if (k0 + 3 < g.Kc) vb[j].w = __ldg(p + 3);
+              }
+            }
+          }
+        } else {
+          const int img = tl.img0 + i / sps, p0 = (i % sps) * kBK + c4 * 4;
+          // dense A: dY of this image, rows = channels, 4 consecutive positions
+          const float* dy = g.dense + (long long)img * g.Co * plane_g;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int o = r0 + 32 * j;
+            if (o < g.Co) {
+              const float* p = dy + (long long)o * plane_g + p0;
+              if (p0 < plane_g) va[j].x = __ldg(p);
+              if (p0 + 1 < plane_g) va[j].y = __ldg(p + 1);
+              if (p0 + 2 < plane_g) va[j].z = __ldg(p + 2);
+              if (p0 + 3 < plane_g) va[j].w = __ldg(p + 3);
+            }
+          }
+          // gathered B: rows = gathered columns of this N tile, 4 consecutive positions of the image
+          long long pb[4]; bool pok[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int p = p0 + e;
+            pok[e] = p < plane_g;
+            const int oy = pok[e] ? p / g.Wg : 0, ox = pok[e] ? p - oy * g.Wg : 0;
+            pb[e] = (long long)img * src_img + (long long)oy * g.Ws + ox;
+          }
+          const int nb = g.BN / 32 + ((g.BN & 31) ? 1 : 0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int kk = tl.n0 + r0 + 32 * j;
+            if (j < nb && r0 + 32 * j < g.BN && kk < g.Kc) {
+              const int ko = koff[kk];
+              if (pok[0]) vb[j].x = __ldg(g.src + pb[0] + ko);
+              if (pok[1]) vb[j].y = __ldg(g.src + pb[1] + ko);
+              if (pok[2]) vb[j].z = __ldg(g.src + pb[2] + ko);
+              if (pok[3]) vb[j].w = __ldg(g.src + pb[3] + ko);
+            }
+          }
+        }
+        if (it >= g.stages) mbar_wait(&sm->empty[s], ((it / g.stages) - 1) & 1);
+        uint8_t* a_dst = ring + s * stage_bytes;
+        uint8_t* b_dst = a_dst + 16384;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 o = va[j];
+          o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
+          *reinterpret_cast<float4*>(a_dst + soff0 + j * 4096) = o;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (r0 + 32 * j < g.BN) {
+            float4 o = vb[j];
+            o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
+            *reinterpret_cast<float4*>(b_dst + soff0 + j * 4096) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->full[s]);
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // ------------------------------------------------------------ MMA issue
+    const uint32_t idesc = idesc_tf32(kBM, g.BN, false, false);
+    int it = 0, tcount = 0;
+    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tcount) {
+      const Tile tl = decode(g, t, MODE, sps);
+      const int buf = tcount & 1;
+      if (tcount >= 2) mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * g.BN;
+      for (int i = 0; i < tl.nk; ++i, ++it) {
+        const int s = it % g.stages;
+        mbar_wait(&sm->full[s], (it / g.stages) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(ring + s * stage_bytes);
+        const uint32_t b_base = a_base + 16384;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int ks = 0; ks < kBK / 8; ++ks)
+            mma_tf32_ss(acc, desc_kmajor(a_base + ks * 32), desc_kmajor(b_base + ks * 32), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          mma_commit(&sm->empty[s]);
+          if (i == tl.nk - 1) mma_commit(&sm->acc_full[buf]);
+        }
+        __syncwarp();
+      }
+      if (tl.nk == 0) {
+        if (elect_one_sync()) mma_commit(&sm->acc_full[buf]);
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue
+    int tcount = 0;
+    for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tcount) {
+      const Tile tl = decode(g, t, MODE, sps);
+      const int buf = tcount & 1;
+      mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * g.BN + ((uint32_t)(warp * 32) << 16);
+      const int rl = warp * 32 + lane;
+      if (MODE != kDw) {
+        const long long m = tl.m0 + rl;
+        const bool ok = m < g.Mtot;
+        const long long n = ok ? m / plane_g : 0;
+        const int p = ok ? (int)(m - n * plane_g) : 0;
+        float* orow = g.out + n * (long long)g.Ncols * plane_g + p;
+        for (int c0 = 0; c0 < g.BN; c0 += 32) {
+          float v[32];
+          if (c0 + 16 < g.BN) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+          if (!ok) continue;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int o = c0 + i;
+            if (o < g.Ncols && o < g.BN) orow[(long long)o * plane_g] = v[i] + (g.bias ? __ldg(g.bias + o) : 0.f);
+          }
+        }
+      } else {
+        const int ncols = min(g.BN, g.Kc - tl.n0);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          float v[32];
+          if (tl.nk > 0) {
+            if (c0 + 16 < g.BN) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          if (rl >= g.Co || tl.nk == 0) continue;
+          float* wrow = g.out + (long long)rl * g.Kc + tl.n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < ncols) atomicAdd(wrow + i, v[i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc(tmem, g.tmem_cols);
+}
+
+// weights (Co, C, kh, kw) -> Wt[c][(o, ky, kx)]: the dense operand of the dx contraction
+__global__ void conv_wt_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Co, int C, int khw) {
+  const int total = Co * C * khw;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int o = e / (C * khw), r = e - o * C * khw, c = r / khw, t = r - c * khw;
+    Wt[(size_t)c * Co * khw + o * khw + t] = W[e];
+  }
+}
+
+// dbias[o] += sum over (n, p) of dY[n][o][p]   (gemv against the ones vector in the reference, base_conv_layer.cpp:312-316)
+template <typename T>
+__global__ void __launch_bounds__(256) conv_bias_grad_kernel(const T* __restrict__ dy, T* __restrict__ db, int N, int Co, int P) {
+  const int o = blockIdx.x;
+  T acc = T(0);
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    const T* p = dy + ((size_t)n * Co + o) * P;
+    for (int i = threadIdx.x; i < P; i += 256) acc += p[i];
+  }
+  __shared__ T s[256];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) s[threadIdx.x] += s[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(db + o, s[0]);
+}
+
+// ---- SIMT forms (double blobs, MMS_MATH_FP32, shapes outside the tensor-core kernel): direct sums
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_fwd_simt(const T* __restrict__ x, const T* __restrict__ W, const T* __restrict__ b, T* __restrict__ y, long long total,
+              int C, int H, int Wd, int Co, int kh, int kw, int OH, int OW) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const int ox = (int)(e % OW); long long r = e / OW;
+    const int oy = (int)(r % OH); r /= OH;
+    const int o = (int)(r % Co); const long long n = r / Co;
+    T acc = b ? b[o] : T(0);
+    for (int c = 0; c < C; ++c)
+      for (int ky = 0; ky < kh; ++ky)
+        for (int kx = 0; kx < kw; ++kx)
+          acc += x[((n * C + c) * H + oy + ky) * Wd + ox + kx] * W[((o * C + c) * kh + ky) * kw + kx];
+    y[e] = acc;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_dx_simt(const T* __restrict__ dy, const T* __restrict__ W, T* __restrict__ dx, long long total, int C, int H, int Wd,
+             int Co, int kh, int kw, int OH, int OW) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const int xx = (int)(e % Wd); long long r = e / Wd;
+    const int yy = (int)(r % H); r /= H;
+    const int c = (int)(r % C); const long long n = r / C;
+    T acc = T(0);
+    for (int o = 0; o < Co; ++o)
+      for (int ky = 0; ky < kh; ++ky) {
+        const int oy = yy - ky;
+        if (oy < 0 || oy >= OH) continue;
+        for (int kx = 0; kx < kw; ++kx) {
+          const int ox = xx - kx;
+          if (ox < 0 || ox >= OW) continue;
+          acc += dy[((n * Co + o) * OH + oy) * OW + ox] * W[((o * C + c) * kh + ky) * kw + kx];
+        }
+      }
+    dx[e] = acc;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_dw_simt(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dW, int N, int C, int H, int Wd, int Co, int kh,
+             int kw, int OH, int OW) {
+  // one CTA per weight: the (n, oy, ox) sum is spread over the threads
+  const int e = blockIdx.x;
+  const int kx = e % kw; int r = e / kw;
+  const int ky = r % kh; r /= kh;
+  const int c = r % C; const int o = r / C;
+  T acc = T(0);
+  const long long total = (long long)N * OH * OW;
+  for (long long i = threadIdx.x; i < total; i += 256) {
+    const int ox = (int)(i % OW); long long q = i / OW;
+    const int oy = (int)(q % OH); const long long n = q / OH;
+    acc += dy[((n * Co + o) * OH + oy) * OW + ox] * x[((n * C + c) * H + oy + ky) * Wd + ox + kx];
+  }
+  __shared__ T s[256];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) s[threadIdx.x] += s[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dW[e] += s[0];
+}
+
+int launch_tc(mms_context* ctx, ConvArgs& g, int mode) {
+  int stages = kMaxStages;
+  const size_t tail = sizeof(Smem) + 2 * sizeof(int) * (size_t)g.Kc + 1024;
+  while (stages > 2 && (size_t)stages * (16384 + g.BN * 128) + tail > 200 * 1024) --stages;
+  g.stages = stages;
+  g.tmem_cols = umma::tmem_cols_pow2(2 * g.BN);
+  const size_t smem = (size_t)stages * (16384 + g.BN * 128) + tail;
+  static bool configured = false;
+  if (!configured) {
+    MMS_MAX_SMEM(conv2d_kernel<kFwd>, 201 * 1024);
+    MMS_MAX_SMEM(conv2d_kernel<kDx>, 201 * 1024);
+    MMS_MAX_SMEM(conv2d_kernel<kDw>, 201 * 1024);
+    configured = true;
+  }
+  const unsigned grid = (unsigned)mms_min<long long>(g.total_tiles, ctx->sm_count);
+  if (mode == kFwd) { MmsKernelScope ks_(ctx, "conv2d_fwd_kernel"); conv2d_kernel<kFwd><<<grid, kThreads, smem, ctx->stream>>>(g); }
+  else if (mode == kDx) { MmsKernelScope ks_(ctx, "conv2d_dx_kernel"); conv2d_kernel<kDx><<<grid, kThreads, smem, ctx->stream>>>(g); }
+  else { MmsKernelScope ks_(ctx, "conv2d_dw_kernel"); conv2d_kernel<kDw><<<grid, kThreads, smem, ctx->stream>>>(g); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+bool tc_shape_ok(int C, int Co, int kh, int kw) {
+  return C * kh * kw <= kMaxKc && Co * kh * kw <= kMaxKc && Co <= 128 && C <= 256;
+}
+
+inline int ew_grid(mms_context* ctx, long long n) {
+  return (int)mms_max<long long>(1, mms_min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16));
+}
+
+}  // namespace
+
+template <typename T>
+int mms_conv2d_forward_impl(mms_context* ctx, const T* x, const T* W, const T* bias, T* top, int N, int C, int H, int Wd,
+                            int Co, int kh, int kw) {
+  MMS_REQUIRE(x && W && top, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && C > 0 && Co > 0 && kh > 0 && kw > 0 && H >= kh && Wd >= kw, MMS_E_INVALID, "bad size");
+  if (N == 0) return 0;
+  const int OH = H - kh + 1, OW = Wd - kw + 1;
+  if (sizeof(T) == 4 && ctx->math == MMS_MATH_TF32 && tc_shape_ok(C, Co, kh, kw)) {
+    ConvArgs g = {};
+    g.src = reinterpret_cast<const float*>(x); g.Cs = C; g.Hs = H; g.Ws = Wd; g.Hg = OH; g.Wg = OW; g.sgn = 1;
+    g.kh = kh; g.kw = kw; g.Kc = C * kh * kw; g.Nimg = N;
+    g.dense = reinterpret_cast<const float*>(W); g.Ncols = Co;
+    g.out = reinterpret_cast<float*>(top); g.bias = reinterpret_cast<const float*>(bias);
+    g.BN = mms_ceil_div(Co, 16) * 16; g.n_tiles = 1; g.isplit = 1;
+    g.Mtot = (long long)N * OH * OW;
+    MMS_REQUIRE(mms_ceil_div(g.Mtot, kBM) <= 0x7fffffff, MMS_E_UNSUPPORTED, "too many rows");
+    g.total_tiles = (unsigned)mms_ceil_div(g.Mtot, kBM);
+    return launch_tc(ctx, g, kFwd);
+  }
+  const long long total = (long long)N * Co * OH * OW;
+  { MmsKernelScope ks_(ctx, "conv2d_fwd_simt");
+    conv_fwd_simt<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(x, W, bias, top, total, C, H, Wd, Co, kh, kw, OH, OW); }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int mms_conv2d_backward_impl(mms_context* ctx, const T* x, const T* W, const T* dtop, T* dW, T* dbias, T* dx, int N, int C,
+                             int H, int Wd, int Co, int kh, int kw) {
+  MMS_REQUIRE(x && W && dtop, MMS_E_INVALID, "null pointer");
+  MMS_REQUIRE(N >= 0 && C > 0 && Co > 0 && kh > 0 && kw > 0 && H >= kh && Wd >= kw, MMS_E_INVALID, "bad size");
+  if (N == 0) return 0;
+  const int OH = H - kh + 1, OW = Wd - kw + 1, P = OH * OW;
+  const bool tc = sizeof(T) == 4 && ctx->math == MMS_MATH_TF32 && tc_shape_ok(C, Co, kh, kw);
+  if (dbias) {
+    dim3 grid(Co, mms_max(1, mms_min(N, mms_ceil_div(4 * ctx->sm_count, Co))));
+    MmsKernelScope ks_(ctx, "conv2d_bias_grad_kernel");
+    conv_bias_grad_kernel<T><<<grid, 256, 0, ctx->stream>>>(dtop, dbias, N, Co, P);
+    MMS_LAUNCH_CHECK();
+  }
+  if (dW) {
+    if (tc) {
+      ConvArgs g = {};
+      g.src = reinterpret_cast<const float*>(x); g.Cs = C; g.Hs = H; g.Ws = Wd; g.Hg = OH; g.Wg = OW; g.sgn = 1;
+      g.kh = kh; g.kw = kw; g.Kc = C * kh * kw; g.Nimg = N;
+      g.dense = reinterpret_cast<const float*>(dtop); g.Co = Co;
+      g.out = reinterpret_cast<float*>(dW);
+      g.n_tiles = mms_ceil_div(g.Kc, 256);
+      g.BN = mms_ceil_div(mms_ceil_div(g.Kc, g.n_tiles), 16) * 16;
+      g.n_tiles = mms_ceil_div(g.Kc, g.BN);
+      g.isplit = mms_max(1, mms_min(N, ctx->sm_count / g.n_tiles));
+      g.total_tiles = (unsigned)(g.n_tiles * g.isplit);
+      MMS_TRY(launch_tc(ctx, g, kDw));
+    } else {
+      MmsKernelScope ks_(ctx, "conv2d_dw_simt");
+      conv_dw_simt<T><<<Co * C * kh * kw, 256, 0, ctx->stream>>>(x, dtop, dW, N, C, H, Wd, Co, kh, kw, OH, OW);
+      MMS_LAUNCH_CHECK();
+    }
+  }
+  if (dx) {
+    if (tc) {
+      void* sp = nullptr;
+      MMS_TRY(mms_scratch(ctx, sizeof(float) * (size_t)C * Co * kh * kw, &sp));
+      float* Wt = static_cast<float*>(sp);
+      { MmsKernelScope ks_(ctx, "conv2d_wt_kernel");
+        conv_wt_kernel<<<mms_ceil_div((long long)C * Co * kh * kw, 256), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const float*>(W), Wt, Co, C, kh * kw); }
+      MMS_LAUNCH_CHECK();
+      ConvArgs g = {};
+      g.src = reinterpret_cast<const float*>(dtop); g.Cs = Co; g.Hs = OH; g.Ws = OW; g.Hg = H; g.Wg = Wd; g.sgn = -1;
+      g.kh = kh; g.kw = kw; g.Kc = Co * kh * kw; g.Nimg = N;
+      g.dense = Wt; g.Ncols = C;
+      g.out = reinterpret_cast<float*>(dx); g.bias = nullptr;
+      g.BN = mms_ceil_div(C, 16) * 16; g.n_tiles = 1; g.isplit = 1;
+      g.Mtot = (long long)N * H * Wd;
+      MMS_REQUIRE(mms_ceil_div(g.Mtot, kBM) <= 0x7fffffff, MMS_E_UNSUPPORTED, "too many rows");
+      g.total_tiles = (unsigned)mms_ceil_div(g.Mtot, kBM);
+      MMS_TRY(launch_tc(ctx, g, kDx));
+    } else {
+      const long long total = (long long)N * C * H * Wd;
+      MmsKernelScope ks_(ctx, "conv2d_dx_simt");
+      conv_dx_simt<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, W, dx, total, C, H, Wd, Co, kh, kw, OH, OW);
+      MMS_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
+template int mms_conv2d_forward_impl<float>(mms_context*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int);
+template int mms_conv2d_forward_impl<double>(mms_context*, const double*, const double*, const double*, double*, int, int, int, int, int, int, int);
+template int mms_conv2d_backward_impl<float>(mms_context*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int, int);
+template int mms_conv2d_backward_impl<double>(mms_context*, const double*, const double*, const double*, double*, double*, double*, int, int, int, int, int, int, int);

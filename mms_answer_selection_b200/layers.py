@@ -58,6 +58,7 @@ _DEFAULTS = {
                               group=1, weight_filler=None, bias_filler=None),   # caffe.proto ConvolutionParameter
     "pooling_param": dict(pool="MAX", kernel_h=0, kernel_w=0, kernel_size=0, stride=1, stride_h=0, stride_w=0,
                           pad=0, pad_h=0, pad_w=0, global_pooling=False),       # caffe.proto PoolingParameter
+    "dropout_param": dict(dropout_ratio=0.5, seed=1701),                 # caffe.proto DropoutParameter (+ the mask seed)
     "bn_param": dict(bn_memory=0.9, scale_filler=None, shift_filler=None),      # caffe.proto:484-488
     "map_param": dict(fixed_axis=1),                                    # caffe.proto:422-424
     "mrr_param": dict(fixed_axis=1),                                    # caffe.proto:426-428
@@ -419,9 +420,10 @@ class FMLayer(Layer):
 
 # ------------------------------------------------------------------------- sentence encoder
 class ConvolutionLayer(Layer):
-    """ConvolutionLayer (conv_layer.cpp, base_conv_layer.cpp) for the sentence convolution of the reference net
-    (do_trec_qa_clean.py:352-358, 412-416): one input channel, kernel (kernel_h x input width), stride 1, pad 0,
-    group 1.  Other geometries are the stock Caffe layer's business and are refused."""
+    """ConvolutionLayer (conv_layer.cpp, base_conv_layer.cpp), stride 1, pad 0, group 1 -- the two geometries of the
+    reference's nets: the sentence convolution (do_trec_qa_clean.py:352-358, 412-416: one input channel, kernel as wide
+    as the input; mms_sentconv_*) and the 2-D convolutions over the similarity tensor (:470-477; mms_conv2d_*).  Other
+    geometries are the stock Caffe layer's business and are refused."""
     exact_num_bottom = 1
 
     def LayerSetUp(self, bottom, top):
@@ -432,13 +434,13 @@ class ConvolutionLayer(Layer):
         self.num_output_ = int(cp["num_output"])
         _check(self.num_output_ > 0, "num_output must be positive")
         self.bias_term_ = bool(cp["bias_term"])
-        _check(bottom[0].num_axes() == 4, "sentence convolution takes (N, 1, L, D) bottoms")
-        _check(bottom[0].channels() == 1 and int(cp["group"]) == 1 and int(cp["stride"]) == 1 and int(cp["pad"]) == 0
-               and self.kernel_w_ == bottom[0].width(),
-               "Convolution (mms_b200): only the sentence convolution (1 channel, kernel_w = input width, stride 1, "
-               "pad 0, group 1) runs here")
+        _check(bottom[0].num_axes() == 4, "convolution takes (N, C, H, W) bottoms")
+        _check(int(cp["group"]) == 1 and int(cp["stride"]) == 1 and int(cp["pad"]) == 0,
+               "Convolution (mms_b200): only stride 1, pad 0, group 1 runs here")
+        self.channels_ = bottom[0].channels()
+        self.sentence_ = self.channels_ == 1 and self.kernel_w_ == bottom[0].width()
         if not self.blobs_:                                   # base_conv_layer.cpp:137-160
-            self.blobs_.append(self._new_blob((self.num_output_, 1, self.kernel_h_, self.kernel_w_), bottom[0]))
+            self.blobs_.append(self._new_blob((self.num_output_, self.channels_, self.kernel_h_, self.kernel_w_), bottom[0]))
             _fill(self.blobs_[0], cp["weight_filler"], self.rng)
             if self.bias_term_:
                 self.blobs_.append(self._new_blob((self.num_output_,), bottom[0]))
@@ -446,19 +448,84 @@ class ConvolutionLayer(Layer):
         self.param_propagate_down_ = [True] * len(self.blobs_)
 
     def Reshape(self, bottom, top):
-        _check(bottom[0].height() >= self.kernel_h_, "kernel taller than the input")
-        top[0].Reshape((bottom[0].num(), self.num_output_, bottom[0].height() - self.kernel_h_ + 1, 1))
+        _check(bottom[0].height() >= self.kernel_h_ and bottom[0].width() >= self.kernel_w_, "kernel larger than the input")
+        _check(bottom[0].channels() == self.channels_, "Input size incompatible with convolution kernel.")
+        top[0].Reshape((bottom[0].num(), self.num_output_, bottom[0].height() - self.kernel_h_ + 1,
+                        bottom[0].width() - self.kernel_w_ + 1))
 
     def Forward_gpu(self, bottom, top):
-        self._call("mms_sentconv_forward", _p(bottom[0]), _p(self.blobs_[0]), _p(self.blobs_[1] if self.bias_term_ else None),
-                   _p(top[0]), bottom[0].num(), bottom[0].height(), bottom[0].width(), self.num_output_, self.kernel_h_)
+        bias = self.blobs_[1] if self.bias_term_ else None
+        if self.sentence_:
+            self._call("mms_sentconv_forward", _p(bottom[0]), _p(self.blobs_[0]), _p(bias), _p(top[0]), bottom[0].num(),
+                       bottom[0].height(), bottom[0].width(), self.num_output_, self.kernel_h_)
+        else:
+            self._call("mms_conv2d_forward", _p(bottom[0]), _p(self.blobs_[0]), _p(bias), _p(top[0]), bottom[0].num(),
+                       self.channels_, bottom[0].height(), bottom[0].width(), self.num_output_, self.kernel_h_,
+                       self.kernel_w_)
 
     def Backward_gpu(self, top, propagate_down, bottom):
         dW = self.blobs_[0] if self.param_propagate_down_[0] else None
         db = self.blobs_[1] if (self.bias_term_ and self.param_propagate_down_[1]) else None
-        self._call("mms_sentconv_backward", _p(bottom[0]), _p(self.blobs_[0]), _p(top[0], True), _p(dW, True), _p(db, True),
-                   _p(bottom[0] if propagate_down[0] else None, True), bottom[0].num(), bottom[0].height(),
-                   bottom[0].width(), self.num_output_, self.kernel_h_)
+        dx = bottom[0] if propagate_down[0] else None
+        if self.sentence_:
+            self._call("mms_sentconv_backward", _p(bottom[0]), _p(self.blobs_[0]), _p(top[0], True), _p(dW, True),
+                       _p(db, True), _p(dx, True), bottom[0].num(), bottom[0].height(), bottom[0].width(),
+                       self.num_output_, self.kernel_h_)
+        else:
+            self._call("mms_conv2d_backward", _p(bottom[0]), _p(self.blobs_[0]), _p(top[0], True), _p(dW, True),
+                       _p(db, True), _p(dx, True), bottom[0].num(), self.channels_, bottom[0].height(), bottom[0].width(),
+                       self.num_output_, self.kernel_h_, self.kernel_w_)
+
+
+class DropoutLayer(Layer):
+    """DropoutLayer (dropout_layer.cpp:13-75, dropout_layer.cu:10-60): TRAIN: top = bottom * (mask > threshold) * scale with
+    one random 32-bit word per element (drawn by mms_dropout_mask, a counter-based generator seeded per forward, or set
+    by the caller in ``rand_vec_``); TEST: a copy.  In place is allowed."""
+    exact_num_bottom = 1
+
+    def LayerSetUp(self, bottom, top):
+        self.threshold_ = float(self.layer_param_.dropout_param["dropout_ratio"])
+        _check(0.0 < self.threshold_ < 1.0, "threshold_ > 0. && threshold_ < 1.")
+        self.scale_ = 1.0 / (1.0 - self.threshold_)
+        self.uint_thres_ = int(4294967295 * self.threshold_)                   # UINT_MAX * threshold_ (dropout_layer.cpp:21)
+        self.rand_vec_ = None
+        self.seed_ = int(self.layer_param_.dropout_param["seed"])
+        self.fixed_mask_ = False
+        self.calls_ = 0
+
+    def Reshape(self, bottom, top):
+        top[0].Reshape(bottom[0].shape)
+        n = bottom[0].count()
+        if self.rand_vec_ is None or self.rand_vec_.numel() != n:
+            self.rand_vec_ = torch.zeros(n, dtype=torch.int32, device=bottom[0].device)
+            self.fixed_mask_ = False
+
+    def set_mask(self, words):
+        """Test hook: use these 32-bit words instead of drawing new ones every forward."""
+        self.rand_vec_.copy_(torch.as_tensor(np.asarray(words, dtype=np.uint32).view(np.int32)).reshape(-1))
+        self.fixed_mask_ = True
+
+    def Forward_gpu(self, bottom, top):
+        n = bottom[0].count()
+        if self.layer_param_.phase == "TRAIN":
+            if not self.fixed_mask_:
+                check(lib().mms_dropout_mask(self.handle.ptr, c_p(self.rand_vec_.data_ptr()), n,
+                                             ctypes.c_ulonglong(self.seed_ + 0x51ED27 * self.calls_)))
+                self.calls_ += 1
+            self._call("mms_dropout", _p(bottom[0]), c_p(self.rand_vec_.data_ptr()), _p(top[0]), n,
+                       ctypes.c_uint(self.uint_thres_), self.real(self.scale_))
+        elif top[0].gpu_data() != bottom[0].gpu_data():
+            top[0].data.copy_(bottom[0].data)
+
+    def Backward_gpu(self, top, propagate_down, bottom):
+        if not propagate_down[0]:
+            return
+        n = bottom[0].count()
+        if self.layer_param_.phase == "TRAIN":
+            self._call("mms_dropout", _p(top[0], True), c_p(self.rand_vec_.data_ptr()), _p(bottom[0], True), n,
+                       ctypes.c_uint(self.uint_thres_), self.real(self.scale_))
+        elif top[0].gpu_diff() != bottom[0].gpu_diff():
+            bottom[0].diff.copy_(top[0].diff)
 
 
 class PoolingLayer(Layer):
@@ -665,7 +732,7 @@ class RankAccuracyLayer(Layer):
 _REGISTRY = {"Embed": EmbedLayer, "SimCross": SimCrossLayer, "SimMatrix": SimMatrixLayer,
              "PairRankLoss": PairRankLossLayer, "FM": FMLayer, "MAP": MAPLayer, "MRR": MRRLayer, "AUC": AUCLayer,
              "RankAccuracy": RankAccuracyLayer, "Convolution": ConvolutionLayer, "Pooling": PoolingLayer,
-             "TanH": TanHLayer, "BN": BNLayer}
+             "TanH": TanHLayer, "BN": BNLayer, "Dropout": DropoutLayer}
 
 
 def create_layer(param):

@@ -402,3 +402,22 @@ def test_sentence_encoder_restatement_matches_reference_fixtures(tag, tol):
         assert err(snp.pool_backward(g[k + name + "/dtop"], mask, src.shape, **geom), g[k + name + "/dx"]) <= tol
     assert err(snp.tanh_forward(g[k + "pool_time/top"]), g[k + "tanh/top"]) <= tol
     assert err(snp.tanh_backward(g[k + "tanh/top"], g[k + "tanh/dtop"]), g[k + "tanh/dx"]) <= tol
+
+
+def test_conv2d_numpy_restatement_matches_the_reference_fixtures():
+    """oracle/conv2d_np.py against tests/golden/conv2d_golden.npz (the reference's ConvolutionLayer compiled in place)."""
+    import os
+    from oracle import conv2d_np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "conv2d_golden.npz"))
+    cases = sorted({k.rsplit("/", 1)[0] for k in g.files})
+    assert len(cases) == 4
+    for c in cases:
+        x, W, b = g[c + "/x"], g[c + "/W"], g[c + "/b"]
+        tol = 2e-5 if x.dtype == np.float32 else 1e-12
+        y = conv2d_np.conv2d_forward(x, W, b)
+        assert np.abs(y - g[c + "/top"]).max() <= tol * np.abs(g[c + "/top"]).max()
+        dW = np.full_like(W, 0.25); db = np.full_like(b, 0.25)
+        dW, db, dx = conv2d_np.conv2d_backward(x, W, g[c + "/dtop"], dW, db)
+        for got, name in ((dW, "dW"), (db, "db"), (dx, "dx")):
+            ref = g[c + "/" + name]
+            assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (c, name)

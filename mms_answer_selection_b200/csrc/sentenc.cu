@@ -472,6 +472,20 @@ __global__ void pool_forward_kernel(const T* __restrict__ x, T* __restrict__ top
   }
 }
 
+// AVE pooling whose windows tile the plane exactly (kernel == stride, no padding, H % kh == 0, W % kw == 0 -- the
+// 4 x 4 / stride 4 pooling of the CNN over the similarity tensor): every input element belongs to one window, so the
+// gradient is a broadcast of dtop / (kh kw); 32-bit index arithmetic, one pass at HBM speed.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_ave_tiled_backward_kernel(const T* __restrict__ dtop, T* __restrict__ dx, unsigned total, unsigned H, unsigned W,
+                               unsigned PW, unsigned kh, unsigned kw, T inv) {
+  const unsigned PHW = (H / kh) * PW;
+  for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += gridDim.x * 256u) {
+    const unsigned w = e % W, r = e / W, h = r % H, nc = r / H;
+    dx[e] = dtop[nc * PHW + (h / kh) * PW + w / kw] * inv;
+  }
+}
+
 template <typename T>
 __global__ void pool_backward_kernel(const T* __restrict__ dtop, const int* __restrict__ mask, T* __restrict__ dx,
                                      long long total, int H, int W, int PH, int PW, int kh, int kw, int sh, int sw, int ph_,
@@ -630,6 +644,14 @@ int mms_pool_backward_impl(mms_context* ctx, const T* dtop, const int* mask, T* 
     MMS_LAUNCH_CHECK();
     return 0;
   }
+  if (method == 1 && pad_h == 0 && pad_w == 0 && kh == sh && kw == sw && H % kh == 0 && W % kw == 0 && PH == H / kh &&
+      PW == W / kw && total < 0xffffffffLL) {
+    MmsKernelScope ks_(ctx, "pool_ave_tiled_backward_kernel");
+    pool_ave_tiled_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(
+        dtop, dx, (unsigned)total, (unsigned)H, (unsigned)W, (unsigned)PW, (unsigned)kh, (unsigned)kw, T(1) / T(kh * kw));
+    MMS_LAUNCH_CHECK();
+    return 0;
+  }
   { MmsKernelScope ks_(ctx, "pool_backward_kernel");
     pool_backward_kernel<T><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dtop, mask, dx, total, H, W, PH, PW, kh, kw, sh,
                                                                         sw, pad_h, pad_w, method); }
@@ -698,6 +720,36 @@ __global__ void bn_channel_sums_kernel(const T* __restrict__ p, const T* __restr
     const int nw = blockDim.x >> 5;
     s0 = threadIdx.x < nw ? red[0][threadIdx.x] : 0.0;
     s1 = threadIdx.x < nw ? red[1][threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (threadIdx.x == 0) { atomicAdd(acc + c, s0); atomicAdd(acc + C + c, s1); }
+  }
+}
+
+// Large planes (HW >= 256: the 36 x 36 planes of the CNN over the similarity tensor): one CTA per (channel, slice of the
+// samples) streams whole planes -- HW contiguous elements -- with no index division in the loop; partial sums in the
+// blob's type per thread (a few hundred values), double across threads and CTAs.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+bn_channel_sums_planes_kernel(const T* __restrict__ p, const T* __restrict__ q, double* __restrict__ acc, int N, int C, int HW,
+                              int slices) {
+  const int c = blockIdx.x / slices, slice = blockIdx.x - c * slices;
+  T t0 = T(0), t1 = T(0);
+  for (int n = slice; n < N; n += slices) {
+    const size_t base = ((size_t)n * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const T a = p[base + i];
+      t0 += a;
+      t1 += MODE == 0 ? a * a : a * q[base + i];
+    }
+  }
+  double s0 = (double)t0, s1 = (double)t1;
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s0 = threadIdx.x < 8 ? red[0][threadIdx.x] : 0.0;
+    s1 = threadIdx.x < 8 ? red[1][threadIdx.x] : 0.0;
     for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
     if (threadIdx.x == 0) { atomicAdd(acc + c, s0); atomicAdd(acc + C + c, s1); }
   }
@@ -906,6 +958,13 @@ int bn_channel_sums(mms_context* ctx, const T* p, const T* q, double* acc, int N
     { MmsKernelScope ks_(ctx, "bn_channel_sums_rows_kernel");
       bn_channel_sums_rows_kernel<T, MODE><<<mms_min(N, ctx->sm_count * 4), threads, per * sizeof(T), ctx->stream>>>(
           p, q, acc, N, C, HW); }
+    MMS_LAUNCH_CHECK();
+    return 0;
+  }
+  if (HW >= 256) {
+    const int slices = (int)mms_max<long long>(1, mms_min<long long>(N, (8LL * ctx->sm_count + C - 1) / C));
+    { MmsKernelScope ks_(ctx, "bn_channel_sums_planes_kernel");
+      bn_channel_sums_planes_kernel<T, MODE><<<C * slices, 256, 0, ctx->stream>>>(p, q, acc, N, C, HW, slices); }
     MMS_LAUNCH_CHECK();
     return 0;
   }

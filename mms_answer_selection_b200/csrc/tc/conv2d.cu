@@ -10,14 +10,14 @@
 // small table), rounded to TF32 on the way, in the canonical 128-byte-swizzled K-major UMMA layout:
 //
 //   forward  Y[(n,oy,ox)][o] = sum_k A[(n,oy,ox)][k] Wm[o][k] + b[o]     A gathered from x,  k = (c,ky,kx)   M = N*OH*OW
-//   dx       dX[(n,y,x)][c]  = sum_k G[(n,y,x)][k]  Wt[c][k]             G gathered from dY with (y-ky, x-kx) and zero
-//                                                                         padding, k = (o,ky,kx), Wt = weights re-laid out
+//   dx       Zt_n[k][p] = sum_o Wm[o][k] dY[n][o][p]  (one batched GEMM, operands in place), then col2im in gather
+//            form: dX[n][c][y][x] = sum_(ky,kx) Zt_n[(c,ky,kx)][(y-ky, x-kx)]  -- what the reference does per sample
 //   dW       dW[o][k]       += sum_(n,p) dY[n][o][p] A[(n,p)][k]         the reduction runs over positions: dY is the
 //                                                                         K-major A operand as it lies in memory, the
 //                                                                         gathered matrix is the B operand; images are
 //                                                                         split over CTAs, red.global.add into dW
 // One persistent kernel (warps 0-3 epilogue, warp 4 MMA issue, warps 5-12 operand staging; mbarrier ring; double-
-// buffered TMEM accumulator), three modes.  The outputs leave in NCHW directly from the accumulator rows (a warp's 32
+// buffered TMEM accumulator), two modes.  The outputs leave in NCHW directly from the accumulator rows (a warp's 32
 // lanes are 32 consecutive positions of one channel plane: 128 contiguous bytes per store).
 #include "../mms_common.cuh"
 #include "tc_gemm.cuh"
@@ -36,7 +36,7 @@ constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps) * 32;
 constexpr int kMaxStages = 6;
 constexpr int kMaxKc = 2048;            // entries of the k-offset table
 
-enum { kFwd = 0, kDx = 1, kDw = 2 };
+enum { kFwd = 0, kDw = 2 };
 
 struct ConvArgs {
   const float* src;        // gathered tensor: x (fwd, dW) or dY (dx): (Nimg, Cs, Hs, Ws)
@@ -89,7 +89,6 @@ conv2d_kernel(const ConvArgs g) {
   const int stage_bytes = 16384 + b_bytes;
   Smem* sm = reinterpret_cast<Smem*>(ring + g.stages * stage_bytes);
   int* koff = reinterpret_cast<int*>(sm + 1);              // g(k): offset of gathered column k
-  int* kyx = koff + g.Kc;                                  // (ky << 16) | kx, for the zero padding of dx
 
   const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
   const int plane_g = g.Hg * g.Wg;
@@ -98,7 +97,6 @@ conv2d_kernel(const ConvArgs g) {
   for (int k = threadIdx.x; k < g.Kc; k += kThreads) {
     const int c = k / (g.kh * g.kw), r = k - c * g.kh * g.kw, ky = r / g.kw, kx = r - ky * g.kw;
     koff[k] = c * g.Hs * g.Ws + g.sgn * (ky * g.Ws + kx);
-    kyx[k] = (ky << 16) | kx;
   }
   if (warp == kEpiWarps) {
     if (lane == 0) {
@@ -124,41 +122,32 @@ conv2d_kernel(const ConvArgs g) {
     int it = 0;
     for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const Tile tl = decode(g, t, MODE, sps);
-      // per-tile row geometry of the gathered operand
-      long long gbase[8]; int gy[8], gx[8]; bool gok[8];
+      // per-tile row geometry of the gathered operand: a loader thread owns ONE row (position) of the tile and half of
+      // the stage's k columns, so that the 32 lanes of a warp read 32 consecutive positions of one (c, ky, kx) plane --
+      // one 128-byte line per load instruction
+      const int grow = tid & 127, ghalf = tid >> 7;
+      long long gbase = 0; bool gok = false;
       if (MODE != kDw) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const long long m = tl.m0 + r0 + 32 * j;
-          gok[j] = m < g.Mtot;
-          const long long n = gok[j] ? m / plane_g : 0;
-          const int p = gok[j] ? (int)(m - n * plane_g) : 0;
-          gy[j] = p / g.Wg; gx[j] = p - gy[j] * g.Wg;
-          gbase[j] = n * src_img + (long long)gy[j] * g.Ws + gx[j];
-        }
+        const long long m = tl.m0 + grow;
+        gok = m < g.Mtot;
+        const long long n = gok ? m / plane_g : 0;
+        const int p = gok ? (int)(m - n * plane_g) : 0;
+        const int gy = p / g.Wg, gx = p - gy * g.Wg;
+        gbase = n * src_img + (long long)gy * g.Ws + gx;
       }
       for (int i = 0; i < tl.nk; ++i, ++it) {
         const int s = it % g.stages;
         float4 va[4], vb[8];
         if (MODE != kDw) {
           const int k0 = i * kBK + c4 * 4;
-          // gathered A: rows = positions, 4 consecutive gathered columns per chunk
-          int ko[4], kq[4];
+          // gathered A: 4 chunks of 4 consecutive gathered columns for this thread's row
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { const int k = k0 + e; ko[e] = k < g.Kc ? koff[k] : 0; kq[e] = k < g.Kc ? kyx[k] : -1; }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int cc = 0; cc < 4; ++cc) {
+            const int kc = i * kBK + (ghalf * 4 + cc) * 4;
             float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              bool ok = gok[j] && kq[e] >= 0;
-              if (MODE == kDx && ok) {
-                const int yy = gy[j] - (kq[e] >> 16), xx = gx[j] - (kq[e] & 0xffff);
-                ok = yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws;
-              }
-              v[e] = ok ? __ldg(g.src + gbase[j] + ko[e]) : 0.f;
-            }
-            va[j] = make_float4(v[0], v[1], v[2], v[3]);
+            for (int e = 0; e < 4; ++e) v[e] = (gok && kc + e < g.Kc) ? __ldg(g.src + gbase + koff[kc + e]) : 0.f;
+            va[cc] = make_float4(v[0], v[1], v[2], v[3]);
           }
           // dense B: weight matrix rows (output columns), 4 consecutive k
           const int nb = g.BN / 32 + ((g.BN & 31) ? 1 : 0);
@@ -223,7 +212,8 @@ conv2d_kernel(const ConvArgs g) {
         for (int j = 0; j < 4; ++j) {
           float4 o = va[j];
           o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
-          *reinterpret_cast<float4*>(a_dst + soff0 + j * 4096) = o;
+          if (MODE != kDw) *reinterpret_cast<float4*>(a_dst + swz128(grow, ghalf * 4 + j)) = o;   // row `grow`, chunk ghalf*4+j
+          else *reinterpret_cast<float4*>(a_dst + soff0 + j * 4096) = o;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -322,15 +312,6 @@ conv2d_kernel(const ConvArgs g) {
   if (warp == kEpiWarps) tmem_dealloc(tmem, g.tmem_cols);
 }
 
-// weights (Co, C, kh, kw) -> Wt[c][(o, ky, kx)]: the dense operand of the dx contraction
-__global__ void conv_wt_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Co, int C, int khw) {
-  const int total = Co * C * khw;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int o = e / (C * khw), r = e - o * C * khw, c = r / khw, t = r - c * khw;
-    Wt[(size_t)c * Co * khw + o * khw + t] = W[e];
-  }
-}
-
 // dbias[o] += sum over (n, p) of dY[n][o][p]   (gemv against the ones vector in the reference, base_conv_layer.cpp:312-316)
 template <typename T>
 __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const T* __restrict__ dy, T* __restrict__ db, int N, int Co, int P) {
@@ -348,6 +329,26 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const T* __restrict
     __syncthreads();
   }
   if (threadIdx.x == 0) atomicAdd(db + o, s[0]);
+}
+
+// col2im_cpu (im2col.cpp:60-90) in gather form: dx[n][c][y][x] = sum over (ky, kx) of Zt[n][(c, ky, kx)][(y - ky, x - kx)]
+// where that position exists; every element of Zt is read exactly once, consecutive x read consecutive addresses.
+__global__ void __launch_bounds__(256)
+conv_col2im_kernel(const float* __restrict__ Zt, float* __restrict__ dx, long long total, int C, int H, int Wd, int kh, int kw,
+                   int OH, int OW) {
+  const int P = OH * OW, khw = kh * kw;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const int x = (int)(e % Wd); long long r = e / Wd;
+    const int y = (int)(r % H); r /= H;
+    const int c = (int)(r % C); const long long n = r / C;
+    const float* z = Zt + ((size_t)n * C + c) * khw * P;
+    float acc = 0.f;
+    const int ky0 = max(0, y - OH + 1), ky1 = min(kh - 1, y);
+    const int kx0 = max(0, x - OW + 1), kx1 = min(kw - 1, x);
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) acc += __ldg(z + (size_t)(ky * kw + kx) * P + (y - ky) * OW + (x - kx));
+    dx[e] = acc;
+  }
 }
 
 // ---- SIMT forms (double blobs, MMS_MATH_FP32, shapes outside the tensor-core kernel): direct sums
@@ -425,13 +426,11 @@ int launch_tc(mms_context* ctx, ConvArgs& g, int mode) {
   static bool configured = false;
   if (!configured) {
     MMS_MAX_SMEM(conv2d_kernel<kFwd>, 201 * 1024);
-    MMS_MAX_SMEM(conv2d_kernel<kDx>, 201 * 1024);
     MMS_MAX_SMEM(conv2d_kernel<kDw>, 201 * 1024);
     configured = true;
   }
   const unsigned grid = (unsigned)mms_min<long long>(g.total_tiles, ctx->sm_count);
   if (mode == kFwd) { MmsKernelScope ks_(ctx, "conv2d_fwd_kernel"); conv2d_kernel<kFwd><<<grid, kThreads, smem, ctx->stream>>>(g); }
-  else if (mode == kDx) { MmsKernelScope ks_(ctx, "conv2d_dx_kernel"); conv2d_kernel<kDx><<<grid, kThreads, smem, ctx->stream>>>(g); }
   else { MmsKernelScope ks_(ctx, "conv2d_dw_kernel"); conv2d_kernel<kDw><<<grid, kThreads, smem, ctx->stream>>>(g); }
   MMS_LAUNCH_CHECK();
   return 0;
@@ -508,23 +507,30 @@ int mms_conv2d_backward_impl(mms_context* ctx, const T* x, const T* W, const T* 
   }
   if (dx) {
     if (tc) {
+      // backward_cpu_gemm + col2im of the reference (base_conv_layer.cpp:289-298), batched: Zt_n [Kc x P] = Wm^T dY_n as
+      // ONE batched TF32 GEMM over the images (both operands read in place, MN-major), then a gather-form col2im in
+      // which consecutive threads read consecutive positions of one row of Zt.  (The contraction as an implicit GEMM
+      // over (o, ky, kx) with C_in output columns re-reads every dY value kh*kw times for a handful of columns: 20 ms
+      // at 4096 x 32 x 36 x 36 -> 4 x 40 x 40 against ~1 ms this way.)
+      const int Kc = C * kh * kw;
+      const long long per_img = (long long)Kc * P;
+      long long chunk = mms_max<long long>(1, (long long)(ctx->scratch_cap / sizeof(float)) / per_img);
+      chunk = mms_min<long long>(chunk, N);
       void* sp = nullptr;
-      MMS_TRY(mms_scratch(ctx, sizeof(float) * (size_t)C * Co * kh * kw, &sp));
-      float* Wt = static_cast<float*>(sp);
-      { MmsKernelScope ks_(ctx, "conv2d_wt_kernel");
-        conv_wt_kernel<<<mms_ceil_div((long long)C * Co * kh * kw, 256), 256, 0, ctx->stream>>>(
-            reinterpret_cast<const float*>(W), Wt, Co, C, kh * kw); }
-      MMS_LAUNCH_CHECK();
-      ConvArgs g = {};
-      g.src = reinterpret_cast<const float*>(dtop); g.Cs = Co; g.Hs = OH; g.Ws = OW; g.Hg = H; g.Wg = Wd; g.sgn = -1;
-      g.kh = kh; g.kw = kw; g.Kc = Co * kh * kw; g.Nimg = N;
-      g.dense = Wt; g.Ncols = C;
-      g.out = reinterpret_cast<float*>(dx); g.bias = nullptr;
-      g.BN = mms_ceil_div(C, 16) * 16; g.n_tiles = 1; g.isplit = 1;
-      g.Mtot = (long long)N * H * Wd;
-      MMS_REQUIRE(mms_ceil_div(g.Mtot, kBM) <= 0x7fffffff, MMS_E_UNSUPPORTED, "too many rows");
-      g.total_tiles = (unsigned)mms_ceil_div(g.Mtot, kBM);
-      MMS_TRY(launch_tc(ctx, g, kDx));
+      MMS_TRY(mms_scratch(ctx, sizeof(float) * (size_t)(chunk * per_img), &sp));
+      float* Zt = static_cast<float*>(sp);
+      for (long long n0 = 0; n0 < N; n0 += chunk) {
+        const int nc = (int)mms_min<long long>(chunk, N - n0);
+        TcGemmArgs t = tc_gemm_args(reinterpret_cast<const float*>(W), Kc, 1,
+                                    reinterpret_cast<const float*>(dtop) + (size_t)n0 * Co * P, P, 1, Zt, P, Kc, P, Co);
+        t.nb1 = nc; t.sA1 = 0; t.sB1 = (long long)Co * P; t.sC1 = per_img;
+        MMS_TRY(mms_tc_gemm(ctx, t));
+        const long long total = (long long)nc * C * H * Wd;
+        { MmsKernelScope ks_(ctx, "conv2d_col2im_kernel");
+          conv_col2im_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(
+              Zt, reinterpret_cast<float*>(dx) + (size_t)n0 * C * H * Wd, total, C, H, Wd, kh, kw, OH, OW); }
+        MMS_LAUNCH_CHECK();
+      }
     } else {
       const long long total = (long long)N * C * H * Wd;
       MmsKernelScope ks_(ctx, "conv2d_dx_simt");

@@ -189,3 +189,44 @@ def test_simcnn_net_vs_chained_oracles():
             blob.data[ix] = w0
             fd = (lp - lm) / (2 * h)
             assert abs(fd - float(grad[ix])) <= 0.05 * max(abs(fd), abs(float(grad[ix]))) + 2e-3, (ix, fd, float(grad[ix]))
+
+
+def test_bn_and_tiled_ave_pool_at_the_cnn_geometry():
+    """The fork's BN on 36 x 36 planes (plane-streaming statistics kernel) and AVE 4 x 4 / stride 4 pooling (tiled fast
+    path) against the numpy restatements pinned to the reference's own layers (oracle/sentenc_np.py)."""
+    rng = np.random.default_rng(12)
+    N, C, H, W = 9, 32, 36, 36
+    x = (rng.normal(0.3, 1.5, (N, C, H, W)) * rng.uniform(0.5, 2, (1, C, 1, 1))).astype(np.float32)
+    bn = mms.BNLayer(mms.LayerParameter("BN", bn_param=dict(scale_filler=dict(type="constant", value=1.0),
+                                                              shift_filler=dict(type="constant", value=1e-3))))
+    bx, bt = mms.Blob(x.shape), mms.Blob(())
+    bx.set_cpu_data(x)
+    bn.SetUp([bx], [bt])
+    scale = rng.uniform(0.5, 1.5, (1, C, 1, 1)).astype(np.float32); shift = rng.uniform(-0.2, 0.2, (1, C, 1, 1)).astype(np.float32)
+    bn.blobs[0].set_cpu_data(scale); bn.blobs[1].set_cpu_data(shift)
+    bn.Forward([bx], [bt])
+    top, xn, std, rm, rv = sentenc_np.bn_forward(x.astype(np.float64), scale.astype(np.float64), shift.astype(np.float64),
+                                                 np.zeros(C), np.zeros(C))
+    assert scaled_err(bt.cpu_data(), top) <= 1e-4
+    assert scaled_err(bn.blobs[2].cpu_data().reshape(-1), rm) <= 1e-5 and scaled_err(bn.blobs[3].cpu_data().reshape(-1), rv) <= 1e-4
+    dy = rng.normal(0, 1, x.shape).astype(np.float32)
+    bt.set_cpu_diff(dy)
+    bn.Backward([bt], [True], [bx])
+    dscale, dshift, dx = sentenc_np.bn_backward(dy.astype(np.float64), xn, scale.astype(np.float64), std)
+    assert scaled_err(bn.blobs[0].cpu_diff().reshape(-1), dscale) <= 1e-4
+    assert scaled_err(bn.blobs[1].cpu_diff().reshape(-1), dshift) <= 1e-4
+    assert scaled_err(bx.cpu_diff(), dx) <= 1e-4
+    for dtype in (np.float32, np.float64):
+        pool = mms.PoolingLayer(mms.LayerParameter("Pooling", dtype=dtype, pooling_param=dict(
+            pool="AVE", kernel_h=4, kernel_w=4, stride_h=4, stride_w=4)))
+        px, pt = mms.Blob(x.shape, dtype=dtype), mms.Blob((), dtype=dtype)
+        px.set_cpu_data(x.astype(dtype))
+        pool.SetUp([px], [pt])
+        pool.Forward([px], [pt])
+        ref, _ = sentenc_np.pool_forward(x.astype(np.float64), 4, 4, 4, 4, method="AVE")
+        assert pt.shape == (N, C, 9, 9) and scaled_err(pt.cpu_data(), ref) <= (1e-6 if dtype == np.float32 else 1e-14)
+        g = rng.normal(0, 1, ref.shape).astype(dtype)
+        pt.set_cpu_diff(g)
+        pool.Backward([pt], [True], [px])
+        dref = sentenc_np.pool_backward(g.astype(np.float64), None, x.shape, 4, 4, 4, 4, method="AVE")
+        assert scaled_err(px.cpu_diff(), dref) <= (1e-6 if dtype == np.float32 else 1e-14)

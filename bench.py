@@ -841,6 +841,15 @@ def extras(world, rank, flush, args):
                                                  "conv_gemm_only_tflops", "hbm_gbs")}
     out["sentence_encoder"]["kernels_ms_per_step"] = {k: v["ms_per_step"] for k, v in r["kernels"].items()}
     torch.cuda.empty_cache()
+    # ---- the net the reference actually trains, up to Flatten: Embed x2 -> SimCross -> Dropout ->
+    #      (Conv5x5 + BN -> AvePool -> TanH) x 2, forward + backward (tools/simcnn_bench.py)
+    import tools.simcnn_bench as simcnn_bench
+    r = simcnn_bench.run(N=c3["N"], iters=3)
+    top = dict(list(r["kernels_ms_per_step"].items())[:12])
+    out["sim_cnn_step"] = {"workload": r["workload"], "ms_per_step": r["ms_per_step"], "qa_pairs_per_sec": r["qa_pairs_per_sec"],
+                           "kernel_ms_sum": r["kernel_ms_sum"], "conv_algorithmic_gflop_per_step": r["conv_algorithmic_gflop_per_step"],
+                           "largest_kernels_ms_per_step": top}
+    torch.cuda.empty_cache()
     # ---- the whole sentence-vector variant as one net (north_star's path end to end): Embed x2 -> sentence encoder x2
     #      (shared parameters) -> SimMatrix -> PairRankLoss, forward + backward into W, the filters, BN and the table
     Ns = c3["N"]

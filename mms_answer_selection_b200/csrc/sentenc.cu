@@ -480,6 +480,18 @@ __global__ void __launch_bounds__(256)
 pool_ave_tiled_backward_kernel(const T* __restrict__ dtop, T* __restrict__ dx, unsigned total, unsigned H, unsigned W,
                                unsigned PW, unsigned kh, unsigned kw, T inv) {
   const unsigned PHW = (H / kh) * PW;
+  if ((W & 3u) == 0 && sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {   // four outputs of one row per thread
+    const unsigned W4 = W >> 2, total4 = total >> 2;
+    for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total4; e += gridDim.x * 256u) {
+      const unsigned w0 = (e % W4) << 2, r = e / W4, h = r % H, nc = r / H;
+      const T* g = dtop + nc * PHW + (h / kh) * PW;
+      float4 o;
+      o.x = (float)(g[w0 / kw] * inv); o.y = (float)(g[(w0 + 1) / kw] * inv);
+      o.z = (float)(g[(w0 + 2) / kw] * inv); o.w = (float)(g[(w0 + 3) / kw] * inv);
+      __stcs(reinterpret_cast<float4*>(dx) + e, o);
+    }
+    return;
+  }
   for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += gridDim.x * 256u) {
     const unsigned w = e % W, r = e / W, h = r % H, nc = r / H;
     dx[e] = dtop[nc * PHW + (h / kh) * PW + w / kw] * inv;

@@ -317,9 +317,17 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const T* __restrict__ dy, T* __restrict__ db, int N, int Co, int P) {
   const int o = blockIdx.x;
   T acc = T(0);
+  const bool vec = sizeof(T) == 4 && (P & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
   for (int n = blockIdx.y; n < N; n += gridDim.y) {
     const T* p = dy + ((size_t)n * Co + o) * P;
-    for (int i = threadIdx.x; i < P; i += 256) acc += p[i];
+    if (vec) {
+      for (int i = threadIdx.x; i < (P >> 2); i += 256) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p) + i);
+        acc += (T)((v.x + v.y) + (v.z + v.w));
+      }
+    } else {
+      for (int i = threadIdx.x; i < P; i += 256) acc += p[i];
+    }
   }
   __shared__ T s[256];
   s[threadIdx.x] = acc;
@@ -329,6 +337,343 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const T* __restrict
     __syncthreads();
   }
   if (threadIdx.x == 0) atomicAdd(db + o, s[0]);
+}
+
+// ---- image-resident variant -------------------------------------------------------------------------------------
+// The planes the CNN convolves are small (4 x 40 x 40 and 32 x 9 x 9 floats per sample: 25.6 and 10.4 KB), so a CTA
+// loads each sample ONCE into shared memory (coalesced 16-byte loads, rounded to TF32 on the way: once per value instead
+// of once per use) and gathers the kh*kw-fold redundant operand tiles from there -- no global-memory latency inside the
+// stage loop, which is what bounded the global-gather kernel above (~3500 cycles per 20 KB stage).  The next sample's
+// loads are in flight (registers) while the current one is being consumed.  forward keeps the whole weight matrix in
+// shared memory in UMMA layout when it fits (conv0: 16 KB); dW streams dY with the loads of four stages in flight.
+constexpr int kImgRegs = 7;             // float4 registers per loader thread for the next sample (<= 28 KB per sample)
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv2d_img_kernel(const ConvArgs g, const int img_floats, const int b_resident, const int tiles_per_img) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int sps_k = (g.Kc + kBK - 1) / kBK;
+  const int b_bytes = g.BN * 128;
+  const int stage_bytes = 16384 + ((MODE == kFwd && b_resident) ? 0 : b_bytes);
+  uint8_t* bres = ring + g.stages * stage_bytes;                          // forward: resident weight blocks
+  const int bres_bytes = (MODE == kFwd && b_resident) ? sps_k * b_bytes : 0;
+  float* img = reinterpret_cast<float*>(bres + bres_bytes);               // the current sample, TF32-rounded
+  Smem* sm = reinterpret_cast<Smem*>(reinterpret_cast<uint8_t*>(img) + ((img_floats * 4 + 127) & ~127));
+  int* koff = reinterpret_cast<int*>(sm + 1);
+  int* ptab = koff + g.Kc;                                 // offset of grid position p inside a source plane
+
+  const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
+  const int plane_g = g.Hg * g.Wg;
+  const int sps = MODE == kDw ? (plane_g + kBK - 1) / kBK : sps_k;
+  for (int k = threadIdx.x; k < g.Kc; k += kThreads) {
+    const int c = k / (g.kh * g.kw), r = k - c * g.kh * g.kw, ky = r / g.kw, kx = r - ky * g.kw;
+    koff[k] = c * g.Hs * g.Ws + ky * g.Ws + kx;
+  }
+  for (int p = threadIdx.x; p < plane_g; p += kThreads) ptab[p] = (p / g.Wg) * g.Ws + p % g.Wg;
+  if (warp == kEpiWarps) {
+    if (lane == 0) {
+      for (int s = 0; s < g.stages; ++s) { mbar_init(&sm->full[s], kLoadWarps); mbar_init(&sm->empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], kEpiWarps); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm->tmem_base, g.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  // the samples of this CTA: forward: n = blockIdx.x, += gridDim.x;  dW: the slice [img0, img1) of its split
+  int n_first, n_step, n_end, n0_tile = 0;
+  if (MODE == kFwd) { n_first = blockIdx.x; n_step = gridDim.x; n_end = g.Nimg; }
+  else {
+    const int nt = blockIdx.x % g.n_tiles, sp = blockIdx.x / g.n_tiles;
+    const int per = (g.Nimg + g.isplit - 1) / g.isplit;
+    n_first = min(g.Nimg, sp * per); n_end = min(g.Nimg, n_first + per); n_step = 1; n0_tile = nt * g.BN;
+  }
+
+  if (warp > kEpiWarps) {
+    // ------------------------------------------------------------ operand staging
+    const int tid = threadIdx.x - (kEpiWarps + 1) * 32;
+    const int r0 = tid >> 3, c4 = tid & 7;
+    const uint32_t soff0 = swz128(r0, c4);
+    const int grow = tid & 127, ghalf = tid >> 7;
+    const int nv = img_floats >> 2;                        // float4 per sample
+    float4 pre[kImgRegs];
+    auto fetch = [&](int n) {                              // the sample's loads, all in flight at once
+      const float4* src = reinterpret_cast<const float4*>(g.src + (long long)n * img_floats);
+#pragma unroll
+      for (int j = 0; j < kImgRegs; ++j) {
+        const int v = tid + j * kLoadThreads;
+        if (v < nv) pre[j] = __ldg(src + v);
+      }
+    };
+    auto park = [&]() {                                    // registers -> shared memory, rounded once
+#pragma unroll
+      for (int j = 0; j < kImgRegs; ++j) {
+        const int v = tid + j * kLoadThreads;
+        if (v < nv) {
+          float4 o = pre[j];
+          o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
+          reinterpret_cast<float4*>(img)[v] = o;
+        }
+      }
+    };
+    if (MODE == kFwd && b_resident) {                      // weight matrix -> UMMA K-major blocks, once
+      for (int i = 0; i < sps_k; ++i) {
+        const int k0 = i * kBK + c4 * 4;
+        for (int j = 0; j * 32 + r0 < g.BN; ++j) {
+          const int row = r0 + 32 * j;
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < g.Ncols) {
+            const float* p = g.dense + (long long)row * g.Kc + k0;
+            if (k0 < g.Kc) o.x = to_tf32(__ldg(p));
+            if (k0 + 1 < g.Kc) o.y = to_tf32(__ldg(p + 1));
+            if (k0 + 2 < g.Kc) o.z = to_tf32(__ldg(p + 2));
+            if (k0 + 3 < g.Kc) o.w = to_tf32(__ldg(p + 3));
+          }
+          *reinterpret_cast<float4*>(bres + i * b_bytes + soff0 + j * 4096) = o;
+        }
+      }
+    }
+    int it = 0;
+    if (n_first < n_end) fetch(n_first);
+    for (int n = n_first; n < n_end; n += n_step) {
+      // every loader has finished gathering from the previous sample before it is overwritten
+      asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads));
+      park();
+      asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads));
+      if (n + n_step < n_end) fetch(n + n_step);           // in flight while this sample is consumed
+      if (MODE == kFwd) {
+        for (int mt = 0; mt < tiles_per_img; ++mt) {
+          const int p = mt * kBM + grow;
+          const bool gok = p < plane_g;
+          const float* rowp = img + (gok ? ptab[p] : 0);
+          for (int i = 0; i < sps; ++i, ++it) {
+            const int s = it % g.stages;
+            float4 va[4], vb[8];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const int kc = i * kBK + (ghalf * 4 + cc) * 4;
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int ko = (kc + e < g.Kc) ? koff[kc + e] : -1;       // uniform over the warp: a broadcast read
+                v[e] = (gok && ko >= 0) ? rowp[ko] : 0.f;
+              }
+              va[cc] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            if (!b_resident) {
+              const int k0 = i * kBK + c4 * 4;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int row = r0 + 32 * j;
+                if (row < g.BN && row < g.Ncols) {
+                  const float* pw = g.dense + (long long)row * g.Kc + k0;
+                  if (k0 + 3 < g.Kc && (g.Kc & 3) == 0) vb[j] = __ldg(reinterpret_cast<const float4*>(pw));
+                  else {
+                    if (k0 < g.Kc) vb[j].x = __ldg(pw);
+                    if (k0 + 1 < g.Kc) vb[j].y = __ldg(pw + 1);
+                    if (k0 + 2 < g.Kc) vb[j].z = __ldg(pw + 2);
+                    if (k0 + 3 < g.Kc) vb[j].w = __ldg(pw + 3);
+                  }
+                }
+              }
+            }
+            if (it >= g.stages) mbar_wait(&sm->empty[s], ((it / g.stages) - 1) & 1);
+            uint8_t* a_dst = ring + s * stage_bytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(a_dst + swz128(grow, ghalf * 4 + j)) = va[j];
+            if (!b_resident) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (r0 + 32 * j < g.BN) {
+                  float4 o = vb[j];
+                  o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
+                  *reinterpret_cast<float4*>(a_dst + 16384 + soff0 + j * 4096) = o;
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->full[s]);
+          }
+        }
+      } else {
+        // dW: stages = 32-position blocks of this sample; dY loads of four stages in flight
+        const float* dy = g.dense + (long long)n * g.Co * plane_g;
+        for (int ib = 0; ib < sps; ib += 4) {
+          float4 va4[4][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int p0 = (ib + q) * kBK + c4 * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              va4[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int o = r0 + 32 * j;
+              if (ib + q < sps && o < g.Co) {
+                const float* p = dy + (long long)o * plane_g + p0;
+                if (p0 + 3 < plane_g && (plane_g & 3) == 0) va4[q][j] = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                  if (p0 < plane_g) va4[q][j].x = __ldg(p);
+                  if (p0 + 1 < plane_g) va4[q][j].y = __ldg(p + 1);
+                  if (p0 + 2 < plane_g) va4[q][j].z = __ldg(p + 2);
+                  if (p0 + 3 < plane_g) va4[q][j].w = __ldg(p + 3);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (ib + q >= sps) break;
+            const int s = it % g.stages;
+            const int p0 = (ib + q) * kBK + c4 * 4;
+            int po[4]; bool pok[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int p = p0 + e;
+              pok[e] = p < plane_g;
+              po[e] = pok[e] ? ptab[p] : 0;
+            }
+            float4 vb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int kk = n0_tile + r0 + 32 * j;
+              if (r0 + 32 * j < g.BN && kk < g.Kc) {
+                const float* base = img + koff[kk];
+                if (pok[0]) vb[j].x = base[po[0]];
+                if (pok[1]) vb[j].y = base[po[1]];
+                if (pok[2]) vb[j].z = base[po[2]];
+                if (pok[3]) vb[j].w = base[po[3]];
+              }
+            }
+            if (it >= g.stages) mbar_wait(&sm->empty[s], ((it / g.stages) - 1) & 1);
+            uint8_t* a_dst = ring + s * stage_bytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 o = va4[q][j];
+              o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
+              *reinterpret_cast<float4*>(a_dst + soff0 + j * 4096) = o;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (r0 + 32 * j < g.BN) *reinterpret_cast<float4*>(a_dst + 16384 + soff0 + j * 4096) = vb[j];
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->full[s]);
+            ++it;
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // ------------------------------------------------------------ MMA issue
+    const uint32_t idesc = idesc_tf32(kBM, g.BN, false, false);
+    int it = 0, tcount = 0;
+    // (the resident weight blocks are written by the loader warps before their first arrive on full[0], behind the
+    // same proxy fence as the stage itself: waiting for a stage also covers them)
+    if (MODE == kFwd) {
+      for (int n = n_first; n < n_end; n += n_step) {
+        for (int mt = 0; mt < tiles_per_img; ++mt, ++tcount) {
+          const int buf = tcount & 1;
+          if (tcount >= 2) mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) - 1) & 1);
+          tc_fence_after();
+          const uint32_t acc = tmem + buf * g.BN;
+          for (int i = 0; i < sps; ++i, ++it) {
+            const int s = it % g.stages;
+            mbar_wait(&sm->full[s], (it / g.stages) & 1);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(ring + s * stage_bytes);
+            const uint32_t b_base = b_resident ? smem_u32(bres + i * b_bytes) : a_base + 16384;
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ks = 0; ks < kBK / 8; ++ks)
+                mma_tf32_ss(acc, desc_kmajor(a_base + ks * 32), desc_kmajor(b_base + ks * 32), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+              mma_commit(&sm->empty[s]);
+              if (i == sps - 1) mma_commit(&sm->acc_full[buf]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else {
+      const int nk = (n_end - n_first) * sps;
+      const uint32_t acc = tmem;
+      for (int i = 0; i < nk; ++i, ++it) {
+        const int s = it % g.stages;
+        mbar_wait(&sm->full[s], (it / g.stages) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(ring + s * stage_bytes);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int ks = 0; ks < kBK / 8; ++ks)
+            mma_tf32_ss(acc, desc_kmajor(a_base + ks * 32), desc_kmajor(a_base + 16384 + ks * 32), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          mma_commit(&sm->empty[s]);
+          if (i == nk - 1) mma_commit(&sm->acc_full[0]);
+        }
+        __syncwarp();
+      }
+      if (nk == 0) {
+        if (elect_one_sync()) mma_commit(&sm->acc_full[0]);
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int rl = warp * 32 + lane;
+    if (MODE == kFwd) {
+      int tcount = 0;
+      for (int n = n_first; n < n_end; n += n_step) {
+        for (int mt = 0; mt < tiles_per_img; ++mt, ++tcount) {
+          const int buf = tcount & 1;
+          mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1);
+          tc_fence_after();
+          const uint32_t acc = tmem + buf * g.BN + ((uint32_t)(warp * 32) << 16);
+          const int p = mt * kBM + rl;
+          const bool ok = p < plane_g;
+          float* orow = g.out + (long long)n * g.Ncols * plane_g + p;
+          for (int c0 = 0; c0 < g.BN; c0 += 32) {
+            float v[32];
+            if (c0 + 16 < g.BN) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+            if (!ok) continue;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int o = c0 + i;
+              if (o < g.Ncols && o < g.BN) orow[(long long)o * plane_g] = v[i] + (g.bias ? __ldg(g.bias + o) : 0.f);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm->acc_empty[buf]);
+        }
+      }
+    } else {
+      const int nk = (n_end - n_first) * sps;
+      mbar_wait(&sm->acc_full[0], 0);
+      tc_fence_after();
+      const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16);
+      const int ncols = min(g.BN, g.Kc - n0_tile);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        float v[32];
+        if (nk > 0) {
+          if (c0 + 16 < g.BN) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+        }
+        if (rl >= g.Co || nk == 0) continue;
+        float* wrow = g.out + (long long)rl * g.Kc + n0_tile + c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < ncols) atomicAdd(wrow + i, v[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc(tmem, g.tmem_cols);
 }
 
 // col2im_cpu (im2col.cpp:60-90) in gather form: dx[n][c][y][x] = sum over (ky, kx) of Zt[n][(c, ky, kx)][(y - ky, x - kx)]
@@ -436,6 +781,45 @@ int launch_tc(mms_context* ctx, ConvArgs& g, int mode) {
   return 0;
 }
 
+// The image-resident kernel when a sample fits its registers / shared memory; else the global-gather kernel.
+int launch_conv(mms_context* ctx, ConvArgs& g, int mode) {
+  const long long img_floats = (long long)g.Cs * g.Hs * g.Ws;
+  const int plane = g.Hg * g.Wg;
+  // per-sample tiles (forward) / stages (dW) must be reasonably full: a 5 x 5 output plane would use 25 of 128 rows
+  const bool img_ok = img_floats % 4 == 0 && img_floats <= (long long)kImgRegs * kLoadThreads * 4 &&
+                      (reinterpret_cast<uintptr_t>(g.src) & 15) == 0 && plane >= 4 * kBM;
+  if (!img_ok) return launch_tc(ctx, g, mode);
+  const int sps_k = mms_ceil_div(g.Kc, kBK);
+  const int b_bytes = g.BN * 128;
+  const int b_resident = mode == kFwd && (size_t)sps_k * b_bytes <= 48 * 1024;
+  const size_t fixed = (size_t)(b_resident ? sps_k * b_bytes : 0) + (((size_t)img_floats * 4 + 127) & ~(size_t)127) + sizeof(Smem) +
+                       sizeof(int) * ((size_t)g.Kc + plane) + 1024;
+  const int stage_bytes = 16384 + (b_resident ? 0 : b_bytes);
+  int stages = kMaxStages;
+  while (stages > 2 && (size_t)stages * stage_bytes + fixed > 200 * 1024) --stages;
+  if ((size_t)stages * stage_bytes + fixed > 200 * 1024) return launch_tc(ctx, g, mode);
+  g.stages = stages;
+  g.tmem_cols = umma::tmem_cols_pow2(2 * g.BN);
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  static bool configured = false;
+  if (!configured) {
+    MMS_MAX_SMEM(conv2d_img_kernel<kFwd>, 201 * 1024);
+    MMS_MAX_SMEM(conv2d_img_kernel<kDw>, 201 * 1024);
+    configured = true;
+  }
+  const int tiles_per_img = mms_ceil_div(plane, kBM);
+  if (mode == kFwd) {
+    const unsigned grid = (unsigned)mms_min(g.Nimg, ctx->sm_count);
+    MmsKernelScope ks_(ctx, "conv2d_fwd_kernel");
+    conv2d_img_kernel<kFwd><<<grid, kThreads, smem, ctx->stream>>>(g, (int)img_floats, b_resident, tiles_per_img);
+  } else {
+    MmsKernelScope ks_(ctx, "conv2d_dw_kernel");
+    conv2d_img_kernel<kDw><<<g.total_tiles, kThreads, smem, ctx->stream>>>(g, (int)img_floats, 0, tiles_per_img);
+  }
+  MMS_LAUNCH_CHECK();
+  return 0;
+}
+
 bool tc_shape_ok(int C, int Co, int kh, int kw) {
   return C * kh * kw <= kMaxKc && Co * kh * kw <= kMaxKc && Co <= 128 && C <= 256;
 }
@@ -463,7 +847,7 @@ int mms_conv2d_forward_impl(mms_context* ctx, const T* x, const T* W, const T* b
     g.Mtot = (long long)N * OH * OW;
     MMS_REQUIRE(mms_ceil_div(g.Mtot, kBM) <= 0x7fffffff, MMS_E_UNSUPPORTED, "too many rows");
     g.total_tiles = (unsigned)mms_ceil_div(g.Mtot, kBM);
-    return launch_tc(ctx, g, kFwd);
+    return launch_conv(ctx, g, kFwd);
   }
   const long long total = (long long)N * Co * OH * OW;
   { MmsKernelScope ks_(ctx, "conv2d_fwd_simt");
@@ -498,7 +882,7 @@ int mms_conv2d_backward_impl(mms_context* ctx, const T* x, const T* W, const T* 
       g.n_tiles = mms_ceil_div(g.Kc, g.BN);
       g.isplit = mms_max(1, mms_min(N, ctx->sm_count / g.n_tiles));
       g.total_tiles = (unsigned)(g.n_tiles * g.isplit);
-      MMS_TRY(launch_tc(ctx, g, kDw));
+      MMS_TRY(launch_conv(ctx, g, kDw));
     } else {
       MmsKernelScope ks_(ctx, "conv2d_dw_simt");
       conv_dw_simt<T><<<Co * C * kh * kw, 256, 0, ctx->stream>>>(x, dtop, dW, N, C, H, Wd, Co, kh, kw, OH, OW);

@@ -127,8 +127,9 @@ def test_conv_without_bias_and_partial_propagation():
     bottom.diff.fill_(7.0)
     lay.Backward([top], [False], [bottom])                    # propagate_down false: the bottom diff is left alone
     assert np.all(bottom.cpu_diff() == 7.0)
-    with pytest.raises(mms.layers.CheckError, match="only the sentence convolution"):
-        bad = mms.create_layer(mms.LayerParameter("Convolution", convolution_param=dict(num_output=3, kernel_size=5)))
+    # strided / padded / grouped convolutions are the stock layer's business
+    with pytest.raises(mms.layers.CheckError, match="only stride 1, pad 0, group 1"):
+        bad = mms.create_layer(mms.LayerParameter("Convolution", convolution_param=dict(num_output=3, kernel_size=5, stride=2)))
         bad.SetUp([blob(np.zeros((2, 4, 9, 9), np.float32), np.float32)], [mms.Blob(())])
 
 

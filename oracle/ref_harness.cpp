@@ -47,6 +47,7 @@ template class PairRankLossLayer<double>;
 // harness then drives the PRODUCT's drop-in layers (mms_answer_selection_b200/caffe_layers/) through
 // the reference's Layer API in Caffe::GPU mode -- see dropin_runtime.cpp.
 #include <cuda_runtime.h>
+#include "mms_grad_exchange.hpp"
 #endif
 
 namespace {
@@ -338,5 +339,64 @@ int mmsref_time(void* h, int iters, int do_backward, const int* propagate_down, 
     });
   });
 }
+
+#ifdef MMS_DROPIN
+// The C++ gradient-exchange glue (caffe_layers/mms_grad_exchange.cpp) with `world` solver replicas on the CURRENT device
+// (virtual ranks): every replica owns `nblobs` reference Blobs with the given counts; their data / diff are filled from
+// data_in / diff_in ([world][sum of counts], host), the blobs are re-bound by GradExchange, on_start and
+// on_gradients_ready (or the fused AdaDelta form when fused != 0) run on one stream per replica, and the replicas'
+// blob contents -- read back through the reference's own Blob::cpu_data() / cpu_diff() -- land in data_out / diff_out.
+int mmsref_grad_exchange_run(int world, int nblobs, const int* counts, const float* data_in, const float* diff_in, int fused,
+                             float* data_out, float* diff_out) {
+  return guarded(nullptr, [&]() {
+    caffe::Caffe::set_mode(caffe::Caffe::GPU);
+    long long total = 0;
+    for (int i = 0; i < nblobs; ++i) total += counts[i];
+    std::vector<std::vector<shared_ptr<Blob<float> > > > own(world);
+    std::vector<caffe::mms::GradExchange<float>*> ex(world);
+    std::vector<cudaStream_t> streams(world);
+    for (int r = 0; r < world; ++r) {
+      std::vector<Blob<float>*> params;
+      long long off = 0;
+      for (int i = 0; i < nblobs; ++i) {
+        shared_ptr<Blob<float> > b(new Blob<float>(std::vector<int>(1, counts[i])));
+        memcpy(b->mutable_cpu_data(), data_in + r * total + off, sizeof(float) * counts[i]);
+        memcpy(b->mutable_cpu_diff(), diff_in + r * total + off, sizeof(float) * counts[i]);
+        b->gpu_data(); b->gpu_diff();                       // device copies exist before the re-binding
+        own[r].push_back(b); params.push_back(b.get());
+        off += counts[i];
+      }
+      ex[r] = new caffe::mms::GradExchange<float>(params, r, world);
+      // the diffs were on the host: write them into the re-bound device buffers
+      off = 0;
+      for (int i = 0; i < nblobs; ++i) {
+        CUDA_CHECK(cudaMemcpy(own[r][i]->mutable_gpu_diff(), diff_in + r * total + off, sizeof(float) * counts[i], cudaMemcpyHostToDevice));
+        off += counts[i];
+      }
+      CUDA_CHECK(cudaStreamCreateWithFlags(&streams[r], cudaStreamNonBlocking));
+      MMS_CAFFE_CHECK(mms_exchange_set_option(ex[r]->handle(), MMS_EXCHANGE_OPT_CTAS, 8));
+    }
+    caffe::mms::GradExchange<float>::Attach(ex);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    for (int r = 0; r < world; ++r) ex[r]->on_start(streams[r], false);
+    for (int r = 0; r < world; ++r) MMS_CAFFE_CHECK(mms_exchange_check(ex[r]->handle(), streams[r]));
+    std::vector<float> lr(nblobs, 1.f), dec(nblobs, 1.f);
+    for (int r = 0; r < world; ++r) {
+      if (fused) ex[r]->on_gradients_ready_adadelta(lr, dec, 1.f, 0.95f, 5e-7f, 5e-4f, 1, streams[r], false);
+      else ex[r]->on_gradients_ready(streams[r], false);
+    }
+    for (int r = 0; r < world; ++r) MMS_CAFFE_CHECK(mms_exchange_check(ex[r]->handle(), streams[r]));
+    for (int r = 0; r < world; ++r) {
+      long long off = 0;
+      for (int i = 0; i < nblobs; ++i) {
+        memcpy(data_out + r * total + off, own[r][i]->cpu_data(), sizeof(float) * counts[i]);
+        memcpy(diff_out + r * total + off, own[r][i]->cpu_diff(), sizeof(float) * counts[i]);
+        off += counts[i];
+      }
+    }
+    for (int r = 0; r < world; ++r) { own[r].clear(); delete ex[r]; cudaStreamDestroy(streams[r]); }
+  });
+}
+#endif
 
 }  // extern "C"

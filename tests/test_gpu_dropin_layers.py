@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import scaled_err
-from oracle import refbind
+from oracle import cport, refbind
 
 needs_dropin = pytest.mark.skipif(not (refbind.dropin_available() and refbind.ref_available()),
                                   reason="oracle/_ref/libmms_{ref,dropin}.so not built (needs /root/reference at build time)")
@@ -252,3 +252,41 @@ def test_dropin_registers_the_reference_layer_types_and_refuses_cpu_mode():
                 layer.forward()
     finally:
         refbind.dropin_lib().mmsref_set_mode(1)
+
+
+@needs_dropin
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,fused", [(2, 0), (4, 0), (4, 1)])
+def test_cpp_grad_exchange_glue(world, fused):
+    """caffe_layers/mms_grad_exchange.cpp -- the C++ body of P2PSync's Params re-binding (parallel.cpp:60-115), on_start
+    (:287-322) and on_gradients_ready (:325-380) -- with `world` solver replicas of reference Blobs on one device:
+    after on_start every replica holds rank 0's weights; after on_gradients_ready every replica's diff is the mean of
+    the replicas' gradients (fixed rank order: bit-exact); the fused form leaves identical updated weights everywhere
+    and zeroed gradients.  Everything is read back through the reference's own Blob::cpu_data / cpu_diff."""
+    import ctypes
+    L = refbind.dropin_lib()
+    counts = np.array([60 * 5, 5, 2 * 5 * 5, 18], dtype=np.int32)          # W, b, M, B (B ragged: padded to 16 bytes inside)
+    total = int(counts.sum())
+    rng = np.random.default_rng(world + fused)
+    data = rng.uniform(-1, 1, (world, total)).astype(np.float32)
+    diff = rng.normal(0, 1e-2, (world, total)).astype(np.float32)
+    out_d, out_g = np.empty_like(data), np.empty_like(diff)
+    L.mmsref_grad_exchange_run.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 2
+    rc = L.mmsref_grad_exchange_run(world, len(counts), counts.ctypes.data, data.ctypes.data, diff.ctypes.data, fused,
+                                    out_d.ctypes.data, out_g.ctypes.data)
+    assert rc == 0, L.mmsref_last_error()
+    acc = diff[0].copy()
+    for r in range(1, world):
+        acc = acc + diff[r]                                              # float adds in rank order, as the kernel does
+    for r in range(world):
+        np.testing.assert_array_equal(out_d[r], out_d[0])               # replicas identical
+        if not fused:
+            np.testing.assert_array_equal(out_d[r], data[0])            # on_start: rank 0's weights everywhere
+            np.testing.assert_array_equal(out_g[r], acc * np.float32(1.0 / world))
+        else:
+            assert not out_g[r].any()                                   # ClearParamDiffs folded in
+    if fused:
+        w, g = data[0].copy(), acc.copy()
+        cport.adadelta_step(w, g, np.zeros_like(w), np.zeros_like(w), grad_scale=1.0 / world, local_decay=5e-4, momentum=0.95,
+                            delta=5e-7, local_rate=1.0)
+        assert scaled_err(out_d[0], w) <= 2e-6

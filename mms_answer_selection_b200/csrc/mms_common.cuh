@@ -60,6 +60,7 @@ struct mms_context {
   struct SimMatCache {
     bool valid = false;
     const void *q = nullptr, *W = nullptr;
+    const void* T = nullptr;                   // where the forward left T = q W (the reference: bottom[1]'s diff)
     int N = 0, K1 = 0, K2 = 0;
     unsigned long long generation = 0;
   } simmat_cache;

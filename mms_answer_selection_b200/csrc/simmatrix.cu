@@ -25,10 +25,9 @@ __global__ void rowdot_kernel(const T* __restrict__ a, const T* __restrict__ Tm,
   }
 }
 
-// out[n,c] = ds[n] * in[n,c]
+// out[n,c] = ds[n] * in[n,c]   (out may be in: no __restrict__ on the pair)
 template <typename T>
-__global__ void rowscale_kernel(const T* __restrict__ in, const T* __restrict__ ds, T* __restrict__ out,
-                                long long total, int K) {
+__global__ void rowscale_kernel(const T* in, const T* __restrict__ ds, T* out, long long total, int K) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x)
     out[e] = ds[e / K] * in[e];
@@ -88,6 +87,7 @@ inline int tc_forward(mms_context* ctx, const float* q, const float* W, float* T
   MMS_TRY(mms_tc_gemm(ctx, g));
   ctx->simmat_cache.valid = true; ctx->simmat_cache.generation = mms_write_clock(); ctx->simmat_cache.q = q; ctx->simmat_cache.W = W;
   ctx->simmat_cache.N = N; ctx->simmat_cache.K1 = K1; ctx->simmat_cache.K2 = K2;
+  ctx->simmat_cache.T = Tm;
   return 0;
 }
 inline int tc_forward(mms_context*, const double*, const double*, double*, int, int, int) { return MMS_E_UNSUPPORTED; }
@@ -132,6 +132,17 @@ inline int tc_backward(mms_context* ctx, const float* q, const float* a, const f
     g.operands_tf32 = 1;
     g.out_rowscale = ds;
     MMS_TRY(mms_tc_gemm(ctx, g));
+  }
+  // The forward parked T = q W where the reference parks it: in bottom[1]'s diff (sim_matrix_layer.cpp:58), which is
+  // the very buffer da is written to.  With MMS_OPT_REUSE_FORWARD and T untouched since, da_n = ds_n W^T q_n = ds_n T_n
+  // (:88-90) is a row scaling of that buffer in place -- 2 N K2 floats of traffic instead of a fourth N x K2 x K1 GEMM.
+  if (da && cached && ctx->simmat_cache.T == da &&
+      mms_unchanged_since(ctx->simmat_cache.generation, da, sizeof(float) * (size_t)N * K2)) {
+    { MmsKernelScope ks_(ctx, "rowscale_kernel");
+      rowscale_kernel<float><<<ew_grid(ctx, (long long)N * K2), 256, 0, ctx->stream>>>(da, ds, da, (long long)N * K2, K2); }
+    MMS_LAUNCH_CHECK();
+    ctx->simmat_cache.T = nullptr;            // T is gone: a second backward recomputes
+    return 0;
   }
   if (da) {   // da = diag(ds) (q W)
     TcGemmArgs g = tc_gemm_args(qr, K1p, 0, Wr, K2p, 1, da, K2, N, K2, K1);

@@ -92,7 +92,7 @@ __device__ __forceinline__ int scale_exp(float maxabs, long long len) {
   while ((1LL << lg) < len) ++lg;
   return 61 - lg - (ilogbf(maxabs) + 1);
 }
-__device__ __forceinline__ long long to_fixed(double x, int e) { return __double2ll_rn(scalbn(x, e)); }
+__device__ __forceinline__ long long to_fixed(double x, double scale) { return __double2ll_rn(x * scale); }   // scale = 2^e: exact
 __device__ __forceinline__ double from_fixed(long long v, int e) { return scalbn((double)v, -e); }
 
 template <typename T> struct Ld16;
@@ -134,6 +134,7 @@ det_reduce_kernel(const T* __restrict__ dtop, T* __restrict__ dW, const DetArgs 
     const int id = a.skeys[rs];
     const float rm = __uint_as_float(a.runmax[r]);
     const int er = rm > 0.f ? scale_exp(rm, re - rs) : 0;
+    const double sr = scalbn(1.0, er), sg = scalbn(1.0, eg);      // the two power-of-two scales, once per chunk
     long long acc[VPL][VN], bacc[VPL][VN];
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
@@ -156,11 +157,11 @@ det_reduce_kernel(const T* __restrict__ dtop, T* __restrict__ dW, const DetArgs 
         const T* e1 = reinterpret_cast<const T*>(&x1[v]);
 #pragma unroll
         for (int c = 0; c < VN; ++c) {
-          acc[v][c] += to_fixed((double)e0[c], er);
-          if (want_bias) bacc[v][c] += to_fixed((double)e0[c], eg);
+          acc[v][c] += to_fixed((double)e0[c], sr);
+          if (want_bias) bacc[v][c] += to_fixed((double)e0[c], sg);
           if (two) {
-            acc[v][c] += to_fixed((double)e1[c], er);
-            if (want_bias) bacc[v][c] += to_fixed((double)e1[c], eg);
+            acc[v][c] += to_fixed((double)e1[c], sr);
+            if (want_bias) bacc[v][c] += to_fixed((double)e1[c], sg);
           }
         }
       }

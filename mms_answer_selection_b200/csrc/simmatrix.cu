@@ -28,6 +28,16 @@ __global__ void rowdot_kernel(const T* __restrict__ a, const T* __restrict__ Tm,
 // out[n,c] = ds[n] * in[n,c]   (out may be in: no __restrict__ on the pair)
 template <typename T>
 __global__ void rowscale_kernel(const T* in, const T* __restrict__ ds, T* out, long long total, int K) {
+  if (sizeof(T) == 4 && (K & 3) == 0 && total < 0x7fffffffLL && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const unsigned K4 = (unsigned)K >> 2, n4 = (unsigned)(total >> 2);            // 16-byte groups, 32-bit index arithmetic
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += gridDim.x * blockDim.x) {
+      const float s = (float)ds[e / K4];
+      float4 v = reinterpret_cast<const float4*>(in)[e];
+      v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+      reinterpret_cast<float4*>(out)[e] = v;
+    }
+    return;
+  }
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x)
     out[e] = ds[e / K] * in[e];

@@ -12,6 +12,7 @@
 // After the first slab almost nothing survives the threshold, so a slab row costs one read of its scores (which are
 // still in L2: mms_rerank_topk sizes the score slab to stay there) and at most one small sort.
 #include <math_constants.h>
+#include <stdint.h>
 
 #include "mms_common.cuh"
 #include "tc/tc_gemm.cuh"
@@ -66,28 +67,65 @@ topk_update_kernel(const float* __restrict__ scores, const long long* __restrict
   __syncthreads();
   float ts = sc[k - 1];
   long long ti = ix[k - 1];
-  const int sub = CAP - k >= 1024 ? 1024 : (CAP - k) / kTopkThreads * kTopkThreads;   // scores scanned between checks
-  for (int c0 = 0; c0 < n; c0 += sub) {
-    const int c1 = min(n, c0 + sub);
-    for (int c = c0 + threadIdx.x; c < c1; c += kTopkThreads) {
-      const float s = __ldcg(row + c);                   // read through L2: the GEMM of this slab has just written it
-      const long long gi = irow ? irow[c] : idx_base + c;
-      if (s == s && gi >= 0 && better(s, gi, ts, ti)) {
-        const int pos = atomicAdd(&cnt, 1);              // < CAP: at most `sub` appends since the last cut
-        sc[pos] = s; ix[pos] = gi;
+  __shared__ int overflow[2];                            // alternating: chunk i resets / reads flag i & 1
+  // cut: sort everything appended so far and keep the k best (called by all threads)
+  auto cut = [&](int have) {
+    for (int t = have + threadIdx.x; t < CAP; t += kTopkThreads) { sc[t] = -CUDART_INF_F; ix[t] = 0x7fffffffffffffffLL; }
+    bitonic_sort<CAP>(sc, ix);
+    if (threadIdx.x == 0) cnt = k;
+    __syncthreads();
+    ts = sc[k - 1]; ti = ix[k - 1];
+  };
+  constexpr int U = 8;                                   // scores per thread and chunk: U loads in flight (L2 latency)
+  int chunk = 0;
+  for (int c0 = 0; c0 < n; c0 += U * kTopkThreads, ++chunk) {
+    int* ovf = &overflow[chunk & 1];
+    float v[U]; long long gi[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int c = c0 + j * kTopkThreads + threadIdx.x;
+      v[j] = c < n ? __ldcg(row + c) : CUDART_NAN_F;     // read through L2: the GEMM of this slab has just written it
+      gi[j] = c < n ? (irow ? irow[c] : idx_base + c) : -1;
+    }
+    const int have0 = cnt;                               // (all threads passed a barrier since cnt last changed)
+    if (threadIdx.x == 0) *ovf = 0;
+    __syncthreads();
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < U; ++j) mine += (v[j] == v[j] && gi[j] >= 0 && better(v[j], gi[j], ts, ti)) ? 1 : 0;
+    if (mine) {
+      int pos = atomicAdd(&cnt, mine);
+      if (pos + mine <= CAP) {
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (v[j] == v[j] && gi[j] >= 0 && better(v[j], gi[j], ts, ti)) { sc[pos] = v[j]; ix[pos] = gi[j]; ++pos; }
+      } else {
+        *ovf = 1;
       }
     }
     __syncthreads();
-    const int have = cnt;
-    const bool last = c1 >= n;
-    if (have > k && (last || have + sub > CAP)) {
-      for (int t = have + threadIdx.x; t < CAP; t += kTopkThreads) { sc[t] = -CUDART_INF_F; ix[t] = 0x7fffffffffffffffLL; }
-      bitonic_sort<CAP>(sc, ix);
-      if (threadIdx.x == 0) cnt = k;
+    if (*ovf) {
+      // too many survivors for the array (an unfilled list, or scores that keep rising): discard this chunk's appends,
+      // cut, and feed the chunk 256 scores at a time -- at most 256 appends between cuts always fit (CAP - k >= 256)
       __syncthreads();
-      ts = sc[k - 1]; ti = ix[k - 1];
+      if (threadIdx.x == 0) cnt = have0;
+      __syncthreads();
+      if (have0 > k) cut(have0);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (v[j] == v[j] && gi[j] >= 0 && better(v[j], gi[j], ts, ti)) {
+          const int pos = atomicAdd(&cnt, 1);
+          sc[pos] = v[j]; ix[pos] = gi[j];
+        }
+        __syncthreads();
+        const int have = cnt;
+        if (have + kTopkThreads > CAP) cut(have);
+        else __syncthreads();
+      }
     }
   }
+  __syncthreads();
+  if (cnt > k) cut(cnt);
   for (int t = threadIdx.x; t < k; t += kTopkThreads) {
     run_s[(size_t)q * k + t] = sc[t];
     run_i[(size_t)q * k + t] = ix[t];
@@ -136,8 +174,13 @@ int mms_rerank_topk_impl(mms_context* ctx, const float* Q, const float* C, const
   MMS_REQUIRE(ctx->math == MMS_MATH_TF32, MMS_E_UNSUPPORTED, "top-k reranking runs on the tensor-core path");
   const long long K1p = tc_pad4(K1), K2p = tc_pad4(K2);
   // score slab: ~48 MB so that it stays in the 126 MB L2 between the GEMM that writes it and the scan that reads it
-  long long slab = (48LL << 20) / (4LL * Nq);
-  slab = mms_max<long long>(2048, mms_min<long long>(slab / 256 * 256, Nc));
+  // ... and so that the slab's GEMM is a whole number of waves of the 74 CTA pairs (256 x 256 tiles): 1000 queries
+  // -> 4 row tiles x 74 column tiles = 4 waves per slab of 18 944 candidates (74 MB of scores)
+  const long long m_tiles = mms_ceil_div(Nq, 256), pairs = mms_max(1, ctx->sm_count / 2);
+  long long slab = (72LL << 20) / (4LL * Nq) / 256;                     // column tiles that fit ~72 MB
+  const long long per_wave = mms_max<long long>(1, pairs / m_tiles);    // column tiles per wave set
+  slab = mms_max<long long>(per_wave, slab / per_wave * per_wave) * 256;
+  slab = mms_max<long long>(2048, mms_min<long long>(slab, Nc));
   const size_t fixed = (size_t)Nq * K1p + (size_t)K1 * K2p + (size_t)Nq * K2p + (size_t)Nq * slab;
   const bool pipelined = !prepared && ctx->concurrency != 0 && slab < Nc;
   const size_t cbuf = prepared ? 0 : (size_t)slab * K2p * (pipelined ? 2 : 1);

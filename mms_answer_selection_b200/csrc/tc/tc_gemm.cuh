@@ -24,6 +24,12 @@ struct TcGemmArgs {
   int operands_tf32;                         // 1: A and B already hold TF32-exact values (rounded by a previous
                                              //    kernel) -> they may be fetched by TMA without a register pass
   int round_out;                             // 1: round the stored result to TF32 (it feeds another contraction)
+  // Threshold epilogue (per-query top-k of candidate scores, tc/../topk.cu): when flt_s != null C is NOT written;
+  // acc[m][n] is compared with row m's current k-th list entry (flt_s / flt_i at [m*flt_k + flt_k-1]; order: value
+  // descending, index ascending, index = flt_base + n) and survivors are appended to row m's candidate buffer
+  // (cand_s / cand_i [m*cand_cap + pos], pos = atomicAdd(cand_n + m, 1); counts beyond cand_cap mean "overflowed").
+  const float* flt_s; const long long* flt_i; int flt_k; long long flt_base;
+  float* cand_s; long long* cand_i; int* cand_n; int cand_cap;
 };
 
 inline TcGemmArgs tc_gemm_args(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn,
@@ -37,6 +43,8 @@ inline TcGemmArgs tc_gemm_args(const float* A, long long lda, int a_mn, const fl
   g.a_rowscale = g.b_rowscale = g.out_rowscale = nullptr;
   g.c_add = nullptr; g.ld_add = g.s_add1 = g.s_add2 = 0;
   g.operands_tf32 = 0; g.round_out = 0;
+  g.flt_s = nullptr; g.flt_i = nullptr; g.flt_k = 0; g.flt_base = 0;
+  g.cand_s = nullptr; g.cand_i = nullptr; g.cand_n = nullptr; g.cand_cap = 0;
   return g;
 }
 

@@ -81,6 +81,24 @@ __device__ __forceinline__ Tile decode_tile(const TcGemmArgs& g, const Geometry&
   return tl;
 }
 
+// Threshold epilogue (TcGemmArgs::flt_*): this thread's accumulator row against the row's current k-th list entry.
+__device__ __forceinline__ void epi_filter(const TcGemmArgs& g, const float (&v)[32], int row, int col0, int ncols) {
+  if (row >= g.M) return;
+  const float ts = __ldg(g.flt_s + (size_t)row * g.flt_k + g.flt_k - 1);
+  const long long ti = __ldg(g.flt_i + (size_t)row * g.flt_k + g.flt_k - 1);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float x = v[i];
+    if (i < ncols && x >= ts) {                            // almost never: one compare per value on the common path
+      const long long gi = g.flt_base + col0 + i;
+      if (x > ts || gi < ti) {
+        const int pos = atomicAdd(g.cand_n + row, 1);
+        if (pos < g.cand_cap) { g.cand_s[(size_t)row * g.cand_cap + pos] = x; g.cand_i[(size_t)row * g.cand_cap + pos] = gi; }
+      }
+    }
+  }
+}
+
 // Epilogue store of one 32 x 32 chunk that a warp has staged in shared memory.  Thread (lane) owns the
 // 4 columns cc = 4*(lane%8) of rows r0 + 4*rr, r0 = lane/8: every warp instruction covers 4 whole
 // 128-byte row segments.  MODE is resolved outside the row loop so that the loop body is a handful
@@ -290,6 +308,10 @@ tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
+        if (g.flt_s) {                                         // threshold epilogue: nothing is stored
+          epi_filter(g, v, row_tm, tl.n0 + c0, min(32, ncols - c0));
+          continue;
+        }
         // transpose through shared memory: TMEM hands every thread one ROW (32 columns); global memory
         // wants every warp instruction to cover whole 128-byte row segments
 #pragma unroll
@@ -489,6 +511,10 @@ tc_gemm_tma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (g.flt_s) {                                         // threshold epilogue: nothing is stored
+          epi_filter(g, v, row_tm, tl.n0 + c0, min(32, ncols - c0));
+          continue;
         }
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4)

@@ -124,3 +124,24 @@ def test_multigpu_topk_merge_equals_single_gpu():
     for r in (0, 1):
         np.testing.assert_array_equal(out[r][0], s.cpu().numpy())
         np.testing.assert_array_equal(out[r][1], i.cpu().numpy())
+
+
+def test_topk_fused_epilogue_and_its_overflow_fallback():
+    """Large enough for the threshold-epilogue form (scores never written): lists equal the top of the full score matrix;
+    and an adversarial candidate order -- every query's scores rise with the candidate index, so every new candidate
+    beats the current threshold and the candidate buffers overflow -- still gives the exact lists (stored fallback)."""
+    Nq, Nc, K, k = 24, 120_000, 64, 50
+    Q, C, W = (torch.from_numpy(x).cuda() for x in synth.make_rerank(Nq, Nc, K, seed=11))
+    rr = Reranker(W, k=k)
+    s1, i1 = rr.local_topk(Q, C, idx_base=7)
+    ref_s, ref_i = _reference_topk(_full_scores(Q, C, W), k, base=7)
+    np.testing.assert_array_equal(s1.cpu().numpy(), ref_s); np.testing.assert_array_equal(i1.cpu().numpy(), ref_i)
+    # rising scores: q > 0, W = identity-like positive, candidates scaled by their index
+    Qp = torch.rand((Nq, K), device="cuda") + 0.5
+    Wp = torch.eye(K, device="cuda")
+    ramp = torch.arange(Nc, device="cuda", dtype=torch.float32).reshape(-1, 1) / Nc + 0.1
+    Cp = (torch.ones((Nc, K), device="cuda") * ramp).contiguous()
+    rr2 = Reranker(Wp, k=k)
+    s2, i2 = rr2.local_topk(Qp, Cp)
+    ref_s2, ref_i2 = _reference_topk(_full_scores(Qp, Cp, Wp), k)
+    np.testing.assert_array_equal(s2.cpu().numpy(), ref_s2); np.testing.assert_array_equal(i2.cpu().numpy(), ref_i2)

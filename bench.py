@@ -691,6 +691,9 @@ def multimodal_line(world, rank, flush, exchange_mode):
     exch, note = None, "none"
     if world > 1:
         exch, note = make_exchange(net.params(), exchange_mode)
+        if exch.backend == "p2p":
+            note = "csrc/exchange.cu (%s): one launch for the 16.8 MB of W_m / bias gradients after Backward, inside the graph" % (
+                "multimem.ld_reduce/st over the NVSwitch multicast mapping" if exch.multicast else "peer loads/stores")
     net.capture(exch)
     ms = _time_ms(net.replay, 10, flush, world)
     if exch:

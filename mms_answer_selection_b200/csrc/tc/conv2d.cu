@@ -242,12 +242,15 @@ conv2d_kernel(const ConvArgs g) {
         const int s = it % g.stages;
         mbar_wait(&sm->full[s], (it / g.stages) & 1);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(ring + s * stage_bytes);
-        const uint32_t b_base = a_base + 16384;
+        // descriptors as (low, constant high) halves stepped by immediates: the issue stream of this one warp, not
+        // the tensor pipe, is what a stage of four small MMAs costs
+        const uint32_t a_lo = desc_lo_k(smem_u32(ring + s * stage_bytes));
+        const uint32_t b_lo = a_lo + (16384u >> 4);
         if (elect_one_sync()) {
-#pragma unroll
-          for (int ks = 0; ks < kBK / 8; ++ks)
-            mma_tf32_ss(acc, desc_kmajor(a_base + ks * 32), desc_kmajor(b_base + ks * 32), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32_ss_lh(acc, a_lo, kDescHiK, b_lo, kDescHiK, idesc, i > 0 ? 1u : 0u);
+          mma_tf32_ss_lh(acc, a_lo + 1 * kDescStepK, kDescHiK, b_lo + 1 * kDescStepK, kDescHiK, idesc, 1u);
+          mma_tf32_ss_lh(acc, a_lo + 2 * kDescStepK, kDescHiK, b_lo + 2 * kDescStepK, kDescHiK, idesc, 1u);
+          mma_tf32_ss_lh(acc, a_lo + 3 * kDescStepK, kDescHiK, b_lo + 3 * kDescStepK, kDescHiK, idesc, 1u);
           mma_commit(&sm->empty[s]);
           if (i == tl.nk - 1) mma_commit(&sm->acc_full[buf]);
         }
@@ -438,15 +441,54 @@ conv2d_img_kernel(const ConvArgs g, const int img_floats, const int b_resident, 
         }
       }
     }
+    const bool fast4 = MODE == kFwd && b_resident && sps == 4;
+    int ko4[4][16];
+    uint32_t sw4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sw4[j] = swz128(grow, ghalf * 4 + j);
+    if (fast4) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int k = i * kBK + ghalf * 16 + e;
+          ko4[i][e] = k < g.Kc ? koff[k] : 0;
+        }
+    }
     int it = 0;
-    if (n_first < n_end) fetch(n_first);
+    if (!fast4 && n_first < n_end) fetch(n_first);
     for (int n = n_first; n < n_end; n += n_step) {
       // every loader has finished gathering from the previous sample before it is overwritten
       asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads));
-      park();
+      if (fast4) fetch(n);                                 // (the register-resident offsets leave no room for a prefetch:
+      park();                                              //  one exposed load latency per sample, ~3 % of its time)
       asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads));
-      if (n + n_step < n_end) fetch(n + n_step);           // in flight while this sample is consumed
-      if (MODE == kFwd) {
+      if (!fast4 && n + n_step < n_end) fetch(n + n_step); // in flight while this sample is consumed
+      if (MODE == kFwd && fast4) {
+        // 4 k blocks (conv0: K = 100), weights resident: the 64 gather offsets of this thread live in registers and the
+        // loop body is 16 shared-memory loads and 4 stores per stage -- no table look-ups, no predicates (columns past K
+        // meet zero weight rows, rows past the plane are never stored: both read a valid address)
+        for (int mt = 0; mt < tiles_per_img; ++mt) {
+          const int p = mt * kBM + grow;
+          const float* rowp = img + (p < plane_g ? ptab[p] : 0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i, ++it) {
+            const int s = it % g.stages;
+            float4 va[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              va[cc] = make_float4(rowp[ko4[i][cc * 4]], rowp[ko4[i][cc * 4 + 1]], rowp[ko4[i][cc * 4 + 2]], rowp[ko4[i][cc * 4 + 3]]);
+            if (it >= g.stages) mbar_wait(&sm->empty[s], ((it / g.stages) - 1) & 1);
+            uint8_t* a_dst = ring + s * stage_bytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(a_dst + sw4[j]) = va[j];
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->full[s]);
+          }
+        }
+      } else if (MODE == kFwd) {
         for (int mt = 0; mt < tiles_per_img; ++mt) {
           const int p = mt * kBM + grow;
           const bool gok = p < plane_g;
@@ -505,59 +547,63 @@ conv2d_img_kernel(const ConvArgs g, const int img_floats, const int b_resident, 
       } else {
         // dW: stages = 32-position blocks of this sample; dY loads of four stages in flight
         const float* dy = g.dense + (long long)n * g.Co * plane_g;
-        for (int ib = 0; ib < sps; ib += 4) {
-          float4 va4[4][4];
+        int kod[8];                                          // gather offsets of this thread's rows: constant for the kernel
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int kk = n0_tile + r0 + 32 * j; kod[j] = kk < g.Kc ? koff[kk] : 0; }
+        // rows of the dY tile = channels: only ceil(Co / 32) of the 4 row groups exist (rows past Co stay unwritten --
+        // they only feed accumulator rows the epilogue never reads)
+        const int ja = (g.Co + 31) / 32;
+        auto load_group = [&](int ib, float4 (&dst)[4][2]) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int p0 = (ib + q) * kBK + c4 * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              va4[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 2; ++j) {
+              dst[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
               const int o = r0 + 32 * j;
-              if (ib + q < sps && o < g.Co) {
+              if (j < ja && ib + q < sps && o < g.Co) {
                 const float* p = dy + (long long)o * plane_g + p0;
-                if (p0 + 3 < plane_g && (plane_g & 3) == 0) va4[q][j] = __ldg(reinterpret_cast<const float4*>(p));
+                if (p0 + 3 < plane_g && (plane_g & 3) == 0) dst[q][j] = __ldg(reinterpret_cast<const float4*>(p));
                 else {
-                  if (p0 < plane_g) va4[q][j].x = __ldg(p);
-                  if (p0 + 1 < plane_g) va4[q][j].y = __ldg(p + 1);
-                  if (p0 + 2 < plane_g) va4[q][j].z = __ldg(p + 2);
-                  if (p0 + 3 < plane_g) va4[q][j].w = __ldg(p + 3);
+                  if (p0 < plane_g) dst[q][j].x = __ldg(p);
+                  if (p0 + 1 < plane_g) dst[q][j].y = __ldg(p + 1);
+                  if (p0 + 2 < plane_g) dst[q][j].z = __ldg(p + 2);
+                  if (p0 + 3 < plane_g) dst[q][j].w = __ldg(p + 3);
                 }
               }
             }
           }
+        };
+        float4 cur[4][2], nxt[4][2];
+        load_group(0, cur);
+        for (int ib = 0; ib < sps; ib += 4) {
+          if (ib + 4 < sps) load_group(ib + 4, nxt);         // in flight while the current four stages are built
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (ib + q >= sps) break;
             const int s = it % g.stages;
             const int p0 = (ib + q) * kBK + c4 * 4;
-            int po[4]; bool pok[4];
+            // positions past the plane meet zero dY columns and gathered rows past K are never stored: both read offset 0
+            int po[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int p = p0 + e;
-              pok[e] = p < plane_g;
-              po[e] = pok[e] ? ptab[p] : 0;
-            }
+            for (int e = 0; e < 4; ++e) po[e] = (p0 + e < plane_g) ? ptab[p0 + e] : 0;
             float4 vb[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              const int kk = n0_tile + r0 + 32 * j;
-              if (r0 + 32 * j < g.BN && kk < g.Kc) {
-                const float* base = img + koff[kk];
-                if (pok[0]) vb[j].x = base[po[0]];
-                if (pok[1]) vb[j].y = base[po[1]];
-                if (pok[2]) vb[j].z = base[po[2]];
-                if (pok[3]) vb[j].w = base[po[3]];
+              if (r0 + 32 * j < g.BN) {
+                const float* base = img + kod[j];
+                vb[j] = make_float4(base[po[0]], base[po[1]], base[po[2]], base[po[3]]);
               }
             }
             if (it >= g.stages) mbar_wait(&sm->empty[s], ((it / g.stages) - 1) & 1);
             uint8_t* a_dst = ring + s * stage_bytes;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 o = va4[q][j];
-              o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
-              *reinterpret_cast<float4*>(a_dst + soff0 + j * 4096) = o;
+            for (int j = 0; j < 2; ++j) {
+              if (j < ja) {
+                float4 o = cur[q][j];
+                o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
+                *reinterpret_cast<float4*>(a_dst + soff0 + j * 4096) = o;
+              }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -567,12 +613,16 @@ conv2d_img_kernel(const ConvArgs g, const int img_floats, const int b_resident, 
             if (lane == 0) mbar_arrive(&sm->full[s]);
             ++it;
           }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { cur[q][0] = nxt[q][0]; cur[q][1] = nxt[q][1]; }
         }
       }
     }
   } else if (warp == kEpiWarps) {
     // ------------------------------------------------------------ MMA issue
     const uint32_t idesc = idesc_tf32(kBM, g.BN, false, false);
+    const uint32_t ring_lo = desc_lo_k(smem_u32(ring)), stage_lo = (uint32_t)stage_bytes >> 4;
+    const uint32_t bres_lo = desc_lo_k(smem_u32(bres)), b_lo_step = (uint32_t)b_bytes >> 4;
     int it = 0, tcount = 0;
     // (the resident weight blocks are written by the loader warps before their first arrive on full[0], behind the
     // same proxy fence as the stage itself: waiting for a stage also covers them)
@@ -587,12 +637,13 @@ conv2d_img_kernel(const ConvArgs g, const int img_floats, const int b_resident, 
             const int s = it % g.stages;
             mbar_wait(&sm->full[s], (it / g.stages) & 1);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(ring + s * stage_bytes);
-            const uint32_t b_base = b_resident ? smem_u32(bres + i * b_bytes) : a_base + 16384;
+            const uint32_t a_lo = ring_lo + s * stage_lo;
+            const uint32_t b_lo = b_resident ? bres_lo + i * b_lo_step : a_lo + (16384u >> 4);
             if (elect_one_sync()) {
-#pragma unroll
-              for (int ks = 0; ks < kBK / 8; ++ks)
-                mma_tf32_ss(acc, desc_kmajor(a_base + ks * 32), desc_kmajor(b_base + ks * 32), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+              mma_tf32_ss_lh(acc, a_lo, kDescHiK, b_lo, kDescHiK, idesc, i > 0 ? 1u : 0u);
+              mma_tf32_ss_lh(acc, a_lo + 1 * kDescStepK, kDescHiK, b_lo + 1 * kDescStepK, kDescHiK, idesc, 1u);
+              mma_tf32_ss_lh(acc, a_lo + 2 * kDescStepK, kDescHiK, b_lo + 2 * kDescStepK, kDescHiK, idesc, 1u);
+              mma_tf32_ss_lh(acc, a_lo + 3 * kDescStepK, kDescHiK, b_lo + 3 * kDescStepK, kDescHiK, idesc, 1u);
               mma_commit(&sm->empty[s]);
               if (i == sps - 1) mma_commit(&sm->acc_full[buf]);
             }
@@ -607,11 +658,13 @@ conv2d_img_kernel(const ConvArgs g, const int img_floats, const int b_resident, 
         const int s = it % g.stages;
         mbar_wait(&sm->full[s], (it / g.stages) & 1);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(ring + s * stage_bytes);
+        const uint32_t a_lo = ring_lo + s * stage_lo;
+        const uint32_t b_lo = a_lo + (16384u >> 4);
         if (elect_one_sync()) {
-#pragma unroll
-          for (int ks = 0; ks < kBK / 8; ++ks)
-            mma_tf32_ss(acc, desc_kmajor(a_base + ks * 32), desc_kmajor(a_base + 16384 + ks * 32), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32_ss_lh(acc, a_lo, kDescHiK, b_lo, kDescHiK, idesc, i > 0 ? 1u : 0u);
+          mma_tf32_ss_lh(acc, a_lo + 1 * kDescStepK, kDescHiK, b_lo + 1 * kDescStepK, kDescHiK, idesc, 1u);
+          mma_tf32_ss_lh(acc, a_lo + 2 * kDescStepK, kDescHiK, b_lo + 2 * kDescStepK, kDescHiK, idesc, 1u);
+          mma_tf32_ss_lh(acc, a_lo + 3 * kDescStepK, kDescHiK, b_lo + 3 * kDescStepK, kDescHiK, idesc, 1u);
           mma_commit(&sm->empty[s]);
           if (i == nk - 1) mma_commit(&sm->acc_full[0]);
         }
@@ -787,7 +840,8 @@ int launch_conv(mms_context* ctx, ConvArgs& g, int mode) {
   const int plane = g.Hg * g.Wg;
   // per-sample tiles (forward) / stages (dW) must be reasonably full: a 5 x 5 output plane would use 25 of 128 rows
   const bool img_ok = img_floats % 4 == 0 && img_floats <= (long long)kImgRegs * kLoadThreads * 4 &&
-                      (reinterpret_cast<uintptr_t>(g.src) & 15) == 0 && plane >= 4 * kBM;
+                      (reinterpret_cast<uintptr_t>(g.src) & 15) == 0 && plane >= 4 * kBM &&
+                      (mode != kDw || g.Co <= 64);          // the image kernel's dW stages two 32-row groups of dY
   if (!img_ok) return launch_tc(ctx, g, mode);
   const int sps_k = mms_ceil_div(g.Kc, kBK);
   const int b_bytes = g.BN * 128;

@@ -221,7 +221,7 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------- our arm
-def build_net(cfg, world, rank):
+def build_net(cfg, world, rank, keep_embed_tops=False):
     """MMSNet over this rank's slice of the GLOBAL synthetic batch (same seed on every rank: the global batch is
     identical everywhere, rank r takes pairs [r N/n, (r+1) N/n)).  Each worker normalises its loss by ITS pair count, as
     every Caffe worker does: dS of the global batch times `world`; the exchange's 1/n (parallel.cpp:377) turns the
@@ -231,7 +231,9 @@ def build_net(cfg, world, rank):
     N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
     full = synth.make_qa_batch(N=cfg["global_N"], L=L, D=D, mc=mc, V=V, seed=synth.SEED)
     sl = slice(rank * N, (rank + 1) * N)
-    net = mms.MMSNet(N, L, D, mc, V)
+    # keep_embed_tops=False: q / a leave the gather as the TF32 operand copy the contractions read and nothing else
+    # (MMS_OPT_STAGE_ONLY); the fp32 tops a Caffe net would expose are not written -- nothing on this path reads them
+    net = mms.MMSNet(N, L, D, mc, V, keep_embed_tops=keep_embed_tops)
     net.set_params(full["W"], full["b"], full["M"], full["B"])
     net.set_inputs(full["idx_q"][sl], full["idx_a"][sl])
     net.set_upstream_gradient(full["dS"][sl] * world)
@@ -304,7 +306,7 @@ def main_ours(args):
     cfg = workload_config(wl, world)
     N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
 
-    net, full, sl = build_net(cfg, world, rank)
+    net, full, sl = build_net(cfg, world, rank, keep_embed_tops=args.embed_tops == "fp32")
     exch, exch_note = None, "none"
     if world > 1:
         exch, exch_note = make_exchange(net.params(), args.exchange)
@@ -441,6 +443,8 @@ def main_ours(args):
         "config": bench_config(wl, cfg, world),
         "run": {"launch": "step recorded as one CUDA graph (%d kernels of libmms_b200.so per step)" % launches_per_step,
                 "grad_exchange": exch_note,
+                "embed_tops": ("fp32 tops + TF32 operand copy" if net.keep_embed_tops else
+                               "TF32 operand copy only (MMS_OPT_STAGE_ONLY; --embed-tops fp32 also writes the fp32 tops)"),
                 "algorithmic_tflops_per_gpu": N * flops_per_pair(L, D, mc) / (total_ms / args.steps / 1e3) / 1e12},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(host_q.numel() * 4 + host_a.numel() * 4), "d2h_bytes_per_step": 4},
@@ -449,7 +453,7 @@ def main_ours(args):
         "roofline": roof,
         "kernels_ms_per_step": {k: round(ms / prof_steps, 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
         "kernel_step_ms_sum": step_ms_prof,
-        "hbm_kernels": hbm_kernel_table(prof, prof_steps, cfg, peaks),
+        "hbm_kernels": hbm_kernel_table(prof, prof_steps, cfg, peaks, net.keep_embed_tops),
     }
     if tf32:
         line["peaks"] = dict(tf32, bf16_tflops_burst_driver=peaks.get("bf16_tflops"), hbm_gbs_driver=peaks.get("hbm_gbs"))
@@ -914,7 +918,7 @@ def ncu_tensor_pipe(wl, name):
         return None
 
 
-def hbm_kernel_table(prof, steps, cfg, peaks):
+def hbm_kernel_table(prof, steps, cfg, peaks, keep_embed_tops=True):
     """Achieved HBM GB/s of the gather / scatter / reduce kernels of the step against the measured copy bandwidth:
     algorithmic bytes per step / the kernel's summed device time per step."""
     N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
@@ -922,7 +926,8 @@ def hbm_kernel_table(prof, steps, cfg, peaks):
     Dp = (D + 31) // 32 * 32                           # rounded copies: rows padded to 128-byte lines
     alg = {
         # id + table row in, row out, and (MMS_OPT_STAGE_TF32, what MMSNet runs) the rounded operand copy out as well
-        "embed_forward_vec": rows * (4 + 8 * D + 4 * Dp),
+        # (keep_embed_tops=False: the fp32 row is not written)
+        "embed_forward_vec": rows * (4 + (8 if keep_embed_tops else 4) * D + 4 * Dp),
         "embed_backward_runs": rows * (4 + 4 * D) + rows * 8 * D,      # id + dtop in, <= one RMW of the dW row
         "tf32_round_kernel": mc * D * 4 * (D + Dp),                    # only M: q and a arrive staged by the gather
         "sum_kernel": 2 * 4 * N * mc * L * L,                          # loss = dot(S, dS)
@@ -988,6 +993,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-multicast", "nccl"])
     ap.add_argument("--try-multicast", action="store_true", help="comm: also time the symmetric-memory / multimem variant")
+    ap.add_argument("--embed-tops", default="staged", choices=["staged", "fp32"],
+                    help="staged: the gather writes only the TF32 operand copy SimCross reads; fp32: also the fp32 tops")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

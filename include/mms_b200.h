@@ -73,7 +73,7 @@ enum {
                                 mms_sentconv_backward the rounded x, of the last forward on the handle. */
   MMS_OPT_CONCURRENCY = 6,   /* 1 (default): independent contractions inside one call may run on private
                                 streams, joined back before the call's last launch on the handle's stream. */
-  MMS_OPT_STAGE_TF32 = 7     /* Embed forward, float: 1 = the gather also writes the operand copy the tensor-core
+  MMS_OPT_STAGE_TF32 = 7,    /* Embed forward, float: 1 = the gather also writes the operand copy the tensor-core
                                 contractions read (TF32 round-to-nearest, rows padded to 128-byte lines) into a
                                 buffer owned by this handle, and publishes it under the top's address.  A later
                                 mms_simcross_forward / _backward whose q or a IS that top (same pointer, shape) reads
@@ -82,6 +82,14 @@ enum {
                                 dropped when the library itself rewrites the top; a caller that lets a foreign
                                 in-place layer modify the top between this Embed and its consumer must not set the
                                 option (or call mms_invalidate_caches).  Default 0. */
+  MMS_OPT_STAGE_ONLY = 8     /* Embed forward with MMS_OPT_STAGE_TF32: 1 = the staged copy is the ONLY thing written; the
+                                fp32 top keeps its address (it is the key the copy is published under) but its memory is
+                                left untouched, which takes a third off the gather's HBM traffic.  For tops whose only
+                                consumers are mms_simcross_forward / _backward mode 2 on the tensor-core path: those
+                                read the staged copy, and fail with MMS_E_INVALID -- rather than read memory nobody
+                                wrote -- when they cannot (other modes, double, MMS_MATH_FP32, a batch cut into
+                                chunks, a stale copy).  Anything else that reads the top sees whatever the buffer
+                                held before.  Default 0. */
 };
 
 typedef struct mms_context* mms_handle_t;

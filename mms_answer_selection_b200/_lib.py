@@ -12,7 +12,7 @@ c_f, c_d = ctypes.c_float, ctypes.c_double
 
 MMS_MATH_TF32, MMS_MATH_FP32 = 0, 1
 MMS_OPT_MATH, MMS_OPT_PRL_GE, MMS_OPT_SCRATCH_BYTES, MMS_OPT_EMBED_DETERMINISTIC = 1, 2, 3, 4
-MMS_OPT_REUSE_FORWARD, MMS_OPT_CONCURRENCY, MMS_OPT_STAGE_TF32 = 5, 6, 7
+MMS_OPT_REUSE_FORWARD, MMS_OPT_CONCURRENCY, MMS_OPT_STAGE_TF32, MMS_OPT_STAGE_ONLY = 5, 6, 7, 8
 MMS_E_INVALID, MMS_E_UNSUPPORTED, MMS_E_NOMEM, MMS_E_FAULT = -1, -2, -3, -4
 MMS_EXCHANGE_OPT_CTAS, MMS_EXCHANGE_OPT_TIMEOUT_MS, MMS_EXCHANGE_OPT_MULTICAST = 1, 2, 3
 MMS_EXCHANGE_MAX_WORLD, MMS_EXCHANGE_CHANNELS, MMS_EXCHANGE_IPC_BYTES = 8, 4, 64

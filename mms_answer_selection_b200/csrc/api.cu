@@ -85,14 +85,14 @@ int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
 
 #include <unordered_map>
 namespace {
-struct StageEntry { mms_context* owner; const float* staged; long long rows; int cols, ld; unsigned long long clock; };
+struct StageEntry { mms_context* owner; const float* staged; long long rows; int cols, ld; unsigned long long clock; bool virt; };
 std::unordered_map<const void*, StageEntry> g_stage;
 std::mutex g_stage_mu;
 }  // namespace
-void mms_stage_publish(mms_context* owner, const void* src, const float* staged, long long rows, int cols, int ld) {
+void mms_stage_publish(mms_context* owner, const void* src, const float* staged, long long rows, int cols, int ld, bool virt) {
   const unsigned long long clock = mms_write_clock();
   std::lock_guard<std::mutex> lk(g_stage_mu);
-  g_stage[src] = StageEntry{owner, staged, rows, cols, ld, clock};
+  g_stage[src] = StageEntry{owner, staged, rows, cols, ld, clock, virt};
 }
 const float* mms_stage_lookup(const void* src, long long rows, int cols, int ld) {
   StageEntry e;
@@ -104,6 +104,23 @@ const float* mms_stage_lookup(const void* src, long long rows, int cols, int ld)
   }
   if (e.rows != rows || e.cols != cols || e.ld != ld) return nullptr;
   return mms_unchanged_since(e.clock, src, sizeof(float) * (size_t)rows * cols) ? e.staged : nullptr;
+}
+bool mms_stage_virtual(const void* src) {
+  StageEntry e;
+  {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    auto it = g_stage.find(src);
+    if (it == g_stage.end() || !it->second.virt) return false;
+    e = it->second;
+  }
+  // a later write through this library put real data there
+  return mms_unchanged_since(e.clock, src, sizeof(float) * (size_t)e.rows * e.cols);
+}
+int mms_stage_require_real(const void* src, bool have_staged, const char* what) {
+  if (have_staged || !mms_stage_virtual(src)) return 0;
+  mms_set_error("%s was produced with MMS_OPT_STAGE_ONLY (its fp32 values were never written) and this call cannot use the "
+                "staged copy: only mode 2 on the tensor-core path with the whole batch in one chunk can", what);
+  return MMS_E_INVALID;
 }
 void mms_stage_drop_owner(mms_context* owner) {
   std::lock_guard<std::mutex> lk(g_stage_mu);
@@ -255,6 +272,7 @@ int mms_set_option(mms_handle_t h, int option, long long value) {
       h->stage_tf32 = value != 0;
       if (!h->stage_tf32) mms_stage_drop_owner(h);
       return 0;
+    case MMS_OPT_STAGE_ONLY: h->stage_only = value != 0; return 0;
     default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
   }
 }
@@ -282,6 +300,7 @@ int mms_get_option(mms_handle_t h, int option, long long* value) {
     case MMS_OPT_REUSE_FORWARD: *value = h->reuse_forward; return 0;
     case MMS_OPT_CONCURRENCY: *value = h->concurrency; return 0;
     case MMS_OPT_STAGE_TF32: *value = h->stage_tf32; return 0;
+    case MMS_OPT_STAGE_ONLY: *value = h->stage_only; return 0;
     default: mms_set_error("unknown option %d", option); return MMS_E_INVALID;
   }
 }

@@ -136,10 +136,47 @@ __global__ void fm_backward_kernel(const T* __restrict__ x, const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(kRedThreads)
 sum_kernel(const T* __restrict__ x, const T* __restrict__ yv, long long n, T* __restrict__ partials,
-           unsigned int* __restrict__ ticket, T* __restrict__ out) {
+           unsigned int* __restrict__ ticket, T* __restrict__ out, int vec) {
   T acc = T(0);
-  for (long long i = blockIdx.x * (long long)kRedThreads + threadIdx.x; i < n;
-       i += (long long)gridDim.x * kRedThreads)
+  const long long t0 = blockIdx.x * (long long)kRedThreads + threadIdx.x, stride = (long long)gridDim.x * kRedThreads;
+  long long done = 0;
+  if (vec) {      // 16-byte streaming loads, four per operand in flight (the scalar loop reached 0.58 of the HBM peak)
+    constexpr int V = 16 / sizeof(T);
+    typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type VT;
+    const long long nv = n / V;
+    const VT* xv = reinterpret_cast<const VT*>(x);
+    const VT* yw = reinterpret_cast<const VT*>(yv);
+    T a4[4] = {T(0), T(0), T(0), T(0)};
+    long long i = t0;
+    for (; i + 3 * stride < nv; i += 4 * stride) {
+      VT xs[4], ys[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xs[j] = __ldcs(xv + i + j * stride); if (yv) ys[j] = __ldcs(yw + i + j * stride); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const T* xe = reinterpret_cast<const T*>(&xs[j]);
+        const T* ye = reinterpret_cast<const T*>(&ys[j]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) a4[j] += yv ? xe[e] * ye[e] : xe[e];
+      }
+    }
+    for (; i < nv; i += stride) {
+      const VT xs = __ldcs(xv + i);
+      const T* xe = reinterpret_cast<const T*>(&xs);
+      if (yv) {
+        const VT ys = __ldcs(yw + i);
+        const T* ye = reinterpret_cast<const T*>(&ys);
+#pragma unroll
+        for (int e = 0; e < V; ++e) a4[0] += xe[e] * ye[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) a4[0] += xe[e];
+      }
+    }
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    done = nv * V;
+  }
+  for (long long i = done + t0; i < n; i += stride)
     acc += yv ? x[i] * yv[i] : x[i];
   acc = block_sum(acc);
   __shared__ bool last;
@@ -282,7 +319,8 @@ int mms_dot_impl(mms_context* ctx, const T* x, const T* y, long long n, T* out) 
   unsigned int* ticket = reinterpret_cast<unsigned int*>(static_cast<double*>(ctx->partials) + 1024);
   { MmsKernelScope ks_(ctx, "sum_kernel");
     MMS_CARVEOUT(sum_kernel<T>);
-    sum_kernel<T><<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, partials, ticket, out); }
+    const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && n >= 4096;
+    sum_kernel<T><<<grid, kRedThreads, 0, ctx->stream>>>(x, y, n, partials, ticket, out, vec); }
   MMS_LAUNCH_CHECK();
   return 0;
 }

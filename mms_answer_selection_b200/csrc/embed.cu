@@ -61,7 +61,7 @@ embed_forward_vec(const T* __restrict__ idx, const T* __restrict__ W, const T* _
       VT v;
       if (ok) v = __ldg(src + c); else vzero(v);
       if (bias) v = vadd(v, __ldg(reinterpret_cast<const VT*>(bias) + c));
-      __stcs(dst + c, v);   // streaming store: the gathered rows are consumed once
+      if (top) __stcs(dst + c, v);   // streaming store: the gathered rows are consumed once (MMS_OPT_STAGE_ONLY: not at all)
       if (staged) reinterpret_cast<VT*>(staged + (size_t)row * lds)[c] = tf32_rn(v);
     }
   }
@@ -233,9 +233,10 @@ int mms_embed_forward_impl(mms_context* ctx, const T* idx, const T* W, const T* 
     }
     { MmsKernelScope ks_(ctx, "embed_forward_vec");
       MMS_CARVEOUT((embed_forward_vec<T, VEC>));
-      embed_forward_vec<T, VEC><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, top, M, D, V,
-                                                                           ctx->fault_flag, staged, lds); }
-    if (staged) mms_stage_publish(ctx, top, ctx->stage_buf, M, D, lds);
+      const bool only = staged && ctx->stage_only;
+      embed_forward_vec<T, VEC><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, only ? nullptr : top, M, D, V,
+                                                                           ctx->fault_flag, staged, lds);
+      if (staged) mms_stage_publish(ctx, top, ctx->stage_buf, M, D, lds, only); }
   } else {
     { MmsKernelScope ks_(ctx, "embed_forward_scalar");
       embed_forward_scalar<T><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, top, M, D, V,

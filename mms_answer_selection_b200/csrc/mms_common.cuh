@@ -28,6 +28,7 @@ struct mms_context {
   cudaEvent_t ev_fork[2] = {nullptr, nullptr};
   cudaEvent_t ev_join[2] = {nullptr, nullptr};
   int concurrency = 1;           // MMS_OPT_CONCURRENCY
+  int stage_only = 0;            // MMS_OPT_STAGE_ONLY: ... and not the fp32 top itself
   int stage_tf32 = 0;            // MMS_OPT_STAGE_TF32: Embed forward also writes the TF32-rounded, row-padded copy
   float* stage_buf = nullptr;    // ... into this buffer (owned by the handle, published in the staging registry)
   size_t stage_bytes = 0;
@@ -75,7 +76,9 @@ struct mms_context {
 // Staging registry (MMS_OPT_STAGE_TF32): producer kernels that know their top will be a tensor-core operand write the
 // rounded, padded copy themselves and publish it under the top's address; consumers look the address up.  An entry is
 // honoured only while no logged write overlaps the top.
-void mms_stage_publish(struct mms_context* owner, const void* src, const float* staged, long long rows, int cols, int ld);
+void mms_stage_publish(struct mms_context* owner, const void* src, const float* staged, long long rows, int cols, int ld, bool virt = false);
+bool mms_stage_virtual(const void* src);   // src was published by a producer that did not write src itself (MMS_OPT_STAGE_ONLY)
+int mms_stage_require_real(const void* src, bool have_staged, const char* what);
 const float* mms_stage_lookup(const void* src, long long rows, int cols, int ld);
 void mms_stage_drop_owner(struct mms_context* owner);
 unsigned long long mms_write_clock();

@@ -289,8 +289,12 @@ int mms_simcross_forward_impl(mms_context* ctx, int mode, const T* q, const T* a
       const int rc = tc_fwd(ctx, q, a, Mw, B, S, N, Lq, La, D, mc);
       if (rc != MMS_E_UNSUPPORTED) return rc;
     }
+    MMS_TRY(mms_stage_require_real(q, false, "bottom q"));
+    MMS_TRY(mms_stage_require_real(a, false, "bottom a"));
     return simcross2_forward_simt<T>(ctx, q, a, Mw, B, S, N, Lq, La, D, mc);
   }
+  MMS_TRY(mms_stage_require_real(q, false, "bottom q"));
+  MMS_TRY(mms_stage_require_real(a, false, "bottom a"));
   const long long total = (long long)N * Lq * La;
   if (mode == 0) {
     MMS_REQUIRE(norm0 && norm1, MMS_E_INVALID, "mode 0 needs the row-norm caches");
@@ -342,6 +346,8 @@ int mms_simcross_backward_impl(mms_context* ctx, int mode, const T* q, const T* 
     if (IsFloat<T>::value && ctx->math == MMS_MATH_TF32)
       rc = tc_bwd(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
     if (rc == MMS_E_UNSUPPORTED) {
+      MMS_TRY(mms_stage_require_real(q, false, "bottom q"));
+      MMS_TRY(mms_stage_require_real(a, false, "bottom a"));
       MMS_TRY(mms_fill<T>(ctx, dq, (long long)N * Lq * D, T(0)));
       MMS_TRY(mms_fill<T>(ctx, da, (long long)N * La * D, T(0)));
       MMS_TRY(mms_fill<T>(ctx, dM, (long long)mc * D * D, T(0)));     // :256
@@ -352,6 +358,8 @@ int mms_simcross_backward_impl(mms_context* ctx, int mode, const T* q, const T* 
     return 0;
   }
   MMS_REQUIRE(S, MMS_E_INVALID, "modes 0/1 read the forward output");
+  MMS_TRY(mms_stage_require_real(q, false, "bottom q"));
+  MMS_TRY(mms_stage_require_real(a, false, "bottom a"));
   const long long t0 = (long long)N * Lq * D, t1 = (long long)N * La * D;
   if (mode == 0) {
     MMS_REQUIRE(norm0 && norm1, MMS_E_INVALID, "mode 0 needs the row-norm caches");

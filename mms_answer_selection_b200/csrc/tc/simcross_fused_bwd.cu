@@ -71,6 +71,7 @@ struct BwdGeom {
                          // 64 / 128 GEMM-B slots filled from private lines / with half of the bytes, 256 no dS loads
   long long u_rows;      // rows of one measure slab of the exported U
   int u_blocked;         // U export layout: 0 row-major (pitch Dp), 1 blocked (tc/simcross_dm.cu)
+  int u_inline;          // dQ: the eight rounding warps export their own piece from registers (no export warps)
   long long u_groups;    // blocked: 32-row groups per measure slab
 };
 
@@ -142,7 +143,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
       for (int s = 0; s < g.stages; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
       mbar_init(&sm->g_full, 4); mbar_init(&sm->g_empty, 1);
       mbar_init(&sm->o_full, 1); mbar_init(&sm->o_empty, 4);
-      for (int j = 0; j < kUBufs; ++j) { mbar_init(&sm->u_full[j], 1); mbar_init(&sm->u_ready[j], DA ? 8 : 4); mbar_init(&sm->u_free[j], DA ? 1 : 5); }
+      for (int j = 0; j < kUBufs; ++j) { mbar_init(&sm->u_full[j], 1); mbar_init(&sm->u_ready[j], (DA || g.u_inline) ? 8 : 4); mbar_init(&sm->u_free[j], (DA || g.u_inline) ? 1 : 5); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -388,8 +389,8 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     bool first = true;
     ChunkIter it;
     it.start(g);
-    if (!DA && set == 1) {
-      if (g.u_blocked && Uexp != nullptr && blockIdx.x == 0) {
+    if (!DA && set == 1 && g.u_blocked && Uexp != nullptr && blockIdx.x == 0) {
+      {
         // rows past the last token row of the last 32-row group are read by the dM kernel: they must be zero
         const int tail0 = (int)(g.u_rows & 31);
         if (tail0 != 0) {
@@ -401,6 +402,8 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
           }
         }
       }
+    }
+    if (!DA && set == 1 && !g.u_inline) {
       while (it.live) {
         const bool valid = (p_lane < g.P) && (it.n0 + p_lane < g.N) && Uexp != nullptr && !(g.dbg & 4);
         const long long grow = (long long)it.n0 * g.Lr + row;    // row of U this thread owns
@@ -437,22 +440,32 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         it.next(g);
       }
     } else {
-      const int step = DA ? 64 : 32;                              // column stride between the pieces of one warp
+      // Two warps per TMEM lane quarter, 32 columns of the chunk each (dQ without u_inline: warps 2-5 alone, 64 columns).
+      // dQ with u_inline: a warp's rounded piece is still in its registers when it has announced the chunk -- it goes to
+      // global memory from there (blocked layout: 128 consecutive bytes per warp and instruction), after the arrival,
+      // so the export never sits between GEMM-A and GEMM-B of this chunk and TMEM is read once, not twice.
+      const bool pair = DA || g.u_inline;
+      const int step = pair ? 64 : 32;                            // column stride between the pieces of one warp
       while (it.live) {
         mbar_wait(&sm->u_full[ur.i], ur.ph);
         tc_fence_after();
         if (TRACE && first && threadIdx.x == 64) trace(tr, 5);
         const int w = it.c == nch - 1 ? wl : CW;
+        float v[32];
+        int cx = -1;                                              // first column of the piece held in v
+        bool wide = false;
         if (!(g.dbg & 1)) {
-          for (int c0 = DA ? set * 32 : 0; c0 < w; c0 += step) {
-            float v[32];
+          for (int c0 = pair ? set * 32 : 0; c0 < w; c0 += step) {
             const uint32_t ta = tmem_U + lane_bits + (uint32_t)(ur.i * CW + c0);
+            cx = c0;
             if (w - c0 > 16) {
+              wide = true;
               tmem_ld32(ta, v);
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = to_tf32(v[i]);
               tmem_st32(ta, v);
             } else {
+              wide = false;
               tmem_ld16(ta, v);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = to_tf32(v[i]);
@@ -466,6 +479,24 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         if (lane == 0) mbar_arrive(&sm->u_ready[ur.i]);
         if (TRACE && first && threadIdx.x == 64) trace(tr, 6);
         first = false;
+        if (!DA && g.u_inline && cx >= 0) {
+          const bool valid = (p_lane < g.P) && (it.n0 + p_lane < g.N) && Uexp != nullptr && !(g.dbg & 4);
+          if (valid) {
+            const long long grow = (long long)it.n0 * g.Lr + row;
+            if (g.u_blocked) {
+              float* urow = Uexp + (((size_t)it.k * g.u_groups + (size_t)(grow >> 5)) * g.Dp + (size_t)(it.c * CW + cx)) * 32 +
+                            (size_t)(grow & 31);
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < 16 || wide) __stcs(urow + (size_t)i * 32, v[i]);
+            } else {
+              float* urow = Uexp + ((size_t)it.k * g.u_rows + grow) * g.Dp + it.c * CW + cx;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < 2 || wide) st_global_v8(urow + i * 8, v + 8 * i);
+            }
+          }
+        }
         ur.advance(kUBufs);
         it.next(g);
       }
@@ -686,6 +717,7 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
 #endif
   g.u_rows = (long long)N * g.Lr;
   g.u_blocked = u_blocked;
+  { static const char* e = getenv("MMS_BWD_EXPORT_WARPS"); g.u_inline = (e && atoi(e)) ? 0 : 1; }   // CW <= 64: one piece per warp
   g.u_groups = (g.u_rows + 31) / 32;
 
   CUtensorMap mapX, mapM;

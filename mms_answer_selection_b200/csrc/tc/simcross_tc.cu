@@ -71,6 +71,8 @@ int mms_tc_simcross2_forward(mms_context* ctx, const float* q, const float* a, c
   // operands a producer already staged (MMS_OPT_STAGE_TF32 on the Embed handle): read in place, no rounding pass
   const float* qs = p.nc_max == N ? mms_stage_lookup(q, (long long)N * Lq, D, Dp) : nullptr;
   const float* as = p.nc_max == N ? mms_stage_lookup(a, (long long)N * La, D, Dp) : nullptr;
+  MMS_TRY(mms_stage_require_real(q, qs != nullptr, "bottom q"));
+  MMS_TRY(mms_stage_require_real(a, as != nullptr, "bottom a"));
   const float* qr = qs ? qs : qr_ws;
   const float* ar = as ? as : ar_ws;
   // the rounded copies stay in the scratch buffer: a backward on the same handle may reuse them (MMS_OPT_REUSE_FORWARD)
@@ -164,6 +166,10 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
   if (phase == 2) { qs = ctx->dm_pending.qr; }
   else if (reuse) { qs = fc.qr; as = fc.ar; }
   else if (nc_max == N) { qs = mms_stage_lookup(q, (long long)N * Lq, D, Dp); as = mms_stage_lookup(a, (long long)N * La, D, Dp); }
+  if (phase != 2) {
+    MMS_TRY(mms_stage_require_real(q, qs != nullptr, "bottom q"));
+    MMS_TRY(mms_stage_require_real(a, as != nullptr, "bottom a"));
+  }
   const float* qr = qs ? qs : qr_ws;
   const float* ar = as ? as : ar_ws;
   if (phase == 2) {

@@ -21,7 +21,7 @@ from .layers import EmbedLayer, LayerParameter, SimCrossLayer
 
 class MMSNet(object):
     def __init__(self, N, L=40, D=300, mc=4, V=60002, dtype=np.float32, device="cuda", bias_term=True,
-                 embed_bias=True, math=None, stage_tf32=True, deterministic=False):
+                 embed_bias=True, math=None, stage_tf32=True, deterministic=False, keep_embed_tops=True):
         self.N, self.L, self.D, self.mc, self.V = N, L, D, mc, V
         self.dtype = np.dtype(dtype)
         self.device = torch.device(device)
@@ -55,6 +55,12 @@ class MMSNet(object):
         if self.dtype == np.float32 and stage_tf32:
             self.embed_q.handle.set_option(_lib.MMS_OPT_STAGE_TF32, 1)
             self.embed_a.handle.set_option(_lib.MMS_OPT_STAGE_TF32, 1)
+            # keep_embed_tops=False (MMS_OPT_STAGE_ONLY): q / a exist only as that operand copy; the fp32 blobs keep
+            # their shape and address but are never written -- nothing in this net reads them
+            if not keep_embed_tops:
+                self.embed_q.handle.set_option(_lib.MMS_OPT_STAGE_ONLY, 1)
+                self.embed_a.handle.set_option(_lib.MMS_OPT_STAGE_ONLY, 1)
+        self.keep_embed_tops = bool(keep_embed_tops) or not (self.dtype == np.float32 and stage_tf32)
         # MMS_OPT_EMBED_DETERMINISTIC: order-independent scatter-add; the two Embed backwards then run one after the
         # other (each is the single writer of the table rows it touches)
         self.deterministic = bool(deterministic)

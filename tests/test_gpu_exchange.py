@@ -366,3 +366,39 @@ def test_staged_tf32_operands_change_nothing():
     for a, b, name in zip(outs[0], outs[1], ("q", "S", "dq", "da")):
         np.testing.assert_array_equal(a, b, err_msg=name)
     assert rounds[1] < 0.5 * rounds[0]          # only M is rounded when q / a arrive staged
+
+
+def test_stage_only_embed_tops_same_results_and_loud_failures():
+    """MMS_OPT_STAGE_ONLY (MMSNet(keep_embed_tops=False)): the gather writes nothing but the TF32 operand copy.  S, dq,
+    da and dM are bit-identical to the net that also writes the fp32 tops (same operands, same kernels), the fp32 top
+    buffers are provably untouched, and a consumer that cannot use the staged copy refuses instead of reading them."""
+    from mms_answer_selection_b200 import _lib
+    N, L, D, mc, V = 384, 40, 300, 4, 4000
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    outs = []
+    for keep in (True, False):
+        net = mms.MMSNet(N, L, D, mc, V, keep_embed_tops=keep)
+        net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
+        net.set_upstream_gradient(d["dS"])
+        net.q.data.fill_(-7.0); net.a.data.fill_(-7.0)
+        net.ClearParamDiffs(); net.ForwardBackward()
+        torch.cuda.synchronize()
+        outs.append([net.S.cpu_data(), net.q.cpu_diff(), net.a.cpu_diff(), net.sim.blobs[0].cpu_diff()])
+        if keep:
+            assert not (net.q.cpu_data() == -7.0).any()
+            w_keep = net.embed_q.blobs[0].cpu_diff()
+        else:
+            assert (net.q.cpu_data() == -7.0).all() and (net.a.cpu_data() == -7.0).all()      # never written
+            w_only = net.embed_q.blobs[0].cpu_diff()
+            # fp32 math cannot use the TF32 copy: refuse, do not read the unwritten top
+            net.sim.handle.set_option(_lib.MMS_OPT_REUSE_FORWARD, 0)
+            net.sim.set_math(_lib.MMS_MATH_FP32)
+            with pytest.raises(Exception, match="STAGE_ONLY"):
+                net.sim.Forward([net.q, net.a], [net.S])
+            with pytest.raises(Exception, match="STAGE_ONLY"):
+                net.sim.Backward([net.S], [True, True], [net.q, net.a])
+            torch.cuda.synchronize()
+    for a, b, name in zip(outs[0], outs[1], ("S", "dq", "da")):
+        np.testing.assert_array_equal(a, b, err_msg=name)
+    for a, b, name in ((outs[0][3], outs[1][3], "dM"), (w_keep, w_only, "dW")):                # float atomics: order differs
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max(), name

@@ -58,7 +58,10 @@ enum {
                                 table row is summed in 64-bit fixed point by one writer, so dW / dbias are bit-identical
                                 from run to run and under any permutation of the token rows (needs D a multiple of
                                 16 bytes and 16-byte aligned blobs, else MMS_E_UNSUPPORTED); 0 = run-merged float
-                                atomics (arrival order, like the reference's kernel).  Default 0. */
+                                atomics (arrival order, like the reference's kernel).  On a handle used for
+                                mms_simcross_backward (mode 2): 1 = every dq / da row has one writer (the measures of a
+                                pair group are never spread over CTAs that add with float atomics), so the bottom
+                                gradients are bit-identical from run to run too.  Default 0. */
   MMS_OPT_REUSE_FORWARD = 5, /* SimCross mode 2, float: 1 = mms_simcross_backward may reuse the TF32-rounded
                                 operands and T = Q M_k that the LAST mms_simcross_forward on this handle left
                                 in the workspace, provided it was called with the same q / a / M pointers and

@@ -284,10 +284,11 @@ int mms_tc_simcross2_forward_fused(mms_context*, const float* qr, const float* a
 // fused bottom gradients (tc/simcross_fused_bwd.cu): which = 0 dq (xr = rounded answers; exports U = G A for the
 // dM contraction), which = 1 da (xr = rounded questions).  _plan tells whether the shape is covered and how many
 // of the `ctas` CTAs it may use share one tile's measures (> 1: `out` must be zeroed by the caller).
-int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int* ksplit);
+int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int allow_split,
+                                         int* ksplit, int* split_from);
 int mms_tc_simcross2_backward_fused(mms_context*, int which, const float* xr, const float* Mr, const float* dS,
                                     float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp, int ksplit,
-                                    int u_blocked = 0);
+                                    int split_from, int u_blocked = 0);
 // weight gradient dM_k += Qall^T U_k from the blocked U export (tc/simcross_dm.cu); _plan: shape covered?
 int mms_tc_simcross2_dm_plan(int D);
 int mms_tc_simcross2_dm(mms_context*, const float* qr, const float* Ub, float* dM, long long rows, int D, int Dp, int mc,

@@ -61,7 +61,10 @@ struct BwdGeom {
   int CW, nch, wl;       // chunk width, chunks per (tile, measure), width of the last chunk
   int nbxB;              // dA: 32-column boxes of M_k per k-block
   int stages, stage_bytes;
-  int ksplit;            // CTAs that share the measures of one pair group
+  int ksplit;            // CTAs that share the measures of one pair group ...
+  unsigned whole;        // ... from group `whole` on: tiles [0, whole) are groups 0.. with all their measures (whole
+                         // waves of the grid), the groups left over are spread by measure so that the last wave is
+                         // 1/ksplit of a tile long instead of a full one
   unsigned total_tiles;
   uint32_t tmem_cols;
   int vec_g, vec_s, vec_out;   // 16-byte dS loads (dQ) / 16-byte Gblk stores / 16-byte output stores
@@ -94,6 +97,16 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
 
 // Walks the chunks (tile, measure, chunk) of this CTA in issue order.  Every role keeps its own copy (the MMA warp
 // and the producer keep two: GEMM-A runs two chunks ahead of GEMM-B).
+// tile t -> its pair group's first pair and its range of measures
+__device__ __forceinline__ void tile_map(const BwdGeom& g, unsigned t, int& n0, int& k_lo, int& k_hi) {
+  if (t < g.whole) { n0 = (int)t * g.P; k_lo = 0; k_hi = g.mc; return; }
+  const unsigned u = t - g.whole;
+  const int ksp = (int)(u % (unsigned)g.ksplit);
+  n0 = (int)(g.whole + u / (unsigned)g.ksplit) * g.P;
+  k_lo = ksp * g.mc / g.ksplit;
+  k_hi = (ksp + 1) * g.mc / g.ksplit;
+}
+
 struct ChunkIter {
   unsigned t;
   int n0, k, k_lo, k_hi, c;
@@ -101,13 +114,7 @@ struct ChunkIter {
   __device__ __forceinline__ void load(const BwdGeom& g) {
     live = t < g.total_tiles;
     c = 0;
-    if (live) {
-      const int ksp = (int)(t % (unsigned)g.ksplit);
-      n0 = (int)(t / (unsigned)g.ksplit) * g.P;
-      k_lo = ksp * g.mc / g.ksplit;
-      k_hi = (ksp + 1) * g.mc / g.ksplit;
-      k = k_lo;
-    }
+    if (live) { tile_map(g, t, n0, k_lo, k_hi); k = k_lo; }
   }
   __device__ __forceinline__ void start(const BwdGeom& g) { t = blockIdx.x; load(g); }
   __device__ __forceinline__ void next(const BwdGeom& g) {
@@ -180,8 +187,9 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         // about 1 us of operands) only ever waits for L2
         if (it.c == 0 && it.k == it.k_lo && (g.dbg & 32)) {
           const unsigned tn = it.t + gridDim.x;
-          if (tn < g.total_tiles && (g.ksplit == 1 || tn / (unsigned)g.ksplit != it.t / (unsigned)g.ksplit)) {
-            const int n0n = (int)(tn / (unsigned)g.ksplit) * g.P;
+          if (tn < g.total_tiles) {
+            int n0n, kl, kh;
+            tile_map(g, tn, n0n, kl, kh);
             for (int x = 0; x < nbxB; ++x) tma_prefetch_l2_5d(&mapX, 32 * x, n0n * Lk, 0, 0, 0);
           }
         }
@@ -514,7 +522,9 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     const int N1 = g.N1, D = g.D;
     int tc = 0;
     for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tc) {
-      const int n0 = (int)(t / (unsigned)g.ksplit) * g.P;
+      int n0, k_lo_, k_hi_;
+      tile_map(g, t, n0, k_lo_, k_hi_);
+      const bool split = g.ksplit > 1 && t >= g.whole;              // this tile's measures are shared: add, do not store
       const bool valid = (p_lane < g.P) && (n0 + p_lane < g.N) && !(g.dbg & 2);
       const long long grow = (long long)n0 * g.Lr + row;
       float* orow = out + grow * D;
@@ -530,19 +540,19 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         if (!valid) continue;
         const int ncols = mms_min(wc, D - c * 32);               // columns of this chunk that exist in the output
         float* dst = orow + c * 32;
-        if (g.ksplit > 1 || !g.vec_out) {
+        if (split || !g.vec_out) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i * 4 < ncols) {
               if (g.vec_out && i * 4 + 4 <= ncols) {
                 const float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                if (g.ksplit > 1) atomicAdd(reinterpret_cast<float4*>(dst + 4 * i), o);
+                if (split) atomicAdd(reinterpret_cast<float4*>(dst + 4 * i), o);
                 else __stcs(reinterpret_cast<float4*>(dst + 4 * i), o);
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   if (i * 4 + j < ncols) {
-                    if (g.ksplit > 1) atomicAdd(dst + 4 * i + j, v[4 * i + j]); else dst[4 * i + j] = v[4 * i + j];
+                    if (split) atomicAdd(dst + 4 * i + j, v[4 * i + j]); else dst[4 * i + j] = v[4 * i + j];
                   }
                 }
               }
@@ -582,9 +592,8 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         *reinterpret_cast<float4*>(gblk + kb * 16384 + swz128(r, c4)) = make_float4(0.f, 0.f, 0.f, 0.f);
     int itk = 0;
     for (unsigned t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-      const int ksp = (int)(t % (unsigned)g.ksplit);
-      const int n0 = (int)(t / (unsigned)g.ksplit) * g.P;
-      const int k_lo = ksp * g.mc / g.ksplit, k_hi = (ksp + 1) * g.mc / g.ksplit;
+      int n0, k_lo, k_hi;
+      tile_map(g, t, n0, k_lo, k_hi);
       const bool valid = (p < g.P) && (n0 + p < g.N) && !(g.dbg & 8);
       for (int k = k_lo; k < k_hi; ++k, ++itk) {
         // The G values of this row are loaded into registers BEFORE waiting for the tile to be free (the loads do
@@ -655,9 +664,14 @@ int chunk_width(int N1) { return N1 + kUBufs * 64 <= 512 ? 64 : (N1 + kUBufs * 3
 // which = 0: dq (N*Lq x D) from dS, ar = rounded answers, Mr; exports U (mc x N*Lq x Dp) when Uexp != nullptr.
 // which = 1: da (N*La x D) from dS, xr = rounded questions, Mr.
 // xr (rows x Dp) and Mr (mc x D x Dp) are TF32-rounded copies with 128-byte-aligned rows; dS is read as is.
-// ksplit > 1 accumulates with atomics: the caller must have zeroed `out`.  Returns MMS_E_UNSUPPORTED for shapes the
+// ksplit > 1 accumulates the rows of pairs [split_from, N) with atomics: the caller must have zeroed those rows of `out`.  Returns MMS_E_UNSUPPORTED for shapes the
 // tile does not cover.
-int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int* ksplit) {
+// ksplit > 1: the measures of the pair groups from pair `*split_from` on are spread over ksplit CTAs, which ADD into the
+// output -- the caller zeroes the output rows of pairs [*split_from, N) first.  Small batches split every group
+// (*split_from = 0); large ones only the groups left over after the last whole wave of the grid.  allow_split = 0
+// (deterministic handles): never, every output row has one writer.
+int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int allow_split,
+                                         int* ksplit, int* split_from) {
   const int sm_count = ctas;
   static const bool disabled = getenv("MMS_NO_FUSED") != nullptr || getenv("MMS_NO_FUSED_BWD") != nullptr;
   if (disabled) return MMS_E_UNSUPPORTED;
@@ -667,19 +681,29 @@ int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D
   const int P = mms_max(1, mms_min(mms_min(128 / Lq, 128 / La), N));
   const long long base = mms_ceil_div(N, P);
   int ks = 1;
-  if (base * 2 <= sm_count) ks = (int)mms_min<long long>(mc, sm_count / base);
-  *ksplit = mms_max(1, ks);
+  long long whole = base;
+  static const bool no_tail = getenv("MMS_BWD_NO_TAIL_SPLIT") != nullptr;
+  if (allow_split && mc > 1) {
+    if (base * 2 <= sm_count) { ks = (int)mms_min<long long>(mc, sm_count / base); whole = 0; }
+    else if (!no_tail) {
+      const long long rest = base % sm_count;
+      if (rest > 0 && rest * 2 <= sm_count) { ks = (int)mms_min<long long>(mc, sm_count / rest); whole = base - rest; }
+    }
+  }
+  if (ks <= 1) { ks = 1; whole = base; }
+  *ksplit = ks;
+  if (split_from) *split_from = (int)mms_min<long long>(N, whole * P);
   (void)which;
   return 0;
 }
 
 int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr, const float* Mr, const float* dS,
                                     float* out, float* Uexp, int N, int Lq, int La, int D, int mc, int Dp,
-                                    int ksplit, int u_blocked) {
+                                    int ksplit, int split_from, int u_blocked) {
   BwdGeom g;
   {
     int unused = 1;
-    MMS_TRY(mms_tc_simcross2_backward_fused_plan(which, N, Lq, La, D, mc, ctx->sm_count, &unused));
+    MMS_TRY(mms_tc_simcross2_backward_fused_plan(which, N, Lq, La, D, mc, ctx->sm_count, 0, &unused, nullptr));
     MMS_REQUIRE(ksplit >= 1 && ksplit <= mc, MMS_E_INVALID, "bad measure split");
   }
   const bool DA = which != 0;
@@ -703,9 +727,13 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   { static const char* e = getenv("MMS_BWD_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
   g.stages = stages;
   g.ksplit = ksplit;
-  const long long total = (long long)mms_ceil_div(N, g.P) * ksplit;
+  const long long groups = mms_ceil_div(N, g.P);
+  MMS_REQUIRE(ksplit == 1 || (split_from >= 0 && split_from % g.P == 0 && split_from <= N), MMS_E_INVALID, "bad split start");
+  const long long whole = ksplit == 1 ? groups : mms_min<long long>(groups, split_from / g.P);
+  const long long total = whole + (groups - whole) * ksplit;
   if (total > 0x7fffffffLL) return MMS_E_UNSUPPORTED;
   g.total_tiles = (unsigned)total;
+  g.whole = (unsigned)whole;
   g.tmem_cols = umma::tmem_cols_pow2((uint32_t)(g.N1 + kUBufs * g.CW));
   g.vec_g = (La % 4 == 0) && ((reinterpret_cast<uintptr_t>(dS) & 15) == 0);
   g.vec_s = g.Lk % 4 == 0;
@@ -734,7 +762,10 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
     configured = true;
   }
   const size_t smem = (size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024;
-  const unsigned grid = (unsigned)mms_min<long long>(total, ctx->sm_count);
+  unsigned grid = (unsigned)mms_min<long long>(total, ctx->sm_count);
+#ifdef MMS_BWD_PROBES
+  { static const char* e = getenv("MMS_BWD_GRID"); if (e && atoi(e) > 0) grid = mms_min<unsigned>(grid, (unsigned)atoi(e)); }
+#endif
   TraceBuf tb;
   MMS_TRY(tb.begin(grid));
   { MmsKernelScope ks_(ctx, DA ? "simcross2_bwd_fused_kernel<dA>" : "simcross2_bwd_fused_kernel<dQ>");

@@ -198,30 +198,32 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
       if (nj) MMS_TRY(mms_tf32_round(ctx, jobs, nj));
     }
     // two kernels side by side only pay when one of them cannot fill the GPU: then each gets half of the SMs
-    int ksplit = 1;
-    MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctx->sm_count, &ksplit));
-    const bool conc = want_conc && ksplit > 1;
-    if (conc) MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, mms_max(1, ctx->sm_count / 2), &ksplit));
-    if (ksplit > 1) {   // the measures of one tile are spread over CTAs that add into the output
-      MMS_CUDA(cudaMemsetAsync(dqc, 0, sizeof(float) * (size_t)nc * Lq * D, ctx->stream));
-      MMS_CUDA(cudaMemsetAsync(dac, 0, sizeof(float) * (size_t)nc * La * D, ctx->stream));
+    // (a handle with MMS_OPT_EMBED_DETERMINISTIC never spreads a pair group's measures over CTAs: one writer per row)
+    const int allow_split = ctx->embed_deterministic ? 0 : 1;
+    int ksplit = 1, split_from = nc;
+    MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, ctx->sm_count, allow_split, &ksplit, &split_from));
+    const bool conc = want_conc && ksplit > 1 && split_from == 0;
+    if (conc) MMS_TRY(mms_tc_simcross2_backward_fused_plan(0, nc, Lq, La, D, mc, mms_max(1, ctx->sm_count / 2), allow_split, &ksplit, &split_from));
+    if (ksplit > 1 && split_from < nc) {   // measures of these pair groups are spread over CTAs that add into the output
+      MMS_CUDA(cudaMemsetAsync(dqc + (size_t)split_from * Lq * D, 0, sizeof(float) * (size_t)(nc - split_from) * Lq * D, ctx->stream));
+      MMS_CUDA(cudaMemsetAsync(dac + (size_t)split_from * La * D, 0, sizeof(float) * (size_t)(nc - split_from) * La * D, ctx->stream));
     }
     if (conc) {
       MMS_TRY(mms_fork(ctx, 0));
       MmsStreamSwitch sw(ctx, 0);
-      MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit));  // :296-299
+      MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit, split_from));  // :296-299
     }
     // dedicated dM kernel (tc/simcross_dm.cu) over the blocked U export; small batches are latency-bound and do
     // better with the 32-byte row-major export and the many small tiles of the generic engine (measured at 50 pairs)
     const int use_dm = mms_tc_simcross2_dm_plan(D) == 0 && (long long)nc * Lq >= 16384;
     const int blocked = use_dm;                               // U in the blocked layout that kernel reads best
-    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp, ksplit, blocked));   // :291-294
+    MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 0, ar, Mr, dSc, dqc, U, nc, Lq, La, D, mc, Dp, ksplit, split_from, blocked));   // :291-294
     if (phase == 0) {
       if (use_dm) MMS_TRY(mms_tc_simcross2_dm(ctx, qr, U, dM, (long long)nc * Lq, D, Dp, mc, blocked));        // :286-289
       else MMS_TRY(gemm_dM(ctx, qr, U, dM, nc * Lq, D, Dp, mc));
     }
     if (conc) MMS_TRY(mms_join(ctx, 0));
-    else MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit));
+    else MMS_TRY(mms_tc_simcross2_backward_fused(ctx, 1, qr, Mr, dSc, dac, nullptr, nc, Lq, La, D, mc, Dp, ksplit, split_from));
   }
   if (phase == 1) {
     mms_context::DmPending& dp = ctx->dm_pending;
@@ -235,7 +237,7 @@ int backward_fused(mms_context* ctx, const float* q, const float* a, const float
 int mms_tc_simcross2_backward_bottoms(mms_context* ctx, const float* q, const float* a, const float* Mw, const float* dS,
                                       float* dq, float* da, int N, int Lq, int La, int D, int mc) {
   int ksplit = 1;
-  if (mms_tc_simcross2_backward_fused_plan(0, N, Lq, La, D, mc, ctx->sm_count, &ksplit) != 0) return MMS_E_UNSUPPORTED;
+  if (mms_tc_simcross2_backward_fused_plan(0, N, Lq, La, D, mc, ctx->sm_count, 0, &ksplit, nullptr) != 0) return MMS_E_UNSUPPORTED;
   return backward_fused(ctx, q, a, Mw, dS, dq, da, nullptr, N, Lq, La, D, mc, 1);
 }
 
@@ -249,7 +251,7 @@ int mms_tc_simcross2_backward(mms_context* ctx, const float* q, const float* a, 
                               int D, int mc) {
   {  // fused kernels for dq / da (tc/simcross_fused_bwd.cu) + one GEMM for dM, when the shape allows
     int ksplit = 1;
-    if (mms_tc_simcross2_backward_fused_plan(0, N, Lq, La, D, mc, ctx->sm_count, &ksplit) == 0) {
+    if (mms_tc_simcross2_backward_fused_plan(0, N, Lq, La, D, mc, ctx->sm_count, 0, &ksplit, nullptr) == 0) {
       const int rc = backward_fused(ctx, q, a, Mw, dS, dq, da, dM, N, Lq, La, D, mc);
       if (rc != MMS_E_UNSUPPORTED) return rc;
     }

@@ -67,6 +67,8 @@ class MMSNet(object):
         if self.deterministic:
             self.embed_q.handle.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1)
             self.embed_a.handle.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1)
+            # on the SimCross handle: dq / da rows have one writer each (no measure split with float atomics)
+            self.sim.handle.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1)
         self._pinned = None
         self._side = None
 

@@ -146,6 +146,20 @@ int mms_embed_backward_f32(mms_handle_t h, const float* idx, const float* dtop, 
                            float* dbias, long long M, int D, int V);
 int mms_embed_backward_f64(mms_handle_t h, const double* idx, const double* dtop, double* dW,
                            double* dbias, long long M, int D, int V);
+/* The Backward_gpu of TWO Embed layers that share their table (param sharing by name, do_trec_qa_clean.py:461-468) as one
+ * scatter-add: dW[idx0[n],:] += dtop0[n,:], dW[idx1[n],:] += dtop1[n,:], dbias += both column sums (embed_layer.cu:59-77
+ * twice).  The token rows of both blobs are grouped by id first, so a table row that occurs k times receives one atomic
+ * add per float instead of k (and its 1200 bytes of dW cross HBM once instead of up to k times: the table gradient is
+ * never L2-resident when the scatter runs).  Same accumulate semantics and the same float-atomic (arrival-order) rounding as
+ * mms_embed_backward; idx1 / dtop1 may be NULL with M1 = 0.
+ * mms_embed_plan_pair does the grouping alone -- it needs the ids only, so a net can run it beside the forward pass; a
+ * following mms_embed_backward_pair on the same handle with the same id blobs and sizes uses it (the caller vouches that
+ * the ids did not change in between), any other call groups the rows itself.  Shapes the grouped kernels do not take
+ * (D % 4 != 0, D > 512, unaligned blobs) and handles with MMS_OPT_EMBED_DETERMINISTIC run mms_embed_backward per blob. */
+int mms_embed_plan_pair_f32(mms_handle_t h, const float* idx0, long long M0, const float* idx1, long long M1, int V);
+int mms_embed_backward_pair_f32(mms_handle_t h, const float* idx0, const float* dtop0, long long M0,
+                                const float* idx1, const float* dtop1, long long M1, float* dW, float* dbias,
+                                int D, int V);
 
 /* --------------------------------------------------------------- SimCross --
  * Replaces SimCrossLayer::Forward_gpu (src/caffe/layers/sim_cross_layer.cu:127-190,

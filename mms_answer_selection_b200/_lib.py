@@ -122,6 +122,8 @@ def lib():
         L.mms_rerank_topk_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
         L.mms_rerank_topk_prepared_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
         L.mms_topk_merge_f32.argtypes = [c_p, c_p, c_p, c_ll, c_ll, c_p, c_p, c_int, c_int]
+        L.mms_embed_plan_pair_f32.argtypes = [c_p, c_p, c_ll, c_p, c_ll, c_int]
+        L.mms_embed_backward_pair_f32.argtypes = [c_p, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_int, c_int]
         L.mms_dropout_mask.argtypes = [c_p, c_p, c_ll, ctypes.c_ulonglong]
         L.mms_tc_gemm_f32.argtypes = [c_p, c_p, c_ll, c_int, c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int,
                                       c_int, c_int]

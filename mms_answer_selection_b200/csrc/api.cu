@@ -233,6 +233,7 @@ int mms_destroy(mms_handle_t h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   mms_tc_destroy_state(h);
+  mms_embed_plan_destroy(h);
   prof_clear(h);
   delete static_cast<std::vector<ProfRecord>*>(h->prof);
   mms_stage_drop_owner(h);
@@ -355,6 +356,14 @@ int mms_check_faults(mms_handle_t h) {
 }
 
 #define H MMS_REQUIRE(h, MMS_E_INVALID, "null handle")
+
+int mms_embed_plan_pair_f32(mms_handle_t h, const float* idx0, long long M0, const float* idx1, long long M1, int V) {
+  H; return mms_embed_plan_pair_impl(h, idx0, M0, idx1, M1, V);
+}
+int mms_embed_backward_pair_f32(mms_handle_t h, const float* idx0, const float* dtop0, long long M0, const float* idx1,
+                                const float* dtop1, long long M1, float* dW, float* dbias, int D, int V) {
+  H; return mms_embed_backward_pair_impl(h, idx0, dtop0, M0, idx1, dtop1, M1, dW, dbias, D, V);
+}
 
 #define MMS_DEFINE_TYPED(T, SUF)                                                                   \
   int mms_embed_forward_##SUF(mms_handle_t h, const T* idx, const T* W, const T* bias, T* top,     \

@@ -11,6 +11,7 @@ struct mms_context {
   int math = MMS_MATH_TF32;
   int prl_ge = 0;
   int embed_deterministic = 0;
+  void* embed_plan = nullptr;    // embed_sorted.cu: token rows grouped by id (mms_embed_plan_pair)
   size_t scratch_cap = (size_t)4 << 30;
   void* scratch = nullptr;       // grows on demand, reused across calls
   size_t scratch_bytes = 0;
@@ -187,6 +188,10 @@ int mms_embed_forward_impl(mms_context*, const T* idx, const T* W, const T* bias
 template <typename T>
 int mms_embed_backward_impl(mms_context*, const T* idx, const T* dtop, T* dW, T* dbias,
                             long long M, int D, int V);
+void mms_embed_plan_destroy(mms_context* ctx);
+int mms_embed_plan_pair_impl(mms_context* ctx, const float* idx0, long long M0, const float* idx1, long long M1, int V);
+int mms_embed_backward_pair_impl(mms_context* ctx, const float* idx0, const float* dtop0, long long M0, const float* idx1,
+                                 const float* dtop1, long long M1, float* dW, float* dbias, int D, int V);
 template <typename T>
 int mms_embed_backward_deterministic(mms_context*, const T* idx, const T* dtop, T* dW, T* dbias, long long M, int D, int V);
 template <typename T>

@@ -244,6 +244,30 @@ class EmbedLayer(Layer):
                    self.M_, self.N_, self.K_)
 
 
+    # -- two Embed layers that share their blobs (param sharing by name): both scatter-adds as one grouped pass
+    def _pair_args(self, other, bottom, bottom_o):
+        _check(other.blobs_[0].shares_storage_with(self.blobs_[0]) and other.N_ == self.N_ and other.K_ == self.K_,
+               "the paired Embed layers must share their table")
+        _check(self.dtype == np.float32, "the paired Embed backward is float32 only")
+        return (_p(bottom), self.M_, _p(bottom_o), other.M_)
+
+    def PlanPair(self, other, bottom, bottom_o):
+        """Groups the token rows of both bottoms by id (mms_embed_plan_pair): needs the ids only, so it can run on a side
+        stream beside the forward pass; the next BackwardPair on this layer with the same bottoms uses it."""
+        self._bind_stream()
+        i0, m0, i1, m1 = self._pair_args(other, bottom, bottom_o)
+        check(lib().mms_embed_plan_pair_f32(self.handle.ptr, i0, m0, i1, m1, self.K_))
+
+    def BackwardPair(self, other, top, top_o, bottom, bottom_o):
+        """Backward of this layer and of ``other`` in one call (mms_embed_backward_pair)."""
+        self._bind_stream()
+        i0, m0, i1, m1 = self._pair_args(other, bottom, bottom_o)
+        dW = self.blobs_[0] if self.param_propagate_down_[0] else None
+        db = self.blobs_[1] if (self.bias_term_ and self.param_propagate_down_[1]) else None
+        check(lib().mms_embed_backward_pair_f32(self.handle.ptr, i0, _p(top, True), m0, i1, _p(top_o, True), m1,
+                                                _p(dW, True), _p(db, True), self.N_, self.K_))
+
+
 # ------------------------------------------------------------------------- SimCross
 class SimCrossLayer(Layer):
     exact_num_bottom = 2

@@ -21,7 +21,8 @@ from .layers import EmbedLayer, LayerParameter, SimCrossLayer
 
 class MMSNet(object):
     def __init__(self, N, L=40, D=300, mc=4, V=60002, dtype=np.float32, device="cuda", bias_term=True,
-                 embed_bias=True, math=None, stage_tf32=True, deterministic=False, keep_embed_tops=True):
+                 embed_bias=True, math=None, stage_tf32=True, deterministic=False, keep_embed_tops=True,
+                 grouped_scatter=True):
         self.N, self.L, self.D, self.mc, self.V = N, L, D, mc, V
         self.dtype = np.dtype(dtype)
         self.device = torch.device(device)
@@ -69,6 +70,9 @@ class MMSNet(object):
             self.embed_a.handle.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1)
             # on the SimCross handle: dq / da rows have one writer each (no measure split with float atomics)
             self.sim.handle.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 1)
+        # both Embed backwards as one scatter-add with the token rows grouped by id (mms_embed_backward_pair); the
+        # deterministic net keeps the per-layer fixed-point kernels
+        self.grouped_scatter = bool(grouped_scatter) and self.dtype == np.float32 and not self.deterministic
         self._pinned = None
         self._side = None
 
@@ -133,8 +137,17 @@ class MMSNet(object):
 
     def Backward(self):
         self.sim.Backward([self.S], [True, True], [self.q, self.a])
+        if self.grouped_scatter:
+            self.embed_q.BackwardPair(self.embed_a, self.q, self.a, self.idx_q, self.idx_a)
+            return
         self.embed_q.Backward([self.q], [False], [self.idx_q])
         self.embed_a.Backward([self.a], [False], [self.idx_a])
+
+    def _plan_scatter(self, side):
+        """The id grouping of this step's scatter-add on ``side`` (it depends on the inputs only)."""
+        if self.grouped_scatter:
+            with torch.cuda.stream(side):
+                self.embed_q.PlanPair(self.embed_a, self.idx_q, self.idx_a)
 
     def ForwardBackward(self, with_loss=True):
         loss = self.Forward(with_loss)
@@ -160,6 +173,7 @@ class MMSNet(object):
         if clear_diffs:
             with torch.cuda.stream(s1):
                 self.ClearParamDiffs()
+        self._plan_scatter(s1)
         with torch.cuda.stream(s2):
             self.embed_a.Forward([self.idx_a], [self.a])
         self.embed_q.Forward([self.idx_q], [self.q])
@@ -186,6 +200,10 @@ class MMSNet(object):
             self.embed_q.Backward([self.q], [False], [self.idx_q])
             self.embed_a.Backward([self.a], [False], [self.idx_a])
             main.wait_stream(s2)                               # the loss branch still joins here
+            return
+        if self.grouped_scatter:                               # one pass over dq and da, rows grouped by id
+            self.embed_q.BackwardPair(self.embed_a, self.q, self.a, self.idx_q, self.idx_a)
+            main.wait_stream(s2)
             return
         s2.wait_stream(main)
         with torch.cuda.stream(s2):
@@ -219,6 +237,7 @@ class MMSNet(object):
         if clear_diffs and solver is None:
             with torch.cuda.stream(s1):
                 self.ClearParamDiffs()
+        self._plan_scatter(s1)
         with torch.cuda.stream(s2):
             self.embed_a.Forward([self.idx_a], [self.a])
         self.embed_q.Forward([self.idx_q], [self.q])

@@ -1,0 +1,138 @@
+"""mms_embed_backward_pair / mms_embed_plan_pair (csrc/embed_sorted.cu): the scatter-add of two Embed layers that share a
+table, token rows grouped by id.  Oracle: numpy's np.add.at in float64 -- the reference's atomicAdd loop
+(src/caffe/layers/embed_layer.cu:29-39) summed exactly; float atomics land in arrival order, hence the 1e-5 tolerances."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from mms_answer_selection_b200 import _lib  # noqa: E402
+
+p = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def oracle(idx0, d0, idx1, d1, W0, b0, V):
+    dW = W0.astype(np.float64).copy()
+    db = b0.astype(np.float64).copy()
+    for idx, d in ((idx0, d0), (idx1, d1)):
+        if idx is None:
+            continue
+        ids = idx.astype(np.int64)
+        ok = (ids >= 0) & (ids < V)
+        np.add.at(dW, ids[ok], d[ok].astype(np.float64))
+        db += d.astype(np.float64).sum(0)            # the reference's bias gradient sums every row (embed_layer.cu:72-76)
+    return dW, db
+
+
+def make_ids(rng, M, V, kind):
+    if kind == "uniform":
+        return rng.integers(0, V, size=M)
+    if kind == "padded":                             # centre-padded sentences: long runs of the pad id
+        ids = rng.integers(0, V - 1, size=M)
+        ids[rng.random(M) < 0.55] = V - 1
+        return ids
+    if kind == "hot":                                # a few ids carry almost everything: runs of thousands of rows
+        hot = rng.integers(0, V, size=5)
+        ids = hot[rng.integers(0, 5, size=M)]
+        cold = rng.random(M) < 0.1
+        ids[cold] = rng.integers(0, V, size=int(cold.sum()))
+        return ids
+    raise ValueError(kind)
+
+
+def run_pair(h, idx0, d0, idx1, d1, W0, b0, D, V, plan_first=False):
+    dev = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+    i0, g0, i1, g1 = dev(idx0), dev(d0), dev(idx1), dev(d1)
+    dW, db = dev(W0), dev(b0)
+    M0 = 0 if idx0 is None else idx0.size
+    M1 = 0 if idx1 is None else idx1.size
+    L = _lib.lib()
+    if plan_first:
+        _lib.check(L.mms_embed_plan_pair_f32(h.ptr, p(i0), M0, p(i1), M1, V))
+    _lib.check(L.mms_embed_backward_pair_f32(h.ptr, p(i0), p(g0), M0, p(i1), p(g1), M1, p(dW), p(db), D, V))
+    torch.cuda.synchronize()
+    return dW.cpu().numpy(), db.cpu().numpy()
+
+
+@pytest.mark.parametrize("M0,M1,D,V,kind", [
+    (4000, 4000, 300, 5000, "padded"),      # the QA net's shape in small
+    (777, 1233, 300, 50, "uniform"),        # every id many times, ragged sizes
+    (20000, 9000, 300, 3000, "hot"),        # runs far beyond one chunk
+    (3000, 0, 300, 2000, "padded"),         # one blob only
+    (1500, 1700, 52, 400, "uniform"),       # one 16-byte group per lane, partly filled
+    (900, 1100, 512, 300, "padded"),        # the widest row the grouped kernels take
+    (5, 3, 300, 100000, "uniform"),         # almost nothing
+])
+@pytest.mark.parametrize("plan_first", [False, True])
+def test_pair_backward_matches_exact_scatter_add(M0, M1, D, V, kind, plan_first):
+    rng = np.random.default_rng(M0 + 3 * M1 + D)
+    idx0 = make_ids(rng, M0, V, kind).astype(np.float32)
+    idx1 = make_ids(rng, M1, V, kind).astype(np.float32) if M1 else None
+    d0 = rng.standard_normal((M0, D)).astype(np.float32)
+    d1 = rng.standard_normal((M1, D)).astype(np.float32) if M1 else None
+    W0 = rng.standard_normal((V, D)).astype(np.float32)          # accumulate semantics: dW and db start non-zero
+    b0 = rng.standard_normal(D).astype(np.float32)
+    h = _lib.Handle()
+    dW, db = run_pair(h, idx0, d0, idx1, d1, W0, b0, D, V, plan_first)
+    rW, rb = oracle(idx0, d0, idx1, d1, W0, b0, V)
+    scale = max(1.0, np.abs(rW).max())
+    assert np.abs(dW - rW).max() <= 2e-6 * scale * max(1.0, np.sqrt(M0 + M1) / 30), "dW"
+    assert np.abs(db - rb).max() <= 1e-5 * max(1.0, np.abs(rb).max()), "db"
+    untouched = np.setdiff1d(np.arange(V), np.concatenate([idx0, idx1 if idx1 is not None else []]).astype(np.int64))
+    np.testing.assert_array_equal(dW[untouched], W0[untouched])                 # rows nobody refers to: bit-identical
+
+
+def test_pair_backward_agrees_with_the_two_per_layer_calls_and_flags_bad_ids():
+    M, D, V = 6000, 300, 4000
+    rng = np.random.default_rng(3)
+    idx0 = make_ids(rng, M, V, "padded").astype(np.float32)
+    idx1 = make_ids(rng, M, V, "padded").astype(np.float32)
+    d0 = rng.standard_normal((M, D)).astype(np.float32)
+    d1 = rng.standard_normal((M, D)).astype(np.float32)
+    zW, zb = np.zeros((V, D), np.float32), np.zeros(D, np.float32)
+    h = _lib.Handle()
+    dW, db = run_pair(h, idx0, d0, idx1, d1, zW, zb, D, V)
+    dev = lambda x: torch.from_numpy(x).cuda()
+    W2, b2 = dev(zW), dev(zb)
+    g = [dev(x) for x in (idx0, d0, idx1, d1)]                   # (kept alive: the calls are asynchronous)
+    for i in (0, 2):
+        _lib.check(_lib.lib().mms_embed_backward_f32(h.ptr, p(g[i]), p(g[i + 1]), p(W2), p(b2), M, D, V))
+    torch.cuda.synchronize()
+    assert np.abs(dW - W2.cpu().numpy()).max() <= 1e-5 * np.abs(dW).max()
+    assert np.abs(db - b2.cpu().numpy()).max() <= 1e-5 * np.abs(db).max()
+    # dW == NULL (param_propagate_down false) still sums the bias gradient; dbias == NULL alone is fine too
+    L = _lib.lib()
+    b3 = dev(zb)
+    _lib.check(L.mms_embed_backward_pair_f32(h.ptr, p(g[0]), p(g[1]), M, p(g[2]), p(g[3]), M, p(None), p(b3), D, V))
+    torch.cuda.synchronize()
+    assert np.abs(b3.cpu().numpy() - db).max() <= 1e-5 * np.abs(db).max()
+    # an id outside [0, V): skipped, and reported by mms_check_faults like the per-layer kernels
+    bad = idx0.copy(); bad[17] = V + 5; bad[99] = -1
+    W4, b4, gbad = dev(zW), dev(zb), dev(bad)
+    _lib.check(L.mms_embed_backward_pair_f32(h.ptr, p(gbad), p(g[1]), M, p(None), p(None), 0, p(W4), p(b4), D, V))
+    with pytest.raises(_lib.MMSError):
+        h.check_faults()
+    rW, _ = oracle(bad, d0, None, None, zW, zb, V)
+    assert np.abs(W4.cpu().numpy() - rW).max() <= 1e-5 * np.abs(rW).max()
+
+
+def test_net_step_with_grouped_scatter_equals_per_layer_scatter():
+    import mms_answer_selection_b200 as mms
+    from mms_answer_selection_b200 import synth
+    N, L, D, mc, V = 300, 40, 300, 4, 3000
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    outs = []
+    for grouped in (False, True):
+        net = mms.MMSNet(N, L, D, mc, V, grouped_scatter=grouped)
+        net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
+        net.set_upstream_gradient(d["dS"])
+        net.capture(with_loss=True, clear_diffs=True)          # graph with the plan on its side branch
+        for _ in range(2):
+            net.replay()
+        torch.cuda.synchronize()
+        outs.append([b.cpu_diff() for b in net.params()])
+    for a, b in zip(*outs):
+        assert np.abs(a - b).max() <= 1e-5 * max(np.abs(a).max(), 1e-30)

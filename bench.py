@@ -221,7 +221,7 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------- our arm
-def build_net(cfg, world, rank, keep_embed_tops=False):
+def build_net(cfg, world, rank, keep_embed_tops=False, grouped_scatter=True):
     """MMSNet over this rank's slice of the GLOBAL synthetic batch (same seed on every rank: the global batch is
     identical everywhere, rank r takes pairs [r N/n, (r+1) N/n)).  Each worker normalises its loss by ITS pair count, as
     every Caffe worker does: dS of the global batch times `world`; the exchange's 1/n (parallel.cpp:377) turns the
@@ -233,7 +233,7 @@ def build_net(cfg, world, rank, keep_embed_tops=False):
     sl = slice(rank * N, (rank + 1) * N)
     # keep_embed_tops=False: q / a leave the gather as the TF32 operand copy the contractions read and nothing else
     # (MMS_OPT_STAGE_ONLY); the fp32 tops a Caffe net would expose are not written -- nothing on this path reads them
-    net = mms.MMSNet(N, L, D, mc, V, keep_embed_tops=keep_embed_tops)
+    net = mms.MMSNet(N, L, D, mc, V, keep_embed_tops=keep_embed_tops, grouped_scatter=grouped_scatter)
     net.set_params(full["W"], full["b"], full["M"], full["B"])
     net.set_inputs(full["idx_q"][sl], full["idx_a"][sl])
     net.set_upstream_gradient(full["dS"][sl] * world)
@@ -306,7 +306,8 @@ def main_ours(args):
     cfg = workload_config(wl, world)
     N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
 
-    net, full, sl = build_net(cfg, world, rank, keep_embed_tops=args.embed_tops == "fp32")
+    net, full, sl = build_net(cfg, world, rank, keep_embed_tops=args.embed_tops == "fp32",
+                              grouped_scatter=args.scatter == "grouped")
     exch, exch_note = None, "none"
     if world > 1:
         exch, exch_note = make_exchange(net.params(), args.exchange)
@@ -929,6 +930,8 @@ def hbm_kernel_table(prof, steps, cfg, peaks, keep_embed_tops=True):
         # (keep_embed_tops=False: the fp32 row is not written)
         "embed_forward_vec": rows * (4 + (8 if keep_embed_tops else 4) * D + 4 * Dp),
         "embed_backward_runs": rows * (4 + 4 * D) + rows * 8 * D,      # id + dtop in, <= one RMW of the dW row
+        # grouped form: the gradient rows once; the touched table rows (<= one per token, not counted) on top
+        "embed_backward_short_runs+embed_backward_long_chunks": rows * (4 + 4 * D),
         "tf32_round_kernel": mc * D * 4 * (D + Dp),                    # only M: q and a arrive staged by the gather
         "sum_kernel": 2 * 4 * N * mc * L * L,                          # loss = dot(S, dS)
         "bias_grad_kernel": 4 * N * mc * L * L,                        # dB += sum_n dS[n]
@@ -936,8 +939,10 @@ def hbm_kernel_table(prof, steps, cfg, peaks, keep_embed_tops=True):
     peak = peaks.get("hbm_gbs", 6650.0)
     out = {}
     for k, b in alg.items():
-        if k in prof and prof[k][1] > 0:
-            gbs = b / (prof[k][1] / steps / 1e3) / 1e9
+        parts = k.split("+")
+        if all(p_ in prof and prof[p_][1] > 0 for p_ in parts):
+            ms = sum(prof[p_][1] for p_ in parts)
+            gbs = b / (ms / steps / 1e3) / 1e9
             out[k] = {"algorithmic_bytes_per_step": int(b), "achieved_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 3)}
     out["peak_gbs"] = peak
     return out
@@ -995,6 +1000,8 @@ def main():
     ap.add_argument("--try-multicast", action="store_true", help="comm: also time the symmetric-memory / multimem variant")
     ap.add_argument("--embed-tops", default="staged", choices=["staged", "fp32"],
                     help="staged: the gather writes only the TF32 operand copy SimCross reads; fp32: also the fp32 tops")
+    ap.add_argument("--scatter", default="grouped", choices=["grouped", "per-layer"],
+                    help="grouped: both Embed backwards as one scatter-add with rows grouped by id; per-layer: two atomic kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

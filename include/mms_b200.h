@@ -155,7 +155,8 @@ int mms_embed_backward_f64(mms_handle_t h, const double* idx, const double* dtop
  * mms_embed_plan_pair does the grouping alone -- it needs the ids only, so a net can run it beside the forward pass; a
  * following mms_embed_backward_pair on the same handle with the same id blobs and sizes uses it (the caller vouches that
  * the ids did not change in between), any other call groups the rows itself.  Shapes the grouped kernels do not take
- * (D % 4 != 0, D > 512, unaligned blobs) and handles with MMS_OPT_EMBED_DETERMINISTIC run mms_embed_backward per blob. */
+ * (D % 4 != 0, D > 512, unaligned blobs), batches below 32 768 token rows (launch-bound: two launches beat six) and
+ * handles with MMS_OPT_EMBED_DETERMINISTIC run mms_embed_backward per blob. */
 int mms_embed_plan_pair_f32(mms_handle_t h, const float* idx0, long long M0, const float* idx1, long long M1, int V);
 int mms_embed_backward_pair_f32(mms_handle_t h, const float* idx0, const float* dtop0, long long M0,
                                 const float* idx1, const float* dtop1, long long M1, float* dW, float* dbias,

@@ -18,8 +18,9 @@
 //     5  one CTA per long chunk: eight warps sum 32 rows each, shared-memory reduction, one set of atomics per chunk
 //   dbias rides along: per-warp column sums -> shared memory -> one set of atomics per CTA.
 //
-// Float only (the double nets use the per-layer kernels); D % 4 == 0, D <= 512, 16-byte aligned blobs -- anything else
-// runs the per-layer kernels of embed.cu, as does a handle with MMS_OPT_EMBED_DETERMINISTIC (embed_det.cu).
+// Float only (the double nets use the per-layer kernels); D % 4 == 0, D <= 512, 16-byte aligned blobs, at least 32 768
+// token rows (smaller batches are launch-bound: two launches beat six) -- anything else runs the per-layer kernels of
+// embed.cu, as does a handle with MMS_OPT_EMBED_DETERMINISTIC (embed_det.cu).
 #include <cub/cub.cuh>
 
 #include "mms_common.cuh"
@@ -30,6 +31,11 @@ constexpr int kLongRun = 128;      // runs up to this many rows are summed by on
 constexpr int kChunkRows = 256;    // rows of a long run per CTA (kWarps x 32: a lane holds one row number of its warp)
 constexpr int kWarps = 8;
 constexpr int kBatch = 8;          // short runs a warp describes at once
+constexpr long long kMinRows = 32768;   // below this the step is launch-bound: two per-layer launches beat plan + reduce
+
+inline bool grouped_shape(const mms_context* ctx, long long Mt, int D) {
+  return !ctx->embed_deterministic && Mt >= kMinRows && D % 4 == 0 && D <= 512;
+}
 
 struct SortedPlan {
   const void* idx0 = nullptr; const void* idx1 = nullptr;
@@ -364,6 +370,7 @@ int mms_embed_plan_pair_impl(mms_context* ctx, const float* idx0, long long M0, 
   MMS_REQUIRE(M0 >= 0 && M1 >= 0 && V > 0, MMS_E_INVALID, "bad size");
   MMS_REQUIRE((idx0 || M0 == 0) && (idx1 || M1 == 0), MMS_E_INVALID, "null pointer");
   if (M0 + M1 == 0) return 0;
+  if (ctx->embed_deterministic || M0 + M1 < kMinRows) return 0;      // the backward will take the per-layer kernels
   return build_plan(ctx, idx0, M0, idx1, M1, V);
 }
 
@@ -372,7 +379,7 @@ int mms_embed_backward_pair_impl(mms_context* ctx, const float* idx0, const floa
   MMS_REQUIRE(M0 >= 0 && M1 >= 0 && D > 0 && V > 0, MMS_E_INVALID, "bad size");
   if (M0 + M1 == 0 || (!dW && !dbias)) return 0;
   MMS_REQUIRE((M0 == 0 || (idx0 && dtop0)) && (M1 == 0 || (idx1 && dtop1)), MMS_E_INVALID, "null pointer");
-  const bool grouped = !ctx->embed_deterministic && D % 4 == 0 && D <= 512 && (M0 == 0 || aligned16(dtop0)) &&
+  const bool grouped = grouped_shape(ctx, M0 + M1, D) && (M0 == 0 || aligned16(dtop0)) &&
                        (M1 == 0 || aligned16(dtop1)) && (!dW || aligned16(dW)) && (!dbias || aligned16(dbias));
   if (!grouped) {      // the per-layer kernels, one blob after the other (the deterministic form needs that order)
     if (M0) MMS_TRY(mms_embed_backward_impl<float>(ctx, idx0, dtop0, dW, dbias, M0, D, V));

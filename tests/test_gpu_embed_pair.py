@@ -58,13 +58,14 @@ def run_pair(h, idx0, d0, idx1, d1, W0, b0, D, V, plan_first=False):
 
 
 @pytest.mark.parametrize("M0,M1,D,V,kind", [
-    (4000, 4000, 300, 5000, "padded"),      # the QA net's shape in small
-    (777, 1233, 300, 50, "uniform"),        # every id many times, ragged sizes
-    (20000, 9000, 300, 3000, "hot"),        # runs far beyond one chunk
-    (3000, 0, 300, 2000, "padded"),         # one blob only
-    (1500, 1700, 52, 400, "uniform"),       # one 16-byte group per lane, partly filled
-    (900, 1100, 512, 300, "padded"),        # the widest row the grouped kernels take
-    (5, 3, 300, 100000, "uniform"),         # almost nothing
+    (20000, 20000, 300, 5000, "padded"),    # the QA net's shape in small
+    (17777, 21233, 300, 50, "uniform"),     # every id hundreds of times, ragged sizes
+    (30000, 9000, 300, 3000, "hot"),        # runs far beyond one chunk
+    (33000, 0, 300, 2000, "padded"),        # one blob only
+    (31500, 11700, 52, 400, "uniform"),     # one 16-byte group per lane, partly filled
+    (19000, 21000, 512, 300, "padded"),     # the widest row the grouped kernels take
+    (16385, 16383, 300, 100000, "uniform"), # just at the row threshold, almost every id once
+    (5, 3, 300, 1000, "uniform"),           # below it: the per-layer kernels
 ])
 @pytest.mark.parametrize("plan_first", [False, True])
 def test_pair_backward_matches_exact_scatter_add(M0, M1, D, V, kind, plan_first):
@@ -86,7 +87,7 @@ def test_pair_backward_matches_exact_scatter_add(M0, M1, D, V, kind, plan_first)
 
 
 def test_pair_backward_agrees_with_the_two_per_layer_calls_and_flags_bad_ids():
-    M, D, V = 6000, 300, 4000
+    M, D, V = 24000, 300, 4000
     rng = np.random.default_rng(3)
     idx0 = make_ids(rng, M, V, "padded").astype(np.float32)
     idx1 = make_ids(rng, M, V, "padded").astype(np.float32)
@@ -122,7 +123,7 @@ def test_pair_backward_agrees_with_the_two_per_layer_calls_and_flags_bad_ids():
 def test_net_step_with_grouped_scatter_equals_per_layer_scatter():
     import mms_answer_selection_b200 as mms
     from mms_answer_selection_b200 import synth
-    N, L, D, mc, V = 300, 40, 300, 4, 3000
+    N, L, D, mc, V = 450, 40, 300, 4, 3000           # 36 000 token rows: above the grouped kernels' threshold
     d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
     outs = []
     for grouped in (False, True):
@@ -130,9 +131,11 @@ def test_net_step_with_grouped_scatter_equals_per_layer_scatter():
         net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
         net.set_upstream_gradient(d["dS"])
         net.capture(with_loss=True, clear_diffs=True)          # graph with the plan on its side branch
+        net.embed_q.handle.profile_enable(True)
         for _ in range(2):
             net.replay()
         torch.cuda.synchronize()
+        assert ("embed_backward_short_runs" in net.embed_q.handle.profile_report()) == grouped
         outs.append([b.cpu_diff() for b in net.params()])
     for a, b in zip(*outs):
         assert np.abs(a - b).max() <= 1e-5 * max(np.abs(a).max(), 1e-30)

@@ -733,6 +733,19 @@ def embed_backward_modes(flush):
         fn = lambda: _lib.check(_lib.lib().mms_embed_backward_f32(h.ptr, p(idx), p(g), p(dW), p(db), M, D, V))
         ms = _time_ms(fn, 10, flush, 1)
         out[name] = {"ms": ms, "algorithmic_gbs": (M * (4 + 4 * D) + M * 8 * D) / (ms / 1e3) / 1e9}
+    # both layers of the step (q: sentences of 3-20 tokens, a: 5-40) as one scatter-add grouped by id, plan included
+    h.set_option(_lib.MMS_OPT_EMBED_DETERMINISTIC, 0)
+    idx_q = torch.from_numpy(synth.make_indices(rng, c3["N"], c3["L"], V, 3, 20).reshape(-1)).cuda()
+    gq = torch.randn((M, D), device="cuda") * 1e-6
+    L_ = _lib.lib()
+    pair = lambda: _lib.check(L_.mms_embed_backward_pair_f32(h.ptr, p(idx_q), p(gq), M, p(idx), p(g), M, p(dW), p(db), D, V))
+    plan = lambda: _lib.check(L_.mms_embed_plan_pair_f32(h.ptr, p(idx_q), M, p(idx), M, V))
+    two = lambda: (_lib.check(L_.mms_embed_backward_f32(h.ptr, p(idx_q), p(gq), p(dW), p(db), M, D, V)),
+                   _lib.check(L_.mms_embed_backward_f32(h.ptr, p(idx), p(g), p(dW), p(db), M, D, V)))
+    ms_pair, ms_plan, ms_two = _time_ms(pair, 10, flush, 1), _time_ms(plan, 10, flush, 1), _time_ms(two, 10, flush, 1)
+    out["both_layers"] = {"rows": 2 * M, "per_layer_atomic_ms": ms_two, "grouped_by_id_ms": ms_pair,
+                          "of_which_plan_ms": ms_plan,
+                          "note": "grouped_by_id_ms includes the id grouping; MMSNet runs that part on a side stream beside the forward"}
     return out
 
 

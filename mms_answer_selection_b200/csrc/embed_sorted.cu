@@ -324,10 +324,11 @@ int build_plan(mms_context* ctx, const float* idx0, long long M0, const float* i
   { MmsKernelScope ks_(ctx, "embed_plan_count");
     plan_count_kernel<<<grid, 256, 0, ctx->stream>>>(idx0, idx1, M0, Mt, V, p->count, ctx->fault_flag); }
   MMS_LAUNCH_CHECK();
+  const int gs = mms_ceil_div(V, kScanBins);
+  { MmsKernelScope ks_(ctx, "embed_plan_totals");
+    plan_totals_kernel<<<gs, kScanThreads, 0, ctx->stream>>>(p->count, p->totals, V); }
+  MMS_LAUNCH_CHECK();
   { MmsKernelScope ks_(ctx, "embed_plan_scan");
-    const int gs = mms_ceil_div(V, kScanBins);
-    plan_totals_kernel<<<gs, kScanThreads, 0, ctx->stream>>>(p->count, p->totals, V);
-    MMS_LAUNCH_CHECK();
     plan_scan_kernel<<<gs, kScanThreads, 0, ctx->stream>>>(p->count, p->totals, p->start, p->cursor, p->run_id, p->chunks,
                                                            p->counters, V); }
   MMS_LAUNCH_CHECK();

@@ -51,7 +51,7 @@ for stage in "$@"; do
       ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$wl.csv \
         python tools/trace_step.py $wl notrace > gpurun_out/ncu_$wl.log 2>&1
       echo "launch list $wl rc=$?"
-      ncu --set full --clock-control none --import-source on -k regex:"simcross2|tc_gemm|embed_|tf32_round" -s 12 -c 12 \
+      ncu --set full --clock-control none --import-source on -k regex:"simcross2|tc_gemm|embed_|tf32_round|short_runs|long_chunks|plan_" -s 13 -c 13 \
         -o gpurun_out/prof_${wl}_fused -f python tools/trace_step.py $wl notrace > gpurun_out/ncu_${wl}_full.log 2>&1
       echo "full $wl rc=$?"; ls -la gpurun_out/prof_${wl}_fused.ncu-rep ;;
     ncu-sentenc)

@@ -10,7 +10,7 @@ from mms_answer_selection_b200 import synth
 cfg = synth.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
 N, L, D, mc, V = cfg["N"], cfg["L"], cfg["D"], cfg["mc"], cfg["V"]
 d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
-net = mms.MMSNet(N, L, D, mc, V)
+net = mms.MMSNet(N, L, D, mc, V, keep_embed_tops=False)      # the configuration bench.py times
 net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"]); net.set_upstream_gradient(d["dS"])
 for i in range(3):
     sys.stderr.write("---- step %d\n" % i)

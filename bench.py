@@ -326,11 +326,13 @@ def main_ours(args):
     if in_graph:
         graph = net.capture_exchange_step(exch, with_loss=True, clear_diffs=True)
         launches_per_step = (count_launches() - l0) // 3                      # 2 warm-up passes + the capture
-        graph_host = net.capture_exchange_step(exch, with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a))
+        graph_host = net.capture_exchange_step(exch, with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a),
+                                               prefetch_inputs=not args.no_input_prefetch)
     else:
         net.capture(with_loss=True, clear_diffs=True)
         launches_per_step = (count_launches() - l0) // 3 + (1 if exch else 0)
-        net.capture(with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a))  # + H2D / D2H nodes for the e2e step
+        net.capture(with_loss=True, clear_diffs=True, host_inputs=(host_q, host_a),      # + H2D / D2H nodes for the e2e step
+                    prefetch_inputs=not args.no_input_prefetch)
 
     def device_step():
         if in_graph:
@@ -448,7 +450,13 @@ def main_ours(args):
                                "TF32 operand copy only (MMS_OPT_STAGE_ONLY; --embed-tops fp32 also writes the fp32 tops)"),
                 "algorithmic_tflops_per_gpu": N * flops_per_pair(L, D, mc) / (total_ms / args.steps / 1e3) / 1e12},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": int(host_q.numel() * 4 + host_a.numel() * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(host_q.numel() * 4 + host_a.numel() * 4), "d2h_bytes_per_step": 4,
+                "note": ("one graph launch + one stream synchronisation per step; the pinned ids are copied H2D every step "
+                         + ("in front of the step's kernels" if args.no_input_prefetch else
+                            "beside the step's kernels into staging buffers and handed to the id blobs at the end of the step "
+                            "(input double buffering: step k computes on the ids step k-1 fetched; --no-input-prefetch puts "
+                            "the copy in front of the kernels)")
+                         + "; the loss is read back D2H every step")},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -1015,6 +1023,8 @@ def main():
                     help="staged: the gather writes only the TF32 operand copy SimCross reads; fp32: also the fp32 tops")
     ap.add_argument("--scatter", default="grouped", choices=["grouped", "per-layer"],
                     help="grouped: both Embed backwards as one scatter-add with rows grouped by id; per-layer: two atomic kernels")
+    ap.add_argument("--no-input-prefetch", action="store_true",
+                    help="e2e: copy the step's ids H2D in front of its kernels instead of beside the previous step's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

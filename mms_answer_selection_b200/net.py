@@ -277,7 +277,8 @@ class MMSNet(object):
                                momentum=solver.momentum, delta=solver.delta, weight_decay=solver.weight_decay,
                                iter_size=solver.iter_size, bucket_blobs=(first, last), channel=channel, clear_diffs=True)
 
-    def capture_exchange_step(self, exch, with_loss=True, clear_diffs=True, solver=None, host_inputs=None, overlap=True):
+    def capture_exchange_step(self, exch, with_loss=True, clear_diffs=True, solver=None, host_inputs=None, overlap=True,
+                              prefetch_inputs=False):
         """Records ForwardBackwardExchange as ONE CUDA graph (the exchange kernels keep their epoch in device memory,
         so a replay is a new exchange).  Two eager passes first: they size the workspaces, fill the tensor-map cache
         and, with ``solver``, allocate the history -- and they are REAL steps, so every rank must call this the same
@@ -295,9 +296,9 @@ class MMSNet(object):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                if host_inputs is not None:
-                    self.set_inputs_from_pinned(*host_inputs)
+                ins = self._inputs_into_graph(host_inputs, prefetch_inputs) if host_inputs is not None else None
                 self.ForwardBackwardExchange(exch, with_loss, clear_diffs, solver, overlap)
+                self._inputs_handover(ins)
                 if host_inputs is not None and with_loss:
                     if getattr(self, "_host_loss", None) is None:
                         self._host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -343,11 +344,37 @@ class MMSNet(object):
         if solver is not None:
             solver.iter += 1
 
-    def capture(self, with_loss=True, clear_diffs=True, host_inputs=None):
+    def _inputs_into_graph(self, host_inputs, prefetch):
+        """Called inside a capture, before the step: the H2D copies of the pinned id tensors.  ``prefetch``: they go into
+        staging buffers on a side stream BESIDE the step's kernels (the ids are the first thing a step needs, so a copy in
+        front of it is fully exposed) and `_inputs_handover` moves them into the id blobs at the end of the step -- every
+        replay computes on the ids its predecessor fetched and fetches the next ones (input double buffering: the caller
+        refills the pinned tensors with batch k+1 before replay k; prime with set_inputs)."""
+        host_q, host_a = host_inputs
+        assert host_q.is_pinned() and host_a.is_pinned()
+        if not prefetch:
+            self.set_inputs_from_pinned(host_q, host_a)
+            return None
+        if getattr(self, "_in_stage", None) is None:
+            self._in_stage = (torch.empty_like(self.idx_q.data), torch.empty_like(self.idx_a.data))
+            self._in_stream = torch.cuda.Stream()
+        self._in_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._in_stream):
+            self._in_stage[0].copy_(host_q.view_as(self._in_stage[0]), non_blocking=True)
+            self._in_stage[1].copy_(host_a.view_as(self._in_stage[1]), non_blocking=True)
+        return self._in_stream
+
+    def _inputs_handover(self, in_stream):
+        if in_stream is not None:
+            torch.cuda.current_stream().wait_stream(in_stream)
+            self.idx_q.data.copy_(self._in_stage[0])
+            self.idx_a.data.copy_(self._in_stage[1])
+
+    def capture(self, with_loss=True, clear_diffs=True, host_inputs=None, prefetch_inputs=False):
         """Records one step.  With `host_inputs=(host_q, host_a)` (pinned tensors) a second graph is recorded
         that also contains the H2D copies of the two id tensors and the D2H copy of the loss scalar into a pinned
         buffer, so that an end-to-end step is ONE graph launch and one stream synchronisation
-        (`replay_from_host`)."""
+        (`replay_from_host`).  `prefetch_inputs`: see `_inputs_into_graph`."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         self.sim.defer_loss_ = True
@@ -373,8 +400,9 @@ class MMSNet(object):
             try:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, stream=side):
-                    self.set_inputs_from_pinned(host_q, host_a)
+                    ins = self._inputs_into_graph(host_inputs, prefetch_inputs)
                     self.ForwardBackwardConcurrent(with_loss, clear_diffs)
+                    self._inputs_handover(ins)
                     if with_loss:
                         self._host_loss.copy_(self.sim.loss_dev_[0], non_blocking=True)
             finally:

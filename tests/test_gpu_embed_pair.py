@@ -141,3 +141,33 @@ def test_net_step_with_grouped_scatter_equals_per_layer_scatter():
         assert ("embed_backward_short_runs" in net.embed_q.handle.profile_report()) == grouped
     for a, b in zip(*outs):
         assert np.abs(a - b).max() <= 1e-5 * max(np.abs(a).max(), 1e-30)
+
+
+def test_prefetched_inputs_arrive_one_replay_later():
+    """capture(host_inputs, prefetch_inputs=True): replay k computes on the ids replay k-1 fetched and fetches the next."""
+    import mms_answer_selection_b200 as mms
+    from mms_answer_selection_b200 import synth
+    N, L, D, mc, V = 64, 40, 300, 4, 2000
+    d1 = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V, seed=1)
+    d2 = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V, seed=2)
+    losses = {}
+    for name, d in (("one", d1), ("two", d2)):                     # plain steps on each batch
+        net = mms.MMSNet(N, L, D, mc, V)
+        net.set_params(d1["W"], d1["b"], d1["M"], d1["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
+        net.set_upstream_gradient(d1["dS"])
+        net.ClearParamDiffs(); losses[name] = float(net.ForwardBackward())
+    net = mms.MMSNet(N, L, D, mc, V)
+    net.set_params(d1["W"], d1["b"], d1["M"], d1["B"]); net.set_inputs(d1["idx_q"], d1["idx_a"])
+    net.set_upstream_gradient(d1["dS"])
+    hq = torch.from_numpy(d2["idx_q"].copy()).pin_memory(); ha = torch.from_numpy(d2["idx_a"].copy()).pin_memory()
+    net.capture(with_loss=True, clear_diffs=True, host_inputs=(hq, ha), prefetch_inputs=True)
+    net.set_inputs(d1["idx_q"], d1["idx_a"])                       # prime: the first replay computes on batch one ...
+    torch.cuda.synchronize()
+    first = net.replay_from_host()                                 # ... and fetches batch two
+    hq.copy_(torch.from_numpy(d1["idx_q"])); ha.copy_(torch.from_numpy(d1["idx_a"]))
+    second = net.replay_from_host()                                # computes on batch two, fetches batch one
+    third = net.replay_from_host()
+    assert abs(first - losses["one"]) <= 1e-5 * abs(losses["one"])
+    assert abs(second - losses["two"]) <= 1e-5 * abs(losses["two"])
+    assert abs(third - losses["one"]) <= 1e-5 * abs(losses["one"])
+    assert abs(losses["one"] - losses["two"]) > 1e-3 * abs(losses["one"])       # the two batches do differ

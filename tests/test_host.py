@@ -64,7 +64,7 @@ def test_committed_bench_lines_follow_the_contract():
     import json
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for name in ("r01_bench_c2_n1.json", "r01_bench_c3_n4.json"):
+    for name in ("r01_bench_c2_n1.json", "r01_bench_c3_n4.json", "r02_bench_c3_n1.json", "r02_bench_c3_n8.json"):
         d = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                   "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
@@ -83,3 +83,11 @@ def test_committed_bench_lines_follow_the_contract():
     ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_ref_c2.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["cpu_baseline"]["kind"] in ("reference", "port")
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]
+    # round 2: both arms print the SAME config object (the driver compares them), at every N
+    for n in (1, 2, 4, 8):
+        ours = json.loads(open(os.path.join(root, "profiles", "r02_bench_c3_n%d.json" % n)).read().strip().splitlines()[-1])
+        ref = json.loads(open(os.path.join(root, "profiles", "r02_bench_ref_c3_n%d.json" % n)).read().strip().splitlines()[-1])
+        assert ours["config"] == ref["config"] and ours["metric"] == ref["metric"] and ours["unit"] == ref["unit"], n
+        assert ours["scaling"] == ref["scaling"] == "strong" and ours["n_gpus"] == ref["n_gpus"] == n
+        if n > 1:
+            assert ours["parity"]["ok"] is True and ours["parity"]["replicas_bit_identical"] is True

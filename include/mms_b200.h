@@ -157,6 +157,11 @@ int mms_embed_backward_f64(mms_handle_t h, const double* idx, const double* dtop
  * the ids did not change in between), any other call groups the rows itself.  Shapes the grouped kernels do not take
  * (D % 4 != 0, D > 512, unaligned blobs), batches below 32 768 token rows (launch-bound: two launches beat six) and
  * handles with MMS_OPT_EMBED_DETERMINISTIC run mms_embed_backward per blob. */
+/* Optional, SimCross mode 2, float, MMS_MATH_TF32: rounds M to TF32 into the handle's workspace AHEAD of the next
+ * mms_simcross_forward on this handle (which then skips that pass when M is the same pointer and unchanged): M does not
+ * depend on the step's inputs, so a net runs this on a side stream beside the Embed gathers.  No reference counterpart
+ * (sim_cross_layer.cpp:146-160 reads M in place).  A no-op until the workspace exists (first forward). */
+int mms_simcross_prepare_f32(mms_handle_t h, const float* M, int D, int mc);
 int mms_embed_plan_pair_f32(mms_handle_t h, const float* idx0, long long M0, const float* idx1, long long M1, int V);
 int mms_embed_backward_pair_f32(mms_handle_t h, const float* idx0, const float* dtop0, long long M0,
                                 const float* idx1, const float* dtop1, long long M1, float* dW, float* dbias,

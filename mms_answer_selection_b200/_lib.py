@@ -13,6 +13,7 @@ c_f, c_d = ctypes.c_float, ctypes.c_double
 MMS_MATH_TF32, MMS_MATH_FP32 = 0, 1
 MMS_OPT_MATH, MMS_OPT_PRL_GE, MMS_OPT_SCRATCH_BYTES, MMS_OPT_EMBED_DETERMINISTIC = 1, 2, 3, 4
 MMS_OPT_REUSE_FORWARD, MMS_OPT_CONCURRENCY, MMS_OPT_STAGE_TF32, MMS_OPT_STAGE_ONLY = 5, 6, 7, 8
+EMBED_GROUPED_MIN_ROWS = 32768      # csrc/embed_sorted.cu kMinRows: below it mms_embed_backward_pair runs the per-layer kernels
 MMS_E_INVALID, MMS_E_UNSUPPORTED, MMS_E_NOMEM, MMS_E_FAULT = -1, -2, -3, -4
 MMS_EXCHANGE_OPT_CTAS, MMS_EXCHANGE_OPT_TIMEOUT_MS, MMS_EXCHANGE_OPT_MULTICAST = 1, 2, 3
 MMS_EXCHANGE_MAX_WORLD, MMS_EXCHANGE_CHANNELS, MMS_EXCHANGE_IPC_BYTES = 8, 4, 64
@@ -122,6 +123,7 @@ def lib():
         L.mms_rerank_topk_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
         L.mms_rerank_topk_prepared_f32.argtypes = [c_p] * 7 + [c_int, c_ll, c_int, c_int, c_int, c_ll]
         L.mms_topk_merge_f32.argtypes = [c_p, c_p, c_p, c_ll, c_ll, c_p, c_p, c_int, c_int]
+        L.mms_simcross_prepare_f32.argtypes = [c_p, c_p, c_int, c_int]
         L.mms_embed_plan_pair_f32.argtypes = [c_p, c_p, c_ll, c_p, c_ll, c_int]
         L.mms_embed_backward_pair_f32.argtypes = [c_p, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_int, c_int]
         L.mms_dropout_mask.argtypes = [c_p, c_p, c_ll, ctypes.c_ulonglong]

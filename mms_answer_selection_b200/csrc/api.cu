@@ -49,6 +49,7 @@ bool mms_unchanged_since(unsigned long long clock, const void* p, size_t bytes) 
 
 int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
   ctx->fwd_cache.valid = false;        // whoever asks for the scratch buffer is about to overwrite it
+  ctx->m_prepared.valid = false;       // (mms_tc_simcross2_forward reads this flag BEFORE it asks)
   ctx->sent_cache.valid = false;
   ctx->simmat_cache.valid = false;
   ctx->dm_pending.valid = false;
@@ -508,6 +509,11 @@ int mms_embed_backward_pair_f32(mms_handle_t h, const float* idx0, const float* 
 MMS_DEFINE_TYPED(float, f32)
 MMS_DEFINE_TYPED(double, f64)
 
+int mms_simcross_prepare_f32(mms_handle_t h, const float* Mw, int D, int mc) {
+  H;
+  MMS_REQUIRE(Mw && D > 0 && mc > 0, MMS_E_INVALID, "bad argument");
+  return mms_tc_simcross2_prepare(h, Mw, D, mc);
+}
 int mms_simcross_backward_bottoms_f32(mms_handle_t h, const float* q, const float* a, const float* Mw, const float* dS,
                                       float* dq, float* da, int N, int Lq, int La, int D, int mc) {
   H;
@@ -520,8 +526,17 @@ int mms_simcross_backward_params_f32(mms_handle_t h, const float* dS, float* dM,
                                      int mc) {
   H;
   MMS_REQUIRE(dS && dM, MMS_E_INVALID, "null pointer");
-  MMS_TRY(mms_tc_simcross2_backward_params(h, dM, N, Lq, La, D, mc));
-  if (dB) MMS_TRY(mms_simcross2_bias_grad<float>(h, dS, dB, N, Lq, La, mc));
+  // dB depends on dS only: with MMS_OPT_CONCURRENCY it is reduced on a private stream beside the dM contraction
+  const bool side_bias = dB && h->concurrency;
+  if (side_bias) {
+    MMS_TRY(mms_fork(h, 1));
+    MmsStreamSwitch sw(h, 1);
+    MMS_TRY(mms_simcross2_bias_grad<float>(h, dS, dB, N, Lq, La, mc));
+  }
+  const int rc = mms_tc_simcross2_backward_params(h, dM, N, Lq, La, D, mc);
+  if (side_bias) MMS_TRY(mms_join(h, 1));
+  MMS_TRY(rc);
+  if (dB && !side_bias) MMS_TRY(mms_simcross2_bias_grad<float>(h, dS, dB, N, Lq, La, mc));
   return 0;
 }
 

@@ -11,6 +11,10 @@ struct mms_context {
   int math = MMS_MATH_TF32;
   int prl_ge = 0;
   int embed_deterministic = 0;
+  struct MPrepared {             // mms_simcross_prepare: M already rounded at the head of the scratch buffer
+    bool valid = false; const void* M = nullptr; const void* at = nullptr; int D = 0, mc = 0;
+    unsigned long long clock = 0;
+  } m_prepared;
   void* embed_plan = nullptr;    // embed_sorted.cu: token rows grouped by id (mms_embed_plan_pair)
   size_t scratch_cap = (size_t)4 << 30;
   void* scratch = nullptr;       // grows on demand, reused across calls
@@ -188,6 +192,7 @@ int mms_embed_forward_impl(mms_context*, const T* idx, const T* W, const T* bias
 template <typename T>
 int mms_embed_backward_impl(mms_context*, const T* idx, const T* dtop, T* dW, T* dbias,
                             long long M, int D, int V);
+int mms_tc_simcross2_prepare(mms_context* ctx, const float* Mw, int D, int mc);
 void mms_embed_plan_destroy(mms_context* ctx);
 int mms_embed_plan_pair_impl(mms_context* ctx, const float* idx0, long long M0, const float* idx1, long long M1, int V);
 int mms_embed_backward_pair_impl(mms_context* ctx, const float* idx0, const float* dtop0, long long M0, const float* idx1,

@@ -320,6 +320,14 @@ class SimCrossLayer(Layer):
                    _p(top[0]), _p(top[0], True), _p(n0), _p(n1), _p(bottom[0], True), _p(bottom[1], True),
                    _p(Mw, True), _p(B, True), N, Lq, La, D, mc, int(propagate_down[0]), int(propagate_down[1]))
 
+    def Prepare(self, bottom):
+        """Rounds M ahead of the next Forward (mms_simcross_prepare): callable on a side stream beside the producers of the
+        bottoms.  No-op for the other modes / double."""
+        if self.dist_mode_ == 2 and self.dtype == np.float32:
+            self._bind_stream()
+            N, Lq, La, D, mc = self._dims(bottom)
+            check(lib().mms_simcross_prepare_f32(self.handle.ptr, _p(self.blobs_[0]), D, mc))
+
     # -- the same backward in two calls (include/mms_b200.h: mms_simcross_backward_bottoms / _params) -------------
     def BackwardBottoms(self, top, bottom):
         """dq, da only; the weight gradient follows in BackwardParams.  Falls back to the whole Backward when the

@@ -19,6 +19,9 @@ from .blob import Blob
 from .layers import EmbedLayer, LayerParameter, SimCrossLayer
 
 
+from . import _lib
+
+
 class MMSNet(object):
     def __init__(self, N, L=40, D=300, mc=4, V=60002, dtype=np.float32, device="cuda", bias_term=True,
                  embed_bias=True, math=None, stage_tf32=True, deterministic=False, keep_embed_tops=True,
@@ -143,6 +146,17 @@ class MMSNet(object):
         self.embed_q.Backward([self.q], [False], [self.idx_q])
         self.embed_a.Backward([self.a], [False], [self.idx_a])
 
+    def _prepare_weights(self, main):
+        """M rounded for the coming forward on a stream of its own (it does not depend on the inputs); returns the stream
+        the caller joins in front of SimCross forward."""
+        if getattr(self, "_prep_stream", None) is None:
+            self._prep_stream = torch.cuda.Stream()
+        sp = self._prep_stream
+        sp.wait_stream(main)
+        with torch.cuda.stream(sp):
+            self.sim.Prepare([self.q, self.a])
+        return sp
+
     def _plan_scatter(self, side):
         """The id grouping of this step's scatter-add on ``side`` (it depends on the inputs only)."""
         if self.grouped_scatter:
@@ -158,9 +172,10 @@ class MMSNet(object):
         r"""The same step with its independent pieces on forked streams (the reference's Net runs layers one
         after the other on the legacy stream, net.cpp:535-591; the data dependencies are all that matters):
 
-            ClearParamDiffs ----------------------------\
-            Embed(q) --\                                 +--> SimCross bwd --> Embed(q) bwd --\
-            Embed(a) ---+--> SimCross fwd (+ loss dot) --/                \--> Embed(a) bwd ---+--> done
+            ClearParamDiffs, id grouping ---------------\
+            round M ---\                                 +--> SimCross dq ‖ da --> Embed bwd (q, a) --\
+            Embed(q) ---+--> SimCross fwd (+ loss dot) --/                     \--> SimCross dM, dB ---+--> done
+            Embed(a) --/
 
         (SimCross backward forks its own da branch inside the library.)  Works eagerly and under stream
         capture; every side stream is joined back into the current stream before returning."""
@@ -170,6 +185,7 @@ class MMSNet(object):
         s1, s2 = self._side
         s1.wait_stream(main)
         s2.wait_stream(main)
+        sp = self._prepare_weights(main)
         if clear_diffs:
             with torch.cuda.stream(s1):
                 self.ClearParamDiffs()
@@ -178,6 +194,7 @@ class MMSNet(object):
             self.embed_a.Forward([self.idx_a], [self.a])
         self.embed_q.Forward([self.idx_q], [self.q])
         main.wait_stream(s2)
+        main.wait_stream(sp)
         saved, self.sim.loss_ = self.sim.loss_, []             # the loss dot (layer.hpp:471-479) goes on a side branch
         try:
             self.sim.Forward([self.q, self.a], [self.S])
@@ -189,8 +206,16 @@ class MMSNet(object):
             with torch.cuda.stream(s2):
                 loss = self.sim.ForwardLoss([self.S])
         main.wait_stream(s1)                                   # diffs are cleared before anything accumulates
-        self.sim.Backward([self.S], [True, True], [self.q, self.a])
+        # dq, da first; the weight gradient (dM, dB) on a branch of its own beside the scatter-add, which needs dq / da only
+        self.sim.BackwardBottoms([self.S], [self.q, self.a])
+        if getattr(self, "_side3", None) is None:
+            self._side3 = torch.cuda.Stream()
+        s3 = self._side3
+        s3.wait_stream(main)
+        with torch.cuda.stream(s3):
+            self.sim.BackwardParams([self.S], [self.q, self.a])
         self._embed_backward_pair(main, s2)
+        main.wait_stream(s3)
         return loss
 
     def _embed_backward_pair(self, main, s2):
@@ -201,7 +226,9 @@ class MMSNet(object):
             self.embed_a.Backward([self.a], [False], [self.idx_a])
             main.wait_stream(s2)                               # the loss branch still joins here
             return
-        if self.grouped_scatter:                               # one pass over dq and da, rows grouped by id
+        # (below the library's row threshold the pair call would run the two per-layer kernels one after the other:
+        #  small batches are latency-bound, side by side is shorter)
+        if self.grouped_scatter and self.idx_q.count() + self.idx_a.count() >= _lib.EMBED_GROUPED_MIN_ROWS:
             self.embed_q.BackwardPair(self.embed_a, self.q, self.a, self.idx_q, self.idx_a)
             main.wait_stream(s2)
             return
@@ -234,6 +261,7 @@ class MMSNet(object):
         s3 = self._side3
         s1.wait_stream(main)
         s2.wait_stream(main)
+        sp = self._prepare_weights(main)
         if clear_diffs and solver is None:
             with torch.cuda.stream(s1):
                 self.ClearParamDiffs()
@@ -242,6 +270,7 @@ class MMSNet(object):
             self.embed_a.Forward([self.idx_a], [self.a])
         self.embed_q.Forward([self.idx_q], [self.q])
         main.wait_stream(s2)
+        main.wait_stream(sp)
         saved, self.sim.loss_ = self.sim.loss_, []
         try:
             self.sim.Forward([self.q, self.a], [self.S])

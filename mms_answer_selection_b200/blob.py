@@ -120,6 +120,11 @@ class Blob(object):
     def set_cpu_data(self, arr, non_blocking=False):
         src = torch.from_numpy(np.ascontiguousarray(arr, dtype=self.dtype).reshape(self._shape))
         self.data.copy_(src, non_blocking=non_blocking)
+        if self.data.is_cuda:
+            # a write the library cannot see: drop whatever it derived from older contents (rounded operand copies kept
+            # by MMS_OPT_REUSE_FORWARD / MMS_OPT_STAGE_TF32 / mms_simcross_prepare)
+            from . import _lib
+            _lib.lib().mms_invalidate_caches()
 
     def set_cpu_diff(self, arr, non_blocking=False):
         src = torch.from_numpy(np.ascontiguousarray(arr, dtype=self.dtype).reshape(self._shape))

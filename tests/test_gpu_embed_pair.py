@@ -171,3 +171,31 @@ def test_prefetched_inputs_arrive_one_replay_later():
     assert abs(second - losses["two"]) <= 1e-5 * abs(losses["two"])
     assert abs(third - losses["one"]) <= 1e-5 * abs(losses["one"])
     assert abs(losses["one"] - losses["two"]) > 1e-3 * abs(losses["one"])       # the two batches do differ
+
+
+def test_prepared_weights_match_and_follow_a_parameter_write():
+    """mms_simcross_prepare: M rounded ahead of the forward gives the same S bit for bit; a parameter written after the
+    prepare (Blob.set_cpu_data -> mms_invalidate_caches) is what the forward uses, not the stale rounded copy."""
+    import mms_answer_selection_b200 as mms
+    from mms_answer_selection_b200 import synth
+    N, L, D, mc, V = 64, 40, 300, 4, 2000
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    net = mms.MMSNet(N, L, D, mc, V)
+    net.set_params(d["W"], d["b"], d["M"], d["B"]); net.set_inputs(d["idx_q"], d["idx_a"])
+    net.Forward()                                                  # sizes the workspace, plain path
+    S0 = net.S.cpu_data().copy()
+    net.sim.handle.profile_enable(True)
+    net.sim.Prepare([net.q, net.a]); net.Forward()
+    torch.cuda.synchronize()
+    rep = net.sim.handle.profile_report()
+    assert rep["tf32_round_kernel"][0] == 1                        # the prepare's launch only: the forward skipped its own
+    np.testing.assert_array_equal(net.S.cpu_data(), S0)
+    net.sim.Prepare([net.q, net.a])
+    net.sim.blobs[0].set_cpu_data(2.0 * d["M"])                    # after the prepare
+    net.Forward()
+    torch.cuda.synchronize()
+    ref = mms.MMSNet(N, L, D, mc, V)
+    ref.set_params(d["W"], d["b"], 2.0 * d["M"], d["B"]); ref.set_inputs(d["idx_q"], d["idx_a"])
+    ref.Forward()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(net.S.cpu_data(), ref.S.cpu_data())

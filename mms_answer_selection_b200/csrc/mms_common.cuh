@@ -1,5 +1,6 @@
 // Shared host/device plumbing for libmms_b200.so (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -161,6 +162,16 @@ int mms_prefer_max_shared(const void* func);
 int mms_scratch(mms_context* ctx, size_t bytes, void** out);
 
 static inline int mms_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+// Developer kill switches (MMS_NO_FUSED, MMS_NO_2CTA, ...: force the generic engine instead of a dedicated kernel) are
+// read from the environment only in builds with -DMMS_DEV_KNOBS (MMS_NVCC_EXTRA); the shipped library ignores them.
+inline bool mms_dev_knob(const char* name) {
+#ifdef MMS_DEV_KNOBS
+  return getenv(name) != nullptr;
+#else
+  (void)name;
+  return false;
+#endif
+}
 template <typename T> __host__ __device__ inline T mms_min(T a, T b) { return a < b ? a : b; }
 template <typename T> __host__ __device__ inline T mms_max(T a, T b) { return a > b ? a : b; }
 

@@ -301,7 +301,7 @@ sentconv_dw_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
 // G: (rows, ldg) TF32-exact gradient rows (zero where no window starts), xr: (rows_total, D) TF32-exact token rows.
 int mms_tc_sentconv_dw(mms_context* ctx, const float* G, long long rows, int ldg, const float* xr, long long rows_total,
                        float* dW, int D, int C, int kh) {
-  static const bool disabled = getenv("MMS_NO_SENTCONV_KERNEL") != nullptr || getenv("MMS_NO_SENTCONV_DW") != nullptr;
+  static const bool disabled = mms_dev_knob("MMS_NO_SENTCONV_KERNEL") || mms_dev_knob("MMS_NO_SENTCONV_DW");
   if (disabled || C > 128 || kh > 5 || kh < 1 || D % 4 != 0 || ldg % 4 != 0 || rows < 1) return MMS_E_UNSUPPORTED;
   if (((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(dW)) & 15) != 0)
     return MMS_E_UNSUPPORTED;
@@ -339,7 +339,7 @@ int mms_tc_sentconv_dw(mms_context* ctx, const float* G, long long rows, int ldg
 int mms_tc_sentconv_shifted(mms_context* ctx, const float* X, long long rows_total, long long ldx, int Kd, const float* F,
                             long long ldf, int Kdf, int Mtot, int kh, float* out, long long ld_out, long long rows,
                             int row_major_out, int dry_run) {
-  static const bool disabled = getenv("MMS_NO_SENTCONV_KERNEL") != nullptr;
+  static const bool disabled = mms_dev_knob("MMS_NO_SENTCONV_KERNEL");
   if (disabled || kh > 8 || kh < 1 || ldx % 4 != 0 || ldf % 4 != 0 || rows < 1 || Mtot < 1 || Kd < 1) return MMS_E_UNSUPPORTED;
   if (!row_major_out && ld_out % 4 != 0) return MMS_E_UNSUPPORTED;
   if (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(F)) & 15) != 0) return MMS_E_UNSUPPORTED;

@@ -201,7 +201,7 @@ bool dm_shape_ok(int D, int* nmb, int* nh, int* Nh0, int* N1) {
 
 // Whether dM can be computed by this kernel from the blocked U layout (the dQ kernel then exports that layout).
 int mms_tc_simcross2_dm_plan(int D) {
-  static const bool disabled = getenv("MMS_NO_FUSED") != nullptr || getenv("MMS_NO_FUSED_DM") != nullptr;
+  static const bool disabled = mms_dev_knob("MMS_NO_FUSED") || mms_dev_knob("MMS_NO_FUSED_DM");
   int nmb, nh, Nh0, N1;
   return (!disabled && dm_shape_ok(D, &nmb, &nh, &Nh0, &N1)) ? 0 : MMS_E_UNSUPPORTED;
 }

@@ -309,7 +309,7 @@ simcross2_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
 // Returns MMS_E_UNSUPPORTED for shapes the fused tile does not cover (the caller composes GEMMs instead).
 int mms_tc_simcross2_forward_fused(mms_context* ctx, const float* qr, const float* ar, const float* Mr,
                                    const float* B, float* S, int N, int Lq, int La, int D, int mc, int Dp) {
-  static const bool disabled = getenv("MMS_NO_FUSED") != nullptr;
+  static const bool disabled = mms_dev_knob("MMS_NO_FUSED");
   if (disabled) return MMS_E_UNSUPPORTED;
   if (Lq > 128 || La > 256) return MMS_E_UNSUPPORTED;
   FwdGeom g;

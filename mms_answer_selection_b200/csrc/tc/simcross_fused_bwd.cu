@@ -673,7 +673,7 @@ int chunk_width(int N1) { return N1 + kUBufs * 64 <= 512 ? 64 : (N1 + kUBufs * 3
 int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D, int mc, int ctas, int allow_split,
                                          int* ksplit, int* split_from) {
   const int sm_count = ctas;
-  static const bool disabled = getenv("MMS_NO_FUSED") != nullptr || getenv("MMS_NO_FUSED_BWD") != nullptr;
+  static const bool disabled = mms_dev_knob("MMS_NO_FUSED") || mms_dev_knob("MMS_NO_FUSED_BWD");
   if (disabled) return MMS_E_UNSUPPORTED;
   if (Lq > 128 || La > 128 || N < 1) return MMS_E_UNSUPPORTED;
   const int N1 = mms_ceil_div(D, 16) * 16;
@@ -682,7 +682,11 @@ int mms_tc_simcross2_backward_fused_plan(int which, int N, int Lq, int La, int D
   const long long base = mms_ceil_div(N, P);
   int ks = 1;
   long long whole = base;
+#ifdef MMS_BWD_PROBES
   static const bool no_tail = getenv("MMS_BWD_NO_TAIL_SPLIT") != nullptr;
+#else
+  const bool no_tail = false;
+#endif
   if (allow_split && mc > 1) {
     if (base * 2 <= sm_count) { ks = (int)mms_min<long long>(mc, sm_count / base); whole = 0; }
     else if (!no_tail) {
@@ -724,7 +728,9 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   int stages = kMaxStages;
   while (stages > 2 && (size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 227 * 1024) --stages;
   if ((size_t)kGblkBytes + (size_t)stages * g.stage_bytes + sizeof(BwdSmem) + 1024 > 227 * 1024) return MMS_E_UNSUPPORTED;
+#ifdef MMS_BWD_PROBES
   { static const char* e = getenv("MMS_BWD_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
+#endif
   g.stages = stages;
   g.ksplit = ksplit;
   const long long groups = mms_ceil_div(N, g.P);
@@ -745,7 +751,10 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
 #endif
   g.u_rows = (long long)N * g.Lr;
   g.u_blocked = u_blocked;
-  { static const char* e = getenv("MMS_BWD_EXPORT_WARPS"); g.u_inline = (e && atoi(e)) ? 0 : 1; }   // CW <= 64: one piece per warp
+  g.u_inline = 1;                           // CW <= 64: one piece per rounding warp
+#ifdef MMS_BWD_PROBES
+  { static const char* e = getenv("MMS_BWD_EXPORT_WARPS"); if (e && atoi(e)) g.u_inline = 0; }
+#endif
   g.u_groups = (g.u_rows + 31) / 32;
 
   CUtensorMap mapX, mapM;

@@ -714,7 +714,7 @@ namespace {
 // The CTA-pair kernel pays when the tile is wide (the B half it saves is large) and there are enough 256-row tiles
 // to fill the 74 pairs; otherwise the single-CTA kernel's smaller tiles spread better.
 int gemm_tma_pair(mms_context* ctx, const TcGemmArgs& a) {
-  static const bool disabled = getenv("MMS_NO_2CTA") != nullptr;
+  static const bool disabled = mms_dev_knob("MMS_NO_2CTA");
   if (disabled || a.M <= 128 || a.N < 256) return MMS_E_UNSUPPORTED;
   Geometry q;
   // column tiles of equal width, each CTA's half a multiple of 32 columns: N = 300 runs as 2 x 192 (78 % of the MMA

@@ -48,7 +48,7 @@ bwd = timed(lambda: lay.Backward([top], [True, True], [bq, ba]))
 f_fwd = N * mc * 2.0 * L * D * (D + L)
 f_all = N * mc * (6.0 * L * D * D + 8.0 * L * L * D)
 print("N=%d fused=%s  fwd %.4f ms (%.1f TF/s alg)  bwd %.4f ms (%.1f TF/s alg)  fwd+bwd %.1f TF/s alg" % (
-    N, "off" if os.environ.get("MMS_NO_FUSED") else "on", fwd, f_fwd / fwd * 1e-9, bwd,
+    N, "off (needs a -DMMS_DEV_KNOBS build)" if os.environ.get("MMS_NO_FUSED") else "on", fwd, f_fwd / fwd * 1e-9, bwd,
     (f_all - f_fwd) / bwd * 1e-9, f_all / (fwd + bwd) * 1e-9))
 h = lay.handle
 h.profile_enable(True)

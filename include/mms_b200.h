@@ -78,7 +78,9 @@ enum {
                                 streams, joined back before the call's last launch on the handle's stream. */
   MMS_OPT_STAGE_TF32 = 7,    /* Embed forward, float: 1 = the gather also writes the operand copy the tensor-core
                                 contractions read (TF32 round-to-nearest, rows padded to 128-byte lines) into a
-                                buffer owned by this handle, and publishes it under the top's address.  A later
+                                buffer owned by this handle (ONE buffer per handle: a second Embed forward on the same
+                                handle replaces the copy of the first -- give every Embed layer its own handle), and
+                                publishes it under the top's address.  A later
                                 mms_simcross_forward / _backward whose q or a IS that top (same pointer, shape) reads
                                 the staged copy instead of re-reading and rounding the top in a pass of its own
                                 (q and a then cross HBM twice per forward instead of three times).  The copy is

@@ -234,6 +234,8 @@ int mms_embed_forward_impl(mms_context* ctx, const T* idx, const T* W, const T* 
     { MmsKernelScope ks_(ctx, "embed_forward_vec");
       MMS_CARVEOUT((embed_forward_vec<T, VEC>));
       const bool only = staged && ctx->stage_only;
+      // the handle owns ONE staging buffer: whatever it published for an earlier top is about to be overwritten
+      if (staged) mms_stage_drop_owner(ctx);
       embed_forward_vec<T, VEC><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(idx, W, bias, only ? nullptr : top, M, D, V,
                                                                            ctx->fault_flag, staged, lds);
       if (staged) mms_stage_publish(ctx, top, ctx->stage_buf, M, D, lds, only); }

@@ -199,3 +199,27 @@ def test_prepared_weights_match_and_follow_a_parameter_write():
     ref.Forward()
     torch.cuda.synchronize()
     np.testing.assert_array_equal(net.S.cpu_data(), ref.S.cpu_data())
+
+
+def test_one_staging_buffer_per_handle_never_serves_a_stale_copy():
+    """MMS_OPT_STAGE_TF32 on ONE handle used for two Embed forwards: the second gather overwrites the staging buffer, so the
+    first top must no longer resolve to it -- SimCross then rounds that top itself and the scores stay right."""
+    from mms_answer_selection_b200 import synth
+    N, L, D, mc, V = 20, 40, 300, 4, 500
+    d = synth.make_qa_batch(N=N, L=L, D=D, mc=mc, V=V)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    W, b, Mw, B = dev(d["W"]), dev(d["b"]), dev(d["M"]), dev(d["B"])
+    iq, ia = dev(d["idx_q"]), dev(d["idx_a"])
+    outs = []
+    for stage in (0, 1):
+        he, hs = _lib.Handle(), _lib.Handle()
+        he.set_option(_lib.MMS_OPT_STAGE_TF32, stage)
+        q = torch.empty((N, L, D), device="cuda"); a = torch.empty((N, L, D), device="cuda")
+        S = torch.empty((N, mc, L, L), device="cuda")
+        Lb = _lib.lib()
+        _lib.check(Lb.mms_embed_forward_f32(he.ptr, p(iq), p(W), p(b), p(q), N * L, D, V))
+        _lib.check(Lb.mms_embed_forward_f32(he.ptr, p(ia), p(W), p(b), p(a), N * L, D, V))      # same handle
+        _lib.check(Lb.mms_simcross_forward_f32(hs.ptr, 2, p(q), p(a), p(Mw), p(B), p(S), None, None, N, L, L, D, mc))
+        torch.cuda.synchronize()
+        outs.append(S.cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])

@@ -47,6 +47,18 @@ bool mms_unchanged_since(unsigned long long clock, const void* p, size_t bytes) 
   return true;
 }
 
+// Has a write to exactly this range (not a blanket "everything may have changed") been noted since `clock`?
+static bool written_since(unsigned long long clock, const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_write_mu);
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes;
+  const unsigned long long first = g_write_clock - clock > (unsigned long long)kWriteLog ? g_write_clock - kWriteLog : clock;
+  for (unsigned long long c = first; c < g_write_clock; ++c) {
+    const WriteNote& w = g_writes[c % kWriteLog];
+    if (w.lo != 0 && w.lo < hi && lo < w.hi) return true;
+  }
+  return false;
+}
+
 int mms_scratch(mms_context* ctx, size_t bytes, void** out) {
   ctx->fwd_cache.valid = false;        // whoever asks for the scratch buffer is about to overwrite it
   ctx->m_prepared.valid = false;       // (mms_tc_simcross2_forward reads this flag BEFORE it asks)
@@ -114,8 +126,9 @@ bool mms_stage_virtual(const void* src) {
     if (it == g_stage.end() || !it->second.virt) return false;
     e = it->second;
   }
-  // a later write through this library put real data there
-  return mms_unchanged_since(e.clock, src, sizeof(float) * (size_t)e.rows * e.cols);
+  // only a later write INTO this top through the library puts real data there; mms_invalidate_caches() ("everything may
+  // have changed") makes the staged copy stale but does not materialise the top -- the consumer then fails loudly
+  return !written_since(e.clock, src, sizeof(float) * (size_t)e.rows * e.cols);
 }
 int mms_stage_require_real(const void* src, bool have_staged, const char* what) {
   if (have_staged || !mms_stage_virtual(src)) return 0;

@@ -401,7 +401,14 @@ def test_stage_only_embed_tops_same_results_and_loud_failures():
                 net.sim.Forward([net.q, net.a], [net.S])
             with pytest.raises(Exception, match="STAGE_ONLY"):
                 net.sim.Backward([net.S], [True, True], [net.q, net.a])
+            # a blanket invalidation makes the staged copy stale but does not materialise the tops: still a refusal
+            net.sim.set_math(_lib.MMS_MATH_TF32)
+            _lib.lib().mms_invalidate_caches()
+            with pytest.raises(Exception, match="STAGE_ONLY"):
+                net.sim.Forward([net.q, net.a], [net.S])
+            net.Forward()                                          # gathering again repairs it
             torch.cuda.synchronize()
+            np.testing.assert_array_equal(net.S.cpu_data(), outs[0][0])
     for a, b, name in zip(outs[0], outs[1], ("S", "dq", "da")):
         np.testing.assert_array_equal(a, b, err_msg=name)
     for a, b, name in ((outs[0][3], outs[1][3], "dM"), (w_keep, w_only, "dW")):                # float atomics: order differs

@@ -75,6 +75,7 @@ struct BwdGeom {
   long long u_rows;      // rows of one measure slab of the exported U
   int u_blocked;         // U export layout: 0 row-major (pitch Dp), 1 blocked (tc/simcross_dm.cu)
   int u_inline;          // dQ: the eight rounding warps export their own piece from registers (no export warps)
+  int a_mn;              // dA: Gblk holds G itself (rows lq), read by GEMM-A as an MN-major A operand (= G^T)
   long long u_groups;    // blocked: 32-row groups per measure slab
 };
 
@@ -255,9 +256,10 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     ChunkIter ia, ib;
     ia.start(g); ib.start(g);
     if (is_a) {
-      const uint32_t idesc_a = idesc_tf32(128, CW, false, true);
-      const uint32_t idesc_al = idesc_tf32(128, wl, false, true);
-      const uint32_t gblk_lo = desc_lo_k(smem_u32(gblk));
+      const bool a_mn = DA && g.a_mn;
+      const uint32_t idesc_a = idesc_tf32(128, CW, a_mn, true);
+      const uint32_t idesc_al = idesc_tf32(128, wl, a_mn, true);
+      const uint32_t gblk_lo = a_mn ? desc_lo_mn(smem_u32(gblk), 16384) : desc_lo_k(smem_u32(gblk));
       const uint32_t ring_lo_mnA = desc_lo_mn(ring_base, 16384);
       const int a_full = nksA >> 2, a_rem = nksA & 3;
       Cursor ua = {0, 0};
@@ -281,6 +283,19 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         const uint32_t idesc = last ? idesc_al : idesc_a;
         if (elect_one_sync()) {
           uint32_t al = gblk_lo, bl = ring_lo_mnA + (uint32_t)slot.i * stage_lo;
+          if (a_mn) {              // A = Gblk read MN-major: 8 contraction rows (1024 bytes) per k-step, no 32-column blocks
+#pragma unroll 1
+            for (int kb = 0; kb < a_full; ++kb) {
+              mma_tf32_ss_lh(d, al, kDescHiMN, bl, kDescHiMN, idesc, kb > 0 ? 1u : 0u);
+              mma_tf32_ss_lh(d, al + 1 * kDescStepMN, kDescHiMN, bl + 1 * kDescStepMN, kDescHiMN, idesc, 1u);
+              mma_tf32_ss_lh(d, al + 2 * kDescStepMN, kDescHiMN, bl + 2 * kDescStepMN, kDescHiMN, idesc, 1u);
+              mma_tf32_ss_lh(d, al + 3 * kDescStepMN, kDescHiMN, bl + 3 * kDescStepMN, kDescHiMN, idesc, 1u);
+              al += 4 * kDescStepMN; bl += 4 * kDescStepMN;
+            }
+            if (a_rem > 0) mma_tf32_ss_lh(d, al, kDescHiMN, bl, kDescHiMN, idesc, a_full > 0 ? 1u : 0u);
+            if (a_rem > 1) mma_tf32_ss_lh(d, al + 1 * kDescStepMN, kDescHiMN, bl + 1 * kDescStepMN, kDescHiMN, idesc, 1u);
+            if (a_rem > 2) mma_tf32_ss_lh(d, al + 2 * kDescStepMN, kDescHiMN, bl + 2 * kDescStepMN, kDescHiMN, idesc, 1u);
+          } else {
 #pragma unroll 1
           for (int kb = 0; kb < a_full; ++kb) {
             mma_tf32_ss_lh(d, al, kDescHiK, bl, kDescHiMN, idesc, kb > 0 ? 1u : 0u);
@@ -292,6 +307,7 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
           if (a_rem > 0) mma_tf32_ss_lh(d, al, kDescHiK, bl, kDescHiMN, idesc, a_full > 0 ? 1u : 0u);
           if (a_rem > 1) mma_tf32_ss_lh(d, al + 1 * kDescStepK, kDescHiK, bl + 1 * kDescStepMN, kDescHiMN, idesc, 1u);
           if (a_rem > 2) mma_tf32_ss_lh(d, al + 2 * kDescStepK, kDescHiK, bl + 2 * kDescStepMN, kDescHiMN, idesc, 1u);
+          }
           mma_commit(&sm->empty[slot.i]);
           mma_commit(&sm->u_full[ua.i]);
           if (last) mma_commit(&sm->g_empty);
@@ -583,8 +599,14 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     }
   } else if (warp >= 10 && warp < 14) {
     // ------------------------------------------------------------ Gblk builders: thread r owns tile row r
+    // dA with a_mn: Gblk holds G itself -- thread r owns CONTRACTION row r = (pair p, lq) and writes the row of G it reads
+    // with 16-byte loads (exactly what the dQ builder does) as 16-byte stores along the M direction of an MN-major
+    // tile; GEMM-A reads that tile transposed through its descriptor.  (Before: one 4-byte load per element down a
+    // column of G, 40 load instructions per thread and measure instead of 10.)
+    const bool a_mn = DA && g.a_mn;
     const int r = (warp - 10) * 32 + lane;
-    const int p = r / g.Lr, l = r - p * g.Lr;
+    const int own = a_mn ? g.Lk : g.Lr;                    // rows per pair in the dimension this thread's index runs over
+    const int p = r / own, l = r - p * own;
     // off-diagonal blocks stay zero for the whole kernel: clear the row once
     for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -599,15 +621,17 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
         // The G values of this row are loaded into registers BEFORE waiting for the tile to be free (the loads do
         // not touch shared memory), 64 at a time with all loads of a batch in flight together.
         const float* Gnk = dS + ((size_t)(n0 + (valid ? p : 0)) * g.mc + k) * g.Lq * g.La;
-        const float* src = DA ? Gnk + l : Gnk + (size_t)l * g.La;   // dA: column la = l (stride La); dQ: row lq = l
-        const int col0 = p * g.Lk;
+        const bool by_row = !DA || a_mn;                            // this thread reads row lq = l of G
+        const float* src = by_row ? Gnk + (size_t)l * g.La : Gnk + l;   // else (dA, K-major Gblk): column la = l, stride La
+        const int nval = a_mn ? g.Lr : g.Lk;                        // values per thread
+        const int col0 = p * nval;
         float v[64];
-        for (int e0 = 0; e0 < g.Lk; e0 += 64) {
+        for (int e0 = 0; e0 < nval; e0 += 64) {
           if (valid && !(g.dbg & 256)) {
-            if (!DA && g.vec_g) {
+            if (by_row && g.vec_g) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                if (e0 + 4 * i < g.Lk) {
+                if (e0 + 4 * i < nval) {
                   const float4 x = __ldcs(reinterpret_cast<const float4*>(src + e0 + 4 * i));
                   v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
                 }
@@ -615,14 +639,23 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
             } else {
 #pragma unroll
               for (int i = 0; i < 64; ++i)
-                if (e0 + i < g.Lk) v[i] = __ldcs(src + (size_t)(e0 + i) * (DA ? g.La : 1));
+                if (e0 + i < nval) v[i] = __ldcs(src + (size_t)(e0 + i) * (by_row ? 1 : g.La));
             }
           }
           if (e0 == 0 && itk > 0) mbar_wait(&sm->g_empty, (uint32_t)(itk - 1) & 1u);   // every GEMM-A of the previous measure has read Gblk
           // a thread's values are consecutive contraction columns of its own Gblk row (dQ: a row of G, dA: a column
           // of G): 16-byte stores whenever the pair blocks start on a multiple of four columns
           if (valid) {
-            if (g.vec_s) {
+            if (a_mn) {               // MN-major tile: [32-wide M block][contraction row r][32 M values], 32-byte-atom swizzle
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (e0 + 4 * i < nval) {
+                  const int m = col0 + e0 + 4 * i;
+                  *reinterpret_cast<float4*>(gblk + (m >> 5) * 16384 + swz128_mn(r, (m & 31) >> 2)) =
+                      make_float4(to_tf32(v[4 * i]), to_tf32(v[4 * i + 1]), to_tf32(v[4 * i + 2]), to_tf32(v[4 * i + 3]));
+                }
+              }
+            } else if (g.vec_s) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 if (e0 + 4 * i < g.Lk) {
@@ -743,6 +776,10 @@ int mms_tc_simcross2_backward_fused(mms_context* ctx, int which, const float* xr
   g.tmem_cols = umma::tmem_cols_pow2((uint32_t)(g.N1 + kUBufs * g.CW));
   g.vec_g = (La % 4 == 0) && ((reinterpret_cast<uintptr_t>(dS) & 15) == 0);
   g.vec_s = g.Lk % 4 == 0;
+  g.a_mn = DA && g.vec_g && g.Lr % 4 == 0;        // rows of G by 16-byte loads, 16-byte stores along M
+#ifdef MMS_BWD_PROBES
+  { static const char* e = getenv("MMS_BWD_DA_KMAJOR"); if (e && atoi(e)) g.a_mn = 0; }
+#endif
   g.vec_out = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   g.Dp = Dp;
   g.dbg = 0;

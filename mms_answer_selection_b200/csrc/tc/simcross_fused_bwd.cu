@@ -6,17 +6,22 @@
 //                                           gradients have the same shape: small product first, D x D product second)
 //
 // One kernel template serves both (DA = false: dQ, DA = true: dA).  One tile = P consecutive QA pairs (their
-// P*Lr output rows, Lr = Lq or La) x a range of measures; the full-width output O [128 x N1] accumulates over the
+// P*Lr output rows, Lr = Lq or La) x a range of measures -- all of them for the pair groups that fill whole waves of
+// the grid, a 1/ksplit share for the groups left over after the last whole wave (and for every group of a small
+// batch), whose CTAs then ADD into pre-zeroed output rows; the full-width output O [128 x N1] accumulates over the
 // measures in TMEM columns [0, N1).  The intermediate U = Gblk * X never exists as a whole: it is produced, rounded
 // and consumed in column chunks of CW (64) columns that rotate through three TMEM buffers behind O,
 //
 //   chunk (tile, k, c):
 //     GEMM-A  U_c [128 x CW] = Gblk * X[:, chunk c]     Gblk [128 x 128]: block-diagonal, block p = G_{n0+p,k} (dQ) or
 //                                                       its transpose (dA), built in shared memory by four builder
-//                                                       warps straight from dS; X = the P pairs' answer (dQ) /
-//                                                       question (dA) rows, MN-major boxes of 32 columns x 128 rows
+//                                                       warps straight from the rows of dS: a K-major tile for dQ;
+//                                                       for dA the same rows as an MN-major tile that GEMM-A reads
+//                                                       transposed through its descriptor.  X = the P pairs' answer
+//                                                       (dQ) / question (dA) rows, MN-major boxes of 32 columns x 128 rows
 //     round   U_c -> tf32 in place (tcgen05.ld / cvt.rna / tcgen05.st); the dQ kernel also writes U_c to global
-//             memory, where the dM contraction (dM_k = Q^T U_k, a reduction over ALL pairs) picks it up
+//             memory -- each rounding warp its own piece, from registers, after announcing the chunk -- where the dM
+//             contraction (dM_k = Q^T U_k, a reduction over ALL pairs) picks it up
 //     GEMM-B  O [128 x N1] += U_c * W_k[chunk c rows]   W_k = M_k^T (dQ, K-major boxes) or M_k (dA, MN-major boxes);
 //                                                       A operand read from TMEM
 //
@@ -27,7 +32,7 @@
 // per measure: 35-41 % tensor-pipe activity.)
 //
 //   warp 0       TMA producer        warp 1       GEMM-A issuer + TMEM allocator        warp 14   GEMM-B issuer
-//   warps 2-9    rounding of U, U export (two warps per TMEM lane quarter)
+//   warps 2-9    rounding of U, U export (two warps per TMEM lane quarter, 32 columns of the chunk each)
 //   warps 10-13  Gblk builders        warps 15-18  output epilogue (one warp per TMEM lane quarter)
 //
 // The issue loops are written for the uniform datapath: every quantity an MMA needs besides the k-step offset is
@@ -399,10 +404,9 @@ simcross2_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __gri
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------ U rounding / export
-    // dA: eight warps round (two per TMEM lane quarter, 32 columns of the chunk each).
-    // dQ: warps 2-5 round the whole chunk; warps 6-9 read the rounded chunk back and write it to global memory for the
-    //     dM contraction.  Row-per-thread stores cost one LSU wavefront per lane and instruction (~1000 cycles per
-    //     chunk for the CTA); issued by the rounding warps they sat on the round -> GEMM-B path of the NEXT chunk.
+    // Eight warps round (two per TMEM lane quarter, 32 columns of the chunk each); in the dQ kernel each then exports the
+    // piece it holds (u_inline).  The older split -- warps 2-5 round the whole chunk, warps 6-9 read it back from TMEM
+    // and export it -- survives for the probes build only (MMS_BWD_EXPORT_WARPS): 0.395 vs 0.386 ms.
     const int quarter = warp & 3;
     const int set = (warp - 2) >> 2;
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;

@@ -91,3 +91,41 @@ def test_committed_bench_lines_follow_the_contract():
         assert ours["scaling"] == ref["scaling"] == "strong" and ours["n_gpus"] == ref["n_gpus"] == n
         if n > 1:
             assert ours["parity"]["ok"] is True and ours["parity"]["replicas_bit_identical"] is True
+
+
+def test_python_mirror_of_the_grouped_scatter_threshold_matches_the_library_source():
+    """`_lib.EMBED_GROUPED_MIN_ROWS` duplicates csrc/embed_sorted.cu's kMinRows (MMSNet uses it to decide whether the pair
+    call would only run the two per-layer kernels one after the other)."""
+    import os
+    import re
+    from mms_answer_selection_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "mms_answer_selection_b200", "csrc", "embed_sorted.cu")).read()
+    m = re.search(r"constexpr long long kMinRows = (\d+);", src)
+    assert m and int(m.group(1)) == _lib.EMBED_GROUPED_MIN_ROWS
+
+
+def test_shipped_library_reads_no_developer_knobs_from_the_environment():
+    """Kill switches and probe knobs are compiled in only with -DMMS_DEV_KNOBS / -DMMS_BWD_PROBES: every getenv in the
+    product sources is the tracing switch, inside the gated helper, or inside an #ifdef block of those macros."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "mms_answer_selection_b200", "csrc")
+    bad = []
+    for path in glob.glob(os.path.join(csrc, "*.cu*")) + glob.glob(os.path.join(csrc, "tc", "*.cu*")):
+        depth = 0                                   # nesting inside #ifdef MMS_DEV_KNOBS / MMS_BWD_PROBES blocks
+        stack = []
+        for n, line in enumerate(open(path), 1):
+            t = line.strip()
+            if re.match(r"#\s*if", t):
+                stack.append(bool(re.match(r"#\s*ifdef\s+(MMS_DEV_KNOBS|MMS_BWD_PROBES)\b", t)))
+            elif re.match(r"#\s*else", t) and stack:
+                stack[-1] = False
+            elif re.match(r"#\s*endif", t) and stack:
+                stack.pop()
+            gated = any(stack)
+            if "getenv(" in line and not gated and "MMS_TC_TRACE" not in line:
+                bad.append("%s:%d: %s" % (os.path.relpath(path, root), n, t))
+    assert not bad, "\n".join(bad)
